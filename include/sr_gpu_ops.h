@@ -1,0 +1,485 @@
+/*
+ * sr_gpu_ops.h -- C-ABI of the B200-native StarRocks BE hot path
+ * (columnar Chunk scan -> predicate/filter -> hash-join build+probe -> hash aggregate,
+ *  plus the hash-partition step of ExchangeSink).
+ *
+ * This is the drop-in boundary: plain C structs, opaque handles, int32 status codes,
+ * no exceptions and no torch / C++ types in any signature.  The C++ adapters in
+ * starrocks_b200/host/ (GpuScanOperator, GpuHashJoinBuild/ProbeOperator,
+ * GpuAggregateBlockingSink/SourceOperator) are thin shims over these calls and keep the
+ * reference's pipeline::Operator / OperatorFactory virtual interface
+ * (be/src/exec/pipeline/operator.h:44-352, :354-456; source_operator.h:37-189).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * StarRocks source tree).
+ *
+ * Conventions
+ *  - every function returning int32_t returns SR_OK (0) or a negative sr_status; the message
+ *    is available from sr_last_error(ctx).
+ *  - a sr_chunk_view mirrors column::Chunk (be/src/column/chunk.h:52): equal-length columns
+ *    addressed by slot id.  `mem` says whether the column pointers are host or device
+ *    addresses.  Host chunks are copied H2D by the callee on the context's stream; device
+ *    chunks are consumed in place (zero copy) and must stay valid until sr_ctx_sync().
+ *  - all work is enqueued on the context's CUDA stream; calls return without synchronising
+ *    unless documented ("_sync" or a pull that hands back host memory).
+ *  - build row indexes are 1-based; 0 means "no row" (the reference reserves build row 0 as a
+ *    sentinel, be/src/exec/join/join_hash_table.cpp:712-752).
+ */
+#ifndef SR_GPU_OPS_H
+#define SR_GPU_OPS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SR_ABI_VERSION 1
+
+/* ---------------------------------------------------------------------------------------
+ * status codes (negative = error).  Mirrors the Status codes the adapters translate to
+ * (be/src/base/status.h): InvalidArgument, NotSupported, MemoryLimitExceeded, InternalError.
+ * ------------------------------------------------------------------------------------- */
+typedef enum sr_status {
+    SR_OK = 0,
+    SR_ERR_INVALID_ARGUMENT = -1,
+    SR_ERR_NOT_SUPPORTED = -2,
+    SR_ERR_OUT_OF_MEMORY = -3,
+    SR_ERR_CUDA = -4,
+    SR_ERR_STATE = -5, /* call made in the wrong phase (e.g. probe before build_finish)          */
+    SR_ERR_NO_DEVICE = -6
+} sr_status;
+
+/* ---------------------------------------------------------------------------------------
+ * logical types -- subset of be/src/types/logical_type.h used by the hot path.
+ * Physical layout = FixedLengthColumnBase<T> (be/src/column/fixed_length_column_base.h:49):
+ * a contiguous array of T.  DATE = int32 julian day (types/date_value.h:120), DATETIME =
+ * int64 (types/timestamp_value.h:165), DECIMAL32/64/128 = DecimalV3<int32/int64/int128>.
+ * ------------------------------------------------------------------------------------- */
+typedef enum sr_type {
+    SR_TYPE_BOOLEAN = 1,  /* uint8  */
+    SR_TYPE_TINYINT = 2,  /* int8   */
+    SR_TYPE_SMALLINT = 3, /* int16  */
+    SR_TYPE_INT = 4,      /* int32  */
+    SR_TYPE_BIGINT = 5,   /* int64  */
+    SR_TYPE_LARGEINT = 6, /* int128 */
+    SR_TYPE_FLOAT = 7,
+    SR_TYPE_DOUBLE = 8,
+    SR_TYPE_DATE = 9,       /* int32 */
+    SR_TYPE_DATETIME = 10,  /* int64 */
+    SR_TYPE_DECIMAL32 = 11, /* int32 */
+    SR_TYPE_DECIMAL64 = 12, /* int64 */
+    SR_TYPE_DECIMAL128 = 13 /* int128 */
+} sr_type;
+
+/* byte width of one value of the type (0 for an unknown type). */
+int32_t sr_type_width(int32_t type);
+
+typedef enum sr_mem { SR_MEM_HOST = 0, SR_MEM_DEVICE = 1 } sr_mem;
+
+/* mirrors FixedLengthColumn / NullableColumn raw buffers (be/src/column/nullable_column.h:32:
+ * data column + uint8 null column, 1 = null). nulls == NULL means "not nullable / no nulls". */
+typedef struct sr_col_view {
+    const void* data;
+    const uint8_t* nulls;
+    int32_t type;    /* sr_type */
+    int32_t slot_id; /* SlotId the column is registered under in the Chunk */
+} sr_col_view;
+
+/* mirrors column::Chunk (be/src/column/chunk.h:52-354). */
+typedef struct sr_chunk_view {
+    const sr_col_view* cols;
+    int32_t num_cols;
+    int32_t mem; /* sr_mem: where the column pointers live */
+    int64_t num_rows;
+} sr_chunk_view;
+
+/* Output chunk.  Buffers are owned by the producing handle and stay valid until the next
+ * pull / release on the same handle (same contract as a ChunkPtr the operator keeps alive). */
+typedef struct sr_col_out {
+    void* data;
+    uint8_t* nulls; /* NULL when the column has no null column */
+    int32_t type;
+    int32_t slot_id;
+} sr_col_out;
+
+#define SR_MAX_OUT_COLS 32
+
+typedef struct sr_chunk_out {
+    sr_col_out cols[SR_MAX_OUT_COLS];
+    int32_t num_cols;
+    int32_t mem; /* sr_mem of the buffers handed back */
+    int64_t num_rows;
+} sr_chunk_out;
+
+/* ---------------------------------------------------------------------------------------
+ * context: one per GPU (one per BE process per device); owns the stream and the device
+ * memory the operators allocate.  Plays the part of RuntimeState + MemTracker for the GPU
+ * side (be/src/exec/pipeline/operator.h:157,350).
+ * ------------------------------------------------------------------------------------- */
+typedef struct sr_ctx sr_ctx;
+
+/* device: CUDA ordinal.  stream: a cudaStream_t to enqueue on, or NULL to create one. */
+sr_ctx* sr_ctx_create(int32_t device, void* cuda_stream);
+void sr_ctx_destroy(sr_ctx* ctx);
+/* cudaStreamSynchronize on the context's stream; surfaces any asynchronous kernel error. */
+int32_t sr_ctx_sync(sr_ctx* ctx);
+/* last error message recorded on this context (never NULL). With ctx == NULL: the message
+ * of the last failed create call on this thread. */
+const char* sr_last_error(sr_ctx* ctx);
+int32_t sr_abi_version(void);
+/* number of kernels this library has launched on the context since creation
+ * (bench.py reports it as gpu_launches). */
+int64_t sr_ctx_kernel_launches(sr_ctx* ctx);
+/* bytes of device memory currently held by the context's handles. */
+int64_t sr_ctx_device_bytes(sr_ctx* ctx);
+void* sr_ctx_stream(sr_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------
+ * scan predicates -- the pushed-down / non-pushdown `col OP const` conjuncts.
+ * Replaces ColumnPredicate::evaluate / evaluate_and (be/src/storage/column_predicate.h:128-149,
+ * column_operator_predicate.h:41-111) and the AND-merge of ChunkPredicateEvaluator::
+ * eval_conjuncts (be/src/exprs/chunk_predicate_evaluator.cpp:84-149).
+ * A NULL input never passes (count_true_with_notnull semantics), except IS_NULL.
+ * ------------------------------------------------------------------------------------- */
+typedef enum sr_pred_op {
+    SR_PRED_EQ = 1,
+    SR_PRED_NE = 2,
+    SR_PRED_LT = 3,
+    SR_PRED_LE = 4,
+    SR_PRED_GT = 5,
+    SR_PRED_GE = 6,
+    SR_PRED_BETWEEN = 7, /* lo <= v <= hi */
+    SR_PRED_IN = 8,
+    SR_PRED_NOT_IN = 9,
+    SR_PRED_IS_NULL = 10,
+    SR_PRED_IS_NOT_NULL = 11
+} sr_pred_op;
+
+#define SR_MAX_IN_LIST 16
+
+typedef struct sr_pred {
+    int32_t slot_id;
+    int32_t op; /* sr_pred_op */
+    /* integer / date / decimal columns compare against ilo (and ihi for BETWEEN);
+     * FLOAT / DOUBLE columns compare against dlo (and dhi). */
+    int64_t ilo, ihi;
+    double dlo, dhi;
+    int64_t in_list[SR_MAX_IN_LIST]; /* IN / NOT_IN on integer-class columns */
+    int32_t in_count;
+    int32_t reserved;
+} sr_pred;
+
+/* ---------------------------------------------------------------------------------------
+ * expressions -- postfix programs over slots; the subset of the vectorized Expr tree the
+ * path needs (be/src/exprs/binary_predicate.cpp:134-143, compound_predicate.cpp,
+ * arithmetic_expr.cpp, column_ref.h).  Integer-class operands are computed in int64 with
+ * two's-complement wrap (the FE casts INT operands of + - * to BIGINT); FLOAT/DOUBLE in
+ * double.  Comparison / AND / OR / NOT follow SQL three-valued logic.
+ * ------------------------------------------------------------------------------------- */
+typedef enum sr_expr_op {
+    SR_EX_COL = 1,    /* push slot value                          */
+    SR_EX_ICONST = 2, /* push ival                                */
+    SR_EX_DCONST = 3, /* push dval                                */
+    SR_EX_ADD = 4,
+    SR_EX_SUB = 5,
+    SR_EX_MUL = 6,
+    SR_EX_TO_DOUBLE = 7, /* cast top of stack to double            */
+    SR_EX_EQ = 8,
+    SR_EX_NE = 9,
+    SR_EX_LT = 10,
+    SR_EX_LE = 11,
+    SR_EX_GT = 12,
+    SR_EX_GE = 13,
+    SR_EX_AND = 14,
+    SR_EX_OR = 15,
+    SR_EX_NOT = 16,
+    SR_EX_IS_NULL = 17,
+    SR_EX_DIV = 18 /* double division only (ints are cast first) */
+} sr_expr_op;
+
+typedef struct sr_expr_node {
+    int32_t op; /* sr_expr_op */
+    int32_t slot_id;
+    int64_t ival;
+    double dval;
+} sr_expr_node;
+
+#define SR_MAX_EXPR_NODES 24
+#define SR_EXPR_STACK 8
+
+typedef struct sr_expr {
+    sr_expr_node nodes[SR_MAX_EXPR_NODES];
+    int32_t num_nodes;
+    int32_t reserved;
+} sr_expr;
+
+/* ---------------------------------------------------------------------------------------
+ * scan + filter.  Replaces OlapChunkSource::_read_chunk_from_storage's filter step
+ * (be/src/exec/pipeline/scan/olap_chunk_source.cpp:676-722): predicate evaluation into a
+ * uint8 selection vector, then Chunk::filter -> Column::filter_range order-preserving
+ * compaction (be/src/column/chunk.cpp:362-372, column_filter_range.cpp:39-148).
+ * The GPU ScanOperator batches many <=4096-row chunks per push.
+ * ------------------------------------------------------------------------------------- */
+typedef struct sr_scan_desc {
+    const sr_pred* preds; /* conjuncts in ColumnPredicate form */
+    int32_t num_preds;
+    int32_t num_filter_exprs;
+    const sr_expr* filter_exprs; /* generic boolean conjuncts (ChunkPredicateEvaluator) */
+    const int32_t* out_slots;    /* slots to emit (in this order) */
+    int32_t num_out_slots;
+    int32_t reserved;
+} sr_scan_desc;
+
+typedef struct sr_scan sr_scan;
+
+sr_scan* sr_scan_create(sr_ctx* ctx, const sr_scan_desc* desc);
+void sr_scan_destroy(sr_scan* scan);
+/* filter one batch.  `out` receives DEVICE buffers (owned by the scan handle, valid until the
+ * next push) holding the surviving rows in input order; out->num_rows is filled after an
+ * internal sync on the tiny row counter. */
+int32_t sr_scan_filter(sr_scan* scan, const sr_chunk_view* in, sr_chunk_out* out);
+/* evaluate only: write the uint8 selection vector (1 = row passes) to `selection`
+ * (host or device pointer according to sel_mem) -- the ColumnPredicate::evaluate contract. */
+int32_t sr_scan_evaluate(sr_scan* scan, const sr_chunk_view* in, uint8_t* selection, int32_t sel_mem);
+
+/* ---------------------------------------------------------------------------------------
+ * hash join.  One sr_join is shared by the build operator and the N probe operators, like
+ * HashJoiner (be/src/exec/hash_joiner.h:191-330).
+ *   append_build  <- HashJoiner::append_chunk_to_ht / JoinHashTable::append_chunk
+ *                    (hash_joiner.cpp:213-223, join_hash_table.cpp:712-752)
+ *   build_finish  <- HashJoiner::build_ht / JoinHashTable::build (join_hash_table.cpp:633-685,
+ *                    selector :161-350, construct_hash_table join_hash_map_method.hpp)
+ *   probe         <- JoinHashTable::probe / JoinHashMap::probe (join_hash_map.hpp:63-134,
+ *                    _probe_from_ht :718-795, _probe_output/_build_output :163-269)
+ * ------------------------------------------------------------------------------------- */
+typedef enum sr_join_type {
+    SR_JOIN_INNER = 0,
+    SR_JOIN_LEFT_OUTER = 1,
+    SR_JOIN_LEFT_SEMI = 2,
+    SR_JOIN_LEFT_ANTI = 3
+} sr_join_type;
+
+/* table layout chosen at build_finish; mirrors JoinHashMapMethodType
+ * (be/src/exec/join/join_hash_map_method_fwd.h) for the families the GPU path implements. */
+typedef enum sr_join_method {
+    SR_JOIN_METHOD_NONE = 0,
+    SR_JOIN_METHOD_DIRECT_MAPPING = 1,       /* <= 16-bit keys: first[key - type_min]           */
+    SR_JOIN_METHOD_RANGE_DIRECT_MAPPING = 2, /* first[key - min_value]                          */
+    SR_JOIN_METHOD_LINEAR_CHAINED = 3        /* open addressing, chain of equal keys in next[]  */
+} sr_join_method;
+
+#define SR_MAX_JOIN_KEYS 2
+#define SR_MAX_JOIN_OUT 16
+
+typedef struct sr_join_desc {
+    int32_t join_type; /* sr_join_type */
+    int32_t num_keys;  /* 1..SR_MAX_JOIN_KEYS; packed key must fit 8 bytes */
+    int32_t build_key_slots[SR_MAX_JOIN_KEYS];
+    int32_t probe_key_slots[SR_MAX_JOIN_KEYS];
+    int32_t key_types[SR_MAX_JOIN_KEYS]; /* sr_type, integer class */
+    /* columns of the build / probe side that appear in the join's output chunk */
+    int32_t num_build_out;
+    int32_t build_out_slots[SR_MAX_JOIN_OUT];
+    int32_t num_probe_out;
+    int32_t probe_out_slots[SR_MAX_JOIN_OUT];
+    /* session switch enable_hash_join_range_direct_mapping_opt (join_hash_table.cpp:259) */
+    int32_t enable_range_direct_mapping;
+    int32_t reserved;
+} sr_join_desc;
+
+typedef struct sr_join sr_join;
+
+typedef struct sr_join_info {
+    int32_t method;         /* sr_join_method */
+    int32_t has_duplicates; /* 1 when some build key occurs more than once */
+    int64_t build_rows;     /* rows appended (excluding the sentinel row 0) */
+    int64_t bucket_size;    /* entries of first[] */
+    int64_t min_value, max_value;
+} sr_join_info;
+
+sr_join* sr_join_create(sr_ctx* ctx, const sr_join_desc* desc);
+void sr_join_destroy(sr_join* join);
+int32_t sr_join_append_build(sr_join* join, const sr_chunk_view* chunk);
+int32_t sr_join_build_finish(sr_join* join);
+int32_t sr_join_is_build_done(const sr_join* join);
+int32_t sr_join_get_info(const sr_join* join, sr_join_info* info);
+/* copy first[] / next[] back to the host (test / debug aid; sizes from sr_join_get_info:
+ * bucket_size and build_rows + 1). Only for the *_MAPPING methods is first[] comparable with
+ * the reference layout. */
+int32_t sr_join_copy_table(sr_join* join, uint32_t* first_host, uint32_t* next_host);
+
+/* Probe one batch (any number of rows).  Output rows keep probe order; matches of one probe
+ * row are adjacent.  `out` holds DEVICE buffers owned by the join handle (per prober_id),
+ * valid until the next probe with the same prober_id.  Also exposes the
+ * (probe_index, build_index) pairs of HashTableProbeState
+ * (be/src/exec/join/join_hash_table_descriptor.h:207-330). */
+int32_t sr_join_probe(sr_join* join, int32_t prober_id, const sr_chunk_view* probe, sr_chunk_out* out);
+/* device pointers to the index pairs of the last probe of prober_id (num = out->num_rows). */
+int32_t sr_join_probe_indexes(sr_join* join, int32_t prober_id, const uint32_t** probe_index_dev,
+                              const uint32_t** build_index_dev);
+
+/* K5: JoinKeyHash / calc_bucket_num (be/src/exec/join/join_hash_map_helper.h:35-54,79-84)
+ * on the device, exposed so the multiplicative hash can be pinned against the reference's
+ * golden vectors.  keys: `n` values of key_type in `mem`; buckets: n uint32 in `mem`. */
+int32_t sr_join_key_hash(sr_ctx* ctx, const void* keys, int32_t key_type, int64_t n, uint32_t log_bucket_size,
+                         uint32_t* buckets, int32_t mem);
+
+/* ---------------------------------------------------------------------------------------
+ * hash aggregate.  One sr_agg is shared by the sink and source operators, like Aggregator
+ * (be/src/exec/aggregator.h:253-637).
+ *   push         <- AggregateBlockingSinkOperator::push_chunk: evaluate_groupby_exprs,
+ *                   build_hash_map, compute_batch_agg_states
+ *                   (aggregate_blocking_sink_operator.cpp:101-138, aggregator.cpp:907-929,
+ *                   1616-1640) or compute_single_agg_state when there is no GROUP BY (:882-905)
+ *   sink_finish  <- set_finishing / sink_complete (:56-89)
+ *   pull         <- AggregateBlockingSourceOperator::pull_chunk -> convert_hash_map_to_chunk
+ *                   (aggregate_blocking_source_operator.cpp:46-72, aggregator.cpp:1696-1791)
+ * Functions: be/src/exprs/agg/{sum,count,avg,maxmin}.h with the nullable wrapper semantics
+ * of nullable_aggregate.h (NULL inputs are skipped; result NULL when no non-null input).
+ * ------------------------------------------------------------------------------------- */
+typedef enum sr_agg_fn_kind {
+    SR_AGG_SUM = 1,
+    SR_AGG_COUNT = 2,      /* COUNT(expr): non-null inputs */
+    SR_AGG_COUNT_STAR = 3, /* COUNT(*) */
+    SR_AGG_AVG = 4,
+    SR_AGG_MIN = 5,
+    SR_AGG_MAX = 6
+} sr_agg_fn_kind;
+
+typedef struct sr_agg_fn {
+    int32_t kind;       /* sr_agg_fn_kind */
+    int32_t input_type; /* sr_type of the argument (decides the result type, sum.h:24-34) */
+    int32_t out_slot;   /* slot id of the result column */
+    int32_t reserved;
+    sr_expr input; /* argument expression over the input chunk's slots (ignored for COUNT_STAR) */
+} sr_agg_fn;
+
+#define SR_MAX_GROUP_KEYS 4
+#define SR_MAX_AGG_FNS 8
+
+typedef struct sr_agg_desc {
+    int32_t num_group_keys; /* 0 = no GROUP BY (single state) */
+    int32_t group_slots[SR_MAX_GROUP_KEYS];
+    int32_t group_types[SR_MAX_GROUP_KEYS];
+    /* optional value ranges of the group-by columns (the FE passes group-by min/max statistics
+     * for the compressed-key variants, aggregator.cpp:1516-1566).  has_ranges != 0 and a small
+     * product of ranges selects the dense, shared-memory accumulated table. */
+    int32_t has_ranges;
+    int32_t group_nullable[SR_MAX_GROUP_KEYS];
+    int64_t group_min[SR_MAX_GROUP_KEYS];
+    int64_t group_max[SR_MAX_GROUP_KEYS];
+    int32_t num_fns;
+    int32_t reserved;
+    sr_agg_fn fns[SR_MAX_AGG_FNS];
+    /* expected number of distinct groups (0 = unknown): initial capacity of the hash table */
+    int64_t expected_groups;
+} sr_agg_desc;
+
+typedef struct sr_agg sr_agg;
+
+sr_agg* sr_agg_create(sr_ctx* ctx, const sr_agg_desc* desc);
+void sr_agg_destroy(sr_agg* agg);
+int32_t sr_agg_push(sr_agg* agg, const sr_chunk_view* chunk);
+int32_t sr_agg_sink_finish(sr_agg* agg);
+/* number of result rows (groups); valid after sink_finish (synchronises on a counter). */
+int64_t sr_agg_num_groups(sr_agg* agg);
+/* Emit up to max_rows groups starting at the handle's cursor: key columns (group_slots order)
+ * then one result column per function.  out_mem selects host (copied back, synchronised) or
+ * device buffers.  Returns SR_OK with out->num_rows == 0 at end of stream. */
+int32_t sr_agg_pull(sr_agg* agg, int64_t max_rows, int32_t out_mem, sr_chunk_out* out);
+/* merge the (already finished) states of `other` into `agg` -- the final phase of a two-phase
+ * distributed aggregate (AggregateFunction::merge, be/src/exprs/agg/aggregate.h:365-445).
+ * Both handles must have been created from the same desc on the same context. */
+int32_t sr_agg_merge(sr_agg* agg, sr_agg* other);
+
+/* ---------------------------------------------------------------------------------------
+ * fused pipeline fragment:  scan -> filter -> [hash-join probe]* -> hash aggregate in ONE
+ * pass over the fact columns (no intermediate Chunk materialisation).  This is what the GPU
+ * ScanOperator runs when the downstream operators of its pipeline are GPU join probes and a
+ * GPU aggregate sink (SURVEY.md section 7 "keep the API, change the cadence").
+ * The joins must be built (sr_join_build_finish) INNER / LEFT_SEMI joins with unique build
+ * keys; otherwise SR_ERR_NOT_SUPPORTED is returned and the caller runs the per-operator path.
+ * ------------------------------------------------------------------------------------- */
+#define SR_MAX_FRAG_JOINS 6
+#define SR_MAX_FRAG_PAYLOAD 2
+
+typedef struct sr_frag_join {
+    sr_join* join;          /* built table (shared, not owned) */
+    int32_t probe_key_slot; /* fact column holding the probe key */
+    int32_t num_payload;    /* build columns carried downstream (<= SR_MAX_FRAG_PAYLOAD) */
+    int32_t payload_build_slots[SR_MAX_FRAG_PAYLOAD];
+} sr_frag_join;
+
+typedef struct sr_fragment_desc {
+    sr_scan_desc scan; /* preds / filter_exprs on fact columns; out_slots ignored */
+    int32_t num_joins;
+    int32_t reserved;
+    sr_frag_join joins[SR_MAX_FRAG_JOINS]; /* probed in this order */
+    sr_agg_desc agg; /* group keys / fn inputs may reference fact slots and payload slots */
+} sr_fragment_desc;
+
+typedef struct sr_fragment sr_fragment;
+
+sr_fragment* sr_fragment_create(sr_ctx* ctx, const sr_fragment_desc* desc);
+void sr_fragment_destroy(sr_fragment* frag);
+/* consume one batch of fact rows (one morsel: any number of rows). */
+int32_t sr_fragment_push(sr_fragment* frag, const sr_chunk_view* fact);
+/* the aggregate the fragment feeds (owned by the fragment): finish / pull / merge through
+ * the sr_agg_* calls. */
+sr_agg* sr_fragment_agg(sr_fragment* frag);
+/* rows that survived scan predicates and all joins so far (synchronises). */
+int64_t sr_fragment_rows_passed(sr_fragment* frag);
+
+/* ---------------------------------------------------------------------------------------
+ * exchange: hash-partition a chunk's rows to `num_channels` destinations.
+ * Replaces ExchangeSinkOperator::push_chunk's hash + shuffle + row-index counting sort
+ * (be/src/exec/pipeline/exchange/exchange_sink_operator.cpp:586-637), Shuffler::
+ * exchange_shuffle (shuffler.h:72-89) and Column::fnv_hash / crc32_hash
+ * (be/src/column/column_hash/column_hash.cpp:138-300, base/hash/hash_util.hpp:127-134,
+ * 242-244).  The transport itself (NCCL all-to-all in place of brpc transmit_chunk) is
+ * driven by the host with the per-channel counts this call produces.
+ * ------------------------------------------------------------------------------------- */
+typedef enum sr_hash_fn { SR_HASH_FNV = 0, SR_HASH_CRC32 = 1 } sr_hash_fn;
+typedef enum sr_reduce_op { SR_REDUCE_MULHI = 0 /* ReduceOp */, SR_REDUCE_MODULO = 1 /* ModuloOp */ } sr_reduce_op;
+
+#define SR_MAX_PART_KEYS 4
+
+typedef struct sr_part_desc {
+    int32_t hash_fn;   /* sr_hash_fn: FNV for HASH_PARTITIONED, CRC32 for BUCKET_SHUFFLE */
+    int32_t reduce_op; /* sr_reduce_op */
+    int32_t num_channels;
+    int32_t num_part_slots;
+    int32_t part_slots[SR_MAX_PART_KEYS];
+} sr_part_desc;
+
+typedef struct sr_xchg sr_xchg;
+
+sr_xchg* sr_xchg_create(sr_ctx* ctx, const sr_part_desc* desc);
+void sr_xchg_destroy(sr_xchg* x);
+/* Partition one batch.  out: DEVICE buffers, all columns of `in` reordered so that the rows
+ * of channel c occupy [offsets[c], offsets[c+1]) in input order (stable, like the reference's
+ * counting sort).  channel_offsets_host: num_channels + 1 int64 written on return (syncs). */
+int32_t sr_xchg_partition(sr_xchg* x, const sr_chunk_view* in, sr_chunk_out* out, int64_t* channel_offsets_host);
+/* hash values + channel ids only (device or host arrays of num_rows uint32, per `mem`). */
+int32_t sr_xchg_hash(sr_xchg* x, const sr_chunk_view* in, uint32_t* hash_values, uint32_t* channel_ids, int32_t mem);
+
+/* ---------------------------------------------------------------------------------------
+ * K11: Column::append_selective gather (be/src/column/fixed_length_column_base.cpp:54):
+ * dst[j] = src[index[j]] for one column; all pointers in `mem`.
+ * ------------------------------------------------------------------------------------- */
+int32_t sr_gather(sr_ctx* ctx, const void* src, int32_t type, const uint32_t* index, int64_t n, void* dst,
+                  int32_t mem);
+
+/* measurement aid: read-only 128-bit-load bandwidth kernel over `bytes` of device memory
+ * (SURVEY.md section 8d "measure the achievable peak"); returns the xor checksum through
+ * *checksum_host after syncing. */
+int32_t sr_bandwidth_probe(sr_ctx* ctx, const void* dev_ptr, int64_t bytes, uint64_t* checksum_host);
+/* write `bytes` of zeros to a scratch buffer larger than L2 (flushes L2 between timed steps) */
+int32_t sr_flush_l2(sr_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SR_GPU_OPS_H */

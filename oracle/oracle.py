@@ -1,0 +1,330 @@
+"""ctypes binding of the CPU oracle (oracle/libsr_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package (starrocks_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+from starrocks_b200 import abi  # noqa: E402
+
+_LIB = None
+
+
+class orc_join_options(C.Structure):
+    _fields_ = [("enable_range_direct_mapping", C.c_int32), ("enable_linear_chained", C.c_int32),
+                ("l2_cache_size", C.c_int64), ("l3_cache_size", C.c_int64), ("force_method", C.c_int32),
+                ("chunk_size", C.c_int32)]
+
+
+class orc_probe_result(C.Structure):
+    _fields_ = [("count", C.c_int64), ("has_remain", C.c_int32), ("match_flag", C.c_int32),
+                ("cur_probe_index", C.c_int32), ("cur_row_match_count", C.c_int32)]
+
+
+class orc_frag_join(C.Structure):
+    _fields_ = [("join", C.c_void_p), ("probe_key_slot", C.c_int32), ("num_payload", C.c_int32),
+                ("payload_build_slots", C.c_int32 * abi.SR_MAX_FRAG_PAYLOAD)]
+
+
+class orc_fragment_desc(C.Structure):
+    _fields_ = [("scan", abi.sr_scan_desc), ("num_joins", C.c_int32), ("reserved", C.c_int32),
+                ("joins", orc_frag_join * abi.SR_MAX_FRAG_JOINS), ("agg", abi.sr_agg_desc)]
+
+
+BUCKET_CHAINED, DIRECT_MAPPING, RANGE_DIRECT_MAPPING, RANGE_DIRECT_MAPPING_SET = 1, 2, 3, 4
+DENSE_RANGE_DIRECT_MAPPING, LINEAR_CHAINED, LINEAR_CHAINED_SET = 5, 6, 7
+
+
+def build():
+    """compile oracle/libsr_oracle.so (g++, seconds)."""
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(_HERE, "libsr_oracle.so")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(_HERE, "sr_oracle.cpp")):
+        build()
+    L = C.CDLL(path)
+    u32, i32, i64, vp = C.c_uint32, C.c_int32, C.c_int64, C.c_void_p
+    sig = {
+        "orc_join_key_hash32": (u32, [u32, u32]),
+        "orc_join_key_hash64": (u32, [C.c_uint64, u32]),
+        "orc_join_key_hash_slice": (u32, [vp, i32, u32]),
+        "orc_calc_bucket_size": (u32, [u32]),
+        "orc_crc32c": (u32, [vp, i32, u32]),
+        "orc_crc_hash_32": (u32, [vp, i32, u32]),
+        "orc_zlib_crc32": (u32, [vp, i32, u32]),
+        "orc_fnv_hash": (u32, [vp, i32, u32]),
+        "orc_xorshift32": (u32, [u32]),
+        "orc_reduce_op": (u32, [u32, u32]),
+        "orc_filter_range": (i64, [vp, vp, i32, i64, i64]),
+        "orc_scan_evaluate": (i32, [vp, vp, vp]),
+        "orc_scan_filter": (i64, [vp, vp, vp, vp]),
+        "orc_eval_expr": (i32, [vp, vp, vp, vp, vp, vp]),
+        "orc_join_create": (vp, [vp, vp]),
+        "orc_join_destroy": (None, [vp]),
+        "orc_join_append_build": (i32, [vp, vp]),
+        "orc_join_build": (i32, [vp]),
+        "orc_join_method": (i32, [vp]),
+        "orc_join_build_rows": (i64, [vp]),
+        "orc_join_bucket_size": (i64, [vp]),
+        "orc_join_min_value": (i64, [vp]),
+        "orc_join_max_value": (i64, [vp]),
+        "orc_join_first": (vp, [vp]),
+        "orc_join_next": (vp, [vp]),
+        "orc_join_probe_chunk": (i32, [vp, vp, i32, vp, vp, vp]),
+        "orc_join_probe_all": (i64, [vp, vp, vp, vp, i64]),
+        "orc_join_output": (i32, [vp, vp, i64, vp, vp, vp, vp]),
+        "orc_agg_create": (vp, [vp]),
+        "orc_agg_destroy": (None, [vp]),
+        "orc_agg_push": (i32, [vp, vp]),
+        "orc_agg_num_groups": (i64, [vp]),
+        "orc_agg_output": (i32, [vp, vp, vp]),
+        "orc_agg_out_type": (i32, [vp, i32]),
+        "orc_agg_num_out_cols": (i32, [vp]),
+        "orc_agg_merge": (i32, [vp, vp]),
+        "orc_hash_partition": (i32, [vp, vp, vp, vp, vp, vp]),
+        "orc_fragment_run": (i32, [vp, vp, i32, vp, vp]),
+        "orc_last_error": (C.c_char_p, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = L
+    return L
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc is not None and rc < 0:
+        raise OracleError(f"oracle error {rc}: {lib().orc_last_error().decode()}")
+    return rc
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _alloc_col(typ, n):
+    w = abi.TYPE_WIDTH[typ]
+    if w == 16:
+        return np.zeros(n, dtype=np.dtype((np.void, 16)))
+    return np.zeros(n, dtype=abi.TYPE_NUMPY[typ])
+
+
+def i128_to_py(arr):
+    """numpy void16 array -> list of python ints (little endian two's complement)."""
+    raw = arr.tobytes()
+    return [int.from_bytes(raw[i * 16:(i + 1) * 16], "little", signed=True) for i in range(len(arr))]
+
+
+def scan_evaluate(scan_desc, chunk):
+    sel = np.zeros(chunk.num_rows, dtype=np.uint8)
+    _check(lib().orc_scan_evaluate(scan_desc.ref(), chunk.ref(), _np_ptr(sel)))
+    return sel
+
+
+def scan_filter(scan_desc, chunk):
+    """-> (rows, {slot: (data, nulls_or_None)})"""
+    n = chunk.num_rows
+    outs, nulls = [], []
+    for s in scan_desc.out_slots:
+        k = chunk.slots.index(s)
+        outs.append(_alloc_col(chunk.types[k], n))
+        nulls.append(np.zeros(n, dtype=np.uint8) if chunk.view.cols[k].nulls else None)
+    pd = (C.c_void_p * max(1, len(outs)))(*[o.ctypes.data for o in outs])
+    pn = (C.c_void_p * max(1, len(outs)))(*[(x.ctypes.data if x is not None else None) for x in nulls])
+    rows = _check(lib().orc_scan_filter(scan_desc.ref(), chunk.ref(), pd, pn))
+    res = {}
+    for s, o, x in zip(scan_desc.out_slots, outs, nulls):
+        res[s] = (o[:rows], None if x is None else x[:rows])
+    return rows, res
+
+
+def eval_expr(expr, chunk):
+    n = chunk.num_rows
+    oi = np.zeros(n, dtype=np.int64)
+    od = np.zeros(n, dtype=np.float64)
+    on = np.zeros(n, dtype=np.uint8)
+    isd = C.c_int32(0)
+    _check(lib().orc_eval_expr(C.byref(expr), chunk.ref(), _np_ptr(oi), _np_ptr(od), _np_ptr(on), C.byref(isd)))
+    return (od if isd.value else oi), on
+
+
+class Join:
+    def __init__(self, desc, options=None, force_method=0, chunk_size=0, l2=1 << 20, l3=32 << 20):
+        self.desc = desc
+        if options is None:
+            options = orc_join_options(desc.enable_range_direct_mapping, 1, l2, l3, force_method, chunk_size)
+        self.chunk_size = chunk_size or 4096
+        self.h = lib().orc_join_create(C.byref(desc), C.byref(options))
+        if not self.h:
+            raise OracleError(lib().orc_last_error().decode())
+        self.build_types = {}
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_join_destroy(self.h)
+            self.h = None
+
+    def append_build(self, chunk):
+        for s, t in zip(chunk.slots, chunk.types):
+            self.build_types[s] = t
+        _check(lib().orc_join_append_build(self.h, chunk.ref()))
+
+    def build(self):
+        _check(lib().orc_join_build(self.h))
+
+    @property
+    def method(self):
+        return lib().orc_join_method(self.h)
+
+    @property
+    def build_rows(self):
+        return lib().orc_join_build_rows(self.h)
+
+    @property
+    def bucket_size(self):
+        return lib().orc_join_bucket_size(self.h)
+
+    @property
+    def min_value(self):
+        return lib().orc_join_min_value(self.h)
+
+    @property
+    def max_value(self):
+        return lib().orc_join_max_value(self.h)
+
+    def first(self):
+        n = self.bucket_size
+        if self.method == DENSE_RANGE_DIRECT_MAPPING:
+            n = self.build_rows + 1
+        p = lib().orc_join_first(self.h)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(n,)).copy()
+
+    def next(self):
+        p = lib().orc_join_next(self.h)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(self.build_rows + 1,)).copy()
+
+    def probe_chunk(self, chunk, first_probe=True):
+        pi = np.zeros(self.chunk_size + 8, dtype=np.uint32)
+        bi = np.zeros(self.chunk_size + 8, dtype=np.uint32)
+        res = orc_probe_result()
+        _check(lib().orc_join_probe_chunk(self.h, chunk.ref(), 1 if first_probe else 0, _np_ptr(pi), _np_ptr(bi),
+                                          C.byref(res)))
+        return pi[:res.count].copy(), bi[:res.count].copy(), res
+
+    def probe_all(self, chunk, cap=None):
+        cap = cap if cap is not None else max(1024, chunk.num_rows * 2)
+        while True:
+            pi = np.zeros(cap, dtype=np.uint32)
+            bi = np.zeros(cap, dtype=np.uint32)
+            n = lib().orc_join_probe_all(self.h, chunk.ref(), _np_ptr(pi), _np_ptr(bi), cap)
+            if n >= 0:
+                return pi[:n], bi[:n]
+            if -n <= cap:
+                _check(int(n))
+            cap = int(-n)
+
+    def output(self, chunk, pi, bi):
+        """-> list of (slot, data, nulls) for probe_out_slots + build_out_slots"""
+        d = self.desc
+        n = len(pi)
+        semi = d.join_type in (abi.JOIN_LEFT_SEMI, abi.JOIN_LEFT_ANTI)
+        slots, outs, nulls = [], [], []
+        for k in range(d.num_probe_out):
+            s = d.probe_out_slots[k]
+            t = chunk.types[chunk.slots.index(s)]
+            slots.append(s)
+            outs.append(_alloc_col(t, n))
+            nulls.append(np.zeros(n, dtype=np.uint8))
+        if not semi:
+            for k in range(d.num_build_out):
+                s = d.build_out_slots[k]
+                slots.append(s)
+                outs.append(_alloc_col(self.build_types[s], n))
+                nulls.append(np.zeros(n, dtype=np.uint8))
+        pd = (C.c_void_p * max(1, len(outs)))(*[o.ctypes.data for o in outs])
+        pn = (C.c_void_p * max(1, len(outs)))(*[x.ctypes.data for x in nulls])
+        pi = np.ascontiguousarray(pi, dtype=np.uint32)
+        bi = np.ascontiguousarray(bi, dtype=np.uint32)
+        _check(lib().orc_join_output(self.h, chunk.ref(), n, _np_ptr(pi), _np_ptr(bi), pd, pn))
+        return list(zip(slots, outs, nulls))
+
+
+class Agg:
+    def __init__(self, desc):
+        self.desc = desc
+        self.h = lib().orc_agg_create(C.byref(desc))
+        if not self.h:
+            raise OracleError(lib().orc_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_agg_destroy(self.h)
+            self.h = None
+
+    def push(self, chunk):
+        _check(lib().orc_agg_push(self.h, chunk.ref()))
+
+    def merge(self, other):
+        _check(lib().orc_agg_merge(self.h, other.h))
+
+    @property
+    def num_groups(self):
+        return lib().orc_agg_num_groups(self.h)
+
+    def output(self):
+        """-> list of (type, data ndarray, nulls ndarray) keys first then results"""
+        n = self.num_groups
+        nc = lib().orc_agg_num_out_cols(self.h)
+        types = [lib().orc_agg_out_type(self.h, k) for k in range(nc)]
+        outs = [_alloc_col(t, n) for t in types]
+        nulls = [np.zeros(n, dtype=np.uint8) for _ in types]
+        pd = (C.c_void_p * max(1, nc))(*[o.ctypes.data for o in outs])
+        pn = (C.c_void_p * max(1, nc))(*[x.ctypes.data for x in nulls])
+        _check(lib().orc_agg_output(self.h, pd, pn))
+        return list(zip(types, outs, nulls))
+
+
+def hash_partition(part_desc, chunk):
+    n = chunk.num_rows
+    hv = np.zeros(n, dtype=np.uint32)
+    ch = np.zeros(n, dtype=np.uint32)
+    ri = np.zeros(n, dtype=np.uint32)
+    st = np.zeros(part_desc.num_channels + 1, dtype=np.int64)
+    _check(lib().orc_hash_partition(C.byref(part_desc), chunk.ref(), _np_ptr(hv), _np_ptr(ch), _np_ptr(ri),
+                                    _np_ptr(st)))
+    return hv, ch, ri, st
+
+
+def fragment_run(scan_desc, joins, agg_desc, fact_chunk, num_threads=1):
+    """joins: list of (Join, probe_key_slot, [payload build slots]).  -> (Agg result, rows_passed)"""
+    d = orc_fragment_desc()
+    d.scan = scan_desc.desc
+    d.num_joins = len(joins)
+    for k, (j, slot, payload) in enumerate(joins):
+        d.joins[k].join = j.h
+        d.joins[k].probe_key_slot = slot
+        d.joins[k].num_payload = len(payload)
+        for q, s in enumerate(payload):
+            d.joins[k].payload_build_slots[q] = s
+    d.agg = agg_desc
+    result = Agg(agg_desc)
+    passed = C.c_int64(0)
+    _check(lib().orc_fragment_run(C.byref(d), fact_chunk.ref(), num_threads, result.h, C.byref(passed)))
+    return result, passed.value

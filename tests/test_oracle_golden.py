@@ -1,0 +1,373 @@
+"""Pins the CPU oracle against the reference's own known-answer tests.
+
+Every test names the reference test it reproduces (paths relative to the StarRocks tree).
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+from starrocks_b200 import abi
+from starrocks_b200.abi import Chunk
+
+
+# ---- be/test/exec/join_hash_map_test.cpp:924-1009  JoinKeyHash ---------------------------------
+@pytest.mark.parametrize("width,stride,expect", [
+    (32, 3, (0, 11)), (32, 7, (0, 14)), (32, 1, (4, 6)),
+    (64, 3, (3, 7)), (64, 7, (4, 7)), (64, 1, (4, 6)),
+])
+def test_join_key_hash_bucket_occupancy(oracle, width, stride, expect):
+    L = oracle.lib()
+    num_buckets, log_buckets = 1 << 16, 16
+    counts = np.zeros(num_buckets, dtype=np.int64)
+    fn = L.orc_join_key_hash32 if width == 32 else L.orc_join_key_hash64
+    for i in range(0, num_buckets * stride * 5, stride):
+        counts[fn(i, log_buckets)] += 1
+    assert (counts.min(), counts.max()) == expect
+
+
+def test_join_key_hash_slice(oracle):
+    # JoinKeyHash<Slice>()(Slice{"abcd",4}, 1<<16, 16) == 11538  (:1007-1008)
+    buf = np.frombuffer(b"abcd", dtype=np.uint8).copy()
+    assert oracle.lib().orc_join_key_hash_slice(buf.ctypes.data, 4, 1 << 16) == 11538
+
+
+def test_calc_bucket_num(oracle):
+    # CalcBucketNum / CalcBucketNums (:1012-1033)
+    L = oracle.lib()
+    assert L.orc_join_key_hash32(1, 2) == 2
+    assert [L.orc_join_key_hash32(v, 2) for v in (1, 2, 3, 4)] == [2, 0, 3, 1]
+
+
+def test_calc_bucket_size(oracle):
+    # JoinBuildProbeFunc uses bucket_size 16 for row_count 10 (:1147-1150); helper :70-77
+    L = oracle.lib()
+    assert L.orc_calc_bucket_size(11) == 16
+    assert L.orc_calc_bucket_size(1) == 2
+    assert L.orc_calc_bucket_size(600001) == 1 << 20
+
+
+# ---- be/test/base/hash/hash_util_test.cpp:78-100 ------------------------------------------------
+def test_hash_util_goldens(oracle):
+    L = oracle.lib()
+    hello = np.frombuffer(b"hello", dtype=np.uint8).copy()
+    assert L.orc_fnv_hash(hello.ctypes.data, 5, 0) == 0x1840de38
+    assert L.orc_fnv_hash(hello.ctypes.data, 5, 0x811C9DC5) == 0x4f9f2cab
+    assert L.orc_fnv_hash(hello.ctypes.data, 0, 0x811C9DC5) == 0x811C9DC5
+    assert L.orc_xorshift32(1) == 0x00042021
+    assert L.orc_xorshift32(0x12345678) == 0x87985aa5
+    sr = np.frombuffer(b"starrocks", dtype=np.uint8).copy()
+    assert L.orc_zlib_crc32(sr.ctypes.data, 9, 0) == zlib.crc32(b"starrocks", 0)
+    # ReduceOp (hash_util.hpp:242-244)
+    assert L.orc_reduce_op(0xFFFFFFFF, 8) == 7 and L.orc_reduce_op(0, 8) == 0
+    assert L.orc_reduce_op(0x80000000, 3) == 1
+
+
+# ---- be/test/column/column_filter_range_test.cpp:25-70 -----------------------------------------
+def test_filter_range_goldens(oracle):
+    L = oracle.lib()
+    v = np.array([10, 11, 12, 13, 14, 15], dtype=np.int32)
+    f = np.array([1, 0, 1, 0, 1, 0], dtype=np.uint8)
+    assert L.orc_filter_range(f.ctypes.data, v.ctypes.data, 4, 0, 6) == 3
+    assert list(v[:3]) == [10, 12, 14]
+    d = np.array([0.1, 0.2, 0.3, 0.4, 0.5, 0.6], dtype=np.float64)
+    f = np.array([1, 0, 1, 1, 0, 1], dtype=np.uint8)
+    assert L.orc_filter_range(f.ctypes.data, d.ctypes.data, 8, 1, 5) == 3
+    assert list(d[:3]) == [0.1, 0.3, 0.4]
+    z = np.array([7, 8, 9, 10], dtype=np.int32)
+    f0 = np.zeros(4, dtype=np.uint8)
+    assert L.orc_filter_range(f0.ctypes.data, z.ctypes.data, 4, 0, 4) == 0
+    o = np.array([100, 200, 300, 400, 500], dtype=np.int32)
+    f1 = np.ones(5, dtype=np.uint8)
+    assert L.orc_filter_range(f1.ctypes.data, o.ctypes.data, 4, 2, 5) == 5
+    assert list(o) == [100, 200, 300, 400, 500]
+
+
+# ---- join build / probe -------------------------------------------------------------------------
+def _int_join(oracle, join_type=abi.JOIN_INNER, key_type=abi.TYPE_INT, build_out=(), probe_out=(), **kw):
+    d = abi.make_join_desc(join_type, [1], [0], [key_type], build_out=build_out, probe_out=probe_out)
+    return oracle.Join(d, **kw)
+
+
+def _nullable_int32(count, start):
+    # JoinHashMapTest::create_int32_nullable_column (:695-709): odd values are NULL
+    vals = np.arange(start, start + count, dtype=np.int32)
+    nulls = (vals % 2 != 0).astype(np.uint8)
+    data = np.where(nulls == 1, 0, vals).astype(np.int32)
+    return data, nulls
+
+
+@pytest.mark.parametrize("method", ["BUCKET_CHAINED", "LINEAR_CHAINED", "RANGE_DIRECT_MAPPING",
+                                    "DENSE_RANGE_DIRECT_MAPPING"])
+def test_join_build_probe_func(oracle, method):
+    # JoinBuildProbeFunc (:1138-1185): build {0..9}, probe {0..9}: every probe row finds exactly one
+    j = _int_join(oracle, force_method=getattr(oracle, method))
+    j.append_build(Chunk([(1, np.arange(10, dtype=np.int32), None)]))
+    j.build()
+    if method == "BUCKET_CHAINED":
+        assert j.bucket_size == 16
+    first, nxt = j.first(), j.next()
+    probe = Chunk([(0, np.arange(10, dtype=np.int32), None)])
+    pi, bi, res = j.probe_chunk(probe)
+    assert res.count == 10 and not res.has_remain
+    assert list(pi) == list(range(10))
+    assert list(bi) == [i + 1 for i in range(10)]  # build row index is 1-based (row 0 = sentinel)
+    assert res.match_flag == 1  # ALL_MATCH_ONE
+    assert nxt[0] == 0 and len(first) > 0
+
+
+@pytest.mark.parametrize("method", ["BUCKET_CHAINED", "LINEAR_CHAINED", "RANGE_DIRECT_MAPPING"])
+def test_join_build_probe_func_nullable(oracle, method):
+    # JoinBuildProbeFuncNullable (:1188-1240): odd rows are NULL on both sides -> found 0 times
+    j = _int_join(oracle, force_method=getattr(oracle, method))
+    bd, bn = _nullable_int32(10, 0)
+    j.append_build(Chunk([(1, bd, bn)]))
+    j.build()
+    pd, pn = _nullable_int32(10, 0)
+    pi, bi, res = j.probe_chunk(Chunk([(0, pd, pn)]))
+    assert list(pi) == [0, 2, 4, 6, 8]
+    assert list(bi) == [1, 3, 5, 7, 9]
+
+
+def test_direct_mapping_join_build_probe_func(oracle):
+    # DirectMappingJoinBuildProbeFunc (:1243-1289): TINYINT keys -> DIRECT_MAPPING
+    j = _int_join(oracle, key_type=abi.TYPE_TINYINT, build_out=[1], probe_out=[0])
+    j.append_build(Chunk([(1, np.array([-5, -3, -1, 0, 1, 3, 5], dtype=np.int8), None)]))
+    j.build()
+    assert j.method == oracle.DIRECT_MAPPING and j.bucket_size == 256
+    probe = Chunk([(0, np.array([-8, -5, 0, 1, 2, 3, 4, 5], dtype=np.int8), None)])
+    pi, bi = j.probe_all(probe)
+    out = j.output(probe, pi, bi)
+    assert [s for s, _, _ in out] == [0, 1]
+    assert sorted(out[1][1].tolist()) == [-5, 0, 1, 3, 5]
+
+
+def test_direct_mapping_join_build_probe_func_nullable(oracle):
+    # DirectMappingJoinBuildProbeFuncNullable (:1292-1351)
+    j = _int_join(oracle, key_type=abi.TYPE_TINYINT, build_out=[1], probe_out=[0])
+    j.append_build(Chunk([(1, np.array([-5, 0, 0, 0, 1, 3, 5], dtype=np.int8),
+                           np.array([0, 1, 0, 1, 0, 0, 0], dtype=np.uint8))]))
+    j.build()
+    probe = Chunk([(0, np.array([-5, 0, 0, 0, 3, 0, 5, 0], dtype=np.int8),
+                    np.array([0, 1, 0, 1, 0, 1, 0, 1], dtype=np.uint8))])
+    pi, bi = j.probe_all(probe)
+    out = j.output(probe, pi, bi)
+    assert sorted(out[1][1].tolist()) == [-5, 0, 3, 5]
+    assert out[1][2].tolist() == [0, 0, 0, 0]
+
+
+def test_probe_from_ht_first_one_to_one_all_match(oracle):
+    # ProbeFromHtFirstOneToOneAllMatch (:1656-1695)
+    j = _int_join(oracle)
+    j.append_build(Chunk([(1, np.arange(4096, dtype=np.int32), None)]))
+    j.build()
+    pi, bi, res = j.probe_chunk(Chunk([(0, np.arange(4096, dtype=np.int32), None)]))
+    assert res.match_flag == 1 and not res.has_remain and res.cur_probe_index == 0
+    assert res.count == 4096 and res.cur_row_match_count == 0
+    assert np.array_equal(pi, np.arange(4096)) and np.array_equal(bi, np.arange(4096) + 1)
+
+
+def test_probe_from_ht_first_one_to_one_most_match(oracle):
+    # ProbeFromHtFirstOneToOneMostMatch (:1698-1745): a quarter of the probe rows find no equal key
+    j = _int_join(oracle)
+    keys = np.array([i for i in range(4096) if i % 4 != 0], dtype=np.int32)
+    j.append_build(Chunk([(1, keys, None)]))
+    j.build()
+    pi, bi, res = j.probe_chunk(Chunk([(0, np.arange(4096, dtype=np.int32), None)]))
+    assert res.match_flag == 2 and not res.has_remain and res.count == 3072
+    assert np.array_equal(pi, keys.astype(np.uint32))
+
+
+@pytest.mark.parametrize("method", ["RANGE_DIRECT_MAPPING", "BUCKET_CHAINED", "LINEAR_CHAINED"])
+def test_probe_from_ht_first_one_to_many(oracle, method):
+    # ProbeFromHtFirstOneToMany (:1748-1812): 3000 probe rows x 2 build matches, chunk_size 4096
+    j = _int_join(oracle, force_method=getattr(oracle, method))
+    build = np.concatenate([np.arange(4096), np.arange(4096)]).astype(np.int32)
+    j.append_build(Chunk([(1, build, None)]))
+    j.build()
+    if method == "RANGE_DIRECT_MAPPING":
+        # same chains the reference test builds by hand: head = second copy, next -> first copy
+        assert np.array_equal(j.next()[4097:], np.arange(1, 4097))
+        assert not j.next()[1:4097].any()
+    probe = Chunk([(0, np.arange(3000, dtype=np.int32), None)])
+    pi1, bi1, r1 = j.probe_chunk(probe, True)
+    assert r1.match_flag == 0 and r1.has_remain and r1.count == 4096
+    assert r1.cur_probe_index == 2048 and r1.cur_row_match_count == 1
+    pi2, bi2, r2 = j.probe_chunk(probe, False)
+    assert r2.match_flag == 0 and not r2.has_remain and r2.count == 1904
+    assert r2.cur_probe_index == 0 and r2.cur_row_match_count == 0
+    pairs = sorted(zip(np.concatenate([pi1, pi2]).tolist(), np.concatenate([bi1, bi2]).tolist()))
+    expect = sorted([(i, i + 1) for i in range(3000)] + [(i, 4097 + i) for i in range(3000)])
+    assert pairs == expect
+
+
+def test_probe_left_outer_found_empty(oracle):
+    # ProbeFromHtForLeftJoinFoundEmpty (:1815-1880): probe rows without a match emit build_index 0
+    j = _int_join(oracle, join_type=abi.JOIN_LEFT_OUTER)
+    j.append_build(Chunk([(1, np.arange(0, 100, 2, dtype=np.int32), None)]))
+    j.build()
+    pi, bi, res = j.probe_chunk(Chunk([(0, np.arange(100, dtype=np.int32), None)]))
+    assert res.count == 100 and list(pi) == list(range(100))
+    assert all((b == 0) == (i % 2 == 1) for i, b in enumerate(bi))
+
+
+def test_one_key_join_hash_table(oracle):
+    # OneKeyJoinHashTable (:2042-2088): build {0..9},{10..19},{20..29}; probe {1..5},{11..},{21..}
+    d = abi.make_join_desc(abi.JOIN_INNER, [3], [0], [abi.TYPE_INT], build_out=[3, 4, 5], probe_out=[0, 1, 2])
+    j = oracle.Join(d)
+    j.append_build(Chunk([(3 + k, np.arange(10 * k, 10 * k + 10, dtype=np.int32), None) for k in range(3)]))
+    j.build()
+    probe = Chunk([(k, np.arange(1 + 10 * k, 6 + 10 * k, dtype=np.int32), None) for k in range(3)])
+    pi, bi = j.probe_all(probe)
+    out = j.output(probe, pi, bi)
+    assert len(out) == 6
+    for k, (slot, data, _) in enumerate(out):
+        assert slot == k
+        assert data.tolist() == list(range(1 + 10 * (k % 3), 6 + 10 * (k % 3)))
+
+
+def test_one_nullable_key_join_hash_table(oracle):
+    # OneNullableKeyJoinHashTable (:2091-2140): NULL keys never match
+    d = abi.make_join_desc(abi.JOIN_INNER, [3], [0], [abi.TYPE_INT], build_out=[3], probe_out=[0])
+    j = oracle.Join(d)
+    bd, bn = _nullable_int32(10, 0)
+    j.append_build(Chunk([(3, bd, bn)]))
+    j.build()
+    pd, pn = _nullable_int32(5, 1)
+    probe = Chunk([(0, pd, pn)])
+    pi, bi = j.probe_all(probe)
+    out = j.output(probe, pi, bi)
+    assert out[0][1].tolist() == [2, 4] and out[1][1].tolist() == [2, 4]
+
+
+def test_selector_rules(oracle):
+    # JoinHashMapSelector::_determine_hash_map_method (join_hash_table.cpp:225-350)
+    def method(keys, join_type=abi.JOIN_INNER, **kw):
+        j = _int_join(oracle, join_type=join_type, **kw)
+        j.append_build(Chunk([(1, np.asarray(keys, dtype=np.int32), None)]))
+        j.build()
+        return j.method
+    assert method(np.arange(1, 1001)) == oracle.RANGE_DIRECT_MAPPING          # interval <= bucket_size
+    assert method([1, 1 << 19]) == oracle.RANGE_DIRECT_MAPPING                 # interval <= L2
+    assert method([1, 1 << 30]) == oracle.LINEAR_CHAINED                       # sparse -> linear chained
+    assert method([1, 1 << 30], l2=1 << 31) == oracle.RANGE_DIRECT_MAPPING
+    assert method(np.arange(1, 1001), join_type=abi.JOIN_LEFT_SEMI) == oracle.RANGE_DIRECT_MAPPING_SET
+    # dense: interval/4 + rows*4 <= 1.1*bucket*4 but interval > bucket and > L2
+    keys = np.arange(0, 3_000_000, 5, dtype=np.int32)
+    assert method(keys, l2=1 << 20) == oracle.DENSE_RANGE_DIRECT_MAPPING
+
+
+# ---- SQL goldens: test/sql/test_join/R/test_join_range_direct_mapping ---------------------------
+def sql_golden_t1(n=1_280_000):
+    """t1 of test/sql/test_join/T/test_join_range_direct_mapping: idx = row_number() = 1..n,
+    c_int = idx, c_int_null = idx if idx % 13 == 0 else NULL, c_bigint_null on % 14."""
+    idx = np.arange(1, n + 1, dtype=np.int32)
+    null13 = (idx % 13 != 0).astype(np.uint8)
+    null14 = (idx % 14 != 0).astype(np.uint8)
+    return idx, null13, idx.astype(np.int64), null14
+
+
+def test_sql_golden_range_direct_mapping_counts(oracle):
+    # R/test_join_range_direct_mapping: `t1 JOIN t1 t2 on c_int` -> 1280000; on c_int_null -> 98461;
+    # `LEFT JOIN on c_bigint_null` -> 1280000 rows of which 91428 have a build match;
+    # w1 = t1 union all t1 self-joined on c_int -> 5120000
+    idx, null13, big, null14 = sql_golden_t1()
+    for key_nulls, expect in ((None, 1280000), (null13, 98461)):
+        j = _int_join(oracle)
+        j.append_build(Chunk([(1, idx, key_nulls)]))
+        j.build()
+        assert j.method == oracle.RANGE_DIRECT_MAPPING
+        pi, bi = j.probe_all(Chunk([(0, idx, key_nulls)]))
+        assert len(pi) == expect
+    j = _int_join(oracle, join_type=abi.JOIN_LEFT_OUTER, key_type=abi.TYPE_BIGINT)
+    j.append_build(Chunk([(1, big, null14)]))
+    j.build()
+    pi, bi = j.probe_all(Chunk([(0, big, null14)]))
+    assert len(pi) == 1280000 and int((bi != 0).sum()) == 91428
+    # `where t2.c_int % 10 != 0` on the joined rows -> 73143
+    t2_c_int = idx[np.maximum(bi, 1) - 1]
+    assert int(((bi != 0) & (t2_c_int % 10 != 0)).sum()) == 73143
+    w1 = np.concatenate([idx, idx])
+    j = _int_join(oracle)
+    j.append_build(Chunk([(1, w1, None)]))
+    j.build()
+    pi, bi = j.probe_all(Chunk([(0, w1, None)]), cap=5_200_000)
+    assert len(pi) == 5120000
+
+
+# ---- aggregate: be/test/exprs/agg/aggregate_test.cpp:61-83 test_sum -----------------------------
+@pytest.mark.parametrize("typ,np_t", [(abi.TYPE_SMALLINT, np.int16), (abi.TYPE_INT, np.int32),
+                                      (abi.TYPE_BIGINT, np.int64), (abi.TYPE_FLOAT, np.float32),
+                                      (abi.TYPE_DOUBLE, np.float64)])
+def test_sum_goldens(oracle, typ, np_t):
+    col1 = np.array(list(range(1024)) + [100, 200], dtype=np_t)   # gen_input_column1
+    col2 = np.arange(2000, 3000, dtype=np_t)                      # gen_input_column2
+    d = abi.make_agg_desc(fns=[(abi.AGG_SUM, typ, 10, [("col", 0)])])
+    a1, a2 = oracle.Agg(d), oracle.Agg(d)
+    a1.push(Chunk([(0, col1, None)]))
+    a2.push(Chunk([(0, col2, None)]))
+    assert a1.output()[0][1][0] == 524076
+    assert a2.output()[0][1][0] == 2499500
+    a2.merge(a1)
+    assert a2.output()[0][1][0] == 3023576
+
+
+def test_count_avg_minmax_goldens(oracle):
+    # aggregate_test.cpp test_count / test_avg / test_max / test_min over the same generators
+    col1 = np.array(list(range(1024)) + [100, 200], dtype=np.int32)
+    fns = [(abi.AGG_COUNT, abi.TYPE_INT, 10, [("col", 0)]), (abi.AGG_AVG, abi.TYPE_INT, 11, [("col", 0)]),
+           (abi.AGG_MAX, abi.TYPE_INT, 12, [("col", 0)]), (abi.AGG_MIN, abi.TYPE_INT, 13, [("col", 0)]),
+           (abi.AGG_COUNT_STAR, abi.TYPE_INT, 14, None)]
+    a = oracle.Agg(abi.make_agg_desc(fns=fns))
+    a.push(Chunk([(0, col1, None)]))
+    out = a.output()
+    assert out[0][1][0] == 1026
+    assert out[1][1][0] == pytest.approx(524076 / 1026)
+    assert out[2][1][0] == 1023 and out[3][1][0] == 0 and out[4][1][0] == 1026
+
+
+def test_sum_nullable_all_null_is_null(oracle):
+    # test_sum_nullable (aggregate_test.cpp:962): NULL inputs are skipped, all-NULL -> NULL result
+    d = abi.make_agg_desc(fns=[(abi.AGG_SUM, abi.TYPE_INT, 10, [("col", 0)])])
+    a = oracle.Agg(d)
+    a.push(Chunk([(0, np.arange(100, dtype=np.int32), (np.arange(100) % 2).astype(np.uint8))]))
+    assert a.output()[0][1][0] == sum(range(0, 100, 2)) and a.output()[0][2][0] == 0
+    b = oracle.Agg(d)
+    b.push(Chunk([(0, np.arange(10, dtype=np.int32), np.ones(10, dtype=np.uint8))]))
+    assert b.output()[0][2][0] == 1
+
+
+# ---- test/sql/test_exchange_hash_function: sum/count per c0 % 10 bucket ------------------------
+def test_group_by_golden_mod10(oracle):
+    # c0 = 1..1000 grouped by c0 % 10: (0,100,50500), (1,100,49600), ...
+    c0 = np.arange(1, 1001, dtype=np.int32)
+    d = abi.make_agg_desc([1], [abi.TYPE_INT], fns=[(abi.AGG_COUNT_STAR, abi.TYPE_INT, 10, None),
+                                                     (abi.AGG_SUM, abi.TYPE_INT, 11, [("col", 0)])])
+    a = oracle.Agg(d)
+    a.push(Chunk([(0, c0, None), (1, (c0 % 10).astype(np.int32), None)]))
+    out = a.output()
+    rows = sorted(zip(out[0][1].tolist(), out[1][1].tolist(), out[2][1].tolist()))
+    assert rows[0] == (0, 100, 50500) and rows[1] == (1, 100, 49600)
+    assert [r[0] for r in rows] == list(range(10))
+    # insertion order of the state arena (aggregator.cpp:1718-1724): first seen key first
+    assert out[0][1].tolist() == [1, 2, 3, 4, 5, 6, 7, 8, 9, 0]
+
+
+# ---- exchange partition -------------------------------------------------------------------------
+def test_hash_partition_matches_python_fnv(oracle):
+    vals = np.array([0, 1, 2, 1000, -1, 123456789], dtype=np.int32)
+
+    def fnv(b, h):
+        for x in b:
+            h = ((x ^ h) * 0x01000193) & 0xFFFFFFFF
+        return h
+    d = abi.make_part_desc([0], 8)
+    hv, ch, ri, st = oracle.hash_partition(d, Chunk([(0, vals, None)]))
+    exp = [fnv(int(v).to_bytes(4, "little", signed=True), 0x811C9DC5) for v in vals]
+    assert hv.tolist() == exp
+    assert ch.tolist() == [(h * 8) >> 32 for h in exp]
+    # stable counting sort: rows of each channel in input order
+    assert sorted(ri.tolist()) == list(range(len(vals)))
+    for c in range(8):
+        rows = ri[st[c]:st[c + 1]].tolist()
+        assert rows == sorted(rows) and all(ch[r] == c for r in rows)
