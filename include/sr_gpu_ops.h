@@ -389,6 +389,9 @@ int64_t sr_agg_num_groups(sr_agg* agg);
  * then one result column per function.  out_mem selects host (copied back, synchronised) or
  * device buffers.  Returns SR_OK with out->num_rows == 0 at end of stream. */
 int32_t sr_agg_pull(sr_agg* agg, int64_t max_rows, int32_t out_mem, sr_chunk_out* out);
+/* Operator::reset_state (be/src/exec/pipeline/operator.h:143): clear every group and state so
+ * the handle can aggregate a new stream; keeps the compiled plan and the table capacity. */
+int32_t sr_agg_reset(sr_agg* agg);
 /* merge the (already finished) states of `other` into `agg` -- the final phase of a two-phase
  * distributed aggregate (AggregateFunction::merge, be/src/exprs/agg/aggregate.h:365-445).
  * Both handles must have been created from the same desc on the same context. */
@@ -429,6 +432,8 @@ int32_t sr_fragment_push(sr_fragment* frag, const sr_chunk_view* fact);
 /* the aggregate the fragment feeds (owned by the fragment): finish / pull / merge through
  * the sr_agg_* calls. */
 sr_agg* sr_fragment_agg(sr_fragment* frag);
+/* reset_state for the whole fragment: clears its aggregate and the rows_passed counter. */
+int32_t sr_fragment_reset(sr_fragment* frag);
 /* rows that survived scan predicates and all joins so far (synchronises). */
 int64_t sr_fragment_rows_passed(sr_fragment* frag);
 
@@ -471,6 +476,18 @@ int32_t sr_xchg_hash(sr_xchg* x, const sr_chunk_view* in, uint32_t* hash_values,
  * ------------------------------------------------------------------------------------- */
 int32_t sr_gather(sr_ctx* ctx, const void* src, int32_t type, const uint32_t* index, int64_t n, void* dst,
                   int32_t mem);
+
+/* sizeof() of the ABI structs as compiled into the library, so a foreign-language binding can
+ * verify its own struct layouts at load time.  which: 0 sr_col_view, 1 sr_chunk_view,
+ * 2 sr_chunk_out, 3 sr_pred, 4 sr_expr, 5 sr_scan_desc, 6 sr_join_desc, 7 sr_join_info,
+ * 8 sr_agg_fn, 9 sr_agg_desc, 10 sr_frag_join, 11 sr_fragment_desc, 12 sr_part_desc.
+ * returns -1 for an unknown index. */
+int32_t sr_abi_sizeof(int32_t which);
+
+/* plumbing aid: synchronous copy on the context's stream. kind: 0 = host->device,
+ * 1 = device->host, 2 = device->device.  Lets hosts without a CUDA runtime binding of their
+ * own (the ctypes tests, a JNI shim) read the device buffers handed back in sr_chunk_out. */
+int32_t sr_memcpy(sr_ctx* ctx, void* dst, const void* src, int64_t bytes, int32_t kind);
 
 /* measurement aid: read-only 128-bit-load bandwidth kernel over `bytes` of device memory
  * (SURVEY.md section 8d "measure the achievable peak"); returns the xor checksum through

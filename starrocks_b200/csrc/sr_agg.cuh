@@ -1,0 +1,1111 @@
+// sr_agg.cuh -- hash aggregate on the device.
+// Replaces K13-K17 of SURVEY.md section 2b:
+//   AggHashMap*::compute_agg_states (phmap lazy_emplace)   be/src/exec/aggregate/agg_hash_map.h:303-415,674-1263
+//   AggregateFunctionBatchHelper::update_batch              be/src/exprs/agg/aggregate.h:407-412
+//   Sum/Count/Avg/MaxMin ::update                           be/src/exprs/agg/sum.h:58-63, count.h:36, avg.h:84-103, maxmin.h
+//   update_batch_single_state (no GROUP BY)                 sum.h:74-81, aggregator.cpp:882-905
+//   Aggregator::convert_hash_map_to_chunk                   be/src/exec/aggregator.cpp:1696-1791
+//
+// Device layout: structure-of-arrays states (one 8-byte array per accumulator word) indexed by
+// slot.  Two slot spaces:
+//   * dense  -- the group-by columns have known small ranges (the FE's min/max statistics that
+//               drive the reference's compressed-key maps): slot = mixed-radix index; tables of
+//               <= 40 KB of state are accumulated in shared memory per CTA and flushed once;
+//   * hash   -- open addressing on the packed fixed-size key (<= 8 bytes incl. a null-flag
+//               byte), slot claimed with one atomicCAS on the key word; states updated with
+//               red.global.add / atom.min / atom.max.
+// int64 sums wrap exactly like the CPU (`sum += v`), so results are bit-exact whatever the
+// order; 128-bit sums use a (lo, hi) pair with an exactly-once carry; double sums use
+// atomicAdd(double) and are order dependent (tolerance 1e-6 relative in the tests).
+#pragma once
+
+#include "sr_join.cuh"
+
+namespace srd {
+
+enum AccMode : int32_t {
+    M_COUNT_STAR = 0,
+    M_COUNT,
+    M_SUM_I64,
+    M_SUM_I128,
+    M_SUM_F64,
+    M_AVG, // double sum + count
+    M_MIN_I64,
+    M_MAX_I64,
+    M_MIN_F64, // stored as order-preserving int64 image of the double
+    M_MAX_F64
+};
+
+#define SR_AGG_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+struct AggFnDev {
+    int32_t kind;
+    int32_t mode;
+    int32_t in_is_double;
+    int32_t track_n; // accn holds the non-null input count (else it equals cnt_star)
+    int32_t result_type;
+    int32_t pad;
+    long long* acc0;
+    long long* acc1;
+    long long* accn;
+    CExpr input;
+};
+
+struct AggDev {
+    int32_t num_keys, num_fns;
+    int32_t dense;
+    int32_t key_bytes; // packed key bytes incl. the null-flag byte
+    int32_t key_value_id[SR_MAX_GROUP_KEYS];
+    int32_t key_width[SR_MAX_GROUP_KEYS];
+    int32_t key_type[SR_MAX_GROUP_KEYS];
+    int32_t key_nullable[SR_MAX_GROUP_KEYS];
+    int32_t key_shift[SR_MAX_GROUP_KEYS]; // bit offset inside the packed key
+    int32_t null_shift;                   // bit offset of the null-flag byte
+    int32_t pad0;
+    long long dense_min[SR_MAX_GROUP_KEYS];
+    long long dense_extent[SR_MAX_GROUP_KEYS]; // range + nullable
+    long long dense_stride[SR_MAX_GROUP_KEYS];
+    unsigned long long cap; // slots (hash: power of two, plus one special slot at index cap)
+    unsigned long long mask;
+    unsigned long long limit; // admission limit for new groups
+    unsigned long long* hkeys;
+    long long* cnt_star;
+    unsigned long long* ngroups;
+    int32_t* flags; // [0] overflow (new group refused), [1] key out of declared range
+    AggFnDev fns[SR_MAX_AGG_FNS];
+};
+
+__device__ __forceinline__ long long f64_sortable(double d) {
+    const long long b = __double_as_longlong(d);
+    return b ^ ((b >> 63) & 0x7fffffffffffffffll);
+}
+__device__ __forceinline__ double f64_unsortable(long long s) {
+    return __longlong_as_double(s ^ ((s >> 63) & 0x7fffffffffffffffll));
+}
+
+__host__ __device__ inline long long acc_init_value(int32_t mode) {
+    switch (mode) {
+    case M_MIN_I64:
+    case M_MIN_F64:
+        return 0x7fffffffffffffffll;
+    case M_MAX_I64:
+    case M_MAX_F64:
+        return (long long)0x8000000000000000ll;
+    default:
+        return 0;
+    }
+}
+
+struct AccPtrs {
+    long long* cnt;
+    long long* acc0[SR_MAX_AGG_FNS];
+    long long* acc1[SR_MAX_AGG_FNS];
+    long long* accn[SR_MAX_AGG_FNS];
+};
+
+// apply one (non-null) input value to the accumulators of slot
+__device__ __forceinline__ void acc_apply(int32_t mode, long long* a0, long long* a1, long long slot, long long bits) {
+    switch (mode) {
+    case M_COUNT:
+        atomicAdd((unsigned long long*)a0 + slot, 1ull);
+        break;
+    case M_SUM_I64:
+        atomicAdd((unsigned long long*)a0 + slot, (unsigned long long)bits);
+        break;
+    case M_SUM_I128: {
+        const unsigned long long v = (unsigned long long)bits;
+        const unsigned long long old = atomicAdd((unsigned long long*)a0 + slot, v);
+        const unsigned long long carry = (old + v) < old ? 1ull : 0ull;
+        const unsigned long long hi = (bits < 0 ? ~0ull : 0ull) + carry;
+        if (hi) atomicAdd((unsigned long long*)a1 + slot, hi);
+        break;
+    }
+    case M_SUM_F64:
+    case M_AVG:
+        atomicAdd((double*)a0 + slot, __longlong_as_double(bits));
+        break;
+    case M_MIN_I64:
+        atomicMin(a0 + slot, bits);
+        break;
+    case M_MAX_I64:
+        atomicMax(a0 + slot, bits);
+        break;
+    case M_MIN_F64:
+        atomicMin(a0 + slot, f64_sortable(__longlong_as_double(bits)));
+        break;
+    case M_MAX_F64:
+        atomicMax(a0 + slot, f64_sortable(__longlong_as_double(bits)));
+        break;
+    default:
+        break;
+    }
+}
+
+// merge a partial state (s0, s1) into the accumulators of slot
+__device__ __forceinline__ void acc_merge(int32_t mode, long long* a0, long long* a1, long long slot, long long s0, long long s1) {
+    switch (mode) {
+    case M_COUNT:
+    case M_SUM_I64:
+        if (s0) atomicAdd((unsigned long long*)a0 + slot, (unsigned long long)s0);
+        break;
+    case M_SUM_I128: {
+        const unsigned long long v = (unsigned long long)s0;
+        const unsigned long long old = atomicAdd((unsigned long long*)a0 + slot, v);
+        const unsigned long long carry = (old + v) < old ? 1ull : 0ull;
+        const unsigned long long hi = (unsigned long long)s1 + carry;
+        if (hi) atomicAdd((unsigned long long*)a1 + slot, hi);
+        break;
+    }
+    case M_SUM_F64:
+    case M_AVG:
+        atomicAdd((double*)a0 + slot, __longlong_as_double(s0));
+        break;
+    case M_MIN_I64:
+    case M_MIN_F64:
+        atomicMin(a0 + slot, s0);
+        break;
+    case M_MAX_I64:
+    case M_MAX_F64:
+        atomicMax(a0 + slot, s0);
+        break;
+    default:
+        break;
+    }
+}
+
+// slot of the row's group; -1 when the row cannot be placed (flags set)
+template <typename Loader>
+__device__ __forceinline__ long long agg_find_slot(const AggDev& a, Loader& ld) {
+    if (a.num_keys == 0) return 0;
+    if (a.dense) {
+        long long slot = 0;
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < SR_MAX_GROUP_KEYS; k++) {
+            if (k < a.num_keys) {
+                int64_t v;
+                const bool nul = ld.load(a.key_value_id[k], v);
+                long long idx;
+                if (nul) {
+                    idx = 0;
+                    bad |= !a.key_nullable[k];
+                } else {
+                    idx = v - a.dense_min[k] + (a.key_nullable[k] ? 1 : 0);
+                    bad |= (v < a.dense_min[k]) || (idx >= a.dense_extent[k]);
+                }
+                slot += idx * a.dense_stride[k];
+            }
+        }
+        if (bad) {
+            a.flags[1] = 1;
+            return -1;
+        }
+        return slot;
+    }
+    unsigned long long key = 0;
+#pragma unroll
+    for (int k = 0; k < SR_MAX_GROUP_KEYS; k++) {
+        if (k < a.num_keys) {
+            int64_t v;
+            const bool nul = ld.load(a.key_value_id[k], v);
+            if (nul) {
+                key |= 1ull << (a.null_shift + k);
+            } else {
+                const int w = a.key_width[k];
+                const unsigned long long m = w == 8 ? ~0ull : ((1ull << (8 * w)) - 1);
+                key |= ((unsigned long long)v & m) << a.key_shift[k];
+            }
+        }
+    }
+    if (key == SR_AGG_EMPTY) return (long long)a.cap; // only possible for full 8-byte keys
+    unsigned long long s = mix64(key) & a.mask;
+    for (unsigned long long tries = 0; tries <= a.mask; tries++) {
+        unsigned long long cur = a.hkeys[s];
+        if (cur == key) return (long long)s;
+        if (cur == SR_AGG_EMPTY) {
+            // admission control: refuse new groups beyond the limit (host grows and retries)
+            if (*(volatile unsigned long long*)a.ngroups >= a.limit) {
+                a.flags[0] = 1;
+                return -1;
+            }
+            cur = atomicCAS(&a.hkeys[s], SR_AGG_EMPTY, key);
+            if (cur == SR_AGG_EMPTY) {
+                atomicAdd(a.ngroups, 1ull);
+                return (long long)s;
+            }
+            if (cur == key) return (long long)s;
+        }
+        s = (s + 1) & a.mask;
+    }
+    a.flags[0] = 1;
+    return -1;
+}
+
+template <typename Loader>
+__device__ __forceinline__ void agg_apply_row(const AggDev& a, const AccPtrs& p, long long slot, Loader& ld) {
+    atomicAdd((unsigned long long*)p.cnt + slot, 1ull);
+#pragma unroll 1
+    for (int f = 0; f < a.num_fns; f++) {
+        const AggFnDev& fn = a.fns[f];
+        if (fn.mode == M_COUNT_STAR) continue;
+        int64_t bits;
+        const bool nul = eval_expr(fn.input, ld, bits);
+        if (nul) continue;
+        acc_apply(fn.mode, p.acc0[f], p.acc1[f], slot, bits);
+        if (fn.track_n) atomicAdd((unsigned long long*)p.accn[f] + slot, 1ull);
+    }
+}
+
+__device__ __forceinline__ void acc_ptrs_global(const AggDev& a, AccPtrs& p) {
+    p.cnt = a.cnt_star;
+    for (int f = 0; f < SR_MAX_AGG_FNS; f++) {
+        p.acc0[f] = a.fns[f].acc0;
+        p.acc1[f] = a.fns[f].acc1;
+        p.accn[f] = a.fns[f].accn;
+    }
+}
+
+// shared-memory accumulators for a dense table: layout [cnt | per fn: acc0, acc1?, accn?]
+__device__ __forceinline__ void acc_ptrs_smem(const AggDev& a, long long* smem, AccPtrs& p) {
+    const long long cap = (long long)a.cap;
+    long long* q = smem;
+    p.cnt = q;
+    q += cap;
+    for (int f = 0; f < SR_MAX_AGG_FNS; f++) {
+        p.acc0[f] = p.acc1[f] = p.accn[f] = nullptr;
+        if (f < a.num_fns && a.fns[f].mode != M_COUNT_STAR) {
+            p.acc0[f] = q;
+            q += cap;
+            if (a.fns[f].mode == M_SUM_I128) {
+                p.acc1[f] = q;
+                q += cap;
+            }
+            if (a.fns[f].track_n) {
+                p.accn[f] = q;
+                q += cap;
+            }
+        }
+    }
+}
+__device__ __forceinline__ void acc_smem_init(const AggDev& a, const AccPtrs& p) {
+    const long long cap = (long long)a.cap;
+    for (long long i = threadIdx.x; i < cap; i += blockDim.x) {
+        p.cnt[i] = 0;
+        for (int f = 0; f < a.num_fns; f++) {
+            if (p.acc0[f]) p.acc0[f][i] = acc_init_value(a.fns[f].mode);
+            if (p.acc1[f]) p.acc1[f][i] = 0;
+            if (p.accn[f]) p.accn[f][i] = 0;
+        }
+    }
+}
+__device__ __forceinline__ void acc_smem_flush(const AggDev& a, const AccPtrs& p) {
+    const long long cap = (long long)a.cap;
+    for (long long i = threadIdx.x; i < cap; i += blockDim.x) {
+        const long long c = p.cnt[i];
+        if (c == 0) continue;
+        atomicAdd((unsigned long long*)a.cnt_star + i, (unsigned long long)c);
+        for (int f = 0; f < a.num_fns; f++) {
+            const AggFnDev& fn = a.fns[f];
+            if (!p.acc0[f]) continue;
+            acc_merge(fn.mode, fn.acc0, fn.acc1, i, p.acc0[f][i], p.acc1[f] ? p.acc1[f][i] : 0);
+            if (p.accn[f] && p.accn[f][i]) atomicAdd((unsigned long long*)fn.accn + i, (unsigned long long)p.accn[f][i]);
+        }
+    }
+}
+
+constexpr int AGG_BLOCK = 256;
+
+// standalone aggregate sink: one pass over a chunk.
+//  SMEM: dense table accumulated in shared memory.  slots_out (optional): pass-1-only mode
+//  (find slots, no update); slots_in (optional): pass-2 mode (slots precomputed).
+template <bool SMEM>
+__global__ void __launch_bounds__(AGG_BLOCK) k_agg_push(const AggDev* __restrict__ ad, VTab vt, int64_t n, long long* __restrict__ slots_out,
+                                                         const long long* __restrict__ slots_in) {
+    extern __shared__ long long s_acc[];
+    const AggDev& a = *ad;
+    AccPtrs p;
+    if (SMEM) {
+        acc_ptrs_smem(a, s_acc, p);
+        acc_smem_init(a, p);
+        __syncthreads();
+    } else {
+        acc_ptrs_global(a, p);
+    }
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        ChunkLoader ld{vt, row};
+        long long slot;
+        if (slots_in)
+            slot = slots_in[row];
+        else
+            slot = agg_find_slot(a, ld);
+        if (slots_out) {
+            slots_out[row] = slot;
+            continue;
+        }
+        if (slot >= 0) agg_apply_row(a, p, slot, ld);
+    }
+    if (SMEM) {
+        __syncthreads();
+        acc_smem_flush(a, p);
+    }
+}
+
+// no GROUP BY: warp-reduce additive functions before touching memory (update_batch_single_state)
+__global__ void __launch_bounds__(AGG_BLOCK) k_agg_push_single(const AggDev* __restrict__ ad, VTab vt, int64_t n) {
+    const AggDev& a = *ad;
+    long long cnt = 0;
+    long long acc[SR_MAX_AGG_FNS];
+    long long accn[SR_MAX_AGG_FNS];
+    for (int f = 0; f < SR_MAX_AGG_FNS; f++) {
+        acc[f] = f < a.num_fns ? acc_init_value(a.fns[f].mode) : 0;
+        accn[f] = 0;
+    }
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        ChunkLoader ld{vt, row};
+        cnt++;
+#pragma unroll 1
+        for (int f = 0; f < a.num_fns; f++) {
+            const AggFnDev& fn = a.fns[f];
+            if (fn.mode == M_COUNT_STAR) continue;
+            int64_t bits;
+            if (eval_expr(fn.input, ld, bits)) continue;
+            accn[f]++;
+            switch (fn.mode) {
+            case M_COUNT:
+                acc[f]++;
+                break;
+            case M_SUM_I64:
+                acc[f] = (long long)((unsigned long long)acc[f] + (unsigned long long)bits);
+                break;
+            case M_SUM_F64:
+            case M_AVG:
+                acc[f] = __double_as_longlong(__longlong_as_double(acc[f]) + __longlong_as_double(bits));
+                break;
+            case M_MIN_I64:
+                acc[f] = min(acc[f], (long long)bits);
+                break;
+            case M_MAX_I64:
+                acc[f] = max(acc[f], (long long)bits);
+                break;
+            case M_MIN_F64:
+                acc[f] = min(acc[f], f64_sortable(__longlong_as_double(bits)));
+                break;
+            case M_MAX_F64:
+                acc[f] = max(acc[f], f64_sortable(__longlong_as_double(bits)));
+                break;
+            default: // M_SUM_I128: apply directly (rare)
+                acc_apply(fn.mode, fn.acc0, fn.acc1, 0, bits);
+                break;
+            }
+        }
+    }
+    cnt = warp_sum(cnt);
+    if (lane_id() == 0 && cnt) atomicAdd((unsigned long long*)a.cnt_star, (unsigned long long)cnt);
+#pragma unroll 1
+    for (int f = 0; f < a.num_fns; f++) {
+        const AggFnDev& fn = a.fns[f];
+        if (fn.mode == M_COUNT_STAR) continue;
+        long long v = acc[f];
+        switch (fn.mode) {
+        case M_SUM_F64:
+        case M_AVG: {
+            double d = __longlong_as_double(v);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(SR_FULL_MASK, d, o);
+            v = __double_as_longlong(d);
+            break;
+        }
+        case M_MIN_I64:
+        case M_MIN_F64:
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(SR_FULL_MASK, v, o));
+            break;
+        case M_MAX_I64:
+        case M_MAX_F64:
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(SR_FULL_MASK, v, o));
+            break;
+        case M_SUM_I128:
+            v = 0;
+            break;
+        default:
+            v = (long long)warp_sum((unsigned long long)v);
+            break;
+        }
+        const long long nn = warp_sum(accn[f]);
+        if (lane_id() == 0 && nn) {
+            if (fn.mode != M_SUM_I128) acc_merge(fn.mode, fn.acc0, fn.acc1, 0, v, 0);
+            if (fn.track_n) atomicAdd((unsigned long long*)fn.accn, (unsigned long long)nn);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fill_i64(long long* p, int64_t n, long long v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void __launch_bounds__(256) k_copy_i64(long long* dst, const long long* src, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// move every occupied slot of `o` into `a` (growth) -- plain stores, slots are unique
+__global__ void __launch_bounds__(256) k_agg_rehash(const AggDev* __restrict__ od, const AggDev* __restrict__ nd) {
+    const AggDev& o = *od;
+    const AggDev& a = *nd;
+    for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s <= o.cap; s += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long t;
+        if (s == o.cap) {
+            if (o.cnt_star[s] == 0) continue;
+            t = a.cap;
+        } else {
+            const unsigned long long key = o.hkeys[s];
+            if (key == SR_AGG_EMPTY) continue;
+            t = mix64(key) & a.mask;
+            while (true) {
+                const unsigned long long cur = atomicCAS(&a.hkeys[t], SR_AGG_EMPTY, key);
+                if (cur == SR_AGG_EMPTY) break;
+                t = (t + 1) & a.mask;
+            }
+        }
+        a.cnt_star[t] = o.cnt_star[s];
+        for (int f = 0; f < a.num_fns; f++) {
+            if (a.fns[f].acc0) a.fns[f].acc0[t] = o.fns[f].acc0[s];
+            if (a.fns[f].acc1) a.fns[f].acc1[t] = o.fns[f].acc1[s];
+            if (a.fns[f].accn) a.fns[f].accn[t] = o.fns[f].accn ? o.fns[f].accn[s] : o.cnt_star[s];
+        }
+    }
+}
+
+// merge every occupied slot of `o` (finished) into `a` (AggregateFunction::merge)
+__global__ void __launch_bounds__(256) k_agg_merge(const AggDev* __restrict__ od, const AggDev* __restrict__ nd) {
+    const AggDev& o = *od;
+    const AggDev& a = *nd;
+    const unsigned long long total = o.dense ? o.cap : o.cap + 1;
+    for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (unsigned long long)gridDim.x * blockDim.x) {
+        const long long c = o.cnt_star[s];
+        if (c == 0) continue;
+        long long t;
+        if (a.dense || a.num_keys == 0) {
+            t = (long long)s;
+        } else if (s == o.cap) {
+            t = (long long)a.cap;
+        } else {
+            const unsigned long long key = o.hkeys[s];
+            unsigned long long q = mix64(key) & a.mask;
+            t = -1;
+            for (unsigned long long tries = 0; tries <= a.mask; tries++) {
+                unsigned long long cur = a.hkeys[q];
+                if (cur == SR_AGG_EMPTY) {
+                    cur = atomicCAS(&a.hkeys[q], SR_AGG_EMPTY, key);
+                    if (cur == SR_AGG_EMPTY) atomicAdd(a.ngroups, 1ull);
+                    if (cur == SR_AGG_EMPTY) cur = key;
+                }
+                if (cur == key) {
+                    t = (long long)q;
+                    break;
+                }
+                q = (q + 1) & a.mask;
+            }
+            if (t < 0) {
+                a.flags[0] = 1;
+                continue;
+            }
+        }
+        atomicAdd((unsigned long long*)a.cnt_star + t, (unsigned long long)c);
+        for (int f = 0; f < a.num_fns; f++) {
+            const AggFnDev& fo = o.fns[f];
+            const AggFnDev& fa = a.fns[f];
+            if (fa.mode == M_COUNT_STAR) continue;
+            const long long n = fo.track_n ? fo.accn[s] : c;
+            if (n == 0) continue;
+            acc_merge(fa.mode, fa.acc0, fa.acc1, t, fo.acc0[s], fo.acc1 ? fo.acc1[s] : 0);
+            if (fa.track_n) atomicAdd((unsigned long long*)fa.accn + t, (unsigned long long)n);
+        }
+    }
+}
+
+// ---- output: ordered compaction of occupied slots -----------------------------------------
+constexpr int EMIT_BLOCK = 256;
+
+__device__ __forceinline__ bool agg_slot_occupied(const AggDev& a, unsigned long long s) {
+    if (a.num_keys == 0) return true; // the single state always yields one row
+    return a.cnt_star[s] != 0;
+}
+
+__global__ void __launch_bounds__(EMIT_BLOCK) k_agg_count(const AggDev* __restrict__ ad, unsigned long long total, uint32_t* __restrict__ block_counts) {
+    __shared__ uint32_t s_cnt[EMIT_BLOCK / 32];
+    const unsigned long long s = (unsigned long long)blockIdx.x * EMIT_BLOCK + threadIdx.x;
+    uint32_t c = (s < total && agg_slot_occupied(*ad, s)) ? 1u : 0u;
+    c = warp_sum(c);
+    if (lane_id() == 0) s_cnt[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < EMIT_BLOCK / 32; w++) t += s_cnt[w];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+struct EmitCol {
+    void* data;
+    uint8_t* nulls;
+    int32_t type;
+    int32_t width;
+};
+struct EmitArgs {
+    EmitCol keys[SR_MAX_GROUP_KEYS];
+    EmitCol res[SR_MAX_AGG_FNS];
+};
+
+__device__ __forceinline__ void store_int_typed(void* dst, int32_t width, long long row, long long v) {
+    switch (width) {
+    case 1:
+        ((int8_t*)dst)[row] = (int8_t)v;
+        break;
+    case 2:
+        ((int16_t*)dst)[row] = (int16_t)v;
+        break;
+    case 4:
+        ((int32_t*)dst)[row] = (int32_t)v;
+        break;
+    default:
+        ((long long*)dst)[row] = v;
+        break;
+    }
+}
+
+__global__ void __launch_bounds__(EMIT_BLOCK) k_agg_emit(const AggDev* __restrict__ ad, unsigned long long total, const uint64_t* __restrict__ block_offsets,
+                                                          EmitArgs ea) {
+    __shared__ uint32_t s_scan[EMIT_BLOCK / 32 + 1];
+    const AggDev& a = *ad;
+    const unsigned long long s = (unsigned long long)blockIdx.x * EMIT_BLOCK + threadIdx.x;
+    const uint32_t occ = (s < total && agg_slot_occupied(a, s)) ? 1u : 0u;
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan<EMIT_BLOCK>(occ, s_scan, &tot);
+    if (!occ) return;
+    const long long o = (long long)(block_offsets[blockIdx.x] + ex);
+    // keys
+    if (a.dense) {
+        unsigned long long rem = s;
+        for (int k = 0; k < a.num_keys; k++) {
+            const long long idx = (long long)(rem / (unsigned long long)a.dense_stride[k]);
+            rem = rem % (unsigned long long)a.dense_stride[k];
+            const bool nul = a.key_nullable[k] && idx == 0;
+            const long long v = nul ? 0 : a.dense_min[k] + idx - (a.key_nullable[k] ? 1 : 0);
+            store_int_typed(ea.keys[k].data, ea.keys[k].width, o, v);
+            if (ea.keys[k].nulls) ea.keys[k].nulls[o] = nul ? 1 : 0;
+        }
+    } else if (a.num_keys > 0) {
+        const unsigned long long key = s == a.cap ? SR_AGG_EMPTY : a.hkeys[s];
+        for (int k = 0; k < a.num_keys; k++) {
+            const int w = a.key_width[k];
+            const unsigned long long m = w == 8 ? ~0ull : ((1ull << (8 * w)) - 1);
+            unsigned long long raw = (key >> a.key_shift[k]) & m;
+            long long v = (long long)raw;
+            if (w < 8 && a.key_type[k] != SR_TYPE_BOOLEAN) v = (long long)(raw << (64 - 8 * w)) >> (64 - 8 * w); // sign extend
+            const bool nul = a.key_nullable[k] && ((key >> (a.null_shift + k)) & 1ull);
+            store_int_typed(ea.keys[k].data, w, o, nul ? 0 : v);
+            if (ea.keys[k].nulls) ea.keys[k].nulls[o] = nul ? 1 : 0;
+        }
+    }
+    // results
+    const long long c = a.cnt_star[s];
+    for (int f = 0; f < a.num_fns; f++) {
+        const AggFnDev& fn = a.fns[f];
+        const EmitCol& ec = ea.res[f];
+        const long long n = fn.mode == M_COUNT_STAR ? c : (fn.track_n ? fn.accn[s] : c);
+        bool nul = false;
+        switch (fn.mode) {
+        case M_COUNT_STAR:
+            ((long long*)ec.data)[o] = c;
+            break;
+        case M_COUNT:
+            ((long long*)ec.data)[o] = fn.acc0[s];
+            break;
+        case M_SUM_I64:
+            nul = n == 0;
+            ((long long*)ec.data)[o] = nul ? 0 : fn.acc0[s];
+            break;
+        case M_SUM_I128:
+            nul = n == 0;
+            ((long long*)ec.data)[2 * o] = nul ? 0 : fn.acc0[s];
+            ((long long*)ec.data)[2 * o + 1] = nul ? 0 : fn.acc1[s];
+            break;
+        case M_SUM_F64:
+            nul = n == 0;
+            ((double*)ec.data)[o] = nul ? 0.0 : __longlong_as_double(fn.acc0[s]);
+            break;
+        case M_AVG: // AvgAggregateFunction::finalize_to_column (avg.h:218-236): sum / count
+            nul = n == 0;
+            ((double*)ec.data)[o] = nul ? 0.0 : __longlong_as_double(fn.acc0[s]) / (double)n;
+            break;
+        case M_MIN_I64:
+        case M_MAX_I64:
+            nul = n == 0;
+            store_int_typed(ec.data, ec.width, o, nul ? 0 : fn.acc0[s]);
+            break;
+        default: { // M_MIN_F64 / M_MAX_F64
+            nul = n == 0;
+            const double d = nul ? 0.0 : f64_unsortable(fn.acc0[s]);
+            if (ec.type == SR_TYPE_FLOAT)
+                ((float*)ec.data)[o] = (float)d;
+            else
+                ((double*)ec.data)[o] = d;
+            break;
+        }
+        }
+        if (ec.nulls) ec.nulls[o] = nul ? 1 : 0;
+    }
+}
+
+} // namespace srd
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct sr_agg {
+    sr_ctx* ctx = nullptr;
+    sr_agg_desc desc;
+    bool compiled = false;
+    bool finished = false;
+    VReg reg;
+    srd::AggDev host; // host mirror of the device descriptor
+    DevBuf dev;       // AggDev on device
+    DevBuf hkeys, cnt_star, counters /* ngroups + flags */;
+    DevBuf acc0[SR_MAX_AGG_FNS], acc1[SR_MAX_AGG_FNS], accn[SR_MAX_AGG_FNS];
+    DevBuf slots_tmp;
+    Staged staged;
+    int64_t ngroups_host = 0; // hash mode: groups after the last synchronising push
+    size_t smem_bytes = 0;    // > 0: dense table accumulated in shared memory
+    // output
+    int64_t out_rows = -1;
+    int64_t cursor = 0;
+    DevBuf block_counts, block_offsets;
+    std::vector<DevBuf> out_bufs;      // device result columns (data, nulls) x (keys + fns)
+    std::vector<std::vector<uint8_t>> host_bufs;
+    int32_t out_types[SR_MAX_GROUP_KEYS + SR_MAX_AGG_FNS];
+    bool out_has_nulls[SR_MAX_GROUP_KEYS + SR_MAX_AGG_FNS];
+};
+
+static int32_t agg_result_type(const sr_agg_fn& f) {
+    switch (f.kind) {
+    case SR_AGG_COUNT:
+    case SR_AGG_COUNT_STAR:
+        return SR_TYPE_BIGINT;
+    case SR_AGG_AVG:
+        return SR_TYPE_DOUBLE;
+    case SR_AGG_SUM:
+        if (srd::is_float_class(f.input_type)) return SR_TYPE_DOUBLE;
+        if (srd::is_decimal(f.input_type)) return SR_TYPE_DECIMAL128;
+        if (f.input_type == SR_TYPE_LARGEINT) return SR_TYPE_LARGEINT;
+        return SR_TYPE_BIGINT;
+    default:
+        return f.input_type;
+    }
+}
+
+static int32_t agg_validate_desc(sr_ctx* ctx, const sr_agg_desc* d) {
+    if (d->num_group_keys < 0 || d->num_group_keys > SR_MAX_GROUP_KEYS) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "num_group_keys %d", d->num_group_keys);
+    if (d->num_fns < 0 || d->num_fns > SR_MAX_AGG_FNS) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "num_fns %d", d->num_fns);
+    for (int k = 0; k < d->num_group_keys; k++) {
+        const int w = srd::type_width(d->group_types[k]);
+        if (w == 0 || w > 8 || srd::is_float_class(d->group_types[k])) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "group key type %d", d->group_types[k]);
+    }
+    for (int f = 0; f < d->num_fns; f++) {
+        const sr_agg_fn& fn = d->fns[f];
+        if (fn.kind < SR_AGG_SUM || fn.kind > SR_AGG_MAX) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "aggregate kind %d", fn.kind);
+        if (fn.kind != SR_AGG_COUNT_STAR && srd::type_width(fn.input_type) == 0) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "aggregate input type %d", fn.input_type);
+        if (fn.kind == SR_AGG_AVG && (srd::is_decimal(fn.input_type) || srd::type_width(fn.input_type) > 8))
+            return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "AVG on decimal / largeint");
+        if ((fn.kind == SR_AGG_MIN || fn.kind == SR_AGG_MAX) && srd::type_width(fn.input_type) > 8)
+            return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "MIN/MAX on 128-bit values");
+    }
+    return SR_OK;
+}
+
+static int32_t agg_upload(sr_agg* a) {
+    sr_ctx* ctx = a->ctx;
+    SR_TRY(a->dev.reserve(ctx, sizeof(srd::AggDev)));
+    SR_CUDA(ctx, cudaMemcpyAsync(a->dev.p, &a->host, sizeof(srd::AggDev), cudaMemcpyHostToDevice, ctx->stream));
+    SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SR_OK;
+}
+
+// allocate + initialise state arrays for `cap` slots into the given buffers, wiring `h`
+static int32_t agg_alloc_tables(sr_agg* a, srd::AggDev* h, uint64_t cap, DevBuf* hkeys, DevBuf* cnt, DevBuf* a0, DevBuf* a1, DevBuf* an) {
+    sr_ctx* ctx = a->ctx;
+    const bool hash = !h->dense && h->num_keys > 0;
+    const uint64_t total = hash ? cap + 1 : cap;
+    const int grid = std::min(grid_for((int64_t)total, 256), ctx->num_sms * 8);
+    h->cap = cap;
+    h->mask = cap - 1;
+    h->limit = hash ? cap / 2 : ~0ull;
+    if (hash) {
+        SR_TRY(hkeys->reserve(ctx, sizeof(uint64_t) * total));
+        srd::k_fill_u64<<<grid, 256, 0, ctx->stream>>>(hkeys->as<unsigned long long>(), (int64_t)total, SR_AGG_EMPTY);
+        SR_LAUNCH_CHECK(ctx);
+        h->hkeys = hkeys->as<unsigned long long>();
+    } else {
+        h->hkeys = nullptr;
+    }
+    SR_TRY(cnt->reserve(ctx, sizeof(int64_t) * total));
+    SR_CUDA(ctx, cudaMemsetAsync(cnt->p, 0, sizeof(int64_t) * total, ctx->stream));
+    h->cnt_star = cnt->as<long long>();
+    for (int f = 0; f < h->num_fns; f++) {
+        srd::AggFnDev& fn = h->fns[f];
+        fn.acc0 = fn.acc1 = fn.accn = nullptr;
+        if (fn.mode == srd::M_COUNT_STAR) continue;
+        SR_TRY(a0[f].reserve(ctx, sizeof(int64_t) * total));
+        srd::k_fill_i64<<<grid, 256, 0, ctx->stream>>>(a0[f].as<long long>(), (int64_t)total, srd::acc_init_value(fn.mode));
+        SR_LAUNCH_CHECK(ctx);
+        fn.acc0 = a0[f].as<long long>();
+        if (fn.mode == srd::M_SUM_I128) {
+            SR_TRY(a1[f].reserve(ctx, sizeof(int64_t) * total));
+            SR_CUDA(ctx, cudaMemsetAsync(a1[f].p, 0, sizeof(int64_t) * total, ctx->stream));
+            fn.acc1 = a1[f].as<long long>();
+        }
+        if (fn.track_n) {
+            SR_TRY(an[f].reserve(ctx, sizeof(int64_t) * total));
+            SR_CUDA(ctx, cudaMemsetAsync(an[f].p, 0, sizeof(int64_t) * total, ctx->stream));
+            fn.accn = an[f].as<long long>();
+        }
+    }
+    return SR_OK;
+}
+
+typedef int32_t (*agg_type_fn)(void* user, int32_t slot);
+typedef bool (*agg_nullable_fn)(void* user, int32_t slot);
+
+// compile the descriptor against the input's slot types (first push).
+static int32_t agg_compile(sr_agg* a, slot_type_fn tf, agg_nullable_fn nf, void* user) {
+    sr_ctx* ctx = a->ctx;
+    const sr_agg_desc& d = a->desc;
+    srd::AggDev& h = a->host;
+    memset(&h, 0, sizeof(h));
+    a->reg = VReg();
+    h.num_keys = d.num_group_keys;
+    h.num_fns = d.num_fns;
+    int bits = 0;
+    bool any_nullable = false;
+    for (int k = 0; k < d.num_group_keys; k++) {
+        const int32_t t = tf(user, d.group_slots[k]);
+        if (t == 0) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "group-by slot %d not in the input", d.group_slots[k]);
+        if (srd::type_width(t) != srd::type_width(d.group_types[k]) || srd::is_float_class(t))
+            return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "group-by slot %d: input type %d differs from group_types %d", d.group_slots[k], t, d.group_types[k]);
+        const int id = a->reg.add(d.group_slots[k], t);
+        if (id >= SR_MAX_VALUES) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "too many distinct columns");
+        h.key_value_id[k] = id;
+        h.key_width[k] = srd::type_width(t);
+        h.key_type[k] = d.group_types[k];
+        h.key_nullable[k] = (d.group_nullable[k] || nf(user, d.group_slots[k])) ? 1 : 0;
+        any_nullable |= h.key_nullable[k] != 0;
+        h.key_shift[k] = bits;
+        bits += 8 * h.key_width[k];
+    }
+    h.null_shift = bits;
+    h.key_bytes = bits / 8 + (any_nullable ? 1 : 0);
+    for (int f = 0; f < d.num_fns; f++) {
+        const sr_agg_fn& fn = d.fns[f];
+        srd::AggFnDev& fd = h.fns[f];
+        fd.kind = fn.kind;
+        fd.result_type = agg_result_type(fn);
+        fd.track_n = 0;
+        if (fn.kind == SR_AGG_COUNT_STAR) {
+            fd.mode = srd::M_COUNT_STAR;
+            continue;
+        }
+        SR_TRY(compile_expr(ctx, &fn.input, &a->reg, tf, user, &fd.input));
+        fd.in_is_double = fd.input.result_is_double;
+        // is any input column of the expression nullable?
+        bool nullable_in = false;
+        for (int k = 0; k < fn.input.num_nodes; k++)
+            if (fn.input.nodes[k].op == SR_EX_COL) nullable_in |= nf(user, fn.input.nodes[k].slot_id);
+        fd.track_n = nullable_in ? 1 : 0;
+        const bool dbl = fd.in_is_double != 0;
+        switch (fn.kind) {
+        case SR_AGG_COUNT:
+            fd.mode = srd::M_COUNT;
+            fd.track_n = 0;
+            break;
+        case SR_AGG_SUM:
+            if (dbl)
+                fd.mode = srd::M_SUM_F64;
+            else
+                fd.mode = (fd.result_type == SR_TYPE_DECIMAL128 || fd.result_type == SR_TYPE_LARGEINT) ? srd::M_SUM_I128 : srd::M_SUM_I64;
+            if (!dbl && srd::is_float_class(fn.input_type)) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "fn %d: input_type is floating but the expression is integer", f);
+            if (dbl && !srd::is_float_class(fn.input_type)) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "fn %d: input_type is integer but the expression is double", f);
+            break;
+        case SR_AGG_AVG:
+            fd.mode = srd::M_AVG;
+            if (!dbl) { // AvgAggregateState<double>: integer inputs are accumulated as double (avg.h:62-66)
+                if (fd.input.num_nodes >= SR_MAX_EXPR_NODES) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "expression too long");
+                fd.input.nodes[fd.input.num_nodes].op = srd::C_I2D;
+                fd.input.num_nodes++;
+                fd.input.result_is_double = 1;
+            }
+            break;
+        case SR_AGG_MIN:
+            fd.mode = dbl ? srd::M_MIN_F64 : srd::M_MIN_I64;
+            break;
+        default:
+            fd.mode = dbl ? srd::M_MAX_F64 : srd::M_MAX_I64;
+            break;
+        }
+    }
+    // slot space
+    h.dense = 0;
+    uint64_t cap = 1;
+    if (d.num_group_keys == 0) {
+        h.dense = 1;
+        cap = 1;
+    } else if (d.has_ranges) {
+        unsigned __int128 prod = 1;
+        bool ok = true;
+        for (int k = 0; k < d.num_group_keys; k++) {
+            if (d.group_max[k] < d.group_min[k]) ok = false;
+            const unsigned __int128 ext = (unsigned __int128)((__int128)d.group_max[k] - d.group_min[k]) + 1 + (h.key_nullable[k] ? 1 : 0);
+            prod *= ext;
+            if (prod > ((unsigned __int128)1 << 22)) ok = false;
+            if (!ok) break;
+        }
+        if (ok) {
+            h.dense = 1;
+            cap = (uint64_t)prod;
+            uint64_t stride = cap;
+            for (int k = 0; k < d.num_group_keys; k++) {
+                h.dense_min[k] = d.group_min[k];
+                h.dense_extent[k] = d.group_max[k] - d.group_min[k] + 1 + (h.key_nullable[k] ? 1 : 0);
+                stride /= (uint64_t)h.dense_extent[k];
+                h.dense_stride[k] = (long long)stride;
+            }
+        }
+    }
+    if (!h.dense) {
+        if (h.key_bytes > 8) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "packed group-by key of %d bytes (> 8) without usable ranges", h.key_bytes);
+        cap = 1ull << 21;
+        const uint64_t want = d.expected_groups > 0 ? (uint64_t)d.expected_groups * 2 : 0;
+        while (cap < want) cap <<= 1;
+    }
+    SR_TRY(a->counters.reserve(ctx, 64));
+    SR_CUDA(ctx, cudaMemsetAsync(a->counters.p, 0, 64, ctx->stream));
+    h.ngroups = a->counters.as<unsigned long long>();
+    h.flags = (int32_t*)(a->counters.as<unsigned long long>() + 1);
+    SR_TRY(agg_alloc_tables(a, &h, cap, &a->hkeys, &a->cnt_star, a->acc0, a->acc1, a->accn));
+    // shared-memory accumulation for small dense tables
+    a->smem_bytes = 0;
+    if (h.dense && d.num_group_keys > 0) {
+        size_t words = 1;
+        for (int f = 0; f < h.num_fns; f++) {
+            if (h.fns[f].mode == srd::M_COUNT_STAR) continue;
+            words += 1 + (h.fns[f].mode == srd::M_SUM_I128 ? 1 : 0) + (h.fns[f].track_n ? 1 : 0);
+        }
+        const size_t bytes = words * cap * sizeof(int64_t);
+        if (bytes <= 40 * 1024) a->smem_bytes = bytes;
+    }
+    SR_TRY(agg_upload(a));
+    a->compiled = true;
+    return SR_OK;
+}
+
+static int32_t agg_grow(sr_agg* a, uint64_t new_cap) {
+    sr_ctx* ctx = a->ctx;
+    srd::AggDev nh = a->host;
+    DevBuf nk, nc, n0[SR_MAX_AGG_FNS], n1[SR_MAX_AGG_FNS], nn[SR_MAX_AGG_FNS], ndev;
+    SR_TRY(agg_alloc_tables(a, &nh, new_cap, &nk, &nc, n0, n1, nn));
+    SR_TRY(ndev.reserve(ctx, sizeof(srd::AggDev)));
+    SR_CUDA(ctx, cudaMemcpyAsync(ndev.p, &nh, sizeof(srd::AggDev), cudaMemcpyHostToDevice, ctx->stream));
+    const int grid = std::min(grid_for((int64_t)a->host.cap + 1, 256), ctx->num_sms * 16);
+    srd::k_agg_rehash<<<grid, 256, 0, ctx->stream>>>((const srd::AggDev*)a->dev.p, (const srd::AggDev*)ndev.p);
+    SR_LAUNCH_CHECK(ctx);
+    SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::swap(a->hkeys, nk);
+    std::swap(a->cnt_star, nc);
+    for (int f = 0; f < SR_MAX_AGG_FNS; f++) {
+        std::swap(a->acc0[f], n0[f]);
+        std::swap(a->acc1[f], n1[f]);
+        std::swap(a->accn[f], nn[f]);
+    }
+    a->host = nh;
+    return agg_upload(a);
+}
+
+// read ngroups + flags (synchronises)
+static int32_t agg_read_counters(sr_agg* a, uint64_t* ngroups, int32_t* overflow, int32_t* bad_range) {
+    sr_ctx* ctx = a->ctx;
+    SR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned + 8, a->counters.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *ngroups = ctx->pinned[8];
+    const int32_t* fl = (const int32_t*)(ctx->pinned + 9);
+    *overflow = fl[0];
+    *bad_range = fl[1];
+    return SR_OK;
+}
+
+static bool staged_slot_nullable(void* user, int32_t slot) {
+    const Staged* st = (const Staged*)user;
+    const int k = st->find(slot);
+    return k >= 0 && st->cols[k].nulls != nullptr;
+}
+
+static int32_t agg_check_nullability(sr_agg* a, const VTab& vt) {
+    // a column that was non-nullable at compile time must stay so (its null-tracking state was elided)
+    const srd::AggDev& h = a->host;
+    for (int k = 0; k < h.num_keys; k++)
+        if (!h.key_nullable[k] && vt.v[h.key_value_id[k]].nulls)
+            return sr_fail(a->ctx, SR_ERR_INVALID_ARGUMENT, "group-by slot %d became nullable; declare it in group_nullable", a->desc.group_slots[k]);
+    for (int f = 0; f < h.num_fns; f++) {
+        const srd::AggFnDev& fn = h.fns[f];
+        if (fn.mode == srd::M_COUNT_STAR || fn.mode == srd::M_COUNT || fn.track_n) continue;
+        for (int k = 0; k < fn.input.num_nodes; k++)
+            if ((fn.input.nodes[k].op == srd::C_LOAD_I || fn.input.nodes[k].op == srd::C_LOAD_D) && vt.v[fn.input.nodes[k].arg].nulls) {
+                // start tracking the non-null count: accn := cnt_star so far
+                srd::AggFnDev& hf = a->host.fns[f];
+                const uint64_t total = (!h.dense && h.num_keys > 0) ? h.cap + 1 : h.cap;
+                SR_TRY(a->accn[f].reserve(a->ctx, sizeof(int64_t) * total));
+                srd::k_copy_i64<<<std::min(grid_for((int64_t)total, 256), a->ctx->num_sms * 8), 256, 0, a->ctx->stream>>>(
+                        a->accn[f].as<long long>(), a->cnt_star.as<long long>(), (int64_t)total);
+                SR_LAUNCH_CHECK(a->ctx);
+                hf.accn = a->accn[f].as<long long>();
+                hf.track_n = 1;
+                a->smem_bytes = 0; // layout changed; fall back to global accumulation
+                SR_TRY(agg_upload(a));
+                break;
+            }
+    }
+    return SR_OK;
+}
+
+// push rows described by vt (already bound) -- shared by sr_agg_push and the unfused paths
+static int32_t agg_push_vtab(sr_agg* a, const VTab& vt, int64_t n) {
+    sr_ctx* ctx = a->ctx;
+    if (n <= 0) return SR_OK;
+    SR_TRY(agg_check_nullability(a, vt));
+    const srd::AggDev& h = a->host;
+    const srd::AggDev* dev = (const srd::AggDev*)a->dev.p;
+    const int grid = std::min(grid_for(n, srd::AGG_BLOCK), ctx->num_sms * 8);
+    if (h.num_keys == 0) {
+        srd::k_agg_push_single<<<grid, srd::AGG_BLOCK, 0, ctx->stream>>>(dev, vt, n);
+        SR_LAUNCH_CHECK(ctx);
+        return SR_OK;
+    }
+    if (h.dense) {
+        if (a->smem_bytes > 0) {
+            srd::k_agg_push<true><<<grid, srd::AGG_BLOCK, a->smem_bytes, ctx->stream>>>(dev, vt, n, nullptr, nullptr);
+        } else {
+            srd::k_agg_push<false><<<grid, srd::AGG_BLOCK, 0, ctx->stream>>>(dev, vt, n, nullptr, nullptr);
+        }
+        SR_LAUNCH_CHECK(ctx);
+        return SR_OK;
+    }
+    // hash mode
+    if ((uint64_t)a->ngroups_host + (uint64_t)n <= h.limit) {
+        // cannot overflow: single fused pass
+        srd::k_agg_push<false><<<grid, srd::AGG_BLOCK, 0, ctx->stream>>>(dev, vt, n, nullptr, nullptr);
+        SR_LAUNCH_CHECK(ctx);
+    } else {
+        // two passes: find/insert slots (growing the table until every row is placed), then update
+        SR_TRY(a->slots_tmp.reserve(ctx, sizeof(int64_t) * (size_t)n));
+        while (true) {
+            srd::k_agg_push<false><<<grid, srd::AGG_BLOCK, 0, ctx->stream>>>((const srd::AggDev*)a->dev.p, vt, n, a->slots_tmp.as<long long>(), nullptr);
+            SR_LAUNCH_CHECK(ctx);
+            uint64_t ng;
+            int32_t ovf, bad;
+            SR_TRY(agg_read_counters(a, &ng, &ovf, &bad));
+            a->ngroups_host = (int64_t)ng;
+            if (!ovf) break;
+            SR_CUDA(ctx, cudaMemsetAsync((uint8_t*)a->counters.p + 8, 0, 8, ctx->stream));
+            SR_TRY(agg_grow(a, a->host.cap * 4));
+        }
+        srd::k_agg_push<false><<<grid, srd::AGG_BLOCK, 0, ctx->stream>>>((const srd::AggDev*)a->dev.p, vt, n, nullptr, a->slots_tmp.as<long long>());
+        SR_LAUNCH_CHECK(ctx);
+        return SR_OK;
+    }
+    uint64_t ng;
+    int32_t ovf, bad;
+    SR_TRY(agg_read_counters(a, &ng, &ovf, &bad));
+    a->ngroups_host = (int64_t)ng;
+    if (ovf) return sr_fail(ctx, SR_ERR_STATE, "aggregate hash table overflow (internal)");
+    return SR_OK;
+}
+
+static int32_t agg_finish_output(sr_agg* a) {
+    sr_ctx* ctx = a->ctx;
+    if (a->out_rows >= 0) return SR_OK;
+    const sr_agg_desc& d = a->desc;
+    if (!a->compiled) {
+        // no input was ever pushed: GROUP BY -> zero rows; no GROUP BY -> one row of empty states
+        if (d.num_group_keys > 0) {
+            a->out_rows = 0;
+            return SR_OK;
+        }
+        Staged empty;
+        struct Tf {
+            static int32_t f(void* u, int32_t slot) {
+                // expressions over an empty input: take the declared input_type of the first fn that uses the slot
+                const sr_agg_desc* dd = (const sr_agg_desc*)u;
+                for (int q = 0; q < dd->num_fns; q++)
+                    for (int k = 0; k < dd->fns[q].input.num_nodes; k++)
+                        if (dd->fns[q].input.nodes[k].op == SR_EX_COL && dd->fns[q].input.nodes[k].slot_id == slot) return dd->fns[q].input_type;
+                return 0;
+            }
+            static bool n(void*, int32_t) { return true; }
+        };
+        SR_TRY(agg_compile(a, Tf::f, Tf::n, (void*)&a->desc));
+    }
+    const srd::AggDev& h = a->host;
+    {
+        uint64_t ng;
+        int32_t ovf, bad;
+        SR_TRY(agg_read_counters(a, &ng, &ovf, &bad));
+        if (bad) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "a group-by value fell outside the declared group_min/group_max range");
+        if (ovf) return sr_fail(ctx, SR_ERR_STATE, "aggregate hash table overflow (internal)");
+    }
+    const uint64_t total = (!h.dense && h.num_keys > 0) ? h.cap + 1 : h.cap;
+    const int blocks = grid_for((int64_t)total, srd::EMIT_BLOCK);
+    SR_TRY(a->block_counts.reserve(ctx, sizeof(uint32_t) * (size_t)blocks));
+    SR_TRY(a->block_offsets.reserve(ctx, sizeof(uint64_t) * (size_t)blocks));
+    srd::k_agg_count<<<blocks, srd::EMIT_BLOCK, 0, ctx->stream>>>((const srd::AggDev*)a->dev.p, total, a->block_counts.as<uint32_t>());
+    SR_LAUNCH_CHECK(ctx);
+    srd::k_scan_counts<<<1, 1024, 0, ctx->stream>>>(a->block_counts.as<uint32_t>(), blocks, a->block_offsets.as<uint64_t>(), ctx->dscratch);
+    SR_LAUNCH_CHECK(ctx);
+    SR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->dscratch, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t rows = (int64_t)ctx->pinned[0];
+    const int nc = d.num_group_keys + d.num_fns;
+    a->out_bufs.clear();
+    a->out_bufs.resize(2 * (size_t)nc);
+    srd::EmitArgs ea;
+    memset(&ea, 0, sizeof(ea));
+    for (int k = 0; k < nc; k++) {
+        int32_t type;
+        bool nullable;
+        if (k < d.num_group_keys) {
+            type = d.group_types[k];
+            nullable = h.key_nullable[k] != 0;
+        } else {
+            const srd::AggFnDev& fn = h.fns[k - d.num_group_keys];
+            type = fn.result_type;
+            nullable = !(fn.mode == srd::M_COUNT || fn.mode == srd::M_COUNT_STAR);
+        }
+        const int w = srd::type_width(type);
+        SR_TRY(a->out_bufs[2 * k].reserve(ctx, (size_t)std::max<int64_t>(rows, 1) * w));
+        if (nullable) SR_TRY(a->out_bufs[2 * k + 1].reserve(ctx, (size_t)std::max<int64_t>(rows, 1)));
+        srd::EmitCol ec;
+        ec.data = a->out_bufs[2 * k].p;
+        ec.nulls = nullable ? (uint8_t*)a->out_bufs[2 * k + 1].p : nullptr;
+        ec.type = type;
+        ec.width = w;
+        if (k < d.num_group_keys)
+            ea.keys[k] = ec;
+        else
+            ea.res[k - d.num_group_keys] = ec;
+        a->out_types[k] = type;
+        a->out_has_nulls[k] = nullable;
+    }
+    if (rows > 0) {
+        srd::k_agg_emit<<<blocks, srd::EMIT_BLOCK, 0, ctx->stream>>>((const srd::AggDev*)a->dev.p, total, a->block_offsets.as<uint64_t>(), ea);
+        SR_LAUNCH_CHECK(ctx);
+    }
+    a->out_rows = rows;
+    a->cursor = 0;
+    return SR_OK;
+}

@@ -1,0 +1,618 @@
+// sr_join.cuh -- hash join build + probe on the device.
+// Replaces K5-K12 of SURVEY.md section 2b:
+//   JoinKeyHash / calc_bucket_num           be/src/exec/join/join_hash_map_helper.h:35-54,79-84
+//   *JoinHashMap::construct_hash_table      be/src/exec/join/join_hash_map_method.hpp:37-86,133-300,542-674
+//   *JoinHashMap::lookup_init               :87-126,300-370,592-618,676-706
+//   JoinHashMap::_probe_from_ht (+outer/semi/anti) be/src/exec/join/join_hash_map.hpp:718-795,950-1030,1186-1255
+//   _probe_output / _build_output           :163-269
+//   JoinHashTable::append_chunk             be/src/exec/join/join_hash_table.cpp:712-752
+//
+// Device layout (B200-first, not the CPU layout):
+//  * build columns are concatenated in HBM with row 0 reserved as the sentinel (same 1-based
+//    build index convention as the reference, so index pairs are comparable);
+//  * DIRECT / RANGE_DIRECT_MAPPING: first[key - min] (uint32 head row) + next[] chain, built
+//    with one atomicExch per row; plus a 1-bit-per-key bitmap (the RANGE_DIRECT_MAPPING_SET
+//    idea) that the fused fragment kernel keeps in shared memory / L1;
+//  * LINEAR_CHAINED: open addressing over {key(int64), head(uint32)} slots with linear
+//    probing, equal keys chained through next[] (AreKeysInChainIdentical), claimed by
+//    atomicCAS on the key word; the multiplicative JoinKeyHash picks the start slot.
+#pragma once
+
+#include "sr_scan.cuh"
+
+namespace srd {
+
+#define SR_HKEY_EMPTY ((int64_t)0x8000000000000000ll)
+
+struct JoinDev {
+    int32_t method;
+    int32_t has_dup;
+    int64_t min_value, max_value;
+    const uint32_t* first;
+    const uint32_t* next;
+    const unsigned long long* hkeys; // LINEAR_CHAINED: cap + 1 slots (last = key == EMPTY)
+    uint32_t hmask;
+    uint32_t hlog;
+    const uint32_t* bitmap; // range methods: bit (key - min) set when a build row has the key
+};
+
+struct KeyCols {
+    DCol c[SR_MAX_JOIN_KEYS];
+    int32_t n;
+    int32_t pad;
+};
+
+// pack the key columns of one row; returns true when any key column is NULL
+__device__ __forceinline__ bool pack_key(const KeyCols& kc, int64_t row, int64_t& key) {
+    if (kc.n == 1) {
+        key = load_int(kc.c[0].data, kc.c[0].type, row);
+        return kc.c[0].nulls != nullptr && kc.c[0].nulls[row] != 0;
+    }
+    uint64_t k = 0;
+    int shift = 0;
+    bool nul = false;
+#pragma unroll
+    for (int q = 0; q < SR_MAX_JOIN_KEYS; q++) {
+        if (q < kc.n) {
+            const int w = kc.c[q].width;
+            const uint64_t mask = w == 8 ? ~0ull : ((1ull << (8 * w)) - 1);
+            k |= ((uint64_t)load_int(kc.c[q].data, kc.c[q].type, row) & mask) << shift;
+            shift += 8 * w;
+            nul |= kc.c[q].nulls != nullptr && kc.c[q].nulls[row] != 0;
+        }
+    }
+    key = (int64_t)k;
+    return nul;
+}
+
+__device__ __forceinline__ uint32_t hash_slot(int64_t key, uint32_t hlog) {
+    return join_key_hash64((uint64_t)key, hlog);
+}
+
+// head build row of `key` (0 = no match)
+__device__ __forceinline__ uint32_t join_lookup(const JoinDev& j, int64_t key) {
+    if (j.method == SR_JOIN_METHOD_LINEAR_CHAINED) {
+        if (key == SR_HKEY_EMPTY) return __ldg(j.first + j.hmask + 1);
+        uint32_t s = hash_slot(key, j.hlog);
+        while (true) {
+            const int64_t k = (int64_t)__ldg(j.hkeys + s);
+            if (k == key) return __ldg(j.first + s);
+            if (k == SR_HKEY_EMPTY) return 0;
+            s = (s + 1) & j.hmask;
+        }
+    }
+    if (key < j.min_value || key > j.max_value) return 0;
+    return __ldg(j.first + (uint64_t)(key - j.min_value));
+}
+
+// pack build keys (rows 1..n) and reduce min / max / null count
+__global__ void __launch_bounds__(256) k_join_pack_keys(KeyCols kc, int64_t n_plus1, long long* __restrict__ keys, uint8_t* __restrict__ knulls,
+                                                         long long* __restrict__ minmax /* [min, max, nulls] */) {
+    long long mn = 0x7fffffffffffffffll, mx = (long long)0x8000000000000000ll, nn = 0;
+    for (int64_t i = 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_plus1; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t key;
+        const bool nul = pack_key(kc, i, key);
+        keys[i] = key;
+        if (knulls) knulls[i] = nul ? 1 : 0;
+        if (!nul) {
+            mn = min(mn, (long long)key);
+            mx = max(mx, (long long)key);
+        } else {
+            nn++;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(SR_FULL_MASK, mn, o));
+        mx = max(mx, __shfl_xor_sync(SR_FULL_MASK, mx, o));
+        nn += __shfl_xor_sync(SR_FULL_MASK, nn, o);
+    }
+    if (lane_id() == 0) {
+        atomicMin(&minmax[0], mn);
+        atomicMax(&minmax[1], mx);
+        if (nn) atomicAdd((unsigned long long*)&minmax[2], (unsigned long long)nn);
+    }
+}
+
+// K6/K8: next[i] = exchange(first[b], i)  (the reference's `next[i]=first[b]; first[b]=i`)
+__global__ void __launch_bounds__(256) k_join_build_direct(const long long* __restrict__ keys, const uint8_t* __restrict__ knulls, int64_t n_plus1,
+                                                            int64_t min_value, uint32_t* __restrict__ first, uint32_t* __restrict__ next,
+                                                            uint32_t* __restrict__ bitmap, int32_t* __restrict__ has_dup) {
+    for (int64_t i = 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_plus1; i += (int64_t)gridDim.x * blockDim.x) {
+        if (knulls && knulls[i]) continue;
+        const uint64_t b = (uint64_t)(keys[i] - min_value);
+        const uint32_t old = atomicExch(&first[b], (uint32_t)i);
+        next[i] = old;
+        if (old != 0)
+            *has_dup = 1;
+        else
+            atomicOr(&bitmap[b >> 5], 1u << (b & 31));
+    }
+}
+
+// K7 analogue: claim a slot for the key (atomicCAS on the key word), then push the row on the
+// slot's chain.
+__global__ void __launch_bounds__(256) k_join_build_hash(const long long* __restrict__ keys, const uint8_t* __restrict__ knulls, int64_t n_plus1,
+                                                          unsigned long long* __restrict__ hkeys, uint32_t hmask, uint32_t hlog,
+                                                          uint32_t* __restrict__ first, uint32_t* __restrict__ next, int32_t* __restrict__ has_dup) {
+    for (int64_t i = 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_plus1; i += (int64_t)gridDim.x * blockDim.x) {
+        if (knulls && knulls[i]) continue;
+        const int64_t key = keys[i];
+        uint32_t s;
+        if (key == SR_HKEY_EMPTY) {
+            s = hmask + 1;
+        } else {
+            s = hash_slot(key, hlog);
+            while (true) {
+                const unsigned long long old = atomicCAS(&hkeys[s], (unsigned long long)SR_HKEY_EMPTY, (unsigned long long)key);
+                if (old == (unsigned long long)SR_HKEY_EMPTY || old == (unsigned long long)key) break;
+                s = (s + 1) & hmask;
+            }
+        }
+        const uint32_t old = atomicExch(&first[s], (uint32_t)i);
+        next[i] = old;
+        if (old != 0) *has_dup = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fill_u64(unsigned long long* p, int64_t n, unsigned long long v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// number of output rows a probe row produces for the join type, given its chain head
+__device__ __forceinline__ uint32_t probe_row_count(const JoinDev& j, int32_t join_type, uint32_t head) {
+    uint32_t cnt = 0;
+    if (head != 0) {
+        cnt = 1;
+        if (j.has_dup) {
+            uint32_t b = __ldg(j.next + head);
+            while (b != 0) {
+                cnt++;
+                b = __ldg(j.next + b);
+            }
+        }
+    }
+    switch (join_type) {
+    case SR_JOIN_INNER:
+        return cnt;
+    case SR_JOIN_LEFT_OUTER:
+        return cnt ? cnt : 1;
+    case SR_JOIN_LEFT_SEMI:
+        return cnt ? 1 : 0;
+    default:
+        return cnt ? 0 : 1;
+    }
+}
+
+constexpr int PROBE_BLOCK = 256;
+
+// pass 1: heads[row] + per-block output counts
+__global__ void __launch_bounds__(PROBE_BLOCK) k_probe_count(JoinDev j, KeyCols kc, int32_t join_type, int64_t n, uint32_t* __restrict__ heads,
+                                                              uint32_t* __restrict__ block_counts) {
+    __shared__ uint32_t s_cnt[PROBE_BLOCK / 32];
+    const int64_t row = (int64_t)blockIdx.x * PROBE_BLOCK + threadIdx.x;
+    uint32_t cnt = 0;
+    if (row < n) {
+        int64_t key;
+        const bool nul = pack_key(kc, row, key);
+        const uint32_t head = nul ? 0u : join_lookup(j, key);
+        heads[row] = head;
+        cnt = probe_row_count(j, join_type, head);
+    }
+    cnt = warp_sum(cnt);
+    if (lane_id() == 0) s_cnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < PROBE_BLOCK / 32; w++) t += s_cnt[w];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+// pass 2: write (probe_index, build_index) pairs in probe order
+__global__ void __launch_bounds__(PROBE_BLOCK) k_probe_write(JoinDev j, int32_t join_type, int64_t n, const uint32_t* __restrict__ heads,
+                                                              const uint64_t* __restrict__ block_offsets, uint32_t* __restrict__ probe_index,
+                                                              uint32_t* __restrict__ build_index) {
+    __shared__ uint32_t s_scan[PROBE_BLOCK / 32 + 1];
+    const int64_t row = (int64_t)blockIdx.x * PROBE_BLOCK + threadIdx.x;
+    uint32_t head = 0, cnt = 0;
+    if (row < n) {
+        head = heads[row];
+        cnt = probe_row_count(j, join_type, head);
+    }
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan<PROBE_BLOCK>(cnt, s_scan, &tot);
+    if (cnt == 0) return;
+    uint64_t o = block_offsets[blockIdx.x] + ex;
+    if (join_type == SR_JOIN_LEFT_SEMI || join_type == SR_JOIN_LEFT_ANTI || head == 0) {
+        probe_index[o] = (uint32_t)row;
+        build_index[o] = 0;
+        return;
+    }
+    uint32_t b = head;
+    while (b != 0) {
+        probe_index[o] = (uint32_t)row;
+        build_index[o] = b;
+        o++;
+        b = j.has_dup ? __ldg(j.next + b) : 0u;
+    }
+}
+
+// K5 exposed for golden-vector pinning
+__global__ void __launch_bounds__(256) k_join_key_hash(const void* __restrict__ keys, int32_t type, int64_t n, uint32_t log_buckets,
+                                                        uint32_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = load_int(keys, type, i);
+        out[i] = type_width(type) == 8 ? join_key_hash64((uint64_t)v, log_buckets) : join_key_hash32((uint32_t)(int32_t)v, log_buckets);
+    }
+}
+
+} // namespace srd
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct BuildCol {
+    int32_t slot = 0, type = 0, width = 0;
+    bool nullable = false;
+    DevBuf data, nulls;
+};
+
+struct ProberState {
+    Staged staged;
+    DevBuf heads, block_counts, block_offsets, probe_index, build_index;
+    std::vector<DevBuf> out_bufs;
+    int64_t last_count = 0;
+};
+
+struct sr_join {
+    sr_ctx* ctx = nullptr;
+    sr_join_desc desc;
+    std::vector<BuildCol*> cols;
+    int64_t rows = 0;     // build rows (without the sentinel)
+    int64_t capacity = 0; // rows the column buffers can hold (incl. sentinel)
+    bool built = false;
+    int32_t method = SR_JOIN_METHOD_NONE;
+    int32_t has_dup = 0;
+    int64_t min_value = 0, max_value = 0, bucket_size = 0, null_keys = 0;
+    uint32_t hmask = 0, hlog = 0;
+    DevBuf keys, knulls, first, next, hkeys, bitmap, flags;
+    Staged staged_build;
+    std::vector<ProberState*> probers;
+    ~sr_join() {
+        for (auto* c : cols) delete c;
+        for (auto* p : probers) delete p;
+    }
+    srd::JoinDev dev() const {
+        srd::JoinDev d;
+        d.method = method;
+        d.has_dup = has_dup;
+        d.min_value = min_value;
+        d.max_value = max_value;
+        d.first = first.as<uint32_t>();
+        d.next = next.as<uint32_t>();
+        d.hkeys = hkeys.as<unsigned long long>();
+        d.hmask = hmask;
+        d.hlog = hlog;
+        d.bitmap = bitmap.as<uint32_t>();
+        return d;
+    }
+    const BuildCol* find_col(int32_t slot) const {
+        for (auto* c : cols)
+            if (c->slot == slot) return c;
+        return nullptr;
+    }
+};
+
+static int32_t join_validate_desc(sr_ctx* ctx, const sr_join_desc* d) {
+    if (d->num_keys < 1 || d->num_keys > SR_MAX_JOIN_KEYS) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "num_keys %d", d->num_keys);
+    if (d->join_type < SR_JOIN_INNER || d->join_type > SR_JOIN_LEFT_ANTI) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "join type %d", d->join_type);
+    int total = 0;
+    for (int k = 0; k < d->num_keys; k++) {
+        const int w = srd::type_width(d->key_types[k]);
+        if (w == 0 || w > 8 || srd::is_float_class(d->key_types[k])) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "join key type %d", d->key_types[k]);
+        total += w;
+    }
+    if (total > 8) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "packed join key wider than 8 bytes");
+    if (d->num_build_out < 0 || d->num_build_out > SR_MAX_JOIN_OUT || d->num_probe_out < 0 || d->num_probe_out > SR_MAX_JOIN_OUT)
+        return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "output slot count");
+    return SR_OK;
+}
+
+static int32_t join_grow(sr_join* j, int64_t need_rows_incl_sentinel) {
+    sr_ctx* ctx = j->ctx;
+    if (need_rows_incl_sentinel <= j->capacity) return SR_OK;
+    int64_t ncap = std::max<int64_t>(need_rows_incl_sentinel, j->capacity + j->capacity / 2);
+    ncap = std::max<int64_t>(ncap, 1024);
+    for (auto* c : j->cols) {
+        SR_TRY(c->data.reserve(ctx, (size_t)ncap * c->width, (size_t)(j->rows + 1) * c->width));
+        if (c->nullable) SR_TRY(c->nulls.reserve(ctx, (size_t)ncap, (size_t)(j->rows + 1)));
+    }
+    j->capacity = ncap;
+    return SR_OK;
+}
+
+static int32_t join_append(sr_join* j, const sr_chunk_view* chunk) {
+    sr_ctx* ctx = j->ctx;
+    if (j->built) return sr_fail(ctx, SR_ERR_STATE, "append_build after build_finish");
+    const cudaMemcpyKind kind = chunk->mem == SR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (j->cols.empty()) {
+        for (int k = 0; k < chunk->num_cols; k++) {
+            const sr_col_view& c = chunk->cols[k];
+            const int w = srd::type_width(c.type);
+            if (w == 0) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "unknown build column type %d", c.type);
+            auto* bc = new BuildCol();
+            bc->slot = c.slot_id;
+            bc->type = c.type;
+            bc->width = w;
+            j->cols.push_back(bc);
+        }
+        for (int k = 0; k < j->desc.num_keys; k++) {
+            const BuildCol* bc = j->find_col(j->desc.build_key_slots[k]);
+            if (!bc) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "build chunk misses key slot %d", j->desc.build_key_slots[k]);
+            if (bc->width != srd::type_width(j->desc.key_types[k])) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "build key %d width differs from key_types", k);
+        }
+    }
+    const int64_t n = chunk->num_rows;
+    SR_TRY(join_grow(j, j->rows + n + 1));
+    for (auto* bc : j->cols) {
+        const sr_col_view* c = find_col(chunk, bc->slot);
+        if (!c) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "build chunk misses slot %d", bc->slot);
+        if (c->type != bc->type) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "build slot %d changed type", bc->slot);
+        if (j->rows == 0) SR_CUDA(ctx, cudaMemsetAsync(bc->data.p, 0, (size_t)bc->width, ctx->stream)); // sentinel row 0
+        if (n > 0)
+            SR_CUDA(ctx, cudaMemcpyAsync((uint8_t*)bc->data.p + (size_t)(j->rows + 1) * bc->width, c->data, (size_t)n * bc->width, kind, ctx->stream));
+        if (c->nulls && !bc->nullable) {
+            // upgrade to nullable (join_hash_table.cpp:726-742): previous rows are non-null, row 0 NULL
+            bc->nullable = true;
+            SR_TRY(bc->nulls.reserve(ctx, (size_t)j->capacity));
+            SR_CUDA(ctx, cudaMemsetAsync(bc->nulls.p, 0, (size_t)(j->rows + 1), ctx->stream));
+            SR_CUDA(ctx, cudaMemsetAsync(bc->nulls.p, 1, 1, ctx->stream));
+        }
+        if (bc->nullable && n > 0) {
+            if (c->nulls)
+                SR_CUDA(ctx, cudaMemcpyAsync((uint8_t*)bc->nulls.p + (j->rows + 1), c->nulls, (size_t)n, kind, ctx->stream));
+            else
+                SR_CUDA(ctx, cudaMemsetAsync((uint8_t*)bc->nulls.p + (j->rows + 1), 0, (size_t)n, ctx->stream));
+        }
+    }
+    if (chunk->mem == SR_MEM_HOST) SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // caller may free host buffers
+    j->rows += n;
+    return SR_OK;
+}
+
+static int32_t join_finish(sr_join* j) {
+    sr_ctx* ctx = j->ctx;
+    if (j->built) return SR_OK;
+    if (j->rows >= 0xFFFFFFF0ll) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "more than 2^32 build rows");
+    const int64_t n1 = j->rows + 1;
+    if (j->cols.empty()) {
+        // empty build side: no chunk was ever appended
+        j->method = SR_JOIN_METHOD_RANGE_DIRECT_MAPPING;
+        j->min_value = 0;
+        j->max_value = -1;
+        j->bucket_size = 0;
+        SR_TRY(j->first.reserve(ctx, 16));
+        SR_TRY(j->next.reserve(ctx, 16));
+        SR_TRY(j->bitmap.reserve(ctx, 16));
+        SR_CUDA(ctx, cudaMemsetAsync(j->first.p, 0, 16, ctx->stream));
+        SR_CUDA(ctx, cudaMemsetAsync(j->next.p, 0, 16, ctx->stream));
+        SR_CUDA(ctx, cudaMemsetAsync(j->bitmap.p, 0, 16, ctx->stream));
+        j->built = true;
+        return SR_OK;
+    }
+    srd::KeyCols kc;
+    kc.n = j->desc.num_keys;
+    bool any_nullable = false;
+    for (int k = 0; k < kc.n; k++) {
+        const BuildCol* bc = j->find_col(j->desc.build_key_slots[k]);
+        kc.c[k].data = bc->data.p;
+        kc.c[k].nulls = bc->nullable ? (const uint8_t*)bc->nulls.p : nullptr;
+        kc.c[k].type = bc->type;
+        kc.c[k].width = bc->width;
+        any_nullable |= bc->nullable;
+    }
+    SR_TRY(j->keys.reserve(ctx, sizeof(int64_t) * (size_t)n1));
+    if (any_nullable) SR_TRY(j->knulls.reserve(ctx, (size_t)n1));
+    SR_TRY(j->flags.reserve(ctx, 64));
+    long long init[4] = {0x7fffffffffffffffll, (long long)0x8000000000000000ll, 0, 0};
+    SR_CUDA(ctx, cudaMemcpyAsync(j->flags.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    SR_CUDA(ctx, cudaMemsetAsync(j->keys.p, 0, 8, ctx->stream));
+    const int grid = std::min(grid_for(j->rows, 256), ctx->num_sms * 8);
+    srd::k_join_pack_keys<<<grid, 256, 0, ctx->stream>>>(kc, n1, j->keys.as<long long>(), any_nullable ? j->knulls.as<uint8_t>() : nullptr,
+                                                        j->flags.as<long long>());
+    SR_LAUNCH_CHECK(ctx);
+    long long mm[4];
+    SR_CUDA(ctx, cudaMemcpyAsync(mm, j->flags.p, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
+    SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    j->null_keys = mm[2];
+    const int64_t valid = j->rows - j->null_keys;
+    const bool one_key = j->desc.num_keys == 1;
+    const int kw = srd::type_width(j->desc.key_types[0]);
+    // --- method selection (JoinHashMapSelector::_determine_hash_map_method, join_hash_table.cpp:225-350,
+    // with the CPU L2/L3 thresholds replaced by an HBM/L2 budget: a direct table is used while it
+    // stays within 64x the row count or 64 MiB (half of B200's L2)) ---
+    j->method = SR_JOIN_METHOD_LINEAR_CHAINED;
+    if (one_key && kw <= 2) {
+        j->method = SR_JOIN_METHOD_DIRECT_MAPPING;
+        if (j->desc.key_types[0] == SR_TYPE_BOOLEAN) {
+            j->min_value = 0;
+            j->max_value = 1;
+        } else {
+            j->min_value = kw == 1 ? -128 : -32768;
+            j->max_value = kw == 1 ? 127 : 32767;
+        }
+    } else if (one_key && j->desc.enable_range_direct_mapping && valid > 0) {
+        const unsigned __int128 interval = (unsigned __int128)((__int128)mm[1] - (__int128)mm[0]) + 1;
+        const uint64_t budget = std::max<uint64_t>((uint64_t)valid * 64, (64ull << 20) / 4);
+        if (interval < 0xFFFFFFFFull && (uint64_t)interval <= budget) {
+            j->method = SR_JOIN_METHOD_RANGE_DIRECT_MAPPING;
+            j->min_value = mm[0];
+            j->max_value = mm[1];
+        }
+    } else if (one_key && valid == 0) {
+        j->method = SR_JOIN_METHOD_RANGE_DIRECT_MAPPING;
+        j->min_value = 0;
+        j->max_value = -1;
+    }
+    SR_TRY(j->next.reserve(ctx, sizeof(uint32_t) * (size_t)n1));
+    SR_CUDA(ctx, cudaMemsetAsync(j->next.p, 0, sizeof(uint32_t) * (size_t)n1, ctx->stream));
+    int32_t* has_dup_dev = (int32_t*)((long long*)j->flags.p + 3);
+    if (j->method == SR_JOIN_METHOD_LINEAR_CHAINED) {
+        uint64_t cap = 1024;
+        while (cap < (uint64_t)std::max<int64_t>(valid, 1) * 2) cap <<= 1;
+        j->hmask = (uint32_t)(cap - 1);
+        j->hlog = (uint32_t)__builtin_ctzll(cap);
+        j->bucket_size = (int64_t)cap + 1;
+        SR_TRY(j->hkeys.reserve(ctx, sizeof(uint64_t) * (cap + 1)));
+        SR_TRY(j->first.reserve(ctx, sizeof(uint32_t) * (cap + 1)));
+        SR_CUDA(ctx, cudaMemsetAsync(j->first.p, 0, sizeof(uint32_t) * (cap + 1), ctx->stream));
+        srd::k_fill_u64<<<std::min(grid_for((int64_t)cap + 1, 256), ctx->num_sms * 8), 256, 0, ctx->stream>>>(
+                j->hkeys.as<unsigned long long>(), (int64_t)cap + 1, (unsigned long long)SR_HKEY_EMPTY);
+        SR_LAUNCH_CHECK(ctx);
+        SR_TRY(j->bitmap.reserve(ctx, 16));
+        srd::k_join_build_hash<<<grid, 256, 0, ctx->stream>>>(j->keys.as<long long>(), any_nullable ? j->knulls.as<uint8_t>() : nullptr, n1,
+                                                             j->hkeys.as<unsigned long long>(), j->hmask, j->hlog, j->first.as<uint32_t>(),
+                                                             j->next.as<uint32_t>(), has_dup_dev);
+        SR_LAUNCH_CHECK(ctx);
+    } else {
+        const int64_t interval = j->max_value - j->min_value + 1;
+        j->bucket_size = interval;
+        const size_t fbytes = sizeof(uint32_t) * (size_t)std::max<int64_t>(interval, 4);
+        const size_t bbytes = sizeof(uint32_t) * (size_t)((std::max<int64_t>(interval, 1) + 31) / 32 + 4);
+        SR_TRY(j->first.reserve(ctx, fbytes));
+        SR_TRY(j->bitmap.reserve(ctx, bbytes));
+        SR_CUDA(ctx, cudaMemsetAsync(j->first.p, 0, fbytes, ctx->stream));
+        SR_CUDA(ctx, cudaMemsetAsync(j->bitmap.p, 0, bbytes, ctx->stream));
+        if (valid > 0) {
+            srd::k_join_build_direct<<<grid, 256, 0, ctx->stream>>>(j->keys.as<long long>(), any_nullable ? j->knulls.as<uint8_t>() : nullptr, n1,
+                                                                   j->min_value, j->first.as<uint32_t>(), j->next.as<uint32_t>(),
+                                                                   j->bitmap.as<uint32_t>(), has_dup_dev);
+            SR_LAUNCH_CHECK(ctx);
+        }
+    }
+    int32_t hd = 0;
+    SR_CUDA(ctx, cudaMemcpyAsync(&hd, has_dup_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    j->has_dup = hd;
+    j->built = true;
+    return SR_OK;
+}
+
+static int32_t join_key_cols(sr_join* j, const Staged& st, srd::KeyCols* kc) {
+    kc->n = j->desc.num_keys;
+    for (int k = 0; k < kc->n; k++) {
+        const int c = st.find(j->desc.probe_key_slots[k]);
+        if (c < 0) return sr_fail(j->ctx, SR_ERR_INVALID_ARGUMENT, "probe chunk misses key slot %d", j->desc.probe_key_slots[k]);
+        if (st.cols[c].width != srd::type_width(j->desc.key_types[k]) || srd::is_float_class(st.cols[c].type))
+            return sr_fail(j->ctx, SR_ERR_INVALID_ARGUMENT, "probe key %d type differs from key_types", k);
+        kc->c[k] = st.cols[c];
+    }
+    return SR_OK;
+}
+
+static int32_t join_probe(sr_join* j, int32_t prober_id, const sr_chunk_view* probe, sr_chunk_out* out) {
+    sr_ctx* ctx = j->ctx;
+    if (!j->built) return sr_fail(ctx, SR_ERR_STATE, "probe before build_finish");
+    if (prober_id < 0 || prober_id > 4096) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "prober_id %d", prober_id);
+    if (probe->num_rows >= 0xFFFFFFF0ll) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "probe batch of more than 2^32 rows");
+    while ((int)j->probers.size() <= prober_id) j->probers.push_back(new ProberState());
+    ProberState& ps = *j->probers[prober_id];
+    SR_TRY(ps.staged.stage(ctx, probe));
+    srd::KeyCols kc;
+    SR_TRY(join_key_cols(j, ps.staged, &kc));
+    const int64_t n = probe->num_rows;
+    const int blocks = grid_for(n, srd::PROBE_BLOCK);
+    const srd::JoinDev jd = j->dev();
+    int64_t total = 0;
+    if (n > 0) {
+        SR_TRY(ps.heads.reserve(ctx, sizeof(uint32_t) * (size_t)n));
+        SR_TRY(ps.block_counts.reserve(ctx, sizeof(uint32_t) * (size_t)blocks));
+        SR_TRY(ps.block_offsets.reserve(ctx, sizeof(uint64_t) * (size_t)blocks));
+        srd::k_probe_count<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, kc, j->desc.join_type, n, ps.heads.as<uint32_t>(),
+                                                                        ps.block_counts.as<uint32_t>());
+        SR_LAUNCH_CHECK(ctx);
+        srd::k_scan_counts<<<1, 1024, 0, ctx->stream>>>(ps.block_counts.as<uint32_t>(), blocks, ps.block_offsets.as<uint64_t>(), ctx->dscratch);
+        SR_LAUNCH_CHECK(ctx);
+        SR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->dscratch, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        total = (int64_t)ctx->pinned[0];
+    }
+    if (total >= 0xFFFFFFF0ll) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "join output of more than 2^32 rows in one batch; probe in smaller batches");
+    SR_TRY(ps.probe_index.reserve(ctx, sizeof(uint32_t) * (size_t)std::max<int64_t>(total, 1)));
+    SR_TRY(ps.build_index.reserve(ctx, sizeof(uint32_t) * (size_t)std::max<int64_t>(total, 1)));
+    if (total > 0) {
+        srd::k_probe_write<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, j->desc.join_type, n, ps.heads.as<uint32_t>(),
+                                                                        ps.block_offsets.as<uint64_t>(), ps.probe_index.as<uint32_t>(),
+                                                                        ps.build_index.as<uint32_t>());
+        SR_LAUNCH_CHECK(ctx);
+    }
+    ps.last_count = total;
+    // materialise output columns: probe_out_slots (gather by probe_index) then build_out_slots
+    const bool semi = j->desc.join_type == SR_JOIN_LEFT_SEMI || j->desc.join_type == SR_JOIN_LEFT_ANTI;
+    const bool outer = j->desc.join_type == SR_JOIN_LEFT_OUTER;
+    const int np = j->desc.num_probe_out, nb = semi ? 0 : j->desc.num_build_out;
+    if (np + nb > SR_MAX_OUT_COLS) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "too many join output columns");
+    if ((int)ps.out_bufs.size() < 2 * (np + nb)) {
+        std::vector<DevBuf> nbv(2 * (np + nb));
+        for (size_t i = 0; i < ps.out_bufs.size(); i++) std::swap(nbv[i], ps.out_bufs[i]);
+        ps.out_bufs.swap(nbv);
+    }
+    srd::GatherArgs ga_p, ga_b;
+    ga_p.n = 0;
+    ga_b.n = 0;
+    out->num_cols = np + nb;
+    out->mem = SR_MEM_DEVICE;
+    out->num_rows = total;
+    for (int k = 0; k < np + nb; k++) {
+        srd::GatherCol g;
+        int32_t slot, type;
+        if (k < np) {
+            slot = j->desc.probe_out_slots[k];
+            const int c = ps.staged.find(slot);
+            if (c < 0) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "probe chunk misses output slot %d", slot);
+            g.src = ps.staged.cols[c].data;
+            g.src_nulls = ps.staged.cols[c].nulls;
+            g.width = ps.staged.cols[c].width;
+            g.zero_is_null = 0;
+            type = ps.staged.cols[c].type;
+        } else {
+            slot = j->desc.build_out_slots[k - np];
+            const BuildCol* bc = j->find_col(slot);
+            if (!bc) {
+                if (j->cols.empty()) return sr_fail(ctx, SR_ERR_STATE, "build side is empty and its column types are unknown (slot %d)", slot);
+                return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "build chunk misses output slot %d", slot);
+            }
+            g.src = bc->data.p;
+            g.src_nulls = bc->nullable ? (const uint8_t*)bc->nulls.p : nullptr;
+            g.width = bc->width;
+            g.zero_is_null = outer ? 1 : 0;
+            type = bc->type;
+        }
+        const bool need_nulls = g.src_nulls != nullptr || g.zero_is_null;
+        SR_TRY(ps.out_bufs[2 * k].reserve(ctx, (size_t)std::max<int64_t>(total, 1) * g.width));
+        if (need_nulls) SR_TRY(ps.out_bufs[2 * k + 1].reserve(ctx, (size_t)std::max<int64_t>(total, 1)));
+        g.dst = ps.out_bufs[2 * k].p;
+        g.dst_nulls = need_nulls ? (uint8_t*)ps.out_bufs[2 * k + 1].p : nullptr;
+        out->cols[k].data = g.dst;
+        out->cols[k].nulls = g.dst_nulls;
+        out->cols[k].type = type;
+        out->cols[k].slot_id = slot;
+        if (k < np)
+            ga_p.c[ga_p.n++] = g;
+        else
+            ga_b.c[ga_b.n++] = g;
+    }
+    if (total > 0) {
+        const int gx = std::min(grid_for(total, 256), ctx->num_sms * 16);
+        if (ga_p.n > 0) {
+            srd::k_gather<<<dim3(gx, ga_p.n), 256, 0, ctx->stream>>>(ps.probe_index.as<uint32_t>(), total, ga_p);
+            SR_LAUNCH_CHECK(ctx);
+        }
+        if (ga_b.n > 0) {
+            srd::k_gather<<<dim3(gx, ga_b.n), 256, 0, ctx->stream>>>(ps.build_index.as<uint32_t>(), total, ga_b);
+            SR_LAUNCH_CHECK(ctx);
+        }
+    }
+    return SR_OK;
+}

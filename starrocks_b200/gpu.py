@@ -1,0 +1,380 @@
+"""ctypes binding of the product library starrocks_b200/libsr_gpu.so (C-ABI: include/sr_gpu_ops.h).
+
+Used by tests/, bench.py and __graft_entry__.py.  There is no CPU fallback: if the library is
+missing or no CUDA device is visible, every entry point raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsr_gpu.so")
+_LIB = None
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC", "-cudart", "static"]
+
+
+def build(verbose=False):
+    """compile libsr_gpu.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    src = os.path.join(_HERE, "csrc", "sr_gpu.cu")
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, src]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+def _needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    csrc = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(_HERE, "..", "include", "sr_gpu_ops.h")]
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if _needs_build():
+        build()
+    L = C.CDLL(LIB_PATH)
+    i32, i64, u32, vp = C.c_int32, C.c_int64, C.c_uint32, C.c_void_p
+    sig = {
+        "sr_abi_version": (i32, []),
+        "sr_type_width": (i32, [i32]),
+        "sr_ctx_create": (vp, [i32, vp]),
+        "sr_ctx_destroy": (None, [vp]),
+        "sr_ctx_sync": (i32, [vp]),
+        "sr_last_error": (C.c_char_p, [vp]),
+        "sr_ctx_kernel_launches": (i64, [vp]),
+        "sr_ctx_device_bytes": (i64, [vp]),
+        "sr_ctx_stream": (vp, [vp]),
+        "sr_scan_create": (vp, [vp, vp]),
+        "sr_scan_destroy": (None, [vp]),
+        "sr_scan_filter": (i32, [vp, vp, vp]),
+        "sr_scan_evaluate": (i32, [vp, vp, vp, i32]),
+        "sr_join_create": (vp, [vp, vp]),
+        "sr_join_destroy": (None, [vp]),
+        "sr_join_append_build": (i32, [vp, vp]),
+        "sr_join_build_finish": (i32, [vp]),
+        "sr_join_is_build_done": (i32, [vp]),
+        "sr_join_get_info": (i32, [vp, vp]),
+        "sr_join_copy_table": (i32, [vp, vp, vp]),
+        "sr_join_probe": (i32, [vp, i32, vp, vp]),
+        "sr_join_probe_indexes": (i32, [vp, i32, vp, vp]),
+        "sr_join_key_hash": (i32, [vp, vp, i32, i64, u32, vp, i32]),
+        "sr_agg_create": (vp, [vp, vp]),
+        "sr_agg_destroy": (None, [vp]),
+        "sr_agg_push": (i32, [vp, vp]),
+        "sr_agg_sink_finish": (i32, [vp]),
+        "sr_agg_num_groups": (i64, [vp]),
+        "sr_agg_pull": (i32, [vp, i64, i32, vp]),
+        "sr_agg_merge": (i32, [vp, vp]),
+        "sr_agg_reset": (i32, [vp]),
+        "sr_fragment_reset": (i32, [vp]),
+        "sr_fragment_create": (vp, [vp, vp]),
+        "sr_fragment_destroy": (None, [vp]),
+        "sr_fragment_push": (i32, [vp, vp]),
+        "sr_fragment_agg": (vp, [vp]),
+        "sr_fragment_rows_passed": (i64, [vp]),
+        "sr_xchg_create": (vp, [vp, vp]),
+        "sr_xchg_destroy": (None, [vp]),
+        "sr_xchg_partition": (i32, [vp, vp, vp, vp]),
+        "sr_xchg_hash": (i32, [vp, vp, vp, vp, i32]),
+        "sr_gather": (i32, [vp, vp, i32, vp, i64, vp, i32]),
+        "sr_memcpy": (i32, [vp, vp, vp, i64, i32]),
+        "sr_abi_sizeof": (i32, [i32]),
+        "sr_bandwidth_probe": (i32, [vp, vp, i64, vp]),
+        "sr_flush_l2": (i32, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    if L.sr_abi_version() != abi.SR_ABI_VERSION:
+        raise RuntimeError("libsr_gpu.so ABI version mismatch")
+    _LIB = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "sr_abi_version", "sr_type_width", "sr_ctx_create", "sr_ctx_destroy", "sr_ctx_sync", "sr_last_error",
+    "sr_ctx_kernel_launches", "sr_ctx_device_bytes", "sr_ctx_stream", "sr_scan_create", "sr_scan_destroy",
+    "sr_scan_filter", "sr_scan_evaluate", "sr_join_create", "sr_join_destroy", "sr_join_append_build",
+    "sr_join_build_finish", "sr_join_is_build_done", "sr_join_get_info", "sr_join_copy_table", "sr_join_probe",
+    "sr_join_probe_indexes", "sr_join_key_hash", "sr_agg_create", "sr_agg_destroy", "sr_agg_push",
+    "sr_agg_sink_finish", "sr_agg_num_groups", "sr_agg_pull", "sr_agg_merge", "sr_agg_reset", "sr_fragment_reset",
+    "sr_fragment_create",
+    "sr_fragment_destroy", "sr_fragment_push", "sr_fragment_agg", "sr_fragment_rows_passed", "sr_xchg_create",
+    "sr_xchg_destroy", "sr_xchg_partition", "sr_xchg_hash", "sr_gather", "sr_memcpy", "sr_abi_sizeof", "sr_bandwidth_probe", "sr_flush_l2",
+]
+
+
+class GpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sr_gpu error {code}: {msg}")
+        self.code = code
+
+
+class Context:
+    def __init__(self, device=0, stream=None):
+        self.h = lib().sr_ctx_create(device, stream)
+        if not self.h:
+            raise GpuError(abi.SR_ERR_NO_DEVICE, lib().sr_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().sr_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        # handles created on this context must be destroyed first; tests call close() explicitly
+        pass
+
+    def check(self, rc):
+        if rc is not None and rc < 0:
+            raise GpuError(rc, lib().sr_last_error(self.h).decode())
+        return rc
+
+    def sync(self):
+        self.check(lib().sr_ctx_sync(self.h))
+
+    @property
+    def launches(self):
+        return lib().sr_ctx_kernel_launches(self.h)
+
+    @property
+    def device_bytes(self):
+        return lib().sr_ctx_device_bytes(self.h)
+
+    @property
+    def stream(self):
+        return lib().sr_ctx_stream(self.h)
+
+    def flush_l2(self):
+        self.check(lib().sr_flush_l2(self.h))
+
+    def bandwidth_probe(self, dev_ptr, nbytes):
+        out = C.c_uint64(0)
+        self.check(lib().sr_bandwidth_probe(self.h, dev_ptr, nbytes, C.byref(out)))
+        return out.value
+
+    def join_key_hash(self, keys, log_buckets):
+        """host numpy int32/int64 keys -> uint32 buckets (K5)"""
+        out = np.zeros(len(keys), dtype=np.uint32)
+        typ = abi.NUMPY_TYPE[keys.dtype]
+        self.check(lib().sr_join_key_hash(self.h, keys.ctypes.data, typ, len(keys), log_buckets, out.ctypes.data,
+                                          abi.MEM_HOST))
+        return out
+
+
+def _copy_dev_to_host(ctx, ptr, nbytes):
+    """D2H copy of a raw device pointer through the library's own plumbing call."""
+    buf = np.empty(nbytes, dtype=np.uint8)
+    if nbytes:
+        ctx.check(lib().sr_memcpy(ctx.h, buf.ctypes.data, ptr, nbytes, 1))
+    return buf
+
+
+def chunk_out_to_host(ctx, out):
+    """sr_chunk_out -> list of (slot, type, data ndarray, nulls ndarray|None).  Device buffers are copied."""
+    ctx.sync()
+    res = []
+    n = out.num_rows
+    for k in range(out.num_cols):
+        c = out.cols[k]
+        w = abi.TYPE_WIDTH[c.type]
+        dt = abi.TYPE_NUMPY.get(c.type)
+        if out.mem == abi.MEM_DEVICE:
+            raw = _copy_dev_to_host(ctx, c.data, n * w) if n else np.empty(0, dtype=np.uint8)
+            nul = (_copy_dev_to_host(ctx, c.nulls, n) if n else np.empty(0, dtype=np.uint8)) if c.nulls else None
+        else:
+            raw = np.ctypeslib.as_array(C.cast(c.data, C.POINTER(C.c_uint8)), shape=(n * w,)).copy() if n else \
+                np.empty(0, dtype=np.uint8)
+            nul = np.ctypeslib.as_array(C.cast(c.nulls, C.POINTER(C.c_uint8)), shape=(n,)).copy() \
+                if (c.nulls and n) else (np.empty(0, dtype=np.uint8) if c.nulls else None)
+        data = raw.view(dt) if dt is not None else raw.view(np.dtype((np.void, 16)))
+        res.append((c.slot_id, c.type, data, nul))
+    return res
+
+
+class Scan:
+    def __init__(self, ctx, scan_desc):
+        self.ctx = ctx
+        self.desc = scan_desc
+        self.h = lib().sr_scan_create(ctx.h, scan_desc.ref())
+        if not self.h:
+            ctx.check(-1)
+
+    def close(self):
+        if self.h:
+            lib().sr_scan_destroy(self.h)
+            self.h = None
+
+    def evaluate(self, chunk):
+        sel = np.zeros(chunk.num_rows, dtype=np.uint8)
+        self.ctx.check(lib().sr_scan_evaluate(self.h, chunk.ref(), sel.ctypes.data, abi.MEM_HOST))
+        return sel
+
+    def filter(self, chunk):
+        out = abi.sr_chunk_out()
+        self.ctx.check(lib().sr_scan_filter(self.h, chunk.ref(), C.byref(out)))
+        return out
+
+
+class Join:
+    def __init__(self, ctx, desc):
+        self.ctx = ctx
+        self.desc = desc
+        self.h = lib().sr_join_create(ctx.h, C.byref(desc))
+        if not self.h:
+            ctx.check(-1)
+
+    def close(self):
+        if self.h:
+            lib().sr_join_destroy(self.h)
+            self.h = None
+
+    def append_build(self, chunk):
+        self.ctx.check(lib().sr_join_append_build(self.h, chunk.ref()))
+
+    def build_finish(self):
+        self.ctx.check(lib().sr_join_build_finish(self.h))
+
+    def info(self):
+        inf = abi.sr_join_info()
+        self.ctx.check(lib().sr_join_get_info(self.h, C.byref(inf)))
+        return inf
+
+    def copy_table(self):
+        inf = self.info()
+        first = np.zeros(max(inf.bucket_size, 1), dtype=np.uint32)
+        nxt = np.zeros(inf.build_rows + 1, dtype=np.uint32)
+        self.ctx.check(lib().sr_join_copy_table(self.h, first.ctypes.data, nxt.ctypes.data))
+        return first[:inf.bucket_size], nxt
+
+    def probe(self, chunk, prober_id=0):
+        out = abi.sr_chunk_out()
+        self.ctx.check(lib().sr_join_probe(self.h, prober_id, chunk.ref(), C.byref(out)))
+        return out
+
+    def probe_indexes(self, n, prober_id=0):
+        pi, bi = C.c_void_p(), C.c_void_p()
+        self.ctx.check(lib().sr_join_probe_indexes(self.h, prober_id, C.byref(pi), C.byref(bi)))
+        self.ctx.sync()
+        if n == 0:
+            return np.empty(0, dtype=np.uint32), np.empty(0, dtype=np.uint32)
+        return (_copy_dev_to_host(self.ctx, pi.value, 4 * n).view(np.uint32),
+                _copy_dev_to_host(self.ctx, bi.value, 4 * n).view(np.uint32))
+
+
+class Agg:
+    def __init__(self, ctx, desc=None, handle=None):
+        self.ctx = ctx
+        self.desc = desc
+        self.owned = handle is None
+        self.h = handle if handle is not None else lib().sr_agg_create(ctx.h, C.byref(desc))
+        if not self.h:
+            ctx.check(-1)
+
+    def close(self):
+        if self.h and self.owned:
+            lib().sr_agg_destroy(self.h)
+        self.h = None
+
+    def push(self, chunk):
+        self.ctx.check(lib().sr_agg_push(self.h, chunk.ref()))
+
+    def finish(self):
+        self.ctx.check(lib().sr_agg_sink_finish(self.h))
+
+    def merge(self, other):
+        self.ctx.check(lib().sr_agg_merge(self.h, other.h))
+
+    def reset(self):
+        self.ctx.check(lib().sr_agg_reset(self.h))
+
+    @property
+    def num_groups(self):
+        return self.ctx.check(lib().sr_agg_num_groups(self.h))
+
+    def pull(self, max_rows=1 << 62, mem=abi.MEM_HOST):
+        out = abi.sr_chunk_out()
+        self.ctx.check(lib().sr_agg_pull(self.h, max_rows, mem, C.byref(out)))
+        return out
+
+    def result(self):
+        """finish + pull everything to the host -> list of (slot, type, data, nulls)"""
+        self.finish()
+        out = self.pull()
+        return chunk_out_to_host(self.ctx, out)
+
+
+class Fragment:
+    def __init__(self, ctx, scan_desc, joins, agg_desc):
+        """joins: list of (Join, probe_key_slot, [payload build slots])"""
+        self.ctx = ctx
+        self._keep = (scan_desc, joins, agg_desc)
+        d = abi.sr_fragment_desc()
+        d.scan = scan_desc.desc
+        d.num_joins = len(joins)
+        for k, (j, slot, payload) in enumerate(joins):
+            d.joins[k].join = j.h
+            d.joins[k].probe_key_slot = slot
+            d.joins[k].num_payload = len(payload)
+            for q, s in enumerate(payload):
+                d.joins[k].payload_build_slots[q] = s
+        d.agg = agg_desc
+        self.desc = d
+        self.h = lib().sr_fragment_create(ctx.h, C.byref(d))
+        if not self.h:
+            ctx.check(-1)
+        self.agg = Agg(ctx, agg_desc, handle=lib().sr_fragment_agg(self.h))
+
+    def close(self):
+        if self.h:
+            lib().sr_fragment_destroy(self.h)
+            self.h = None
+
+    def push(self, chunk):
+        self.ctx.check(lib().sr_fragment_push(self.h, chunk.ref()))
+
+    def reset(self):
+        self.ctx.check(lib().sr_fragment_reset(self.h))
+
+    @property
+    def rows_passed(self):
+        return self.ctx.check(lib().sr_fragment_rows_passed(self.h))
+
+
+class Xchg:
+    def __init__(self, ctx, part_desc):
+        self.ctx = ctx
+        self.desc = part_desc
+        self.h = lib().sr_xchg_create(ctx.h, C.byref(part_desc))
+        if not self.h:
+            ctx.check(-1)
+
+    def close(self):
+        if self.h:
+            lib().sr_xchg_destroy(self.h)
+            self.h = None
+
+    def hash(self, chunk):
+        n = chunk.num_rows
+        hv = np.zeros(n, dtype=np.uint32)
+        ch = np.zeros(n, dtype=np.uint32)
+        self.ctx.check(lib().sr_xchg_hash(self.h, chunk.ref(), hv.ctypes.data, ch.ctypes.data, abi.MEM_HOST))
+        return hv, ch
+
+    def partition(self, chunk):
+        out = abi.sr_chunk_out()
+        offs = np.zeros(self.desc.num_channels + 1, dtype=np.int64)
+        self.ctx.check(lib().sr_xchg_partition(self.h, chunk.ref(), C.byref(out), offs.ctypes.data))
+        return out, offs

@@ -1,0 +1,540 @@
+"""GPU parity tests: the CUDA path (through the C-ABI of libsr_gpu.so) against the CPU oracle on
+the same seeded inputs.  Bit-exact for integer / index / COUNT / SUM(int64) / decimal work; 1e-6
+relative for double SUM / AVG (the tolerance BASELINE.json states).  Join and group-by outputs
+are compared as sorted multisets (row order is an implementation artefact in the reference too).
+"""
+import numpy as np
+import pytest
+
+from starrocks_b200 import abi, ssb
+from starrocks_b200.abi import Chunk
+from tests.helpers import assert_rows_equal, gpu_rows, oracle_rows, rand_nulls, rows_sorted, col_to_py
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [0, 1, 31, 255, 256, 1025, 4096, 100003]
+
+
+# ---------------------------------------------------------------------------------------------
+# K5 JoinKeyHash on the device, pinned by the reference's golden vectors
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,stride,expect", [
+    (np.int32, 3, (0, 11)), (np.int32, 7, (0, 14)), (np.int32, 1, (4, 6)),
+    (np.int64, 3, (3, 7)), (np.int64, 7, (4, 7)), (np.int64, 1, (4, 6)),
+])
+def test_join_key_hash_golden(gpu, ctx, dtype, stride, expect):
+    # be/test/exec/join_hash_map_test.cpp:924-1009
+    nb = 1 << 16
+    keys = np.arange(0, nb * stride * 5, stride, dtype=dtype)
+    buckets = ctx.join_key_hash(keys, 16)
+    counts = np.bincount(buckets, minlength=nb)
+    assert (counts.min(), counts.max()) == expect
+    assert ctx.join_key_hash(np.array([1, 2, 3, 4], dtype=np.int32), 2).tolist() == [2, 0, 3, 1]
+
+
+# ---------------------------------------------------------------------------------------------
+# scan predicates + order-preserving compaction (K1-K4)
+# ---------------------------------------------------------------------------------------------
+def _scan_inputs(n, seed=7):
+    rng = np.random.default_rng(seed)
+    return Chunk([
+        (0, rng.integers(-50, 50, n, dtype=np.int32), None),
+        (1, rng.integers(-10**12, 10**12, n, dtype=np.int64), rand_nulls(rng, n)),
+        (2, rng.normal(0, 10, n), rand_nulls(rng, n, 0.05)),
+        (3, rng.integers(-100, 100, n).astype(np.int16), None),
+        (4, rng.integers(0, 2, n).astype(np.uint8), None, abi.TYPE_BOOLEAN),
+        (5, rng.random(n).astype(np.float32), None),
+    ])
+
+
+SCAN_CASES = [
+    dict(preds=[abi.make_pred(0, abi.PRED_BETWEEN, -10, 20)]),
+    dict(preds=[abi.make_pred(0, abi.PRED_GE, 0), abi.make_pred(1, abi.PRED_LT, 0), abi.make_pred(3, abi.PRED_NE, 7)]),
+    dict(preds=[abi.make_pred(2, abi.PRED_GT, 1.5, is_double=True), abi.make_pred(5, abi.PRED_LE, 0.5, is_double=True)]),
+    dict(preds=[abi.make_pred(0, abi.PRED_IN, in_list=[1, 2, 3, -7]), abi.make_pred(1, abi.PRED_IS_NOT_NULL)]),
+    dict(preds=[abi.make_pred(1, abi.PRED_IS_NULL)]),
+    dict(preds=[abi.make_pred(3, abi.PRED_NOT_IN, in_list=[0, 1])]),
+    dict(preds=[abi.make_pred(0, abi.PRED_EQ, 1000)]),                      # nothing passes
+    dict(preds=[]),                                                         # everything passes
+    dict(exprs=[abi.make_expr([("col", 0), ("i", 2), "*", ("col", 3), "+", ("i", 10), ">"])]),
+    dict(exprs=[abi.make_expr([("col", 1), ("i", 0), ">", ("col", 2), ("d", 0.0), "<", "or"])]),   # 3-valued OR
+    dict(exprs=[abi.make_expr([("col", 1), "isnull", "not", ("col", 0), ("col", 3), "<=", "and"])]),
+    dict(preds=[abi.make_pred(4, abi.PRED_EQ, 1)], exprs=[abi.make_expr([("col", 2), ("col", 5), "/", ("d", 3.0), ">"])]),
+]
+
+
+@pytest.mark.parametrize("case", range(len(SCAN_CASES)))
+@pytest.mark.parametrize("n", SIZES)
+def test_scan_filter_parity(gpu, ctx, oracle, case, n):
+    c = SCAN_CASES[case]
+    chunk = _scan_inputs(n)
+    sd = abi.ScanDesc(preds=c.get("preds", []), filter_exprs=c.get("exprs", []), out_slots=[0, 1, 2, 3, 4, 5])
+    scan = gpu.Scan(ctx, sd)
+    try:
+        sel = scan.evaluate(chunk)
+        assert np.array_equal(sel, oracle.scan_evaluate(sd, chunk))
+        out = gpu.chunk_out_to_host(ctx, scan.filter(chunk))
+        rows, exp = oracle.scan_filter(sd, chunk)
+        assert len(out) == 6
+        for slot, typ, data, nulls in out:
+            assert len(data) == rows
+            assert np.array_equal(data.view(np.uint8), exp[slot][0].view(np.uint8)), f"slot {slot}"  # bit-exact, in order
+            if exp[slot][1] is not None:
+                assert np.array_equal(nulls, exp[slot][1])
+    finally:
+        scan.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# hash join build + probe (K6-K12)
+# ---------------------------------------------------------------------------------------------
+def _join_pairs(gpu, ctx, oracle, desc, build_chunks, probe_chunk, expect_method=None):
+    gj = gpu.Join(ctx, desc)
+    oj = oracle.Join(desc)
+    try:
+        for bc in build_chunks:
+            gj.append_build(bc)
+            oj.append_build(bc)
+        gj.build_finish()
+        oj.build()
+        if expect_method is not None:
+            assert gj.info().method == expect_method
+        out = gj.probe(probe_chunk)
+        n = out.num_rows
+        gpi, gbi = gj.probe_indexes(n)
+        opi, obi = oj.probe_all(probe_chunk, cap=max(1024, 4 * probe_chunk.num_rows + 16))
+        assert sorted(zip(gpi.tolist(), gbi.tolist())) == sorted(zip(opi.tolist(), obi.tolist()))
+        assert np.all(np.diff(gpi.astype(np.int64)) >= 0)  # probe order kept
+        gout = gpu.chunk_out_to_host(ctx, out)
+        oout = oj.output(probe_chunk, opi, obi)
+        assert [s for s, _, _, _ in gout] == [s for s, _, _ in oout]
+        grow = rows_sorted([col_to_py(t, d, nl) for _, t, d, nl in gout])
+        orow = rows_sorted([col_to_py(desc_type(desc, oj, probe_chunk, s), d, nl) for s, d, nl in oout])
+        assert grow == orow
+        return gj.info(), n
+    finally:
+        gj.close()
+
+
+def desc_type(desc, oj, probe_chunk, slot):
+    if slot in probe_chunk.slots:
+        return probe_chunk.types[probe_chunk.slots.index(slot)]
+    return oj.build_types[slot]
+
+
+JOIN_TYPES = [abi.JOIN_INNER, abi.JOIN_LEFT_OUTER, abi.JOIN_LEFT_SEMI, abi.JOIN_LEFT_ANTI]
+
+
+@pytest.mark.parametrize("join_type", JOIN_TYPES)
+@pytest.mark.parametrize("kind", ["range_unique", "range_dup_nulls", "sparse_i64", "tiny_i8", "small_i16", "two_keys"])
+def test_join_parity(gpu, ctx, oracle, join_type, kind):
+    rng = np.random.default_rng(11)
+    nb, npr = 5000, 20011
+    expect = None
+    if kind == "range_unique":
+        bkey = rng.permutation(np.arange(100, 100 + nb, dtype=np.int32))
+        pkey = rng.integers(0, 100 + 2 * nb, npr, dtype=np.int32)
+        bn = pn = None
+        ktypes, expect = [abi.TYPE_INT], abi.JOIN_METHOD_RANGE_DIRECT_MAPPING
+    elif kind == "range_dup_nulls":
+        bkey = rng.integers(0, 800, nb, dtype=np.int32)
+        pkey = rng.integers(-50, 900, npr, dtype=np.int32)
+        bn, pn = rand_nulls(rng, nb), rand_nulls(rng, npr)
+        ktypes, expect = [abi.TYPE_INT], abi.JOIN_METHOD_RANGE_DIRECT_MAPPING
+    elif kind == "sparse_i64":
+        pool = rng.integers(-2**62, 2**62, 3000, dtype=np.int64)
+        pool[0] = np.iinfo(np.int64).min  # the table's EMPTY sentinel value is a legal key
+        bkey = pool[rng.integers(0, 3000, nb)]
+        pkey = np.concatenate([pool[rng.integers(0, 3000, npr // 2)], rng.integers(-2**62, 2**62, npr - npr // 2, dtype=np.int64)])
+        bn, pn = None, rand_nulls(rng, npr, 0.02)
+        ktypes, expect = [abi.TYPE_BIGINT], abi.JOIN_METHOD_LINEAR_CHAINED
+    elif kind == "tiny_i8":
+        bkey = rng.integers(-128, 128, 300).astype(np.int8)
+        pkey = rng.integers(-128, 128, npr).astype(np.int8)
+        bn = pn = None
+        nb = 300
+        ktypes, expect = [abi.TYPE_TINYINT], abi.JOIN_METHOD_DIRECT_MAPPING
+    elif kind == "small_i16":
+        bkey = rng.integers(-3000, 3000, nb).astype(np.int16)
+        pkey = rng.integers(-4000, 4000, npr).astype(np.int16)
+        bn, pn = rand_nulls(rng, nb, 0.05), None
+        ktypes, expect = [abi.TYPE_SMALLINT], abi.JOIN_METHOD_DIRECT_MAPPING
+    else:  # two int32 keys packed into one 8-byte key (SERIALIZED_FIXED_SIZE_BIGINT)
+        bkey = rng.integers(0, 60, nb, dtype=np.int32)
+        pkey = rng.integers(0, 70, npr, dtype=np.int32)
+        bn = pn = None
+        ktypes, expect = [abi.TYPE_INT, abi.TYPE_INT], abi.JOIN_METHOD_LINEAR_CHAINED
+    bpay = rng.integers(0, 10**6, nb, dtype=np.int32)
+    bpay2 = rng.normal(size=nb)
+    ppay = rng.integers(0, 10**9, npr, dtype=np.int64)
+    if kind == "two_keys":
+        bkey2 = rng.integers(-5, 5, nb, dtype=np.int32)
+        pkey2 = rng.integers(-6, 6, npr, dtype=np.int32)
+        d = abi.make_join_desc(join_type, [10, 13], [0, 3], ktypes, build_out=[11, 12], probe_out=[0, 1])
+        half = nb // 2
+        builds = [Chunk([(10, bkey[:half].copy(), None), (13, bkey2[:half].copy(), None), (11, bpay[:half].copy(), None), (12, bpay2[:half].copy(), None)]),
+                  Chunk([(10, bkey[half:].copy(), None), (13, bkey2[half:].copy(), None), (11, bpay[half:].copy(), None), (12, bpay2[half:].copy(), None)])]
+        probe = Chunk([(0, pkey, None), (3, pkey2, None), (1, ppay, None)])
+    else:
+        d = abi.make_join_desc(join_type, [10], [0], ktypes, build_out=[11, 12, 10], probe_out=[0, 1])
+        half = nb // 3
+        builds = [Chunk([(10, bkey[:half].copy(), None if bn is None else bn[:half].copy()), (11, bpay[:half].copy(), None), (12, bpay2[:half].copy(), None)]),
+                  Chunk([(10, bkey[half:].copy(), None if bn is None else bn[half:].copy()), (11, bpay[half:].copy(), None), (12, bpay2[half:].copy(), None)])]
+        probe = Chunk([(0, pkey, pn), (1, ppay, None)])
+    _join_pairs(gpu, ctx, oracle, d, builds, probe, expect_method=expect)
+
+
+def test_join_one_key_golden(gpu, ctx):
+    # be/test/exec/join_hash_map_test.cpp:2042-2088 OneKeyJoinHashTable through the CUDA path
+    d = abi.make_join_desc(abi.JOIN_INNER, [3], [0], [abi.TYPE_INT], build_out=[3, 4, 5], probe_out=[0, 1, 2])
+    j = gpu.Join(ctx, d)
+    try:
+        j.append_build(Chunk([(3 + k, np.arange(10 * k, 10 * k + 10, dtype=np.int32), None) for k in range(3)]))
+        j.build_finish()
+        out = gpu.chunk_out_to_host(ctx, j.probe(Chunk([(k, np.arange(1 + 10 * k, 6 + 10 * k, dtype=np.int32), None) for k in range(3)])))
+        assert len(out) == 6
+        for k, (slot, _, data, _) in enumerate(out):
+            assert slot == k and data.tolist() == list(range(1 + 10 * (k % 3), 6 + 10 * (k % 3)))
+        first, nxt = j.copy_table()
+        assert first.tolist() == list(range(1, 11)) and not nxt.any()   # first[key - min] = build row (1-based)
+    finally:
+        j.close()
+
+
+def test_join_sql_golden_counts(gpu, ctx):
+    # test/sql/test_join/R/test_join_range_direct_mapping (see tests/test_oracle_golden.py)
+    from tests.test_oracle_golden import sql_golden_t1
+    idx, null13, big, null14 = sql_golden_t1()
+    for keyc, nulls, ktype, jt, expect in ((idx, None, abi.TYPE_INT, abi.JOIN_INNER, 1280000),
+                                           (idx, null13, abi.TYPE_INT, abi.JOIN_INNER, 98461),
+                                           (big, null14, abi.TYPE_BIGINT, abi.JOIN_LEFT_OUTER, 1280000)):
+        j = gpu.Join(ctx, abi.make_join_desc(jt, [1], [0], [ktype], build_out=[1], probe_out=[0]))
+        try:
+            j.append_build(Chunk([(1, keyc, nulls)]))
+            j.build_finish()
+            out = j.probe(Chunk([(0, keyc, nulls)]))
+            assert out.num_rows == expect
+            if jt == abi.JOIN_LEFT_OUTER:
+                _, bi = j.probe_indexes(out.num_rows)
+                assert int((bi != 0).sum()) == 91428
+        finally:
+            j.close()
+    w1 = np.concatenate([idx, idx])
+    j = gpu.Join(ctx, abi.make_join_desc(abi.JOIN_INNER, [1], [0], [abi.TYPE_INT], build_out=[], probe_out=[0]))
+    try:
+        j.append_build(Chunk([(1, w1, None)]))
+        j.build_finish()
+        assert j.info().has_duplicates == 1
+        assert j.probe(Chunk([(0, w1, None)])).num_rows == 5120000
+    finally:
+        j.close()
+
+
+def test_join_empty_sides(gpu, ctx):
+    d = abi.make_join_desc(abi.JOIN_INNER, [1], [0], [abi.TYPE_INT], build_out=[1], probe_out=[0])
+    j = gpu.Join(ctx, d)
+    try:
+        j.append_build(Chunk([(1, np.empty(0, dtype=np.int32), None)]))
+        j.build_finish()
+        assert j.probe(Chunk([(0, np.arange(10, dtype=np.int32), None)])).num_rows == 0
+        assert j.probe(Chunk([(0, np.empty(0, dtype=np.int32), None)])).num_rows == 0
+    finally:
+        j.close()
+    j = gpu.Join(ctx, abi.make_join_desc(abi.JOIN_LEFT_ANTI, [1], [0], [abi.TYPE_INT], build_out=[], probe_out=[0]))
+    try:
+        j.append_build(Chunk([(1, np.empty(0, dtype=np.int32), None)]))
+        j.build_finish()
+        assert j.probe(Chunk([(0, np.arange(10, dtype=np.int32), None)])).num_rows == 10
+    finally:
+        j.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# hash aggregate (K13-K17)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("typ,np_t", [(abi.TYPE_SMALLINT, np.int16), (abi.TYPE_INT, np.int32), (abi.TYPE_BIGINT, np.int64),
+                                      (abi.TYPE_FLOAT, np.float32), (abi.TYPE_DOUBLE, np.float64)])
+def test_agg_sum_golden(gpu, ctx, typ, np_t):
+    # be/test/exprs/agg/aggregate_test.cpp:61-83 test_sum: 524076 / 2499500 / merged 3023576
+    col1 = np.array(list(range(1024)) + [100, 200], dtype=np_t)
+    col2 = np.arange(2000, 3000, dtype=np_t)
+    d = abi.make_agg_desc(fns=[(abi.AGG_SUM, typ, 10, [("col", 0)])])
+    a1, a2 = gpu.Agg(ctx, d), gpu.Agg(ctx, d)
+    try:
+        a1.push(Chunk([(0, col1, None)]))
+        a2.push(Chunk([(0, col2, None)]))
+        a2.merge(a1)
+        assert a1.result()[0][2][0] == 524076
+        assert a2.result()[0][2][0] == 3023576
+    finally:
+        a1.close()
+        a2.close()
+
+
+def _agg_case(name, n, rng):
+    k1 = rng.integers(0, 7, n, dtype=np.int32)
+    k2 = rng.integers(-3, 4, n).astype(np.int16)
+    k3 = rng.integers(-10**9, 10**9, n, dtype=np.int64)
+    v32 = rng.integers(-10**6, 10**6, n, dtype=np.int32)
+    v64 = rng.integers(-10**15, 10**15, n, dtype=np.int64)
+    vd = rng.normal(100, 50, n)
+    vf = rng.random(n).astype(np.float32)
+    dec = rng.integers(-2**62, 2**62, n, dtype=np.int64)
+    cols = [(0, k1, rand_nulls(rng, n, 0.05) if "nullkey" in name else None), (1, k2, None), (2, k3, None),
+            (3, v32, rand_nulls(rng, n, 0.2) if "nullval" in name else None), (4, v64, None), (5, vd, None), (6, vf, None),
+            (7, dec, None, abi.TYPE_DECIMAL64)]
+    fns = [(abi.AGG_SUM, abi.TYPE_INT, 20, [("col", 3)]), (abi.AGG_COUNT, abi.TYPE_INT, 21, [("col", 3)]),
+           (abi.AGG_COUNT_STAR, abi.TYPE_INT, 22, None), (abi.AGG_AVG, abi.TYPE_INT, 23, [("col", 3)]),
+           (abi.AGG_MIN, abi.TYPE_BIGINT, 24, [("col", 4)]), (abi.AGG_MAX, abi.TYPE_INT, 25, [("col", 3)]),
+           (abi.AGG_SUM, abi.TYPE_DOUBLE, 26, [("col", 5)]), (abi.AGG_SUM, abi.TYPE_DECIMAL64, 27, [("col", 7)])]
+    fns2 = [(abi.AGG_SUM, abi.TYPE_BIGINT, 30, [("col", 3), ("col", 4), "*", ("i", 3), "+"]),
+            (abi.AGG_MIN, abi.TYPE_DOUBLE, 31, [("col", 5)]), (abi.AGG_MAX, abi.TYPE_FLOAT, 32, [("col", 6)]),
+            (abi.AGG_AVG, abi.TYPE_DOUBLE, 33, [("col", 5), ("col", 6), "*"])]
+    if name.startswith("nogroup"):
+        d = abi.make_agg_desc(fns=fns if "a" in name.split("_")[1] else fns2)
+        fl = (3, 6) if "a" in name.split("_")[1] else (1, 3)
+    elif name.startswith("dense"):
+        d = abi.make_agg_desc([0, 1], [abi.TYPE_INT, abi.TYPE_SMALLINT], fns=fns if "_a" in name else fns2,
+                              ranges=[(0, 6), (-3, 3)], group_nullable=[1 if "nullkey" in name else 0, 0])
+        fl = (2 + 3, 2 + 6) if "_a" in name else (2 + 1, 2 + 3)
+    elif name.startswith("hash2"):
+        d = abi.make_agg_desc([0, 1], [abi.TYPE_INT, abi.TYPE_SMALLINT], fns=fns, group_nullable=[1 if "nullkey" in name else 0, 0])
+        fl = (2 + 3, 2 + 6)
+    else:  # hash on a high-cardinality int64 key
+        d = abi.make_agg_desc([2], [abi.TYPE_BIGINT], fns=fns2)
+        fl = (1 + 1, 1 + 3)
+    return d, cols, fl
+
+
+@pytest.mark.parametrize("name", ["nogroup_a", "nogroup_b", "nogroup_a_nullval", "dense_a", "dense_b", "dense_a_nullkey_nullval",
+                                  "hash2_a", "hash2_a_nullkey_nullval", "hash1_b"])
+@pytest.mark.parametrize("n", [0, 1, 1000, 70001])
+def test_agg_parity(gpu, ctx, oracle, name, n):
+    rng = np.random.default_rng(5)
+    d, cols, fl = _agg_case(name, n, rng)
+    # push in two chunks to exercise state carry-over
+    cut = n // 3
+    def sub(lo, hi):
+        return Chunk([(c[0], c[1][lo:hi].copy(), None if c[2] is None else c[2][lo:hi].copy()) + tuple(c[3:]) for c in cols])
+    ga, oa = gpu.Agg(ctx, d), oracle.Agg(d)
+    try:
+        for lo, hi in ((0, cut), (cut, n)):
+            ch = sub(lo, hi)
+            ga.push(ch)
+            oa.push(ch)
+        assert_rows_equal(gpu_rows(ga.result()), oracle_rows(oa), float_cols=fl)
+    finally:
+        ga.close()
+
+
+def test_agg_hash_growth_two_pass(gpu, ctx, oracle):
+    # 3 M rows, ~2.6 M distinct int64 keys: forces the find/insert + update two-pass path and a table growth
+    rng = np.random.default_rng(9)
+    n = 3_000_000
+    keys = rng.integers(0, 20_000_000, n, dtype=np.int64)
+    vals = rng.integers(0, 1000, n, dtype=np.int64)
+    d = abi.make_agg_desc([0], [abi.TYPE_BIGINT], fns=[(abi.AGG_SUM, abi.TYPE_BIGINT, 10, [("col", 1)]),
+                                                        (abi.AGG_COUNT_STAR, abi.TYPE_BIGINT, 11, None)])
+    ch = Chunk([(0, keys, None), (1, vals, None)])
+    ga, oa = gpu.Agg(ctx, d), oracle.Agg(d)
+    try:
+        ga.push(ch)
+        ga.push(ch)
+        oa.push(ch)
+        oa.push(ch)
+        res = ga.result()
+        order = np.argsort(res[0][2], kind="stable")
+        oo = oa.output()
+        oorder = np.argsort(oo[0][1], kind="stable")
+        assert len(res[0][2]) == len(oo[0][1]) == len(np.unique(keys))
+        for k in range(3):
+            assert np.array_equal(res[k][2][order], oo[k][1][oorder])
+    finally:
+        ga.close()
+
+
+def test_agg_pull_paging_and_device_output(gpu, ctx):
+    keys = np.arange(10000, dtype=np.int32)
+    d = abi.make_agg_desc([0], [abi.TYPE_INT], fns=[(abi.AGG_SUM, abi.TYPE_INT, 10, [("col", 0)])], ranges=[(0, 9999)])
+    a = gpu.Agg(ctx, d)
+    try:
+        a.push(Chunk([(0, keys, None)]))
+        a.finish()
+        assert a.num_groups == 10000
+        seen = []
+        while True:
+            out = a.pull(max_rows=4096, mem=abi.MEM_DEVICE)   # chunk_size paging like AggregateBlockingSourceOperator
+            if out.num_rows == 0:
+                break
+            got = gpu.chunk_out_to_host(ctx, out)
+            assert got[0][2].tolist() == got[1][2].tolist()
+            seen += got[0][2].tolist()
+        assert seen == list(range(10000))
+    finally:
+        a.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# fused fragment: SSB Q4.1 and Q1.1 shapes against the chunk-at-a-time oracle pipeline
+# ---------------------------------------------------------------------------------------------
+def _run_q41(gpu, ctx, oracle, sf, n, pushes=1):
+    dims = ssb.gen_dims(sf)
+    lo = ssb.gen_lineorder(sf, n=n)
+    gjoins, gkeep = ssb.build_dims(gpu, dims, ssb.dim_plans_q41(), ctx=ctx)
+    ojoins, okeep = ssb.build_dims(oracle, dims, ssb.dim_plans_q41())
+    agg_desc = ssb.q41_agg_desc()
+    frag = gpu.Fragment(ctx, abi.ScanDesc(), gjoins, agg_desc)
+    try:
+        step = (n + pushes - 1) // pushes
+        for p in range(pushes):
+            part = {k: v[p * step:(p + 1) * step].copy() for k, v in lo.items()}
+            frag.push(ssb.fact_chunk(part, ssb.Q41_FACT_COLS))
+        got = gpu_rows(frag.agg.result())
+        passed = frag.rows_passed
+        ores, opassed = oracle.fragment_run(abi.ScanDesc(), ojoins, agg_desc, ssb.fact_chunk(lo, ssb.Q41_FACT_COLS), num_threads=4)
+        assert passed == opassed
+        assert_rows_equal(got, oracle_rows(ores))
+        return got, passed
+    finally:
+        frag.close()
+        for j, _, _ in gjoins:
+            j.close()
+        for item in gkeep:
+            item[0].close()
+
+
+def test_fragment_q41_parity(gpu, ctx, oracle):
+    got, passed = _run_q41(gpu, ctx, oracle, sf=0.1, n=600_000)
+    assert len(got) == 35 and passed > 0          # 7 years x 5 AMERICA nations
+    assert sum(1 for _ in got) == 35
+
+
+def test_fragment_q41_multi_push_and_ragged(gpu, ctx, oracle):
+    _run_q41(gpu, ctx, oracle, sf=0.05, n=300_007, pushes=3)
+    _run_q41(gpu, ctx, oracle, sf=0.01, n=5, pushes=1)
+
+
+def test_fragment_q11_parity(gpu, ctx, oracle):
+    lo = ssb.gen_lineorder(1, n=1_000_003)
+    sd = abi.ScanDesc(preds=ssb.q11_scan_preds())
+    agg_desc = ssb.q11_agg_desc()
+    frag = gpu.Fragment(ctx, sd, [], agg_desc)
+    try:
+        ch = ssb.fact_chunk(lo, ssb.Q11_FACT_COLS)
+        frag.push(ch)
+        got = gpu_rows(frag.agg.result())
+        ores, opassed = oracle.fragment_run(sd, [], agg_desc, ch, num_threads=2)
+        assert frag.rows_passed == opassed
+        assert_rows_equal(got, oracle_rows(ores))
+        m = ((lo["lo_orderdate"] >= 19930101) & (lo["lo_orderdate"] <= 19931231) & (lo["lo_discount"] >= 1) &
+             (lo["lo_discount"] <= 3) & (lo["lo_quantity"] < 25))
+        assert got[0][0] == int((lo["lo_extendedprice"][m].astype(np.int64) * lo["lo_discount"][m]).sum())
+    finally:
+        frag.close()
+
+
+def test_fragment_hash_group_and_semi_join(gpu, ctx, oracle):
+    # group-by without declared ranges -> hash table path inside the fused kernel; a LEFT SEMI join with a
+    # sparse (hash) build side; a generic filter expression on the fact table
+    rng = np.random.default_rng(3)
+    n = 400_000
+    fact = Chunk([(0, rng.integers(0, 5000, n, dtype=np.int32), None), (1, rng.integers(0, 10**9, n, dtype=np.int64), rand_nulls(rng, n, 0.01)),
+                  (2, rng.integers(0, 100, n, dtype=np.int32), None), (3, rng.integers(1, 1000, n, dtype=np.int32), None)])
+    dim1 = Chunk([(10, np.arange(0, 5000, 2, dtype=np.int32), None), (11, rng.integers(0, 1000, 2500, dtype=np.int32), None)])
+    dim2 = Chunk([(20, rng.integers(0, 10**9, 300_000, dtype=np.int64), None)])
+    d1 = abi.make_join_desc(abi.JOIN_INNER, [10], [0], [abi.TYPE_INT], build_out=[11])
+    d2 = abi.make_join_desc(abi.JOIN_LEFT_SEMI, [20], [1], [abi.TYPE_BIGINT])
+    sd = abi.ScanDesc(filter_exprs=[abi.make_expr([("col", 2), ("col", 3), "+", ("i", 50), ">"])])
+    agg_desc = abi.make_agg_desc([11, 2], [abi.TYPE_INT, abi.TYPE_INT],
+                                 fns=[(abi.AGG_SUM, abi.TYPE_BIGINT, 30, [("col", 3), ("col", 11), "*"]), (abi.AGG_COUNT_STAR, 0, 31, None),
+                                      (abi.AGG_MAX, abi.TYPE_BIGINT, 32, [("col", 1)])])
+    gj1, gj2 = gpu.Join(ctx, d1), gpu.Join(ctx, d2)
+    oj1, oj2 = oracle.Join(d1), oracle.Join(d2)
+    frag = None
+    try:
+        for j, ch in ((gj1, dim1), (gj2, dim2), (oj1, dim1), (oj2, dim2)):
+            j.append_build(ch)
+        gj1.build_finish()
+        gj2.build_finish()
+        oj1.build()
+        oj2.build()
+        assert gj2.info().method == abi.JOIN_METHOD_LINEAR_CHAINED
+        frag = gpu.Fragment(ctx, sd, [(gj1, 0, [11]), (gj2, 1, [])], agg_desc)
+        frag.push(fact)
+        got = gpu_rows(frag.agg.result())
+        ores, opassed = oracle.fragment_run(sd, [(oj1, 0, [11]), (oj2, 1, [])], agg_desc, fact, num_threads=3)
+        assert frag.rows_passed == opassed
+        assert_rows_equal(got, oracle_rows(ores))
+    finally:
+        if frag:
+            frag.close()
+        gj1.close()
+        gj2.close()
+
+
+def test_fragment_rejects_duplicate_build_keys(gpu, ctx):
+    d = abi.make_join_desc(abi.JOIN_INNER, [10], [0], [abi.TYPE_INT])
+    j = gpu.Join(ctx, d)
+    try:
+        j.append_build(Chunk([(10, np.array([1, 1, 2], dtype=np.int32), None)]))
+        j.build_finish()
+        with pytest.raises(gpu.GpuError) as ei:
+            gpu.Fragment(ctx, abi.ScanDesc(), [(j, 0, [])], abi.make_agg_desc(fns=[(abi.AGG_COUNT_STAR, 0, 1, None)]))
+        assert ei.value.code == abi.SR_ERR_NOT_SUPPORTED    # caller must take the per-operator GPU path; no CPU fallback
+    finally:
+        j.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# exchange partitioning (K18)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hash_fn,reduce_op", [(abi.HASH_FNV, abi.REDUCE_MULHI), (abi.HASH_CRC32, abi.REDUCE_MODULO)])
+@pytest.mark.parametrize("nch", [1, 8, 37])
+@pytest.mark.parametrize("n", [0, 1, 1023, 50_001])
+def test_xchg_partition_parity(gpu, ctx, oracle, hash_fn, reduce_op, nch, n):
+    rng = np.random.default_rng(21)
+    chunk = Chunk([(0, rng.integers(-10**6, 10**6, n, dtype=np.int32), rand_nulls(rng, n, 0.05)),
+                   (1, rng.integers(-10**15, 10**15, n, dtype=np.int64), None), (2, rng.normal(size=n), None)])
+    d = abi.make_part_desc([0, 1], nch, hash_fn=hash_fn, reduce_op=reduce_op)
+    x = gpu.Xchg(ctx, d)
+    try:
+        ohv, och, ori, ost = oracle.hash_partition(d, chunk)
+        hv, ch = x.hash(chunk)
+        assert np.array_equal(hv, ohv) and np.array_equal(ch, och)
+        out, offs = x.partition(chunk)
+        assert offs.tolist() == ost.tolist()
+        got = gpu.chunk_out_to_host(ctx, out)
+        for k, (slot, typ, data, nulls) in enumerate(got):
+            src = chunk._keep[k][0]
+            assert np.array_equal(data.view(np.uint8), src[ori].view(np.uint8))      # stable: same row order as the reference's counting sort
+        assert np.array_equal(got[0][3], chunk._keep[0][1][ori])
+    finally:
+        x.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# loud failures (no silent fallback)
+# ---------------------------------------------------------------------------------------------
+def test_errors_are_loud(gpu, ctx):
+    with pytest.raises(gpu.GpuError):
+        gpu.Join(ctx, abi.make_join_desc(abi.JOIN_INNER, [1], [0], [abi.TYPE_DOUBLE]))
+    j = gpu.Join(ctx, abi.make_join_desc(abi.JOIN_INNER, [1], [0], [abi.TYPE_INT]))
+    try:
+        with pytest.raises(gpu.GpuError) as ei:
+            j.probe(Chunk([(0, np.arange(4, dtype=np.int32), None)]))
+        assert ei.value.code == abi.SR_ERR_STATE
+    finally:
+        j.close()
+    a = gpu.Agg(ctx, abi.make_agg_desc([0], [abi.TYPE_INT], fns=[(abi.AGG_COUNT_STAR, 0, 1, None)], ranges=[(0, 3)]))
+    try:
+        a.push(Chunk([(0, np.array([0, 1, 9], dtype=np.int32), None)]))   # 9 is outside the declared range
+        with pytest.raises(gpu.GpuError):
+            a.result()
+    finally:
+        a.close()
+    s = gpu.Scan(ctx, abi.ScanDesc(preds=[abi.make_pred(5, abi.PRED_EQ, 1)], out_slots=[0]))
+    try:
+        with pytest.raises(gpu.GpuError):
+            s.filter(Chunk([(0, np.arange(4, dtype=np.int32), None)]))   # slot 5 does not exist
+    finally:
+        s.close()
