@@ -400,7 +400,7 @@ def run_gpu(args):
                        "fact_rows_per_gpu": n, "global_fact_rows": n * world, "dims": {k: int(v) for k, v in sz.items() if k != "lineorder"},
                        "parallelism": f"dp{world}: fact sharded, dimensions replicated (broadcast join), partial aggregates gathered over NCCL",
                        "l2": "inputs (14.4 GB/GPU) >> 126 MB L2, no flush needed", "late_materialization": True,
-                       "join_order_sampled": [int(x) for x in getattr(frag, "order", [])] or None,
+                       "fragment_plan": frag.plan(),
                        "rows_reaching_aggregate_per_gpu": int(rows_passed), "build_ms": build_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"),

@@ -128,6 +128,9 @@ int32_t sr_ctx_sync(sr_ctx* ctx);
 /* last error message recorded on this context (never NULL). With ctx == NULL: the message
  * of the last failed create call on this thread. */
 const char* sr_last_error(sr_ctx* ctx);
+/* sr_status of the last failure recorded on this context -- needed after a *_create call
+ * returned NULL (the status cannot travel in the return value there). */
+int32_t sr_last_error_code(sr_ctx* ctx);
 int32_t sr_abi_version(void);
 /* number of kernels this library has launched on the context since creation
  * (bench.py reports it as gpu_launches). */
@@ -432,6 +435,19 @@ int32_t sr_fragment_push(sr_fragment* frag, const sr_chunk_view* fact);
 /* the aggregate the fragment feeds (owned by the fragment): finish / pull / merge through
  * the sr_agg_* calls. */
 sr_agg* sr_fragment_agg(sr_fragment* frag);
+/* the plan the fragment chose on its first batch: probe order (indexes into desc->joins), the
+ * pass rate each join measured on the sample, shared memory per CTA and the persistent grid. */
+typedef struct sr_fragment_plan {
+    int32_t num_joins;
+    int32_t order[SR_MAX_FRAG_JOINS];
+    int32_t bitmap_in_smem[SR_MAX_FRAG_JOINS]; /* per probe position */
+    double pass_rate[SR_MAX_FRAG_JOINS];       /* per desc->joins index */
+    int32_t smem_bytes;
+    int32_t grid;
+    int32_t block;
+    int32_t agg_in_smem;
+} sr_fragment_plan;
+int32_t sr_fragment_get_plan(sr_fragment* frag, sr_fragment_plan* plan);
 /* reset_state for the whole fragment: clears its aggregate and the rows_passed counter. */
 int32_t sr_fragment_reset(sr_fragment* frag);
 /* rows that survived scan predicates and all joins so far (synchronises). */

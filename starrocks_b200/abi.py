@@ -146,6 +146,12 @@ class sr_fragment_desc(C.Structure):
                 ("joins", sr_frag_join * SR_MAX_FRAG_JOINS), ("agg", sr_agg_desc)]
 
 
+class sr_fragment_plan(C.Structure):
+    _fields_ = [("num_joins", C.c_int32), ("order", C.c_int32 * SR_MAX_FRAG_JOINS),
+                ("bitmap_in_smem", C.c_int32 * SR_MAX_FRAG_JOINS), ("pass_rate", C.c_double * SR_MAX_FRAG_JOINS),
+                ("smem_bytes", C.c_int32), ("grid", C.c_int32), ("block", C.c_int32), ("agg_in_smem", C.c_int32)]
+
+
 class sr_part_desc(C.Structure):
     _fields_ = [("hash_fn", C.c_int32), ("reduce_op", C.c_int32), ("num_channels", C.c_int32),
                 ("num_part_slots", C.c_int32), ("part_slots", C.c_int32 * SR_MAX_PART_KEYS)]

@@ -319,7 +319,7 @@ constexpr int AGG_BLOCK = 256;
 //  SMEM: dense table accumulated in shared memory.  slots_out (optional): pass-1-only mode
 //  (find slots, no update); slots_in (optional): pass-2 mode (slots precomputed).
 template <bool SMEM>
-__global__ void __launch_bounds__(AGG_BLOCK) k_agg_push(const AggDev* __restrict__ ad, VTab vt, int64_t n, long long* __restrict__ slots_out,
+__global__ void __launch_bounds__(AGG_BLOCK) k_agg_push(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, int64_t n, long long* __restrict__ slots_out,
                                                          const long long* __restrict__ slots_in) {
     extern __shared__ long long s_acc[];
     const AggDev& a = *ad;
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(AGG_BLOCK) k_agg_push(const AggDev* __restrict
 }
 
 // no GROUP BY: warp-reduce additive functions before touching memory (update_batch_single_state)
-__global__ void __launch_bounds__(AGG_BLOCK) k_agg_push_single(const AggDev* __restrict__ ad, VTab vt, int64_t n) {
+__global__ void __launch_bounds__(AGG_BLOCK) k_agg_push_single(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, int64_t n) {
     const AggDev& a = *ad;
     long long cnt = 0;
     long long acc[SR_MAX_AGG_FNS];

@@ -8,210 +8,29 @@
 //   AggregateBlockingSinkOperator::push_chunk               aggregate/aggregate_blocking_sink_operator.cpp:101-138
 //
 // B200 design (HBM-bound integer/gather work, no tensor cores):
-//  * persistent CTAs (grid = SMs x resident CTAs), each thread owns 4 consecutive rows so the
-//    first-touched column of a tile is one 128-bit ld.global.nc.L1::no_allocate per thread;
-//  * late materialisation: a column is only loaded for rows still alive, so DRAM sectors of
-//    later columns are skipped when all 8 rows of a 32-byte sector are already filtered out;
-//  * every range-mapped join is first tested against its 1-bit-per-key bitmap; the bitmaps of
-//    the earliest (most selective) joins are copied into shared memory once per CTA, later
-//    ones are read through L1/L2 (they stay resident: SSB dimensions are a few hundred KB);
-//  * the build row index (first[]) and payload columns are only fetched for rows that survive
-//    all joins; the group-by / SUM update goes to shared-memory accumulators when the table is
-//    small, flushed once per CTA;
-//  * join order: measured pass rates on a sample of the first batch (adaptive), most selective
-//    first -- inner joins commute and the result is order independent.
+//  * persistent CTAs (grid = SMs x resident CTAs).  The main loop streams the scan-predicate
+//    columns and the FIRST join's key column: each thread owns groups of 4 consecutive rows, so a
+//    tile column is one 128-bit ld.global.nc.L1::no_allocate per thread and group;
+//  * selection-vector cascade: rows that survive stage k are appended (warp ballot + popc) to a
+//    per-warp queue in shared memory; as soon as a queue holds 32 rows the warp runs stage k+1
+//    for 32 rows at once (one row per lane).  Later stages therefore always execute with full
+//    warps, their column loads are issued for 32 rows together, and the dependent-load chain of
+//    a tile is one DRAM round trip instead of one per join;
+//  * late materialisation: a column is only loaded for rows still alive, so DRAM sectors of later
+//    columns are skipped when all 8 rows of a 32-byte sector were filtered out;
+//  * every range-mapped join is tested against its 1-bit-per-key bitmap; the bitmaps of the
+//    earliest joins are copied into shared memory once per CTA, the others are read through
+//    L1/L2 (SSB dimension bitmaps are 25-375 KB and stay L2 resident);
+//  * the build row index (first[]) and payload columns are only fetched for rows that survive all
+//    joins; the group-by / SUM update of the final queue goes to shared-memory accumulators when
+//    the table is small, flushed once per CTA;
+//  * join order: pass rates measured on a sample of the first batch (adaptive), most selective
+//    first, smaller table first on a tie -- inner joins commute, the result is order independent.
 #pragma once
 
 #include "sr_agg.cuh"
 
-namespace srd {
-
-struct FragJoinDev {
-    JoinDev j;
-    int32_t key_value_id;
-    int32_t smem_off; // word offset of the bitmap copy in dynamic shared memory, -1 = global
-    int32_t bitmap_words;
-    int32_t use_bitmap; // range-mapped table: test the bitmap; otherwise probe the hash table
-    int32_t need_head;  // a payload column of this join is read downstream
-    int32_t pad;
-};
-
-struct FragDev {
-    int32_t num_preds, num_exprs, num_joins, pad;
-    CPred preds[8];
-    CExpr exprs[4];
-    FragJoinDev joins[SR_MAX_FRAG_JOINS];
-    unsigned long long* rows_passed;
-};
-
-constexpr int FRAG_BLOCK = 512;
-constexpr int FRAG_ROWS = 4;
-constexpr int FRAG_TILE = FRAG_BLOCK * FRAG_ROWS;
-
-struct FragLoader {
-    const VTab& vt;
-    int64_t row;
-    uint32_t bidx[SR_MAX_FRAG_JOINS];
-    __device__ __forceinline__ bool load(int id, int64_t& bits) const {
-        const VDesc& d = vt.v[id];
-        if (d.src < 0) {
-            const bool nul = d.nulls != nullptr && d.nulls[row] != 0;
-            bits = is_float_class(d.type) ? __double_as_longlong(load_double(d.data, d.type, row)) : load_int(d.data, d.type, row);
-            return nul;
-        }
-        const int64_t r = bidx[d.src];
-        const bool nul = d.nulls != nullptr && d.nulls[r] != 0;
-        if (is_float_class(d.type))
-            bits = __double_as_longlong(d.type == SR_TYPE_FLOAT ? (double)__ldg((const float*)d.data + r) : __ldg((const double*)d.data + r));
-        else
-            bits = load_int_cached(d.data, d.type, r);
-        return nul;
-    }
-};
-
-// load one fact value for each alive row of the thread's 4-row group
-__device__ __forceinline__ void load_rows4(const VDesc& d, int64_t row0, uint32_t alive, int64_t vals[FRAG_ROWS], uint32_t& nullmask) {
-    nullmask = 0;
-    const int w = type_width(d.type);
-    if (w == 4 && alive == 0xF && !is_float_class(d.type) && (((uintptr_t)d.data) & 15) == 0) {
-        const int4 v = ldg_stream_v4((const int32_t*)d.data + row0); // row0 % 4 == 0 and cudaMalloc alignment -> 16B aligned
-        vals[0] = v.x;
-        vals[1] = v.y;
-        vals[2] = v.z;
-        vals[3] = v.w;
-    } else {
-#pragma unroll
-        for (int r = 0; r < FRAG_ROWS; r++) {
-            if (alive & (1u << r)) {
-                vals[r] = is_float_class(d.type) ? __double_as_longlong(load_double(d.data, d.type, row0 + r)) : load_int(d.data, d.type, row0 + r);
-            }
-        }
-    }
-    if (d.nulls) {
-#pragma unroll
-        for (int r = 0; r < FRAG_ROWS; r++)
-            if ((alive & (1u << r)) && d.nulls[row0 + r]) nullmask |= 1u << r;
-    }
-}
-
-__device__ __forceinline__ bool frag_join_hit(const FragJoinDev& fj, const uint32_t* smem, int64_t key) {
-    if (fj.use_bitmap) {
-        if (key < fj.j.min_value || key > fj.j.max_value) return false;
-        const uint64_t idx = (uint64_t)(key - fj.j.min_value);
-        const uint32_t word = fj.smem_off >= 0 ? smem[fj.smem_off + (idx >> 5)] : __ldg(fj.j.bitmap + (idx >> 5));
-        return (word >> (idx & 31)) & 1u;
-    }
-    return join_lookup(fj.j, key) != 0;
-}
-
-template <bool SMEM_AGG>
-__global__ void __launch_bounds__(FRAG_BLOCK) k_fragment(const FragDev* __restrict__ fdp, const AggDev* __restrict__ adp, VTab vt, int64_t n,
-                                                          int32_t agg_smem_word_off) {
-    extern __shared__ __align__(16) uint32_t smem[];
-    const FragDev& fd = *fdp;
-    const AggDev& ad = *adp;
-    // stage the bitmaps of the leading joins in shared memory
-    for (int j = 0; j < fd.num_joins; j++) {
-        const FragJoinDev& fj = fd.joins[j];
-        if (fj.smem_off >= 0)
-            for (int w = threadIdx.x; w < fj.bitmap_words; w += blockDim.x) smem[fj.smem_off + w] = fj.j.bitmap[w];
-    }
-    AccPtrs acc;
-    if (SMEM_AGG) {
-        acc_ptrs_smem(ad, (long long*)(smem + agg_smem_word_off), acc);
-        acc_smem_init(ad, acc);
-    } else {
-        acc_ptrs_global(ad, acc);
-    }
-    __syncthreads();
-
-    unsigned long long passed = 0;
-    const int64_t num_tiles = (n + FRAG_TILE - 1) / FRAG_TILE;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int64_t row0 = tile * FRAG_TILE + (int64_t)threadIdx.x * FRAG_ROWS;
-        uint32_t alive = 0;
-#pragma unroll
-        for (int r = 0; r < FRAG_ROWS; r++)
-            if (row0 + r < n) alive |= 1u << r;
-        int64_t vals[FRAG_ROWS];
-        uint32_t nullmask;
-        // ---- scan conjuncts (ColumnPredicate form) ----
-#pragma unroll 1
-        for (int p = 0; p < fd.num_preds && alive; p++) {
-            const CPred& pr = fd.preds[p];
-            load_rows4(vt.v[pr.value_id], row0, alive, vals, nullmask);
-#pragma unroll
-            for (int r = 0; r < FRAG_ROWS; r++)
-                if ((alive & (1u << r)) && !eval_pred(pr, vals[r], (nullmask >> r) & 1u)) alive &= ~(1u << r);
-        }
-        // ---- generic boolean conjuncts ----
-#pragma unroll 1
-        for (int e = 0; e < fd.num_exprs && alive; e++) {
-#pragma unroll 1
-            for (int r = 0; r < FRAG_ROWS; r++) {
-                if (alive & (1u << r)) {
-                    ChunkLoader ld{vt, row0 + r};
-                    int64_t bits;
-                    const bool nul = eval_expr(fd.exprs[e], ld, bits);
-                    if (nul || bits == 0) alive &= ~(1u << r);
-                }
-            }
-        }
-        // ---- join probes, most selective first ----
-#pragma unroll 1
-        for (int j = 0; j < fd.num_joins && alive; j++) {
-            const FragJoinDev& fj = fd.joins[j];
-            load_rows4(vt.v[fj.key_value_id], row0, alive, vals, nullmask);
-            alive &= ~nullmask; // NULL keys never match (join_hash_table.cpp:166-170)
-#pragma unroll
-            for (int r = 0; r < FRAG_ROWS; r++)
-                if ((alive & (1u << r)) && !frag_join_hit(fj, smem, vals[r])) alive &= ~(1u << r);
-        }
-        // ---- survivors: build row indexes, group slot, aggregate update ----
-        if (alive) {
-#pragma unroll 1
-            for (int r = 0; r < FRAG_ROWS; r++) {
-                if (!(alive & (1u << r))) continue;
-                FragLoader ld{vt, row0 + r, {0, 0, 0, 0, 0, 0}};
-                for (int j = 0; j < fd.num_joins; j++) {
-                    const FragJoinDev& fj = fd.joins[j];
-                    if (fj.need_head) {
-                        int64_t key;
-                        ld.load(fj.key_value_id, key);
-                        ld.bidx[j] = join_lookup(fj.j, key);
-                    }
-                }
-                const long long slot = agg_find_slot(ad, ld);
-                if (slot >= 0) agg_apply_row(ad, acc, slot, ld);
-                passed++;
-            }
-        }
-    }
-    if (SMEM_AGG) {
-        __syncthreads();
-        acc_smem_flush(ad, acc);
-    }
-    passed = warp_sum(passed);
-    if (lane_id() == 0 && passed) atomicAdd(fd.rows_passed, passed);
-}
-
-// adaptive join ordering: independent pass counts of each join on a sample of rows
-__global__ void __launch_bounds__(256) k_frag_sample(const FragDev* __restrict__ fdp, VTab vt, int64_t n, unsigned long long* __restrict__ counts) {
-    const FragDev& fd = *fdp;
-    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
-        ChunkLoader ld{vt, row};
-        for (int j = 0; j < fd.num_joins; j++) {
-            const FragJoinDev& fj = fd.joins[j];
-            int64_t key;
-            const bool nul = ld.load(fj.key_value_id, key);
-            const bool hit = !nul && join_lookup(fj.j, key) != 0;
-            const uint32_t m = __ballot_sync(__activemask(), hit);
-            if (hit && (m & lanemask_lt()) == 0) atomicAdd(&counts[j], (unsigned long long)__popc(m));
-        }
-    }
-}
-
-} // namespace srd
+#include "sr_frag_kernel.cuh"
 
 // ---------------------------------------------------------------------------------------
 // host side
@@ -224,15 +43,14 @@ struct sr_fragment {
     sr_frag_join joins[SR_MAX_FRAG_JOINS];
     sr_agg* agg = nullptr;
     bool compiled = false;
-    VReg reg;          // fact + payload values
-    int num_fact_values = 0;
-    std::vector<int32_t> value_src;       // per value: -1 fact, j = payload of (ordered) join j
+    VReg reg; // fact + payload values
+    std::vector<int32_t> value_src;         // per value: -1 fact, j = payload of (ordered) join j
     std::vector<const BuildCol*> value_col; // payload column for src >= 0
     srd::FragDev host;
     DevBuf dev, counters;
     Staged staged;
     size_t smem_bytes = 0;
-    int32_t agg_smem_word_off = 0;
+    int32_t queue_word_off = 0;
     bool smem_agg = false;
     int grid = 0;
     int order[SR_MAX_FRAG_JOINS];
@@ -328,8 +146,8 @@ static int32_t frag_compile(sr_fragment* f) {
     }
     // aggregate (its expressions may reference fact slots and payload slots)
     SR_TRY(agg_compile(f->agg, frag_slot_type, frag_slot_nullable, &tc));
-    // the fragment and its aggregate must share one value table: rebuild the aggregate's
-    // value ids on top of the fragment registry
+    // the fragment and its aggregate share one value table: rebuild the aggregate's value ids on top
+    // of the fragment registry
     {
         VReg merged = f->reg;
         std::vector<int> remap(f->agg->reg.slots.size());
@@ -388,8 +206,11 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
     for (int j = 0; j < f->num_joins; j++) f->pass_rate[j] = sample > 0 ? (double)counts[j] / (double)sample : 1.0;
     std::vector<int> ord(f->num_joins);
     for (int j = 0; j < f->num_joins; j++) ord[j] = j;
+    // most selective first; pass rates within 15 % of each other count as a tie -> smaller table first
+    // (the first join sees every row: its bitmap should fit shared memory)
     std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
-        if (f->pass_rate[a] != f->pass_rate[b]) return f->pass_rate[a] < f->pass_rate[b];
+        const double pa = f->pass_rate[a], pb = f->pass_rate[b];
+        if (std::abs(pa - pb) > 0.15 * std::max(pa, pb)) return pa < pb;
         return h.joins[a].bitmap_words < h.joins[b].bitmap_words;
     });
     srd::FragJoinDev reordered[SR_MAX_FRAG_JOINS];
@@ -402,30 +223,33 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
     for (int q = 0; q < f->num_joins; q++) h.joins[q] = reordered[q];
     for (size_t k = 0; k < f->value_src.size(); k++)
         if (f->value_src[k] >= 0) f->value_src[k] = inv[f->value_src[k]];
-    // shared memory: aggregate accumulators first (8-byte aligned), then bitmaps greedily in probe order
+    // stream the second join's key together with the first when most of its 64-byte DRAM bursts would
+    // be touched anyway: 1 - (1 - p)^16 >= 0.74 for p >= 0.08
+    h.eager1 = (f->num_joins >= 2 && f->pass_rate[ord[0]] >= 0.08) ? 1 : 0;
+    // dynamic shared memory: [aggregate accumulators | bitmaps | per-warp queues]
     size_t words = 0;
     f->smem_agg = f->agg->smem_bytes > 0;
-    f->agg_smem_word_off = 0;
-    if (f->smem_agg) words += f->agg->smem_bytes / 4;
-    const size_t budget_words = (96 * 1024) / 4; // keeps >= 2 CTAs of 512 threads resident per SM
+    if (f->smem_agg) words += (f->agg->smem_bytes + 15) / 16 * 4;
+    const size_t budget_words = (96 * 1024) / 4; // keeps 2 CTAs of 512 threads resident per SM
+    const size_t queue_words = (size_t)srd::FRAG_WARPS * srd::FRAG_WARP_QWORDS;
     for (int q = 0; q < f->num_joins; q++) {
         srd::FragJoinDev& fj = h.joins[q];
         fj.smem_off = -1;
-        if (fj.use_bitmap && words + (size_t)fj.bitmap_words <= budget_words) {
+        if (fj.use_bitmap && words + (size_t)fj.bitmap_words + queue_words <= budget_words) {
             fj.smem_off = (int32_t)words;
             words += (size_t)fj.bitmap_words;
             words = (words + 3) & ~(size_t)3;
-        } else {
-            break; // later joins see few rows; their bitmaps stay in L1/L2
         }
     }
+    f->queue_word_off = (int32_t)words;
+    words += queue_words;
     f->smem_bytes = words * 4;
     SR_CUDA(ctx, cudaMemcpyAsync(f->dev.p, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
     SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     // occupancy-sized persistent grid
     int per_sm = 0;
-    SR_CUDA(ctx, cudaFuncSetAttribute(srd::k_fragment<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(f->smem_bytes, 1)));
-    SR_CUDA(ctx, cudaFuncSetAttribute(srd::k_fragment<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(f->smem_bytes, 1)));
+    SR_CUDA(ctx, cudaFuncSetAttribute(srd::k_fragment<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_bytes));
+    SR_CUDA(ctx, cudaFuncSetAttribute(srd::k_fragment<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_bytes));
     if (f->smem_agg)
         SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, srd::k_fragment<true>, srd::FRAG_BLOCK, f->smem_bytes));
     else
@@ -439,19 +263,20 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
 static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
     sr_ctx* ctx = f->ctx;
     if (f->agg->finished) return sr_fail(ctx, SR_ERR_STATE, "fragment push after sink_finish");
+    if (fact->num_rows >= 0xFFFFFFF0ll) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "fragment batch of more than 2^32 rows; push smaller morsels");
     SR_TRY(f->staged.stage(ctx, fact));
     const int64_t n = fact->num_rows;
     bool first = !f->compiled;
     if (first) SR_TRY(frag_compile(f));
     VTab vt;
     SR_TRY(frag_bind_vtab(f, &vt));
-    if (first) SR_TRY(frag_plan(f, vt, n));
+    if (first) {
+        SR_TRY(frag_plan(f, vt, n));
+        SR_TRY(frag_bind_vtab(f, &vt)); // the plan reorders the joins: payload values now point at the new positions
+    }
     if (n == 0) return SR_OK;
     SR_TRY(agg_check_nullability(f->agg, vt));
-    if (f->agg->smem_bytes == 0 && f->smem_agg) {
-        // nullability change forced the aggregate to global accumulation
-        f->smem_agg = false;
-    }
+    if (f->agg->smem_bytes == 0 && f->smem_agg) f->smem_agg = false; // a nullability change forced global accumulation
     sr_agg* a = f->agg;
     const srd::AggDev& ah = a->host;
     const bool hash = !ah.dense && ah.num_keys > 0;
@@ -465,10 +290,10 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
     const int grid = (int)std::min<int64_t>(f->grid, (n + srd::FRAG_TILE - 1) / srd::FRAG_TILE);
     if (f->smem_agg)
         srd::k_fragment<true><<<grid, srd::FRAG_BLOCK, f->smem_bytes, ctx->stream>>>((const srd::FragDev*)f->dev.p, (const srd::AggDev*)a->dev.p, vt, n,
-                                                                                    f->agg_smem_word_off);
+                                                                                    f->queue_word_off);
     else
         srd::k_fragment<false><<<grid, srd::FRAG_BLOCK, f->smem_bytes, ctx->stream>>>((const srd::FragDev*)f->dev.p, (const srd::AggDev*)a->dev.p, vt, n,
-                                                                                     f->agg_smem_word_off);
+                                                                                     f->queue_word_off);
     SR_LAUNCH_CHECK(ctx);
     if (hash) {
         uint64_t ng;

@@ -189,6 +189,10 @@ sr_ctx* sr_ctx_create(int32_t device, void* cuda_stream) {
         sr_fail(nullptr, SR_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
         return nullptr;
     }
+    // late materialisation touches single 32-byte sectors of the later columns: do not let L2 widen those
+    // misses to 64/128-byte fetches (a hint; harmless where unsupported)
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    cudaGetLastError();
     sr_ctx* ctx = new sr_ctx();
     ctx->device = device;
     if (cuda_stream) {
@@ -231,6 +235,10 @@ int32_t sr_ctx_sync(sr_ctx* ctx) {
 
 const char* sr_last_error(sr_ctx* ctx) {
     return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+int32_t sr_last_error_code(sr_ctx* ctx) {
+    return ctx ? ctx->err_code : SR_ERR_INVALID_ARGUMENT;
 }
 
 int64_t sr_ctx_kernel_launches(sr_ctx* ctx) {
@@ -670,6 +678,23 @@ int32_t sr_fragment_push(sr_fragment* frag, const sr_chunk_view* fact) {
 
 sr_agg* sr_fragment_agg(sr_fragment* frag) {
     return frag ? frag->agg : nullptr;
+}
+
+int32_t sr_fragment_get_plan(sr_fragment* frag, sr_fragment_plan* plan) {
+    if (!frag || !plan) return SR_ERR_INVALID_ARGUMENT;
+    if (!frag->compiled) return sr_fail(frag->ctx, SR_ERR_STATE, "the fragment plans on its first push");
+    memset(plan, 0, sizeof(*plan));
+    plan->num_joins = frag->num_joins;
+    for (int q = 0; q < frag->num_joins; q++) {
+        plan->order[q] = frag->order[q];
+        plan->bitmap_in_smem[q] = frag->host.joins[q].smem_off >= 0 ? 1 : 0;
+        plan->pass_rate[q] = frag->pass_rate[q];
+    }
+    plan->smem_bytes = (int32_t)frag->smem_bytes;
+    plan->grid = frag->grid;
+    plan->block = srd::FRAG_BLOCK;
+    plan->agg_in_smem = frag->smem_agg ? 1 : 0;
+    return SR_OK;
 }
 
 int32_t sr_fragment_reset(sr_fragment* frag) {

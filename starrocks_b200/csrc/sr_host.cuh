@@ -19,6 +19,7 @@ struct sr_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string err;
+    int32_t err_code = 0;
     int64_t launches = 0;
     int64_t dev_bytes = 0;
     int num_sms = 148;
@@ -52,10 +53,12 @@ static int32_t sr_fail(sr_ctx* ctx, int32_t code, const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
-    if (ctx)
+    if (ctx) {
         ctx->err = buf;
-    else
+        ctx->err_code = code;
+    } else {
         g_create_err = buf;
+    }
     return code;
 }
 

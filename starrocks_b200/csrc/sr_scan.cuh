@@ -34,7 +34,7 @@ constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
 
 // selection[i] = all conjuncts true-and-not-null.  block_counts[b] = survivors of tile b.
-__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_select(const ScanProg* __restrict__ prog, VTab vt, int64_t n,
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_select(const ScanProg* __restrict__ prog, const __grid_constant__ VTab vt, int64_t n,
                                                              uint8_t* __restrict__ sel, uint32_t* __restrict__ block_counts) {
     __shared__ uint32_t s_cnt[SCAN_BLOCK / 32];
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;

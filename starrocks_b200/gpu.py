@@ -51,6 +51,7 @@ def lib():
         "sr_ctx_destroy": (None, [vp]),
         "sr_ctx_sync": (i32, [vp]),
         "sr_last_error": (C.c_char_p, [vp]),
+        "sr_last_error_code": (i32, [vp]),
         "sr_ctx_kernel_launches": (i64, [vp]),
         "sr_ctx_device_bytes": (i64, [vp]),
         "sr_ctx_stream": (vp, [vp]),
@@ -77,6 +78,7 @@ def lib():
         "sr_agg_merge": (i32, [vp, vp]),
         "sr_agg_reset": (i32, [vp]),
         "sr_fragment_reset": (i32, [vp]),
+        "sr_fragment_get_plan": (i32, [vp, vp]),
         "sr_fragment_create": (vp, [vp, vp]),
         "sr_fragment_destroy": (None, [vp]),
         "sr_fragment_push": (i32, [vp, vp]),
@@ -103,12 +105,12 @@ def lib():
 
 
 EXPORTED_SYMBOLS = [
-    "sr_abi_version", "sr_type_width", "sr_ctx_create", "sr_ctx_destroy", "sr_ctx_sync", "sr_last_error",
+    "sr_abi_version", "sr_type_width", "sr_ctx_create", "sr_ctx_destroy", "sr_ctx_sync", "sr_last_error", "sr_last_error_code",
     "sr_ctx_kernel_launches", "sr_ctx_device_bytes", "sr_ctx_stream", "sr_scan_create", "sr_scan_destroy",
     "sr_scan_filter", "sr_scan_evaluate", "sr_join_create", "sr_join_destroy", "sr_join_append_build",
     "sr_join_build_finish", "sr_join_is_build_done", "sr_join_get_info", "sr_join_copy_table", "sr_join_probe",
     "sr_join_probe_indexes", "sr_join_key_hash", "sr_agg_create", "sr_agg_destroy", "sr_agg_push",
-    "sr_agg_sink_finish", "sr_agg_num_groups", "sr_agg_pull", "sr_agg_merge", "sr_agg_reset", "sr_fragment_reset",
+    "sr_agg_sink_finish", "sr_agg_num_groups", "sr_agg_pull", "sr_agg_merge", "sr_agg_reset", "sr_fragment_reset", "sr_fragment_get_plan",
     "sr_fragment_create",
     "sr_fragment_destroy", "sr_fragment_push", "sr_fragment_agg", "sr_fragment_rows_passed", "sr_xchg_create",
     "sr_xchg_destroy", "sr_xchg_partition", "sr_xchg_hash", "sr_gather", "sr_memcpy", "sr_abi_sizeof", "sr_bandwidth_probe", "sr_flush_l2",
@@ -210,7 +212,7 @@ class Scan:
         self.desc = scan_desc
         self.h = lib().sr_scan_create(ctx.h, scan_desc.ref())
         if not self.h:
-            ctx.check(-1)
+            ctx.check(lib().sr_last_error_code(ctx.h) or -1)
 
     def close(self):
         if self.h:
@@ -234,7 +236,7 @@ class Join:
         self.desc = desc
         self.h = lib().sr_join_create(ctx.h, C.byref(desc))
         if not self.h:
-            ctx.check(-1)
+            ctx.check(lib().sr_last_error_code(ctx.h) or -1)
 
     def close(self):
         if self.h:
@@ -281,7 +283,7 @@ class Agg:
         self.owned = handle is None
         self.h = handle if handle is not None else lib().sr_agg_create(ctx.h, C.byref(desc))
         if not self.h:
-            ctx.check(-1)
+            ctx.check(lib().sr_last_error_code(ctx.h) or -1)
 
     def close(self):
         if self.h and self.owned:
@@ -334,7 +336,7 @@ class Fragment:
         self.desc = d
         self.h = lib().sr_fragment_create(ctx.h, C.byref(d))
         if not self.h:
-            ctx.check(-1)
+            ctx.check(lib().sr_last_error_code(ctx.h) or -1)
         self.agg = Agg(ctx, agg_desc, handle=lib().sr_fragment_agg(self.h))
 
     def close(self):
@@ -348,6 +350,14 @@ class Fragment:
     def reset(self):
         self.ctx.check(lib().sr_fragment_reset(self.h))
 
+    def plan(self):
+        p = abi.sr_fragment_plan()
+        self.ctx.check(lib().sr_fragment_get_plan(self.h, C.byref(p)))
+        nj = p.num_joins
+        return {"order": list(p.order[:nj]), "bitmap_in_smem": list(p.bitmap_in_smem[:nj]),
+                "pass_rate": [round(x, 4) for x in p.pass_rate[:nj]], "smem_bytes": p.smem_bytes, "grid": p.grid,
+                "block": p.block, "agg_in_smem": bool(p.agg_in_smem)}
+
     @property
     def rows_passed(self):
         return self.ctx.check(lib().sr_fragment_rows_passed(self.h))
@@ -359,7 +369,7 @@ class Xchg:
         self.desc = part_desc
         self.h = lib().sr_xchg_create(ctx.h, C.byref(part_desc))
         if not self.h:
-            ctx.check(-1)
+            ctx.check(lib().sr_last_error_code(ctx.h) or -1)
 
     def close(self):
         if self.h:
