@@ -421,8 +421,11 @@ typedef struct sr_frag_join {
 typedef struct sr_fragment_desc {
     sr_scan_desc scan; /* preds / filter_exprs on fact columns; out_slots ignored */
     int32_t num_joins;
-    int32_t reserved;
-    sr_frag_join joins[SR_MAX_FRAG_JOINS]; /* probed in this order */
+    /* execution mode: 0 = decide from the pass rates sampled on the first batch, 1 = single fused kernel
+     * (warp-queue cascade), 2 = selection-vector passes (stream -> gather -> aggregate).  Both modes give
+     * identical results; the knob exists for tests and experiments. */
+    int32_t mode_hint;
+    sr_frag_join joins[SR_MAX_FRAG_JOINS]; /* hint order; the fragment reorders by measured pass rate */
     sr_agg_desc agg; /* group keys / fn inputs may reference fact slots and payload slots */
 } sr_fragment_desc;
 
@@ -446,6 +449,11 @@ typedef struct sr_fragment_plan {
     int32_t grid;
     int32_t block;
     int32_t agg_in_smem;
+    int32_t mode;             /* 1 = fused cascade kernel, 2 = selection-vector passes */
+    int32_t num_stream_joins; /* mode 2: joins tested by the streaming pass */
+    int32_t num_gather_passes;
+    int32_t reserved;
+    double pred_rate; /* fraction of sampled rows passing the scan conjuncts */
 } sr_fragment_plan;
 int32_t sr_fragment_get_plan(sr_fragment* frag, sr_fragment_plan* plan);
 /* reset_state for the whole fragment: clears its aggregate and the rows_passed counter. */

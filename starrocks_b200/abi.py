@@ -142,14 +142,16 @@ class sr_frag_join(C.Structure):
 
 
 class sr_fragment_desc(C.Structure):
-    _fields_ = [("scan", sr_scan_desc), ("num_joins", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("scan", sr_scan_desc), ("num_joins", C.c_int32), ("mode_hint", C.c_int32),
                 ("joins", sr_frag_join * SR_MAX_FRAG_JOINS), ("agg", sr_agg_desc)]
 
 
 class sr_fragment_plan(C.Structure):
     _fields_ = [("num_joins", C.c_int32), ("order", C.c_int32 * SR_MAX_FRAG_JOINS),
                 ("bitmap_in_smem", C.c_int32 * SR_MAX_FRAG_JOINS), ("pass_rate", C.c_double * SR_MAX_FRAG_JOINS),
-                ("smem_bytes", C.c_int32), ("grid", C.c_int32), ("block", C.c_int32), ("agg_in_smem", C.c_int32)]
+                ("smem_bytes", C.c_int32), ("grid", C.c_int32), ("block", C.c_int32), ("agg_in_smem", C.c_int32),
+                ("mode", C.c_int32), ("num_stream_joins", C.c_int32), ("num_gather_passes", C.c_int32),
+                ("reserved", C.c_int32), ("pred_rate", C.c_double)]
 
 
 class sr_part_desc(C.Structure):

@@ -31,6 +31,7 @@
 #include "sr_agg.cuh"
 
 #include "sr_frag_kernel.cuh"
+#include "sr_frag_pass.cuh"
 
 // ---------------------------------------------------------------------------------------
 // host side
@@ -55,6 +56,15 @@ struct sr_fragment {
     int grid = 0;
     int order[SR_MAX_FRAG_JOINS];
     double pass_rate[SR_MAX_FRAG_JOINS];
+    double pred_rate = 1.0;
+    // selective mode (sr_frag_pass.cuh): streaming pass -> gather passes -> final pass
+    int force_mode = 0; // 0 = choose from the sampled pass rates, 1 = fused cascade kernel, 2 = selection-vector passes
+    bool selective = false;
+    srd::PassDev pass;
+    std::vector<int> gather_joins; // probe positions that get a pass of their own
+    DevBuf sel[2], pass_counters;
+    size_t stream_smem = 0;
+    int stream_grid = 0;
 };
 
 struct FragTypeCtx {
@@ -194,8 +204,9 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
     SR_TRY(f->dev.reserve(ctx, sizeof(srd::FragDev)));
     SR_CUDA(ctx, cudaMemcpyAsync(f->dev.p, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
     const int64_t sample = std::min<int64_t>(n, 1 << 16);
-    unsigned long long counts[SR_MAX_FRAG_JOINS] = {0};
-    if (f->num_joins > 1 && sample > 0) {
+    unsigned long long counts[SR_MAX_FRAG_JOINS + 1] = {0};
+    counts[SR_MAX_FRAG_JOINS] = (unsigned long long)sample;
+    if (sample > 0 && (f->num_joins > 0 || h.num_preds > 0 || h.num_exprs > 0)) {
         unsigned long long* dcounts = f->counters.as<unsigned long long>() + 8;
         SR_CUDA(ctx, cudaMemsetAsync(dcounts, 0, sizeof(counts), ctx->stream));
         srd::k_frag_sample<<<grid_for(sample, 256), 256, 0, ctx->stream>>>((const srd::FragDev*)f->dev.p, vt, sample, dcounts);
@@ -204,6 +215,7 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
         SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     for (int j = 0; j < f->num_joins; j++) f->pass_rate[j] = sample > 0 ? (double)counts[j] / (double)sample : 1.0;
+    f->pred_rate = sample > 0 ? (double)counts[SR_MAX_FRAG_JOINS] / (double)sample : 1.0;
     std::vector<int> ord(f->num_joins);
     for (int j = 0; j < f->num_joins; j++) ord[j] = j;
     // most selective first; pass rates within 15 % of each other count as a tie -> smaller table first
@@ -226,6 +238,49 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
     // stream the second join's key together with the first when most of its 64-byte DRAM bursts would
     // be touched anyway: 1 - (1 - p)^16 >= 0.74 for p >= 0.08
     h.eager1 = (f->num_joins >= 2 && f->pass_rate[ord[0]] >= 0.08) ? 1 : 0;
+    // ---- mode: when few rows reach the aggregate, run selection-vector passes instead of the cascade ----
+    double total_rate = f->pred_rate;
+    for (int q = 0; q < f->num_joins; q++) total_rate *= f->pass_rate[ord[q]];
+    f->selective = f->force_mode == 2 || (f->force_mode == 0 && total_rate < 0.25 && n >= (1 << 16));
+    if (f->selective) {
+        // joins whose key column is streamed: the first one, and the second when >= 8 % of the rows reach it
+        int ns = f->num_joins > 0 ? 1 : 0;
+        if (f->num_joins > 1 && f->pred_rate * f->pass_rate[ord[0]] >= 0.08) ns = 2;
+        // trailing joins that filter (almost) nothing are tested inline by the final pass
+        int ff = f->num_joins;
+        while (ff > ns && f->pass_rate[ord[ff - 1]] >= 0.9) ff--;
+        f->pass.num_stream_joins = ns;
+        f->pass.final_first_join = ff;
+        f->pass.pad0 = f->pass.pad1 = 0;
+        f->gather_joins.clear();
+        for (int q = ns; q < ff; q++) f->gather_joins.push_back(q);
+        // streaming pass shared memory: bitmaps of the streamed joins only
+        size_t sw = 0;
+        const size_t sbudget = (100 * 1024) / 4;
+        for (int q = 0; q < f->num_joins; q++) {
+            srd::FragJoinDev& fj = h.joins[q];
+            fj.smem_off = -1;
+            if (q < ns && fj.use_bitmap && sw + (size_t)fj.bitmap_words <= sbudget) {
+                fj.smem_off = (int32_t)sw;
+                sw += ((size_t)fj.bitmap_words + 3) & ~(size_t)3;
+            }
+        }
+        f->stream_smem = sw * 4;
+        f->smem_agg = f->agg->smem_bytes > 0;
+        f->smem_bytes = f->agg->smem_bytes;
+        f->queue_word_off = 0;
+        SR_CUDA(ctx, cudaMemcpyAsync(f->dev.p, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+        SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int per_sm = 0;
+        SR_CUDA(ctx, cudaFuncSetAttribute(srd::k_frag_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(f->stream_smem, 16)));
+        SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, srd::k_frag_stream, srd::STREAM_BLOCK, f->stream_smem));
+        if (per_sm < 1) return sr_fail(ctx, SR_ERR_CUDA, "streaming pass does not fit on an SM (smem %zu)", f->stream_smem);
+        f->stream_grid = per_sm * ctx->num_sms;
+        f->grid = ctx->num_sms * 8;
+        SR_TRY(f->pass_counters.reserve(ctx, 16 * sizeof(uint64_t)));
+        f->compiled = true;
+        return SR_OK;
+    }
     // dynamic shared memory: [aggregate accumulators | bitmaps | per-warp queues]
     size_t words = 0;
     f->smem_agg = f->agg->smem_bytes > 0;
@@ -286,6 +341,39 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
             if (a->host.cap >= (1ull << 33)) return sr_fail(ctx, SR_ERR_OUT_OF_MEMORY, "aggregate table would exceed 2^33 slots; push smaller batches");
             SR_TRY(agg_grow(a, a->host.cap * 4));
         }
+    }
+    if (f->selective) {
+        const srd::FragDev* fdev = (const srd::FragDev*)f->dev.p;
+        SR_TRY(f->sel[0].reserve(ctx, sizeof(uint32_t) * (size_t)n + 64));
+        if (!f->gather_joins.empty()) SR_TRY(f->sel[1].reserve(ctx, sizeof(uint32_t) * (size_t)n + 64));
+        unsigned long long* cnt = f->pass_counters.as<unsigned long long>();
+        SR_CUDA(ctx, cudaMemsetAsync(cnt, 0, 16 * sizeof(uint64_t), ctx->stream));
+        const int sgrid = (int)std::min<int64_t>(f->stream_grid, (n + srd::STREAM_TILE - 1) / srd::STREAM_TILE);
+        srd::k_frag_stream<<<sgrid, srd::STREAM_BLOCK, f->stream_smem, ctx->stream>>>(fdev, f->pass, vt, n, f->sel[0].as<uint32_t>(), cnt);
+        SR_LAUNCH_CHECK(ctx);
+        int cur = 0, k = 0;
+        for (int q : f->gather_joins) {
+            srd::k_frag_gather_join<<<f->grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, q, vt, f->sel[cur].as<uint32_t>(), cnt + k,
+                                                                                  f->sel[cur ^ 1].as<uint32_t>(), cnt + k + 1);
+            SR_LAUNCH_CHECK(ctx);
+            cur ^= 1;
+            k++;
+        }
+        if (f->smem_agg)
+            srd::k_frag_gather_agg<true><<<f->grid, srd::GATHER_BLOCK, a->smem_bytes, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, f->pass, vt,
+                                                                                                   f->sel[cur].as<uint32_t>(), cnt + k);
+        else
+            srd::k_frag_gather_agg<false><<<f->grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, f->pass, vt,
+                                                                                        f->sel[cur].as<uint32_t>(), cnt + k);
+        SR_LAUNCH_CHECK(ctx);
+        if (hash) {
+            uint64_t ng;
+            int32_t ovf, bad;
+            SR_TRY(agg_read_counters(a, &ng, &ovf, &bad));
+            a->ngroups_host = (int64_t)ng;
+            if (ovf) return sr_fail(ctx, SR_ERR_STATE, "aggregate hash table overflow (internal)");
+        }
+        return SR_OK;
     }
     const int grid = (int)std::min<int64_t>(f->grid, (n + srd::FRAG_TILE - 1) / srd::FRAG_TILE);
     if (f->smem_agg)

@@ -407,6 +407,22 @@ __global__ void __launch_bounds__(256) k_frag_sample(const FragDev* __restrict__
     const FragDev& fd = *fdp;
     for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
         ChunkLoader ld{vt, row};
+        {
+            // rows passing every scan conjunct -> counts[SR_MAX_FRAG_JOINS]
+            bool pass = true;
+            for (int p = 0; p < fd.num_preds && pass; p++) {
+                int64_t bits;
+                const bool nul = ld.load(fd.preds[p].value_id, bits);
+                pass = eval_pred(fd.preds[p], bits, nul);
+            }
+            for (int e = 0; e < fd.num_exprs && pass; e++) {
+                int64_t bits;
+                const bool nul = eval_expr(fd.exprs[e], ld, bits);
+                pass = !nul && bits != 0;
+            }
+            const uint32_t m = __ballot_sync(__activemask(), pass);
+            if (pass && (m & lanemask_lt()) == 0) atomicAdd(&counts[SR_MAX_FRAG_JOINS], (unsigned long long)__popc(m));
+        }
         for (int j = 0; j < fd.num_joins; j++) {
             const FragJoinDev& fj = fd.joins[j];
             int64_t key;

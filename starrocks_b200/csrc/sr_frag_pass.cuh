@@ -1,0 +1,282 @@
+// sr_frag_pass.cuh -- the SELECTIVE mode of the fused fragment: a short pipeline of passes connected by
+// device-resident selection vectors (the GPU form of the reference's Filter / selection vector,
+// be/src/column/chunk.cpp:362 and storage late materialisation):
+//
+//   pass S  k_frag_stream       streams the scan-predicate columns and the key columns of the leading joins
+//                               (128-bit loads, next tile prefetched), tests their bitmaps, appends the
+//                               surviving row ids to a selection vector (warp-aggregated atomicAdd);
+//   pass G  k_frag_gather_join  one per remaining selective join: lane-per-row gather of the key for the
+//                               selected rows only (late materialisation at DRAM-sector granularity),
+//                               bitmap / hash test, appends survivors to the next selection vector;
+//   pass F  k_frag_gather_agg   remaining non-selective joins inline, build-row lookups, payload gathers,
+//                               group slot, aggregate update in shared-memory accumulators.
+//
+// Every pass runs with full warps; the selection vectors are tiny next to the fact columns (4 B per
+// surviving row), and no pass waits on the host: a pass reads its input length from the counter the
+// previous pass bumped (same stream).  Row order inside a selection vector is not kept -- the consumer
+// is an aggregate.
+#pragma once
+
+#include "sr_frag_kernel.cuh"
+
+namespace srd {
+
+struct PassDev {
+    int32_t num_stream_joins; // joins [0, num_stream_joins) are tested by the streaming pass
+    int32_t final_first_join; // joins [final_first_join, S) are tested inline by the final pass
+    int32_t pad0, pad1;
+};
+
+// bitmap / hash test against the global copies only (gather passes do not stage bitmaps)
+__device__ __forceinline__ bool join_hit_global(const FragJoinDev& fj, int64_t key) {
+    if (fj.use_bitmap) {
+        if (key < fj.j.min_value || key > fj.j.max_value) return false;
+        const uint64_t idx = (uint64_t)(key - fj.j.min_value);
+        return (__ldg(fj.j.bitmap + (idx >> 5)) >> (idx & 31)) & 1u;
+    }
+    return join_lookup(fj.j, key) != 0;
+}
+
+constexpr int STREAM_BLOCK = 512;
+constexpr int STREAM_ROWS = 4;
+constexpr int STREAM_GROUPS = 2;
+constexpr int STREAM_TILE = STREAM_BLOCK * STREAM_ROWS * STREAM_GROUPS;
+constexpr int STREAM_MAX_JOINS = 2;
+
+// append the rows flagged in `alive` (bit i -> row base_i + (i & 3)) to sel_out
+__device__ __forceinline__ void warp_append_rows(uint32_t alive_all, int64_t row0_g0, int64_t row0_g1, uint32_t* __restrict__ sel_out,
+                                                 unsigned long long* __restrict__ counter) {
+    const uint32_t cnt = __popc(alive_all);
+    const uint32_t incl = warp_incl_scan(cnt);
+    const uint32_t total = __shfl_sync(SR_FULL_MASK, incl, 31);
+    if (total == 0) return;
+    unsigned long long base = 0;
+    if (lane_id() == 0) base = atomicAdd(counter, (unsigned long long)total);
+    base = __shfl_sync(SR_FULL_MASK, base, 0);
+    unsigned long long pos = base + incl - cnt;
+#pragma unroll
+    for (int i = 0; i < STREAM_GROUPS * STREAM_ROWS; i++) {
+        if ((alive_all >> i) & 1u) {
+            const int64_t rb = i < STREAM_ROWS ? row0_g0 : row0_g1;
+            sel_out[pos++] = (uint32_t)(rb + (i & (STREAM_ROWS - 1)));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream(const FragDev* __restrict__ fdp, PassDev pd, const __grid_constant__ VTab vt, int64_t n,
+                                                                 uint32_t* __restrict__ sel_out, unsigned long long* __restrict__ counter) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ FragJoinDev s_joins[STREAM_MAX_JOINS];
+    __shared__ CPred s_preds[8];
+    const FragDev& fd = *fdp;
+    const int SJ = pd.num_stream_joins;
+    for (int i = threadIdx.x; i < (int)(sizeof(FragJoinDev) / 4) * SJ; i += blockDim.x) ((uint32_t*)s_joins)[i] = ((const uint32_t*)fd.joins)[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(CPred) / 4) * fd.num_preds; i += blockDim.x) ((uint32_t*)s_preds)[i] = ((const uint32_t*)fd.preds)[i];
+    for (int j = 0; j < SJ; j++) {
+        const FragJoinDev& fj = fd.joins[j];
+        if (fj.smem_off >= 0)
+            for (int w = threadIdx.x; w < fj.bitmap_words; w += blockDim.x) smem[fj.smem_off + w] = fj.j.bitmap[w];
+    }
+    __syncthreads();
+
+    // fast path: the streamed key columns are int32-class, 16-byte aligned and not nullable, and no scan
+    // conjunct precedes the joins -> one 128-bit load per thread, group and column, prefetched a tile ahead
+    bool fast = SJ > 0 && fd.num_preds == 0 && fd.num_exprs == 0;
+    const int32_t* keyp[STREAM_MAX_JOINS] = {nullptr, nullptr};
+    for (int j = 0; j < SJ && fast; j++) {
+        const VDesc& d = vt.v[s_joins[j].key_value_id];
+        fast = type_width(d.type) == 4 && !is_float_class(d.type) && d.nulls == nullptr && (((uintptr_t)d.data) & 15) == 0;
+        keyp[j] = (const int32_t*)d.data;
+    }
+    const bool two = SJ > 1;
+    const int64_t num_tiles = (n + STREAM_TILE - 1) / STREAM_TILE;
+    const int64_t full_tiles = n / STREAM_TILE;
+    int4 pk[STREAM_MAX_JOINS][STREAM_GROUPS];
+#pragma unroll
+    for (int j = 0; j < STREAM_MAX_JOINS; j++)
+#pragma unroll
+        for (int g = 0; g < STREAM_GROUPS; g++) pk[j][g] = make_int4(0, 0, 0, 0);
+    auto prefetch = [&](int64_t tile) {
+        if (fast && tile < full_tiles) {
+#pragma unroll
+            for (int g = 0; g < STREAM_GROUPS; g++) {
+                const int64_t r0 = tile * STREAM_TILE + (int64_t)g * (STREAM_BLOCK * STREAM_ROWS) + (int64_t)threadIdx.x * STREAM_ROWS;
+                pk[0][g] = ldg_stream_v4(keyp[0] + r0);
+                if (two) pk[1][g] = ldg_stream_v4(keyp[1] + r0);
+            }
+        }
+    };
+    prefetch(blockIdx.x);
+
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int64_t row0[STREAM_GROUPS];
+        uint32_t alive[STREAM_GROUPS];
+#pragma unroll
+        for (int g = 0; g < STREAM_GROUPS; g++) {
+            row0[g] = tile * STREAM_TILE + (int64_t)g * (STREAM_BLOCK * STREAM_ROWS) + (int64_t)threadIdx.x * STREAM_ROWS;
+            alive[g] = 0;
+#pragma unroll
+            for (int r = 0; r < STREAM_ROWS; r++)
+                if (row0[g] + r < n) alive[g] |= 1u << r;
+        }
+        if (fast && tile < full_tiles) {
+            int32_t k1[STREAM_GROUPS][STREAM_ROWS];
+#pragma unroll
+            for (int g = 0; g < STREAM_GROUPS; g++) {
+                const int32_t k0[STREAM_ROWS] = {pk[0][g].x, pk[0][g].y, pk[0][g].z, pk[0][g].w};
+                k1[g][0] = pk[1][g].x;
+                k1[g][1] = pk[1][g].y;
+                k1[g][2] = pk[1][g].z;
+                k1[g][3] = pk[1][g].w;
+#pragma unroll
+                for (int r = 0; r < STREAM_ROWS; r++)
+                    if (!frag_join_hit(s_joins[0], smem, (int64_t)k0[r])) alive[g] &= ~(1u << r);
+            }
+            prefetch(tile + gridDim.x);
+            if (two) {
+#pragma unroll
+                for (int g = 0; g < STREAM_GROUPS; g++)
+#pragma unroll
+                    for (int r = 0; r < STREAM_ROWS; r++)
+                        if ((alive[g] & (1u << r)) && !frag_join_hit(s_joins[1], smem, (int64_t)k1[g][r])) alive[g] &= ~(1u << r);
+            }
+        } else {
+            int64_t vals[STREAM_GROUPS][STREAM_ROWS];
+            uint32_t nullmask[STREAM_GROUPS];
+#pragma unroll 1
+            for (int p = 0; p < fd.num_preds; p++) {
+                const VDesc& d = vt.v[s_preds[p].value_id];
+#pragma unroll
+                for (int g = 0; g < STREAM_GROUPS; g++) load_rows4(d, row0[g], alive[g], vals[g], nullmask[g]);
+#pragma unroll
+                for (int g = 0; g < STREAM_GROUPS; g++)
+#pragma unroll
+                    for (int r = 0; r < STREAM_ROWS; r++)
+                        if ((alive[g] & (1u << r)) && !eval_pred(s_preds[p], vals[g][r], (nullmask[g] >> r) & 1u)) alive[g] &= ~(1u << r);
+            }
+#pragma unroll 1
+            for (int e = 0; e < fd.num_exprs; e++) {
+#pragma unroll 1
+                for (int g = 0; g < STREAM_GROUPS; g++)
+#pragma unroll 1
+                    for (int r = 0; r < STREAM_ROWS; r++) {
+                        if (alive[g] & (1u << r)) {
+                            ChunkLoader ld{vt, row0[g] + r};
+                            int64_t bits;
+                            const bool nul = eval_expr(fd.exprs[e], ld, bits);
+                            if (nul || bits == 0) alive[g] &= ~(1u << r);
+                        }
+                    }
+            }
+#pragma unroll 1
+            for (int j = 0; j < SJ; j++) {
+                const VDesc& d = vt.v[s_joins[j].key_value_id];
+#pragma unroll
+                for (int g = 0; g < STREAM_GROUPS; g++) load_rows4(d, row0[g], alive[g], vals[g], nullmask[g]);
+#pragma unroll
+                for (int g = 0; g < STREAM_GROUPS; g++) {
+                    alive[g] &= ~nullmask[g]; // NULL keys never match (join_hash_table.cpp:166-170)
+#pragma unroll
+                    for (int r = 0; r < STREAM_ROWS; r++)
+                        if ((alive[g] & (1u << r)) && !frag_join_hit(s_joins[j], smem, vals[g][r])) alive[g] &= ~(1u << r);
+                }
+            }
+        }
+        static_assert(STREAM_GROUPS == 2, "two groups of alive bits are packed into one word");
+        warp_append_rows(alive[0] | (alive[1] << STREAM_ROWS), row0[0], row0[1], sel_out, counter);
+    }
+}
+
+constexpr int GATHER_BLOCK = 256;
+
+// one selective join on the selected rows: sel_in[0, *n_in) -> sel_out (appended at *counter_out)
+__global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_join(const FragDev* __restrict__ fdp, int32_t j, const __grid_constant__ VTab vt,
+                                                                    const uint32_t* __restrict__ sel_in, const unsigned long long* __restrict__ n_in_ptr,
+                                                                    uint32_t* __restrict__ sel_out, unsigned long long* __restrict__ counter_out) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ FragJoinDev s_join;
+    for (int i = threadIdx.x; i < (int)(sizeof(FragJoinDev) / 4); i += blockDim.x) ((uint32_t*)&s_join)[i] = ((const uint32_t*)&fdp->joins[j])[i];
+    __syncthreads();
+    const unsigned long long n_in = *n_in_ptr;
+    const FragJoinDev& fj = s_join;
+    const VDesc& d = vt.v[fj.key_value_id];
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x; i0 < n_in; i0 += stride) {
+        const unsigned long long i = i0 + threadIdx.x;
+        bool hit = false;
+        uint32_t row = 0;
+        if (i < n_in) {
+            row = sel_in[i];
+            const int64_t key = load_int(d.data, d.type, (int64_t)row);
+            const bool nul = d.nulls != nullptr && d.nulls[row] != 0;
+            hit = !nul && join_hit_global(fj, key); // global bitmap copy: L1/L2 resident
+        }
+        const uint32_t m = __ballot_sync(SR_FULL_MASK, hit);
+        if (m) {
+            unsigned long long base = 0;
+            if (lane_id() == 0) base = atomicAdd(counter_out, (unsigned long long)__popc(m));
+            base = __shfl_sync(SR_FULL_MASK, base, 0);
+            if (hit) sel_out[base + __popc(m & lanemask_lt())] = row;
+        }
+    }
+}
+
+// final pass: remaining joins inline, payload lookups, aggregate update
+template <bool SMEM_AGG>
+__global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg(const FragDev* __restrict__ fdp, const AggDev* __restrict__ adp, PassDev pd,
+                                                                   const __grid_constant__ VTab vt, const uint32_t* __restrict__ sel_in,
+                                                                   const unsigned long long* __restrict__ n_in_ptr) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ FragJoinDev s_joins[SR_MAX_FRAG_JOINS];
+    const FragDev& fd = *fdp;
+    const AggDev& ad = *adp;
+    const int S = fd.num_joins;
+    for (int i = threadIdx.x; i < (int)(sizeof(FragJoinDev) / 4) * S; i += blockDim.x) ((uint32_t*)s_joins)[i] = ((const uint32_t*)fd.joins)[i];
+    AccPtrs acc;
+    if (SMEM_AGG) {
+        acc_ptrs_smem(ad, (long long*)smem, acc);
+        acc_smem_init(ad, acc);
+    } else {
+        acc_ptrs_global(ad, acc);
+    }
+    __syncthreads();
+    const unsigned long long n_in = *n_in_ptr;
+    unsigned long long passed = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
+        const uint32_t row = sel_in[i];
+        FragLoader ld{vt, (int64_t)row, {0, 0, 0, 0, 0, 0}};
+        bool ok = true;
+#pragma unroll 1
+        for (int j = 0; j < S && ok; j++) {
+            const FragJoinDev& fj = s_joins[j];
+            const bool test = j >= pd.final_first_join;
+            if (!test && !fj.need_head) continue;
+            int64_t key;
+            const bool nul = ld.load(fj.key_value_id, key);
+            if (test && nul) {
+                ok = false;
+                break;
+            }
+            if (fj.need_head || !fj.use_bitmap) {
+                const uint32_t head = join_lookup(fj.j, key);
+                ld.bidx[j] = head;
+                if (test && head == 0) ok = false;
+            } else if (test) {
+                if (!join_hit_global(fj, key)) ok = false;
+            }
+        }
+        if (!ok) continue;
+        const long long slot = agg_find_slot(ad, ld);
+        if (slot >= 0) agg_apply_row(ad, acc, slot, ld);
+        passed++;
+    }
+    if (SMEM_AGG) {
+        __syncthreads();
+        acc_smem_flush(ad, acc);
+    }
+    passed = warp_sum(passed);
+    if (lane_id() == 0 && passed) atomicAdd(fd.rows_passed, passed);
+}
+
+} // namespace srd

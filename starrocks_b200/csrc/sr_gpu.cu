@@ -655,6 +655,7 @@ sr_fragment* sr_fragment_create(sr_ctx* ctx, const sr_fragment_desc* desc) {
     f->preds.assign(desc->scan.preds, desc->scan.preds + desc->scan.num_preds);
     f->exprs.assign(desc->scan.filter_exprs, desc->scan.filter_exprs + desc->scan.num_filter_exprs);
     f->num_joins = desc->num_joins;
+    f->force_mode = (desc->mode_hint == 1 || desc->mode_hint == 2) ? desc->mode_hint : 0;
     for (int j = 0; j < desc->num_joins; j++) f->joins[j] = desc->joins[j];
     f->agg = new sr_agg();
     f->agg->ctx = ctx;
@@ -694,6 +695,15 @@ int32_t sr_fragment_get_plan(sr_fragment* frag, sr_fragment_plan* plan) {
     plan->grid = frag->grid;
     plan->block = srd::FRAG_BLOCK;
     plan->agg_in_smem = frag->smem_agg ? 1 : 0;
+    plan->mode = frag->selective ? 2 : 1;
+    plan->num_stream_joins = frag->selective ? frag->pass.num_stream_joins : 0;
+    plan->num_gather_passes = frag->selective ? (int32_t)frag->gather_joins.size() : 0;
+    plan->pred_rate = frag->pred_rate;
+    if (frag->selective) {
+        plan->smem_bytes = (int32_t)frag->stream_smem;
+        plan->grid = frag->stream_grid;
+        plan->block = srd::STREAM_BLOCK;
+    }
     return SR_OK;
 }
 

@@ -319,13 +319,15 @@ class Agg:
 
 
 class Fragment:
-    def __init__(self, ctx, scan_desc, joins, agg_desc):
-        """joins: list of (Join, probe_key_slot, [payload build slots])"""
+    def __init__(self, ctx, scan_desc, joins, agg_desc, mode=0):
+        """joins: list of (Join, probe_key_slot, [payload build slots]); mode: 0 auto, 1 fused cascade,
+        2 selection-vector passes"""
         self.ctx = ctx
         self._keep = (scan_desc, joins, agg_desc)
         d = abi.sr_fragment_desc()
         d.scan = scan_desc.desc
         d.num_joins = len(joins)
+        d.mode_hint = mode
         for k, (j, slot, payload) in enumerate(joins):
             d.joins[k].join = j.h
             d.joins[k].probe_key_slot = slot
@@ -356,7 +358,10 @@ class Fragment:
         nj = p.num_joins
         return {"order": list(p.order[:nj]), "bitmap_in_smem": list(p.bitmap_in_smem[:nj]),
                 "pass_rate": [round(x, 4) for x in p.pass_rate[:nj]], "smem_bytes": p.smem_bytes, "grid": p.grid,
-                "block": p.block, "agg_in_smem": bool(p.agg_in_smem)}
+                "block": p.block, "agg_in_smem": bool(p.agg_in_smem),
+                "mode": {1: "fused-cascade", 2: "selection-vector-passes"}.get(p.mode, p.mode),
+                "num_stream_joins": p.num_stream_joins, "num_gather_passes": p.num_gather_passes,
+                "pred_rate": round(p.pred_rate, 4)}
 
     @property
     def rows_passed(self):

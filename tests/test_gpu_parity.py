@@ -377,13 +377,13 @@ def test_agg_pull_paging_and_device_output(gpu, ctx):
 # ---------------------------------------------------------------------------------------------
 # fused fragment: SSB Q4.1 and Q1.1 shapes against the chunk-at-a-time oracle pipeline
 # ---------------------------------------------------------------------------------------------
-def _run_q41(gpu, ctx, oracle, sf, n, pushes=1):
+def _run_q41(gpu, ctx, oracle, sf, n, pushes=1, mode=0):
     dims = ssb.gen_dims(sf)
     lo = ssb.gen_lineorder(sf, n=n)
     gjoins, gkeep = ssb.build_dims(gpu, dims, ssb.dim_plans_q41(), ctx=ctx)
     ojoins, okeep = ssb.build_dims(oracle, dims, ssb.dim_plans_q41())
     agg_desc = ssb.q41_agg_desc()
-    frag = gpu.Fragment(ctx, abi.ScanDesc(), gjoins, agg_desc)
+    frag = gpu.Fragment(ctx, abi.ScanDesc(), gjoins, agg_desc, mode=mode)
     try:
         step = (n + pushes - 1) // pushes
         for p in range(pushes):
@@ -403,22 +403,25 @@ def _run_q41(gpu, ctx, oracle, sf, n, pushes=1):
             item[0].close()
 
 
-def test_fragment_q41_parity(gpu, ctx, oracle):
-    got, passed = _run_q41(gpu, ctx, oracle, sf=0.1, n=600_000)
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_fragment_q41_parity(gpu, ctx, oracle, mode):
+    got, passed = _run_q41(gpu, ctx, oracle, sf=0.1, n=600_000, mode=mode)
     assert len(got) == 35 and passed > 0          # 7 years x 5 AMERICA nations
     assert sum(1 for _ in got) == 35
 
 
-def test_fragment_q41_multi_push_and_ragged(gpu, ctx, oracle):
-    _run_q41(gpu, ctx, oracle, sf=0.05, n=300_007, pushes=3)
-    _run_q41(gpu, ctx, oracle, sf=0.01, n=5, pushes=1)
+@pytest.mark.parametrize("mode", [1, 2])
+def test_fragment_q41_multi_push_and_ragged(gpu, ctx, oracle, mode):
+    _run_q41(gpu, ctx, oracle, sf=0.05, n=300_007, pushes=3, mode=mode)
+    _run_q41(gpu, ctx, oracle, sf=0.01, n=5, pushes=1, mode=mode)
 
 
-def test_fragment_q11_parity(gpu, ctx, oracle):
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_fragment_q11_parity(gpu, ctx, oracle, mode):
     lo = ssb.gen_lineorder(1, n=1_000_003)
     sd = abi.ScanDesc(preds=ssb.q11_scan_preds())
     agg_desc = ssb.q11_agg_desc()
-    frag = gpu.Fragment(ctx, sd, [], agg_desc)
+    frag = gpu.Fragment(ctx, sd, [], agg_desc, mode=mode)
     try:
         ch = ssb.fact_chunk(lo, ssb.Q11_FACT_COLS)
         frag.push(ch)
@@ -433,7 +436,8 @@ def test_fragment_q11_parity(gpu, ctx, oracle):
         frag.close()
 
 
-def test_fragment_hash_group_and_semi_join(gpu, ctx, oracle):
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_fragment_hash_group_and_semi_join(gpu, ctx, oracle, mode):
     # group-by without declared ranges -> hash table path inside the fused kernel; a LEFT SEMI join with a
     # sparse (hash) build side; a generic filter expression on the fact table
     rng = np.random.default_rng(3)
@@ -459,7 +463,7 @@ def test_fragment_hash_group_and_semi_join(gpu, ctx, oracle):
         oj1.build()
         oj2.build()
         assert gj2.info().method == abi.JOIN_METHOD_LINEAR_CHAINED
-        frag = gpu.Fragment(ctx, sd, [(gj1, 0, [11]), (gj2, 1, [])], agg_desc)
+        frag = gpu.Fragment(ctx, sd, [(gj1, 0, [11]), (gj2, 1, [])], agg_desc, mode=mode)
         frag.push(fact)
         got = gpu_rows(frag.agg.result())
         ores, opassed = oracle.fragment_run(sd, [(oj1, 0, [11]), (oj2, 1, [])], agg_desc, fact, num_threads=3)
