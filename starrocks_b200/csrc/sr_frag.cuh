@@ -344,8 +344,10 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
     }
     if (f->selective) {
         const srd::FragDev* fdev = (const srd::FragDev*)f->dev.p;
-        SR_TRY(f->sel[0].reserve(ctx, sizeof(uint32_t) * (size_t)n + 64));
-        if (!f->gather_joins.empty()) SR_TRY(f->sel[1].reserve(ctx, sizeof(uint32_t) * (size_t)n + 64));
+        // worst case every row survives, plus one partly used chunk per warp of the writing pass
+        const size_t slack = (size_t)srd::SEL_CHUNK * ((size_t)f->stream_grid * (srd::STREAM_BLOCK / 32) + (size_t)f->grid * (srd::GATHER_BLOCK / 32));
+        SR_TRY(f->sel[0].reserve(ctx, sizeof(uint32_t) * ((size_t)n + slack)));
+        if (!f->gather_joins.empty()) SR_TRY(f->sel[1].reserve(ctx, sizeof(uint32_t) * ((size_t)n + slack)));
         unsigned long long* cnt = f->pass_counters.as<unsigned long long>();
         SR_CUDA(ctx, cudaMemsetAsync(cnt, 0, 16 * sizeof(uint64_t), ctx->stream));
         const int sgrid = (int)std::min<int64_t>(f->stream_grid, (n + srd::STREAM_TILE - 1) / srd::STREAM_TILE);

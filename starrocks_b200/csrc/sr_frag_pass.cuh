@@ -37,23 +37,99 @@ __device__ __forceinline__ bool join_hit_global(const FragJoinDev& fj, int64_t k
     return join_lookup(fj.j, key) != 0;
 }
 
+__device__ __forceinline__ uint32_t ldg_u32_pred(const uint32_t* p, bool pred) {
+    uint32_t r;
+    asm volatile(
+            "{ .reg .pred q; setp.ne.u32 q, %2, 0; mov.u32 %0, 0;\n"
+            "  @q ld.global.nc.u32 %0, [%1]; }"
+            : "=r"(r)
+            : "l"(p), "r"((uint32_t)pred));
+    return r;
+}
+
+// Test N keys (bit i of `alive` says whether key i is still wanted) against one join and clear the bits of
+// the misses.  For bitmap joins the N word fetches are issued back to back (predicated, branch-free) so a
+// thread pays one L2 round trip for its whole group instead of one per row.
+template <int N, typename K>
+__device__ __forceinline__ uint32_t join_test_batch(const FragJoinDev& fj, const uint32_t* smem, const K (&keys)[N], uint32_t alive) {
+    if (fj.use_bitmap) {
+        const int64_t mn = fj.j.min_value, mx = fj.j.max_value;
+        uint32_t words[N];
+        uint32_t want = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const bool p = ((alive >> i) & 1u) && keys[i] >= mn && keys[i] <= mx;
+            const uint64_t idx = (uint64_t)(keys[i] - mn);
+            want |= (p ? 1u : 0u) << i;
+            if (fj.smem_off >= 0)
+                words[i] = p ? smem[fj.smem_off + (idx >> 5)] : 0u;
+            else
+                words[i] = ldg_u32_pred(fj.j.bitmap + (idx >> 5), p);
+        }
+        uint32_t out = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const uint64_t idx = (uint64_t)(keys[i] - mn);
+            out |= (((want >> i) & 1u) & (words[i] >> (idx & 31))) << i;
+        }
+        return out;
+    }
+    uint32_t out = alive;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        if (((alive >> i) & 1u) && join_lookup(fj.j, keys[i]) == 0) out &= ~(1u << i);
+    return out;
+}
+
 constexpr int STREAM_BLOCK = 512;
 constexpr int STREAM_ROWS = 4;
 constexpr int STREAM_GROUPS = 2;
 constexpr int STREAM_TILE = STREAM_BLOCK * STREAM_ROWS * STREAM_GROUPS;
 constexpr int STREAM_MAX_JOINS = 2;
 
-// append the rows flagged in `alive` (bit i -> row base_i + (i & 3)) to sel_out
-__device__ __forceinline__ void warp_append_rows(uint32_t alive_all, int64_t row0_g0, int64_t row0_g1, uint32_t* __restrict__ sel_out,
-                                                 unsigned long long* __restrict__ counter) {
+// Selection vectors are written through a per-warp chunk allocator: a warp takes SEL_CHUNK entries at a
+// time from the global counter (one same-address atomic per ~SEL_CHUNK survivors instead of one per
+// tile -- same-address atomics serialise in L2) and pads what it leaves unused with SEL_INVALID, which
+// the consuming pass skips.  The counter therefore counts allocated entries, valid or not.
+#define SEL_INVALID 0xFFFFFFFFu
+constexpr uint32_t SEL_CHUNK = 256;
+
+struct WarpSelWriter {
+    uint32_t* __restrict__ out;
+    unsigned long long* __restrict__ counter;
+    unsigned long long pos, end; // warp-uniform
+    __device__ __forceinline__ void init(uint32_t* o, unsigned long long* c) {
+        out = o;
+        counter = c;
+        pos = end = 0;
+    }
+    // reserve `total` (<= SEL_CHUNK, warp-uniform) entries, returns the start index
+    __device__ __forceinline__ unsigned long long reserve(uint32_t total) {
+        if (pos + total > end) {
+            for (unsigned long long i = pos + lane_id(); i < end; i += 32) out[i] = SEL_INVALID;
+            unsigned long long base = 0;
+            if (lane_id() == 0) base = atomicAdd(counter, (unsigned long long)SEL_CHUNK);
+            pos = __shfl_sync(SR_FULL_MASK, base, 0);
+            end = pos + SEL_CHUNK;
+        }
+        const unsigned long long p = pos;
+        pos += total;
+        return p;
+    }
+    __device__ __forceinline__ void finish() {
+        for (unsigned long long i = pos + lane_id(); i < end; i += 32) out[i] = SEL_INVALID;
+        pos = end;
+    }
+};
+
+// append the rows flagged in `alive` (bit i -> row base_i + (i & 3)) to the selection vector
+__device__ __forceinline__ void warp_append_rows(uint32_t alive_all, int64_t row0_g0, int64_t row0_g1, WarpSelWriter& w) {
     const uint32_t cnt = __popc(alive_all);
     const uint32_t incl = warp_incl_scan(cnt);
     const uint32_t total = __shfl_sync(SR_FULL_MASK, incl, 31);
     if (total == 0) return;
-    unsigned long long base = 0;
-    if (lane_id() == 0) base = atomicAdd(counter, (unsigned long long)total);
-    base = __shfl_sync(SR_FULL_MASK, base, 0);
-    unsigned long long pos = base + incl - cnt;
+    uint32_t* __restrict__ sel_out = w.out;
+    unsigned long long pos = w.reserve(total) + incl - cnt;
 #pragma unroll
     for (int i = 0; i < STREAM_GROUPS * STREAM_ROWS; i++) {
         if ((alive_all >> i) & 1u) {
@@ -107,6 +183,8 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream(const FragDev* 
         }
     };
     prefetch(blockIdx.x);
+    WarpSelWriter writer;
+    writer.init(sel_out, counter);
 
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int64_t row0[STREAM_GROUPS];
@@ -120,26 +198,14 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream(const FragDev* 
                 if (row0[g] + r < n) alive[g] |= 1u << r;
         }
         if (fast && tile < full_tiles) {
-            int32_t k1[STREAM_GROUPS][STREAM_ROWS];
-#pragma unroll
-            for (int g = 0; g < STREAM_GROUPS; g++) {
-                const int32_t k0[STREAM_ROWS] = {pk[0][g].x, pk[0][g].y, pk[0][g].z, pk[0][g].w};
-                k1[g][0] = pk[1][g].x;
-                k1[g][1] = pk[1][g].y;
-                k1[g][2] = pk[1][g].z;
-                k1[g][3] = pk[1][g].w;
-#pragma unroll
-                for (int r = 0; r < STREAM_ROWS; r++)
-                    if (!frag_join_hit(s_joins[0], smem, (int64_t)k0[r])) alive[g] &= ~(1u << r);
-            }
-            prefetch(tile + gridDim.x);
-            if (two) {
-#pragma unroll
-                for (int g = 0; g < STREAM_GROUPS; g++)
-#pragma unroll
-                    for (int r = 0; r < STREAM_ROWS; r++)
-                        if ((alive[g] & (1u << r)) && !frag_join_hit(s_joins[1], smem, (int64_t)k1[g][r])) alive[g] &= ~(1u << r);
-            }
+            static_assert(STREAM_GROUPS == 2 && STREAM_ROWS == 4, "8 keys per thread and column");
+            const int32_t k0[8] = {pk[0][0].x, pk[0][0].y, pk[0][0].z, pk[0][0].w, pk[0][1].x, pk[0][1].y, pk[0][1].z, pk[0][1].w};
+            const int32_t k1[8] = {pk[1][0].x, pk[1][0].y, pk[1][0].z, pk[1][0].w, pk[1][1].x, pk[1][1].y, pk[1][1].z, pk[1][1].w};
+            prefetch(tile + gridDim.x); // next tile's keys stay in flight while this tile is tested
+            uint32_t a8 = join_test_batch<8>(s_joins[0], smem, k0, 0xFFu);
+            if (two) a8 = join_test_batch<8>(s_joins[1], smem, k1, a8);
+            alive[0] = a8 & 0xFu;
+            alive[1] = a8 >> 4;
         } else {
             int64_t vals[STREAM_GROUPS][STREAM_ROWS];
             uint32_t nullmask[STREAM_GROUPS];
@@ -183,8 +249,9 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream(const FragDev* 
             }
         }
         static_assert(STREAM_GROUPS == 2, "two groups of alive bits are packed into one word");
-        warp_append_rows(alive[0] | (alive[1] << STREAM_ROWS), row0[0], row0[1], sel_out, counter);
+        warp_append_rows(alive[0] | (alive[1] << STREAM_ROWS), row0[0], row0[1], writer);
     }
+    writer.finish();
 }
 
 constexpr int GATHER_BLOCK = 256;
@@ -200,25 +267,26 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_join(const FragDev
     const unsigned long long n_in = *n_in_ptr;
     const FragJoinDev& fj = s_join;
     const VDesc& d = vt.v[fj.key_value_id];
+    WarpSelWriter writer;
+    writer.init(sel_out, counter_out);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x; i0 < n_in; i0 += stride) {
         const unsigned long long i = i0 + threadIdx.x;
         bool hit = false;
-        uint32_t row = 0;
-        if (i < n_in) {
-            row = sel_in[i];
+        uint32_t row = SEL_INVALID;
+        if (i < n_in) row = sel_in[i];
+        if (row != SEL_INVALID) {
             const int64_t key = load_int(d.data, d.type, (int64_t)row);
             const bool nul = d.nulls != nullptr && d.nulls[row] != 0;
             hit = !nul && join_hit_global(fj, key); // global bitmap copy: L1/L2 resident
         }
         const uint32_t m = __ballot_sync(SR_FULL_MASK, hit);
         if (m) {
-            unsigned long long base = 0;
-            if (lane_id() == 0) base = atomicAdd(counter_out, (unsigned long long)__popc(m));
-            base = __shfl_sync(SR_FULL_MASK, base, 0);
+            const unsigned long long base = writer.reserve(__popc(m));
             if (hit) sel_out[base + __popc(m & lanemask_lt())] = row;
         }
     }
+    writer.finish();
 }
 
 // final pass: remaining joins inline, payload lookups, aggregate update
@@ -245,6 +313,7 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg(const FragDev*
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
         const uint32_t row = sel_in[i];
+        if (row == SEL_INVALID) continue;
         FragLoader ld{vt, (int64_t)row, {0, 0, 0, 0, 0, 0}};
         bool ok = true;
 #pragma unroll 1
