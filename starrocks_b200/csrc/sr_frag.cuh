@@ -152,6 +152,7 @@ static int32_t frag_compile(sr_fragment* f) {
         h.joins[j].use_bitmap = jn->method != SR_JOIN_METHOD_LINEAR_CHAINED ? 1 : 0;
         h.joins[j].bitmap_words = (int32_t)((std::max<int64_t>(jn->bucket_size, 1) + 31) / 32);
         h.joins[j].need_head = 0;
+        h.joins[j].idx32 = (h.joins[j].use_bitmap && jn->min_value >= INT32_MIN && jn->max_value <= INT32_MAX && jn->max_value >= jn->min_value) ? 1 : 0;
         f->order[j] = j;
     }
     // aggregate (its expressions may reference fact slots and payload slots)

@@ -12,7 +12,7 @@ struct FragJoinDev {
     int32_t bitmap_words;
     int32_t use_bitmap; // range-mapped table: test the bitmap; otherwise probe the hash table
     int32_t need_head;  // a payload column of this join is read downstream
-    int32_t pad;
+    int32_t idx32;      // bitmap join whose [min, max] fits int32: 32-bit index arithmetic is exact
 };
 
 struct FragDev {

@@ -52,6 +52,37 @@ __device__ __forceinline__ uint32_t ldg_u32_pred(const uint32_t* p, bool pred) {
 // thread pays one L2 round trip for its whole group instead of one per row.
 template <int N, typename K>
 __device__ __forceinline__ uint32_t join_test_batch(const FragJoinDev& fj, const uint32_t* smem, const K (&keys)[N], uint32_t alive) {
+    if (sizeof(K) == 4 && fj.use_bitmap && fj.idx32) {
+        // int32 keys against a table whose [min, max] fits int32: one unsigned subtract + compare does the
+        // range check, and the whole test stays in 32-bit arithmetic (the stream kernel is issue bound)
+        const uint32_t umin = (uint32_t)(int32_t)fj.j.min_value;
+        const uint32_t span = (uint32_t)(fj.j.max_value - fj.j.min_value);
+        uint32_t out = 0;
+        if (fj.smem_off >= 0) {
+            const uint32_t* bm = smem + fj.smem_off;
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                const uint32_t idx = (uint32_t)keys[i] - umin;
+                const bool p = ((alive >> i) & 1u) && idx <= span;
+                const uint32_t word = p ? bm[idx >> 5] : 0u;
+                out |= ((word >> (idx & 31)) & 1u) << i;
+            }
+        } else {
+            uint32_t words[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                const uint32_t idx = (uint32_t)keys[i] - umin;
+                const bool p = ((alive >> i) & 1u) && idx <= span;
+                words[i] = ldg_u32_pred(fj.j.bitmap + (idx >> 5), p);
+            }
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                const uint32_t idx = (uint32_t)keys[i] - umin;
+                out |= ((words[i] >> (idx & 31)) & 1u) << i;
+            }
+        }
+        return out;
+    }
     if (fj.use_bitmap) {
         const int64_t mn = fj.j.min_value, mx = fj.j.max_value;
         uint32_t words[N];
@@ -192,10 +223,16 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream(const FragDev* 
 #pragma unroll
         for (int g = 0; g < STREAM_GROUPS; g++) {
             row0[g] = tile * STREAM_TILE + (int64_t)g * (STREAM_BLOCK * STREAM_ROWS) + (int64_t)threadIdx.x * STREAM_ROWS;
-            alive[g] = 0;
+            alive[g] = 0xFu;
+        }
+        if (tile >= full_tiles) { // only the last tile can be ragged
 #pragma unroll
-            for (int r = 0; r < STREAM_ROWS; r++)
-                if (row0[g] + r < n) alive[g] |= 1u << r;
+            for (int g = 0; g < STREAM_GROUPS; g++) {
+                alive[g] = 0;
+#pragma unroll
+                for (int r = 0; r < STREAM_ROWS; r++)
+                    if (row0[g] + r < n) alive[g] |= 1u << r;
+            }
         }
         if (fast && tile < full_tiles) {
             static_assert(STREAM_GROUPS == 2 && STREAM_ROWS == 4, "8 keys per thread and column");
