@@ -241,9 +241,48 @@ __device__ __forceinline__ long long agg_find_slot(const AggDev& a, Loader& ld) 
     return -1;
 }
 
-template <typename Loader>
+// shared-memory accumulators: explicit .shared reductions (a generic-address atomic on a shared
+// location is far slower than red.shared)
+__device__ __forceinline__ void red_shared_add_u64(long long* p, unsigned long long v) {
+    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "l"(v) : "memory");
+}
+__device__ __forceinline__ void acc_apply_shared(int32_t mode, long long* a0, long long* a1, long long slot, long long bits) {
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(a0 + slot);
+    switch (mode) {
+    case M_COUNT:
+        asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(s0), "l"(1ull) : "memory");
+        break;
+    case M_SUM_I64:
+        asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(s0), "l"((unsigned long long)bits) : "memory");
+        break;
+    case M_SUM_F64:
+    case M_AVG:
+        asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(s0), "d"(__longlong_as_double(bits)) : "memory");
+        break;
+    case M_MIN_I64:
+        asm volatile("red.shared.min.s64 [%0], %1;" ::"r"(s0), "l"(bits) : "memory");
+        break;
+    case M_MAX_I64:
+        asm volatile("red.shared.max.s64 [%0], %1;" ::"r"(s0), "l"(bits) : "memory");
+        break;
+    case M_MIN_F64:
+        asm volatile("red.shared.min.s64 [%0], %1;" ::"r"(s0), "l"(f64_sortable(__longlong_as_double(bits))) : "memory");
+        break;
+    case M_MAX_F64:
+        asm volatile("red.shared.max.s64 [%0], %1;" ::"r"(s0), "l"(f64_sortable(__longlong_as_double(bits))) : "memory");
+        break;
+    default: // M_SUM_I128 needs the old value for the carry
+        acc_apply(mode, a0, a1, slot, bits);
+        break;
+    }
+}
+
+template <bool SHARED = false, typename Loader>
 __device__ __forceinline__ void agg_apply_row(const AggDev& a, const AccPtrs& p, long long slot, Loader& ld) {
-    atomicAdd((unsigned long long*)p.cnt + slot, 1ull);
+    if (SHARED)
+        red_shared_add_u64(p.cnt + slot, 1ull);
+    else
+        atomicAdd((unsigned long long*)p.cnt + slot, 1ull);
 #pragma unroll 1
     for (int f = 0; f < a.num_fns; f++) {
         const AggFnDev& fn = a.fns[f];
@@ -251,8 +290,13 @@ __device__ __forceinline__ void agg_apply_row(const AggDev& a, const AccPtrs& p,
         int64_t bits;
         const bool nul = eval_expr(fn.input, ld, bits);
         if (nul) continue;
-        acc_apply(fn.mode, p.acc0[f], p.acc1[f], slot, bits);
-        if (fn.track_n) atomicAdd((unsigned long long*)p.accn[f] + slot, 1ull);
+        if (SHARED) {
+            acc_apply_shared(fn.mode, p.acc0[f], p.acc1[f], slot, bits);
+            if (fn.track_n) red_shared_add_u64(p.accn[f] + slot, 1ull);
+        } else {
+            acc_apply(fn.mode, p.acc0[f], p.acc1[f], slot, bits);
+            if (fn.track_n) atomicAdd((unsigned long long*)p.accn[f] + slot, 1ull);
+        }
     }
 }
 
@@ -342,7 +386,7 @@ __global__ void __launch_bounds__(AGG_BLOCK) k_agg_push(const AggDev* __restrict
             slots_out[row] = slot;
             continue;
         }
-        if (slot >= 0) agg_apply_row(a, p, slot, ld);
+        if (slot >= 0) agg_apply_row<SMEM>(a, p, slot, ld);
     }
     if (SMEM) {
         __syncthreads();

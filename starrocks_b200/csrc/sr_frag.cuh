@@ -65,6 +65,7 @@ struct sr_fragment {
     DevBuf sel[2], pass_counters;
     size_t stream_smem = 0;
     int stream_grid = 0;
+    int final_grid = 0;
 };
 
 struct FragTypeCtx {
@@ -250,9 +251,32 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
         // trailing joins that filter (almost) nothing are tested inline by the final pass
         int ff = f->num_joins;
         while (ff > ns && f->pass_rate[ord[ff - 1]] >= 0.9) ff--;
+        memset(&f->pass, 0, sizeof(f->pass));
         f->pass.num_stream_joins = ns;
         f->pass.final_first_join = ff;
-        f->pass.pad0 = f->pass.pad1 = 0;
+        // fact values the final pass reads: keys of the joins it looks up or tests, group keys, aggregate inputs
+        {
+            std::vector<int> need;
+            auto want = [&](int id) {
+                if (id >= 0 && id < (int)f->value_src.size() && f->value_src[id] < 0 && std::find(need.begin(), need.end(), id) == need.end()) need.push_back(id);
+            };
+            for (int q = 0; q < f->num_joins; q++)
+                if (h.joins[q].need_head || q >= ff) want(h.joins[q].key_value_id);
+            const srd::AggDev& ah = f->agg->host;
+            for (int k = 0; k < ah.num_keys; k++) want(ah.key_value_id[k]);
+            for (int q = 0; q < ah.num_fns; q++)
+                for (int k = 0; k < ah.fns[q].input.num_nodes; k++)
+                    if (ah.fns[q].input.nodes[k].op == srd::C_LOAD_I || ah.fns[q].input.nodes[k].op == srd::C_LOAD_D) want(ah.fns[q].input.nodes[k].arg);
+            for (int k = 0; k < SR_FINAL_PREFETCH; k++) f->pass.final_vals[k] = -1;
+            for (int k = 0; k < SR_MAX_VALUES; k++) f->pass.final_slot[k] = -1;
+            // measured on B200 (profiles/r1_notes.md): the burst costs more issue slots and registers than the
+            // latency it hides -- the final pass is L1TEX-gather bound, not latency bound -- so it stays off
+            const bool kFinalPrefetch = false;
+            for (size_t k = 0; kFinalPrefetch && k < need.size() && k < SR_FINAL_PREFETCH; k++) {
+                f->pass.final_vals[k] = (int8_t)need[k];
+                f->pass.final_slot[need[k]] = (int8_t)k;
+            }
+        }
         f->gather_joins.clear();
         for (int q = ns; q < ff; q++) f->gather_joins.push_back(q);
         // streaming pass shared memory: bitmaps of the streamed joins only
@@ -277,7 +301,15 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
         SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, srd::k_frag_stream, srd::STREAM_BLOCK, f->stream_smem));
         if (per_sm < 1) return sr_fail(ctx, SR_ERR_CUDA, "streaming pass does not fit on an SM (smem %zu)", f->stream_smem);
         f->stream_grid = per_sm * ctx->num_sms;
-        f->grid = ctx->num_sms * 8;
+        // gather passes: exactly one wave of resident CTAs (grid-stride loops; a partial second wave only adds a tail)
+        int gj = 0, ga = 0;
+        SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gj, srd::k_frag_gather_join, srd::GATHER_BLOCK, 0));
+        if (f->smem_agg)
+            SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ga, srd::k_frag_gather_agg<true>, srd::GATHER_BLOCK, f->agg->smem_bytes));
+        else
+            SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ga, srd::k_frag_gather_agg<false>, srd::GATHER_BLOCK, 0));
+        f->grid = std::max(gj, 1) * ctx->num_sms;
+        f->final_grid = std::max(ga, 1) * ctx->num_sms;
         SR_TRY(f->pass_counters.reserve(ctx, 16 * sizeof(uint64_t)));
         f->compiled = true;
         return SR_OK;
@@ -363,10 +395,10 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
             k++;
         }
         if (f->smem_agg)
-            srd::k_frag_gather_agg<true><<<f->grid, srd::GATHER_BLOCK, a->smem_bytes, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, f->pass, vt,
+            srd::k_frag_gather_agg<true><<<f->final_grid, srd::GATHER_BLOCK, a->smem_bytes, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, f->pass, vt,
                                                                                                    f->sel[cur].as<uint32_t>(), cnt + k);
         else
-            srd::k_frag_gather_agg<false><<<f->grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, f->pass, vt,
+            srd::k_frag_gather_agg<false><<<f->final_grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, f->pass, vt,
                                                                                         f->sel[cur].as<uint32_t>(), cnt + k);
         SR_LAUNCH_CHECK(ctx);
         if (hash) {

@@ -40,7 +40,18 @@ struct FragLoader {
     const VTab& vt;
     int64_t row;
     uint32_t bidx[SR_MAX_FRAG_JOINS];
+    // optional: fact values fetched ahead of time by the caller (final pass) -- pslot[id] = index into pv or -1
+    const int64_t* pv;
+    const int8_t* pslot;
+    uint32_t pnull;
     __device__ __forceinline__ bool load(int id, int64_t& bits) const {
+        if (pslot) {
+            const int q = pslot[id];
+            if (q >= 0) {
+                bits = pv[q];
+                return (pnull >> q) & 1u;
+            }
+        }
         const VDesc& d = vt.v[id];
         if (d.src < 0) {
             const bool nul = d.nulls != nullptr && d.nulls[row] != 0;
@@ -129,6 +140,7 @@ struct Cascade {
     uint32_t* qc;             // this warp's fill counts
     int S, NQ;
     int eager1;
+    int shared_acc; // the accumulators live in shared memory
     uint32_t lane;
     unsigned long long passed;
 
@@ -171,7 +183,12 @@ struct Cascade {
                 }
             }
             const long long slot = agg_find_slot(ad, ld);
-            if (slot >= 0) agg_apply_row(ad, acc, slot, ld);
+            if (slot >= 0) {
+                if (shared_acc)
+                    agg_apply_row<true>(ad, acc, slot, ld);
+                else
+                    agg_apply_row<false>(ad, acc, slot, ld);
+            }
             passed++;
         }
     }
@@ -269,7 +286,7 @@ __global__ void __launch_bounds__(FRAG_BLOCK, 2) k_fragment(const FragDev* __res
     }
 
     // queue k feeds join k+1 (k+1 < S) or the aggregate (the last queue)
-    Cascade cs{vt, ad, acc, s_joins, smem, wq, wq + (SR_MAX_FRAG_JOINS + 1) * FRAG_QCAP, S, S > 1 ? S : 1, fast1 ? 1 : 0, lane_id(), 0ull};
+    Cascade cs{vt, ad, acc, s_joins, smem, wq, wq + (SR_MAX_FRAG_JOINS + 1) * FRAG_QCAP, S, S > 1 ? S : 1, fast1 ? 1 : 0, SMEM_AGG ? 1 : 0, lane_id(), 0ull};
 
     const int64_t num_tiles = (n + FRAG_TILE - 1) / FRAG_TILE;
     const int64_t full_tiles = n / FRAG_TILE; // tiles [0, full_tiles) have every row in range

@@ -24,8 +24,13 @@ namespace srd {
 struct PassDev {
     int32_t num_stream_joins; // joins [0, num_stream_joins) are tested by the streaming pass
     int32_t final_first_join; // joins [final_first_join, S) are tested inline by the final pass
-    int32_t pad0, pad1;
+    // fact columns the final pass reads: fetched for a row in one burst before anything depends on them
+    int8_t final_vals[8];              // value ids, -1 = unused
+    int8_t final_slot[SR_MAX_VALUES];  // value id -> index into final_vals, -1 = not prefetched
+    int8_t pad[4];
 };
+
+#define SR_FINAL_PREFETCH 8
 
 // bitmap / hash test against the global copies only (gather passes do not stage bitmaps)
 __device__ __forceinline__ bool join_hit_global(const FragJoinDev& fj, int64_t key) {
@@ -328,7 +333,7 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_join(const FragDev
 
 // final pass: remaining joins inline, payload lookups, aggregate update
 template <bool SMEM_AGG>
-__global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg(const FragDev* __restrict__ fdp, const AggDev* __restrict__ adp, PassDev pd,
+__global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg(const FragDev* __restrict__ fdp, const AggDev* __restrict__ adp, const __grid_constant__ PassDev pd,
                                                                    const __grid_constant__ VTab vt, const uint32_t* __restrict__ sel_in,
                                                                    const unsigned long long* __restrict__ n_in_ptr) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -351,6 +356,8 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg(const FragDev*
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
         const uint32_t row = sel_in[i];
         if (row == SEL_INVALID) continue;
+        // (a variant that fetched every fact value of the row in one burst before the dependent lookups was
+        // measured slower on B200 -- more issue slots and registers than latency hidden, see profiles/)
         FragLoader ld{vt, (int64_t)row, {0, 0, 0, 0, 0, 0}};
         bool ok = true;
 #pragma unroll 1
@@ -374,7 +381,7 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg(const FragDev*
         }
         if (!ok) continue;
         const long long slot = agg_find_slot(ad, ld);
-        if (slot >= 0) agg_apply_row(ad, acc, slot, ld);
+        if (slot >= 0) agg_apply_row<SMEM_AGG>(ad, acc, slot, ld);
         passed++;
     }
     if (SMEM_AGG) {
