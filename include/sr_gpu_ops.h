@@ -456,6 +456,10 @@ typedef struct sr_fragment_plan {
     double pred_rate; /* fraction of sampled rows passing the scan conjuncts */
 } sr_fragment_plan;
 int32_t sr_fragment_get_plan(sr_fragment* frag, sr_fragment_plan* plan);
+/* device time of the passes of the LAST push in selection-vector mode (CUDA events on the context's
+ * stream; synchronises): ms[0] = streaming pass, ms[1] = gather-join passes, ms[2] = final pass.
+ * Returns SR_ERR_STATE when the last push did not run in that mode. */
+int32_t sr_fragment_last_pass_ms(sr_fragment* frag, float ms[3]);
 /* reset_state for the whole fragment: clears its aggregate and the rows_passed counter. */
 int32_t sr_fragment_reset(sr_fragment* frag);
 /* rows that survived scan predicates and all joins so far (synchronises). */

@@ -66,6 +66,12 @@ struct sr_fragment {
     size_t stream_smem = 0;
     int stream_grid = 0;
     int final_grid = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool timed_push = false;
+    ~sr_fragment() {
+        for (int e = 0; e < 4; e++)
+            if (ev[e]) cudaEventDestroy(ev[e]);
+    }
 };
 
 struct FragTypeCtx {
@@ -384,8 +390,13 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
         unsigned long long* cnt = f->pass_counters.as<unsigned long long>();
         SR_CUDA(ctx, cudaMemsetAsync(cnt, 0, 16 * sizeof(uint64_t), ctx->stream));
         const int sgrid = (int)std::min<int64_t>(f->stream_grid, (n + srd::STREAM_TILE - 1) / srd::STREAM_TILE);
+        // pass boundaries are bracketed with CUDA events (bench.py reads them back as per-kernel durations)
+        if (!f->ev[0])
+            for (int e = 0; e < 4; e++) SR_CUDA(ctx, cudaEventCreate(&f->ev[e]));
+        SR_CUDA(ctx, cudaEventRecord(f->ev[0], ctx->stream));
         srd::k_frag_stream<<<sgrid, srd::STREAM_BLOCK, f->stream_smem, ctx->stream>>>(fdev, f->pass, vt, n, f->sel[0].as<uint32_t>(), cnt);
         SR_LAUNCH_CHECK(ctx);
+        SR_CUDA(ctx, cudaEventRecord(f->ev[1], ctx->stream));
         int cur = 0, k = 0;
         for (int q : f->gather_joins) {
             srd::k_frag_gather_join<<<f->grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, q, vt, f->sel[cur].as<uint32_t>(), cnt + k,
@@ -394,6 +405,7 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
             cur ^= 1;
             k++;
         }
+        SR_CUDA(ctx, cudaEventRecord(f->ev[2], ctx->stream));
         if (f->smem_agg)
             srd::k_frag_gather_agg<true><<<f->final_grid, srd::GATHER_BLOCK, a->smem_bytes, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, f->pass, vt,
                                                                                                    f->sel[cur].as<uint32_t>(), cnt + k);
@@ -401,6 +413,8 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
             srd::k_frag_gather_agg<false><<<f->final_grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, f->pass, vt,
                                                                                         f->sel[cur].as<uint32_t>(), cnt + k);
         SR_LAUNCH_CHECK(ctx);
+        SR_CUDA(ctx, cudaEventRecord(f->ev[3], ctx->stream));
+        f->timed_push = true;
         if (hash) {
             uint64_t ng;
             int32_t ovf, bad;

@@ -707,6 +707,16 @@ int32_t sr_fragment_get_plan(sr_fragment* frag, sr_fragment_plan* plan) {
     return SR_OK;
 }
 
+int32_t sr_fragment_last_pass_ms(sr_fragment* frag, float ms[3]) {
+    if (!frag || !ms) return SR_ERR_INVALID_ARGUMENT;
+    sr_ctx* ctx = frag->ctx;
+    SR_BIND(ctx);
+    if (!frag->timed_push) return sr_fail(ctx, SR_ERR_STATE, "no timed push (selection-vector mode only)");
+    SR_CUDA(ctx, cudaEventSynchronize(frag->ev[3]));
+    for (int k = 0; k < 3; k++) SR_CUDA(ctx, cudaEventElapsedTime(&ms[k], frag->ev[k], frag->ev[k + 1]));
+    return SR_OK;
+}
+
 int32_t sr_fragment_reset(sr_fragment* frag) {
     if (!frag) return SR_ERR_INVALID_ARGUMENT;
     sr_ctx* ctx = frag->ctx;

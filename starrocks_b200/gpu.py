@@ -79,6 +79,7 @@ def lib():
         "sr_agg_reset": (i32, [vp]),
         "sr_fragment_reset": (i32, [vp]),
         "sr_fragment_get_plan": (i32, [vp, vp]),
+        "sr_fragment_last_pass_ms": (i32, [vp, vp]),
         "sr_fragment_create": (vp, [vp, vp]),
         "sr_fragment_destroy": (None, [vp]),
         "sr_fragment_push": (i32, [vp, vp]),
@@ -110,7 +111,7 @@ EXPORTED_SYMBOLS = [
     "sr_scan_filter", "sr_scan_evaluate", "sr_join_create", "sr_join_destroy", "sr_join_append_build",
     "sr_join_build_finish", "sr_join_is_build_done", "sr_join_get_info", "sr_join_copy_table", "sr_join_probe",
     "sr_join_probe_indexes", "sr_join_key_hash", "sr_agg_create", "sr_agg_destroy", "sr_agg_push",
-    "sr_agg_sink_finish", "sr_agg_num_groups", "sr_agg_pull", "sr_agg_merge", "sr_agg_reset", "sr_fragment_reset", "sr_fragment_get_plan",
+    "sr_agg_sink_finish", "sr_agg_num_groups", "sr_agg_pull", "sr_agg_merge", "sr_agg_reset", "sr_fragment_reset", "sr_fragment_get_plan", "sr_fragment_last_pass_ms",
     "sr_fragment_create",
     "sr_fragment_destroy", "sr_fragment_push", "sr_fragment_agg", "sr_fragment_rows_passed", "sr_xchg_create",
     "sr_xchg_destroy", "sr_xchg_partition", "sr_xchg_hash", "sr_gather", "sr_memcpy", "sr_abi_sizeof", "sr_bandwidth_probe", "sr_flush_l2",
@@ -351,6 +352,15 @@ class Fragment:
 
     def reset(self):
         self.ctx.check(lib().sr_fragment_reset(self.h))
+
+    def last_pass_ms(self):
+        """device ms of the (stream, gather-join, final) passes of the last push; None in fused-cascade mode"""
+        ms = (C.c_float * 3)()
+        rc = lib().sr_fragment_last_pass_ms(self.h, ms)
+        if rc == abi.SR_ERR_STATE:
+            return None
+        self.ctx.check(rc)
+        return [float(x) for x in ms]
 
     def plan(self):
         p = abi.sr_fragment_plan()
