@@ -440,26 +440,22 @@ def run_gpu(args):
 
 
 def step_tail(frag, final, ctx, gpu, abi, ssb, torch, dist, dev, world, rank, MAXG):
-    """N > 1 tail of a step: pull partial states on the device, gather to rank 0 over NCCL, final merge."""
+    """N > 1 tail of a step: pull partial states on the device, gather to rank 0 over NCCL (the UNPARTITIONED exchange of
+    the two-phase aggregate), final merge by a GPU aggregate on rank 0."""
+    from starrocks_b200.distributed import gather_partial_states
     out = frag.agg.pull(mem=abi.MEM_DEVICE)
     g = out.num_rows
-    part = torch.zeros((4, MAXG), dtype=torch.int64, device=dev)
+    cols = []
     for k in range(4):
         w = abi.TYPE_WIDTH[out.cols[k].type]
         t = torch.empty(g, dtype=torch.int32 if w == 4 else torch.int64, device=dev)
         ctx.check(gpu.lib().sr_memcpy(ctx.h, t.data_ptr(), out.cols[k].data, g * w, 2))
-        part[k, :g] = t
-    cnt = torch.tensor([g], dtype=torch.int64, device=dev)
-    parts = [torch.empty_like(part) for _ in range(world)] if rank == 0 else None
-    cnts = [torch.empty_like(cnt) for _ in range(world)] if rank == 0 else None
-    dist.gather(part, parts, dst=0)
-    dist.gather(cnt, cnts, dst=0)
+        cols.append(t)
+    gathered = gather_partial_states(cols, MAXG, dst=0)
     if rank != 0:
         return None
     final.reset()
-    for p, c in zip(parts, cnts):
-        gg = int(c.item())
-        pc = p[:, :gg].contiguous()
+    for pc in gathered:
         ch = abi.Chunk([(ssb.D_YEAR, pc[0].to(torch.int32).contiguous(), None, abi.TYPE_INT),
                         (ssb.C_NATION, pc[1].to(torch.int32).contiguous(), None, abi.TYPE_INT),
                         (ssb.OUT_SUM_REVENUE, pc[2].contiguous(), None, abi.TYPE_BIGINT),

@@ -1,0 +1,229 @@
+// API-identical shim of the pipeline operator interface so the GPU operators can be exercised the way the BE's
+// PipelineDriver exercises them.  Names, signatures and contracts follow
+//   be/src/exec/pipeline/operator.h:44-352   (Operator), :354-456 (OperatorFactory)
+//   be/src/exec/pipeline/source_operator.h:37-189 (SourceOperator / SourceOperatorFactory)
+//   be/src/exec/pipeline/operator_with_dependency.h:41-49
+//   be/src/base/status.h, statusor.h (Status / StatusOr, RETURN_IF_ERROR)
+// In a real BE build these headers are the BE's own; only this directory's gpu/*.h would be added.
+#pragma once
+
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../column/chunk.h"
+
+namespace starrocks {
+
+class Status {
+public:
+    Status() = default;
+    static Status OK() { return Status(); }
+    static Status InternalError(std::string m) { return Status(1, std::move(m)); }
+    static Status InvalidArgument(std::string m) { return Status(2, std::move(m)); }
+    static Status NotSupported(std::string m) { return Status(3, std::move(m)); }
+    static Status MemoryLimitExceeded(std::string m) { return Status(4, std::move(m)); }
+    static Status EndOfFile(std::string m) { return Status(5, std::move(m)); }
+    bool ok() const { return _code == 0; }
+    bool is_end_of_file() const { return _code == 5; }
+    int code() const { return _code; }
+    const std::string& message() const { return _msg; }
+    std::string to_string() const { return ok() ? "OK" : _msg; }
+
+private:
+    Status(int c, std::string m) : _code(c), _msg(std::move(m)) {}
+    int _code = 0;
+    std::string _msg;
+};
+
+template <typename T>
+class StatusOr {
+public:
+    StatusOr(Status s) : _status(std::move(s)) {}
+    StatusOr(T v) : _value(std::move(v)) {}
+    bool ok() const { return _status.ok(); }
+    const Status& status() const { return _status; }
+    T& value() { return _value; }
+    T& operator*() { return _value; }
+
+private:
+    Status _status;
+    T _value{};
+};
+
+#define RETURN_IF_ERROR(stmt)          \
+    do {                               \
+        Status _s = (stmt);            \
+        if (!_s.ok()) return _s;       \
+    } while (0)
+
+// RuntimeState: only what the operators read (be/src/runtime/runtime_state.h:130 chunk_size = batch_size,
+// default vector_chunk_size 4096, be/src/common/config.h:915)
+class RuntimeState {
+public:
+    explicit RuntimeState(int chunk_size = 4096) : _chunk_size(chunk_size) {}
+    int chunk_size() const { return _chunk_size; }
+    bool is_cancelled() const { return _cancelled; }
+    void set_cancelled() { _cancelled = true; }
+
+private:
+    int _chunk_size;
+    bool _cancelled = false;
+};
+
+namespace pipeline {
+
+class OperatorFactory;
+
+class Operator {
+public:
+    Operator(OperatorFactory* factory, int32_t id, std::string name, int32_t plan_node_id, bool is_subordinate, int32_t driver_sequence)
+            : _factory(factory), _id(id), _name(std::move(name)), _plan_node_id(plan_node_id), _driver_sequence(driver_sequence) {
+        (void)is_subordinate;
+    }
+    virtual ~Operator() = default;
+
+    virtual Status prepare(RuntimeState* state) { return Status::OK(); }
+    virtual Status set_finishing(RuntimeState* state) { return Status::OK(); }
+    virtual Status set_finished(RuntimeState* state) { return Status::OK(); }
+    virtual Status set_cancelled(RuntimeState* state) { return Status::OK(); }
+    virtual void close(RuntimeState* state) {}
+
+    virtual bool has_output() const = 0;
+    virtual bool need_input() const = 0;
+    virtual bool is_finished() const = 0;
+    virtual bool pending_finish() const { return false; }
+
+    virtual StatusOr<ChunkPtr> pull_chunk(RuntimeState* state) = 0;
+    virtual Status push_chunk(RuntimeState* state, const ChunkPtr& chunk) = 0;
+
+    int32_t get_id() const { return _id; }
+    int32_t get_plan_node_id() const { return _plan_node_id; }
+    std::string get_raw_name() const { return _name; }
+    std::string get_name() const { return _name + "_" + std::to_string(_plan_node_id) + (is_finished() ? "(X)" : "(O)"); }
+
+protected:
+    OperatorFactory* _factory;
+    const int32_t _id;
+    const std::string _name;
+    const int32_t _plan_node_id;
+    const int32_t _driver_sequence;
+};
+using OperatorPtr = std::shared_ptr<Operator>;
+using Operators = std::vector<OperatorPtr>;
+
+class SourceOperator : public Operator {
+public:
+    using Operator::Operator;
+    bool need_input() const override { return false; }
+    Status push_chunk(RuntimeState* state, const ChunkPtr& chunk) override { return Status::InternalError("Shouldn't push chunk to source operator"); }
+};
+
+// be/src/exec/pipeline/operator_with_dependency.h:41-49
+class OperatorWithDependency : public Operator {
+public:
+    using Operator::Operator;
+    virtual bool is_ready() const = 0;
+};
+
+class OperatorFactory {
+public:
+    OperatorFactory(int32_t id, std::string name, int32_t plan_node_id) : _id(id), _name(std::move(name)), _plan_node_id(plan_node_id) {}
+    virtual ~OperatorFactory() = default;
+    virtual OperatorPtr create(int32_t degree_of_parallelism, int32_t driver_sequence) = 0;
+    virtual bool is_source() const { return false; }
+    int32_t id() const { return _id; }
+    int32_t plan_node_id() const { return _plan_node_id; }
+    virtual Status prepare(RuntimeState* state) { return Status::OK(); }
+    virtual void close(RuntimeState* state) {}
+    std::string get_name() const { return _name + "_(" + std::to_string(_plan_node_id) + ")"; }
+    virtual bool support_event_scheduler() const { return false; }
+
+protected:
+    const int32_t _id;
+    const std::string _name;
+    const int32_t _plan_node_id;
+};
+using OpFactoryPtr = std::shared_ptr<OperatorFactory>;
+using OpFactories = std::vector<OpFactoryPtr>;
+
+class SourceOperatorFactory : public OperatorFactory {
+public:
+    using OperatorFactory::OperatorFactory;
+    bool is_source() const override { return true; }
+    void set_degree_of_parallelism(size_t dop) { _degree_of_parallelism = dop; }
+    size_t degree_of_parallelism() const { return _degree_of_parallelism; }
+
+protected:
+    size_t _degree_of_parallelism = 1;
+};
+
+// The pull/push loop of PipelineDriver::process (be/src/exec/pipeline/pipeline_driver.cpp:270-500) for one driver:
+// for each adjacent pair, pull when the upstream has output and the downstream needs input, propagate finishing,
+// enforce the chunk_size limit (:372-378).  Returns when the sink is finished or no operator can make progress
+// (the real driver would park in the poller; tests call process() again after the dependency is released).
+class PipelineDriver {
+public:
+    explicit PipelineDriver(Operators ops) : _operators(std::move(ops)), _finishing_sent(_operators.size(), false) {}
+    enum State { READY, PRECONDITION_BLOCK, FINISH };
+
+    Status prepare(RuntimeState* state) {
+        for (auto& op : _operators) RETURN_IF_ERROR(op->prepare(state));
+        return Status::OK();
+    }
+
+    StatusOr<State> process(RuntimeState* state) {
+        const size_t n = _operators.size();
+        for (auto& op : _operators) {
+            auto* dep = dynamic_cast<OperatorWithDependency*>(op.get());
+            if (dep != nullptr && !dep->is_ready()) return PRECONDITION_BLOCK;
+        }
+        while (true) {
+            bool progressed = false;
+            for (size_t i = _first_unfinished; i + 1 < n; i++) {
+                auto& curr = _operators[i];
+                auto& next = _operators[i + 1];
+                if (curr->has_output() && next->need_input() && !next->is_finished()) {
+                    StatusOr<ChunkPtr> maybe = curr->pull_chunk(state);
+                    if (!maybe.ok() && !maybe.status().is_end_of_file()) return maybe.status();
+                    if (maybe.ok() && maybe.value() != nullptr && maybe.value()->num_rows() > 0) {
+                        if ((int)maybe.value()->num_rows() > state->chunk_size())
+                            return Status::InternalError("Intermediate chunk size must not be greater than " + std::to_string(state->chunk_size()) +
+                                                         ", actually " + std::to_string(maybe.value()->num_rows()) + " after " + curr->get_name());
+                        RETURN_IF_ERROR(next->push_chunk(state, maybe.value()));
+                        _rows_moved += maybe.value()->num_rows();
+                    }
+                    progressed = true;
+                }
+                if (curr->is_finished() && !_finishing_sent[i + 1]) { // :424-437
+                    RETURN_IF_ERROR(next->set_finishing(state));
+                    _finishing_sent[i + 1] = true;
+                    progressed = true;
+                }
+            }
+            while (_first_unfinished + 1 < n && _operators[_first_unfinished]->is_finished() && _finishing_sent[_first_unfinished + 1])
+                _first_unfinished++;
+            if (_operators.back()->is_finished()) {
+                for (auto& op : _operators) RETURN_IF_ERROR(op->set_finished(state));
+                return FINISH;
+            }
+            if (!progressed) return READY;
+        }
+    }
+
+    void close(RuntimeState* state) {
+        for (auto& op : _operators) op->close(state);
+    }
+    size_t rows_moved() const { return _rows_moved; }
+
+private:
+    Operators _operators;
+    std::vector<bool> _finishing_sent;
+    size_t _first_unfinished = 0;
+    size_t _rows_moved = 0;
+};
+
+} // namespace pipeline
+} // namespace starrocks

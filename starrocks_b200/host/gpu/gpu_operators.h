@@ -1,0 +1,543 @@
+// GPU drop-in operators for the StarRocks pipeline engine, written against the reference's Operator /
+// OperatorFactory interface (exec/pipeline/operator.h) and the C-ABI of libsr_gpu.so (include/sr_gpu_ops.h).
+//
+//   GpuScanOperator                      <- ScanOperator + OlapChunkSource filter step
+//                                           (exec/pipeline/scan/scan_operator.cpp:286-309, olap_chunk_source.cpp:676-722)
+//   GpuHashJoinBuildOperator             <- HashJoinBuildOperator   (exec/pipeline/hashjoin/hash_join_build_operator.cpp:41-220)
+//   GpuHashJoinProbeOperator             <- HashJoinProbeOperator   (exec/pipeline/hashjoin/hash_join_probe_operator.cpp:55-117)
+//   GpuAggregateBlockingSinkOperator     <- AggregateBlockingSinkOperator   (aggregate/aggregate_blocking_sink_operator.cpp:56-138)
+//   GpuAggregateBlockingSourceOperator   <- AggregateBlockingSourceOperator (aggregate/aggregate_blocking_source_operator.cpp:46-72)
+//   GpuFragmentSinkOperator              the fused form: the scan's downstream probes + aggregate sink collapsed into
+//                                           one sink that feeds sr_fragment_push ("keep the API, change
+//                                           the cadence")
+// Shared contexts mirror HashJoiner / Aggregator (exec/hash_joiner.h:191-330, exec/aggregator.h:253-637): one object
+// shared by the build and probe (sink and source) operators, ref-counted through shared_ptr.
+//
+// Cadence: the pipeline contract is <= chunk_size (4096) rows per chunk.  One kernel launch per 4096 rows is hopeless
+// on a GPU, so every operator accumulates `batch_chunks` input chunks (64, the IO-task batch of the reference's
+// ChunkSource, scan_operator.h:119) into one contiguous batch before calling the library, and slices device results
+// back into <= chunk_size chunks.  need_input() / has_output() expose exactly that buffering to the driver.
+#pragma once
+
+#include <deque>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../exec/pipeline/operator.h"
+
+namespace starrocks::pipeline {
+
+inline Status sr_to_status(sr_ctx* ctx, int32_t rc) {
+    if (rc == SR_OK) return Status::OK();
+    const std::string msg = std::string("sr_gpu: ") + sr_last_error(ctx);
+    switch (rc) {
+    case SR_ERR_INVALID_ARGUMENT:
+        return Status::InvalidArgument(msg);
+    case SR_ERR_NOT_SUPPORTED:
+        return Status::NotSupported(msg);
+    case SR_ERR_OUT_OF_MEMORY:
+        return Status::MemoryLimitExceeded(msg);
+    default:
+        return Status::InternalError(msg);
+    }
+}
+#define RETURN_IF_SR_ERROR(ctx, expr) RETURN_IF_ERROR(sr_to_status((ctx), (expr)))
+
+// contiguous accumulation of equal-schema host chunks (the batch handed to one library call)
+class ChunkBatch {
+public:
+    void append(const Chunk& c) {
+        if (_cols.empty()) {
+            for (size_t i = 0; i < c.num_columns(); i++) {
+                const Column& col = *c.get_column_by_index(i);
+                _cols.push_back(Col{c.slot_of_index(i), col.logical_type(), col.type_size(), col.is_nullable(), {}, {}});
+            }
+        }
+        const size_t n = c.num_rows();
+        for (size_t i = 0; i < _cols.size(); i++) {
+            Col& dst = _cols[i];
+            const Column& col = *c.get_column_by_slot_id(dst.slot);
+            const size_t old = dst.data.size();
+            dst.data.resize(old + n * dst.width);
+            memcpy(dst.data.data() + old, col.raw_data(), n * dst.width);
+            if (col.is_nullable() && !dst.nullable) { // upgrade like JoinHashTable::append_chunk does
+                dst.nullable = true;
+                dst.nulls.assign(_rows, 0);
+            }
+            if (dst.nullable) {
+                const size_t oldn = dst.nulls.size();
+                dst.nulls.resize(oldn + n, 0);
+                if (col.is_nullable()) memcpy(dst.nulls.data() + oldn, col.null_data(), n);
+            }
+        }
+        _rows += n;
+    }
+    size_t rows() const { return _rows; }
+    bool empty() const { return _rows == 0; }
+    void clear() {
+        for (auto& c : _cols) {
+            c.data.clear();
+            c.nulls.clear();
+        }
+        _rows = 0;
+    }
+    sr_chunk_view view() {
+        _views.clear();
+        for (auto& c : _cols) _views.push_back(sr_col_view{c.data.data(), c.nullable ? c.nulls.data() : nullptr, c.type, c.slot});
+        return sr_chunk_view{_views.data(), (int32_t)_views.size(), SR_MEM_HOST, (int64_t)_rows};
+    }
+
+private:
+    struct Col {
+        SlotId slot;
+        int32_t type;
+        size_t width;
+        bool nullable;
+        std::vector<uint8_t> data, nulls;
+    };
+    std::vector<Col> _cols;
+    std::vector<sr_col_view> _views;
+    size_t _rows = 0;
+};
+
+// device (or host) sr_chunk_out -> host Chunks of <= chunk_size rows appended to `queue`
+inline Status slice_out_to_chunks(sr_ctx* ctx, const sr_chunk_out& out, int chunk_size, std::deque<ChunkPtr>* queue) {
+    const int64_t n = out.num_rows;
+    if (n == 0) return Status::OK();
+    std::vector<ColumnPtr> cols(out.num_cols);
+    std::vector<std::shared_ptr<NullColumn>> nulls(out.num_cols);
+    for (int k = 0; k < out.num_cols; k++) {
+        const sr_col_out& c = out.cols[k];
+        cols[k] = make_column(c.type, (size_t)n);
+        const int64_t bytes = n * sr_type_width(c.type);
+        if (out.mem == SR_MEM_DEVICE)
+            RETURN_IF_SR_ERROR(ctx, sr_memcpy(ctx, cols[k]->mutable_raw_data(), c.data, bytes, 1));
+        else
+            memcpy(cols[k]->mutable_raw_data(), c.data, (size_t)bytes);
+        if (c.nulls != nullptr) {
+            nulls[k] = std::make_shared<NullColumn>(SR_TYPE_BOOLEAN);
+            nulls[k]->resize((size_t)n);
+            if (out.mem == SR_MEM_DEVICE)
+                RETURN_IF_SR_ERROR(ctx, sr_memcpy(ctx, nulls[k]->mutable_raw_data(), c.nulls, n, 1));
+            else
+                memcpy(nulls[k]->mutable_raw_data(), c.nulls, (size_t)n);
+        }
+    }
+    Chunk whole;
+    for (int k = 0; k < out.num_cols; k++) {
+        if (nulls[k])
+            whole.append_column(std::make_shared<NullableColumn>(cols[k], nulls[k]), out.cols[k].slot_id);
+        else
+            whole.append_column(cols[k], out.cols[k].slot_id);
+    }
+    for (int64_t off = 0; off < n; off += chunk_size) queue->push_back(whole.slice((size_t)off, (size_t)std::min<int64_t>(chunk_size, n - off)));
+    return Status::OK();
+}
+
+constexpr int kGpuBatchChunks = 64; // ScanOperator::_buffer_size / io task batch (scan_operator.h:119)
+
+// ------------------------------------------------------------------------------------------------------------
+// scan
+// ------------------------------------------------------------------------------------------------------------
+class GpuScanOperator final : public SourceOperator {
+public:
+    // `morsel`: the decoded chunks the storage layer would hand over (TabletReader -> ChunkIterator::get_next); the
+    // operator owns predicate evaluation + Chunk::filter on the device.
+    GpuScanOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, sr_ctx* ctx, const sr_scan_desc& desc,
+                    std::vector<ChunkPtr> morsel)
+            : SourceOperator(f, id, "gpu_olap_scan", plan_node_id, false, seq), _ctx(ctx), _desc(desc), _morsel(std::move(morsel)) {}
+    ~GpuScanOperator() override {
+        if (_scan) sr_scan_destroy(_scan);
+    }
+    Status prepare(RuntimeState* state) override {
+        _scan = sr_scan_create(_ctx, &_desc);
+        return _scan ? Status::OK() : sr_to_status(_ctx, sr_last_error_code(_ctx));
+    }
+    bool has_output() const override { return !_out.empty() || _next < _morsel.size(); }
+    bool is_finished() const override { return _out.empty() && _next >= _morsel.size(); }
+    StatusOr<ChunkPtr> pull_chunk(RuntimeState* state) override {
+        if (_out.empty() && _next < _morsel.size()) {
+            _batch.clear();
+            for (int k = 0; k < kGpuBatchChunks && _next < _morsel.size(); k++) _batch.append(*_morsel[_next++]);
+            sr_chunk_view v = _batch.view();
+            sr_chunk_out out;
+            RETURN_IF_SR_ERROR(_ctx, sr_scan_filter(_scan, &v, &out));
+            RETURN_IF_ERROR(slice_out_to_chunks(_ctx, out, state->chunk_size(), &_out));
+        }
+        if (_out.empty()) return ChunkPtr(nullptr);
+        ChunkPtr c = _out.front();
+        _out.pop_front();
+        return c;
+    }
+
+private:
+    sr_ctx* _ctx;
+    sr_scan_desc _desc;
+    sr_scan* _scan = nullptr;
+    std::vector<ChunkPtr> _morsel;
+    size_t _next = 0;
+    ChunkBatch _batch;
+    std::deque<ChunkPtr> _out;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// hash join
+// ------------------------------------------------------------------------------------------------------------
+class GpuHashJoiner { // HashJoiner: shared by the build operator and the probe operators
+public:
+    GpuHashJoiner(sr_ctx* ctx, const sr_join_desc& desc) : _ctx(ctx), _desc(desc) {}
+    ~GpuHashJoiner() {
+        if (_join) sr_join_destroy(_join);
+    }
+    Status prepare() {
+        if (_join) return Status::OK();
+        _join = sr_join_create(_ctx, &_desc);
+        return _join ? Status::OK() : sr_to_status(_ctx, sr_last_error_code(_ctx));
+    }
+    sr_ctx* ctx() const { return _ctx; }
+    sr_join* join() const { return _join; }
+    bool is_build_done() const { return _join != nullptr && sr_join_is_build_done(_join) != 0; } // HashJoiner::is_build_done
+
+private:
+    sr_ctx* _ctx;
+    sr_join_desc _desc;
+    sr_join* _join = nullptr;
+};
+using GpuHashJoinerPtr = std::shared_ptr<GpuHashJoiner>;
+
+class GpuHashJoinBuildOperator final : public Operator {
+public:
+    GpuHashJoinBuildOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, GpuHashJoinerPtr joiner)
+            : Operator(f, id, "gpu_hash_join_build", plan_node_id, false, seq), _joiner(std::move(joiner)) {}
+    Status prepare(RuntimeState* state) override { return _joiner->prepare(); }
+    bool has_output() const override { return false; }
+    bool need_input() const override { return !_finished; }
+    bool is_finished() const override { return _finished; }
+    StatusOr<ChunkPtr> pull_chunk(RuntimeState*) override { return Status::InternalError("pull_chunk on a sink"); }
+    Status push_chunk(RuntimeState* state, const ChunkPtr& chunk) override { // HashJoiner::append_chunk_to_ht
+        _batch.append(*chunk);
+        if (_batch.rows() >= (size_t)kGpuBatchChunks * state->chunk_size()) RETURN_IF_ERROR(_flush());
+        return Status::OK();
+    }
+    Status set_finishing(RuntimeState* state) override { // build_ht + enter_probe_phase (hash_join_build_operator.cpp:86-220)
+        if (_finished) return Status::OK();
+        RETURN_IF_ERROR(_flush());
+        RETURN_IF_SR_ERROR(_joiner->ctx(), sr_join_build_finish(_joiner->join()));
+        _finished = true;
+        return Status::OK();
+    }
+
+private:
+    Status _flush() {
+        if (_batch.empty()) return Status::OK();
+        sr_chunk_view v = _batch.view();
+        RETURN_IF_SR_ERROR(_joiner->ctx(), sr_join_append_build(_joiner->join(), &v));
+        _batch.clear();
+        return Status::OK();
+    }
+    GpuHashJoinerPtr _joiner;
+    ChunkBatch _batch;
+    bool _finished = false;
+};
+
+class GpuHashJoinProbeOperator final : public OperatorWithDependency {
+public:
+    GpuHashJoinProbeOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, GpuHashJoinerPtr joiner)
+            : OperatorWithDependency(f, id, "gpu_hash_join_probe", plan_node_id, false, seq), _joiner(std::move(joiner)), _prober_id(seq) {}
+    Status prepare(RuntimeState* state) override { return _joiner->prepare(); }
+    bool is_ready() const override { return _joiner->is_build_done(); } // hash_join_probe_operator.cpp:75-77
+    bool has_output() const override { return !_out.empty(); }
+    bool need_input() const override { return _out.empty() && !_finishing; }
+    bool is_finished() const override { return _finishing && _out.empty() && _batch.empty(); }
+    Status push_chunk(RuntimeState* state, const ChunkPtr& chunk) override {
+        _batch.append(*chunk);
+        if (_batch.rows() >= (size_t)kGpuBatchChunks * state->chunk_size()) RETURN_IF_ERROR(_probe(state));
+        return Status::OK();
+    }
+    StatusOr<ChunkPtr> pull_chunk(RuntimeState* state) override {
+        if (_out.empty()) return ChunkPtr(nullptr);
+        ChunkPtr c = _out.front();
+        _out.pop_front();
+        return c;
+    }
+    Status set_finishing(RuntimeState* state) override {
+        _finishing = true;
+        return _probe(state);
+    }
+
+private:
+    Status _probe(RuntimeState* state) {
+        if (_batch.empty()) return Status::OK();
+        sr_chunk_view v = _batch.view();
+        sr_chunk_out out;
+        RETURN_IF_SR_ERROR(_joiner->ctx(), sr_join_probe(_joiner->join(), _prober_id, &v, &out));
+        RETURN_IF_ERROR(slice_out_to_chunks(_joiner->ctx(), out, state->chunk_size(), &_out));
+        _batch.clear();
+        return Status::OK();
+    }
+    GpuHashJoinerPtr _joiner;
+    int32_t _prober_id;
+    ChunkBatch _batch;
+    std::deque<ChunkPtr> _out;
+    bool _finishing = false;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// aggregate
+// ------------------------------------------------------------------------------------------------------------
+class GpuAggregator { // Aggregator: shared by the blocking sink and source
+public:
+    GpuAggregator(sr_ctx* ctx, const sr_agg_desc& desc) : _ctx(ctx), _desc(desc) {}
+    explicit GpuAggregator(sr_ctx* ctx, sr_agg* borrowed) : _ctx(ctx), _agg(borrowed), _owned(false) {}
+    ~GpuAggregator() {
+        if (_agg && _owned) sr_agg_destroy(_agg);
+    }
+    Status prepare() {
+        if (_agg) return Status::OK();
+        _agg = sr_agg_create(_ctx, &_desc);
+        return _agg ? Status::OK() : sr_to_status(_ctx, sr_last_error_code(_ctx));
+    }
+    sr_ctx* ctx() const { return _ctx; }
+    sr_agg* agg() const { return _agg; }
+    void bind(sr_agg* borrowed) { // the fused fragment owns its aggregate and creates it once the builds are done
+        _agg = borrowed;
+        _owned = false;
+    }
+    bool is_sink_complete() const { return _sink_complete; }
+    void sink_complete() { _sink_complete = true; }
+
+private:
+    sr_ctx* _ctx;
+    sr_agg_desc _desc{};
+    sr_agg* _agg = nullptr;
+    bool _owned = true;
+    bool _sink_complete = false;
+};
+using GpuAggregatorPtr = std::shared_ptr<GpuAggregator>;
+
+class GpuAggregateBlockingSinkOperator final : public Operator {
+public:
+    GpuAggregateBlockingSinkOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, GpuAggregatorPtr agg)
+            : Operator(f, id, "gpu_aggregate_blocking_sink", plan_node_id, false, seq), _aggregator(std::move(agg)) {}
+    Status prepare(RuntimeState* state) override { return _aggregator->prepare(); }
+    bool has_output() const override { return false; }
+    bool need_input() const override { return !_finished; }
+    bool is_finished() const override { return _finished; }
+    StatusOr<ChunkPtr> pull_chunk(RuntimeState*) override { return Status::InternalError("pull_chunk on a sink"); }
+    Status push_chunk(RuntimeState* state, const ChunkPtr& chunk) override {
+        _batch.append(*chunk);
+        if (_batch.rows() >= (size_t)kGpuBatchChunks * state->chunk_size()) RETURN_IF_ERROR(_flush());
+        return Status::OK();
+    }
+    Status set_finishing(RuntimeState* state) override { // sink_complete (aggregate_blocking_sink_operator.cpp:56-89)
+        if (_finished) return Status::OK();
+        RETURN_IF_ERROR(_flush());
+        RETURN_IF_SR_ERROR(_aggregator->ctx(), sr_agg_sink_finish(_aggregator->agg()));
+        _aggregator->sink_complete();
+        _finished = true;
+        return Status::OK();
+    }
+
+private:
+    Status _flush() {
+        if (_batch.empty()) return Status::OK();
+        sr_chunk_view v = _batch.view();
+        RETURN_IF_SR_ERROR(_aggregator->ctx(), sr_agg_push(_aggregator->agg(), &v));
+        _batch.clear();
+        return Status::OK();
+    }
+    GpuAggregatorPtr _aggregator;
+    ChunkBatch _batch;
+    bool _finished = false;
+};
+
+class GpuAggregateBlockingSourceOperator final : public SourceOperator {
+public:
+    GpuAggregateBlockingSourceOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, GpuAggregatorPtr agg)
+            : SourceOperator(f, id, "gpu_aggregate_blocking_source", plan_node_id, false, seq), _aggregator(std::move(agg)) {}
+    bool has_output() const override { return _aggregator->is_sink_complete() && !_eos; }
+    bool is_finished() const override { return _aggregator->is_sink_complete() && _eos; }
+    StatusOr<ChunkPtr> pull_chunk(RuntimeState* state) override { // convert_hash_map_to_chunk, chunk_size groups per call
+        sr_chunk_out out;
+        RETURN_IF_SR_ERROR(_aggregator->ctx(), sr_agg_pull(_aggregator->agg(), state->chunk_size(), SR_MEM_HOST, &out));
+        if (out.num_rows == 0) {
+            _eos = true;
+            return ChunkPtr(nullptr);
+        }
+        std::deque<ChunkPtr> q;
+        RETURN_IF_ERROR(slice_out_to_chunks(_aggregator->ctx(), out, state->chunk_size(), &q));
+        return q.front();
+    }
+
+private:
+    GpuAggregatorPtr _aggregator;
+    bool _eos = false;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// fused fragment sink: [probe x N -> aggregate sink] collapsed behind one sink operator
+// ------------------------------------------------------------------------------------------------------------
+class GpuFragment {
+public:
+    GpuFragment(sr_ctx* ctx, sr_fragment_desc desc, std::vector<GpuHashJoinerPtr> joiners)
+            : _ctx(ctx), _desc(desc), _joiners(std::move(joiners)), _aggregator(std::make_shared<GpuAggregator>(ctx, (sr_agg*)nullptr)) {}
+    ~GpuFragment() {
+        if (_frag) sr_fragment_destroy(_frag);
+    }
+    bool builds_done() const {
+        for (auto& j : _joiners)
+            if (!j->is_build_done()) return false;
+        return true;
+    }
+    Status prepare() { // needs the builds: called lazily from the first push
+        if (_frag) return Status::OK();
+        for (size_t k = 0; k < _joiners.size(); k++) _desc.joins[k].join = _joiners[k]->join();
+        _frag = sr_fragment_create(_ctx, &_desc);
+        if (!_frag) return sr_to_status(_ctx, sr_last_error_code(_ctx));
+        _aggregator->bind(sr_fragment_agg(_frag));
+        return Status::OK();
+    }
+    sr_ctx* ctx() const { return _ctx; }
+    sr_fragment* frag() const { return _frag; }
+    GpuAggregatorPtr aggregator() const { return _aggregator; }
+
+private:
+    sr_ctx* _ctx;
+    sr_fragment_desc _desc;
+    std::vector<GpuHashJoinerPtr> _joiners;
+    sr_fragment* _frag = nullptr;
+    GpuAggregatorPtr _aggregator;
+};
+using GpuFragmentPtr = std::shared_ptr<GpuFragment>;
+
+class GpuFragmentSinkOperator final : public OperatorWithDependency {
+public:
+    GpuFragmentSinkOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, GpuFragmentPtr frag, size_t batch_rows = 1 << 22)
+            : OperatorWithDependency(f, id, "gpu_fragment_sink", plan_node_id, false, seq), _frag(std::move(frag)), _batch_rows(batch_rows) {}
+    bool is_ready() const override { return _frag->builds_done(); }
+    bool has_output() const override { return false; }
+    bool need_input() const override { return !_finished; }
+    bool is_finished() const override { return _finished; }
+    StatusOr<ChunkPtr> pull_chunk(RuntimeState*) override { return Status::InternalError("pull_chunk on a sink"); }
+    Status push_chunk(RuntimeState* state, const ChunkPtr& chunk) override {
+        _batch.append(*chunk);
+        if (_batch.rows() >= _batch_rows) RETURN_IF_ERROR(_flush());
+        return Status::OK();
+    }
+    Status set_finishing(RuntimeState* state) override {
+        if (_finished) return Status::OK();
+        RETURN_IF_ERROR(_frag->prepare());
+        RETURN_IF_ERROR(_flush());
+        RETURN_IF_SR_ERROR(_frag->ctx(), sr_agg_sink_finish(sr_fragment_agg(_frag->frag())));
+        _frag->aggregator()->sink_complete();
+        _finished = true;
+        return Status::OK();
+    }
+
+private:
+    Status _flush() {
+        if (_batch.empty()) return Status::OK();
+        RETURN_IF_ERROR(_frag->prepare());
+        sr_chunk_view v = _batch.view();
+        RETURN_IF_SR_ERROR(_frag->ctx(), sr_fragment_push(_frag->frag(), &v));
+        RETURN_IF_SR_ERROR(_frag->ctx(), sr_ctx_sync(_frag->ctx())); // the host batch is reused
+        _batch.clear();
+        return Status::OK();
+    }
+    GpuFragmentPtr _frag;
+    size_t _batch_rows;
+    ChunkBatch _batch;
+    bool _finished = false;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// factories (what HashJoinNode / AggregateBlockingNode::_decompose_to_pipeline<...> are instantiated with)
+// ------------------------------------------------------------------------------------------------------------
+class GpuScanOperatorFactory final : public SourceOperatorFactory {
+public:
+    GpuScanOperatorFactory(int32_t id, int32_t plan_node_id, sr_ctx* ctx, sr_scan_desc desc, std::vector<std::vector<ChunkPtr>> morsels)
+            : SourceOperatorFactory(id, "gpu_olap_scan", plan_node_id), _ctx(ctx), _desc(desc), _morsels(std::move(morsels)) {
+        set_degree_of_parallelism(_morsels.size());
+    }
+    OperatorPtr create(int32_t dop, int32_t seq) override {
+        return std::make_shared<GpuScanOperator>(this, _id, _plan_node_id, seq, _ctx, _desc, _morsels[seq]);
+    }
+
+private:
+    sr_ctx* _ctx;
+    sr_scan_desc _desc;
+    std::vector<std::vector<ChunkPtr>> _morsels;
+};
+
+class GpuHashJoinerFactory { // HashJoinerFactory (hashjoin/hash_joiner_factory.cpp:57-79): prober i uses builder i % builder_dop
+public:
+    GpuHashJoinerFactory(sr_ctx* ctx, sr_join_desc desc) : _joiner(std::make_shared<GpuHashJoiner>(ctx, desc)) {}
+    GpuHashJoinerPtr create_builder(int32_t, int32_t) { return _joiner; }
+    GpuHashJoinerPtr create_prober(int32_t, int32_t) { return _joiner; }
+    GpuHashJoinerPtr get() { return _joiner; }
+
+private:
+    GpuHashJoinerPtr _joiner;
+};
+using GpuHashJoinerFactoryPtr = std::shared_ptr<GpuHashJoinerFactory>;
+
+class GpuHashJoinBuildOperatorFactory final : public OperatorFactory {
+public:
+    GpuHashJoinBuildOperatorFactory(int32_t id, int32_t plan_node_id, GpuHashJoinerFactoryPtr f)
+            : OperatorFactory(id, "gpu_hash_join_build", plan_node_id), _f(std::move(f)) {}
+    OperatorPtr create(int32_t dop, int32_t seq) override {
+        return std::make_shared<GpuHashJoinBuildOperator>(this, _id, _plan_node_id, seq, _f->create_builder(dop, seq));
+    }
+
+private:
+    GpuHashJoinerFactoryPtr _f;
+};
+
+class GpuHashJoinProbeOperatorFactory final : public OperatorFactory {
+public:
+    GpuHashJoinProbeOperatorFactory(int32_t id, int32_t plan_node_id, GpuHashJoinerFactoryPtr f)
+            : OperatorFactory(id, "gpu_hash_join_probe", plan_node_id), _f(std::move(f)) {}
+    OperatorPtr create(int32_t dop, int32_t seq) override {
+        return std::make_shared<GpuHashJoinProbeOperator>(this, _id, _plan_node_id, seq, _f->create_prober(dop, seq));
+    }
+
+private:
+    GpuHashJoinerFactoryPtr _f;
+};
+
+class GpuAggregatorFactory {
+public:
+    GpuAggregatorFactory(sr_ctx* ctx, sr_agg_desc desc) : _agg(std::make_shared<GpuAggregator>(ctx, desc)) {}
+    GpuAggregatorPtr get_or_create(size_t) { return _agg; }
+
+private:
+    GpuAggregatorPtr _agg;
+};
+using GpuAggregatorFactoryPtr = std::shared_ptr<GpuAggregatorFactory>;
+
+class GpuAggregateBlockingSinkOperatorFactory final : public OperatorFactory {
+public:
+    GpuAggregateBlockingSinkOperatorFactory(int32_t id, int32_t plan_node_id, GpuAggregatorFactoryPtr f)
+            : OperatorFactory(id, "gpu_aggregate_blocking_sink", plan_node_id), _f(std::move(f)) {}
+    OperatorPtr create(int32_t dop, int32_t seq) override {
+        return std::make_shared<GpuAggregateBlockingSinkOperator>(this, _id, _plan_node_id, seq, _f->get_or_create(seq));
+    }
+
+private:
+    GpuAggregatorFactoryPtr _f;
+};
+
+class GpuAggregateBlockingSourceOperatorFactory final : public SourceOperatorFactory {
+public:
+    GpuAggregateBlockingSourceOperatorFactory(int32_t id, int32_t plan_node_id, GpuAggregatorFactoryPtr f)
+            : SourceOperatorFactory(id, "gpu_aggregate_blocking_source", plan_node_id), _f(std::move(f)) {}
+    OperatorPtr create(int32_t dop, int32_t seq) override {
+        return std::make_shared<GpuAggregateBlockingSourceOperator>(this, _id, _plan_node_id, seq, _f->get_or_create(seq));
+    }
+
+private:
+    GpuAggregatorFactoryPtr _f;
+};
+
+} // namespace starrocks::pipeline

@@ -1,0 +1,310 @@
+// Drives the GPU operators through the reference's pipeline protocol (PipelineDriver::process pull/push/finishing,
+// dependency of the probe on the build) on an SSB Q4.1-shaped plan, the way be/test/exec/pipeline/pipeline_test_base
+// assembles OpFactories without an FE:
+//
+//   build pipelines (x4):  GpuScanOperator(dimension, predicate) -> GpuHashJoinBuildOperator
+//   probe pipeline  (A):   GpuScanOperator(lineorder) -> GpuHashJoinProbeOperator x4 -> GpuAggregateBlockingSinkOperator
+//   probe pipeline  (B):   GpuScanOperator(lineorder) -> GpuFragmentSinkOperator            (fused form)
+//   result pipeline:       GpuAggregateBlockingSourceOperator -> ResultSink (collects rows)
+//
+// A and B must give the same groups, and both must match a straightforward row-at-a-time evaluation of the query in
+// this file (the checker).  Exit code 0 = pass.  Needs a CUDA device (run by tests/test_host_pipeline.py -m gpu).
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <tuple>
+
+#include "../gpu/gpu_operators.h"
+
+using namespace starrocks;
+using namespace starrocks::pipeline;
+
+namespace {
+
+enum Slots { LO_ORDERDATE = 0, LO_CUSTKEY, LO_SUPPKEY, LO_PARTKEY, LO_REVENUE, LO_SUPPLYCOST, C_CUSTKEY = 10, C_REGION, C_NATION, S_SUPPKEY = 20, S_REGION,
+             P_PARTKEY = 30, P_MFGR, D_DATEKEY = 40, D_YEAR, OUT_REV = 50, OUT_COST };
+
+struct Rng {
+    uint64_t s;
+    uint32_t next(uint32_t lo, uint32_t hi) { // [lo, hi)
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        return lo + (uint32_t)((s >> 33) % (hi - lo));
+    }
+};
+
+ChunkPtr make_chunk(const std::vector<std::pair<SlotId, std::vector<int32_t>>>& cols) {
+    auto c = std::make_shared<Chunk>();
+    for (auto& [slot, v] : cols) c->append_column(std::make_shared<Int32Column>(SR_TYPE_INT, v), slot);
+    return c;
+}
+
+std::vector<ChunkPtr> split(const ChunkPtr& whole, size_t chunk_size) {
+    std::vector<ChunkPtr> out;
+    for (size_t off = 0; off < whole->num_rows(); off += chunk_size) out.push_back(whole->slice(off, std::min(chunk_size, whole->num_rows() - off)));
+    return out;
+}
+
+class ResultSink final : public Operator {
+public:
+    ResultSink() : Operator(nullptr, 99, "result_sink", 99, false, 0) {}
+    bool has_output() const override { return false; }
+    bool need_input() const override { return !_finished; }
+    bool is_finished() const override { return _finished; }
+    StatusOr<ChunkPtr> pull_chunk(RuntimeState*) override { return Status::InternalError("sink"); }
+    Status push_chunk(RuntimeState*, const ChunkPtr& c) override {
+        chunks.push_back(c);
+        return Status::OK();
+    }
+    Status set_finishing(RuntimeState*) override {
+        _finished = true;
+        return Status::OK();
+    }
+    std::vector<ChunkPtr> chunks;
+
+private:
+    bool _finished = false;
+};
+
+#define CHECK_OK(expr)                                                              \
+    do {                                                                            \
+        Status _st = (expr);                                                        \
+        if (!_st.ok()) {                                                            \
+            fprintf(stderr, "FAILED %s: %s\n", #expr, _st.to_string().c_str());     \
+            exit(2);                                                                \
+        }                                                                           \
+    } while (0)
+
+void run_to_finish(PipelineDriver& d, RuntimeState* state, const char* name) {
+    CHECK_OK(d.prepare(state));
+    for (int spin = 0; spin < 1000000; spin++) {
+        auto st = d.process(state);
+        if (!st.ok()) {
+            fprintf(stderr, "driver %s failed: %s\n", name, st.status().to_string().c_str());
+            exit(2);
+        }
+        if (st.value() == PipelineDriver::FINISH) return;
+        if (st.value() == PipelineDriver::PRECONDITION_BLOCK) {
+            fprintf(stderr, "driver %s is still blocked on its dependency\n", name);
+            exit(2);
+        }
+    }
+    fprintf(stderr, "driver %s made no progress\n", name);
+    exit(2);
+}
+
+using Groups = std::map<std::pair<int32_t, int32_t>, std::pair<int64_t, int64_t>>;
+
+Groups collect(const ResultSink& sink) {
+    Groups g;
+    for (auto& c : sink.chunks) {
+        auto* y = (const int32_t*)c->get_column_by_slot_id(D_YEAR)->raw_data();
+        auto* n = (const int32_t*)c->get_column_by_slot_id(C_NATION)->raw_data();
+        auto* r = (const int64_t*)c->get_column_by_slot_id(OUT_REV)->raw_data();
+        auto* s = (const int64_t*)c->get_column_by_slot_id(OUT_COST)->raw_data();
+        for (size_t i = 0; i < c->num_rows(); i++) g[{y[i], n[i]}] = {r[i], s[i]};
+    }
+    return g;
+}
+
+sr_expr col_expr(int32_t slot) {
+    sr_expr e{};
+    e.nodes[0].op = SR_EX_COL;
+    e.nodes[0].slot_id = slot;
+    e.num_nodes = 1;
+    return e;
+}
+
+} // namespace
+
+int main(int argc, char** argv) {
+    const size_t n_fact = argc > 1 ? (size_t)atoll(argv[1]) : 1000000;
+    const int n_cust = 30000, n_supp = 2000, n_part = 20000, n_dates = 2556;
+    sr_ctx* ctx = sr_ctx_create(0, nullptr);
+    if (!ctx) {
+        fprintf(stderr, "sr_ctx_create failed: %s\n", sr_last_error(nullptr));
+        return 3;
+    }
+    RuntimeState state(4096);
+    Rng rng{20240921};
+
+    // ---- synthetic SSB-shaped tables ----
+    std::vector<int32_t> c_key(n_cust), c_region(n_cust), c_nation(n_cust), s_key(n_supp), s_region(n_supp), p_key(n_part), p_mfgr(n_part), d_key(n_dates),
+            d_year(n_dates);
+    for (int i = 0; i < n_cust; i++) {
+        c_key[i] = i + 1;
+        c_region[i] = rng.next(0, 5);
+        c_nation[i] = c_region[i] * 5 + rng.next(0, 5);
+    }
+    for (int i = 0; i < n_supp; i++) {
+        s_key[i] = i + 1;
+        s_region[i] = rng.next(0, 5);
+    }
+    for (int i = 0; i < n_part; i++) {
+        p_key[i] = i + 1;
+        p_mfgr[i] = rng.next(0, 5);
+    }
+    for (int i = 0; i < n_dates; i++) {
+        d_year[i] = 1992 + i / 366;
+        d_key[i] = d_year[i] * 10000 + (i % 366) + 101; // unique, sparse like yyyymmdd
+    }
+    std::vector<int32_t> lo_date(n_fact), lo_cust(n_fact), lo_supp(n_fact), lo_part(n_fact), lo_rev(n_fact), lo_cost(n_fact);
+    for (size_t i = 0; i < n_fact; i++) {
+        lo_date[i] = d_key[rng.next(0, n_dates)];
+        lo_cust[i] = rng.next(1, n_cust + 1);
+        lo_supp[i] = rng.next(1, n_supp + 1);
+        lo_part[i] = rng.next(1, n_part + 1);
+        lo_rev[i] = rng.next(81000, 10400001);
+        lo_cost[i] = rng.next(54000, 125001);
+    }
+    // ---- the checker: row-at-a-time evaluation of the query ----
+    Groups expect;
+    for (size_t i = 0; i < n_fact; i++) {
+        if (s_region[lo_supp[i] - 1] != 1 || c_region[lo_cust[i] - 1] != 1 || p_mfgr[lo_part[i] - 1] > 1) continue;
+        const int32_t year = lo_date[i] / 10000;
+        auto& g = expect[{year, c_nation[lo_cust[i] - 1]}];
+        g.first += lo_rev[i];
+        g.second += lo_cost[i];
+    }
+
+    // ---- descriptors ----
+    auto eq_pred = [](int32_t slot, int64_t v) {
+        sr_pred p{};
+        p.slot_id = slot;
+        p.op = SR_PRED_EQ;
+        p.ilo = v;
+        return p;
+    };
+    sr_pred supp_pred = eq_pred(S_REGION, 1), cust_pred = eq_pred(C_REGION, 1), part_pred{};
+    part_pred.slot_id = P_MFGR;
+    part_pred.op = SR_PRED_IN;
+    part_pred.in_list[0] = 0;
+    part_pred.in_list[1] = 1;
+    part_pred.in_count = 2;
+    struct Dim {
+        const char* name;
+        ChunkPtr table;
+        sr_pred* pred;
+        int32_t key_slot, probe_slot;
+        std::vector<int32_t> payload;
+    };
+    std::vector<Dim> dims = {
+            {"supplier", make_chunk({{S_SUPPKEY, s_key}, {S_REGION, s_region}}), &supp_pred, S_SUPPKEY, LO_SUPPKEY, {}},
+            {"customer", make_chunk({{C_CUSTKEY, c_key}, {C_REGION, c_region}, {C_NATION, c_nation}}), &cust_pred, C_CUSTKEY, LO_CUSTKEY, {C_NATION}},
+            {"part", make_chunk({{P_PARTKEY, p_key}, {P_MFGR, p_mfgr}}), &part_pred, P_PARTKEY, LO_PARTKEY, {}},
+            {"dates", make_chunk({{D_DATEKEY, d_key}, {D_YEAR, d_year}}), nullptr, D_DATEKEY, LO_ORDERDATE, {D_YEAR}},
+    };
+    ChunkPtr lineorder = make_chunk({{LO_ORDERDATE, lo_date}, {LO_CUSTKEY, lo_cust}, {LO_SUPPKEY, lo_supp}, {LO_PARTKEY, lo_part}, {LO_REVENUE, lo_rev},
+                                     {LO_SUPPLYCOST, lo_cost}});
+    sr_agg_desc agg_desc{};
+    agg_desc.num_group_keys = 2;
+    agg_desc.group_slots[0] = D_YEAR;
+    agg_desc.group_slots[1] = C_NATION;
+    agg_desc.group_types[0] = agg_desc.group_types[1] = SR_TYPE_INT;
+    agg_desc.has_ranges = 1;
+    agg_desc.group_min[0] = 1992;
+    agg_desc.group_max[0] = 1998;
+    agg_desc.group_min[1] = 0;
+    agg_desc.group_max[1] = 24;
+    agg_desc.num_fns = 2;
+    agg_desc.fns[0] = sr_agg_fn{SR_AGG_SUM, SR_TYPE_INT, OUT_REV, 0, col_expr(LO_REVENUE)};
+    agg_desc.fns[1] = sr_agg_fn{SR_AGG_SUM, SR_TYPE_INT, OUT_COST, 0, col_expr(LO_SUPPLYCOST)};
+
+    Groups results[2];
+    for (int fused = 0; fused < 2; fused++) {
+        // ---- build pipelines: scan(dim) -> hash join build; the joiner is shared with the probe side ----
+        std::vector<GpuHashJoinerFactoryPtr> joiner_factories;
+        std::vector<std::vector<int32_t>> out_slot_store(dims.size());
+        // slots still needed downstream of join k on the probe side
+        std::vector<std::vector<int32_t>> probe_out = {{LO_ORDERDATE, LO_CUSTKEY, LO_PARTKEY, LO_REVENUE, LO_SUPPLYCOST},
+                                                       {LO_ORDERDATE, LO_PARTKEY, LO_REVENUE, LO_SUPPLYCOST},
+                                                       {LO_ORDERDATE, LO_REVENUE, LO_SUPPLYCOST, C_NATION},
+                                                       {LO_REVENUE, LO_SUPPLYCOST, C_NATION}};
+        for (size_t k = 0; k < dims.size(); k++) {
+            Dim& dm = dims[k];
+            out_slot_store[k] = {dm.key_slot};
+            for (int32_t p : dm.payload) out_slot_store[k].push_back(p);
+            sr_scan_desc sd{};
+            sd.preds = dm.pred;
+            sd.num_preds = dm.pred ? 1 : 0;
+            sd.out_slots = out_slot_store[k].data();
+            sd.num_out_slots = (int32_t)out_slot_store[k].size();
+            sr_join_desc jd{};
+            jd.join_type = SR_JOIN_INNER;
+            jd.num_keys = 1;
+            jd.build_key_slots[0] = dm.key_slot;
+            jd.probe_key_slots[0] = dm.probe_slot;
+            jd.key_types[0] = SR_TYPE_INT;
+            jd.enable_range_direct_mapping = 1;
+            jd.num_build_out = (int32_t)dm.payload.size();
+            for (size_t p = 0; p < dm.payload.size(); p++) jd.build_out_slots[p] = dm.payload[p];
+            jd.num_probe_out = (int32_t)probe_out[k].size();
+            for (size_t p = 0; p < probe_out[k].size(); p++) jd.probe_out_slots[p] = probe_out[k][p];
+            auto jf = std::make_shared<GpuHashJoinerFactory>(ctx, jd);
+            joiner_factories.push_back(jf);
+            GpuScanOperatorFactory scan_f(1, 1, ctx, sd, {split(dm.table, 4096)});
+            GpuHashJoinBuildOperatorFactory build_f(2, 2, jf);
+            PipelineDriver build_driver({scan_f.create(1, 0), build_f.create(1, 0)});
+            run_to_finish(build_driver, &state, dm.name);
+            build_driver.close(&state);
+        }
+        // ---- probe pipeline ----
+        sr_scan_desc fact_scan{};
+        std::vector<int32_t> fact_out = {LO_ORDERDATE, LO_CUSTKEY, LO_SUPPKEY, LO_PARTKEY, LO_REVENUE, LO_SUPPLYCOST};
+        fact_scan.out_slots = fact_out.data();
+        fact_scan.num_out_slots = (int32_t)fact_out.size();
+        GpuScanOperatorFactory fact_f(3, 3, ctx, fact_scan, {split(lineorder, 4096)});
+        GpuAggregatorPtr aggregator;
+        GpuFragmentPtr fragment;
+        Operators ops = {fact_f.create(1, 0)};
+        GpuAggregatorFactoryPtr agg_f;
+        if (!fused) {
+            for (size_t k = 0; k < dims.size(); k++) {
+                GpuHashJoinProbeOperatorFactory pf(4 + (int)k, 4 + (int)k, joiner_factories[k]);
+                ops.push_back(pf.create(1, 0));
+            }
+            agg_f = std::make_shared<GpuAggregatorFactory>(ctx, agg_desc);
+            GpuAggregateBlockingSinkOperatorFactory sink_f(8, 8, agg_f);
+            ops.push_back(sink_f.create(1, 0));
+            aggregator = agg_f->get_or_create(0);
+        } else {
+            sr_fragment_desc fd{};
+            fd.num_joins = (int32_t)dims.size();
+            std::vector<GpuHashJoinerPtr> joiners;
+            for (size_t k = 0; k < dims.size(); k++) {
+                fd.joins[k].probe_key_slot = dims[k].probe_slot;
+                fd.joins[k].num_payload = (int32_t)dims[k].payload.size();
+                for (size_t p = 0; p < dims[k].payload.size(); p++) fd.joins[k].payload_build_slots[p] = dims[k].payload[p];
+                joiners.push_back(joiner_factories[k]->get());
+            }
+            fd.agg = agg_desc;
+            fragment = std::make_shared<GpuFragment>(ctx, fd, joiners);
+            ops.push_back(std::make_shared<GpuFragmentSinkOperator>(nullptr, 8, 8, 0, fragment, (size_t)1 << 18));
+            aggregator = fragment->aggregator();
+        }
+        PipelineDriver probe_driver(ops);
+        run_to_finish(probe_driver, &state, fused ? "probe(fused)" : "probe(per-operator)");
+        // ---- result pipeline ----
+        auto sink = std::make_shared<ResultSink>();
+        auto source = std::make_shared<GpuAggregateBlockingSourceOperator>(nullptr, 9, 9, 0, aggregator);
+        PipelineDriver result_driver({source, sink});
+        run_to_finish(result_driver, &state, "result");
+        results[fused] = collect(*sink);
+        result_driver.close(&state);
+        probe_driver.close(&state);
+        printf("%s path: %zu groups, %zu rows moved between operators\n", fused ? "fused fragment" : "per-operator", results[fused].size(),
+               probe_driver.rows_moved());
+    }
+    int rc = 0;
+    if (results[0] != expect) {
+        fprintf(stderr, "per-operator pipeline differs from the checker (%zu vs %zu groups)\n", results[0].size(), expect.size());
+        rc = 1;
+    }
+    if (results[1] != expect) {
+        fprintf(stderr, "fused pipeline differs from the checker (%zu vs %zu groups)\n", results[1].size(), expect.size());
+        rc = 1;
+    }
+    printf("kernel launches: %lld\n", (long long)sr_ctx_kernel_launches(ctx));
+    sr_ctx_destroy(ctx);
+    printf(rc == 0 ? "PIPELINE_Q41_OK\n" : "PIPELINE_Q41_MISMATCH\n");
+    return rc;
+}

@@ -1,0 +1,109 @@
+"""N > 1 host logic on CPU: world-size-2 gloo runs of (a) the two-phase aggregate (partial states gathered to rank 0
+and merged) and (b) the HASH_PARTITIONED exchange (FNV + ReduceOp partition, all_to_all, local join + aggregate).
+The per-rank compute is done by the oracle here (no GPU in this container); on the GPU box bench.py drives the same
+starrocks_b200.distributed functions over NCCL with the CUDA operators."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from starrocks_b200 import abi, ssb
+from starrocks_b200.abi import Chunk
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _init(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+
+def _two_phase_worker(rank, world, port, q):
+    from oracle import oracle
+    from starrocks_b200.distributed import gather_partial_states
+    from tests.helpers import oracle_rows
+    _init(rank, world, port)
+    dims = ssb.gen_dims(0.05)
+    n = 200_000
+    lo = ssb.gen_lineorder(0.05, n=n)                       # every rank generates the same table and takes its shard
+    shard = {k: v[rank::world].copy() for k, v in lo.items()}
+    ojoins, keep = ssb.build_dims(oracle, dims, ssb.dim_plans_q41())      # broadcast join: dimensions replicated
+    part, _ = oracle.fragment_run(abi.ScanDesc(), ojoins, ssb.q41_agg_desc(), ssb.fact_chunk(shard, ssb.Q41_FACT_COLS), num_threads=1)
+    out = part.output()
+    cols = [torch.from_numpy(np.ascontiguousarray(o[1]).astype(np.int64)) for o in out]
+    gathered = gather_partial_states(cols, max_rows=175, dst=0)
+    if rank == 0:
+        final_desc = abi.make_agg_desc([ssb.D_YEAR, ssb.C_NATION], [abi.TYPE_INT, abi.TYPE_INT],
+                                       fns=[(abi.AGG_SUM, abi.TYPE_BIGINT, 50, [("col", 50)]), (abi.AGG_SUM, abi.TYPE_BIGINT, 51, [("col", 51)])])
+        final = oracle.Agg(final_desc)
+        for g in gathered:
+            final.push(Chunk([(ssb.D_YEAR, g[0].numpy().astype(np.int32), None), (ssb.C_NATION, g[1].numpy().astype(np.int32), None),
+                              (50, g[2].numpy().copy(), None), (51, g[3].numpy().copy(), None)]))
+        whole, _ = oracle.fragment_run(abi.ScanDesc(), ojoins, ssb.q41_agg_desc(), ssb.fact_chunk(lo, ssb.Q41_FACT_COLS), num_threads=1)
+        q.put(oracle_rows(final) == oracle_rows(whole))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _shuffle_worker(rank, world, port, q):
+    from oracle import oracle
+    from starrocks_b200.distributed import exchange_partitions, gather_partial_states
+    from tests.helpers import oracle_rows
+    _init(rank, world, port)
+    rng = np.random.default_rng(77)
+    n = 100_000
+    keys = rng.integers(0, 5000, n, dtype=np.int32)
+    vals = rng.integers(-1000, 1000, n, dtype=np.int64)
+    my_k, my_v = keys[rank::world].copy(), vals[rank::world].copy()
+    pd_ = abi.make_part_desc([0], world)                    # HASH_PARTITIONED: FNV + ReduceOp
+    hv, ch, ri, st = oracle.hash_partition(pd_, Chunk([(0, my_k, None), (1, my_v, None)]))
+    recv = exchange_partitions([torch.from_numpy(my_k[ri]), torch.from_numpy(my_v[ri])], st.tolist())
+    rk, rv = recv[0].numpy(), recv[1].numpy()
+    # every key now lives on exactly one rank: ReduceOp(fnv(key), world) == rank for all received rows
+    hv2, ch2, _, _ = oracle.hash_partition(pd_, Chunk([(0, rk.copy(), None), (1, rv.copy(), None)]))
+    ok = bool((ch2 == rank).all())
+    d = abi.make_agg_desc([0], [abi.TYPE_INT], fns=[(abi.AGG_SUM, abi.TYPE_BIGINT, 10, [("col", 1)]), (abi.AGG_COUNT_STAR, 0, 11, None)])
+    local = oracle.Agg(d)
+    local.push(Chunk([(0, rk.copy(), None), (1, rv.copy(), None)]))
+    out = local.output()
+    ng = torch.tensor([local.num_groups], dtype=torch.int64)
+    dist.all_reduce(ng)
+    cols = [torch.from_numpy(np.ascontiguousarray(o[1]).astype(np.int64)) for o in out]
+    gathered = gather_partial_states(cols, max_rows=5000, dst=0)
+    if rank == 0:
+        whole = oracle.Agg(d)
+        whole.push(Chunk([(0, keys, None), (1, vals, None)]))
+        rows = sorted(tuple(int(x) for x in r) for g in gathered for r in zip(g[0].tolist(), g[1].tolist(), g[2].tolist()))
+        q.put(ok and int(ng.item()) == whole.num_groups and rows == [tuple(r) for r in oracle_rows(whole)])
+    else:
+        q.put(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("worker", [_two_phase_worker, _shuffle_worker])
+def test_world_size_2_gloo(oracle, worker):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = []
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0, f"rank exited with {p.exitcode}"
+    while not q.empty():
+        results.append(q.get())
+    assert results and all(results)
