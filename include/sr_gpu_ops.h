@@ -76,7 +76,16 @@ typedef enum sr_type {
 /* byte width of one value of the type (0 for an unknown type). */
 int32_t sr_type_width(int32_t type);
 
-typedef enum sr_mem { SR_MEM_HOST = 0, SR_MEM_DEVICE = 1 } sr_mem;
+/* SR_MEM_HOST: pageable or pinned host memory, staged with H2D copies on the context's stream.
+ * SR_MEM_DEVICE: device pointers, read in place.
+ * SR_MEM_HOST_PINNED: page-locked host memory mapped into the device address space (cudaHostAlloc /
+ *   cudaHostRegister, e.g. a registered ColumnAllocator pool).  sr_fragment_push reads such columns IN PLACE over
+ *   PCIe (late materialisation: a column is only fetched for the 32-byte sectors holding rows that survived the
+ *   earlier joins, so far fewer bytes cross the bus than a full H2D copy); every other entry point treats it like
+ *   SR_MEM_HOST.  Passing unpinned memory with this tag is rejected with SR_ERR_INVALID_ARGUMENT.  The buffers
+ *   must stay valid and unmodified until the next synchronising call on the context (sr_ctx_sync,
+ *   sr_agg_sink_finish, sr_fragment_rows_passed). */
+typedef enum sr_mem { SR_MEM_HOST = 0, SR_MEM_DEVICE = 1, SR_MEM_HOST_PINNED = 2 } sr_mem;
 
 /* mirrors FixedLengthColumn / NullableColumn raw buffers (be/src/column/nullable_column.h:32:
  * data column + uint8 null column, 1 = null). nulls == NULL means "not nullable / no nulls". */

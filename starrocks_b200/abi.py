@@ -40,7 +40,7 @@ NUMPY_TYPE = {
     np.dtype(np.float64): TYPE_DOUBLE,
 }
 
-MEM_HOST, MEM_DEVICE = 0, 1
+MEM_HOST, MEM_DEVICE, MEM_HOST_PINNED = 0, 1, 2
 
 # sr_pred_op
 PRED_EQ, PRED_NE, PRED_LT, PRED_LE, PRED_GT, PRED_GE, PRED_BETWEEN, PRED_IN, PRED_NOT_IN = 1, 2, 3, 4, 5, 6, 7, 8, 9

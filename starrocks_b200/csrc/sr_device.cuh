@@ -72,6 +72,10 @@ __device__ __forceinline__ int64_t ldg_stream_s64(const void* p) {
     asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(r) : "l"(p));
     return r;
 }
+// request a line into L2 without waiting for it (no destination register, no scoreboard)
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 // value of integer-class column at row i, sign/zero extended to int64 (truncating int128)
 __device__ __forceinline__ int64_t load_int(const void* data, int32_t type, int64_t i) {

@@ -278,9 +278,9 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
             // measured on B200 (profiles/r1_notes.md): the burst costs more issue slots and registers than the
             // latency it hides -- the final pass is L1TEX-gather bound, not latency bound -- so it stays off
             const bool kFinalPrefetch = false;
-            for (size_t k = 0; kFinalPrefetch && k < need.size() && k < SR_FINAL_PREFETCH; k++) {
-                f->pass.final_vals[k] = (int8_t)need[k];
-                f->pass.final_slot[need[k]] = (int8_t)k;
+            for (size_t k = 0; k < need.size() && k < SR_FINAL_PREFETCH; k++) {
+                f->pass.final_vals[k] = (int8_t)need[k]; // also the L2 prefetch list of host-resident input
+                if (kFinalPrefetch) f->pass.final_slot[need[k]] = (int8_t)k;
             }
         }
         f->gather_joins.clear();
@@ -358,7 +358,9 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
     sr_ctx* ctx = f->ctx;
     if (f->agg->finished) return sr_fail(ctx, SR_ERR_STATE, "fragment push after sink_finish");
     if (fact->num_rows >= 0xFFFFFFF0ll) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "fragment batch of more than 2^32 rows; push smaller morsels");
-    SR_TRY(f->staged.stage(ctx, fact));
+    // page-locked mapped host columns are read in place: the passes after the first only touch the sectors of
+    // surviving rows, so most of the batch never crosses PCIe
+    SR_TRY(f->staged.stage(ctx, fact, nullptr, /*in_place_pinned=*/true));
     const int64_t n = fact->num_rows;
     bool first = !f->compiled;
     if (first) SR_TRY(frag_compile(f));
@@ -387,6 +389,7 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
         const size_t slack = (size_t)srd::SEL_CHUNK * ((size_t)f->stream_grid * (srd::STREAM_BLOCK / 32) + (size_t)f->grid * (srd::GATHER_BLOCK / 32));
         SR_TRY(f->sel[0].reserve(ctx, sizeof(uint32_t) * ((size_t)n + slack)));
         if (!f->gather_joins.empty()) SR_TRY(f->sel[1].reserve(ctx, sizeof(uint32_t) * ((size_t)n + slack)));
+        f->pass.host_input = fact->mem == SR_MEM_HOST_PINNED ? 1 : 0;
         unsigned long long* cnt = f->pass_counters.as<unsigned long long>();
         SR_CUDA(ctx, cudaMemsetAsync(cnt, 0, 16 * sizeof(uint64_t), ctx->stream));
         const int sgrid = (int)std::min<int64_t>(f->stream_grid, (n + srd::STREAM_TILE - 1) / srd::STREAM_TILE);

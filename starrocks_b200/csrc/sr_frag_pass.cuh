@@ -27,7 +27,8 @@ struct PassDev {
     // fact columns the final pass reads: fetched for a row in one burst before anything depends on them
     int8_t final_vals[8];              // value ids, -1 = unused
     int8_t final_slot[SR_MAX_VALUES];  // value id -> index into final_vals, -1 = not prefetched
-    int8_t pad[4];
+    int8_t host_input; // the fact columns of this push live in pinned host memory (SR_MEM_HOST_PINNED)
+    int8_t pad[3];
 };
 
 #define SR_FINAL_PREFETCH 8
@@ -208,8 +209,15 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream(const FragDev* 
     for (int j = 0; j < STREAM_MAX_JOINS; j++)
 #pragma unroll
         for (int g = 0; g < STREAM_GROUPS; g++) pk[j][g] = make_int4(0, 0, 0, 0);
+    // Each CTA streams a CONTIGUOUS run of tiles (not a grid-stride walk): the rows a warp appends to one
+    // selection-vector chunk then come from a narrow band of the table (~25 tiles) instead of being spread over
+    // the whole batch, so the later gather passes touch neighbouring sectors / pages back to back.
+    const int64_t tiles_per_cta = (num_tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t tile_begin = (int64_t)blockIdx.x * tiles_per_cta;
+    const int64_t tile_end = tile_begin + tiles_per_cta < num_tiles ? tile_begin + tiles_per_cta : num_tiles;
+    const int64_t prefetch_end = tile_end < full_tiles ? tile_end : full_tiles;
     auto prefetch = [&](int64_t tile) {
-        if (fast && tile < full_tiles) {
+        if (fast && tile < prefetch_end) {
 #pragma unroll
             for (int g = 0; g < STREAM_GROUPS; g++) {
                 const int64_t r0 = tile * STREAM_TILE + (int64_t)g * (STREAM_BLOCK * STREAM_ROWS) + (int64_t)threadIdx.x * STREAM_ROWS;
@@ -218,11 +226,11 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream(const FragDev* 
             }
         }
     };
-    prefetch(blockIdx.x);
+    prefetch(tile_begin);
     WarpSelWriter writer;
     writer.init(sel_out, counter);
 
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int64_t tile = tile_begin; tile < tile_end; tile++) {
         int64_t row0[STREAM_GROUPS];
         uint32_t alive[STREAM_GROUPS];
 #pragma unroll
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream(const FragDev* 
             static_assert(STREAM_GROUPS == 2 && STREAM_ROWS == 4, "8 keys per thread and column");
             const int32_t k0[8] = {pk[0][0].x, pk[0][0].y, pk[0][0].z, pk[0][0].w, pk[0][1].x, pk[0][1].y, pk[0][1].z, pk[0][1].w};
             const int32_t k1[8] = {pk[1][0].x, pk[1][0].y, pk[1][0].z, pk[1][0].w, pk[1][1].x, pk[1][1].y, pk[1][1].z, pk[1][1].w};
-            prefetch(tile + gridDim.x); // next tile's keys stay in flight while this tile is tested
+            prefetch(tile + 1); // next tile's keys stay in flight while this tile is tested
             uint32_t a8 = join_test_batch<8>(s_joins[0], smem, k0, 0xFFu);
             if (two) a8 = join_test_batch<8>(s_joins[1], smem, k1, a8);
             alive[0] = a8 & 0xFu;
@@ -298,6 +306,18 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream(const FragDev* 
 
 constexpr int GATHER_BLOCK = 256;
 
+// the contiguous run [begin, end) of a selection vector of n entries that the calling warp owns (a multiple
+// of 32 entries, so every warp-wide read of the vector is one aligned 128-byte line)
+__device__ __forceinline__ void warp_sel_range(unsigned long long n, unsigned long long& begin, unsigned long long& end) {
+    const unsigned long long warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    const unsigned long long me = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    unsigned long long per = (n + warps - 1) / warps;
+    per = (per + 31) & ~31ull;
+    begin = me * per;
+    end = begin + per < n ? begin + per : n;
+    if (begin > n) begin = n;
+}
+
 // one selective join on the selected rows: sel_in[0, *n_in) -> sel_out (appended at *counter_out)
 __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_join(const FragDev* __restrict__ fdp, int32_t j, const __grid_constant__ VTab vt,
                                                                     const uint32_t* __restrict__ sel_in, const unsigned long long* __restrict__ n_in_ptr,
@@ -311,9 +331,12 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_join(const FragDev
     const VDesc& d = vt.v[fj.key_value_id];
     WarpSelWriter writer;
     writer.init(sel_out, counter_out);
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x; i0 < n_in; i0 += stride) {
-        const unsigned long long i = i0 + threadIdx.x;
+    // each warp walks its own contiguous run of the input vector (whole chunks of one producer warp), so what
+    // it appends keeps the producer's locality
+    unsigned long long w_begin, w_end;
+    warp_sel_range(n_in, w_begin, w_end);
+    for (unsigned long long i0 = w_begin; i0 < w_end; i0 += 32) {
+        const unsigned long long i = i0 + lane_id();
         bool hit = false;
         uint32_t row = SEL_INVALID;
         if (i < n_in) row = sel_in[i];
@@ -352,9 +375,12 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg(const FragDev*
     __syncthreads();
     const unsigned long long n_in = *n_in_ptr;
     unsigned long long passed = 0;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
+    unsigned long long w_begin, w_end;
+    warp_sel_range(n_in, w_begin, w_end);
+    for (unsigned long long i = w_begin + lane_id(); i < w_end; i += 32) {
         const uint32_t row = sel_in[i];
+        // (prefetch.global.L2 of the next row's host-resident values was measured: reads of mapped host memory are
+        // not kept in L2, the prefetch only doubled the PCIe requests -- 117 -> 224 ms on SSB Q4.1 SF100)
         if (row == SEL_INVALID) continue;
         // (a variant that fetched every fact value of the row in one burst before the dependent lookups was
         // measured slower on B200 -- more issue slots and registers than latency hidden, see profiles/)

@@ -157,10 +157,23 @@ struct Staged {
     std::vector<srd::DCol> cols;
     std::vector<int32_t> slots;
     int64_t num_rows = 0;
-    int32_t stage(sr_ctx* ctx, const sr_chunk_view* in, const std::vector<int32_t>* only_slots = nullptr) {
+    // device-visible alias of a page-locked, mapped host buffer (SR_MEM_HOST_PINNED); fails for pageable memory
+    static int32_t mapped_alias(sr_ctx* ctx, const void* host, int32_t slot, const void** dev) {
+        cudaPointerAttributes at;
+        memset(&at, 0, sizeof(at));
+        if (cudaPointerGetAttributes(&at, host) != cudaSuccess || at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) {
+            cudaGetLastError();
+            return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "slot %d: SR_MEM_HOST_PINNED buffer is not page-locked mapped host memory", slot);
+        }
+        *dev = at.devicePointer;
+        return SR_OK;
+    }
+    int32_t stage(sr_ctx* ctx, const sr_chunk_view* in, const std::vector<int32_t>* only_slots = nullptr, bool in_place_pinned = false) {
         cols.clear();
         slots.clear();
         num_rows = in->num_rows;
+        if (in->mem != SR_MEM_HOST && in->mem != SR_MEM_DEVICE && in->mem != SR_MEM_HOST_PINNED)
+            return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "unknown memory kind %d", in->mem);
         if ((int)bufs.size() < 2 * in->num_cols) {
             std::vector<DevBuf> nb(2 * in->num_cols);
             for (size_t i = 0; i < bufs.size(); i++) std::swap(nb[i], bufs[i]);
@@ -179,6 +192,15 @@ struct Staged {
             if (in->mem == SR_MEM_DEVICE) {
                 d.data = c.data;
                 d.nulls = c.nulls;
+            } else if (in->mem == SR_MEM_HOST_PINNED && in_place_pinned && in->num_rows > 0) {
+                const void* p = nullptr;
+                SR_TRY(mapped_alias(ctx, c.data, c.slot_id, &p));
+                d.data = p;
+                d.nulls = nullptr;
+                if (c.nulls) {
+                    SR_TRY(mapped_alias(ctx, c.nulls, c.slot_id, &p));
+                    d.nulls = (const uint8_t*)p;
+                }
             } else {
                 SR_TRY(bufs[2 * k].reserve(ctx, (size_t)in->num_rows * w + 16));
                 SR_CUDA(ctx, cudaMemcpyAsync(bufs[2 * k].p, c.data, (size_t)in->num_rows * w, cudaMemcpyHostToDevice, ctx->stream));

@@ -376,7 +376,7 @@ static int32_t join_append(sr_join* j, const sr_chunk_view* chunk) {
                 SR_CUDA(ctx, cudaMemsetAsync((uint8_t*)bc->nulls.p + (j->rows + 1), 0, (size_t)n, ctx->stream));
         }
     }
-    if (chunk->mem == SR_MEM_HOST) SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // caller may free host buffers
+    if (chunk->mem != SR_MEM_DEVICE) SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // caller may free host buffers
     j->rows += n;
     return SR_OK;
 }

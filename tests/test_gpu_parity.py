@@ -377,7 +377,8 @@ def test_agg_pull_paging_and_device_output(gpu, ctx):
 # ---------------------------------------------------------------------------------------------
 # fused fragment: SSB Q4.1 and Q1.1 shapes against the chunk-at-a-time oracle pipeline
 # ---------------------------------------------------------------------------------------------
-def _run_q41(gpu, ctx, oracle, sf, n, pushes=1, mode=0):
+def _run_q41(gpu, ctx, oracle, sf, n, pushes=1, mode=0, pinned=False):
+    import torch
     dims = ssb.gen_dims(sf)
     lo = ssb.gen_lineorder(sf, n=n)
     gjoins, gkeep = ssb.build_dims(gpu, dims, ssb.dim_plans_q41(), ctx=ctx)
@@ -388,7 +389,16 @@ def _run_q41(gpu, ctx, oracle, sf, n, pushes=1, mode=0):
         step = (n + pushes - 1) // pushes
         for p in range(pushes):
             part = {k: v[p * step:(p + 1) * step].copy() for k, v in lo.items()}
-            frag.push(ssb.fact_chunk(part, ssb.Q41_FACT_COLS))
+            if pinned:
+                # page-locked host columns read in place by the fragment kernels (SR_MEM_HOST_PINNED)
+                pin = {k: torch.from_numpy(part[k]).pin_memory() for k in ssb.Q41_FACT_COLS}
+                rows = len(part[ssb.Q41_FACT_COLS[0]])
+                frag.push(Chunk([(ssb.LO_SLOTS[k], pin[k].data_ptr(), None, abi.TYPE_INT) for k in ssb.Q41_FACT_COLS],
+                                num_rows=rows, mem=abi.MEM_HOST_PINNED))
+                ctx.sync()   # the buffers must outlive the asynchronous passes
+                del pin
+            else:
+                frag.push(ssb.fact_chunk(part, ssb.Q41_FACT_COLS))
         got = gpu_rows(frag.agg.result())
         passed = frag.rows_passed
         ores, opassed = oracle.fragment_run(abi.ScanDesc(), ojoins, agg_desc, ssb.fact_chunk(lo, ssb.Q41_FACT_COLS), num_threads=4)
@@ -414,6 +424,23 @@ def test_fragment_q41_parity(gpu, ctx, oracle, mode):
 def test_fragment_q41_multi_push_and_ragged(gpu, ctx, oracle, mode):
     _run_q41(gpu, ctx, oracle, sf=0.05, n=300_007, pushes=3, mode=mode)
     _run_q41(gpu, ctx, oracle, sf=0.01, n=5, pushes=1, mode=mode)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_fragment_q41_pinned_host_columns_in_place(gpu, ctx, oracle, mode):
+    _run_q41(gpu, ctx, oracle, sf=0.1, n=600_000, pushes=2, mode=mode, pinned=True)
+
+
+def test_fragment_rejects_pageable_memory_tagged_pinned(gpu, ctx):
+    lo = ssb.gen_lineorder(0.01, n=1000)
+    frag = gpu.Fragment(ctx, abi.ScanDesc(), [], ssb.q11_agg_desc())
+    try:
+        ch = ssb.fact_chunk(lo, ssb.Q11_FACT_COLS, mem=abi.MEM_HOST_PINNED)
+        with pytest.raises(gpu.GpuError) as ei:
+            frag.push(ch)
+        assert ei.value.code == abi.SR_ERR_INVALID_ARGUMENT
+    finally:
+        frag.close()
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
