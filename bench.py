@@ -42,6 +42,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=0, help="rows of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--merge", choices=["allreduce", "gather"], default="allreduce",
+                    help="N>1 merge of the partial aggregates: in-place all-reduce of the dense slot arrays (SURVEY 8e) or "
+                         "gather of partial rows to rank 0 + final aggregate (the reference plan's UNPARTITIONED exchange)")
     return ap.parse_args()
 
 
@@ -282,14 +285,25 @@ def run_gpu(args):
     final = gpu.Agg(ctx, final_desc) if world > 1 else None
     MAXG = 175
 
-    def step(chunk):
-        """one pass: push the shard, finish, pull the result to the host (N > 1: gather + final merge)"""
-        frag.reset()
-        frag.push(chunk)
+    def finish_step():
+        """tail of a step: merge across ranks (N > 1) and bring the result to the host of rank 0"""
+        if world > 1 and args.merge == "allreduce":
+            from starrocks_b200.distributed import all_reduce_dense_state
+            all_reduce_dense_state(frag.agg.dense_state(), dev)   # NCCL on the context's stream, in place
+            frag.agg.finish()
+            if rank != 0:
+                return None
+            return gpu.chunk_out_to_host(ctx, frag.agg.pull(mem=abi.MEM_HOST))
         frag.agg.finish()
         if world == 1:
             return gpu.chunk_out_to_host(ctx, frag.agg.pull(mem=abi.MEM_HOST))
         return step_tail(frag, final, ctx, gpu, abi, ssb, torch, dist, dev, world, rank, MAXG)
+
+    def step(chunk):
+        """one pass: push the shard, merge, pull the result to the host"""
+        frag.reset()
+        frag.push(chunk)
+        return finish_step()
 
     def barrier():
         if world > 1:
@@ -312,22 +326,28 @@ def run_gpu(args):
     barrier()
     ev0.record(stream)
     pass_ms = [0.0, 0.0, 0.0]
+    trace = [] if os.environ.get("SR_BENCH_TRACE") else None   # host-side phase timestamps (debug aid)
     for s in range(args.steps):
         # push() launches only the hot kernels of the path after the first batch (k_frag_stream,
         # k_frag_gather_join, k_frag_gather_agg -- or the single k_fragment in fused-cascade mode)
+        t0 = time.perf_counter()
         frag.reset()
         kev[s][0].record(stream)
         frag.push(dchunk)
         kev[s][1].record(stream)
-        frag.agg.finish()
-        if world == 1:
-            result = gpu.chunk_out_to_host(ctx, frag.agg.pull(mem=abi.MEM_HOST))
-        else:
-            result = step_tail(frag, final, ctx, gpu, abi, ssb, torch, dist, dev, world, rank, MAXG)
+        t1 = time.perf_counter()
+        result = finish_step()
+        t2 = time.perf_counter()
         pm = frag.last_pass_ms()  # events recorded inside push(); the step already synchronised on its result
         if pm is not None:
             pass_ms = [a + b for a, b in zip(pass_ms, pm)]
+        if trace is not None:
+            trace.append((t1 - t0, t2 - t1, time.perf_counter() - t2))
     ev1.record(stream)
+    if trace:
+        k = len(trace)
+        sys.stderr.write(f"[trace rank {rank}] enqueue reset+push {sum(t[0] for t in trace) / k * 1e3:.3f} ms, finish_step "
+                         f"{sum(t[1] for t in trace) / k * 1e3:.3f} ms, last_pass_ms {sum(t[2] for t in trace) / k * 1e3:.3f} ms\n")
     barrier()
     launches = ctx.launches - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -471,26 +491,19 @@ def run_gpu(args):
 def step_tail(frag, final, ctx, gpu, abi, ssb, torch, dist, dev, world, rank, MAXG):
     """N > 1 tail of a step: pull partial states on the device, gather to rank 0 over NCCL (the UNPARTITIONED exchange of
     the two-phase aggregate), final merge by a GPU aggregate on rank 0."""
-    from starrocks_b200.distributed import gather_partial_states
+    from starrocks_b200.distributed import all_gather_partial_states, device_view
     out = frag.agg.pull(mem=abi.MEM_DEVICE)
     g = out.num_rows
-    cols = []
-    for k in range(4):
-        w = abi.TYPE_WIDTH[out.cols[k].type]
-        t = torch.empty(g, dtype=torch.int32 if w == 4 else torch.int64, device=dev)
-        ctx.check(gpu.lib().sr_memcpy(ctx.h, t.data_ptr(), out.cols[k].data, g * w, 2))
-        cols.append(t)
-    gathered = gather_partial_states(cols, MAXG, dst=0)
+    # the pulled columns stay owned by the aggregate handle until its next pull: alias them, no copy
+    cols = [device_view(out.cols[k].data, g, abi.TYPE_WIDTH[out.cols[k].type], dev) for k in range(4)]
+    pc = all_gather_partial_states(cols, MAXG, dst=0)   # one NCCL collective, one host sync on rank 0
     if rank != 0:
         return None
     final.reset()
-    for pc in gathered:
-        ch = abi.Chunk([(ssb.D_YEAR, pc[0].to(torch.int32).contiguous(), None, abi.TYPE_INT),
-                        (ssb.C_NATION, pc[1].to(torch.int32).contiguous(), None, abi.TYPE_INT),
-                        (ssb.OUT_SUM_REVENUE, pc[2].contiguous(), None, abi.TYPE_BIGINT),
-                        (ssb.OUT_SUM_SUPPLYCOST, pc[3].contiguous(), None, abi.TYPE_BIGINT)], mem=abi.MEM_DEVICE)
-        final.push(ch)
-        ctx.sync()
+    keep = [pc[0].to(torch.int32), pc[1].to(torch.int32), pc[2], pc[3]]
+    final.push(abi.Chunk([(ssb.D_YEAR, keep[0], None, abi.TYPE_INT), (ssb.C_NATION, keep[1], None, abi.TYPE_INT),
+                          (ssb.OUT_SUM_REVENUE, keep[2], None, abi.TYPE_BIGINT),
+                          (ssb.OUT_SUM_SUPPLYCOST, keep[3], None, abi.TYPE_BIGINT)], mem=abi.MEM_DEVICE))
     return final.result()
 
 

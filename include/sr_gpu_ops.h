@@ -409,6 +409,27 @@ int32_t sr_agg_reset(sr_agg* agg);
  * Both handles must have been created from the same desc on the same context. */
 int32_t sr_agg_merge(sr_agg* agg, sr_agg* other);
 
+/* Element-wise mergeable view of a DENSE aggregate table (group-by columns with declared ranges, or no
+ * GROUP BY): one array per state component, every array indexed by the same slot number on every
+ * instance created from the same desc.  Partial states of fragment instances on several GPUs are then
+ * merged IN PLACE by an all-reduce per array (reduce = SR_REDUCE_SUM / MIN / MAX over int64 or double
+ * elements) -- SURVEY.md 8e "ncclAllReduce on a dense slot array when the group domain is tiny and
+ * enumerable" -- instead of the gather + sr_agg_merge exchange; afterwards every instance holds the
+ * final state and any of them can be pulled.  Call between the last push and the first pull.  The arrays
+ * are written by work queued on the context's stream: run the collective on that stream (or sr_ctx_sync
+ * first).  All instances must have been fed the same chunk schema (same column nullability), so that they
+ * expose the same list of arrays.  SR_ERR_NOT_SUPPORTED for hash tables and for 128-bit sums (carry is not
+ * element-wise). */
+typedef enum sr_state_reduce { SR_REDUCE_SUM = 0, SR_REDUCE_MIN = 1, SR_REDUCE_MAX = 2 } sr_state_reduce;
+typedef struct sr_agg_state_array {
+    void* data;        /* device pointer */
+    int64_t count;     /* elements */
+    int32_t elem_type; /* SR_TYPE_BIGINT or SR_TYPE_DOUBLE */
+    int32_t reduce;    /* sr_state_reduce */
+} sr_agg_state_array;
+#define SR_MAX_STATE_ARRAYS (1 + 3 * SR_MAX_AGG_FNS)
+int32_t sr_agg_dense_state(sr_agg* agg, sr_agg_state_array* arrays, int32_t max_arrays, int32_t* num_arrays);
+
 /* ---------------------------------------------------------------------------------------
  * fused pipeline fragment:  scan -> filter -> [hash-join probe]* -> hash aggregate in ONE
  * pass over the fact columns (no intermediate Chunk materialisation).  This is what the GPU

@@ -159,6 +159,13 @@ class sr_part_desc(C.Structure):
                 ("num_part_slots", C.c_int32), ("part_slots", C.c_int32 * SR_MAX_PART_KEYS)]
 
 
+STATE_REDUCE_SUM, STATE_REDUCE_MIN, STATE_REDUCE_MAX = 0, 1, 2
+
+
+class sr_agg_state_array(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("count", C.c_int64), ("elem_type", C.c_int32), ("reduce", C.c_int32)]
+
+
 # ---------------------------------------------------------------------------------------------
 # builders
 # ---------------------------------------------------------------------------------------------

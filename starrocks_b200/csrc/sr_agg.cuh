@@ -1096,13 +1096,6 @@ static int32_t agg_finish_output(sr_agg* a) {
         SR_TRY(agg_compile(a, Tf::f, Tf::n, (void*)&a->desc));
     }
     const srd::AggDev& h = a->host;
-    {
-        uint64_t ng;
-        int32_t ovf, bad;
-        SR_TRY(agg_read_counters(a, &ng, &ovf, &bad));
-        if (bad) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "a group-by value fell outside the declared group_min/group_max range");
-        if (ovf) return sr_fail(ctx, SR_ERR_STATE, "aggregate hash table overflow (internal)");
-    }
     const uint64_t total = (!h.dense && h.num_keys > 0) ? h.cap + 1 : h.cap;
     const int blocks = grid_for((int64_t)total, srd::EMIT_BLOCK);
     SR_TRY(a->block_counts.reserve(ctx, sizeof(uint32_t) * (size_t)blocks));
@@ -1111,12 +1104,23 @@ static int32_t agg_finish_output(sr_agg* a) {
     SR_LAUNCH_CHECK(ctx);
     srd::k_scan_counts<<<1, 1024, 0, ctx->stream>>>(a->block_counts.as<uint32_t>(), blocks, a->block_offsets.as<uint64_t>(), ctx->dscratch);
     SR_LAUNCH_CHECK(ctx);
+    // one read-back, one synchronisation: the row count and the table's status counters together
     SR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->dscratch, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned + 8, a->counters.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
     SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    {
+        const int32_t* fl = (const int32_t*)(ctx->pinned + 9);
+        if (fl[1]) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "a group-by value fell outside the declared group_min/group_max range");
+        if (fl[0]) return sr_fail(ctx, SR_ERR_STATE, "aggregate hash table overflow (internal)");
+    }
     const int64_t rows = (int64_t)ctx->pinned[0];
     const int nc = d.num_group_keys + d.num_fns;
-    a->out_bufs.clear();
-    a->out_bufs.resize(2 * (size_t)nc);
+    // output buffers are kept across finish/reset cycles (they only grow): a repeated query pays no cudaMalloc/cudaFree
+    if (a->out_bufs.size() < 2 * (size_t)nc) {
+        std::vector<DevBuf> nb(2 * (size_t)nc);
+        for (size_t i = 0; i < a->out_bufs.size(); i++) std::swap(nb[i], a->out_bufs[i]);
+        a->out_bufs.swap(nb);
+    }
     srd::EmitArgs ea;
     memset(&ea, 0, sizeof(ea));
     for (int k = 0; k < nc; k++) {

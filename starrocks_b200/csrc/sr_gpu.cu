@@ -552,6 +552,52 @@ int32_t sr_agg_reset(sr_agg* a) {
     return agg_reset_impl(a);
 }
 
+int32_t sr_agg_dense_state(sr_agg* a, sr_agg_state_array* arrays, int32_t max_arrays, int32_t* num_arrays) {
+    if (!a || !arrays || !num_arrays) return SR_ERR_INVALID_ARGUMENT;
+    sr_ctx* ctx = a->ctx;
+    SR_BIND(ctx);
+    *num_arrays = 0;
+    if (a->out_rows >= 0) return sr_fail(ctx, SR_ERR_STATE, "dense state requested after the output was materialised");
+    if (!a->compiled) return sr_fail(ctx, SR_ERR_STATE, "dense state requested before any input was pushed");
+    const srd::AggDev& h = a->host;
+    if (!h.dense && h.num_keys > 0) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "hash aggregate tables have no element-wise mergeable layout");
+    int n = 0;
+    auto add = [&](void* p, int32_t type, int32_t reduce) {
+        if (n < max_arrays) arrays[n] = sr_agg_state_array{p, (int64_t)h.cap, type, reduce};
+        n++;
+    };
+    add(h.cnt_star, SR_TYPE_BIGINT, SR_REDUCE_SUM);
+    for (int f = 0; f < h.num_fns; f++) {
+        const srd::AggFnDev& fn = h.fns[f];
+        switch (fn.mode) {
+        case srd::M_COUNT_STAR:
+            break; // cnt_star itself
+        case srd::M_COUNT:
+        case srd::M_SUM_I64:
+            add(fn.acc0, SR_TYPE_BIGINT, SR_REDUCE_SUM);
+            break;
+        case srd::M_SUM_F64:
+        case srd::M_AVG:
+            add(fn.acc0, SR_TYPE_DOUBLE, SR_REDUCE_SUM);
+            break;
+        case srd::M_MIN_I64:
+        case srd::M_MIN_F64: // doubles are kept as their order-preserving int64 image
+            add(fn.acc0, SR_TYPE_BIGINT, SR_REDUCE_MIN);
+            break;
+        case srd::M_MAX_I64:
+        case srd::M_MAX_F64:
+            add(fn.acc0, SR_TYPE_BIGINT, SR_REDUCE_MAX);
+            break;
+        default:
+            return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "aggregate function %d keeps a state that is not element-wise mergeable", f);
+        }
+        if (fn.accn) add(fn.accn, SR_TYPE_BIGINT, SR_REDUCE_SUM);
+    }
+    if (n > max_arrays) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "%d state arrays, room for %d", n, max_arrays);
+    *num_arrays = n;
+    return SR_OK;
+}
+
 int32_t sr_agg_merge(sr_agg* a, sr_agg* o) {
     if (!a || !o) return SR_ERR_INVALID_ARGUMENT;
     sr_ctx* ctx = a->ctx;
@@ -901,6 +947,10 @@ int32_t sr_abi_sizeof(int32_t which) {
         return (int32_t)sizeof(sr_fragment_desc);
     case 12:
         return (int32_t)sizeof(sr_part_desc);
+    case 13:
+        return (int32_t)sizeof(sr_agg_state_array);
+    case 14:
+        return (int32_t)sizeof(sr_fragment_plan);
     default:
         return -1;
     }

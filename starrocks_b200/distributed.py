@@ -37,6 +37,79 @@ def gather_partial_states(cols, max_rows, dst=0):
     return out
 
 
+class _DevicePtr:
+    """zero-copy view of a device buffer handed back by the C-ABI (sr_chunk_out column) for torch.as_tensor"""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_view(ptr, n, width, device):
+    """1-D integer tensor aliasing `n` values of `width` bytes at device address `ptr` (no copy)."""
+    if n == 0:
+        return torch.empty(0, dtype=torch.int32 if width == 4 else torch.int64, device=device)
+    return torch.as_tensor(_DevicePtr(ptr, n, "<i4" if width == 4 else "<i8"), device=device)
+
+
+def all_gather_partial_states(cols, max_rows, dst=0):
+    """Same exchange as gather_partial_states in ONE collective and one host sync: every rank contributes a packed
+    [len(cols) * max_rows + 1] int64 buffer (last word = its row count); `dst` returns one concatenated int64 tensor
+    per column (rank 0's rows first), the others return None without waiting."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    g = int(cols[0].numel())
+    if g > max_rows:
+        raise ValueError(f"{g} partial rows exceed the gather capacity {max_rows}")
+    dev = cols[0].device
+    nc = len(cols)
+    packed = torch.zeros(nc * max_rows + 1, dtype=torch.int64, device=dev)
+    for k, c in enumerate(cols):
+        packed[k * max_rows:k * max_rows + g] = c
+    packed[-1] = g
+    flat = torch.empty(world * (nc * max_rows + 1), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(flat, packed)
+    if rank != dst:
+        return None
+    out = flat.view(world, nc * max_rows + 1)
+    counts = [int(x) for x in out[:, -1].tolist()]
+    return [torch.cat([out[r, k * max_rows:k * max_rows + counts[r]] for r in range(world)]) for k in range(nc)]
+
+
+_REDUCE_OPS = {0: "SUM", 1: "MIN", 2: "MAX"}
+
+
+def dense_state_views(arrays, device):
+    """[(tensor aliasing the state array, reduce code)] for what sr_agg_dense_state returned"""
+    out = []
+    for ptr, count, elem_type, reduce in arrays:
+        typestr = "<f8" if elem_type == 8 else "<i8"   # SR_TYPE_DOUBLE = 8, else int64 states
+        out.append((torch.as_tensor(_DevicePtr(ptr, count, typestr), device=device), reduce))
+    return out
+
+
+def all_reduce_dense_state(arrays, device):
+    """In-place merge of dense aggregate tables across ranks (all-reduce on the enumerable slot array).
+    arrays: what sr_agg_dense_state returned on this rank -- [(device_ptr, count, elem_type, reduce)]; every rank
+    passes the same list shape.  Afterwards every rank's table holds the final states."""
+    views = [(t, getattr(dist.ReduceOp, _REDUCE_OPS[reduce])) for t, reduce in dense_state_views(arrays, device)]
+    # adjacent arrays with the same operator and dtype travel in one collective
+    k = 0
+    while k < len(views):
+        t, op = views[k]
+        group = [t]
+        while k + len(group) < len(views) and views[k + len(group)][1] == op and views[k + len(group)][0].dtype == t.dtype:
+            group.append(views[k + len(group)][0])
+        if len(group) == 1:
+            dist.all_reduce(t, op=op)
+        else:
+            flat = torch.cat(group)
+            dist.all_reduce(flat, op=op)
+            off = 0
+            for g in group:
+                g.copy_(flat[off:off + g.numel()])
+                off += g.numel()
+        k += len(group)
+
+
 def exchange_partitions(cols, channel_offsets):
     """HASH_PARTITIONED exchange.  cols: list of 1-D tensors already reordered so that the rows of channel c occupy
     [channel_offsets[c], channel_offsets[c+1]) (what sr_xchg_partition / the reference's counting sort produce);

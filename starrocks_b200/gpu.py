@@ -76,6 +76,7 @@ def lib():
         "sr_agg_num_groups": (i64, [vp]),
         "sr_agg_pull": (i32, [vp, i64, i32, vp]),
         "sr_agg_merge": (i32, [vp, vp]),
+        "sr_agg_dense_state": (i32, [vp, vp, i32, vp]),
         "sr_agg_reset": (i32, [vp]),
         "sr_fragment_reset": (i32, [vp]),
         "sr_fragment_get_plan": (i32, [vp, vp]),
@@ -111,7 +112,7 @@ EXPORTED_SYMBOLS = [
     "sr_scan_filter", "sr_scan_evaluate", "sr_join_create", "sr_join_destroy", "sr_join_append_build",
     "sr_join_build_finish", "sr_join_is_build_done", "sr_join_get_info", "sr_join_copy_table", "sr_join_probe",
     "sr_join_probe_indexes", "sr_join_key_hash", "sr_agg_create", "sr_agg_destroy", "sr_agg_push",
-    "sr_agg_sink_finish", "sr_agg_num_groups", "sr_agg_pull", "sr_agg_merge", "sr_agg_reset", "sr_fragment_reset", "sr_fragment_get_plan", "sr_fragment_last_pass_ms",
+    "sr_agg_sink_finish", "sr_agg_num_groups", "sr_agg_pull", "sr_agg_merge", "sr_agg_dense_state", "sr_agg_reset", "sr_fragment_reset", "sr_fragment_get_plan", "sr_fragment_last_pass_ms",
     "sr_fragment_create",
     "sr_fragment_destroy", "sr_fragment_push", "sr_fragment_agg", "sr_fragment_rows_passed", "sr_xchg_create",
     "sr_xchg_destroy", "sr_xchg_partition", "sr_xchg_hash", "sr_gather", "sr_memcpy", "sr_abi_sizeof", "sr_bandwidth_probe", "sr_flush_l2",
@@ -302,6 +303,14 @@ class Agg:
 
     def reset(self):
         self.ctx.check(lib().sr_agg_reset(self.h))
+
+    def dense_state(self):
+        """[(device_ptr, count, elem_type, reduce)] -- the element-wise mergeable arrays of a dense table"""
+        n_max = 1 + 3 * abi.SR_MAX_AGG_FNS
+        arr = (abi.sr_agg_state_array * n_max)()
+        n = C.c_int32(0)
+        self.ctx.check(lib().sr_agg_dense_state(self.h, arr, n_max, C.byref(n)))
+        return [(arr[k].data, arr[k].count, arr[k].elem_type, arr[k].reduce) for k in range(n.value)]
 
     @property
     def num_groups(self):

@@ -31,7 +31,7 @@ def _init(rank, world, port):
 
 def _two_phase_worker(rank, world, port, q):
     from oracle import oracle
-    from starrocks_b200.distributed import gather_partial_states
+    from starrocks_b200.distributed import all_gather_partial_states, gather_partial_states
     from tests.helpers import oracle_rows
     _init(rank, world, port)
     dims = ssb.gen_dims(0.05)
@@ -43,6 +43,12 @@ def _two_phase_worker(rank, world, port, q):
     out = part.output()
     cols = [torch.from_numpy(np.ascontiguousarray(o[1]).astype(np.int64)) for o in out]
     gathered = gather_partial_states(cols, max_rows=175, dst=0)
+    packed = all_gather_partial_states(cols, max_rows=175, dst=0)      # same exchange, one collective (bench.py's path)
+    if rank == 0:
+        for k in range(len(cols)):
+            assert torch.equal(packed[k], torch.cat([g[k] for g in gathered]))
+    else:
+        assert packed is None and gathered is None
     if rank == 0:
         final_desc = abi.make_agg_desc([ssb.D_YEAR, ssb.C_NATION], [abi.TYPE_INT, abi.TYPE_INT],
                                        fns=[(abi.AGG_SUM, abi.TYPE_BIGINT, 50, [("col", 50)]), (abi.AGG_SUM, abi.TYPE_BIGINT, 51, [("col", 51)])])

@@ -327,6 +327,50 @@ def test_agg_parity(gpu, ctx, oracle, name, n):
         ga.close()
 
 
+@pytest.mark.parametrize("name", ["dense_b", "nogroup_b"])
+def test_agg_dense_state_elementwise_merge(gpu, ctx, oracle, name):
+    # two "fragment instances" aggregate disjoint halves; their dense tables are merged in place by the element-wise
+    # reduction an all-reduce would apply (sr_agg_dense_state), then either instance yields the final result
+    import torch
+    from starrocks_b200.distributed import dense_state_views
+    rng = np.random.default_rng(11)
+    n = 50_001
+    d, cols, fl = _agg_case(name, n, rng)
+    def sub(lo, hi):
+        return Chunk([(c[0], c[1][lo:hi].copy(), None if c[2] is None else c[2][lo:hi].copy()) + tuple(c[3:]) for c in cols])
+    a, b, oa = gpu.Agg(ctx, d), gpu.Agg(ctx, d), oracle.Agg(d)
+    try:
+        a.push(sub(0, n // 2))
+        b.push(sub(n // 2, n))
+        oa.push(sub(0, n))
+        ctx.sync()
+        va, vb = dense_state_views(a.dense_state(), "cuda:0"), dense_state_views(b.dense_state(), "cuda:0")
+        assert len(va) == len(vb) >= 2
+        for (ta, ra), (tb, rb) in zip(va, vb):
+            assert ra == rb and ta.shape == tb.shape and ta.dtype == tb.dtype
+            merged = ta + tb if ra == abi.STATE_REDUCE_SUM else (torch.minimum(ta, tb) if ra == abi.STATE_REDUCE_MIN else torch.maximum(ta, tb))
+            ta.copy_(merged)
+        torch.cuda.synchronize()
+        assert_rows_equal(gpu_rows(a.result()), oracle_rows(oa), float_cols=fl)
+    finally:
+        a.close()
+        b.close()
+
+
+@pytest.mark.parametrize("name", ["dense_a", "hash1_b"])
+def test_agg_dense_state_refused_when_not_elementwise(gpu, ctx, name):
+    rng = np.random.default_rng(12)
+    d, cols, _ = _agg_case(name, 1000, rng)
+    a = gpu.Agg(ctx, d)
+    try:
+        a.push(Chunk([(c[0], c[1], c[2]) + tuple(c[3:]) for c in cols]))
+        with pytest.raises(gpu.GpuError) as ei:
+            a.dense_state()
+        assert ei.value.code == abi.SR_ERR_NOT_SUPPORTED     # 128-bit decimal sum / hash table
+    finally:
+        a.close()
+
+
 def test_agg_hash_growth_two_pass(gpu, ctx, oracle):
     # 3 M rows, ~2.6 M distinct int64 keys: forces the find/insert + update two-pass path and a table growth
     rng = np.random.default_rng(9)
