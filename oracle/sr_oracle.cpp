@@ -1271,7 +1271,8 @@ struct FnState {
 
 struct Key128 {
     uint64_t lo = 0, hi = 0;
-    bool operator==(const Key128& o) const { return lo == o.lo && hi == o.hi; }
+    uint32_t nul = 0; // bit k: group key k is NULL (kept apart so that 16 full key bytes fit)
+    bool operator==(const Key128& o) const { return lo == o.lo && hi == o.hi && nul == o.nul; }
 };
 
 struct orc_agg {
@@ -1334,7 +1335,7 @@ extern "C" orc_agg* orc_agg_create(const sr_agg_desc* desc) {
         a->key_off_bits[k] = bits;
         bits += 8 * w;
     }
-    if (bits + desc->num_group_keys > 128) {
+    if (bits > 128) {
         delete a;
         fail(SR_ERR_NOT_SUPPORTED, "group key wider than 16 bytes");
         return nullptr;
@@ -1367,7 +1368,7 @@ static void agg_grow(orc_agg* a) {
     std::vector<int32_t> ng(ncap, -1);
     const uint64_t mask = ncap - 1;
     for (int64_t g = 0; g < a->num_groups; g++) {
-        uint64_t s = mix64(a->group_keys[g].lo ^ mix64(a->group_keys[g].hi)) & mask;
+        uint64_t s = mix64(a->group_keys[g].lo ^ mix64(a->group_keys[g].hi + a->group_keys[g].nul)) & mask;
         while (ng[s] >= 0) s = (s + 1) & mask;
         ng[s] = (int32_t)g;
         nk[s] = a->group_keys[g];
@@ -1378,7 +1379,7 @@ static void agg_grow(orc_agg* a) {
 }
 
 static inline int32_t agg_find_or_insert(orc_agg* a, const Key128& k) {
-    uint64_t s = mix64(k.lo ^ mix64(k.hi)) & a->cap_mask;
+    uint64_t s = mix64(k.lo ^ mix64(k.hi + k.nul)) & a->cap_mask;
     while (true) {
         const int32_t g = a->slot_group[s];
         if (g < 0) break;
@@ -1419,10 +1420,10 @@ static inline uint64_t key_get(const Key128& k, int off_bits, int w) {
 // null flags of group keys live in the top bits of `hi` (bit 127-k): a NULL key is its own
 // group (agg_hash_map.h:363-395 keeps a dedicated null-key state).
 static inline void key_set_null(Key128* k, int idx) {
-    k->hi |= 1ull << (63 - idx);
+    k->nul |= 1u << idx;
 }
 static inline bool key_is_null(const Key128& k, int idx) {
-    return (k.hi >> (63 - idx)) & 1;
+    return (k.nul >> idx) & 1;
 }
 
 static inline void fn_update_int(FnState& s, int32_t kind, int64_t v) {

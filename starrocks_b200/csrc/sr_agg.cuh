@@ -61,7 +61,7 @@ struct AggDev {
     int32_t key_nullable[SR_MAX_GROUP_KEYS];
     int32_t key_shift[SR_MAX_GROUP_KEYS]; // bit offset inside the packed key
     int32_t null_shift;                   // bit offset of the null-flag byte
-    int32_t pad0;
+    int32_t wide;                         // packed key of 9..16 bytes: hkeys holds (lo, hi) pairs, claimed with a 128-bit CAS
     long long dense_min[SR_MAX_GROUP_KEYS];
     long long dense_extent[SR_MAX_GROUP_KEYS]; // range + nullable
     long long dense_stride[SR_MAX_GROUP_KEYS];
@@ -173,6 +173,43 @@ __device__ __forceinline__ void acc_merge(int32_t mode, long long* a0, long long
     }
 }
 
+// ---- packed group key: up to 8 bytes in one word, or (wide) 9..16 bytes in a 16-byte aligned (lo, hi) pair.
+// A column never straddles the two words (agg_compile lays them out that way).  An empty slot is all ones.
+struct HKey {
+    unsigned long long lo, hi;
+};
+__device__ __forceinline__ void hkey_or(HKey& k, unsigned long long bits, int shift) {
+    if (shift < 64)
+        k.lo |= bits << shift;
+    else
+        k.hi |= bits << (shift - 64);
+}
+__device__ __forceinline__ unsigned long long hkey_bits(const HKey& k, int shift) { return shift < 64 ? k.lo >> shift : k.hi >> (shift - 64); }
+__device__ __forceinline__ bool hkey_is_empty(const AggDev& a, const HKey& k) { return k.lo == SR_AGG_EMPTY && (!a.wide || k.hi == SR_AGG_EMPTY); }
+__device__ __forceinline__ bool hkey_eq(const AggDev& a, const HKey& x, const HKey& y) { return x.lo == y.lo && (!a.wide || x.hi == y.hi); }
+__device__ __forceinline__ unsigned long long hkey_hash(const AggDev& a, const HKey& k) { return a.wide ? mix64(k.lo ^ mix64(k.hi + 0x9e3779b97f4a7c15ull)) : mix64(k.lo); }
+__device__ __forceinline__ HKey hkey_load(const AggDev& a, unsigned long long s) {
+    if (!a.wide) return HKey{a.hkeys[s], 0};
+    HKey v; // ONE 16-byte access: a claim publishes both words at once, a split load could pair an old lo with a new hi
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "l"(a.hkeys + 2 * s) : "memory");
+    return v;
+}
+// try to claim the empty slot s for `key`; returns what the slot held before (empty = we own it now)
+__device__ __forceinline__ HKey hkey_claim(const AggDev& a, unsigned long long s, const HKey& key) {
+    if (!a.wide) return HKey{atomicCAS(&a.hkeys[s], SR_AGG_EMPTY, key.lo), 0};
+    HKey old;
+    asm volatile(
+            "{ .reg .b128 c, n, o;\n"
+            "  mov.b128 c, {%2, %3};\n"
+            "  mov.b128 n, {%4, %5};\n"
+            "  atom.global.cas.b128 o, [%6], c, n;\n"
+            "  mov.b128 {%0, %1}, o; }"
+            : "=l"(old.lo), "=l"(old.hi)
+            : "l"(SR_AGG_EMPTY), "l"(SR_AGG_EMPTY), "l"(key.lo), "l"(key.hi), "l"(a.hkeys + 2 * s)
+            : "memory");
+    return old;
+}
+
 // slot of the row's group; -1 when the row cannot be placed (flags set)
 template <typename Loader>
 __device__ __forceinline__ long long agg_find_slot(const AggDev& a, Loader& ld) {
@@ -202,38 +239,38 @@ __device__ __forceinline__ long long agg_find_slot(const AggDev& a, Loader& ld) 
         }
         return slot;
     }
-    unsigned long long key = 0;
+    HKey key{0, 0};
 #pragma unroll
     for (int k = 0; k < SR_MAX_GROUP_KEYS; k++) {
         if (k < a.num_keys) {
             int64_t v;
             const bool nul = ld.load(a.key_value_id[k], v);
             if (nul) {
-                key |= 1ull << (a.null_shift + k);
+                hkey_or(key, 1ull, a.null_shift + k);
             } else {
                 const int w = a.key_width[k];
                 const unsigned long long m = w == 8 ? ~0ull : ((1ull << (8 * w)) - 1);
-                key |= ((unsigned long long)v & m) << a.key_shift[k];
+                hkey_or(key, (unsigned long long)v & m, a.key_shift[k]);
             }
         }
     }
-    if (key == SR_AGG_EMPTY) return (long long)a.cap; // only possible for full 8-byte keys
-    unsigned long long s = mix64(key) & a.mask;
+    if (hkey_is_empty(a, key)) return (long long)a.cap; // only possible for full 8- / 16-byte keys
+    unsigned long long s = hkey_hash(a, key) & a.mask;
     for (unsigned long long tries = 0; tries <= a.mask; tries++) {
-        unsigned long long cur = a.hkeys[s];
-        if (cur == key) return (long long)s;
-        if (cur == SR_AGG_EMPTY) {
+        HKey cur = hkey_load(a, s);
+        if (hkey_eq(a, cur, key)) return (long long)s;
+        if (hkey_is_empty(a, cur)) {
             // admission control: refuse new groups beyond the limit (host grows and retries)
             if (*(volatile unsigned long long*)a.ngroups >= a.limit) {
                 a.flags[0] = 1;
                 return -1;
             }
-            cur = atomicCAS(&a.hkeys[s], SR_AGG_EMPTY, key);
-            if (cur == SR_AGG_EMPTY) {
+            cur = hkey_claim(a, s, key);
+            if (hkey_is_empty(a, cur)) {
                 atomicAdd(a.ngroups, 1ull);
                 return (long long)s;
             }
-            if (cur == key) return (long long)s;
+            if (hkey_eq(a, cur, key)) return (long long)s;
         }
         s = (s + 1) & a.mask;
     }
@@ -501,12 +538,12 @@ __global__ void __launch_bounds__(256) k_agg_rehash(const AggDev* __restrict__ o
             if (o.cnt_star[s] == 0) continue;
             t = a.cap;
         } else {
-            const unsigned long long key = o.hkeys[s];
-            if (key == SR_AGG_EMPTY) continue;
-            t = mix64(key) & a.mask;
+            const HKey key = hkey_load(o, s);
+            if (hkey_is_empty(o, key)) continue;
+            t = hkey_hash(a, key) & a.mask;
             while (true) {
-                const unsigned long long cur = atomicCAS(&a.hkeys[t], SR_AGG_EMPTY, key);
-                if (cur == SR_AGG_EMPTY) break;
+                const HKey cur = hkey_claim(a, t, key);
+                if (hkey_is_empty(a, cur)) break;
                 t = (t + 1) & a.mask;
             }
         }
@@ -533,17 +570,19 @@ __global__ void __launch_bounds__(256) k_agg_merge(const AggDev* __restrict__ od
         } else if (s == o.cap) {
             t = (long long)a.cap;
         } else {
-            const unsigned long long key = o.hkeys[s];
-            unsigned long long q = mix64(key) & a.mask;
+            const HKey key = hkey_load(o, s);
+            unsigned long long q = hkey_hash(a, key) & a.mask;
             t = -1;
             for (unsigned long long tries = 0; tries <= a.mask; tries++) {
-                unsigned long long cur = a.hkeys[q];
-                if (cur == SR_AGG_EMPTY) {
-                    cur = atomicCAS(&a.hkeys[q], SR_AGG_EMPTY, key);
-                    if (cur == SR_AGG_EMPTY) atomicAdd(a.ngroups, 1ull);
-                    if (cur == SR_AGG_EMPTY) cur = key;
+                HKey cur = hkey_load(a, q);
+                if (hkey_is_empty(a, cur)) {
+                    cur = hkey_claim(a, q, key);
+                    if (hkey_is_empty(a, cur)) {
+                        atomicAdd(a.ngroups, 1ull);
+                        cur = key;
+                    }
                 }
-                if (cur == key) {
+                if (hkey_eq(a, cur, key)) {
                     t = (long long)q;
                     break;
                 }
@@ -639,14 +678,14 @@ __global__ void __launch_bounds__(EMIT_BLOCK) k_agg_emit(const AggDev* __restric
             if (ea.keys[k].nulls) ea.keys[k].nulls[o] = nul ? 1 : 0;
         }
     } else if (a.num_keys > 0) {
-        const unsigned long long key = s == a.cap ? SR_AGG_EMPTY : a.hkeys[s];
+        const HKey key = s == a.cap ? HKey{SR_AGG_EMPTY, SR_AGG_EMPTY} : hkey_load(a, s);
         for (int k = 0; k < a.num_keys; k++) {
             const int w = a.key_width[k];
             const unsigned long long m = w == 8 ? ~0ull : ((1ull << (8 * w)) - 1);
-            unsigned long long raw = (key >> a.key_shift[k]) & m;
+            unsigned long long raw = hkey_bits(key, a.key_shift[k]) & m;
             long long v = (long long)raw;
             if (w < 8 && a.key_type[k] != SR_TYPE_BOOLEAN) v = (long long)(raw << (64 - 8 * w)) >> (64 - 8 * w); // sign extend
-            const bool nul = a.key_nullable[k] && ((key >> (a.null_shift + k)) & 1ull);
+            const bool nul = a.key_nullable[k] && (hkey_bits(key, a.null_shift + k) & 1ull);
             store_int_typed(ea.keys[k].data, w, o, nul ? 0 : v);
             if (ea.keys[k].nulls) ea.keys[k].nulls[o] = nul ? 1 : 0;
         }
@@ -784,8 +823,9 @@ static int32_t agg_alloc_tables(sr_agg* a, srd::AggDev* h, uint64_t cap, DevBuf*
     h->mask = cap - 1;
     h->limit = hash ? cap / 2 : ~0ull;
     if (hash) {
-        SR_TRY(hkeys->reserve(ctx, sizeof(uint64_t) * total));
-        srd::k_fill_u64<<<grid, 256, 0, ctx->stream>>>(hkeys->as<unsigned long long>(), (int64_t)total, SR_AGG_EMPTY);
+        const uint64_t kwords = total * (h->wide ? 2 : 1);
+        SR_TRY(hkeys->reserve(ctx, sizeof(uint64_t) * kwords));
+        srd::k_fill_u64<<<grid, 256, 0, ctx->stream>>>(hkeys->as<unsigned long long>(), (int64_t)kwords, SR_AGG_EMPTY);
         SR_LAUNCH_CHECK(ctx);
         h->hkeys = hkeys->as<unsigned long long>();
     } else {
@@ -839,14 +879,23 @@ static int32_t agg_compile(sr_agg* a, slot_type_fn tf, agg_nullable_fn nf, void*
         if (id >= SR_MAX_VALUES) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "too many distinct columns");
         h.key_value_id[k] = id;
         h.key_width[k] = srd::type_width(t);
+        if (h.key_width[k] > 8) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "group-by slot %d: 128-bit group keys are not supported", d.group_slots[k]);
         h.key_type[k] = d.group_types[k];
         h.key_nullable[k] = (d.group_nullable[k] || nf(user, d.group_slots[k])) ? 1 : 0;
         any_nullable |= h.key_nullable[k] != 0;
-        h.key_shift[k] = bits;
-        bits += 8 * h.key_width[k];
     }
+    // pack widest first: every column then starts at a multiple of its own width and never straddles the (lo, hi) words
+    for (int w = 8; w >= 1; w >>= 1)
+        for (int k = 0; k < d.num_group_keys; k++) {
+            if (h.key_width[k] != w) continue;
+            if (bits < 64 && bits + 8 * w > 64) bits = 64;
+            h.key_shift[k] = bits;
+            bits += 8 * w;
+        }
+    if (any_nullable && bits < 64 && bits + 8 > 64) bits = 64;
     h.null_shift = bits;
     h.key_bytes = bits / 8 + (any_nullable ? 1 : 0);
+    h.wide = h.key_bytes > 8 ? 1 : 0;
     for (int f = 0; f < d.num_fns; f++) {
         const sr_agg_fn& fn = d.fns[f];
         srd::AggFnDev& fd = h.fns[f];
@@ -924,7 +973,7 @@ static int32_t agg_compile(sr_agg* a, slot_type_fn tf, agg_nullable_fn nf, void*
         }
     }
     if (!h.dense) {
-        if (h.key_bytes > 8) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "packed group-by key of %d bytes (> 8) without usable ranges", h.key_bytes);
+        if (h.key_bytes > 16) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "packed group-by key of %d bytes (> 16) without usable ranges", h.key_bytes);
         cap = 1ull << 21;
         const uint64_t want = d.expected_groups > 0 ? (uint64_t)d.expected_groups * 2 : 0;
         while (cap < want) cap <<= 1;

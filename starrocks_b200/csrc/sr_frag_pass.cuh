@@ -79,7 +79,11 @@ __device__ __forceinline__ uint32_t join_test_batch(const FragJoinDev& fj, const
             for (int i = 0; i < N; i++) {
                 const uint32_t idx = (uint32_t)keys[i] - umin;
                 const bool p = ((alive >> i) & 1u) && idx <= span;
+#ifdef SR_EXPERIMENT_FAKE_SMEM
+                words[i] = p ? smem[(idx >> 5) & 4095u] : 0u; // timing experiment only: WRONG results
+#else
                 words[i] = ldg_u32_pred(fj.j.bitmap + (idx >> 5), p);
+#endif
             }
 #pragma unroll
             for (int i = 0; i < N; i++) {

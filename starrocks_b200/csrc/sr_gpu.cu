@@ -524,7 +524,7 @@ static int32_t agg_reset_impl(sr_agg* a) {
     const uint64_t total = hash ? h.cap + 1 : h.cap;
     const int grid = std::min(grid_for((int64_t)total, 256), ctx->num_sms * 8);
     if (hash) {
-        srd::k_fill_u64<<<grid, 256, 0, ctx->stream>>>(a->hkeys.as<unsigned long long>(), (int64_t)total, SR_AGG_EMPTY);
+        srd::k_fill_u64<<<grid, 256, 0, ctx->stream>>>(a->hkeys.as<unsigned long long>(), (int64_t)(total * (h.wide ? 2 : 1)), SR_AGG_EMPTY);
         SR_LAUNCH_CHECK(ctx);
     }
     SR_CUDA(ctx, cudaMemsetAsync(a->cnt_star.p, 0, sizeof(int64_t) * total, ctx->stream));

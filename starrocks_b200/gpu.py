@@ -22,7 +22,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 def build(verbose=False):
     """compile libsr_gpu.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
     src = os.path.join(_HERE, "csrc", "sr_gpu.cu")
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, src]
+    extra = os.environ.get("SR_NVCC_EXTRA", "").split()   # e.g. -DSR_EXPERIMENT_... for timing experiments
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, src]
     subprocess.check_call(cmd)
     return LIB_PATH
 

@@ -280,6 +280,13 @@ def _agg_case(name, n, rng):
     vd = rng.normal(100, 50, n)
     vf = rng.random(n).astype(np.float32)
     dec = rng.integers(-2**62, 2**62, n, dtype=np.int64)
+    if "lowcard" in name:
+        k3 = k3 % 5
+    if "full16" in name:          # the all-ones 16-byte key (-1, -1) collides with the empty marker: special slot
+        k3[::97] = -1
+        v64[::97] = -1
+        k3[1::2] = k3[:-1:2][:len(k3[1::2])]
+        v64[1::2] = v64[:-1:2][:len(v64[1::2])]
     cols = [(0, k1, rand_nulls(rng, n, 0.05) if "nullkey" in name else None), (1, k2, None), (2, k3, None),
             (3, v32, rand_nulls(rng, n, 0.2) if "nullval" in name else None), (4, v64, None), (5, vd, None), (6, vf, None),
             (7, dec, None, abi.TYPE_DECIMAL64)]
@@ -297,6 +304,13 @@ def _agg_case(name, n, rng):
         d = abi.make_agg_desc([0, 1], [abi.TYPE_INT, abi.TYPE_SMALLINT], fns=fns if "_a" in name else fns2,
                               ranges=[(0, 6), (-3, 3)], group_nullable=[1 if "nullkey" in name else 0, 0])
         fl = (2 + 3, 2 + 6) if "_a" in name else (2 + 1, 2 + 3)
+    elif name.startswith("wide_full16"):   # two int64 keys: exactly 16 packed bytes (128-bit CAS claim)
+        d = abi.make_agg_desc([2, 4], [abi.TYPE_BIGINT, abi.TYPE_BIGINT], fns=fns2)
+        fl = (2 + 1, 2 + 3)
+    elif name.startswith("wide"):          # int32 + int64 + int16 (+ null flags): 14..15 packed bytes
+        d = abi.make_agg_desc([0, 2, 1], [abi.TYPE_INT, abi.TYPE_BIGINT, abi.TYPE_SMALLINT], fns=fns,
+                              group_nullable=[1 if "nullkey" in name else 0, 0, 0])
+        fl = (3 + 3, 3 + 6)
     elif name.startswith("hash2"):
         d = abi.make_agg_desc([0, 1], [abi.TYPE_INT, abi.TYPE_SMALLINT], fns=fns, group_nullable=[1 if "nullkey" in name else 0, 0])
         fl = (2 + 3, 2 + 6)
@@ -307,7 +321,8 @@ def _agg_case(name, n, rng):
 
 
 @pytest.mark.parametrize("name", ["nogroup_a", "nogroup_b", "nogroup_a_nullval", "dense_a", "dense_b", "dense_a_nullkey_nullval",
-                                  "hash2_a", "hash2_a_nullkey_nullval", "hash1_b"])
+                                  "hash2_a", "hash2_a_nullkey_nullval", "hash1_b", "wide_a", "wide_lowcard_nullkey_nullval",
+                                  "wide_full16"])
 @pytest.mark.parametrize("n", [0, 1, 1000, 70001])
 def test_agg_parity(gpu, ctx, oracle, name, n):
     rng = np.random.default_rng(5)
@@ -545,6 +560,48 @@ def test_fragment_hash_group_and_semi_join(gpu, ctx, oracle, mode):
             frag.close()
         gj1.close()
         gj2.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_fragment_tpch_q3_parity(gpu, ctx, oracle, mode):
+    # TPC-H Q3 shape: customer -> J1, orders SEMI J1 -> J2 (payload), lineitem INNER J2 -> group by a 12-byte key
+    # (l_orderkey, o_orderdate, o_shippriority), SUM(decimal64 expression) -> decimal128
+    from starrocks_b200 import tpch
+    t = tpch.gen_tables(0.1)
+    li = t["lineitem"]
+    gj2, gkeep = tpch.q3_build_gpu(gpu, ctx, t)
+    oj2, okeep = tpch.q3_build_oracle(oracle, t)
+    assert gj2.info().build_rows == oj2.build_rows > 0
+    _, _, _, _, li_scan = tpch.q3_descs()
+    agg_desc = tpch.q3_agg_desc()
+    payload = [tpch.O_ORDERDATE, tpch.O_SHIPPRIORITY]
+    frag = gpu.Fragment(ctx, li_scan, [(gj2, tpch.L_ORDERKEY, payload)], agg_desc, mode=mode)
+    try:
+        n = len(li["l_orderkey"])
+        for lo, hi in ((0, n // 2), (n // 2, n)):
+            frag.push(tpch.table_chunk(li, tpch.LINEITEM_COLS, rows=(lo, hi)))
+        got = gpu_rows(frag.agg.result())
+        ores, opassed = oracle.fragment_run(li_scan, [(oj2, tpch.L_ORDERKEY, payload)], agg_desc,
+                                            tpch.table_chunk(li, tpch.LINEITEM_COLS), num_threads=3)
+        assert frag.rows_passed == opassed > 0
+        assert_rows_equal(got, oracle_rows(ores))
+        # independent restatement with numpy on a handful of groups
+        cust_ok = set(t["customer"]["c_custkey"][t["customer"]["c_mktsegment"] == tpch.BUILDING].tolist())
+        o = t["orders"]
+        okeys = {int(k): int(d) for k, c, d in zip(o["o_orderkey"], o["o_custkey"], o["o_orderdate"]) if d < tpch.CUTOFF and int(c) in cust_ok}
+        m = (li["l_shipdate"] > tpch.CUTOFF) & np.isin(li["l_orderkey"], np.fromiter(okeys.keys(), dtype=np.int32))
+        rev = {}
+        for k, p, d in zip(li["l_orderkey"][m].tolist(), li["l_extendedprice"][m].tolist(), li["l_discount"][m].tolist()):
+            rev[k] = rev.get(k, 0) + p * (100 - d)
+        assert len(got) == len(rev)
+        for row in got[:50]:
+            assert row[1] == okeys[row[0]] and row[2] == 0 and row[3] == rev[row[0]]
+    finally:
+        frag.close()
+        gj2.close()
+        for x in gkeep:
+            if hasattr(x, "close"):
+                x.close()
 
 
 def test_fragment_rejects_duplicate_build_keys(gpu, ctx):
