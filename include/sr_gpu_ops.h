@@ -412,7 +412,7 @@ int32_t sr_agg_merge(sr_agg* agg, sr_agg* other);
 /* Element-wise mergeable view of a DENSE aggregate table (group-by columns with declared ranges, or no
  * GROUP BY): one array per state component, every array indexed by the same slot number on every
  * instance created from the same desc.  Partial states of fragment instances on several GPUs are then
- * merged IN PLACE by an all-reduce per array (reduce = SR_REDUCE_SUM / MIN / MAX over int64 or double
+ * merged IN PLACE by an all-reduce per array (reduce = SR_STATE_SUM / MIN / MAX over int64 or double
  * elements) -- SURVEY.md 8e "ncclAllReduce on a dense slot array when the group domain is tiny and
  * enumerable" -- instead of the gather + sr_agg_merge exchange; afterwards every instance holds the
  * final state and any of them can be pulled.  Call between the last push and the first pull.  The arrays
@@ -420,7 +420,7 @@ int32_t sr_agg_merge(sr_agg* agg, sr_agg* other);
  * first).  All instances must have been fed the same chunk schema (same column nullability), so that they
  * expose the same list of arrays.  SR_ERR_NOT_SUPPORTED for hash tables and for 128-bit sums (carry is not
  * element-wise). */
-typedef enum sr_state_reduce { SR_REDUCE_SUM = 0, SR_REDUCE_MIN = 1, SR_REDUCE_MAX = 2 } sr_state_reduce;
+typedef enum sr_state_reduce { SR_STATE_SUM = 0, SR_STATE_MIN = 1, SR_STATE_MAX = 2 } sr_state_reduce;
 typedef struct sr_agg_state_array {
     void* data;        /* device pointer */
     int64_t count;     /* elements */

@@ -566,7 +566,7 @@ int32_t sr_agg_dense_state(sr_agg* a, sr_agg_state_array* arrays, int32_t max_ar
         if (n < max_arrays) arrays[n] = sr_agg_state_array{p, (int64_t)h.cap, type, reduce};
         n++;
     };
-    add(h.cnt_star, SR_TYPE_BIGINT, SR_REDUCE_SUM);
+    add(h.cnt_star, SR_TYPE_BIGINT, SR_STATE_SUM);
     for (int f = 0; f < h.num_fns; f++) {
         const srd::AggFnDev& fn = h.fns[f];
         switch (fn.mode) {
@@ -574,24 +574,24 @@ int32_t sr_agg_dense_state(sr_agg* a, sr_agg_state_array* arrays, int32_t max_ar
             break; // cnt_star itself
         case srd::M_COUNT:
         case srd::M_SUM_I64:
-            add(fn.acc0, SR_TYPE_BIGINT, SR_REDUCE_SUM);
+            add(fn.acc0, SR_TYPE_BIGINT, SR_STATE_SUM);
             break;
         case srd::M_SUM_F64:
         case srd::M_AVG:
-            add(fn.acc0, SR_TYPE_DOUBLE, SR_REDUCE_SUM);
+            add(fn.acc0, SR_TYPE_DOUBLE, SR_STATE_SUM);
             break;
         case srd::M_MIN_I64:
         case srd::M_MIN_F64: // doubles are kept as their order-preserving int64 image
-            add(fn.acc0, SR_TYPE_BIGINT, SR_REDUCE_MIN);
+            add(fn.acc0, SR_TYPE_BIGINT, SR_STATE_MIN);
             break;
         case srd::M_MAX_I64:
         case srd::M_MAX_F64:
-            add(fn.acc0, SR_TYPE_BIGINT, SR_REDUCE_MAX);
+            add(fn.acc0, SR_TYPE_BIGINT, SR_STATE_MAX);
             break;
         default:
             return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "aggregate function %d keeps a state that is not element-wise mergeable", f);
         }
-        if (fn.accn) add(fn.accn, SR_TYPE_BIGINT, SR_REDUCE_SUM);
+        if (fn.accn) add(fn.accn, SR_TYPE_BIGINT, SR_STATE_SUM);
     }
     if (n > max_arrays) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "%d state arrays, room for %d", n, max_arrays);
     *num_arrays = n;
