@@ -412,6 +412,41 @@ def test_agg_hash_growth_two_pass(gpu, ctx, oracle):
         ga.close()
 
 
+@pytest.mark.parametrize("wide,expected,nkeys,n", [(False, 0, 300_000, 700_000), (True, 0, 300_000, 700_000),
+                                                    (False, 0, 5_000_000, 1_700_000), (False, 16_000_000, 3_000_000, 5_000_000)])
+def test_agg_partitioned_push_parity(gpu, ctx, oracle, monkeypatch, wide, expected, nkeys, n):
+    # Tables far larger than L2 take the radix-partitioned push (scatter by home-slot range, apply bucket by bucket
+    # with the table slice prefetched into L2); the thresholds are lowered through the library's tuning knobs so that
+    # small inputs reach it.  A following small batch takes the direct path.  Third case: more groups than the table
+    # admits (2^21 slots, limit 2^20) -> refused rows are re-applied after a growth.  Fourth: default thresholds.
+    if expected == 0:
+        monkeypatch.setenv("SR_AGG_PARTITION_MIN_ROWS", "100000")
+        monkeypatch.setenv("SR_AGG_PARTITION_MIN_TABLE_BYTES", str(1 << 20))
+    rng = np.random.default_rng(21)
+    k64 = rng.integers(0, nkeys, n, dtype=np.int64) * 1_000_003 - 7
+    k32 = rng.integers(0, 3, n, dtype=np.int32)
+    v = rng.integers(-1000, 1000, n, dtype=np.int64)
+    vn = rand_nulls(rng, n, 0.1)
+    fns = [(abi.AGG_SUM, abi.TYPE_BIGINT, 10, [("col", 2), ("i", 3), "*"]), (abi.AGG_COUNT_STAR, 0, 11, None),
+           (abi.AGG_MIN, abi.TYPE_BIGINT, 12, [("col", 2)]), (abi.AGG_COUNT, abi.TYPE_BIGINT, 13, [("col", 2)])]
+    if wide:
+        d = abi.make_agg_desc([1, 0], [abi.TYPE_INT, abi.TYPE_BIGINT], fns=fns, expected_groups=expected)
+    else:
+        d = abi.make_agg_desc([0], [abi.TYPE_BIGINT], fns=fns, expected_groups=expected)
+    def sub(lo, hi):
+        return Chunk([(0, k64[lo:hi].copy(), None), (1, k32[lo:hi].copy(), None), (2, v[lo:hi].copy(), vn[lo:hi].copy())])
+    ga, oa = gpu.Agg(ctx, d), oracle.Agg(d)
+    try:
+        launches0 = ctx.launches
+        for lo, hi in ((0, n - 50_000), (n - 50_000, n)):
+            ga.push(sub(lo, hi))
+            oa.push(sub(lo, hi))
+        assert ctx.launches - launches0 >= 8          # histogram + scan + scatter + bounds + one apply per bucket
+        assert_rows_equal(gpu_rows(ga.result()), oracle_rows(oa))
+    finally:
+        ga.close()
+
+
 def test_agg_pull_paging_and_device_output(gpu, ctx):
     keys = np.arange(10000, dtype=np.int32)
     d = abi.make_agg_desc([0], [abi.TYPE_INT], fns=[(abi.AGG_SUM, abi.TYPE_INT, 10, [("col", 0)])], ranges=[(0, 9999)])
