@@ -260,6 +260,19 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
         memset(&f->pass, 0, sizeof(f->pass));
         f->pass.num_stream_joins = ns;
         f->pass.final_first_join = ff;
+        // a streamed join whose build row the final pass looks up (payload) hands its int32 key over through the
+        // selection vector: one random fact-sector read less per surviving row
+        f->pass.carry_join = -1;
+        f->pass.carry_value_id = -1;
+        for (int q = 0; q < ns; q++) {
+            const int id = h.joins[q].key_value_id;
+            const int32_t kt = f->reg.types[id];
+            if (h.joins[q].need_head && srd::type_width(kt) == 4 && !srd::is_float_class(kt) && id < 127) {
+                f->pass.carry_join = (int8_t)q;
+                f->pass.carry_value_id = (int8_t)id;
+                break;
+            }
+        }
         // fact values the final pass reads: keys of the joins it looks up or tests, group keys, aggregate inputs
         {
             std::vector<int> need;
@@ -303,8 +316,9 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
         SR_CUDA(ctx, cudaMemcpyAsync(f->dev.p, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
         SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         int per_sm = 0;
-        SR_CUDA(ctx, cudaFuncSetAttribute(srd::k_frag_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(f->stream_smem, 16)));
-        SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, srd::k_frag_stream, srd::STREAM_BLOCK, f->stream_smem));
+        SR_CUDA(ctx, cudaFuncSetAttribute(srd::k_frag_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(f->stream_smem, 16)));
+        SR_CUDA(ctx, cudaFuncSetAttribute(srd::k_frag_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(f->stream_smem, 16)));
+        SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, srd::k_frag_stream<false>, srd::STREAM_BLOCK, f->stream_smem));
         if (per_sm < 1) return sr_fail(ctx, SR_ERR_CUDA, "streaming pass does not fit on an SM (smem %zu)", f->stream_smem);
         f->stream_grid = per_sm * ctx->num_sms;
         // gather passes: exactly one wave of resident CTAs (grid-stride loops; a partial second wave only adds a tail)
@@ -387,9 +401,13 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
         const srd::FragDev* fdev = (const srd::FragDev*)f->dev.p;
         // worst case every row survives, plus one partly used chunk per warp of the writing pass
         const size_t slack = (size_t)srd::SEL_CHUNK * ((size_t)f->stream_grid * (srd::STREAM_BLOCK / 32) + (size_t)f->grid * (srd::GATHER_BLOCK / 32));
-        SR_TRY(f->sel[0].reserve(ctx, sizeof(uint32_t) * ((size_t)n + slack)));
-        if (!f->gather_joins.empty()) SR_TRY(f->sel[1].reserve(ctx, sizeof(uint32_t) * ((size_t)n + slack)));
-        f->pass.host_input = fact->mem == SR_MEM_HOST_PINNED ? 1 : 0;
+        SR_TRY(f->sel[0].reserve(ctx, sizeof(srd::SelEntry) * ((size_t)n + slack)));
+        if (!f->gather_joins.empty()) SR_TRY(f->sel[1].reserve(ctx, sizeof(srd::SelEntry) * ((size_t)n + slack)));
+        // this push's pass parameters: the carried key (planned in f->pass) is only used for host-resident input
+        srd::PassDev pass = f->pass;
+        pass.host_input = fact->mem == SR_MEM_HOST_PINNED ? 1 : 0;
+        const bool carry = pass.host_input && pass.carry_join >= 0;
+        if (!carry) pass.carry_join = pass.carry_value_id = -1;
         unsigned long long* cnt = f->pass_counters.as<unsigned long long>();
         SR_CUDA(ctx, cudaMemsetAsync(cnt, 0, 16 * sizeof(uint64_t), ctx->stream));
         const int sgrid = (int)std::min<int64_t>(f->stream_grid, (n + srd::STREAM_TILE - 1) / srd::STREAM_TILE);
@@ -397,24 +415,27 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
         if (!f->ev[0])
             for (int e = 0; e < 4; e++) SR_CUDA(ctx, cudaEventCreate(&f->ev[e]));
         SR_CUDA(ctx, cudaEventRecord(f->ev[0], ctx->stream));
-        srd::k_frag_stream<<<sgrid, srd::STREAM_BLOCK, f->stream_smem, ctx->stream>>>(fdev, f->pass, vt, n, f->sel[0].as<uint32_t>(), cnt);
+        if (carry)
+            srd::k_frag_stream<true><<<sgrid, srd::STREAM_BLOCK, f->stream_smem, ctx->stream>>>(fdev, pass, vt, n, f->sel[0].as<srd::SelEntry>(), cnt);
+        else
+            srd::k_frag_stream<false><<<sgrid, srd::STREAM_BLOCK, f->stream_smem, ctx->stream>>>(fdev, pass, vt, n, f->sel[0].as<srd::SelEntry>(), cnt);
         SR_LAUNCH_CHECK(ctx);
         SR_CUDA(ctx, cudaEventRecord(f->ev[1], ctx->stream));
         int cur = 0, k = 0;
         for (int q : f->gather_joins) {
-            srd::k_frag_gather_join<<<f->grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, q, vt, f->sel[cur].as<uint32_t>(), cnt + k,
-                                                                                  f->sel[cur ^ 1].as<uint32_t>(), cnt + k + 1);
+            srd::k_frag_gather_join<<<f->grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, q, vt, f->sel[cur].as<srd::SelEntry>(), cnt + k,
+                                                                                  f->sel[cur ^ 1].as<srd::SelEntry>(), cnt + k + 1);
             SR_LAUNCH_CHECK(ctx);
             cur ^= 1;
             k++;
         }
         SR_CUDA(ctx, cudaEventRecord(f->ev[2], ctx->stream));
         if (f->smem_agg)
-            srd::k_frag_gather_agg<true><<<f->final_grid, srd::GATHER_BLOCK, a->smem_bytes, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, f->pass, vt,
-                                                                                                   f->sel[cur].as<uint32_t>(), cnt + k);
+            srd::k_frag_gather_agg<true><<<f->final_grid, srd::GATHER_BLOCK, a->smem_bytes, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, pass, vt,
+                                                                                                   f->sel[cur].as<srd::SelEntry>(), cnt + k);
         else
-            srd::k_frag_gather_agg<false><<<f->final_grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, f->pass, vt,
-                                                                                        f->sel[cur].as<uint32_t>(), cnt + k);
+            srd::k_frag_gather_agg<false><<<f->final_grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, pass, vt,
+                                                                                        f->sel[cur].as<srd::SelEntry>(), cnt + k);
         SR_LAUNCH_CHECK(ctx);
         SR_CUDA(ctx, cudaEventRecord(f->ev[3], ctx->stream));
         f->timed_push = true;

@@ -40,17 +40,14 @@ struct FragLoader {
     const VTab& vt;
     int64_t row;
     uint32_t bidx[SR_MAX_FRAG_JOINS];
-    // optional: fact values fetched ahead of time by the caller (final pass) -- pslot[id] = index into pv or -1
-    const int64_t* pv;
-    const int8_t* pslot;
-    uint32_t pnull;
+    // optional: one fact value that travelled with the row id in the selection vector (the key of a streamed join
+    // whose build row the final pass looks up) -- saves the final pass one random sector read per row
+    int32_t carry_id;  // value id, -1 = none
+    int32_t carry_val; // non-NULL by construction: the row passed that join
     __device__ __forceinline__ bool load(int id, int64_t& bits) const {
-        if (pslot) {
-            const int q = pslot[id];
-            if (q >= 0) {
-                bits = pv[q];
-                return (pnull >> q) & 1u;
-            }
+        if (id == carry_id) {
+            bits = (int64_t)carry_val;
+            return false;
         }
         const VDesc& d = vt.v[id];
         if (d.src < 0) {
@@ -173,7 +170,7 @@ struct Cascade {
     // last queue: build-row lookups, group slot, aggregate update; one row per lane
     __device__ __forceinline__ void consume_final(uint32_t row32, bool valid) {
         if (valid) {
-            FragLoader ld{vt, (int64_t)row32, {0, 0, 0, 0, 0, 0}};
+            FragLoader ld{vt, (int64_t)row32, {0, 0, 0, 0, 0, 0}, -1, 0};
 #pragma unroll 1
             for (int j = 0; j < S; j++) {
                 if (joins[j].need_head) {

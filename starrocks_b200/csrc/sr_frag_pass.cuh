@@ -28,8 +28,18 @@ struct PassDev {
     int8_t final_vals[8];              // value ids, -1 = unused
     int8_t final_slot[SR_MAX_VALUES];  // value id -> index into final_vals, -1 = not prefetched
     int8_t host_input; // the fact columns of this push live in pinned host memory (SR_MEM_HOST_PINNED)
-    int8_t pad[3];
+    // the int32 key of one streamed join whose build row the final pass needs travels in the upper half of the
+    // selection-vector entries, so the final pass does not gather it from the fact table again
+    int8_t carry_join;     // index of that join among the streamed joins, -1 = none
+    int8_t carry_value_id; // its key's value id
+    int8_t pad[1];
 };
+
+// selection-vector entry: row id (low 32 bits) + carried key (high 32 bits)
+typedef unsigned long long SelEntry;
+__device__ __forceinline__ uint32_t sel_row(SelEntry e) { return (uint32_t)e; }
+__device__ __forceinline__ int32_t sel_carry(SelEntry e) { return (int32_t)(e >> 32); }
+__device__ __forceinline__ SelEntry sel_make(uint32_t row, int32_t carry) { return (SelEntry)row | ((SelEntry)(uint32_t)carry << 32); }
 
 #define SR_FINAL_PREFETCH 8
 
@@ -136,10 +146,10 @@ constexpr int STREAM_MAX_JOINS = 2;
 constexpr uint32_t SEL_CHUNK = 256;
 
 struct WarpSelWriter {
-    uint32_t* __restrict__ out;
+    SelEntry* __restrict__ out;
     unsigned long long* __restrict__ counter;
     unsigned long long pos, end; // warp-uniform
-    __device__ __forceinline__ void init(uint32_t* o, unsigned long long* c) {
+    __device__ __forceinline__ void init(SelEntry* o, unsigned long long* c) {
         out = o;
         counter = c;
         pos = end = 0;
@@ -163,25 +173,33 @@ struct WarpSelWriter {
     }
 };
 
-// append the rows flagged in `alive` (bit i -> row base_i + (i & 3)) to the selection vector
-__device__ __forceinline__ void warp_append_rows(uint32_t alive_all, int64_t row0_g0, int64_t row0_g1, WarpSelWriter& w) {
+// append the rows flagged in `alive` (bit i -> row base_i + (i & 3)) with their carried keys to the selection vector
+template <bool CARRY>
+__device__ __forceinline__ void warp_append_rows(uint32_t alive_all, int64_t row0_g0, int64_t row0_g1,
+                                                 const int32_t (&carry)[STREAM_GROUPS * STREAM_ROWS], WarpSelWriter& w) {
     const uint32_t cnt = __popc(alive_all);
     const uint32_t incl = warp_incl_scan(cnt);
     const uint32_t total = __shfl_sync(SR_FULL_MASK, incl, 31);
     if (total == 0) return;
-    uint32_t* __restrict__ sel_out = w.out;
+    SelEntry* __restrict__ sel_out = w.out;
     unsigned long long pos = w.reserve(total) + incl - cnt;
 #pragma unroll
     for (int i = 0; i < STREAM_GROUPS * STREAM_ROWS; i++) {
         if ((alive_all >> i) & 1u) {
-            const int64_t rb = i < STREAM_ROWS ? row0_g0 : row0_g1;
-            sel_out[pos++] = (uint32_t)(rb + (i & (STREAM_ROWS - 1)));
+            const int64_t row = (i < STREAM_ROWS ? row0_g0 : row0_g1) + (i & (STREAM_ROWS - 1));
+            sel_out[pos++] = sel_make((uint32_t)row, CARRY ? carry[i] : 0);
         }
     }
 }
 
+// CARRY: the key of streamed join pd.carry_join rides in the upper half of the entries.  Only instantiated for
+// host-resident input: holding the tile's keys in registers through the append costs the streaming kernel ~25 %
+// when it runs at HBM speed (register spills; re-reading the key for the survivors instead was worse still, it puts
+// an L2 round trip on every tile's critical path) but nothing when the kernel waits on PCIe, and there every sector
+// the final pass does not have to fetch is worth ~2.5 ns of bus time.
+template <bool CARRY>
 __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream(const FragDev* __restrict__ fdp, PassDev pd, const __grid_constant__ VTab vt, int64_t n,
-                                                                 uint32_t* __restrict__ sel_out, unsigned long long* __restrict__ counter) {
+                                                                 SelEntry* __restrict__ sel_out, unsigned long long* __restrict__ counter) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ FragJoinDev s_joins[STREAM_MAX_JOINS];
     __shared__ CPred s_preds[8];
@@ -251,6 +269,11 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream(const FragDev* 
                     if (row0[g] + r < n) alive[g] |= 1u << r;
             }
         }
+        int32_t carry[STREAM_GROUPS * STREAM_ROWS];
+        if (CARRY) {
+#pragma unroll
+            for (int i = 0; i < STREAM_GROUPS * STREAM_ROWS; i++) carry[i] = 0;
+        }
         if (fast && tile < full_tiles) {
             static_assert(STREAM_GROUPS == 2 && STREAM_ROWS == 4, "8 keys per thread and column");
             const int32_t k0[8] = {pk[0][0].x, pk[0][0].y, pk[0][0].z, pk[0][0].w, pk[0][1].x, pk[0][1].y, pk[0][1].z, pk[0][1].w};
@@ -260,6 +283,10 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream(const FragDev* 
             if (two) a8 = join_test_batch<8>(s_joins[1], smem, k1, a8);
             alive[0] = a8 & 0xFu;
             alive[1] = a8 >> 4;
+            if (CARRY) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) carry[i] = pd.carry_join == 0 ? k0[i] : k1[i];
+            }
         } else {
             int64_t vals[STREAM_GROUPS][STREAM_ROWS];
             uint32_t nullmask[STREAM_GROUPS];
@@ -300,10 +327,16 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream(const FragDev* 
                     for (int r = 0; r < STREAM_ROWS; r++)
                         if ((alive[g] & (1u << r)) && !frag_join_hit(s_joins[j], smem, vals[g][r])) alive[g] &= ~(1u << r);
                 }
+                if (CARRY && j == pd.carry_join) {
+#pragma unroll
+                    for (int g = 0; g < STREAM_GROUPS; g++)
+#pragma unroll
+                        for (int r = 0; r < STREAM_ROWS; r++) carry[g * STREAM_ROWS + r] = (int32_t)vals[g][r];
+                }
             }
         }
         static_assert(STREAM_GROUPS == 2, "two groups of alive bits are packed into one word");
-        warp_append_rows(alive[0] | (alive[1] << STREAM_ROWS), row0[0], row0[1], writer);
+        warp_append_rows<CARRY>(alive[0] | (alive[1] << STREAM_ROWS), row0[0], row0[1], carry, writer);
     }
     writer.finish();
 }
@@ -324,8 +357,8 @@ __device__ __forceinline__ void warp_sel_range(unsigned long long n, unsigned lo
 
 // one selective join on the selected rows: sel_in[0, *n_in) -> sel_out (appended at *counter_out)
 __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_join(const FragDev* __restrict__ fdp, int32_t j, const __grid_constant__ VTab vt,
-                                                                    const uint32_t* __restrict__ sel_in, const unsigned long long* __restrict__ n_in_ptr,
-                                                                    uint32_t* __restrict__ sel_out, unsigned long long* __restrict__ counter_out) {
+                                                                    const SelEntry* __restrict__ sel_in, const unsigned long long* __restrict__ n_in_ptr,
+                                                                    SelEntry* __restrict__ sel_out, unsigned long long* __restrict__ counter_out) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ FragJoinDev s_join;
     for (int i = threadIdx.x; i < (int)(sizeof(FragJoinDev) / 4); i += blockDim.x) ((uint32_t*)&s_join)[i] = ((const uint32_t*)&fdp->joins[j])[i];
@@ -342,8 +375,9 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_join(const FragDev
     for (unsigned long long i0 = w_begin; i0 < w_end; i0 += 32) {
         const unsigned long long i = i0 + lane_id();
         bool hit = false;
-        uint32_t row = SEL_INVALID;
-        if (i < n_in) row = sel_in[i];
+        SelEntry entry = (SelEntry)SEL_INVALID;
+        if (i < n_in) entry = sel_in[i];
+        const uint32_t row = sel_row(entry);
         if (row != SEL_INVALID) {
             const int64_t key = load_int(d.data, d.type, (int64_t)row);
             const bool nul = d.nulls != nullptr && d.nulls[row] != 0;
@@ -352,7 +386,7 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_join(const FragDev
         const uint32_t m = __ballot_sync(SR_FULL_MASK, hit);
         if (m) {
             const unsigned long long base = writer.reserve(__popc(m));
-            if (hit) sel_out[base + __popc(m & lanemask_lt())] = row;
+            if (hit) sel_out[base + __popc(m & lanemask_lt())] = entry; // the carried key travels along
         }
     }
     writer.finish();
@@ -361,7 +395,7 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_join(const FragDev
 // final pass: remaining joins inline, payload lookups, aggregate update
 template <bool SMEM_AGG>
 __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg(const FragDev* __restrict__ fdp, const AggDev* __restrict__ adp, const __grid_constant__ PassDev pd,
-                                                                   const __grid_constant__ VTab vt, const uint32_t* __restrict__ sel_in,
+                                                                   const __grid_constant__ VTab vt, const SelEntry* __restrict__ sel_in,
                                                                    const unsigned long long* __restrict__ n_in_ptr) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ FragJoinDev s_joins[SR_MAX_FRAG_JOINS];
@@ -376,19 +410,22 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg(const FragDev*
     } else {
         acc_ptrs_global(ad, acc);
     }
-    __syncthreads();
+    // Measured and rejected (profiles/r1_notes.md): requesting the NEXT row's fact sectors with prefetch.global.L2
+    // while the current row walks its dependent chain.  HBM-resident input: 0.73 -> 1.27 ms (the prefetch fetches
+    // whole 128-byte lines where the loads need one 32-byte sector: 4x the DRAM traffic of a pass that is bound by
+    // random-sector throughput, not latency).  Host-resident input: mapped host memory is not kept in L2, the
+    // prefetch only doubled the PCIe requests (117 -> 224 ms on SSB Q4.1 SF100).
     const unsigned long long n_in = *n_in_ptr;
     unsigned long long passed = 0;
     unsigned long long w_begin, w_end;
     warp_sel_range(n_in, w_begin, w_end);
     for (unsigned long long i = w_begin + lane_id(); i < w_end; i += 32) {
-        const uint32_t row = sel_in[i];
-        // (prefetch.global.L2 of the next row's host-resident values was measured: reads of mapped host memory are
-        // not kept in L2, the prefetch only doubled the PCIe requests -- 117 -> 224 ms on SSB Q4.1 SF100)
+        const SelEntry entry = sel_in[i];
+        const uint32_t row = sel_row(entry);
         if (row == SEL_INVALID) continue;
         // (a variant that fetched every fact value of the row in one burst before the dependent lookups was
         // measured slower on B200 -- more issue slots and registers than latency hidden, see profiles/)
-        FragLoader ld{vt, (int64_t)row, {0, 0, 0, 0, 0, 0}};
+        FragLoader ld{vt, (int64_t)row, {0, 0, 0, 0, 0, 0}, pd.carry_join >= 0 ? (int32_t)pd.carry_value_id : -1, sel_carry(entry)};
         bool ok = true;
 #pragma unroll 1
         for (int j = 0; j < S && ok; j++) {
