@@ -168,11 +168,12 @@ def known_traffic():
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the reference's CPU implementation of the path = the oracle (the BE cannot be built here)
 # ---------------------------------------------------------------------------------------------------
-def pcie_bytes_in_place(n, plan, width=4, n_cols=6, sector=32):
+def pcie_bytes_in_place(n, plan, width=4, n_cols=6, sector=64):
     """Bytes the fragment kernels fetch from pinned host memory for one in-place push: column k (in plan order) is read
-    only for rows that survived the scan predicate and joins < k, at 32-byte sector granularity; with uniformly
-    distributed survivors of density d a sector of 32/width rows is touched with probability 1-(1-d)^(32/width).
-    The aggregate input columns are read at the density left after the last join."""
+    only for rows that survived the scan predicate and joins < k, in 64-byte bus blocks (the granularity measured with
+    scripts/pcie_stride.cu); with uniformly distributed survivors of density d a block of 64/width rows is touched with
+    probability 1-(1-d)^(64/width).  The aggregate input columns are read at the density left after the last join; the
+    key of the streamed join whose payload is needed travels in the selection vector and is not read again."""
     per = sector // width
     d = float(plan.get("pred_rate", 1.0))
     total = 0.0
@@ -404,7 +405,7 @@ def run_gpu(args):
         e2e["input_bytes_per_step"] = n * ALGO_BYTES_PER_ROW * world
         e2e["h2d_bytes_per_step"] = int(pcie_bytes_in_place(n, frag.plan()) * world)
         e2e["transfer"] = ("in-place reads of the pinned host columns by the fragment kernels (no staging copy); "
-                           "h2d_bytes_per_step = 32-byte-sector model from the measured pass rates")
+                           "h2d_bytes_per_step = 64-byte bus-block model from the measured pass rates")
         # (2) the same call with a full H2D staging copy of every column (SR_MEM_HOST), for comparison
         full = run_e2e(abi.MEM_HOST)
         full["h2d_bytes_per_step"] = n * ALGO_BYTES_PER_ROW * world
@@ -451,13 +452,13 @@ def run_gpu(args):
         if sum(pass_ms) > 0:
             # per-kernel view: the streaming pass reads its key columns in full (4 B/row each); the gather passes touch
             # single 32-byte sectors, their DRAM traffic is what ncu measured (profiles/traffic.json)
-            names = ["k_frag_stream", "k_frag_gather_join", "k_frag_gather_agg"]
+            names = ["k_frag_stream_tests", "k_frag_gather_join", "k_frag_gather_agg"]
             ktr = traffic.get("kernels", {})
             kernels = []
             for nm, ms in zip(names, pass_ms):
                 ms /= args.steps
                 ent = {"name": nm, "ms": ms, "dram_bytes_per_launch": ktr.get(nm)}
-                if nm == "k_frag_stream":
+                if nm == "k_frag_stream_tests":
                     ab = n * 4 * max(1, plan["num_stream_joins"])
                     ent.update({"algorithmic_bytes": ab, "achieved_gbs": ab / (ms / 1000.0) / 1e9 if ms > 0 else None,
                                 "frac": ab / (ms / 1000.0) / 1e9 / peak if ms > 0 else None})
@@ -474,7 +475,7 @@ def run_gpu(args):
                        "rows_reaching_aggregate_per_gpu": int(rows_passed), "build_ms": build_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic.get("dram_bytes_per_launch"),
-                         "kernel": "fragment push = k_frag_stream + k_frag_gather_join + k_frag_gather_agg" if kernels else "k_fragment",
+                         "kernel": "fragment push = k_frag_stream_tests + k_frag_gather_join + k_frag_gather_agg" if kernels else "k_fragment",
                          "kernel_ms": kernel_ms, "kernels": kernels,
                          "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_ROW, "peak_source": peak_src,
                          "note": "achieved = 24 B/row (SURVEY 8d) x rows / CUDA-event duration of one fragment push (all its kernels); "

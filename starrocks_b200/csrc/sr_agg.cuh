@@ -701,62 +701,69 @@ __global__ void __launch_bounds__(AGG_BLOCK) k_agg_part_apply(const AggDev* __re
     }
 }
 
-// no GROUP BY: warp-reduce additive functions before touching memory (update_batch_single_state)
-__global__ void __launch_bounds__(AGG_BLOCK) k_agg_push_single(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, int64_t n) {
-    const AggDev& a = *ad;
-    long long cnt = 0;
+// no GROUP BY: every thread keeps the single state in registers over its rows, a warp reduction and one atomic per
+// warp follow at the end (update_batch_single_state).  Used by the standalone push and by the fragment's final pass --
+// a per-row atomic on the one state serialises (global: in L2; shared: 64-bit shared atomics are CAS spin loops).
+struct SingleAcc {
+    long long cnt;
     long long acc[SR_MAX_AGG_FNS];
     long long accn[SR_MAX_AGG_FNS];
+};
+__device__ __forceinline__ void single_acc_init(const AggDev& a, SingleAcc& s) {
+    s.cnt = 0;
     for (int f = 0; f < SR_MAX_AGG_FNS; f++) {
-        acc[f] = f < a.num_fns ? acc_init_value(a.fns[f].mode) : 0;
-        accn[f] = 0;
+        s.acc[f] = f < a.num_fns ? acc_init_value(a.fns[f].mode) : 0;
+        s.accn[f] = 0;
     }
-    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
-        ChunkLoader ld{vt, row};
-        cnt++;
+}
+template <typename Loader>
+__device__ __forceinline__ void single_acc_row(const AggDev& a, SingleAcc& s, Loader& ld) {
+    s.cnt++;
 #pragma unroll 1
-        for (int f = 0; f < a.num_fns; f++) {
-            const AggFnDev& fn = a.fns[f];
-            if (fn.mode == M_COUNT_STAR) continue;
-            int64_t bits;
-            if (eval_expr(fn.input, ld, bits)) continue;
-            accn[f]++;
-            switch (fn.mode) {
-            case M_COUNT:
-                acc[f]++;
-                break;
-            case M_SUM_I64:
-                acc[f] = (long long)((unsigned long long)acc[f] + (unsigned long long)bits);
-                break;
-            case M_SUM_F64:
-            case M_AVG:
-                acc[f] = __double_as_longlong(__longlong_as_double(acc[f]) + __longlong_as_double(bits));
-                break;
-            case M_MIN_I64:
-                acc[f] = min(acc[f], (long long)bits);
-                break;
-            case M_MAX_I64:
-                acc[f] = max(acc[f], (long long)bits);
-                break;
-            case M_MIN_F64:
-                acc[f] = min(acc[f], f64_sortable(__longlong_as_double(bits)));
-                break;
-            case M_MAX_F64:
-                acc[f] = max(acc[f], f64_sortable(__longlong_as_double(bits)));
-                break;
-            default: // M_SUM_I128: apply directly (rare)
-                acc_apply(fn.mode, fn.acc0, fn.acc1, 0, bits);
-                break;
-            }
+    for (int f = 0; f < a.num_fns; f++) {
+        const AggFnDev& fn = a.fns[f];
+        if (fn.mode == M_COUNT_STAR) continue;
+        int64_t bits;
+        if (eval_expr(fn.input, ld, bits)) continue;
+        s.accn[f]++;
+        switch (fn.mode) {
+        case M_COUNT:
+            s.acc[f]++;
+            break;
+        case M_SUM_I64:
+            s.acc[f] = (long long)((unsigned long long)s.acc[f] + (unsigned long long)bits);
+            break;
+        case M_SUM_F64:
+        case M_AVG:
+            s.acc[f] = __double_as_longlong(__longlong_as_double(s.acc[f]) + __longlong_as_double(bits));
+            break;
+        case M_MIN_I64:
+            s.acc[f] = min(s.acc[f], (long long)bits);
+            break;
+        case M_MAX_I64:
+            s.acc[f] = max(s.acc[f], (long long)bits);
+            break;
+        case M_MIN_F64:
+            s.acc[f] = min(s.acc[f], f64_sortable(__longlong_as_double(bits)));
+            break;
+        case M_MAX_F64:
+            s.acc[f] = max(s.acc[f], f64_sortable(__longlong_as_double(bits)));
+            break;
+        default: // M_SUM_I128: apply directly (rare)
+            acc_apply(fn.mode, fn.acc0, fn.acc1, 0, bits);
+            break;
         }
     }
-    cnt = warp_sum(cnt);
+}
+// all 32 lanes of every warp must call this (converged)
+__device__ __forceinline__ void single_acc_flush(const AggDev& a, SingleAcc& s) {
+    const long long cnt = warp_sum(s.cnt);
     if (lane_id() == 0 && cnt) atomicAdd((unsigned long long*)a.cnt_star, (unsigned long long)cnt);
 #pragma unroll 1
     for (int f = 0; f < a.num_fns; f++) {
         const AggFnDev& fn = a.fns[f];
         if (fn.mode == M_COUNT_STAR) continue;
-        long long v = acc[f];
+        long long v = s.acc[f];
         switch (fn.mode) {
         case M_SUM_F64:
         case M_AVG: {
@@ -783,12 +790,23 @@ __global__ void __launch_bounds__(AGG_BLOCK) k_agg_push_single(const AggDev* __r
             v = (long long)warp_sum((unsigned long long)v);
             break;
         }
-        const long long nn = warp_sum(accn[f]);
+        const long long nn = warp_sum(s.accn[f]);
         if (lane_id() == 0 && nn) {
             if (fn.mode != M_SUM_I128) acc_merge(fn.mode, fn.acc0, fn.acc1, 0, v, 0);
             if (fn.track_n) atomicAdd((unsigned long long*)fn.accn, (unsigned long long)nn);
         }
     }
+}
+
+__global__ void __launch_bounds__(AGG_BLOCK) k_agg_push_single(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, int64_t n) {
+    const AggDev& a = *ad;
+    SingleAcc s;
+    single_acc_init(a, s);
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        ChunkLoader ld{vt, row};
+        single_acc_row(a, s, ld);
+    }
+    single_acc_flush(a, s);
 }
 
 __global__ void __launch_bounds__(256) k_fill_i64(long long* p, int64_t n, long long v) {
@@ -1256,9 +1274,11 @@ static int32_t agg_compile(sr_agg* a, slot_type_fn tf, agg_nullable_fn nf, void*
     h.ngroups = a->counters.as<unsigned long long>();
     h.flags = (int32_t*)(a->counters.as<unsigned long long>() + 1);
     SR_TRY(agg_alloc_tables(a, &h, cap, &a->hkeys, &a->cnt_star, a->acc0, a->acc1, a->accn));
-    // shared-memory accumulation for small dense tables
+    // shared-memory accumulation for small dense tables -- including the single state of a query without GROUP BY
+    // inside a fused fragment (every surviving row would otherwise hit the same global address with an atomic; the
+    // standalone push reduces per warp instead, k_agg_push_single)
     a->smem_bytes = 0;
-    if (h.dense && d.num_group_keys > 0) {
+    if (h.dense) {
         size_t words = 1;
         for (int f = 0; f < h.num_fns; f++) {
             if (h.fns[f].mode == srd::M_COUNT_STAR) continue;

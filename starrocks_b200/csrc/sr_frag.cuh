@@ -199,8 +199,8 @@ static int32_t frag_compile(sr_fragment* f) {
                 }
         if (!found) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "slot %d is neither a fact column nor a join payload", f->reg.slots[k]);
     }
-    SR_TRY(f->counters.reserve(ctx, 128));
-    SR_CUDA(ctx, cudaMemsetAsync(f->counters.p, 0, 128, ctx->stream));
+    SR_TRY(f->counters.reserve(ctx, 256));
+    SR_CUDA(ctx, cudaMemsetAsync(f->counters.p, 0, 256, ctx->stream));
     h.rows_passed = f->counters.as<unsigned long long>();
     return SR_OK;
 }
@@ -212,8 +212,10 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
     SR_TRY(f->dev.reserve(ctx, sizeof(srd::FragDev)));
     SR_CUDA(ctx, cudaMemcpyAsync(f->dev.p, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
     const int64_t sample = std::min<int64_t>(n, 1 << 16);
-    unsigned long long counts[SR_MAX_FRAG_JOINS + 1] = {0};
+    unsigned long long counts[24] = {0}; // [0, 6): joins, [6]: all conjuncts, [16 + p]: conjuncts 0..p
+    static_assert(SR_MAX_FRAG_JOINS + 1 <= 16, "sample counter layout");
     counts[SR_MAX_FRAG_JOINS] = (unsigned long long)sample;
+    for (int p = 0; p < 8; p++) counts[16 + p] = (unsigned long long)sample;
     if (sample > 0 && (f->num_joins > 0 || h.num_preds > 0 || h.num_exprs > 0)) {
         unsigned long long* dcounts = f->counters.as<unsigned long long>() + 8;
         SR_CUDA(ctx, cudaMemsetAsync(dcounts, 0, sizeof(counts), ctx->stream));
@@ -273,6 +275,53 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
                 break;
             }
         }
+        // the streaming pass in "tests" form (k_frag_stream_tests): every scan conjunct must reduce to an int32 range
+        // and every streamed column must be int32-class; otherwise the generic streaming kernel runs
+        {
+            bool ok = h.num_exprs == 0 && h.num_preds + ns > 0 && h.num_preds + ns <= SR_MAX_STREAM_TESTS;
+            int nt = 0;
+            auto int32_class = [&](int id) { return srd::type_width(f->reg.types[id]) == 4 && !srd::is_float_class(f->reg.types[id]); };
+            for (int p = 0; p < h.num_preds && ok; p++) {
+                const srd::CPred& cp = h.preds[p];
+                long long lo = INT32_MIN, hi = INT32_MAX;
+                switch (cp.op) {
+                case SR_PRED_EQ: lo = hi = cp.ilo; break;
+                case SR_PRED_LT: hi = cp.ilo - 1; break;
+                case SR_PRED_LE: hi = cp.ilo; break;
+                case SR_PRED_GT: lo = cp.ilo + 1; break;
+                case SR_PRED_GE: lo = cp.ilo; break;
+                case SR_PRED_BETWEEN: lo = cp.ilo; hi = cp.ihi; break;
+                default: ok = false; break;
+                }
+                lo = std::max<long long>(lo, INT32_MIN);
+                hi = std::min<long long>(hi, INT32_MAX);
+                if (cp.is_double || !int32_class(cp.value_id) || lo > hi) ok = false;
+                if (!ok) break;
+                srd::StreamTest& st = f->pass.tests[nt++];
+                st.kind = 0;
+                st.value_id = cp.value_id;
+                st.join = -1;
+                st.lo = (uint32_t)(int32_t)lo;
+                st.span = (uint32_t)(hi - lo);
+            }
+            for (int q = 0; q < ns && ok; q++) {
+                if (!int32_class(h.joins[q].key_value_id)) {
+                    ok = false;
+                    break;
+                }
+                srd::StreamTest& st = f->pass.tests[nt++];
+                st.kind = 1;
+                st.value_id = h.joins[q].key_value_id;
+                st.join = q;
+                st.lo = st.span = 0;
+            }
+            f->pass.num_tests = ok ? nt : 0;
+            // the second test's column is streamed with vector loads as well when >= 8 % of the rows reach it
+            // (most of its 64-byte DRAM bursts would be touched anyway, and the loads do not wait for test 0)
+            double reach1 = 1.0;
+            if (ok && nt > 1) reach1 = f->pass.tests[0].kind == 0 ? (double)counts[16] / (double)std::max<int64_t>(sample, 1) : f->pred_rate * f->pass_rate[ord[0]];
+            f->pass.num_vec = (ok && nt > 1 && reach1 >= 0.08) ? 2 : 1;
+        }
         // fact values the final pass reads: keys of the joins it looks up or tests, group keys, aggregate inputs
         {
             std::vector<int> need;
@@ -318,13 +367,17 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
         int per_sm = 0;
         SR_CUDA(ctx, cudaFuncSetAttribute(srd::k_frag_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(f->stream_smem, 16)));
         SR_CUDA(ctx, cudaFuncSetAttribute(srd::k_frag_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(f->stream_smem, 16)));
+        SR_CUDA(ctx, cudaFuncSetAttribute(srd::k_frag_stream_tests<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(f->stream_smem, 16)));
+        SR_CUDA(ctx, cudaFuncSetAttribute(srd::k_frag_stream_tests<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(f->stream_smem, 16)));
         SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, srd::k_frag_stream<false>, srd::STREAM_BLOCK, f->stream_smem));
         if (per_sm < 1) return sr_fail(ctx, SR_ERR_CUDA, "streaming pass does not fit on an SM (smem %zu)", f->stream_smem);
         f->stream_grid = per_sm * ctx->num_sms;
         // gather passes: exactly one wave of resident CTAs (grid-stride loops; a partial second wave only adds a tail)
         int gj = 0, ga = 0;
         SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gj, srd::k_frag_gather_join, srd::GATHER_BLOCK, 0));
-        if (f->smem_agg)
+        if (f->agg->host.num_keys == 0)
+            SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ga, srd::k_frag_gather_agg<false, true>, srd::GATHER_BLOCK, 0));
+        else if (f->smem_agg)
             SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ga, srd::k_frag_gather_agg<true>, srd::GATHER_BLOCK, f->agg->smem_bytes));
         else
             SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ga, srd::k_frag_gather_agg<false>, srd::GATHER_BLOCK, 0));
@@ -415,10 +468,23 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
         if (!f->ev[0])
             for (int e = 0; e < 4; e++) SR_CUDA(ctx, cudaEventCreate(&f->ev[e]));
         SR_CUDA(ctx, cudaEventRecord(f->ev[0], ctx->stream));
-        if (carry)
+        // range-form conjuncts and streamed joins on plain (non-nullable) int32 columns -> the tests kernel;
+        // everything else -> the generic streaming kernel
+        bool tests = pass.num_tests > 0;
+        for (int t = 0; t < pass.num_tests && tests; t++) {
+            const VDesc& d = vt.v[pass.tests[t].value_id];
+            if (d.nulls != nullptr || (t < pass.num_vec && (((uintptr_t)d.data) & 15) != 0)) tests = false;
+        }
+        if (tests) {
+            if (carry)
+                srd::k_frag_stream_tests<true><<<sgrid, srd::STREAM_BLOCK, f->stream_smem, ctx->stream>>>(fdev, pass, vt, n, f->sel[0].as<srd::SelEntry>(), cnt);
+            else
+                srd::k_frag_stream_tests<false><<<sgrid, srd::STREAM_BLOCK, f->stream_smem, ctx->stream>>>(fdev, pass, vt, n, f->sel[0].as<srd::SelEntry>(), cnt);
+        } else if (carry) {
             srd::k_frag_stream<true><<<sgrid, srd::STREAM_BLOCK, f->stream_smem, ctx->stream>>>(fdev, pass, vt, n, f->sel[0].as<srd::SelEntry>(), cnt);
-        else
+        } else {
             srd::k_frag_stream<false><<<sgrid, srd::STREAM_BLOCK, f->stream_smem, ctx->stream>>>(fdev, pass, vt, n, f->sel[0].as<srd::SelEntry>(), cnt);
+        }
         SR_LAUNCH_CHECK(ctx);
         SR_CUDA(ctx, cudaEventRecord(f->ev[1], ctx->stream));
         int cur = 0, k = 0;
@@ -430,7 +496,10 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
             k++;
         }
         SR_CUDA(ctx, cudaEventRecord(f->ev[2], ctx->stream));
-        if (f->smem_agg)
+        if (ah.num_keys == 0)
+            srd::k_frag_gather_agg<false, true><<<f->final_grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, pass, vt,
+                                                                                              f->sel[cur].as<srd::SelEntry>(), cnt + k);
+        else if (f->smem_agg)
             srd::k_frag_gather_agg<true><<<f->final_grid, srd::GATHER_BLOCK, a->smem_bytes, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, pass, vt,
                                                                                                    f->sel[cur].as<srd::SelEntry>(), cnt + k);
         else

@@ -424,10 +424,15 @@ __global__ void __launch_bounds__(256) k_frag_sample(const FragDev* __restrict__
         {
             // rows passing every scan conjunct -> counts[SR_MAX_FRAG_JOINS]
             bool pass = true;
-            for (int p = 0; p < fd.num_preds && pass; p++) {
-                int64_t bits;
-                const bool nul = ld.load(fd.preds[p].value_id, bits);
-                pass = eval_pred(fd.preds[p], bits, nul);
+            for (int p = 0; p < fd.num_preds; p++) {
+                if (pass) {
+                    int64_t bits;
+                    const bool nul = ld.load(fd.preds[p].value_id, bits);
+                    pass = eval_pred(fd.preds[p], bits, nul);
+                }
+                // rows passing conjuncts 0..p -> counts[16 + p] (how many rows reach the next streamed column)
+                const uint32_t mp = __ballot_sync(__activemask(), pass);
+                if (pass && (mp & lanemask_lt()) == 0) atomicAdd(&counts[16 + p], (unsigned long long)__popc(mp));
             }
             for (int e = 0; e < fd.num_exprs && pass; e++) {
                 int64_t bits;

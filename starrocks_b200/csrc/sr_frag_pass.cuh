@@ -21,7 +21,19 @@
 
 namespace srd {
 
+// one test of the streaming pass in "fast" form (k_frag_stream_tests)
+struct StreamTest {
+    int32_t kind;     // 0: scan predicate as a range, lo <= v <= lo + span; 1: streamed join `join`
+    int32_t value_id; // the int32-class column it reads
+    int32_t join;
+    uint32_t lo, span;
+};
+#define SR_MAX_STREAM_TESTS 6
+
 struct PassDev {
+    int32_t num_tests; // > 0: the streaming pass can run as k_frag_stream_tests (subject to the batch's nullability)
+    int32_t num_vec;   // its first num_vec (1 or 2) tests read their column with prefetched 128-bit loads
+    StreamTest tests[SR_MAX_STREAM_TESTS];
     int32_t num_stream_joins; // joins [0, num_stream_joins) are tested by the streaming pass
     int32_t final_first_join; // joins [final_first_join, S) are tested inline by the final pass
     // fact columns the final pass reads: fetched for a row in one burst before anything depends on them
@@ -214,41 +226,16 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream(const FragDev* 
     }
     __syncthreads();
 
-    // fast path: the streamed key columns are int32-class, 16-byte aligned and not nullable, and no scan
-    // conjunct precedes the joins -> one 128-bit load per thread, group and column, prefetched a tile ahead
-    bool fast = SJ > 0 && fd.num_preds == 0 && fd.num_exprs == 0;
-    const int32_t* keyp[STREAM_MAX_JOINS] = {nullptr, nullptr};
-    for (int j = 0; j < SJ && fast; j++) {
-        const VDesc& d = vt.v[s_joins[j].key_value_id];
-        fast = type_width(d.type) == 4 && !is_float_class(d.type) && d.nulls == nullptr && (((uintptr_t)d.data) & 15) == 0;
-        keyp[j] = (const int32_t*)d.data;
-    }
-    const bool two = SJ > 1;
+    // (the common shapes -- range conjuncts and joins on plain int32 columns -- run in k_frag_stream_tests below;
+    // this kernel is the general form: any predicate, generic filter expressions, nullable / wide key columns)
     const int64_t num_tiles = (n + STREAM_TILE - 1) / STREAM_TILE;
     const int64_t full_tiles = n / STREAM_TILE;
-    int4 pk[STREAM_MAX_JOINS][STREAM_GROUPS];
-#pragma unroll
-    for (int j = 0; j < STREAM_MAX_JOINS; j++)
-#pragma unroll
-        for (int g = 0; g < STREAM_GROUPS; g++) pk[j][g] = make_int4(0, 0, 0, 0);
     // Each CTA streams a CONTIGUOUS run of tiles (not a grid-stride walk): the rows a warp appends to one
     // selection-vector chunk then come from a narrow band of the table (~25 tiles) instead of being spread over
     // the whole batch, so the later gather passes touch neighbouring sectors / pages back to back.
     const int64_t tiles_per_cta = (num_tiles + gridDim.x - 1) / gridDim.x;
     const int64_t tile_begin = (int64_t)blockIdx.x * tiles_per_cta;
     const int64_t tile_end = tile_begin + tiles_per_cta < num_tiles ? tile_begin + tiles_per_cta : num_tiles;
-    const int64_t prefetch_end = tile_end < full_tiles ? tile_end : full_tiles;
-    auto prefetch = [&](int64_t tile) {
-        if (fast && tile < prefetch_end) {
-#pragma unroll
-            for (int g = 0; g < STREAM_GROUPS; g++) {
-                const int64_t r0 = tile * STREAM_TILE + (int64_t)g * (STREAM_BLOCK * STREAM_ROWS) + (int64_t)threadIdx.x * STREAM_ROWS;
-                pk[0][g] = ldg_stream_v4(keyp[0] + r0);
-                if (two) pk[1][g] = ldg_stream_v4(keyp[1] + r0);
-            }
-        }
-    };
-    prefetch(tile_begin);
     WarpSelWriter writer;
     writer.init(sel_out, counter);
 
@@ -274,20 +261,7 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream(const FragDev* 
 #pragma unroll
             for (int i = 0; i < STREAM_GROUPS * STREAM_ROWS; i++) carry[i] = 0;
         }
-        if (fast && tile < full_tiles) {
-            static_assert(STREAM_GROUPS == 2 && STREAM_ROWS == 4, "8 keys per thread and column");
-            const int32_t k0[8] = {pk[0][0].x, pk[0][0].y, pk[0][0].z, pk[0][0].w, pk[0][1].x, pk[0][1].y, pk[0][1].z, pk[0][1].w};
-            const int32_t k1[8] = {pk[1][0].x, pk[1][0].y, pk[1][0].z, pk[1][0].w, pk[1][1].x, pk[1][1].y, pk[1][1].z, pk[1][1].w};
-            prefetch(tile + 1); // next tile's keys stay in flight while this tile is tested
-            uint32_t a8 = join_test_batch<8>(s_joins[0], smem, k0, 0xFFu);
-            if (two) a8 = join_test_batch<8>(s_joins[1], smem, k1, a8);
-            alive[0] = a8 & 0xFu;
-            alive[1] = a8 >> 4;
-            if (CARRY) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) carry[i] = pd.carry_join == 0 ? k0[i] : k1[i];
-            }
-        } else {
+        {
             int64_t vals[STREAM_GROUPS][STREAM_ROWS];
             uint32_t nullmask[STREAM_GROUPS];
 #pragma unroll 1
@@ -337,6 +311,121 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream(const FragDev* 
         }
         static_assert(STREAM_GROUPS == 2, "two groups of alive bits are packed into one word");
         warp_append_rows<CARRY>(alive[0] | (alive[1] << STREAM_ROWS), row0[0], row0[1], carry, writer);
+    }
+    writer.finish();
+}
+
+// Streaming pass over a list of TESTS (PassDev::tests): scan predicates in range form (lo <= v <= lo + span on an
+// int32-class column: EQ / LT / LE / GT / GE / BETWEEN all reduce to one unsigned subtract + compare) followed by the
+// streamed joins.  The columns of the first one or two tests are read with 128-bit loads prefetched a tile ahead (most
+// of their sectors are needed anyway); every later test loads its column only for the rows still alive (predicated
+// loads, issued back to back).  The host picks this kernel when every test column is int32-class and not nullable
+// (frag_push); anything else takes the generic path of k_frag_stream.
+template <int N>
+__device__ __forceinline__ uint32_t stream_test(const StreamTest& st, const FragJoinDev* s_joins, const uint32_t* smem, const int32_t (&k)[N], uint32_t alive) {
+    if (st.kind == 0) {
+        uint32_t out = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) out |= ((uint32_t)k[i] - st.lo <= st.span ? 1u : 0u) << i;
+        return out & alive;
+    }
+    return join_test_batch<N>(s_joins[st.join], smem, k, alive);
+}
+
+template <bool CARRY>
+__global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream_tests(const FragDev* __restrict__ fdp, PassDev pd, const __grid_constant__ VTab vt, int64_t n,
+                                                                       SelEntry* __restrict__ sel_out, unsigned long long* __restrict__ counter) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ FragJoinDev s_joins[STREAM_MAX_JOINS];
+    __shared__ StreamTest s_tests[SR_MAX_STREAM_TESTS];
+    const FragDev& fd = *fdp;
+    const int SJ = pd.num_stream_joins;
+    const int NT = pd.num_tests;
+    const int NV = pd.num_vec;
+    for (int i = threadIdx.x; i < (int)(sizeof(FragJoinDev) / 4) * SJ; i += blockDim.x) ((uint32_t*)s_joins)[i] = ((const uint32_t*)fd.joins)[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(StreamTest) / 4) * NT; i += blockDim.x) ((uint32_t*)s_tests)[i] = ((const uint32_t*)pd.tests)[i];
+    for (int j = 0; j < SJ; j++) {
+        const FragJoinDev& fj = fd.joins[j];
+        if (fj.smem_off >= 0)
+            for (int w = threadIdx.x; w < fj.bitmap_words; w += blockDim.x) smem[fj.smem_off + w] = fj.j.bitmap[w];
+    }
+    __syncthreads();
+    const int32_t* col0 = (const int32_t*)vt.v[pd.tests[0].value_id].data;
+    const int32_t* col1 = NV > 1 ? (const int32_t*)vt.v[pd.tests[1].value_id].data : nullptr;
+    const int64_t num_tiles = (n + STREAM_TILE - 1) / STREAM_TILE;
+    const int64_t full_tiles = n / STREAM_TILE;
+    const int64_t tiles_per_cta = (num_tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t tile_begin = (int64_t)blockIdx.x * tiles_per_cta;
+    const int64_t tile_end = tile_begin + tiles_per_cta < num_tiles ? tile_begin + tiles_per_cta : num_tiles;
+    const int64_t prefetch_end = tile_end < full_tiles ? tile_end : full_tiles;
+    int4 pk[2][STREAM_GROUPS];
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int g = 0; g < STREAM_GROUPS; g++) pk[j][g] = make_int4(0, 0, 0, 0);
+    auto prefetch = [&](int64_t tile) {
+        if (tile < prefetch_end) {
+#pragma unroll
+            for (int g = 0; g < STREAM_GROUPS; g++) {
+                const int64_t r0 = tile * STREAM_TILE + (int64_t)g * (STREAM_BLOCK * STREAM_ROWS) + (int64_t)threadIdx.x * STREAM_ROWS;
+                pk[0][g] = ldg_stream_v4(col0 + r0);
+                if (col1) pk[1][g] = ldg_stream_v4(col1 + r0);
+            }
+        }
+    };
+    prefetch(tile_begin);
+    WarpSelWriter writer;
+    writer.init(sel_out, counter);
+    static_assert(STREAM_GROUPS == 2 && STREAM_ROWS == 4, "8 rows per thread and tile");
+    for (int64_t tile = tile_begin; tile < tile_end; tile++) {
+        int64_t row0[STREAM_GROUPS];
+#pragma unroll
+        for (int g = 0; g < STREAM_GROUPS; g++)
+            row0[g] = tile * STREAM_TILE + (int64_t)g * (STREAM_BLOCK * STREAM_ROWS) + (int64_t)threadIdx.x * STREAM_ROWS;
+        int32_t carry[8];
+        if (CARRY) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) carry[i] = 0;
+        }
+        uint32_t a8 = 0xFFu;
+        int first_pred = 0; // tests [first_pred, NT) load their column for the live rows only
+        if (tile < full_tiles) {
+            const int32_t k0[8] = {pk[0][0].x, pk[0][0].y, pk[0][0].z, pk[0][0].w, pk[0][1].x, pk[0][1].y, pk[0][1].z, pk[0][1].w};
+            const int32_t k1[8] = {pk[1][0].x, pk[1][0].y, pk[1][0].z, pk[1][0].w, pk[1][1].x, pk[1][1].y, pk[1][1].z, pk[1][1].w};
+            prefetch(tile + 1); // the next tile's vector columns stay in flight while this tile is tested
+            a8 = stream_test<8>(s_tests[0], s_joins, smem, k0, 0xFFu);
+            if (CARRY && s_tests[0].kind == 1 && s_tests[0].join == pd.carry_join) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) carry[i] = k0[i];
+            }
+            if (NV > 1) {
+                a8 = stream_test<8>(s_tests[1], s_joins, smem, k1, a8);
+                if (CARRY && s_tests[1].kind == 1 && s_tests[1].join == pd.carry_join) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) carry[i] = k1[i];
+                }
+            }
+            first_pred = NV;
+        } else { // the ragged last tile: every test through predicated loads
+            a8 = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (row0[i >> 2] + (i & 3) < n) a8 |= 1u << i;
+        }
+#pragma unroll 1
+        for (int t = first_pred; t < NT; t++) {
+            const StreamTest& st = s_tests[t];
+            const int32_t* col = (const int32_t*)vt.v[st.value_id].data;
+            int32_t kk[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) kk[i] = ldg_stream_s32_pred(col + row0[i >> 2] + (i & 3), (a8 >> i) & 1u);
+            a8 = stream_test<8>(st, s_joins, smem, kk, a8);
+            if (CARRY && st.kind == 1 && st.join == pd.carry_join) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) carry[i] = kk[i];
+            }
+        }
+        warp_append_rows<CARRY>(a8, row0[0], row0[1], carry, writer);
     }
     writer.finish();
 }
@@ -392,8 +481,9 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_join(const FragDev
     writer.finish();
 }
 
-// final pass: remaining joins inline, payload lookups, aggregate update
-template <bool SMEM_AGG>
+// final pass: remaining joins inline, payload lookups, aggregate update.  SINGLE: no GROUP BY (its register state
+// would only cost the grouped instantiations spills).
+template <bool SMEM_AGG, bool SINGLE = false>
 __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg(const FragDev* __restrict__ fdp, const AggDev* __restrict__ adp, const __grid_constant__ PassDev pd,
                                                                    const __grid_constant__ VTab vt, const SelEntry* __restrict__ sel_in,
                                                                    const unsigned long long* __restrict__ n_in_ptr) {
@@ -417,6 +507,9 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg(const FragDev*
     // prefetch only doubled the PCIe requests (117 -> 224 ms on SSB Q4.1 SF100).
     const unsigned long long n_in = *n_in_ptr;
     unsigned long long passed = 0;
+    constexpr bool single = SINGLE;
+    SingleAcc sacc;
+    if (single) single_acc_init(ad, sacc);
     unsigned long long w_begin, w_end;
     warp_sel_range(n_in, w_begin, w_end);
     for (unsigned long long i = w_begin + lane_id(); i < w_end; i += 32) {
@@ -447,10 +540,16 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg(const FragDev*
             }
         }
         if (!ok) continue;
-        const long long slot = agg_find_slot(ad, ld);
-        if (slot >= 0) agg_apply_row<SMEM_AGG>(ad, acc, slot, ld);
+        if (single) { // no GROUP BY: the state lives in the thread, not behind an atomic
+            single_acc_row(ad, sacc, ld);
+        } else {
+            const long long slot = agg_find_slot(ad, ld);
+            if (slot >= 0) agg_apply_row<SMEM_AGG>(ad, acc, slot, ld);
+        }
         passed++;
     }
+    __syncwarp();
+    if (single) single_acc_flush(ad, sacc);
     if (SMEM_AGG) {
         __syncthreads();
         acc_smem_flush(ad, acc);
