@@ -93,7 +93,7 @@ __device__ __forceinline__ uint32_t join_test_batch(const FragJoinDev& fj, const
                 const uint32_t idx = (uint32_t)keys[i] - umin;
                 const bool p = ((alive >> i) & 1u) && idx <= span;
                 const uint32_t word = p ? bm[idx >> 5] : 0u;
-                out |= ((word >> (idx & 31)) & 1u) << i;
+                out |= (__funnelshift_r(word, 0u, idx) & 1u) << i; // shifts by idx mod 32
             }
         } else {
             uint32_t words[N];
@@ -110,7 +110,7 @@ __device__ __forceinline__ uint32_t join_test_batch(const FragJoinDev& fj, const
 #pragma unroll
             for (int i = 0; i < N; i++) {
                 const uint32_t idx = (uint32_t)keys[i] - umin;
-                out |= ((words[i] >> (idx & 31)) & 1u) << i;
+                out |= (__funnelshift_r(words[i], 0u, idx) & 1u) << i;
             }
         }
         return out;
@@ -193,13 +193,24 @@ __device__ __forceinline__ void warp_append_rows(uint32_t alive_all, int64_t row
     const uint32_t incl = warp_incl_scan(cnt);
     const uint32_t total = __shfl_sync(SR_FULL_MASK, incl, 31);
     if (total == 0) return;
-    SelEntry* __restrict__ sel_out = w.out;
-    unsigned long long pos = w.reserve(total) + incl - cnt;
+    SelEntry* __restrict__ sel_out = w.out + (w.reserve(total) + incl - cnt);
+    if (CARRY) {
+        uint32_t pos = 0;
 #pragma unroll
-    for (int i = 0; i < STREAM_GROUPS * STREAM_ROWS; i++) {
-        if ((alive_all >> i) & 1u) {
-            const int64_t row = (i < STREAM_ROWS ? row0_g0 : row0_g1) + (i & (STREAM_ROWS - 1));
-            sel_out[pos++] = sel_make((uint32_t)row, CARRY ? carry[i] : 0);
+        for (int i = 0; i < STREAM_GROUPS * STREAM_ROWS; i++) {
+            if ((alive_all >> i) & 1u) {
+                const int64_t row = (i < STREAM_ROWS ? row0_g0 : row0_g1) + (i & (STREAM_ROWS - 1));
+                sel_out[pos++] = sel_make((uint32_t)row, carry[i]);
+            }
+        }
+    } else {
+        // few rows survive (a lane holds 0..2 of its 8): walk the set bits instead of testing all eight
+        const uint32_t r0 = (uint32_t)row0_g0, r1 = (uint32_t)row0_g1 - STREAM_ROWS;
+        uint32_t m = alive_all, pos = 0;
+        while (m) {
+            const uint32_t i = (uint32_t)__ffs((int)m) - 1u;
+            m &= m - 1u;
+            sel_out[pos++] = (SelEntry)((i < STREAM_ROWS ? r0 : r1) + i);
         }
     }
 }
