@@ -93,7 +93,8 @@ __device__ __forceinline__ uint32_t join_test_batch(const FragJoinDev& fj, const
                 const uint32_t idx = (uint32_t)keys[i] - umin;
                 const bool p = ((alive >> i) & 1u) && idx <= span;
                 const uint32_t word = p ? bm[idx >> 5] : 0u;
-                out |= (__funnelshift_r(word, 0u, idx) & 1u) << i; // shifts by idx mod 32
+                // rotate bit (idx mod 32) of the word to position i, then one 3-input logic op merges it into `out`
+                out |= __funnelshift_r(word, word, idx - (uint32_t)i) & (1u << i);
             }
         } else {
             uint32_t words[N];
@@ -110,7 +111,7 @@ __device__ __forceinline__ uint32_t join_test_batch(const FragJoinDev& fj, const
 #pragma unroll
             for (int i = 0; i < N; i++) {
                 const uint32_t idx = (uint32_t)keys[i] - umin;
-                out |= (__funnelshift_r(words[i], 0u, idx) & 1u) << i;
+                out |= __funnelshift_r(words[i], words[i], idx - (uint32_t)i) & (1u << i);
             }
         }
         return out;
