@@ -72,6 +72,26 @@ __device__ __forceinline__ int64_t ldg_stream_s64(const void* p) {
     asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(r) : "l"(p));
     return r;
 }
+// predicated streaming loads: no branch, so the loads of a group issue back to back
+__device__ __forceinline__ int32_t ldg_stream_s32_pred(const void* p, bool pred) {
+    int32_t r;
+    asm volatile(
+            "{ .reg .pred q; setp.ne.u32 q, %2, 0; mov.s32 %0, 0;\n"
+            "  @q ld.global.nc.L1::no_allocate.s32 %0, [%1]; }"
+            : "=r"(r)
+            : "l"(p), "r"((uint32_t)pred));
+    return r;
+}
+__device__ __forceinline__ int64_t ldg_stream_s64_pred(const void* p, bool pred) {
+    int64_t r;
+    asm volatile(
+            "{ .reg .pred q; setp.ne.u32 q, %2, 0; mov.s64 %0, 0;\n"
+            "  @q ld.global.nc.L1::no_allocate.s64 %0, [%1]; }"
+            : "=l"(r)
+            : "l"(p), "r"((uint32_t)pred));
+    return r;
+}
+
 // request a line into L2 without waiting for it (no destination register, no scoreboard)
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));

@@ -459,7 +459,7 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
         // this push's pass parameters: the carried key (planned in f->pass) is only used for host-resident input
         srd::PassDev pass = f->pass;
         pass.host_input = fact->mem == SR_MEM_HOST_PINNED ? 1 : 0;
-        const bool carry = pass.host_input && pass.carry_join >= 0;
+        const bool carry = pass.host_input && pass.carry_join >= 0; // (HBM input, measured: stream +0.27 ms, final -0.09 ms)
         if (!carry) pass.carry_join = pass.carry_value_id = -1;
         unsigned long long* cnt = f->pass_counters.as<unsigned long long>();
         SR_CUDA(ctx, cudaMemsetAsync(cnt, 0, 16 * sizeof(uint64_t), ctx->stream));

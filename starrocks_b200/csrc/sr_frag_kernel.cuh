@@ -65,26 +65,6 @@ struct FragLoader {
     }
 };
 
-// predicated streaming loads: no branch, so the loads of a group issue back to back
-__device__ __forceinline__ int32_t ldg_stream_s32_pred(const void* p, bool pred) {
-    int32_t r;
-    asm volatile(
-            "{ .reg .pred q; setp.ne.u32 q, %2, 0; mov.s32 %0, 0;\n"
-            "  @q ld.global.nc.L1::no_allocate.s32 %0, [%1]; }"
-            : "=r"(r)
-            : "l"(p), "r"((uint32_t)pred));
-    return r;
-}
-__device__ __forceinline__ int64_t ldg_stream_s64_pred(const void* p, bool pred) {
-    int64_t r;
-    asm volatile(
-            "{ .reg .pred q; setp.ne.u32 q, %2, 0; mov.s64 %0, 0;\n"
-            "  @q ld.global.nc.L1::no_allocate.s64 %0, [%1]; }"
-            : "=l"(r)
-            : "l"(p), "r"((uint32_t)pred));
-    return r;
-}
-
 // one fact value for each alive row of a 4-row group (warp-uniform descriptor)
 __device__ __forceinline__ void load_rows4(const VDesc& d, int64_t row0, uint32_t alive, int64_t vals[FRAG_ROWS], uint32_t& nullmask) {
     nullmask = 0;

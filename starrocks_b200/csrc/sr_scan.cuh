@@ -103,6 +103,152 @@ struct CompactArgs {
     int32_t n;
 };
 
+// ---- warp-tile scan: 8 consecutive rows per lane, 256 rows per warp -----------------------------------------------
+// k_scan_mask    conjuncts -> one selection BYTE PER LANE (bit r = row r of the lane's 8 rows survives), the tile's
+//                survivor count, and (optionally) the reference-style uint8-per-row Filter
+// k_scan_lvl1    first level of the exclusive scan of the tile counts (1024 tiles per block)
+// k_scan_compact order-preserving compaction of every output column in ONE pass: a warp's survivors land in one
+//                contiguous output run (tile offset + lane prefix + rank inside the lane)
+// FAST form of the conjuncts: lo <= v <= lo + span on non-nullable int32-class columns (EQ / LT / LE / GT / GE /
+// BETWEEN all reduce to it); the first column is read with two 128-bit loads per lane, the later ones only for the
+// rows still alive (predicated loads).
+constexpr int SCANW_ROWS = 8;
+constexpr int SCANW_TILE = 32 * SCANW_ROWS;
+constexpr int SCANW_BLOCK = 256;
+#define SR_MAX_SCAN_RANGE_TESTS 8
+
+struct RangeTest {
+    int32_t value_id;
+    uint32_t lo, span;
+};
+struct ScanTests {
+    int32_t num_tests; // 0: generic evaluation
+    int32_t vec0;      // the first column may be read with 128-bit loads (16-byte aligned)
+    RangeTest t[SR_MAX_SCAN_RANGE_TESTS];
+};
+
+template <bool FAST>
+__global__ void __launch_bounds__(SCANW_BLOCK) k_scan_mask(const ScanProg* __restrict__ prog, const __grid_constant__ ScanTests st, const __grid_constant__ VTab vt,
+                                                            int64_t n, uint8_t* __restrict__ mask_bits, uint32_t* __restrict__ tile_counts,
+                                                            uint8_t* __restrict__ sel_bytes) {
+    const int64_t ntiles = (n + SCANW_TILE - 1) / SCANW_TILE;
+    const int64_t warps = (int64_t)gridDim.x * (SCANW_BLOCK / 32);
+    const uint32_t lane = lane_id();
+    for (int64_t tile = (int64_t)blockIdx.x * (SCANW_BLOCK / 32) + (threadIdx.x >> 5); tile < ntiles; tile += warps) {
+        const int64_t base = tile * SCANW_TILE + (int64_t)lane * SCANW_ROWS;
+        uint32_t m = 0;
+#pragma unroll
+        for (int r = 0; r < SCANW_ROWS; r++)
+            if (base + r < n) m |= 1u << r;
+        if (FAST) {
+            const bool full = m == 0xFFu;
+#pragma unroll 1
+            for (int t = 0; t < st.num_tests; t++) {
+                const RangeTest& rt = st.t[t];
+                const int32_t* col = (const int32_t*)vt.v[rt.value_id].data;
+                int32_t k[SCANW_ROWS];
+                if (t == 0 && st.vec0 && full) {
+                    const int4 a = ldg_stream_v4(col + base), b = ldg_stream_v4(col + base + 4);
+                    k[0] = a.x, k[1] = a.y, k[2] = a.z, k[3] = a.w, k[4] = b.x, k[5] = b.y, k[6] = b.z, k[7] = b.w;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < SCANW_ROWS; r++) k[r] = ldg_stream_s32_pred(col + base + r, (m >> r) & 1u);
+                }
+                uint32_t pass = 0;
+#pragma unroll
+                for (int r = 0; r < SCANW_ROWS; r++) pass |= ((uint32_t)k[r] - rt.lo <= rt.span ? 1u : 0u) << r;
+                m &= pass;
+            }
+        } else {
+#pragma unroll 1
+            for (int r = 0; r < SCANW_ROWS; r++) {
+                if (!((m >> r) & 1u)) continue;
+                ChunkLoader ld{vt, base + r};
+                bool pass = true;
+                for (int p = 0; p < prog->num_preds && pass; p++) {
+                    int64_t bits;
+                    const bool nul = ld.load(prog->preds[p].value_id, bits);
+                    pass = eval_pred(prog->preds[p], bits, nul);
+                }
+                for (int e = 0; e < prog->num_exprs && pass; e++) {
+                    int64_t bits;
+                    const bool nul = eval_expr(prog->exprs[e], ld, bits);
+                    pass = !nul && bits != 0;
+                }
+                if (!pass) m &= ~(1u << r);
+            }
+        }
+        if (mask_bits) mask_bits[tile * 32 + lane] = (uint8_t)m;
+        if (sel_bytes) {
+#pragma unroll
+            for (int r = 0; r < SCANW_ROWS; r++)
+                if (base + r < n) sel_bytes[base + r] = (uint8_t)((m >> r) & 1u);
+        }
+        if (tile_counts) {
+            const uint32_t c = warp_sum((uint32_t)__popc(m));
+            if (lane == 0) tile_counts[tile] = c;
+        }
+    }
+}
+
+// exclusive scan inside blocks of 1024 counts; block_sums[b] = total of block b
+__global__ void __launch_bounds__(1024) k_scan_lvl1(const uint32_t* __restrict__ counts, int64_t n, uint32_t* __restrict__ local_excl, uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t s_scan[1024 / 32 + 1];
+    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    const uint32_t v = i < n ? counts[i] : 0;
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan<1024>(v, s_scan, &tot);
+    if (i < n) local_excl[i] = ex;
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+template <typename T>
+__device__ __forceinline__ void compact_rows(const void* __restrict__ src, void* __restrict__ dst, int64_t base, uint32_t m, uint64_t out_pos) {
+    const T* s = (const T*)src + base;
+    T* d = (T*)dst + out_pos;
+    uint32_t q = 0;
+#pragma unroll
+    for (int r = 0; r < SCANW_ROWS; r++)
+        if ((m >> r) & 1u) d[q++] = s[r];
+}
+
+__global__ void __launch_bounds__(SCANW_BLOCK) k_scan_compact(const uint8_t* __restrict__ mask_bits, const uint32_t* __restrict__ local_excl,
+                                                               const uint64_t* __restrict__ block_offsets, CompactArgs args, int64_t n) {
+    const int64_t ntiles = (n + SCANW_TILE - 1) / SCANW_TILE;
+    const int64_t warps = (int64_t)gridDim.x * (SCANW_BLOCK / 32);
+    const uint32_t lane = lane_id();
+    for (int64_t tile = (int64_t)blockIdx.x * (SCANW_BLOCK / 32) + (threadIdx.x >> 5); tile < ntiles; tile += warps) {
+        const uint32_t m = mask_bits[tile * 32 + lane];
+        const uint32_t cnt = __popc(m);
+        const uint32_t incl = warp_incl_scan(cnt);
+        if (__shfl_sync(SR_FULL_MASK, incl, 31) == 0) continue;
+        const int64_t base = tile * SCANW_TILE + (int64_t)lane * SCANW_ROWS;
+        const uint64_t out_pos = block_offsets[tile >> 10] + local_excl[tile] + (incl - cnt);
+        if (cnt == 0) continue;
+#pragma unroll 1
+        for (int c = 0; c < args.n; c++) {
+            const CompactCol col = args.c[c];
+            switch (col.width) {
+            case 1:
+                compact_rows<uint8_t>(col.src, col.dst, base, m, out_pos);
+                break;
+            case 2:
+                compact_rows<uint16_t>(col.src, col.dst, base, m, out_pos);
+                break;
+            case 4:
+                compact_rows<uint32_t>(col.src, col.dst, base, m, out_pos);
+                break;
+            case 8:
+                compact_rows<uint64_t>(col.src, col.dst, base, m, out_pos);
+                break;
+            default:
+                compact_rows<int4>(col.src, col.dst, base, m, out_pos);
+                break;
+            }
+        }
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ void copy_elem(const void* src, void* dst, int64_t s, int64_t d) {
     ((T*)dst)[d] = ((const T*)src)[s];
@@ -205,6 +351,9 @@ struct sr_scan {
     DevBuf prog;
     Staged staged;
     DevBuf sel, block_counts, tile_offsets;
+    // warp-tile scan (k_scan_mask / k_scan_lvl1 / k_scan_compact)
+    DevBuf mask_bits, tile_counts, local_excl, block_sums, block_offsets;
+    srd::ScanTests tests; // range form of the conjuncts (num_tests == 0: generic evaluation)
     std::vector<DevBuf> out_bufs; // 2 per out slot
 };
 
@@ -227,6 +376,31 @@ static int32_t scan_compile(sr_scan* s) {
     }
     hp->num_preds = (int32_t)s->preds.size();
     hp->num_exprs = (int32_t)s->exprs.size();
+    // range form: every conjunct is EQ / LT / LE / GT / GE / BETWEEN with integer bounds on an int32-class column
+    memset(&s->tests, 0, sizeof(s->tests));
+    {
+        bool ok = s->exprs.empty() && !s->preds.empty() && s->preds.size() <= SR_MAX_SCAN_RANGE_TESTS;
+        for (size_t k = 0; k < s->preds.size() && ok; k++) {
+            const srd::CPred& cp = hp->preds[k];
+            long long lo = INT32_MIN, hi = INT32_MAX;
+            switch (cp.op) {
+            case SR_PRED_EQ: lo = hi = cp.ilo; break;
+            case SR_PRED_LT: hi = cp.ilo - 1; break;
+            case SR_PRED_LE: hi = cp.ilo; break;
+            case SR_PRED_GT: lo = cp.ilo + 1; break;
+            case SR_PRED_GE: lo = cp.ilo; break;
+            case SR_PRED_BETWEEN: lo = cp.ilo; hi = cp.ihi; break;
+            default: ok = false; break;
+            }
+            lo = std::max<long long>(lo, INT32_MIN);
+            hi = std::min<long long>(hi, INT32_MAX);
+            const int32_t t = s->reg.types[cp.value_id];
+            if (cp.is_double || srd::type_width(t) != 4 || srd::is_float_class(t) || lo > hi) ok = false;
+            if (!ok) break;
+            s->tests.t[k] = srd::RangeTest{cp.value_id, (uint32_t)(int32_t)lo, (uint32_t)(hi - lo)};
+        }
+        s->tests.num_tests = ok ? (int32_t)s->preds.size() : 0;
+    }
     SR_TRY(s->prog.reserve(ctx, sizeof(srd::ScanProg)));
     SR_CUDA(ctx, cudaMemcpyAsync(s->prog.p, hp, sizeof(srd::ScanProg), cudaMemcpyHostToDevice, ctx->stream));
     SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // hostbuf goes out of scope
@@ -243,21 +417,37 @@ static int32_t scan_select(sr_scan* s, const sr_chunk_view* in, bool want_counts
     VTab vt;
     SR_TRY(bind_vtab(ctx, s->reg, s->staged, &vt));
     const int64_t n = in->num_rows;
-    const int tiles = grid_for(n, srd::SCAN_TILE);
-    SR_TRY(s->sel.reserve(ctx, (size_t)std::max<int64_t>(n, 1)));
+    const int64_t tiles = (n + srd::SCANW_TILE - 1) / srd::SCANW_TILE;
+    const int64_t nblk = (tiles + 1023) / 1024;
+    if (!want_counts) SR_TRY(s->sel.reserve(ctx, (size_t)std::max<int64_t>(n, 1)));
     if (want_counts) {
-        SR_TRY(s->block_counts.reserve(ctx, sizeof(uint32_t) * (size_t)tiles));
-        SR_TRY(s->tile_offsets.reserve(ctx, sizeof(uint64_t) * (size_t)tiles));
+        SR_TRY(s->mask_bits.reserve(ctx, (size_t)std::max<int64_t>(tiles, 1) * 32));
+        SR_TRY(s->tile_counts.reserve(ctx, sizeof(uint32_t) * (size_t)std::max<int64_t>(tiles, 1)));
+        SR_TRY(s->local_excl.reserve(ctx, sizeof(uint32_t) * (size_t)std::max<int64_t>(tiles, 1)));
+        SR_TRY(s->block_sums.reserve(ctx, sizeof(uint32_t) * (size_t)std::max<int64_t>(nblk, 1)));
+        SR_TRY(s->block_offsets.reserve(ctx, sizeof(uint64_t) * (size_t)std::max<int64_t>(nblk, 1)));
     }
+    // the fast (range) form needs plain columns in THIS batch: not nullable; vector loads on the first one if aligned
+    srd::ScanTests tests = s->tests;
+    for (int t = 0; t < tests.num_tests; t++)
+        if (vt.v[tests.t[t].value_id].nulls != nullptr) tests.num_tests = 0;
+    tests.vec0 = tests.num_tests > 0 && (((uintptr_t)vt.v[tests.t[0].value_id].data) & 15) == 0 ? 1 : 0;
     if (n > 0) {
-        srd::k_scan_select<<<tiles, srd::SCAN_BLOCK, 0, ctx->stream>>>((const srd::ScanProg*)s->prog.p, vt, n, s->sel.as<uint8_t>(),
-                                                                      want_counts ? s->block_counts.as<uint32_t>() : nullptr);
+        const int grid = (int)std::min<int64_t>((tiles + srd::SCANW_BLOCK / 32 - 1) / (srd::SCANW_BLOCK / 32), (int64_t)ctx->num_sms * 8);
+        uint8_t* mask = want_counts ? s->mask_bits.as<uint8_t>() : nullptr;
+        uint32_t* counts = want_counts ? s->tile_counts.as<uint32_t>() : nullptr;
+        uint8_t* bytes = want_counts ? nullptr : s->sel.as<uint8_t>();
+        if (tests.num_tests > 0)
+            srd::k_scan_mask<true><<<grid, srd::SCANW_BLOCK, 0, ctx->stream>>>((const srd::ScanProg*)s->prog.p, tests, vt, n, mask, counts, bytes);
+        else
+            srd::k_scan_mask<false><<<grid, srd::SCANW_BLOCK, 0, ctx->stream>>>((const srd::ScanProg*)s->prog.p, tests, vt, n, mask, counts, bytes);
         SR_LAUNCH_CHECK(ctx);
     }
     if (want_counts) {
         if (n > 0) {
-            srd::k_scan_counts<<<1, 1024, 0, ctx->stream>>>(s->block_counts.as<uint32_t>(), tiles, s->tile_offsets.as<uint64_t>(),
-                                                           ctx->dscratch);
+            srd::k_scan_lvl1<<<(int)nblk, 1024, 0, ctx->stream>>>(s->tile_counts.as<uint32_t>(), tiles, s->local_excl.as<uint32_t>(), s->block_sums.as<uint32_t>());
+            SR_LAUNCH_CHECK(ctx);
+            srd::k_scan_counts<<<1, 1024, 0, ctx->stream>>>(s->block_sums.as<uint32_t>(), nblk, s->block_offsets.as<uint64_t>(), ctx->dscratch);
             SR_LAUNCH_CHECK(ctx);
             SR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->dscratch, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
             SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
