@@ -314,17 +314,32 @@ __device__ __forceinline__ void agg_count_new_groups(const AggDev& a, bool inser
 
 // shared-memory accumulators: explicit .shared reductions (a generic-address atomic on a shared
 // location is far slower than red.shared)
+// 64-bit add into shared memory through NATIVE 32-bit shared atomics: add the low word (atom returns the old value ->
+// exactly one adder sees each wrap), then add high word + carry when that is not zero.  A 64-bit shared atomic
+// compiles to a compare-and-swap spin loop (SASS ATOMS.CAST.SPIN.64), which collapses when the lanes of a warp hit
+// the same few group slots.  Readers only look at the slots after a barrier, so the two halves need not move together.
+__device__ __forceinline__ void smem_add_u64(long long* p, unsigned long long v) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(p);
+    const uint32_t lo = (uint32_t)v;
+    uint32_t hi = (uint32_t)(v >> 32);
+    if (lo) {
+        uint32_t old;
+        asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(s), "r"(lo) : "memory");
+        hi += (old + lo) < old ? 1u : 0u;
+    }
+    if (hi) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(s + 4), "r"(hi) : "memory");
+}
 __device__ __forceinline__ void red_shared_add_u64(long long* p, unsigned long long v) {
-    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "l"(v) : "memory");
+    smem_add_u64(p, v);
 }
 __device__ __forceinline__ void acc_apply_shared(int32_t mode, long long* a0, long long* a1, long long slot, long long bits) {
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(a0 + slot);
     switch (mode) {
     case M_COUNT:
-        asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(s0), "l"(1ull) : "memory");
+        smem_add_u64(a0 + slot, 1ull);
         break;
     case M_SUM_I64:
-        asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(s0), "l"((unsigned long long)bits) : "memory");
+        smem_add_u64(a0 + slot, (unsigned long long)bits);
         break;
     case M_SUM_F64:
     case M_AVG:

@@ -124,6 +124,7 @@ static int32_t frag_bind_vtab(sr_fragment* f, VTab* vt) {
             vt->v[k].src = f->value_src[k];
         }
     }
+    vt_mark_plain32(vt);
     return SR_OK;
 }
 

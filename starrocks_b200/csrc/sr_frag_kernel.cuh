@@ -51,6 +51,10 @@ struct FragLoader {
         }
         const VDesc& d = vt.v[id];
         if (d.src < 0) {
+            if (vt.plain32) { // non-nullable int32-class fact columns only (warp-uniform)
+                bits = (int64_t)ldg_stream_s32((const int32_t*)d.data + row);
+                return false;
+            }
             const bool nul = d.nulls != nullptr && d.nulls[row] != 0;
             bits = is_float_class(d.type) ? __double_as_longlong(load_double(d.data, d.type, row)) : load_int(d.data, d.type, row);
             return nul;

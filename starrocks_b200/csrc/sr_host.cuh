@@ -238,8 +238,20 @@ struct VDesc {
 struct VTab {
     VDesc v[SR_MAX_VALUES];
     int32_t n;
-    int32_t pad;
+    // every value read from the kernel's own row is a non-nullable int32-class column: the loaders skip the type
+    // dispatch and the null probe (the common shape of fact tables: dictionary codes, keys, dates, int measures)
+    int32_t plain32;
 };
+
+static inline void vt_mark_plain32(VTab* vt) {
+    vt->plain32 = 1;
+    for (int k = 0; k < vt->n; k++) {
+        const VDesc& d = vt->v[k];
+        if (d.src >= 0) continue;
+        const bool i32 = d.type == SR_TYPE_INT || d.type == SR_TYPE_DATE || d.type == SR_TYPE_DECIMAL32;
+        if (!i32 || d.nulls != nullptr) vt->plain32 = 0;
+    }
+}
 
 // host-side registry mapping slot -> value id while compiling
 struct VReg {
@@ -430,6 +442,7 @@ static int32_t bind_vtab(sr_ctx* ctx, const VReg& reg, const Staged& st, VTab* v
         vt->v[k].type = st.cols[c].type;
         vt->v[k].src = -1;
     }
+    vt_mark_plain32(vt);
     return SR_OK;
 }
 

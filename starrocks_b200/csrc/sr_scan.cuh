@@ -16,6 +16,10 @@ struct ChunkLoader {
     int64_t row;
     __device__ __forceinline__ bool load(int id, int64_t& bits) const {
         const VDesc& d = vt.v[id];
+        if (vt.plain32) { // every column of this batch is a non-nullable int32-class column (warp-uniform)
+            bits = (int64_t)ldg_stream_s32((const int32_t*)d.data + row);
+            return false;
+        }
         const bool nul = d.nulls != nullptr && d.nulls[row] != 0;
         bits = is_float_class(d.type) ? __double_as_longlong(load_double(d.data, d.type, row)) : load_int(d.data, d.type, row);
         return nul;
