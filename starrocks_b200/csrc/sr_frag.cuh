@@ -63,6 +63,7 @@ struct sr_fragment {
     srd::PassDev pass;
     std::vector<int> gather_joins; // probe positions that get a pass of their own
     DevBuf sel[2], pass_counters;
+    double est_rate = 1.0; // sampled fraction of the fact rows that reaches the aggregate
     size_t stream_smem = 0;
     int stream_grid = 0;
     int final_grid = 0;
@@ -252,6 +253,7 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
     // ---- mode: when few rows reach the aggregate, run selection-vector passes instead of the cascade ----
     double total_rate = f->pred_rate;
     for (int q = 0; q < f->num_joins; q++) total_rate *= f->pass_rate[ord[q]];
+    f->est_rate = total_rate;
     f->selective = f->force_mode == 2 || (f->force_mode == 0 && total_rate < 0.25 && n >= (1 << 16));
     if (f->selective) {
         // joins whose key column is streamed: the first one, and the second when >= 8 % of the rows reach it
@@ -445,8 +447,12 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
     const srd::AggDev& ah = a->host;
     const bool hash = !ah.dense && ah.num_keys > 0;
     if (hash) {
-        // survivors are unknown before the pass: make the table large enough for the worst case
-        while ((uint64_t)a->ngroups_host + (uint64_t)n > a->host.limit) {
+        // Survivors are unknown before the pass.  The single-kernel cascade has no way to retry a row, so its table is
+        // made large enough for the worst case (every row a new group).  The selection-vector passes size the table
+        // from the sampled survivor estimate (x2 + slack) and re-apply the rows the table refused after growing it.
+        uint64_t want = (uint64_t)n;
+        if (f->selective) want = std::min<uint64_t>((uint64_t)n, (uint64_t)((double)n * std::min(1.0, f->est_rate) * 2.0) + (1u << 16));
+        while ((uint64_t)a->ngroups_host + want > a->host.limit) {
             if (a->host.cap >= (1ull << 33)) return sr_fail(ctx, SR_ERR_OUT_OF_MEMORY, "aggregate table would exceed 2^33 slots; push smaller batches");
             SR_TRY(agg_grow(a, a->host.cap * 4));
         }
@@ -497,24 +503,47 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
             k++;
         }
         SR_CUDA(ctx, cudaEventRecord(f->ev[2], ctx->stream));
+        // hash table: rows it refuses go to the other selection buffer (free by now) and are retried after a growth
+        if (hash) SR_TRY(f->sel[cur ^ 1].reserve(ctx, sizeof(srd::SelEntry) * ((size_t)n + slack)));
+        srd::SelEntry* fail_list = hash ? f->sel[cur ^ 1].as<srd::SelEntry>() : nullptr;
+        unsigned long long* fail_count = cnt + 8;
         if (ah.num_keys == 0)
             srd::k_frag_gather_agg<false, true><<<f->final_grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, pass, vt,
-                                                                                              f->sel[cur].as<srd::SelEntry>(), cnt + k);
+                                                                                              f->sel[cur].as<srd::SelEntry>(), cnt + k, nullptr, nullptr);
         else if (f->smem_agg)
             srd::k_frag_gather_agg<true><<<f->final_grid, srd::GATHER_BLOCK, a->smem_bytes, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, pass, vt,
-                                                                                                   f->sel[cur].as<srd::SelEntry>(), cnt + k);
+                                                                                                   f->sel[cur].as<srd::SelEntry>(), cnt + k, nullptr, nullptr);
         else
             srd::k_frag_gather_agg<false><<<f->final_grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, pass, vt,
-                                                                                        f->sel[cur].as<srd::SelEntry>(), cnt + k);
+                                                                                        f->sel[cur].as<srd::SelEntry>(), cnt + k, fail_list, fail_count);
         SR_LAUNCH_CHECK(ctx);
         SR_CUDA(ctx, cudaEventRecord(f->ev[3], ctx->stream));
         f->timed_push = true;
         if (hash) {
-            uint64_t ng;
-            int32_t ovf, bad;
-            SR_TRY(agg_read_counters(a, &ng, &ovf, &bad));
-            a->ngroups_host = (int64_t)ng;
-            if (ovf) return sr_fail(ctx, SR_ERR_STATE, "aggregate hash table overflow (internal)");
+            int fc = 8; // index of the live fail counter in `cnt`
+            while (true) {
+                uint64_t ng;
+                int32_t ovf, bad;
+                SR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned + 16, cnt + fc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                SR_TRY(agg_read_counters(a, &ng, &ovf, &bad)); // synchronises
+                a->ngroups_host = (int64_t)ng;
+                const uint64_t failed = ctx->pinned[16];
+                if (failed == 0) break;
+                // grow so that the refused rows fit even if each of them is a new group, then re-apply them
+                SR_CUDA(ctx, cudaMemsetAsync((uint8_t*)a->counters.p + 8, 0, 8, ctx->stream)); // overflow / range flags
+                uint64_t cap = a->host.cap;
+                while ((uint64_t)a->ngroups_host + failed > cap / 2) cap *= 4;
+                if (cap > (1ull << 33)) return sr_fail(ctx, SR_ERR_OUT_OF_MEMORY, "aggregate table would exceed 2^33 slots; push smaller batches");
+                SR_TRY(agg_grow(a, cap));
+                cur ^= 1; // the fail list becomes the input, the old input buffer the new fail list
+                const int nfc = fc == 8 ? 9 : 8;
+                SR_CUDA(ctx, cudaMemsetAsync(cnt + nfc, 0, 8, ctx->stream));
+                srd::k_frag_gather_agg<false><<<f->final_grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, pass, vt,
+                                                                                            f->sel[cur].as<srd::SelEntry>(), cnt + fc,
+                                                                                            f->sel[cur ^ 1].as<srd::SelEntry>(), cnt + nfc);
+                SR_LAUNCH_CHECK(ctx);
+                fc = nfc;
+            }
         }
         return SR_OK;
     }

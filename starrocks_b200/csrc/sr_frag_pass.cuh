@@ -498,12 +498,18 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_join(const FragDev
 template <bool SMEM_AGG, bool SINGLE = false>
 __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg(const FragDev* __restrict__ fdp, const AggDev* __restrict__ adp, const __grid_constant__ PassDev pd,
                                                                    const __grid_constant__ VTab vt, const SelEntry* __restrict__ sel_in,
-                                                                   const unsigned long long* __restrict__ n_in_ptr) {
+                                                                   const unsigned long long* __restrict__ n_in_ptr, SelEntry* __restrict__ fail_list,
+                                                                   unsigned long long* __restrict__ fail_count) {
+    // Hash aggregate tables are sized from the SAMPLED survivor estimate, not for the worst case "every row is a new
+    // group" (a 65 M-row batch would allocate and clear a 13 GB table for 0.2 M groups).  A row the table cannot admit
+    // (admission limit) is appended to fail_list; the host grows the table and runs this kernel again over that list.
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ FragJoinDev s_joins[SR_MAX_FRAG_JOINS];
     const FragDev& fd = *fdp;
     const AggDev& ad = *adp;
     const int S = fd.num_joins;
+    const bool hash_table = !SINGLE && !ad.dense && ad.num_keys > 0;
+    unsigned long long known_groups = hash_table && fail_list ? *(volatile unsigned long long*)ad.ngroups : 0ull;
     for (int i = threadIdx.x; i < (int)(sizeof(FragJoinDev) / 4) * S; i += blockDim.x) ((uint32_t*)s_joins)[i] = ((const uint32_t*)fd.joins)[i];
     AccPtrs acc;
     if (SMEM_AGG) {
@@ -554,6 +560,17 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg(const FragDev*
         if (!ok) continue;
         if (single) { // no GROUP BY: the state lives in the thread, not behind an atomic
             single_acc_row(ad, sacc, ld);
+        } else if (hash_table) {
+            HKey key;
+            agg_pack_key(ad, ld, key);
+            bool inserted;
+            const long long slot = agg_find_slot_key(ad, key, inserted, known_groups);
+            agg_count_new_groups(ad, inserted, known_groups);
+            if (slot < 0) {
+                if (fail_list) fail_list[atomicAdd(fail_count, 1ull)] = entry; // retried after the table has grown
+                continue;
+            }
+            agg_apply_row<SMEM_AGG>(ad, acc, slot, ld);
         } else {
             const long long slot = agg_find_slot(ad, ld);
             if (slot >= 0) agg_apply_row<SMEM_AGG>(ad, acc, slot, ld);

@@ -639,6 +639,27 @@ def test_fragment_tpch_q3_parity(gpu, ctx, oracle, mode):
                 x.close()
 
 
+def test_fragment_hash_table_grows_when_the_sampled_estimate_is_wrong(gpu, ctx, oracle):
+    # the plan samples the first 64 K rows: none of them passes the conjunct, so the hash table is sized for ~0 groups;
+    # the remaining 2.9 M rows all pass and all are new groups -> refused rows are re-applied after the table has grown
+    n = 3_000_000
+    idx = np.arange(n, dtype=np.int32)
+    rng = np.random.default_rng(31)
+    fact = Chunk([(0, idx, None), (1, rng.permutation(n).astype(np.int32), None), (2, rng.integers(-50, 50, n, dtype=np.int32), None)])
+    sd = abi.ScanDesc(preds=[abi.make_pred(0, abi.PRED_GE, 70_000)])
+    agg_desc = abi.make_agg_desc([1], [abi.TYPE_INT], fns=[(abi.AGG_SUM, abi.TYPE_INT, 10, [("col", 2)]), (abi.AGG_COUNT_STAR, 0, 11, None)])
+    frag = gpu.Fragment(ctx, sd, [], agg_desc, mode=2)
+    try:
+        frag.push(fact)
+        assert frag.rows_passed == n - 70_000
+        got = gpu_rows(frag.agg.result())
+        ores, opassed = oracle.fragment_run(sd, [], agg_desc, fact, num_threads=4)
+        assert opassed == n - 70_000 and len(got) == n - 70_000
+        assert_rows_equal(got, oracle_rows(ores))
+    finally:
+        frag.close()
+
+
 def test_fragment_rejects_duplicate_build_keys(gpu, ctx):
     d = abi.make_join_desc(abi.JOIN_INNER, [10], [0], [abi.TYPE_INT])
     j = gpu.Join(ctx, d)
