@@ -1069,8 +1069,9 @@ struct sr_agg {
     int64_t out_rows = -1;
     int64_t cursor = 0;
     DevBuf block_counts, block_offsets;
+    ScanScratch scan_scratch;
     std::vector<DevBuf> out_bufs;      // device result columns (data, nulls) x (keys + fns)
-    std::vector<std::vector<uint8_t>> host_bufs;
+    std::vector<PinnedBuf> host_bufs; // host-memory pull: page-locked, the D2H copies are plain DMA
     int32_t out_types[SR_MAX_GROUP_KEYS + SR_MAX_AGG_FNS];
     bool out_has_nulls[SR_MAX_GROUP_KEYS + SR_MAX_AGG_FNS];
 };
@@ -1437,8 +1438,7 @@ static int32_t agg_push_partitioned(sr_agg* a, const VTab& vt, int64_t n) {
         srd::k_agg_part_hist<<<grid, srd::AGGP_BLOCK, 0, ctx->stream>>>(dev, vt, done, m, log2p, shift, a->part_hist.as<uint32_t>());
         SR_LAUNCH_CHECK(ctx);
         if (trace) SR_CUDA(ctx, cudaEventRecord(tev[1], ctx->stream));
-        srd::k_scan_counts<<<1, 1024, 0, ctx->stream>>>(a->part_hist.as<uint32_t>(), (int64_t)P * grid, a->part_offs.as<uint64_t>(), ctx->dscratch);
-        SR_LAUNCH_CHECK(ctx);
+        SR_TRY(scan_counts(ctx, &a->scan_scratch, a->part_hist.as<uint32_t>(), (int64_t)P * grid, a->part_offs.as<uint64_t>()));
         if (trace) SR_CUDA(ctx, cudaEventRecord(tev[2], ctx->stream));
         srd::k_agg_part_scatter<<<grid, srd::AGGP_BLOCK, srd::AGGP_SCATTER_SMEM, ctx->stream>>>(dev, vt, done, m, log2p, shift, a->part_offs.as<uint64_t>(), st);
         SR_LAUNCH_CHECK(ctx);
@@ -1586,8 +1586,7 @@ static int32_t agg_finish_output(sr_agg* a) {
     SR_TRY(a->block_offsets.reserve(ctx, sizeof(uint64_t) * (size_t)blocks));
     srd::k_agg_count<<<blocks, srd::EMIT_BLOCK, 0, ctx->stream>>>((const srd::AggDev*)a->dev.p, total, a->block_counts.as<uint32_t>());
     SR_LAUNCH_CHECK(ctx);
-    srd::k_scan_counts<<<1, 1024, 0, ctx->stream>>>(a->block_counts.as<uint32_t>(), blocks, a->block_offsets.as<uint64_t>(), ctx->dscratch);
-    SR_LAUNCH_CHECK(ctx);
+    SR_TRY(scan_counts(ctx, &a->scan_scratch, a->block_counts.as<uint32_t>(), blocks, a->block_offsets.as<uint64_t>()));
     // one read-back, one synchronisation: the row count and the table's status counters together
     SR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->dscratch, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     SR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned + 8, a->counters.p, 16, cudaMemcpyDeviceToHost, ctx->stream));

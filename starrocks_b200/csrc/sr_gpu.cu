@@ -151,6 +151,7 @@ struct sr_xchg {
     sr_part_desc desc;
     Staged staged;
     DevBuf hash_values, channel_ids, counts, offsets, row_index;
+    ScanScratch scan_scratch;
     std::vector<DevBuf> out_bufs;
 };
 
@@ -484,7 +485,7 @@ int32_t sr_agg_pull(sr_agg* a, int64_t max_rows, int32_t out_mem, sr_chunk_out* 
     out->num_cols = nc;
     out->mem = out_mem;
     out->num_rows = std::max<int64_t>(n, 0);
-    if (out_mem == SR_MEM_HOST) a->host_bufs.resize(2 * (size_t)nc);
+    if (out_mem == SR_MEM_HOST && a->host_bufs.size() < 2 * (size_t)nc) a->host_bufs.resize(2 * (size_t)nc);
     for (int k = 0; k < nc; k++) {
         const int32_t type = a->out_rows > 0 || a->compiled ? a->out_types[k] : (k < d.num_group_keys ? d.group_types[k] : agg_result_type(d.fns[k - d.num_group_keys]));
         const int w = srd::type_width(type);
@@ -499,13 +500,13 @@ int32_t sr_agg_pull(sr_agg* a, int64_t max_rows, int32_t out_mem, sr_chunk_out* 
             out->cols[k].data = (void*)ddata;
             out->cols[k].nulls = (uint8_t*)dnull;
         } else {
-            a->host_bufs[2 * k].resize((size_t)n * w);
-            SR_CUDA(ctx, cudaMemcpyAsync(a->host_bufs[2 * k].data(), ddata, (size_t)n * w, cudaMemcpyDeviceToHost, ctx->stream));
-            out->cols[k].data = a->host_bufs[2 * k].data();
+            if (!a->host_bufs[2 * k].reserve((size_t)n * w)) return sr_fail(ctx, SR_ERR_OUT_OF_MEMORY, "pinned host buffer of %zu bytes", (size_t)n * w);
+            SR_CUDA(ctx, cudaMemcpyAsync(a->host_bufs[2 * k].p, ddata, (size_t)n * w, cudaMemcpyDeviceToHost, ctx->stream));
+            out->cols[k].data = a->host_bufs[2 * k].p;
             if (dnull) {
-                a->host_bufs[2 * k + 1].resize((size_t)n);
-                SR_CUDA(ctx, cudaMemcpyAsync(a->host_bufs[2 * k + 1].data(), dnull, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-                out->cols[k].nulls = a->host_bufs[2 * k + 1].data();
+                if (!a->host_bufs[2 * k + 1].reserve((size_t)n)) return sr_fail(ctx, SR_ERR_OUT_OF_MEMORY, "pinned host buffer of %zu bytes", (size_t)n);
+                SR_CUDA(ctx, cudaMemcpyAsync(a->host_bufs[2 * k + 1].p, dnull, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+                out->cols[k].nulls = (uint8_t*)a->host_bufs[2 * k + 1].p;
             }
         }
     }
@@ -870,8 +871,7 @@ int32_t sr_xchg_partition(sr_xchg* x, const sr_chunk_view* in, sr_chunk_out* out
     SR_TRY(x->row_index.reserve(ctx, sizeof(uint32_t) * (size_t)n));
     srd::k_part_hash<<<tiles, srd::PART_BLOCK, 0, ctx->stream>>>(pc, n, nullptr, x->channel_ids.as<uint32_t>(), x->counts.as<uint32_t>(), tiles);
     SR_LAUNCH_CHECK(ctx);
-    srd::k_scan_counts<<<1, 1024, 0, ctx->stream>>>(x->counts.as<uint32_t>(), ncounts, x->offsets.as<uint64_t>(), ctx->dscratch);
-    SR_LAUNCH_CHECK(ctx);
+    SR_TRY(scan_counts(ctx, &x->scan_scratch, x->counts.as<uint32_t>(), ncounts, x->offsets.as<uint64_t>()));
     srd::k_part_scatter<<<tiles, srd::PART_BLOCK, 0, ctx->stream>>>(x->channel_ids.as<uint32_t>(), n, nch, x->offsets.as<uint64_t>(), tiles,
                                                                    x->row_index.as<uint32_t>());
     SR_LAUNCH_CHECK(ctx);

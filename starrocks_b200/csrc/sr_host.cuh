@@ -72,6 +72,48 @@ static int32_t sr_fail(sr_ctx* ctx, int32_t code, const char* fmt, ...) {
     } while (0)
 
 // grow-only device buffer
+// page-locked host buffer for results handed back in host memory: a D2H copy into pageable memory is staged by the
+// driver at a few GB/s, into pinned memory it is one DMA at the link rate
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+    PinnedBuf(PinnedBuf&& o) noexcept : p(o.p), cap(o.cap) {
+        o.p = nullptr;
+        o.cap = 0;
+    }
+    PinnedBuf& operator=(PinnedBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p;
+            cap = o.cap;
+            o.p = nullptr;
+            o.cap = 0;
+        }
+        return *this;
+    }
+    ~PinnedBuf() { release(); }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    bool reserve(size_t bytes) {
+        if (bytes <= cap) return true;
+        release();
+        const size_t ncap = (std::max<size_t>(bytes, 4096) + 4095) & ~(size_t)4095;
+        if (cudaHostAlloc(&p, ncap, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return false;
+        }
+        cap = ncap;
+        return true;
+    }
+};
+
 struct DevBuf {
     sr_ctx* ctx = nullptr;
     void* p = nullptr;

@@ -261,6 +261,7 @@ struct BuildCol {
 struct ProberState {
     Staged staged;
     DevBuf heads, block_counts, block_offsets, probe_index, build_index;
+    ScanScratch scan_scratch;
     std::vector<DevBuf> out_bufs;
     int64_t last_count = 0;
 };
@@ -532,8 +533,7 @@ static int32_t join_probe(sr_join* j, int32_t prober_id, const sr_chunk_view* pr
         srd::k_probe_count<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, kc, j->desc.join_type, n, ps.heads.as<uint32_t>(),
                                                                         ps.block_counts.as<uint32_t>());
         SR_LAUNCH_CHECK(ctx);
-        srd::k_scan_counts<<<1, 1024, 0, ctx->stream>>>(ps.block_counts.as<uint32_t>(), blocks, ps.block_offsets.as<uint64_t>(), ctx->dscratch);
-        SR_LAUNCH_CHECK(ctx);
+        SR_TRY(scan_counts(ctx, &ps.scan_scratch, ps.block_counts.as<uint32_t>(), blocks, ps.block_offsets.as<uint64_t>()));
         SR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->dscratch, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
         SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         total = (int64_t)ctx->pinned[0];
