@@ -222,6 +222,16 @@ __device__ __forceinline__ void compact_rows(const void* __restrict__ src, void*
     for (int r = 0; r < SCANW_ROWS; r++)
         if ((m >> r) & 1u) d[q++] = s[r];
 }
+// dense tile, 4-byte column: the lane's 8 consecutive values by two 128-bit loads instead of up to 8 scalar ones
+__device__ __forceinline__ void compact_rows_vec32(const void* __restrict__ src, void* __restrict__ dst, int64_t base, uint32_t m, uint64_t out_pos) {
+    const int4 a = ldg_stream_v4((const uint32_t*)src + base), b = ldg_stream_v4((const uint32_t*)src + base + 4);
+    const uint32_t v[SCANW_ROWS] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w, (uint32_t)b.x, (uint32_t)b.y, (uint32_t)b.z, (uint32_t)b.w};
+    uint32_t* d = (uint32_t*)dst + out_pos;
+    uint32_t q = 0;
+#pragma unroll
+    for (int r = 0; r < SCANW_ROWS; r++)
+        if ((m >> r) & 1u) d[q++] = v[r];
+}
 
 __global__ void __launch_bounds__(SCANW_BLOCK) k_scan_compact(const uint8_t* __restrict__ mask_bits, const uint32_t* __restrict__ local_excl,
                                                                const uint64_t* __restrict__ block_offsets, CompactArgs args, int64_t n) {
@@ -232,9 +242,12 @@ __global__ void __launch_bounds__(SCANW_BLOCK) k_scan_compact(const uint8_t* __r
         const uint32_t m = mask_bits[tile * 32 + lane];
         const uint32_t cnt = __popc(m);
         const uint32_t incl = warp_incl_scan(cnt);
-        if (__shfl_sync(SR_FULL_MASK, incl, 31) == 0) continue;
+        const uint32_t tile_total = __shfl_sync(SR_FULL_MASK, incl, 31);
+        if (tile_total == 0) continue;
         const int64_t base = tile * SCANW_TILE + (int64_t)lane * SCANW_ROWS;
         const uint64_t out_pos = block_offsets[tile >> 10] + local_excl[tile] + (incl - cnt);
+        // a tile where a quarter of the rows survive touches nearly every sector anyway: vector loads (warp-uniform)
+        const bool dense = tile_total >= SCANW_TILE / 4 && (tile + 1) * SCANW_TILE <= n;
         if (cnt == 0) continue;
 #pragma unroll 1
         for (int c = 0; c < args.n; c++) {
@@ -247,7 +260,10 @@ __global__ void __launch_bounds__(SCANW_BLOCK) k_scan_compact(const uint8_t* __r
                 compact_rows<uint16_t>(col.src, col.dst, base, m, out_pos);
                 break;
             case 4:
-                compact_rows<uint32_t>(col.src, col.dst, base, m, out_pos);
+                if (dense && (((uintptr_t)col.src) & 15) == 0)
+                    compact_rows_vec32(col.src, col.dst, base, m, out_pos);
+                else
+                    compact_rows<uint32_t>(col.src, col.dst, base, m, out_pos);
                 break;
             case 8:
                 compact_rows<uint64_t>(col.src, col.dst, base, m, out_pos);

@@ -701,6 +701,40 @@ def test_xchg_partition_parity(gpu, ctx, oracle, hash_fn, reduce_op, nch, n):
         x.close()
 
 
+def test_large_batches_take_the_two_level_scan(gpu, ctx, oracle):
+    # 5 M-row probe (19.5 K block counts) and a 37-channel partition of 3 M rows (> 16 K tile x channel counts): the
+    # exclusive scans behind the ordered outputs switch from the single-block walk to the two-level form
+    rng = np.random.default_rng(41)
+    n = 5_000_000
+    bkeys = rng.integers(0, 50_000, 60_000, dtype=np.int32)                # duplicates on the build side
+    build = Chunk([(10, bkeys, None), (11, np.arange(60_000, dtype=np.int32), None)])
+    probe = Chunk([(0, rng.integers(0, 100_000, n, dtype=np.int32), None), (1, np.arange(n, dtype=np.int32), None)])
+    d = abi.make_join_desc(abi.JOIN_INNER, [10], [0], [abi.TYPE_INT], build_out=[11], probe_out=[1])
+    gj, oj = gpu.Join(ctx, d), oracle.Join(d)
+    x = gpu.Xchg(ctx, abi.make_part_desc([0], 37))
+    try:
+        gj.append_build(build)
+        gj.build_finish()
+        oj.append_build(build)
+        oj.build()
+        out = gj.probe(probe)
+        pi, bi = oj.probe_all(probe)
+        assert out.num_rows == len(pi)
+        gpi, gbi = gj.probe_indexes(out.num_rows)
+        assert np.array_equal(gpi, pi)                                         # probe order kept
+        pack = lambda p, b: np.sort((p.astype(np.uint64) << np.uint64(32)) | b.astype(np.uint64))   # noqa: E731
+        assert np.array_equal(pack(gpi, gbi), pack(pi, bi))                    # same pairs (order inside a duplicate chain is free)
+        part = Chunk([(0, rng.integers(-10**6, 10**6, 3_000_000, dtype=np.int32), None)])
+        ohv, och, ori, ost = oracle.hash_partition(abi.make_part_desc([0], 37), part)
+        pout, offs = x.partition(part)
+        assert offs.tolist() == ost.tolist()
+        got = gpu.chunk_out_to_host(ctx, pout)
+        assert np.array_equal(got[0][2], part._keep[0][0][ori])
+    finally:
+        gj.close()
+        x.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # loud failures (no silent fallback)
 # ---------------------------------------------------------------------------------------------
