@@ -18,6 +18,8 @@
 //    atomicCAS on the key word; the multiplicative JoinKeyHash picks the start slot.
 #pragma once
 
+#include <cub/device/device_radix_sort.cuh> // stable (bucket, row) sort for the deterministic-chain pass of the build (cold path)
+
 #include "sr_scan.cuh"
 
 namespace srd {
@@ -152,6 +154,45 @@ __global__ void __launch_bounds__(256) k_join_build_hash(const long long* __rest
         const uint32_t old = atomicExch(&first[s], (uint32_t)i);
         next[i] = old;
         if (old != 0) *has_dup = 1;
+    }
+}
+
+// ---- deterministic chains -------------------------------------------------------------------------------------
+// The parallel build links duplicate keys in arrival order.  The reference builds sequentially
+// (`next[i] = first[b]; first[b] = i`, join_hash_map_method.hpp:37-86), so a chain lists its rows by DESCENDING
+// build index and that is the order in which a probe row's matches are emitted.  When duplicates exist the chains are
+// rebuilt to that order: bucket id per build row -> stable radix sort of (bucket, row) -> predecessor links.
+__global__ void __launch_bounds__(256) k_join_bucket_ids(const long long* __restrict__ keys, const uint8_t* __restrict__ knulls, int64_t n_plus1, int32_t method,
+                                                          int64_t min_value, const unsigned long long* __restrict__ hkeys, uint32_t hmask, uint32_t hlog,
+                                                          uint32_t invalid, uint32_t* __restrict__ bucket, uint32_t* __restrict__ row) {
+    for (int64_t i = 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_plus1; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t b = invalid;
+        if (!(knulls && knulls[i])) {
+            const int64_t key = keys[i];
+            if (method == SR_JOIN_METHOD_LINEAR_CHAINED) {
+                if (key == SR_HKEY_EMPTY) {
+                    b = hmask + 1;
+                } else {
+                    b = hash_slot(key, hlog);
+                    while ((int64_t)hkeys[b] != key) b = (b + 1) & hmask; // the key was inserted by the build pass
+                }
+            } else {
+                b = (uint32_t)(uint64_t)(key - min_value);
+            }
+        }
+        bucket[i - 1] = b;
+        row[i - 1] = (uint32_t)i;
+    }
+}
+// sorted by (bucket, row): a row's predecessor in its bucket is its `next`, the last row of a bucket is the head
+__global__ void __launch_bounds__(256) k_join_relink(const uint32_t* __restrict__ bucket, const uint32_t* __restrict__ row, int64_t n, uint32_t invalid,
+                                                      uint32_t* __restrict__ first, uint32_t* __restrict__ next) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = bucket[p];
+        if (b == invalid) continue;
+        const uint32_t i = row[p];
+        next[i] = (p > 0 && bucket[p - 1] == b) ? row[p - 1] : 0u;
+        if (p + 1 == n || bucket[p + 1] != b) first[b] = i;
     }
 }
 
@@ -496,6 +537,32 @@ static int32_t join_finish(sr_join* j) {
     SR_CUDA(ctx, cudaMemcpyAsync(&hd, has_dup_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     j->has_dup = hd;
+    const int64_t rows = j->rows;
+    if (hd && rows > 0) {
+        // duplicate build keys: put every chain into the reference's order (descending build index)
+        const uint64_t nb = (uint64_t)j->bucket_size;
+        if (nb >= 0xFFFFFFFFull) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "join table of %llu buckets with duplicate keys", (unsigned long long)nb);
+        const uint32_t invalid = (uint32_t)nb; // sorts after every real bucket
+        int bits = 1;
+        while ((1ull << bits) <= nb) bits++;
+        DevBuf b_in, b_out, r_in, r_out, tmp;
+        SR_TRY(b_in.reserve(ctx, sizeof(uint32_t) * (size_t)rows));
+        SR_TRY(b_out.reserve(ctx, sizeof(uint32_t) * (size_t)rows));
+        SR_TRY(r_in.reserve(ctx, sizeof(uint32_t) * (size_t)rows));
+        SR_TRY(r_out.reserve(ctx, sizeof(uint32_t) * (size_t)rows));
+        srd::k_join_bucket_ids<<<grid, 256, 0, ctx->stream>>>(j->keys.as<long long>(), any_nullable ? j->knulls.as<uint8_t>() : nullptr, n1, j->method, j->min_value,
+                                                             j->hkeys.as<unsigned long long>(), j->hmask, j->hlog, invalid, b_in.as<uint32_t>(), r_in.as<uint32_t>());
+        SR_LAUNCH_CHECK(ctx);
+        size_t tmp_bytes = 0;
+        SR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, b_in.as<uint32_t>(), b_out.as<uint32_t>(), r_in.as<uint32_t>(), r_out.as<uint32_t>(),
+                                                     (int)rows, 0, bits, ctx->stream));
+        SR_TRY(tmp.reserve(ctx, std::max<size_t>(tmp_bytes, 16)));
+        SR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, b_in.as<uint32_t>(), b_out.as<uint32_t>(), r_in.as<uint32_t>(), r_out.as<uint32_t>(),
+                                                     (int)rows, 0, bits, ctx->stream)); // LSD radix sort: stable, rows stay ascending inside a bucket
+        srd::k_join_relink<<<grid, 256, 0, ctx->stream>>>(b_out.as<uint32_t>(), r_out.as<uint32_t>(), rows, invalid, j->first.as<uint32_t>(), j->next.as<uint32_t>());
+        SR_LAUNCH_CHECK(ctx);
+        SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the scratch buffers go out of scope
+    }
     j->built = true;
     return SR_OK;
 }
