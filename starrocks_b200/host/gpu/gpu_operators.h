@@ -20,6 +20,7 @@
 #pragma once
 
 #include <deque>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -448,6 +449,77 @@ private:
     GpuFragmentPtr _frag;
     size_t _batch_rows;
     ChunkBatch _batch;
+    bool _finished = false;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// ExchangeSinkOperator, HASH_PARTITIONED part (exchange_sink_operator.cpp:586-637 + Shuffler, shuffler.h:72-106):
+// hash the partition columns (FNV + ReduceOp, or CRC32 + modulo for BUCKET_SHUFFLE), reorder the rows so that every
+// channel's rows are contiguous and in input order, hand each channel's slice to its sender.  The transport itself
+// (brpc to another BE, NCCL all-to-all between the GPUs of one box) is the caller's ChannelSender.
+// ------------------------------------------------------------------------------------------------------------
+class GpuExchangeSinkOperator final : public Operator {
+public:
+    // sender(channel, chunk): called once per non-empty channel and flushed batch, rows in input order
+    using ChannelSender = std::function<Status(int32_t channel, const ChunkPtr& chunk)>;
+    GpuExchangeSinkOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, sr_ctx* ctx, const sr_part_desc& desc, ChannelSender sender,
+                            size_t batch_rows = 1 << 22)
+            : Operator(f, id, "gpu_exchange_sink", plan_node_id, false, seq), _ctx(ctx), _desc(desc), _sender(std::move(sender)), _batch_rows(batch_rows) {}
+    ~GpuExchangeSinkOperator() override {
+        if (_xchg) sr_xchg_destroy(_xchg);
+    }
+    Status prepare(RuntimeState* state) override {
+        _xchg = sr_xchg_create(_ctx, &_desc);
+        return _xchg ? Status::OK() : sr_to_status(_ctx, sr_last_error_code(_ctx));
+    }
+    bool has_output() const override { return false; }
+    bool need_input() const override { return !_finished; }
+    bool is_finished() const override { return _finished; }
+    StatusOr<ChunkPtr> pull_chunk(RuntimeState*) override { return Status::InternalError("pull_chunk on a sink"); }
+    Status push_chunk(RuntimeState* state, const ChunkPtr& chunk) override {
+        _batch.append(*chunk);
+        if (_batch.rows() >= _batch_rows) RETURN_IF_ERROR(_flush());
+        return Status::OK();
+    }
+    Status set_finishing(RuntimeState* state) override {
+        if (_finished) return Status::OK();
+        RETURN_IF_ERROR(_flush());
+        _finished = true;
+        return Status::OK();
+    }
+    int64_t rows_sent(int32_t channel) const { return _rows_sent[channel]; }
+
+private:
+    Status _flush() {
+        if (_batch.empty()) return Status::OK();
+        sr_chunk_view v = _batch.view();
+        sr_chunk_out out;
+        std::vector<int64_t> offs(_desc.num_channels + 1, 0);
+        RETURN_IF_SR_ERROR(_ctx, sr_xchg_partition(_xchg, &v, &out, offs.data()));
+        _rows_sent.resize(_desc.num_channels, 0);
+        // the partitioned columns come back as device buffers: slice them per channel into host chunks
+        std::deque<ChunkPtr> whole;
+        RETURN_IF_ERROR(slice_out_to_chunks(_ctx, out, (int)std::max<int64_t>(out.num_rows, 1), &whole));
+        if (!whole.empty()) {
+            const ChunkPtr& all = whole.front();
+            for (int32_t c = 0; c < _desc.num_channels; c++) {
+                const int64_t lo = offs[c], hi = offs[c + 1];
+                if (hi <= lo) continue;
+                ChunkPtr part = all->slice((size_t)lo, (size_t)(hi - lo));
+                _rows_sent[c] += hi - lo;
+                RETURN_IF_ERROR(_sender(c, part));
+            }
+        }
+        _batch.clear();
+        return Status::OK();
+    }
+    sr_ctx* _ctx;
+    sr_part_desc _desc;
+    ChannelSender _sender;
+    size_t _batch_rows;
+    sr_xchg* _xchg = nullptr;
+    ChunkBatch _batch;
+    std::vector<int64_t> _rows_sent;
     bool _finished = false;
 };
 

@@ -295,6 +295,50 @@ int main(int argc, char** argv) {
                probe_driver.rows_moved());
     }
     int rc = 0;
+    {
+        // ---- HASH_PARTITIONED exchange sink: 8 channels on lo_custkey; every row must arrive once, on the channel
+        // ReduceOp(fnv_hash(key), 8) names (hash_util.hpp:127-134,242-244), in input order per channel ----
+        const int nch = 8;
+        std::vector<int32_t> rowid(n_fact);
+        for (size_t i = 0; i < n_fact; i++) rowid[i] = (int32_t)i;
+        auto whole = make_chunk({{LO_CUSTKEY, lo_cust}, {LO_REVENUE, rowid}});
+        sr_part_desc pd{};
+        pd.hash_fn = SR_HASH_FNV;
+        pd.reduce_op = SR_REDUCE_MULHI;
+        pd.num_channels = nch;
+        pd.num_part_slots = 1;
+        pd.part_slots[0] = LO_CUSTKEY;
+        std::vector<std::vector<ChunkPtr>> received(nch);
+        auto sink = std::make_shared<GpuExchangeSinkOperator>(nullptr, 11, 11, 0, ctx, pd, [&](int32_t ch, const ChunkPtr& c) {
+            received[ch].push_back(c);
+            return Status::OK();
+        }, (size_t)1 << 18);
+        CHECK_OK(sink->prepare(&state));
+        for (auto& c : split(whole, 4096)) CHECK_OK(sink->push_chunk(&state, c));
+        CHECK_OK(sink->set_finishing(&state));
+        size_t total = 0;
+        bool ok = true;
+        for (int ch = 0; ch < nch; ch++) {
+            int32_t last = -1;
+            for (auto& c : received[ch]) {
+                auto* k = (const int32_t*)c->get_column_by_slot_id(LO_CUSTKEY)->raw_data();
+                auto* id = (const int32_t*)c->get_column_by_slot_id(LO_REVENUE)->raw_data();
+                for (size_t i = 0; i < c->num_rows(); i++) {
+                    uint32_t h = 0x811C9DC5u; // FNV seed (HashUtil::FNV_SEED)
+                    for (int b = 0; b < 4; b++) h = (((uint32_t)k[i] >> (8 * b) & 0xFFu) ^ h) * 0x01000193u;
+                    const int32_t want = (int32_t)(((uint64_t)h * (uint64_t)nch) >> 32);
+                    ok = ok && want == ch && id[i] > last && lo_cust[id[i]] == k[i];
+                    last = id[i];
+                    total++;
+                }
+            }
+        }
+        if (!ok || total != n_fact) {
+            fprintf(stderr, "exchange sink: %zu of %zu rows arrived, placement/order %s\n", total, n_fact, ok ? "ok" : "WRONG");
+            rc = 1;
+        }
+        printf("exchange sink: %zu rows over %d channels, placement and per-channel order verified\n", total, nch);
+    }
     if (results[0] != expect) {
         fprintf(stderr, "per-operator pipeline differs from the checker (%zu vs %zu groups)\n", results[0].size(), expect.size());
         rc = 1;
