@@ -339,6 +339,47 @@ int32_t sr_join_key_hash(sr_ctx* ctx, const void* keys, int32_t key_type, int64_
                          uint32_t* buckets, int32_t mem);
 
 /* ---------------------------------------------------------------------------------------
+ * runtime filter: what HashJoinBuildOperator::set_finishing publishes to the scans of the probe side
+ * (hash_join_build_operator.cpp:100-215) -- min/max + has_null (MinMaxRuntimeFilter, be/src/runtime/runtime_filter.h:584)
+ * and a split-block bloom filter with the reference's exact layout and hashing (SimdBlockFilter, runtime_filter.h:79-240:
+ * 32-byte buckets of 8 words, bucket = hash & mask, bit i = (uint32(hash >> log_buckets) * SALT[i]) >> 27;
+ * hash = phmap_mix<8>(std::hash(value)), runtime_filter.h:1270-1276).  The directory bytes equal the reference's
+ * `_directory`, so a filter built here can be merged with / shipped to CPU BEs and vice versa.
+ * Integer-class single-column keys (width <= 8).
+ * ------------------------------------------------------------------------------------- */
+typedef struct sr_rf sr_rf;
+typedef struct sr_rf_info {
+    int64_t min_value, max_value; /* min > max: no non-NULL key was inserted */
+    int64_t num_inserted;         /* non-NULL keys */
+    int32_t has_null;             /* a NULL key was inserted (null-safe joins) */
+    int32_t log_num_buckets;      /* directory = 2^log_num_buckets buckets of 32 bytes; 0: no bloom part */
+    int32_t key_type;
+    int32_t reserved;
+} sr_rf_info;
+/* Build from key number `key_index` of a finished join build side.  with_bloom = 0 builds the min/max part only.
+ * insert_nulls != 0 records NULL build keys (has_null) -- the reference does so for null-safe equal joins. */
+sr_rf* sr_join_build_runtime_filter(sr_join* join, int32_t key_index, int32_t with_bloom, int32_t insert_nulls);
+/* Build from a column of a chunk (the general RuntimeFilterBuilder path); expected_rows sizes the bloom directory
+ * exactly like SimdBlockFilter::init(expected_rows). */
+sr_rf* sr_rf_create(sr_ctx* ctx, int32_t key_type, int64_t expected_rows, int32_t with_bloom);
+int32_t sr_rf_insert(sr_rf* rf, const sr_chunk_view* in, int32_t slot_id, int32_t insert_nulls);
+void sr_rf_destroy(sr_rf* rf);
+int32_t sr_rf_get_info(sr_rf* rf, sr_rf_info* info);
+/* bloom directory: copy out (bytes = 32 << log_num_buckets) / merge another filter in: OR of the directories
+ * (SimdBlockFilter::merge; `mem` says where `directory` lives; NULL when `other` has no bloom part) and union of
+ * min/max/has_null/num_inserted taken from `other` -- the wire-compatible parts of serialize / merge. */
+int32_t sr_rf_copy_directory(sr_rf* rf, void* dst, int64_t bytes, int32_t mem);
+int32_t sr_rf_merge_directory(sr_rf* rf, const void* directory, int64_t bytes, int32_t mem, const sr_rf_info* other);
+/* RuntimeFilter::evaluate on one column of a chunk: selection[i] = has_null for NULL rows, else min <= v <= max and
+ * bloom test.  merge_and != 0: rows already 0 in `selection` stay 0 (the merged-selection use of the probe collector). */
+int32_t sr_rf_evaluate(sr_rf* rf, const sr_chunk_view* in, int32_t slot_id, uint8_t* selection, int32_t sel_mem, int32_t merge_and);
+/* Attach the filter to a scan: rows of `probe_slot` that fail it are dropped by sr_scan_filter / sr_scan_evaluate after
+ * the conjuncts (the ScanOperator side of runtime filters, scan_operator.h:212-225).  At most SR_MAX_SCAN_RFS per scan;
+ * the filter must outlive the scan. */
+#define SR_MAX_SCAN_RFS 4
+int32_t sr_scan_add_runtime_filter(sr_scan* scan, sr_rf* rf, int32_t probe_slot);
+
+/* ---------------------------------------------------------------------------------------
  * hash aggregate.  One sr_agg is shared by the sink and source operators, like Aggregator
  * (be/src/exec/aggregator.h:253-637).
  *   push         <- AggregateBlockingSinkOperator::push_chunk: evaluate_groupby_exprs,
@@ -538,7 +579,8 @@ int32_t sr_gather(sr_ctx* ctx, const void* src, int32_t type, const uint32_t* in
 /* sizeof() of the ABI structs as compiled into the library, so a foreign-language binding can
  * verify its own struct layouts at load time.  which: 0 sr_col_view, 1 sr_chunk_view,
  * 2 sr_chunk_out, 3 sr_pred, 4 sr_expr, 5 sr_scan_desc, 6 sr_join_desc, 7 sr_join_info,
- * 8 sr_agg_fn, 9 sr_agg_desc, 10 sr_frag_join, 11 sr_fragment_desc, 12 sr_part_desc.
+ * 8 sr_agg_fn, 9 sr_agg_desc, 10 sr_frag_join, 11 sr_fragment_desc, 12 sr_part_desc, 13 sr_agg_state_array,
+ * 14 sr_fragment_plan, 15 sr_rf_info.
  * returns -1 for an unknown index. */
 int32_t sr_abi_sizeof(int32_t which);
 

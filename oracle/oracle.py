@@ -95,6 +95,16 @@ def lib():
         "orc_agg_merge": (i32, [vp, vp]),
         "orc_hash_partition": (i32, [vp, vp, vp, vp, vp, vp]),
         "orc_fragment_run": (i32, [vp, vp, i32, vp, vp]),
+        "orc_rf_create": (vp, [i32, i64, i32]),
+        "orc_rf_destroy": (None, [vp]),
+        "orc_rf_insert_hash": (None, [vp, C.c_uint64]),
+        "orc_rf_test_hash": (i32, [vp, C.c_uint64]),
+        "orc_rf_value_hash": (C.c_uint64, [i64]),
+        "orc_rf_insert": (i32, [vp, vp, i32, i32]),
+        "orc_rf_merge": (i32, [vp, vp]),
+        "orc_rf_evaluate": (i32, [vp, vp, i32, vp, i32]),
+        "orc_rf_get_info": (i32, [vp, vp]),
+        "orc_rf_directory": (vp, [vp, vp]),
         "orc_last_error": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
@@ -310,6 +320,53 @@ def hash_partition(part_desc, chunk):
     _check(lib().orc_hash_partition(C.byref(part_desc), chunk.ref(), _np_ptr(hv), _np_ptr(ch), _np_ptr(ri),
                                     _np_ptr(st)))
     return hv, ch, ri, st
+
+
+class RuntimeFilter:
+    """MinMaxRuntimeFilter + SimdBlockFilter restatement (orc_rf_*)"""
+
+    def __init__(self, key_type, expected_rows, with_bloom=True):
+        self.h = lib().orc_rf_create(key_type, expected_rows, 1 if with_bloom else 0)
+        if not self.h:
+            raise OracleError(lib().orc_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_rf_destroy(self.h)
+            self.h = None
+
+    def insert_hash(self, h):
+        lib().orc_rf_insert_hash(self.h, h)
+
+    def test_hash(self, h):
+        return bool(lib().orc_rf_test_hash(self.h, h))
+
+    def insert(self, chunk, slot, insert_nulls=False):
+        _check(lib().orc_rf_insert(self.h, chunk.ref(), slot, 1 if insert_nulls else 0))
+
+    def merge(self, other):
+        _check(lib().orc_rf_merge(self.h, other.h))
+
+    def evaluate(self, chunk, slot, selection=None):
+        sel = np.zeros(chunk.num_rows, dtype=np.uint8) if selection is None else np.ascontiguousarray(selection, dtype=np.uint8).copy()
+        _check(lib().orc_rf_evaluate(self.h, chunk.ref(), slot, _np_ptr(sel), 0 if selection is None else 1))
+        return sel
+
+    def info(self):
+        inf = abi.sr_rf_info()
+        _check(lib().orc_rf_get_info(self.h, C.byref(inf)))
+        return inf
+
+    def directory(self):
+        n = C.c_int64(0)
+        p = lib().orc_rf_directory(self.h, C.byref(n))
+        if n.value == 0:
+            return np.empty(0, dtype=np.uint32)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(n.value // 4,)).copy()
+
+
+def value_hash(v):
+    return int(lib().orc_rf_value_hash(int(v)))
 
 
 def fragment_run(scan_desc, joins, agg_desc, fact_chunk, num_threads=1):

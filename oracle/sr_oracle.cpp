@@ -1950,3 +1950,118 @@ extern "C" int32_t orc_fragment_run(const orc_fragment_desc* desc, const sr_chun
     if (rows_passed) *rows_passed = passed;
     return SR_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// runtime filter: min/max + has_null (MinMaxRuntimeFilter, runtime_filter.h:584-) and the split-block bloom filter
+// (SimdBlockFilter, runtime_filter.h:79-240; init runtime_filter.cpp:26-35; make_mask :114-123; SALT :58-59)
+// ---------------------------------------------------------------------------------------
+static const uint32_t RF_SALT[8] = {0x47b6137b, 0x44974d91, 0x8824ad5b, 0xa2b7289d, 0x705495c7, 0x2df1424b, 0x9efc4947, 0x5c6bfb31};
+
+struct orc_rf {
+    int32_t key_type = 0;
+    int32_t log_num_buckets = 0; // 0: no bloom part
+    uint64_t directory_mask = 0;
+    std::vector<uint32_t> directory; // 8 words per bucket
+    int64_t min_value = INT64_MAX, max_value = INT64_MIN;
+    int64_t num_inserted = 0;
+    bool has_null = false;
+};
+
+extern "C" orc_rf* orc_rf_create(int32_t key_type, int64_t expected_rows, int32_t with_bloom) {
+    if (type_width(key_type) == 0 || type_width(key_type) > 8 || is_float_class(key_type)) {
+        fail(SR_ERR_NOT_SUPPORTED, "runtime filter key type");
+        return nullptr;
+    }
+    auto* rf = new orc_rf();
+    rf->key_type = key_type;
+    if (with_bloom) { // SimdBlockFilter::init
+        const uint64_t nums = (uint64_t)std::max<int64_t>(1, expected_rows);
+        const int log_heap_space = (int)std::ceil(std::log2((double)nums));
+        rf->log_num_buckets = std::max(1, log_heap_space - 5);
+        rf->directory_mask = (1ull << std::min(63, rf->log_num_buckets)) - 1;
+        rf->directory.assign((size_t)8 << rf->log_num_buckets, 0u);
+    }
+    return rf;
+}
+extern "C" void orc_rf_destroy(orc_rf* rf) {
+    delete rf;
+}
+static inline void rf_make_mask(uint32_t key, uint32_t* masks) {
+    for (int i = 0; i < 8; i++) masks[i] = 1u << ((key * RF_SALT[i]) >> 27);
+}
+extern "C" void orc_rf_insert_hash(orc_rf* rf, uint64_t hash) {
+    if (rf->log_num_buckets == 0) return;
+    uint32_t masks[8];
+    rf_make_mask((uint32_t)(hash >> rf->log_num_buckets), masks);
+    uint32_t* b = rf->directory.data() + 8 * (hash & rf->directory_mask);
+    for (int i = 0; i < 8; i++) b[i] |= masks[i];
+}
+extern "C" int32_t orc_rf_test_hash(const orc_rf* rf, uint64_t hash) {
+    if (rf->log_num_buckets == 0) return 1;
+    uint32_t masks[8];
+    rf_make_mask((uint32_t)(hash >> rf->log_num_buckets), masks);
+    const uint32_t* b = rf->directory.data() + 8 * (hash & rf->directory_mask);
+    for (int i = 0; i < 8; i++)
+        if ((b[i] & masks[i]) == 0) return 0;
+    return 1;
+}
+// phmap_mix<8> (base/phmap/phmap_utils.h:86-95) over std::hash<integer> (identity on the value converted to size_t)
+extern "C" uint64_t orc_rf_value_hash(int64_t value) {
+    const unsigned __int128 p = (unsigned __int128)(uint64_t)value * 0xde5fb9d2630458e9ull;
+    return (uint64_t)(p >> 64) + (uint64_t)p;
+}
+extern "C" int32_t orc_rf_insert(orc_rf* rf, const sr_chunk_view* in, int32_t slot_id, int32_t insert_nulls) {
+    const sr_col_view* c = find_col(in, slot_id);
+    if (!c) return fail(SR_ERR_INVALID_ARGUMENT, "runtime filter slot not in chunk");
+    if (type_width(c->type) != type_width(rf->key_type) || is_float_class(c->type)) return fail(SR_ERR_INVALID_ARGUMENT, "runtime filter key type differs");
+    for (int64_t i = 0; i < in->num_rows; i++) {
+        if (c->nulls && c->nulls[i]) {
+            if (insert_nulls) rf->has_null = true;
+            continue;
+        }
+        const int64_t v = load_int(c->data, c->type, i);
+        rf->min_value = std::min(rf->min_value, v);
+        rf->max_value = std::max(rf->max_value, v);
+        rf->num_inserted++;
+        orc_rf_insert_hash(rf, orc_rf_value_hash(v));
+    }
+    return SR_OK;
+}
+extern "C" int32_t orc_rf_merge(orc_rf* rf, const orc_rf* other) {
+    if (rf->log_num_buckets != other->log_num_buckets) return fail(SR_ERR_INVALID_ARGUMENT, "bloom directories of different size");
+    for (size_t i = 0; i < rf->directory.size(); i++) rf->directory[i] |= other->directory[i];
+    rf->min_value = std::min(rf->min_value, other->min_value);
+    rf->max_value = std::max(rf->max_value, other->max_value);
+    rf->num_inserted += other->num_inserted;
+    rf->has_null = rf->has_null || other->has_null;
+    return SR_OK;
+}
+extern "C" int32_t orc_rf_evaluate(const orc_rf* rf, const sr_chunk_view* in, int32_t slot_id, uint8_t* selection, int32_t merge_and) {
+    const sr_col_view* c = find_col(in, slot_id);
+    if (!c) return fail(SR_ERR_INVALID_ARGUMENT, "runtime filter slot not in chunk");
+    for (int64_t i = 0; i < in->num_rows; i++) {
+        uint8_t pass;
+        if (c->nulls && c->nulls[i]) {
+            pass = rf->has_null ? 1 : 0;
+        } else {
+            const int64_t v = load_int(c->data, c->type, i);
+            pass = v >= rf->min_value && v <= rf->max_value && orc_rf_test_hash(rf, orc_rf_value_hash(v));
+        }
+        selection[i] = merge_and ? (uint8_t)(selection[i] && pass) : pass;
+    }
+    return SR_OK;
+}
+extern "C" int32_t orc_rf_get_info(const orc_rf* rf, sr_rf_info* info) {
+    info->min_value = rf->min_value;
+    info->max_value = rf->max_value;
+    info->num_inserted = rf->num_inserted;
+    info->has_null = rf->has_null ? 1 : 0;
+    info->log_num_buckets = rf->log_num_buckets;
+    info->key_type = rf->key_type;
+    info->reserved = 0;
+    return SR_OK;
+}
+extern "C" const void* orc_rf_directory(const orc_rf* rf, int64_t* bytes) {
+    *bytes = (int64_t)rf->directory.size() * 4;
+    return rf->directory.data();
+}

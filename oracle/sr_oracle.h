@@ -174,6 +174,20 @@ typedef struct orc_fragment_desc {
 int32_t orc_fragment_run(const orc_fragment_desc* desc, const sr_chunk_view* fact, int32_t num_threads,
                          orc_agg* result, int64_t* rows_passed);
 
+/* ---- runtime filter: MinMaxRuntimeFilter + SimdBlockFilter (be/src/runtime/runtime_filter.h:58-59,79-240,584-,
+ * 1270-1290; runtime_filter.cpp:26-35,114-123).  Pinned by be/test/runtime/runtime_filter_core_test.cpp:49-123. */
+typedef struct orc_rf orc_rf;
+orc_rf* orc_rf_create(int32_t key_type, int64_t expected_rows, int32_t with_bloom);
+void orc_rf_destroy(orc_rf* rf);
+void orc_rf_insert_hash(orc_rf* rf, uint64_t hash);    /* SimdBlockFilter::insert_hash */
+int32_t orc_rf_test_hash(const orc_rf* rf, uint64_t hash); /* SimdBlockFilter::test_hash */
+uint64_t orc_rf_value_hash(int64_t value);             /* phmap_mix<8>(std::hash<T>(value)) for integer-class T */
+int32_t orc_rf_insert(orc_rf* rf, const sr_chunk_view* in, int32_t slot_id, int32_t insert_nulls);
+int32_t orc_rf_merge(orc_rf* rf, const orc_rf* other); /* SimdBlockFilter::merge + min/max/has_null union */
+int32_t orc_rf_evaluate(const orc_rf* rf, const sr_chunk_view* in, int32_t slot_id, uint8_t* selection, int32_t merge_and);
+int32_t orc_rf_get_info(const orc_rf* rf, sr_rf_info* info);
+const void* orc_rf_directory(const orc_rf* rf, int64_t* bytes);
+
 const char* orc_last_error(void);
 
 #ifdef __cplusplus

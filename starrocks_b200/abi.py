@@ -159,6 +159,11 @@ class sr_part_desc(C.Structure):
                 ("num_part_slots", C.c_int32), ("part_slots", C.c_int32 * SR_MAX_PART_KEYS)]
 
 
+class sr_rf_info(C.Structure):
+    _fields_ = [("min_value", C.c_int64), ("max_value", C.c_int64), ("num_inserted", C.c_int64), ("has_null", C.c_int32),
+                ("log_num_buckets", C.c_int32), ("key_type", C.c_int32), ("reserved", C.c_int32)]
+
+
 STATE_REDUCE_SUM, STATE_REDUCE_MIN, STATE_REDUCE_MAX = 0, 1, 2
 
 
@@ -207,6 +212,10 @@ class Chunk:
 
     def ref(self):
         return C.byref(self.view)
+
+    def columns(self):
+        """-> [(slot_id, data, nulls_or_None)] as passed to the constructor"""
+        return [(s, d, nl) for s, (d, nl) in zip(self.slots, self._keep)]
 
 
 def _ptr_of(x):

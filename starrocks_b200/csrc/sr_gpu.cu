@@ -403,6 +403,174 @@ int32_t sr_join_probe_indexes(sr_join* join, int32_t prober_id, const uint32_t**
     return SR_OK;
 }
 
+// ------------------------------------------------------------------ runtime filter
+static int32_t rf_insert_dcol(sr_rf* rf, const srd::DCol& col, int64_t n, int32_t insert_nulls) {
+    sr_ctx* ctx = rf->ctx;
+    if (srd::type_width(col.type) > 8 || srd::is_float_class(col.type)) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "runtime filter on column type %d", col.type);
+    if (n <= 0) return SR_OK;
+    rf->stats_valid = false;
+    srd::k_rf_insert_col<<<std::min(grid_for(n, 256), ctx->num_sms * 8), 256, 0, ctx->stream>>>(col, n, rf->log_num_buckets ? rf->dir.as<uint32_t>() : nullptr, rf->dir_mask,
+                                                                                                 rf->log_num_buckets, insert_nulls ? 1 : 0, rf->stats.as<long long>());
+    SR_LAUNCH_CHECK(ctx);
+    return SR_OK;
+}
+
+sr_rf* sr_rf_create(sr_ctx* ctx, int32_t key_type, int64_t expected_rows, int32_t with_bloom) {
+    if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);
+    sr_rf* rf = new sr_rf();
+    if (rf_init(rf, ctx, key_type, expected_rows, with_bloom) != SR_OK) {
+        delete rf;
+        return nullptr;
+    }
+    return rf;
+}
+
+void sr_rf_destroy(sr_rf* rf) {
+    if (!rf) return;
+    cudaSetDevice(rf->ctx->device);
+    cudaStreamSynchronize(rf->ctx->stream);
+    delete rf;
+}
+
+int32_t sr_rf_insert(sr_rf* rf, const sr_chunk_view* in, int32_t slot_id, int32_t insert_nulls) {
+    if (!rf || !in) return SR_ERR_INVALID_ARGUMENT;
+    sr_ctx* ctx = rf->ctx;
+    SR_BIND(ctx);
+    const std::vector<int32_t> only{slot_id};
+    SR_TRY(rf->staged.stage(ctx, in, &only));
+    const int c = rf->staged.find(slot_id);
+    if (c < 0) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "chunk misses slot %d", slot_id);
+    SR_TRY(rf_insert_dcol(rf, rf->staged.cols[c], in->num_rows, insert_nulls));
+    if (in->mem != SR_MEM_DEVICE) SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // caller may free host buffers
+    return SR_OK;
+}
+
+sr_rf* sr_join_build_runtime_filter(sr_join* join, int32_t key_index, int32_t with_bloom, int32_t insert_nulls) {
+    if (!join) return nullptr;
+    sr_ctx* ctx = join->ctx;
+    cudaSetDevice(ctx->device);
+    if (!join->built) {
+        sr_fail(ctx, SR_ERR_STATE, "build_runtime_filter before build_finish");
+        return nullptr;
+    }
+    if (key_index < 0 || key_index >= join->desc.num_keys) {
+        sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "key_index %d", key_index);
+        return nullptr;
+    }
+    sr_rf* rf = new sr_rf();
+    // the directory is sized by the hash table's row count (hash_join_build_operator.cpp:140: ht_row_count)
+    if (rf_init(rf, ctx, join->desc.key_types[key_index], join->rows, with_bloom) != SR_OK) {
+        delete rf;
+        return nullptr;
+    }
+    const BuildCol* bc = join->find_col(join->desc.build_key_slots[key_index]);
+    if (bc && join->rows > 0) { // build columns keep the sentinel in row 0
+        srd::DCol col;
+        col.data = (const uint8_t*)bc->data.p + bc->width;
+        col.nulls = bc->nullable ? bc->nulls.as<uint8_t>() + 1 : nullptr;
+        col.type = bc->type;
+        col.width = bc->width;
+        if (rf_insert_dcol(rf, col, join->rows, insert_nulls) != SR_OK) {
+            delete rf;
+            return nullptr;
+        }
+    }
+    return rf;
+}
+
+int32_t sr_rf_get_info(sr_rf* rf, sr_rf_info* info) {
+    if (!rf || !info) return SR_ERR_INVALID_ARGUMENT;
+    SR_BIND(rf->ctx);
+    SR_TRY(rf_read_stats(rf));
+    info->min_value = rf->hstats[0];
+    info->max_value = rf->hstats[1];
+    info->num_inserted = rf->hstats[2];
+    info->has_null = rf->hstats[3] != 0;
+    info->log_num_buckets = rf->log_num_buckets;
+    info->key_type = rf->key_type;
+    info->reserved = 0;
+    return SR_OK;
+}
+
+int32_t sr_rf_copy_directory(sr_rf* rf, void* dst, int64_t bytes, int32_t mem) {
+    if (!rf || (!dst && bytes > 0)) return SR_ERR_INVALID_ARGUMENT;
+    sr_ctx* ctx = rf->ctx;
+    SR_BIND(ctx);
+    if (bytes != (int64_t)rf->dir_bytes()) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "directory is %zu bytes, caller passed %lld", rf->dir_bytes(), (long long)bytes);
+    SR_TRY(copy_out(ctx, dst, rf->dir.p, (size_t)bytes, mem));
+    SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SR_OK;
+}
+
+int32_t sr_rf_merge_directory(sr_rf* rf, const void* directory, int64_t bytes, int32_t mem, const sr_rf_info* other) {
+    if (!rf || !other) return SR_ERR_INVALID_ARGUMENT;
+    sr_ctx* ctx = rf->ctx;
+    SR_BIND(ctx);
+    if (other->log_num_buckets != rf->log_num_buckets) // SimdBlockFilter::merge DCHECKs equal sizes
+        return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "bloom directories of different size (2^%d vs 2^%d buckets)", rf->log_num_buckets, other->log_num_buckets);
+    if (bytes != (int64_t)rf->dir_bytes() || (bytes > 0 && !directory)) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "directory is %zu bytes, caller passed %lld", rf->dir_bytes(), (long long)bytes);
+    rf->stats_valid = false;
+    if (bytes > 0) {
+        DevBuf tmp;
+        const uint32_t* src = (const uint32_t*)directory;
+        if (mem != SR_MEM_DEVICE) {
+            SR_TRY(tmp.reserve(ctx, (size_t)bytes));
+            SR_CUDA(ctx, cudaMemcpyAsync(tmp.p, directory, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+            src = tmp.as<uint32_t>();
+        }
+        const int64_t words = bytes / 4;
+        srd::k_or_u32<<<std::min(grid_for(words, 256), ctx->num_sms * 8), 256, 0, ctx->stream>>>(rf->dir.as<uint32_t>(), src, words);
+        SR_LAUNCH_CHECK(ctx);
+        if (mem != SR_MEM_DEVICE) SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // tmp is freed on return
+    }
+    srd::k_rf_merge_stats<<<1, 1, 0, ctx->stream>>>(rf->stats.as<long long>(), other->min_value, other->max_value, other->num_inserted, other->has_null ? 1 : 0);
+    SR_LAUNCH_CHECK(ctx);
+    return SR_OK;
+}
+
+int32_t sr_rf_evaluate(sr_rf* rf, const sr_chunk_view* in, int32_t slot_id, uint8_t* selection, int32_t sel_mem, int32_t merge_and) {
+    if (!rf || !in || (!selection && in->num_rows > 0)) return SR_ERR_INVALID_ARGUMENT;
+    sr_ctx* ctx = rf->ctx;
+    SR_BIND(ctx);
+    const int64_t n = in->num_rows;
+    if (n <= 0) return SR_OK;
+    const std::vector<int32_t> only{slot_id};
+    SR_TRY(rf->staged.stage(ctx, in, &only));
+    const int c = rf->staged.find(slot_id);
+    if (c < 0) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "chunk misses slot %d", slot_id);
+    const srd::DCol& col = rf->staged.cols[c];
+    if (srd::type_width(col.type) > 8 || srd::is_float_class(col.type)) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "runtime filter on column type %d", col.type);
+    srd::RfDev d;
+    SR_TRY(rf_device_desc(rf, &d));
+    DevBuf tmp;
+    uint8_t* dsel = selection;
+    if (sel_mem != SR_MEM_DEVICE) {
+        SR_TRY(tmp.reserve(ctx, (size_t)n));
+        if (merge_and) SR_CUDA(ctx, cudaMemcpyAsync(tmp.p, selection, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        dsel = tmp.as<uint8_t>();
+    }
+    srd::k_rf_evaluate<<<std::min(grid_for(n, 256), ctx->num_sms * 8), 256, 0, ctx->stream>>>(d, col, n, dsel, merge_and ? 1 : 0);
+    SR_LAUNCH_CHECK(ctx);
+    if (sel_mem != SR_MEM_DEVICE) {
+        SR_CUDA(ctx, cudaMemcpyAsync(selection, dsel, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else if (in->mem != SR_MEM_DEVICE) {
+        SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SR_OK;
+}
+
+int32_t sr_scan_add_runtime_filter(sr_scan* scan, sr_rf* rf, int32_t probe_slot) {
+    if (!scan || !rf) return SR_ERR_INVALID_ARGUMENT;
+    sr_ctx* ctx = scan->ctx;
+    if (rf->ctx != ctx) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "runtime filter belongs to another context");
+    if (scan->rfs.size() >= SR_MAX_SCAN_RFS) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "more than %d runtime filters on one scan", SR_MAX_SCAN_RFS);
+    scan->rfs.emplace_back(rf, probe_slot);
+    scan->compiled = false; // the probe column joins the value table at the next batch
+    return SR_OK;
+}
+
 int32_t sr_join_key_hash(sr_ctx* ctx, const void* keys, int32_t key_type, int64_t n, uint32_t log_bucket_size, uint32_t* buckets, int32_t mem) {
     SR_BIND(ctx);
     const int w = srd::type_width(key_type);
@@ -953,6 +1121,8 @@ int32_t sr_abi_sizeof(int32_t which) {
         return (int32_t)sizeof(sr_agg_state_array);
     case 14:
         return (int32_t)sizeof(sr_fragment_plan);
+    case 15:
+        return (int32_t)sizeof(sr_rf_info);
     default:
         return -1;
     }

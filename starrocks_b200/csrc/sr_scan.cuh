@@ -7,7 +7,7 @@
 // reference's Filter), block counts + one scan, then a scatter that keeps input order.
 #pragma once
 
-#include "sr_host.cuh"
+#include "sr_rf.cuh"
 
 namespace srd {
 
@@ -129,9 +129,13 @@ struct ScanTests {
     int32_t num_tests; // 0: generic evaluation
     int32_t vec0;      // the first column may be read with 128-bit loads (16-byte aligned)
     RangeTest t[SR_MAX_SCAN_RANGE_TESTS];
+    // runtime filters attached to the scan (sr_scan_add_runtime_filter): applied to the rows the conjuncts keep
+    int32_t num_rfs;
+    int32_t pad;
+    RfDev rfs[SR_MAX_SCAN_RFS];
 };
 
-template <bool FAST>
+template <bool FAST, bool RF>
 __global__ void __launch_bounds__(SCANW_BLOCK) k_scan_mask(const ScanProg* __restrict__ prog, const __grid_constant__ ScanTests st, const __grid_constant__ VTab vt,
                                                             int64_t n, uint8_t* __restrict__ mask_bits, uint32_t* __restrict__ tile_counts,
                                                             uint8_t* __restrict__ sel_bytes) {
@@ -180,6 +184,22 @@ __global__ void __launch_bounds__(SCANW_BLOCK) k_scan_mask(const ScanProg* __res
                     pass = !nul && bits != 0;
                 }
                 if (!pass) m &= ~(1u << r);
+            }
+        }
+        if (RF) {
+            // RuntimeFilterProbeCollector::evaluate: every filter ANDs into the selection; a NULL probe value passes
+            // only a filter that saw a NULL build key.  Only surviving rows pay the bucket read (one 32-byte sector).
+#pragma unroll 1
+            for (int f = 0; f < st.num_rfs; f++) {
+                const RfDev& rf = st.rfs[f];
+#pragma unroll 1
+                for (int r = 0; r < SCANW_ROWS; r++) {
+                    if (!((m >> r) & 1u)) continue;
+                    int64_t bits;
+                    const bool nul = ChunkLoader{vt, base + r}.load(rf.value_id, bits);
+                    const bool pass = nul ? rf.has_null != 0 : rf_test(rf, bits);
+                    if (!pass) m &= ~(1u << r);
+                }
             }
         }
         if (mask_bits) mask_bits[tile * 32 + lane] = (uint8_t)m;
@@ -406,6 +426,8 @@ struct sr_scan {
     // warp-tile scan (k_scan_mask / k_scan_lvl1 / k_scan_compact)
     DevBuf mask_bits, tile_counts, local_excl, block_sums, block_offsets;
     srd::ScanTests tests; // range form of the conjuncts (num_tests == 0: generic evaluation)
+    std::vector<std::pair<sr_rf*, int32_t>> rfs; // runtime filters (filter, probe slot)
+    std::vector<int32_t> rf_value_ids;
     std::vector<DevBuf> out_bufs; // 2 per out slot
 };
 
@@ -453,6 +475,15 @@ static int32_t scan_compile(sr_scan* s) {
         }
         s->tests.num_tests = ok ? (int32_t)s->preds.size() : 0;
     }
+    s->rf_value_ids.clear();
+    for (auto& rf : s->rfs) {
+        const int32_t t = staged_slot_type(&s->staged, rf.second);
+        if (t == 0) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "runtime filter probes unknown slot %d", rf.second);
+        if (srd::type_width(t) > 8 || srd::is_float_class(t)) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "runtime filter on slot %d: integer-class columns only", rf.second);
+        const int id = s->reg.add(rf.second, t);
+        if (id >= SR_MAX_VALUES) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "too many distinct columns");
+        s->rf_value_ids.push_back(id);
+    }
     SR_TRY(s->prog.reserve(ctx, sizeof(srd::ScanProg)));
     SR_CUDA(ctx, cudaMemcpyAsync(s->prog.p, hp, sizeof(srd::ScanProg), cudaMemcpyHostToDevice, ctx->stream));
     SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // hostbuf goes out of scope
@@ -484,15 +515,27 @@ static int32_t scan_select(sr_scan* s, const sr_chunk_view* in, bool want_counts
     for (int t = 0; t < tests.num_tests; t++)
         if (vt.v[tests.t[t].value_id].nulls != nullptr) tests.num_tests = 0;
     tests.vec0 = tests.num_tests > 0 && (((uintptr_t)vt.v[tests.t[0].value_id].data) & 15) == 0 ? 1 : 0;
+    tests.num_rfs = (int32_t)s->rfs.size();
+    for (size_t f = 0; f < s->rfs.size(); f++) {
+        SR_TRY(rf_device_desc(s->rfs[f].first, &tests.rfs[f])); // reads min/max once the build side is complete
+        tests.rfs[f].value_id = s->rf_value_ids[f];
+    }
     if (n > 0) {
         const int grid = (int)std::min<int64_t>((tiles + srd::SCANW_BLOCK / 32 - 1) / (srd::SCANW_BLOCK / 32), (int64_t)ctx->num_sms * 8);
         uint8_t* mask = want_counts ? s->mask_bits.as<uint8_t>() : nullptr;
         uint32_t* counts = want_counts ? s->tile_counts.as<uint32_t>() : nullptr;
         uint8_t* bytes = want_counts ? nullptr : s->sel.as<uint8_t>();
-        if (tests.num_tests > 0)
-            srd::k_scan_mask<true><<<grid, srd::SCANW_BLOCK, 0, ctx->stream>>>((const srd::ScanProg*)s->prog.p, tests, vt, n, mask, counts, bytes);
-        else
-            srd::k_scan_mask<false><<<grid, srd::SCANW_BLOCK, 0, ctx->stream>>>((const srd::ScanProg*)s->prog.p, tests, vt, n, mask, counts, bytes);
+        const srd::ScanProg* prog = (const srd::ScanProg*)s->prog.p;
+        if (tests.num_rfs > 0) {
+            if (tests.num_tests > 0)
+                srd::k_scan_mask<true, true><<<grid, srd::SCANW_BLOCK, 0, ctx->stream>>>(prog, tests, vt, n, mask, counts, bytes);
+            else
+                srd::k_scan_mask<false, true><<<grid, srd::SCANW_BLOCK, 0, ctx->stream>>>(prog, tests, vt, n, mask, counts, bytes);
+        } else if (tests.num_tests > 0) {
+            srd::k_scan_mask<true, false><<<grid, srd::SCANW_BLOCK, 0, ctx->stream>>>(prog, tests, vt, n, mask, counts, bytes);
+        } else {
+            srd::k_scan_mask<false, false><<<grid, srd::SCANW_BLOCK, 0, ctx->stream>>>(prog, tests, vt, n, mask, counts, bytes);
+        }
         SR_LAUNCH_CHECK(ctx);
     }
     if (want_counts) {

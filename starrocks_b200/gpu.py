@@ -70,6 +70,15 @@ def lib():
         "sr_join_probe": (i32, [vp, i32, vp, vp]),
         "sr_join_probe_indexes": (i32, [vp, i32, vp, vp]),
         "sr_join_key_hash": (i32, [vp, vp, i32, i64, u32, vp, i32]),
+        "sr_join_build_runtime_filter": (vp, [vp, i32, i32, i32]),
+        "sr_rf_create": (vp, [vp, i32, i64, i32]),
+        "sr_rf_insert": (i32, [vp, vp, i32, i32]),
+        "sr_rf_destroy": (None, [vp]),
+        "sr_rf_get_info": (i32, [vp, vp]),
+        "sr_rf_copy_directory": (i32, [vp, vp, i64, i32]),
+        "sr_rf_merge_directory": (i32, [vp, vp, i64, i32, vp]),
+        "sr_rf_evaluate": (i32, [vp, vp, i32, vp, i32, i32]),
+        "sr_scan_add_runtime_filter": (i32, [vp, vp, i32]),
         "sr_agg_create": (vp, [vp, vp]),
         "sr_agg_destroy": (None, [vp]),
         "sr_agg_push": (i32, [vp, vp]),
@@ -116,6 +125,8 @@ EXPORTED_SYMBOLS = [
     "sr_agg_sink_finish", "sr_agg_num_groups", "sr_agg_pull", "sr_agg_merge", "sr_agg_dense_state", "sr_agg_reset", "sr_fragment_reset", "sr_fragment_get_plan", "sr_fragment_last_pass_ms",
     "sr_fragment_create",
     "sr_fragment_destroy", "sr_fragment_push", "sr_fragment_agg", "sr_fragment_rows_passed", "sr_xchg_create",
+    "sr_join_build_runtime_filter", "sr_rf_create", "sr_rf_insert", "sr_rf_destroy", "sr_rf_get_info", "sr_rf_copy_directory",
+    "sr_rf_merge_directory", "sr_rf_evaluate", "sr_scan_add_runtime_filter",
     "sr_xchg_destroy", "sr_xchg_partition", "sr_xchg_hash", "sr_gather", "sr_memcpy", "sr_abi_sizeof", "sr_bandwidth_probe", "sr_flush_l2",
 ]
 
@@ -231,6 +242,54 @@ class Scan:
         out = abi.sr_chunk_out()
         self.ctx.check(lib().sr_scan_filter(self.h, chunk.ref(), C.byref(out)))
         return out
+
+    def add_runtime_filter(self, rf, probe_slot):
+        self.ctx.check(lib().sr_scan_add_runtime_filter(self.h, rf.h, probe_slot))
+        self._rfs = getattr(self, "_rfs", []) + [rf]  # the filter must outlive the scan
+
+
+class RuntimeFilter:
+    """sr_rf: min/max + SimdBlockFilter-compatible bloom filter (include/sr_gpu_ops.h)"""
+
+    def __init__(self, ctx, key_type=None, expected_rows=0, with_bloom=True, handle=None):
+        self.ctx = ctx
+        self.h = handle if handle is not None else lib().sr_rf_create(ctx.h, key_type, expected_rows, 1 if with_bloom else 0)
+        if not self.h:
+            ctx.check(lib().sr_last_error_code(ctx.h) or -1)
+
+    @classmethod
+    def from_join(cls, join, key_index=0, with_bloom=True, insert_nulls=False):
+        h = lib().sr_join_build_runtime_filter(join.h, key_index, 1 if with_bloom else 0, 1 if insert_nulls else 0)
+        return cls(join.ctx, handle=h)
+
+    def close(self):
+        if self.h:
+            lib().sr_rf_destroy(self.h)
+            self.h = None
+
+    def insert(self, chunk, slot, insert_nulls=False):
+        self.ctx.check(lib().sr_rf_insert(self.h, chunk.ref(), slot, 1 if insert_nulls else 0))
+
+    def info(self):
+        inf = abi.sr_rf_info()
+        self.ctx.check(lib().sr_rf_get_info(self.h, C.byref(inf)))
+        return inf
+
+    def directory(self):
+        logb = self.info().log_num_buckets
+        out = np.zeros((8 << logb) if logb else 0, dtype=np.uint32)
+        self.ctx.check(lib().sr_rf_copy_directory(self.h, out.ctypes.data, out.nbytes, abi.MEM_HOST))
+        return out
+
+    def merge(self, directory, info):
+        """directory: uint32 array (host) of the other filter, info: its sr_rf_info"""
+        d = np.ascontiguousarray(directory, dtype=np.uint32)
+        self.ctx.check(lib().sr_rf_merge_directory(self.h, d.ctypes.data if d.size else None, d.nbytes, abi.MEM_HOST, C.byref(info)))
+
+    def evaluate(self, chunk, slot, selection=None):
+        sel = np.zeros(chunk.num_rows, dtype=np.uint8) if selection is None else np.ascontiguousarray(selection, dtype=np.uint8).copy()
+        self.ctx.check(lib().sr_rf_evaluate(self.h, chunk.ref(), slot, sel.ctypes.data, abi.MEM_HOST, 0 if selection is None else 1))
+        return sel
 
 
 class Join:

@@ -31,7 +31,8 @@ def test_ctypes_layouts_match_the_compiled_structs(gpu):
     L = gpu.lib()
     structs = [abi.sr_col_view, abi.sr_chunk_view, abi.sr_chunk_out, abi.sr_pred, abi.sr_expr, abi.sr_scan_desc,
                abi.sr_join_desc, abi.sr_join_info, abi.sr_agg_fn, abi.sr_agg_desc, abi.sr_frag_join,
-               abi.sr_fragment_desc, abi.sr_part_desc, abi.sr_agg_state_array, abi.sr_fragment_plan]
+               abi.sr_fragment_desc, abi.sr_part_desc, abi.sr_agg_state_array, abi.sr_fragment_plan,
+               abi.sr_rf_info]
     for k, st in enumerate(structs):
         assert L.sr_abi_sizeof(k) == C.sizeof(st), st.__name__
     assert L.sr_abi_sizeof(99) == -1

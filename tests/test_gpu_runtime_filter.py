@@ -1,0 +1,188 @@
+"""GPU parity tests for runtime filters: the CUDA min/max + split-block bloom filter against the CPU
+restatement of MinMaxRuntimeFilter / SimdBlockFilter (oracle/sr_oracle.cpp, pinned by the reference's own
+runtime_filter_core_test.cpp vectors in tests/test_oracle_golden.py).  Everything is integer/bit work: the bloom
+DIRECTORY BYTES, the info block and every selection byte must be identical.
+"""
+import numpy as np
+import pytest
+
+from starrocks_b200 import abi
+from starrocks_b200.abi import Chunk
+from tests.helpers import rand_nulls
+
+pytestmark = pytest.mark.gpu
+
+KEY_CASES = [
+    (np.int32, abi.TYPE_INT, -10**6, 10**6),
+    (np.int64, abi.TYPE_BIGINT, -2**62, 2**62),
+    (np.int16, abi.TYPE_SMALLINT, -30000, 30000),
+    (np.int8, abi.TYPE_TINYINT, -128, 128),
+    (np.int32, abi.TYPE_DATE, 700000, 740000),
+]
+
+
+def _same_info(a, b):
+    for f in ("min_value", "max_value", "num_inserted", "has_null", "log_num_buckets", "key_type"):
+        assert getattr(a, f) == getattr(b, f), f
+
+
+@pytest.mark.parametrize("dtype,typ,lo,hi", KEY_CASES)
+@pytest.mark.parametrize("n", [0, 1, 33, 1000, 100_003])
+@pytest.mark.parametrize("with_bloom", [True, False])
+def test_rf_insert_builds_the_reference_directory(gpu, ctx, oracle, dtype, typ, lo, hi, n, with_bloom):
+    rng = np.random.default_rng(5 + n)
+    keys = rng.integers(lo, hi, n).astype(dtype)
+    nulls = rand_nulls(rng, n, 0.1) if n > 1 else None
+    chunk = Chunk([(7, keys, nulls, typ)])
+    g = gpu.RuntimeFilter(ctx, typ, n, with_bloom)
+    o = oracle.RuntimeFilter(typ, n, with_bloom)
+    try:
+        # two inserts (chunks arrive one at a time on the build side); the second one records NULLs
+        g.insert(chunk, 7, insert_nulls=False)
+        o.insert(chunk, 7, insert_nulls=False)
+        _same_info(g.info(), o.info())
+        g.insert(chunk, 7, insert_nulls=True)
+        o.insert(chunk, 7, insert_nulls=True)
+        _same_info(g.info(), o.info())
+        assert np.array_equal(g.directory(), o.directory())
+        # evaluate on a probe column that overlaps the key domain, with NULLs
+        m = 50_021
+        pk = np.concatenate([keys[rng.integers(0, max(n, 1), m // 2)] if n else np.zeros(m // 2, dtype=dtype),
+                             rng.integers(lo, hi, m - m // 2).astype(dtype)])
+        probe = Chunk([(3, pk, rand_nulls(rng, m, 0.05), typ)])
+        sel = g.evaluate(probe, 3)
+        assert np.array_equal(sel, o.evaluate(probe, 3))
+        prior = rng.integers(0, 2, m).astype(np.uint8)
+        assert np.array_equal(g.evaluate(probe, 3, prior), o.evaluate(probe, 3, prior))
+        if n:  # no false negatives among the inserted (non-NULL) keys
+            hit = Chunk([(3, keys, None, typ)])
+            inserted = np.ones(n, dtype=bool) if nulls is None else nulls == 0
+            assert g.evaluate(hit, 3)[inserted].all()
+    finally:
+        g.close()
+
+
+def test_rf_merge_is_the_union(gpu, ctx, oracle):
+    # SimdBlockFilter::merge (runtime_filter.h:126-140) + min/max/has_null union (RuntimeBloomFilter::merge)
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, 10**6, 40_000, dtype=np.int32)
+    b = rng.integers(-10**6, 0, 30_000, dtype=np.int32)
+    bn = rand_nulls(rng, len(b), 0.01)
+    ca, cb = Chunk([(0, a, None)]), Chunk([(0, b, bn)])
+    ga, gb = gpu.RuntimeFilter(ctx, abi.TYPE_INT, 70_000), gpu.RuntimeFilter(ctx, abi.TYPE_INT, 70_000)
+    oa, ob = oracle.RuntimeFilter(abi.TYPE_INT, 70_000), oracle.RuntimeFilter(abi.TYPE_INT, 70_000)
+    try:
+        ga.insert(ca, 0)
+        oa.insert(ca, 0)
+        gb.insert(cb, 0, insert_nulls=True)
+        ob.insert(cb, 0, insert_nulls=True)
+        # GPU filter <- directory built on the CPU (a filter shipped from a CPU BE) and vice versa
+        ga.merge(ob.directory(), ob.info())
+        oa.merge(ob)
+        _same_info(ga.info(), oa.info())
+        assert np.array_equal(ga.directory(), oa.directory())
+        both = Chunk([(0, np.concatenate([a, b[bn == 0]]), None)])
+        assert ga.evaluate(both, 0).all()
+        # sizes must agree (SimdBlockFilter::merge DCHECK)
+        small = gpu.RuntimeFilter(ctx, abi.TYPE_INT, 100)
+        with pytest.raises(gpu.GpuError):
+            small.merge(ob.directory(), ob.info())
+        small.close()
+    finally:
+        ga.close()
+        gb.close()
+
+
+@pytest.mark.parametrize("kind", ["range_i32", "sparse_i64_nulls", "two_keys"])
+def test_join_build_publishes_its_runtime_filter(gpu, ctx, oracle, kind):
+    # HashJoinBuildOperator::set_finishing -> create_runtime_filters (hash_join_build_operator.cpp:100-215): the filter
+    # of key k holds exactly the build rows' key-k values, sized by the table's row count
+    rng = np.random.default_rng(21)
+    nb = 30_000
+    if kind == "range_i32":
+        cols = [(0, rng.integers(1000, 90_000, nb, dtype=np.int32), None)]
+        ktypes, kslots = [abi.TYPE_INT], [0]
+    elif kind == "sparse_i64_nulls":
+        cols = [(0, rng.integers(-2**60, 2**60, nb, dtype=np.int64), rand_nulls(rng, nb, 0.03))]
+        ktypes, kslots = [abi.TYPE_BIGINT], [0]
+    else:
+        cols = [(0, rng.integers(0, 5000, nb, dtype=np.int32), None), (1, rng.integers(-300, 300, nb, dtype=np.int32), None)]
+        ktypes, kslots = [abi.TYPE_INT, abi.TYPE_INT], [0, 1]
+    build = Chunk(cols + [(5, rng.integers(0, 100, nb, dtype=np.int32), None)])
+    d = abi.make_join_desc(abi.JOIN_INNER, kslots, [10 + s for s in kslots], ktypes, build_out=[5], probe_out=[10])
+    j = gpu.Join(ctx, d)
+    try:
+        half = nb // 2
+        j.append_build(Chunk([(s, a[:half], None if nl is None else nl[:half]) for s, a, nl in build.columns()]))
+        j.append_build(Chunk([(s, a[half:], None if nl is None else nl[half:]) for s, a, nl in build.columns()]))
+        j.build_finish()
+        for k, slot in enumerate(kslots):
+            for insert_nulls in (False, True):
+                g = gpu.RuntimeFilter.from_join(j, k, True, insert_nulls)
+                o = oracle.RuntimeFilter(ktypes[k], nb, True)
+                o.insert(build, slot, insert_nulls)
+                _same_info(g.info(), o.info())
+                assert np.array_equal(g.directory(), o.directory())
+                g.close()
+    finally:
+        j.close()
+
+
+@pytest.mark.parametrize("fast", [True, False])
+@pytest.mark.parametrize("n", [0, 257, 100_003, 1_000_003])
+def test_scan_applies_attached_runtime_filters(gpu, ctx, oracle, fast, n):
+    # ScanOperator side (scan_operator.h:212-225, RuntimeFilterProbeCollector::evaluate): conjuncts AND every filter
+    rng = np.random.default_rng(31 + n)
+    dim1 = rng.choice(200_000, 20_000, replace=False).astype(np.int32)
+    dim2 = rng.integers(-2**40, 2**40, 5000, dtype=np.int64)
+    k1 = rng.integers(0, 200_000, n, dtype=np.int32)
+    k2 = np.where(rng.random(n) < 0.5, dim2[rng.integers(0, len(dim2), n)], rng.integers(-2**40, 2**40, n, dtype=np.int64))
+    chunk = Chunk([
+        (0, rng.integers(0, 100, n, dtype=np.int32), None),
+        (1, k1, None),
+        (2, k2, None if fast else rand_nulls(rng, n, 0.05)),
+        (3, rng.integers(0, 10**6, n, dtype=np.int64), None),
+    ])
+    preds = [abi.make_pred(0, abi.PRED_BETWEEN, 10, 80)] if fast else [abi.make_pred(0, abi.PRED_NE, 7), abi.make_pred(3, abi.PRED_GE, 1000)]
+    sd = abi.ScanDesc(preds=preds, filter_exprs=[], out_slots=[0, 1, 2, 3])
+    g1, g2 = gpu.RuntimeFilter(ctx, abi.TYPE_INT, len(dim1)), gpu.RuntimeFilter(ctx, abi.TYPE_BIGINT, len(dim2))
+    o1, o2 = oracle.RuntimeFilter(abi.TYPE_INT, len(dim1)), oracle.RuntimeFilter(abi.TYPE_BIGINT, len(dim2))
+    c1 = Chunk([(0, dim1, None)])
+    c2 = Chunk([(0, dim2, rand_nulls(rng, len(dim2), 0.01))])
+    for f, c in ((g1, c1), (o1, c1), (g2, c2), (o2, c2)):
+        f.insert(c, 0, insert_nulls=True)
+    scan = gpu.Scan(ctx, sd)
+    try:
+        scan.add_runtime_filter(g1, 1)
+        scan.add_runtime_filter(g2, 2)
+        expect = oracle.scan_evaluate(sd, chunk)
+        expect = o1.evaluate(chunk, 1, expect)
+        expect = o2.evaluate(chunk, 2, expect)
+        assert np.array_equal(scan.evaluate(chunk), expect)
+        out = gpu.chunk_out_to_host(ctx, scan.filter(chunk))
+        keep = expect.astype(bool)
+        for (slot, typ, data, nulls), (s0, arr, nl) in zip(out, chunk.columns()):
+            assert slot == s0 and np.array_equal(data, arr[keep])
+            if nl is not None:
+                assert np.array_equal(nulls, nl[keep])
+        if n:  # the filters do drop rows the conjuncts keep
+            assert expect.sum() < oracle.scan_evaluate(sd, chunk).sum()
+    finally:
+        scan.close()
+        g1.close()
+        g2.close()
+
+
+def test_runtime_filter_errors_are_loud(gpu, ctx):
+    with pytest.raises(gpu.GpuError):
+        gpu.RuntimeFilter(ctx, abi.TYPE_DOUBLE, 10)
+    rf = gpu.RuntimeFilter(ctx, abi.TYPE_INT, 10)
+    with pytest.raises(gpu.GpuError):
+        rf.insert(Chunk([(0, np.arange(4, dtype=np.int32), None)]), 9)  # slot not in the chunk
+    scan = gpu.Scan(ctx, abi.ScanDesc(preds=[], filter_exprs=[], out_slots=[0]))
+    for _ in range(4):
+        scan.add_runtime_filter(rf, 0)
+    with pytest.raises(gpu.GpuError):
+        scan.add_runtime_filter(rf, 0)
+    scan.close()
+    rf.close()

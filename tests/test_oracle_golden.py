@@ -371,3 +371,65 @@ def test_hash_partition_matches_python_fnv(oracle):
     for c in range(8):
         rows = ri[st[c]:st[c + 1]].tolist()
         assert rows == sorted(rows) and all(ch[r] == c for r in rows)
+
+
+# ---- runtime filter (be/test/runtime/runtime_filter_core_test.cpp) -------------------------------
+def test_simd_block_filter_insert_and_test_golden(oracle):
+    # :49-61 SimdBlockFilterInsertAndTest: init(100); insert_hash(1, 18, ..., 188); every inserted hash tests true,
+    # hash + 1 tests false
+    bf = oracle.RuntimeFilter(abi.TYPE_BIGINT, 100)
+    assert bf.info().log_num_buckets == 2          # ceil(log2(100)) - 5 = 2 -> 4 buckets of 32 bytes
+    for i in range(1, 201, 17):
+        bf.insert_hash(i)
+    for i in range(1, 201, 17):
+        assert bf.test_hash(i) and not bf.test_hash(i + 1)
+    # make_mask in plain Python: bit (uint32(hash >> log_buckets) * SALT[k]) >> 27 of word k of bucket hash & mask
+    salt = [0x47b6137b, 0x44974d91, 0x8824ad5b, 0xa2b7289d, 0x705495c7, 0x2df1424b, 0x9efc4947, 0x5c6bfb31]
+    exp = np.zeros(4 * 8, dtype=np.uint32)
+    for i in range(1, 201, 17):
+        for k in range(8):
+            exp[8 * (i & 3) + k] |= np.uint32(1 << ((((i >> 2) * salt[k]) & 0xFFFFFFFF) >> 27))
+    assert np.array_equal(bf.directory(), exp)
+
+
+def test_simd_block_filter_merge_golden(oracle):
+    # :79-102 SimdBlockFilterMerge
+    left, right, merged = (oracle.RuntimeFilter(abi.TYPE_BIGINT, 100) for _ in range(3))
+    for i in range(1, 201, 17):
+        left.insert_hash(i)
+        right.insert_hash(i + 1)
+    merged.merge(left)
+    merged.merge(right)
+    for i in range(1, 201, 17):
+        assert merged.test_hash(i) and merged.test_hash(i + 1) and not merged.test_hash(i + 2)
+
+
+def test_min_max_runtime_filter_golden(oracle):
+    # :104-123 MinMaxRangeAndNullableSemantics: insert 10, 20 -> {5,10,15,20,25} -> 0,1,1,1,0; NULL rows 0 until insert_null
+    rf = oracle.RuntimeFilter(abi.TYPE_INT, 2, with_bloom=False)
+    rf.insert(Chunk([(0, np.array([10, 20], dtype=np.int32), None)]), 0)
+    col = np.array([5, 10, 15, 20, 25, 0, 0], dtype=np.int32)
+    nulls = np.array([0, 0, 0, 0, 0, 1, 1], dtype=np.uint8)
+    assert rf.evaluate(Chunk([(0, col[:5].copy(), None)]), 0).tolist() == [0, 1, 1, 1, 0]
+    assert rf.evaluate(Chunk([(0, col, nulls)]), 0).tolist() == [0, 1, 1, 1, 0, 0, 0]
+    rf.insert(Chunk([(0, np.array([0], dtype=np.int32), np.array([1], dtype=np.uint8))]), 0, insert_nulls=True)
+    assert rf.evaluate(Chunk([(0, col, nulls)]), 0).tolist() == [0, 1, 1, 1, 0, 1, 1]
+
+
+def test_runtime_bloom_filter_values(oracle):
+    # RuntimeBloomFilter::compute_hash = phmap_mix<8>(std::hash<T>(v)) (runtime_filter.h:1270-1276, phmap_utils.h:86-95)
+    def mix(a):
+        p = (a & 0xFFFFFFFFFFFFFFFF) * 0xde5fb9d2630458e9
+        return ((p >> 64) + p) & 0xFFFFFFFFFFFFFFFF
+    for v in (0, 1, 42, -1, 2**31 - 1, -2**31, 123456789012345):
+        assert oracle.value_hash(v) == mix(v)
+    rng = np.random.default_rng(5)
+    keys = rng.integers(-10**6, 10**6, 5000, dtype=np.int32)
+    rf = oracle.RuntimeFilter(abi.TYPE_INT, len(keys))
+    rf.insert(Chunk([(0, keys, None)]), 0)
+    assert rf.evaluate(Chunk([(0, keys, None)]), 0).all()                      # no false negatives
+    other = rng.integers(2 * 10**6, 3 * 10**6, 5000, dtype=np.int32)
+    assert not rf.evaluate(Chunk([(0, other, None)]), 0).any()                 # outside [min, max]
+    inside = np.setdiff1d(np.arange(-10**6, 10**6, 7, dtype=np.int32), keys)[:20000]
+    fp = rf.evaluate(Chunk([(0, inside, None)]), 0).mean()
+    assert fp < 0.05                                                           # 8 bits per key, 8 probes in one block
