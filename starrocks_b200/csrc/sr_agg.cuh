@@ -444,12 +444,16 @@ __device__ __forceinline__ void acc_smem_flush(const AggDev& a, const AccPtrs& p
 }
 
 constexpr int AGG_BLOCK = 256;
+// the row-at-a-time push kernels wait on one DRAM access after the other (ncu: 55-60 % of the stall samples are
+// long-scoreboard waits at the key / input loads), so their throughput is proportional to the warps in flight: cap the
+// registers at 32 for full occupancy (measured: 40 registers = 6 CTAs/SM made the dense push 2.93 -> 4.07 ms per 200 M rows)
+constexpr int AGG_MIN_BLOCKS = 8;
 
 // standalone aggregate sink: one pass over a chunk.
 //  SMEM: dense table accumulated in shared memory.  slots_out (optional): pass-1-only mode
 //  (find slots, no update); slots_in (optional): pass-2 mode (slots precomputed).
 template <bool SMEM>
-__global__ void __launch_bounds__(AGG_BLOCK) k_agg_push(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, int64_t n, long long* __restrict__ slots_out,
+__global__ void __launch_bounds__(AGG_BLOCK, AGG_MIN_BLOCKS) k_agg_push(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, int64_t n, long long* __restrict__ slots_out,
                                                          const long long* __restrict__ slots_in) {
     extern __shared__ long long s_acc[];
     const AggDev& a = *ad;
@@ -813,7 +817,7 @@ __device__ __forceinline__ void single_acc_flush(const AggDev& a, SingleAcc& s) 
     }
 }
 
-__global__ void __launch_bounds__(AGG_BLOCK) k_agg_push_single(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, int64_t n) {
+__global__ void __launch_bounds__(AGG_BLOCK, AGG_MIN_BLOCKS) k_agg_push_single(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, int64_t n) {
     const AggDev& a = *ad;
     SingleAcc s;
     single_acc_init(a, s);
@@ -1240,6 +1244,7 @@ static int32_t agg_compile(sr_agg* a, slot_type_fn tf, agg_nullable_fn nf, void*
                 if (fd.input.num_nodes >= SR_MAX_EXPR_NODES) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "expression too long");
                 fd.input.nodes[fd.input.num_nodes].op = srd::C_I2D;
                 fd.input.num_nodes++;
+                fd.input.form = srd::F_GENERIC; // no longer the shape compile_expr recognised
                 fd.input.result_is_double = 1;
             }
             break;

@@ -518,6 +518,7 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg(const FragDev*
     } else {
         acc_ptrs_global(ad, acc);
     }
+    __syncthreads(); // s_joins and the shared accumulators are filled cooperatively: no warp may run ahead of that
     // Measured and rejected (profiles/r1_notes.md): requesting the NEXT row's fact sectors with prefetch.global.L2
     // while the current row walks its dependent chain.  HBM-resident input: 0.73 -> 1.27 ms (the prefetch fetches
     // whole 128-byte lines where the loads need one 32-byte sector: 4x the DRAM traffic of a pass that is bound by

@@ -447,6 +447,15 @@ static int32_t compile_expr(sr_ctx* ctx, const sr_expr* e, VReg* reg, slot_type_
     if (sp != 1) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "expression does not reduce to one value");
     out->num_nodes = n;
     out->result_is_double = tst[0];
+    out->form = srd::F_GENERIC;
+    out->pad = 0;
+    const auto is_load = [&](int k) { return out->nodes[k].op == srd::C_LOAD_I || out->nodes[k].op == srd::C_LOAD_D; };
+    const auto is_const = [&](int k) { return out->nodes[k].op == srd::C_ICONST || out->nodes[k].op == srd::C_DCONST; };
+    if (n == 1 && is_load(0)) out->form = srd::F_COL;
+    if (n == 3 && is_load(0) && srd::cexpr_is_simple_arith(out->nodes[2].op)) {
+        if (is_load(1)) out->form = srd::F_BIN_CC;
+        if (is_const(1)) out->form = srd::F_BIN_CK;
+    }
     return SR_OK;
 }
 

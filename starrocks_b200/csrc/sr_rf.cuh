@@ -46,6 +46,40 @@ __device__ __forceinline__ bool rf_test(const RfDev& r, long long v) {
     return miss == 0;
 }
 
+// R rows at once: all bucket reads are issued before any is tested (2 x LDG.128 per row in flight), which is what the
+// scan needs -- the directory usually sits in L2 and the test is latency-, not bandwidth-bound.
+// active: bit r = row r is to be tested; returns the bits of the rows that pass.
+template <int R>
+__device__ __forceinline__ uint32_t rf_test_rows(const RfDev& rf, const long long (&v)[R], uint32_t active) {
+    uint32_t in = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) in |= (((active >> r) & 1u) && v[r] >= rf.min_value && v[r] <= rf.max_value ? 1u : 0u) << r;
+    if (rf.dir == nullptr || in == 0) return in;
+    uint4 lo[R], hi[R];
+    uint32_t key[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const unsigned long long h = rf_value_hash(v[r]);
+        key[r] = (uint32_t)(h >> rf.log_buckets);
+        const uint4* b = (const uint4*)(rf.dir + 8 * (h & rf.dir_mask));
+        lo[r] = hi[r] = make_uint4(0, 0, 0, 0);
+        if ((in >> r) & 1u) {
+            lo[r] = __ldg(b);
+            hi[r] = __ldg(b + 1);
+        }
+    }
+    uint32_t pass = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const uint32_t w[8] = {lo[r].x, lo[r].y, lo[r].z, lo[r].w, hi[r].x, hi[r].y, hi[r].z, hi[r].w};
+        uint32_t miss = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) miss |= ~w[i] & (1u << ((key[r] * rf_salt(i)) >> 27));
+        pass |= (miss == 0 ? 1u : 0u) << r;
+    }
+    return pass & in;
+}
+
 // stats: [0] min, [1] max, [2] inserted, [3] has_null
 __device__ __forceinline__ void rf_insert_one(uint32_t* dir, unsigned long long dir_mask, int log_buckets, long long v) {
     const unsigned long long h = rf_value_hash(v);

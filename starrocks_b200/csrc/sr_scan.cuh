@@ -190,16 +190,27 @@ __global__ void __launch_bounds__(SCANW_BLOCK) k_scan_mask(const ScanProg* __res
             // RuntimeFilterProbeCollector::evaluate: every filter ANDs into the selection; a NULL probe value passes
             // only a filter that saw a NULL build key.  Only surviving rows pay the bucket read (one 32-byte sector).
 #pragma unroll 1
-            for (int f = 0; f < st.num_rfs; f++) {
+            for (int f = 0; f < st.num_rfs && m != 0; f++) {
                 const RfDev& rf = st.rfs[f];
-#pragma unroll 1
-                for (int r = 0; r < SCANW_ROWS; r++) {
-                    if (!((m >> r) & 1u)) continue;
-                    int64_t bits;
-                    const bool nul = ChunkLoader{vt, base + r}.load(rf.value_id, bits);
-                    const bool pass = nul ? rf.has_null != 0 : rf_test(rf, bits);
-                    if (!pass) m &= ~(1u << r);
+                uint32_t nulls = 0;
+                long long v[SCANW_ROWS];
+                const int32_t* c32 = (const int32_t*)vt.v[rf.value_id].data;
+                if (vt.plain32 && m == 0xFFu && (((uintptr_t)c32) & 15) == 0) { // whole tile alive: two 128-bit loads
+                    const int4 a = ldg_stream_v4(c32 + base), b = ldg_stream_v4(c32 + base + 4);
+                    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < SCANW_ROWS; r++) {
+                        int64_t bits = 0;
+                        if ((m >> r) & 1u) nulls |= (ChunkLoader{vt, base + r}.load(rf.value_id, bits) ? 1u : 0u) << r;
+                        v[r] = bits;
+                    }
                 }
+                static_assert(SCANW_ROWS == 8, "two half-tiles of four rows");
+                const long long va[4] = {v[0], v[1], v[2], v[3]}, vb[4] = {v[4], v[5], v[6], v[7]};
+                const uint32_t test = m & ~nulls;
+                const uint32_t pass = rf_test_rows<4>(rf, va, test & 15u) | (rf_test_rows<4>(rf, vb, test >> 4) << 4);
+                m = pass | (rf.has_null ? m & nulls : 0u);
             }
         }
         if (mask_bits) mask_bits[tile * 32 + lane] = (uint8_t)m;

@@ -12,7 +12,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsr_gpu.so")
+LIB_PATH = os.environ.get("SR_GPU_LIB") or os.path.join(_HERE, "libsr_gpu.so")   # SR_GPU_LIB: an experimental build
 _LIB = None
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
@@ -31,6 +31,8 @@ def build(verbose=False):
 def _needs_build():
     if not os.path.exists(LIB_PATH):
         return True
+    if os.environ.get("SR_GPU_LIB"):
+        return False
     t = os.path.getmtime(LIB_PATH)
     csrc = os.path.join(_HERE, "csrc")
     srcs = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(_HERE, "..", "include", "sr_gpu_ops.h")]

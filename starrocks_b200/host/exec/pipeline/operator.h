@@ -7,9 +7,13 @@
 // In a real BE build these headers are the BE's own; only this directory's gpu/*.h would be added.
 #pragma once
 
+#include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <memory>
+#include <set>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -160,6 +164,43 @@ protected:
     size_t _degree_of_parallelism = 1;
 };
 
+// be/src/exec/pipeline/runtime_filter_types.h:140-245.  The build operator of a join publishes its filters once
+// (set_collector, first caller wins); drivers whose source consumes them stay PRECONDITION_BLOCKed until every holder
+// is ready (pipeline_driver.h:357-364 local_rf_block).  The collector type is the execution layer's business.
+class RuntimeFilterHolder {
+public:
+    void set_collector(std::shared_ptr<void> collector) {
+        void* expected = nullptr;
+        if (_collector.compare_exchange_strong(expected, collector.get(), std::memory_order_release, std::memory_order_acquire))
+            _collector_ownership = std::move(collector);
+    }
+    void* get_collector() const { return _collector.load(std::memory_order_acquire); }
+    bool is_ready() const { return get_collector() != nullptr; }
+
+private:
+    std::shared_ptr<void> _collector_ownership;
+    std::atomic<void*> _collector{nullptr};
+};
+
+class RuntimeFilterHub { // keyed by the plan node id of the join that produces the filters (factory level: sequence -1)
+public:
+    void add_holder(int32_t plan_node_id) { _holders.emplace(plan_node_id, std::make_unique<RuntimeFilterHolder>()); }
+    void set_collector(int32_t plan_node_id, std::shared_ptr<void> collector) { get_holder(plan_node_id)->set_collector(std::move(collector)); }
+    RuntimeFilterHolder* get_holder(int32_t plan_node_id) {
+        auto it = _holders.find(plan_node_id);
+        return it == _holders.end() ? nullptr : it->second.get();
+    }
+    std::vector<RuntimeFilterHolder*> gather_holders(const std::set<int32_t>& ids) {
+        std::vector<RuntimeFilterHolder*> out;
+        for (int32_t id : ids)
+            if (auto* h = get_holder(id)) out.push_back(h);
+        return out;
+    }
+
+private:
+    std::unordered_map<int32_t, std::unique_ptr<RuntimeFilterHolder>> _holders;
+};
+
 // The pull/push loop of PipelineDriver::process (be/src/exec/pipeline/pipeline_driver.cpp:270-500) for one driver:
 // for each adjacent pair, pull when the upstream has output and the downstream needs input, propagate finishing,
 // enforce the chunk_size limit (:372-378).  Returns when the sink is finished or no operator can make progress
@@ -174,8 +215,16 @@ public:
         return Status::OK();
     }
 
+    void set_local_rf_holders(std::vector<RuntimeFilterHolder*> holders) { _local_rf_holders = std::move(holders); }
+    bool local_rf_block() { // pipeline_driver.h:357-364
+        if (_all_local_rf_ready) return false;
+        _all_local_rf_ready = std::all_of(_local_rf_holders.begin(), _local_rf_holders.end(), [](auto* h) { return h->is_ready(); });
+        return !_all_local_rf_ready;
+    }
+
     StatusOr<State> process(RuntimeState* state) {
         const size_t n = _operators.size();
+        if (local_rf_block()) return PRECONDITION_BLOCK;
         for (auto& op : _operators) {
             auto* dep = dynamic_cast<OperatorWithDependency*>(op.get());
             if (dep != nullptr && !dep->is_ready()) return PRECONDITION_BLOCK;
@@ -223,6 +272,8 @@ private:
     std::vector<bool> _finishing_sent;
     size_t _first_unfinished = 0;
     size_t _rows_moved = 0;
+    std::vector<RuntimeFilterHolder*> _local_rf_holders;
+    bool _all_local_rf_ready = false;
 };
 
 } // namespace pipeline

@@ -136,6 +136,36 @@ inline Status slice_out_to_chunks(sr_ctx* ctx, const sr_chunk_out& out, int chun
     return Status::OK();
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// runtime filters: RuntimeFilterBuildDescriptor / RuntimeFilterProbeDescriptor / RuntimeFilterCollector
+// (be/src/exec/runtime_filter/runtime_filter_descriptor.h, be/src/exec/pipeline/runtime_filter_types.h:60-138)
+// ------------------------------------------------------------------------------------------------------------
+struct GpuRuntimeFilterBuildDesc {
+    int32_t filter_id;
+    int32_t key_index; // build_expr_order: which join key the filter is built from
+    bool with_bloom;   // false: min/max only
+    bool insert_nulls; // null-safe equal join
+};
+struct GpuRuntimeFilterProbeDesc {
+    int32_t filter_id;
+    int32_t build_plan_node_id; // the join whose holder carries the filter
+    int32_t probe_slot;         // probe_expr: a plain slot ref of the scan's chunk
+};
+class GpuRuntimeFilterCollector { // owns the device filters of one join
+public:
+    ~GpuRuntimeFilterCollector() {
+        for (auto& kv : _filters) sr_rf_destroy(kv.second);
+    }
+    void add(int32_t filter_id, sr_rf* rf) { _filters[filter_id] = rf; }
+    sr_rf* find(int32_t filter_id) const {
+        auto it = _filters.find(filter_id);
+        return it == _filters.end() ? nullptr : it->second;
+    }
+
+private:
+    std::unordered_map<int32_t, sr_rf*> _filters;
+};
+
 constexpr int kGpuBatchChunks = 64; // ScanOperator::_buffer_size / io task batch (scan_operator.h:119)
 
 // ------------------------------------------------------------------------------------------------------------
@@ -155,15 +185,29 @@ public:
         _scan = sr_scan_create(_ctx, &_desc);
         return _scan ? Status::OK() : sr_to_status(_ctx, sr_last_error_code(_ctx));
     }
+    // ScanOperator consumes the runtime filters of the joins above it (scan_operator.h:212-225); the driver keeps this
+    // operator PRECONDITION_BLOCKed until the holders returned by rf_holders() are ready.
+    void set_runtime_filters(RuntimeFilterHub* hub, std::vector<GpuRuntimeFilterProbeDesc> probes) {
+        _hub = hub;
+        _rf_probes = std::move(probes);
+    }
+    std::vector<RuntimeFilterHolder*> rf_holders() const {
+        std::set<int32_t> ids;
+        for (auto& p : _rf_probes) ids.insert(p.build_plan_node_id);
+        return _hub ? _hub->gather_holders(ids) : std::vector<RuntimeFilterHolder*>();
+    }
+    int64_t rows_after_scan() const { return _rows_out; }
     bool has_output() const override { return !_out.empty() || _next < _morsel.size(); }
     bool is_finished() const override { return _out.empty() && _next >= _morsel.size(); }
     StatusOr<ChunkPtr> pull_chunk(RuntimeState* state) override {
+        if (!_rf_attached) RETURN_IF_ERROR(_attach_runtime_filters());
         if (_out.empty() && _next < _morsel.size()) {
             _batch.clear();
             for (int k = 0; k < kGpuBatchChunks && _next < _morsel.size(); k++) _batch.append(*_morsel[_next++]);
             sr_chunk_view v = _batch.view();
             sr_chunk_out out;
             RETURN_IF_SR_ERROR(_ctx, sr_scan_filter(_scan, &v, &out));
+            _rows_out += out.num_rows;
             RETURN_IF_ERROR(slice_out_to_chunks(_ctx, out, state->chunk_size(), &_out));
         }
         if (_out.empty()) return ChunkPtr(nullptr);
@@ -173,9 +217,24 @@ public:
     }
 
 private:
+    Status _attach_runtime_filters() {
+        _rf_attached = true;
+        for (auto& p : _rf_probes) {
+            RuntimeFilterHolder* h = _hub ? _hub->get_holder(p.build_plan_node_id) : nullptr;
+            if (!h || !h->is_ready()) return Status::InternalError("runtime filter " + std::to_string(p.filter_id) + " is not ready");
+            sr_rf* rf = static_cast<GpuRuntimeFilterCollector*>(h->get_collector())->find(p.filter_id);
+            if (!rf) continue; // the build side chose not to produce it
+            RETURN_IF_SR_ERROR(_ctx, sr_scan_add_runtime_filter(_scan, rf, p.probe_slot));
+        }
+        return Status::OK();
+    }
     sr_ctx* _ctx;
     sr_scan_desc _desc;
     sr_scan* _scan = nullptr;
+    RuntimeFilterHub* _hub = nullptr;
+    std::vector<GpuRuntimeFilterProbeDesc> _rf_probes;
+    bool _rf_attached = false;
+    int64_t _rows_out = 0;
     std::vector<ChunkPtr> _morsel;
     size_t _next = 0;
     ChunkBatch _batch;
@@ -212,6 +271,11 @@ public:
     GpuHashJoinBuildOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, GpuHashJoinerPtr joiner)
             : Operator(f, id, "gpu_hash_join_build", plan_node_id, false, seq), _joiner(std::move(joiner)) {}
     Status prepare(RuntimeState* state) override { return _joiner->prepare(); }
+    // what HashJoinNode hands the build operator factory: the filters to build and the hub that carries them
+    void set_runtime_filters(RuntimeFilterHub* hub, std::vector<GpuRuntimeFilterBuildDesc> descs) {
+        _hub = hub;
+        _rf_descs = std::move(descs);
+    }
     bool has_output() const override { return false; }
     bool need_input() const override { return !_finished; }
     bool is_finished() const override { return _finished; }
@@ -225,6 +289,15 @@ public:
         if (_finished) return Status::OK();
         RETURN_IF_ERROR(_flush());
         RETURN_IF_SR_ERROR(_joiner->ctx(), sr_join_build_finish(_joiner->join()));
+        if (_hub) { // create_runtime_filters + set_collector (hash_join_build_operator.cpp:100-215): publish even when empty
+            auto collector = std::make_shared<GpuRuntimeFilterCollector>();
+            for (auto& d : _rf_descs) {
+                sr_rf* rf = sr_join_build_runtime_filter(_joiner->join(), d.key_index, d.with_bloom ? 1 : 0, d.insert_nulls ? 1 : 0);
+                if (!rf) return sr_to_status(_joiner->ctx(), sr_last_error_code(_joiner->ctx()));
+                collector->add(d.filter_id, rf);
+            }
+            _hub->set_collector(_plan_node_id, collector);
+        }
         _finished = true;
         return Status::OK();
     }
@@ -240,6 +313,8 @@ private:
     GpuHashJoinerPtr _joiner;
     ChunkBatch _batch;
     bool _finished = false;
+    RuntimeFilterHub* _hub = nullptr;
+    std::vector<GpuRuntimeFilterBuildDesc> _rf_descs;
 };
 
 class GpuHashJoinProbeOperator final : public OperatorWithDependency {

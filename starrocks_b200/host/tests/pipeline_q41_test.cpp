@@ -5,6 +5,8 @@
 //   build pipelines (x4):  GpuScanOperator(dimension, predicate) -> GpuHashJoinBuildOperator
 //   probe pipeline  (A):   GpuScanOperator(lineorder) -> GpuHashJoinProbeOperator x4 -> GpuAggregateBlockingSinkOperator
 //   probe pipeline  (B):   GpuScanOperator(lineorder) -> GpuFragmentSinkOperator            (fused form)
+//   probe pipeline  (C):   A, with every build operator publishing a runtime filter (min/max + bloom) through the
+//                          RuntimeFilterHub and the lineorder scan consuming them (local_rf_block until they are ready)
 //   result pipeline:       GpuAggregateBlockingSourceOperator -> ResultSink (collects rows)
 //
 // A and B must give the same groups, and both must match a straightforward row-at-a-time evaluation of the query in
@@ -209,8 +211,12 @@ int main(int argc, char** argv) {
     agg_desc.fns[0] = sr_agg_fn{SR_AGG_SUM, SR_TYPE_INT, OUT_REV, 0, col_expr(LO_REVENUE)};
     agg_desc.fns[1] = sr_agg_fn{SR_AGG_SUM, SR_TYPE_INT, OUT_COST, 0, col_expr(LO_SUPPLYCOST)};
 
-    Groups results[2];
-    for (int fused = 0; fused < 2; fused++) {
+    Groups results[3];
+    size_t rows_after_scan[3] = {0, 0, 0};
+    for (int variant = 0; variant < 3; variant++) {
+        const bool fused = variant == 1, with_rf = variant == 2;
+        RuntimeFilterHub hub;
+        std::vector<std::pair<OperatorPtr, OperatorPtr>> build_ops;
         // ---- build pipelines: scan(dim) -> hash join build; the joiner is shared with the probe side ----
         std::vector<GpuHashJoinerFactoryPtr> joiner_factories;
         std::vector<std::vector<int32_t>> out_slot_store(dims.size());
@@ -242,11 +248,22 @@ int main(int argc, char** argv) {
             auto jf = std::make_shared<GpuHashJoinerFactory>(ctx, jd);
             joiner_factories.push_back(jf);
             GpuScanOperatorFactory scan_f(1, 1, ctx, sd, {split(dm.table, 4096)});
-            GpuHashJoinBuildOperatorFactory build_f(2, 2, jf);
-            PipelineDriver build_driver({scan_f.create(1, 0), build_f.create(1, 0)});
-            run_to_finish(build_driver, &state, dm.name);
-            build_driver.close(&state);
+            GpuHashJoinBuildOperatorFactory build_f(2, 20 + (int)k, jf);
+            build_ops.emplace_back(scan_f.create(1, 0), build_f.create(1, 0));
+            if (with_rf) {
+                hub.add_holder(20 + (int)k);
+                static_cast<GpuHashJoinBuildOperator*>(build_ops.back().second.get())
+                        ->set_runtime_filters(&hub, {GpuRuntimeFilterBuildDesc{(int32_t)k, 0, true, false}});
+            }
         }
+        auto run_builds = [&]() {
+            for (size_t k = 0; k < dims.size(); k++) {
+                PipelineDriver build_driver({build_ops[k].first, build_ops[k].second});
+                run_to_finish(build_driver, &state, dims[k].name);
+                build_driver.close(&state);
+            }
+        };
+        if (!with_rf) run_builds();
         // ---- probe pipeline ----
         sr_scan_desc fact_scan{};
         std::vector<int32_t> fact_out = {LO_ORDERDATE, LO_CUSTKEY, LO_SUPPKEY, LO_PARTKEY, LO_REVENUE, LO_SUPPLYCOST};
@@ -256,6 +273,12 @@ int main(int argc, char** argv) {
         GpuAggregatorPtr aggregator;
         GpuFragmentPtr fragment;
         Operators ops = {fact_f.create(1, 0)};
+        auto* fact_scan_op = static_cast<GpuScanOperator*>(ops[0].get());
+        if (with_rf) {
+            std::vector<GpuRuntimeFilterProbeDesc> probes;
+            for (size_t k = 0; k < dims.size(); k++) probes.push_back(GpuRuntimeFilterProbeDesc{(int32_t)k, 20 + (int32_t)k, dims[k].probe_slot});
+            fact_scan_op->set_runtime_filters(&hub, probes);
+        }
         GpuAggregatorFactoryPtr agg_f;
         if (!fused) {
             for (size_t k = 0; k < dims.size(); k++) {
@@ -282,17 +305,34 @@ int main(int argc, char** argv) {
             aggregator = fragment->aggregator();
         }
         PipelineDriver probe_driver(ops);
-        run_to_finish(probe_driver, &state, fused ? "probe(fused)" : "probe(per-operator)");
+        if (with_rf) {
+            // the probe-side driver must park until every build operator has published its collector
+            probe_driver.set_local_rf_holders(fact_scan_op->rf_holders());
+            auto st = probe_driver.process(&state);
+            if (!st.ok() || st.value() != PipelineDriver::PRECONDITION_BLOCK || !probe_driver.local_rf_block()) {
+                fprintf(stderr, "probe driver was not blocked on its local runtime filters\n");
+                return 2;
+            }
+            run_builds();
+            if (probe_driver.local_rf_block()) {
+                fprintf(stderr, "runtime filters were not published by the build operators\n");
+                return 2;
+            }
+        }
+        run_to_finish(probe_driver, &state, fused ? "probe(fused)" : with_rf ? "probe(per-operator + runtime filters)" : "probe(per-operator)");
+        rows_after_scan[variant] = (size_t)fact_scan_op->rows_after_scan();
         // ---- result pipeline ----
         auto sink = std::make_shared<ResultSink>();
         auto source = std::make_shared<GpuAggregateBlockingSourceOperator>(nullptr, 9, 9, 0, aggregator);
         PipelineDriver result_driver({source, sink});
         run_to_finish(result_driver, &state, "result");
-        results[fused] = collect(*sink);
+        results[variant] = collect(*sink);
         result_driver.close(&state);
         probe_driver.close(&state);
-        printf("%s path: %zu groups, %zu rows moved between operators\n", fused ? "fused fragment" : "per-operator", results[fused].size(),
+        printf("%s path: %zu groups, %zu rows left the scan, %zu rows moved between operators\n",
+               fused ? "fused fragment" : with_rf ? "per-operator + runtime filters" : "per-operator", results[variant].size(), rows_after_scan[variant],
                probe_driver.rows_moved());
+        ops.clear(); // scans go before the hub that owns their filters
     }
     int rc = 0;
     {
@@ -342,6 +382,22 @@ int main(int argc, char** argv) {
     if (results[0] != expect) {
         fprintf(stderr, "per-operator pipeline differs from the checker (%zu vs %zu groups)\n", results[0].size(), expect.size());
         rc = 1;
+    }
+    if (results[2] != expect) {
+        fprintf(stderr, "per-operator pipeline with runtime filters differs from the checker (%zu vs %zu groups)\n", results[2].size(), expect.size());
+        rc = 1;
+    }
+    {
+        // the filters are exact enough to drop (almost) every row the joins would drop: the scan must emit at least the
+        // joined rows and far fewer than the table (bloom false positives only)
+        size_t joined = 0;
+        for (size_t i = 0; i < n_fact; i++)
+            joined += s_region[lo_supp[i] - 1] == 1 && c_region[lo_cust[i] - 1] == 1 && p_mfgr[lo_part[i] - 1] <= 1;
+        if (rows_after_scan[2] < joined || rows_after_scan[2] > joined + n_fact / 50 || rows_after_scan[0] != n_fact) {
+            fprintf(stderr, "runtime filters: %zu rows left the scan, %zu join (of %zu)\n", rows_after_scan[2], joined, n_fact);
+            rc = 1;
+        }
+        printf("runtime filters: scan output %zu -> %zu rows (%zu rows join)\n", rows_after_scan[0], rows_after_scan[2], joined);
     }
     if (results[1] != expect) {
         fprintf(stderr, "fused pipeline differs from the checker (%zu vs %zu groups)\n", results[1].size(), expect.size());

@@ -639,6 +639,36 @@ def test_fragment_tpch_q3_parity(gpu, ctx, oracle, mode):
                 x.close()
 
 
+def test_fragment_tpch_q3_is_stable_over_repeated_runs(gpu, ctx, oracle):
+    # regression: the final pass used its shared copy of the join descriptors before every warp had written it (missing
+    # barrier) -- about one run in ten looked a payload up through an all-zero descriptor and produced a (key, 0, 0) group
+    from starrocks_b200 import tpch
+    t = tpch.gen_tables(0.1)
+    li = t["lineitem"]
+    gj2, gkeep = tpch.q3_build_gpu(gpu, ctx, t)
+    oj2, okeep = tpch.q3_build_oracle(oracle, t)
+    _, _, _, _, li_scan = tpch.q3_descs()
+    agg_desc = tpch.q3_agg_desc()
+    payload = [tpch.O_ORDERDATE, tpch.O_SHIPPRIORITY]
+    try:
+        ores, _ = oracle.fragment_run(li_scan, [(oj2, tpch.L_ORDERKEY, payload)], agg_desc, tpch.table_chunk(li, tpch.LINEITEM_COLS), num_threads=3)
+        exp = oracle_rows(ores)
+        n = len(li["l_orderkey"])
+        for it in range(25):
+            frag = gpu.Fragment(ctx, li_scan, [(gj2, tpch.L_ORDERKEY, payload)], agg_desc, mode=(0, 2)[it & 1])
+            try:
+                for lo, hi in ((0, n // 2), (n // 2, n)):
+                    frag.push(tpch.table_chunk(li, tpch.LINEITEM_COLS, rows=(lo, hi)))
+                assert gpu_rows(frag.agg.result()) == exp, f"run {it}"
+            finally:
+                frag.close()
+    finally:
+        gj2.close()
+        for x in gkeep:
+            if hasattr(x, "close"):
+                x.close()
+
+
 def test_fragment_hash_table_grows_when_the_sampled_estimate_is_wrong(gpu, ctx, oracle):
     # the plan samples the first 64 K rows: none of them passes the conjunct, so the hash table is sized for ~0 groups;
     # the remaining 2.9 M rows all pass and all are new groups -> refused rows are re-applied after the table has grown

@@ -5,10 +5,13 @@ covered by the fused fragment) on HBM-resident chunks, one B200:
 
   sr_scan_evaluate / sr_scan_filter   SSB Q1.1 conjuncts; filter materialises two surviving columns
   sr_join_probe                       INNER join against a 3 M-row dense-key build side, one payload column, 20 % match
+  runtime filter                      the same join with its build-side filter (min/max + bloom) attached to the scan:
+                                      scan_filter(+filter) then join_probe on the survivors
   sr_agg_push                         no GROUP BY / dense (7 x 25 groups) / hash (1 M groups)
 Each line: milliseconds (best of N), rows/s and algorithmic GB/s (input columns read + output written).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import sys
@@ -38,6 +41,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=200_000_000)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only-agg", action="store_true")
     args = ap.parse_args()
     n = args.rows
     dev = torch.device("cuda:0")
@@ -56,37 +60,54 @@ def main():
     def report(name, ms, bytes_):
         out[name] = {"ms": round(ms, 3), "rows_per_s": n / ms * 1e3, "algorithmic_gbs": bytes_ / ms / 1e6}
 
-    # ---- scan ----
-    q11 = ssb.fact_chunk(cols, ssb.Q11_FACT_COLS, mem=abi.MEM_DEVICE)
-    scan_all = gpu.Scan(ctx, abi.ScanDesc(preds=ssb.q11_scan_preds()))
-    sel = torch.empty(n, dtype=torch.uint8, device=dev)
-    L = gpu.lib()
-    report("scan_evaluate (3 conjuncts -> uint8 selection)",
-           best_ms(lambda: ctx.check(L.sr_scan_evaluate(scan_all.h, q11.ref(), sel.data_ptr(), abi.MEM_DEVICE)), stream, args.reps), n * (12 + 1))
-    scan2 = gpu.Scan(ctx, abi.ScanDesc(preds=ssb.q11_scan_preds(), out_slots=[ssb.LO_SLOTS["lo_extendedprice"], ssb.LO_SLOTS["lo_discount"]]))
-    passed = scan2.filter(q11).num_rows
-    report("scan_filter (3 conjuncts, 2 columns out, %.1f %% pass)" % (100.0 * passed / n), best_ms(lambda: scan2.filter(q11), stream, args.reps), n * 16)
-    scan_half = gpu.Scan(ctx, abi.ScanDesc(preds=[abi.make_pred(ssb.LO_SLOTS["lo_quantity"], abi.PRED_LE, 25)],
-                                           out_slots=[ssb.LO_SLOTS[c] for c in ssb.Q11_FACT_COLS]))
-    passed = scan_half.filter(q11).num_rows
-    report("scan_filter (1 conjunct, 4 columns out, %.1f %% pass)" % (100.0 * passed / n), best_ms(lambda: scan_half.filter(q11), stream, args.reps),
-           n * 16 + passed * 16)
+    if not args.only_agg:
+        # ---- scan ----
+        q11 = ssb.fact_chunk(cols, ssb.Q11_FACT_COLS, mem=abi.MEM_DEVICE)
+        scan_all = gpu.Scan(ctx, abi.ScanDesc(preds=ssb.q11_scan_preds()))
+        sel = torch.empty(n, dtype=torch.uint8, device=dev)
+        L = gpu.lib()
+        report("scan_evaluate (3 conjuncts -> uint8 selection)",
+               best_ms(lambda: ctx.check(L.sr_scan_evaluate(scan_all.h, q11.ref(), sel.data_ptr(), abi.MEM_DEVICE)), stream, args.reps), n * (12 + 1))
+        scan2 = gpu.Scan(ctx, abi.ScanDesc(preds=ssb.q11_scan_preds(), out_slots=[ssb.LO_SLOTS["lo_extendedprice"], ssb.LO_SLOTS["lo_discount"]]))
+        passed = scan2.filter(q11).num_rows
+        report("scan_filter (3 conjuncts, 2 columns out, %.1f %% pass)" % (100.0 * passed / n), best_ms(lambda: scan2.filter(q11), stream, args.reps), n * 16)
+        scan_half = gpu.Scan(ctx, abi.ScanDesc(preds=[abi.make_pred(ssb.LO_SLOTS["lo_quantity"], abi.PRED_LE, 25)],
+                                               out_slots=[ssb.LO_SLOTS[c] for c in ssb.Q11_FACT_COLS]))
+        passed = scan_half.filter(q11).num_rows
+        report("scan_filter (1 conjunct, 4 columns out, %.1f %% pass)" % (100.0 * passed / n), best_ms(lambda: scan_half.filter(q11), stream, args.reps),
+               n * 16 + passed * 16)
 
-    # ---- join probe ----
-    nb = 3_000_000
-    rng = np.random.default_rng(3)
-    keep = np.sort(rng.choice(np.arange(1, nb + 1, dtype=np.int32), size=nb // 5, replace=False))
-    build = abi.Chunk([(100, keep, None), (101, (keep % 25).astype(np.int32), None)])
-    jd = abi.make_join_desc(abi.JOIN_INNER, [100], [ssb.LO_SLOTS["lo_custkey"]], [abi.TYPE_INT], build_out=[101],
-                            probe_out=[ssb.LO_SLOTS["lo_custkey"], ssb.LO_SLOTS["lo_revenue"]])
-    j = gpu.Join(ctx, jd)
-    j.append_build(build)
-    j.build_finish()
-    probe = abi.Chunk([(ssb.LO_SLOTS["lo_custkey"], cols["lo_custkey"], None, abi.TYPE_INT), (ssb.LO_SLOTS["lo_revenue"], cols["lo_revenue"], None, abi.TYPE_INT)],
-                      mem=abi.MEM_DEVICE)
-    matched = j.probe(probe).num_rows
-    report("join_probe INNER (%.1f %% match, 2 probe + 1 build column out)" % (100.0 * matched / n), best_ms(lambda: j.probe(probe), stream, args.reps),
-           n * 4 + matched * (8 + 12))
+        # ---- join probe ----
+        nb = 3_000_000
+        rng = np.random.default_rng(3)
+        keep = np.sort(rng.choice(np.arange(1, nb + 1, dtype=np.int32), size=nb // 5, replace=False))
+        build = abi.Chunk([(100, keep, None), (101, (keep % 25).astype(np.int32), None)])
+        jd = abi.make_join_desc(abi.JOIN_INNER, [100], [ssb.LO_SLOTS["lo_custkey"]], [abi.TYPE_INT], build_out=[101],
+                                probe_out=[ssb.LO_SLOTS["lo_custkey"], ssb.LO_SLOTS["lo_revenue"]])
+        j = gpu.Join(ctx, jd)
+        j.append_build(build)
+        j.build_finish()
+        probe = abi.Chunk([(ssb.LO_SLOTS["lo_custkey"], cols["lo_custkey"], None, abi.TYPE_INT), (ssb.LO_SLOTS["lo_revenue"], cols["lo_revenue"], None, abi.TYPE_INT)],
+                          mem=abi.MEM_DEVICE)
+        matched = j.probe(probe).num_rows
+        report("join_probe INNER (%.1f %% match, 2 probe + 1 build column out)" % (100.0 * matched / n), best_ms(lambda: j.probe(probe), stream, args.reps),
+               n * 4 + matched * (8 + 12))
+
+        # ---- runtime filter: the join's build-side filter on the scan, then the probe on what survives ----
+        rf = gpu.RuntimeFilter.from_join(j, 0, True, False)
+        scan_rf = gpu.Scan(ctx, abi.ScanDesc(preds=[], out_slots=[ssb.LO_SLOTS["lo_custkey"], ssb.LO_SLOTS["lo_revenue"]]))
+        scan_rf.add_runtime_filter(rf, ssb.LO_SLOTS["lo_custkey"])
+        kept = scan_rf.filter(probe)
+        survivors = kept.num_rows
+        report("scan_filter + runtime filter (bloom of %d keys, %.1f %% pass, 2 columns out)" % (len(keep), 100.0 * survivors / n),
+               best_ms(lambda: scan_rf.filter(probe), stream, args.reps), n * 8 + survivors * 8)
+
+        def scan_then_probe():
+            o = scan_rf.filter(probe)
+            v = abi.sr_chunk_view(C.cast(o.cols, C.POINTER(abi.sr_col_view)), o.num_cols, abi.MEM_DEVICE, o.num_rows)  # same column layout
+            ctx.check(L.sr_join_probe(j.h, 0, C.byref(v), C.byref(abi.sr_chunk_out())))
+        report("scan_filter + runtime filter -> join_probe (vs join_probe on every row above)", best_ms(scan_then_probe, stream, args.reps),
+               n * 8 + survivors * 8 + survivors * 4 + matched * 20)
 
     # ---- aggregate ----
     def agg_case(name, desc, columns, bytes_):
