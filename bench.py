@@ -52,51 +52,68 @@ def parse_args():
 # clocks sampling (B200_PROFILING.md recipe)
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled through NVML from a background thread (about 1 kHz: the timed region of the
+    default run is ~20 ms, far shorter than one `nvidia-smi -lms` period).  Started before the warm-up; only the samples
+    taken between mark_begin() and mark_end() -- the timed region -- are reported (`window: "timed"`); if the region was
+    too short to catch any, the samples of the warm-up + timed window are reported and `window` says so."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
 
     def __init__(self, device_index):
-        self.path = f"/tmp/sr_clocks_{os.getpid()}.csv"
-        self.proc = None
         self.idx = device_index
+        self.samples = []   # (t, sm_mhz, reason bits)
+        self.t0 = self.t1 = None
+        self.thread = None
+        self.smax = None
+        self.err = None
+        self._stop = False
 
     def start(self):
         try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.idx
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.smax = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        except Exception as e:  # noqa: BLE001
+            self.err = f"NVML unavailable: {e}"
+            return
+
+        def loop():
+            while not self._stop:
+                try:
+                    self.samples.append((time.perf_counter(), pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), int(get_reasons(h))))
+                except Exception as e:  # noqa: BLE001
+                    self.err = str(e)
+                    return
+                time.sleep(0.001)
+        import threading
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.f.close()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            p = [x.strip() for x in line.split(",")]
-            if len(p) < 9:
-                continue
-            try:
-                sm.append(float(p[1]))
-                smax.append(float(p[2]))
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if p[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        try:
-            os.remove(self.path)
-        except OSError:
-            pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop = True
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": [self.err or "no samples"], "samples": 0}
+        timed = [x for x in self.samples if self.t0 is not None and self.t1 is not None and self.t0 <= x[0] <= self.t1]
+        window = "timed"
+        if not timed:
+            timed, window = self.samples, "warm-up + timed (timed region shorter than one sample period)"
+        bits = 0
+        for _, _, r in timed:
+            bits |= r
+        return {"sm_mhz": statistics.median(x[1] for x in timed), "sm_min_mhz": min(x[1] for x in timed), "sm_max_mhz": self.smax,
+                "reasons": sorted(nm for b, nm in self.REASONS.items() if bits & b), "samples": len(timed), "window": window,
+                "source": "NVML nvmlDeviceGetClockInfo / CurrentClocksEventReasons, 1 ms period"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -312,19 +329,20 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- warm-up ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     result = None
     for _ in range(max(args.warmup, 1)):
         result = step(dchunk)
     barrier()
 
     # ---- timed: value (HBM-resident inputs) ----
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = ctx.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    sampler.mark_begin()
     ev0.record(stream)
     pass_ms = [0.0, 0.0, 0.0]
     trace = [] if os.environ.get("SR_BENCH_TRACE") else None   # host-side phase timestamps (debug aid)
@@ -350,6 +368,7 @@ def run_gpu(args):
         sys.stderr.write(f"[trace rank {rank}] enqueue reset+push {sum(t[0] for t in trace) / k * 1e3:.3f} ms, finish_step "
                          f"{sum(t[1] for t in trace) / k * 1e3:.3f} ms, last_pass_ms {sum(t[2] for t in trace) / k * 1e3:.3f} ms\n")
     barrier()
+    sampler.mark_end()
     launches = ctx.launches - launches0
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = ev0.elapsed_time(ev1)

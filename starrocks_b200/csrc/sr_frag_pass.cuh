@@ -456,6 +456,12 @@ __device__ __forceinline__ void warp_sel_range(unsigned long long n, unsigned lo
     if (begin > n) begin = n;
 }
 
+// the final pass is a chain of dependent gathers per row: latency bound, so resident warps matter more than spills.
+// Measured on SSB Q4.1 SF100 (9.6 M rows reach it): 66 registers / 3 CTAs per SM 0.89 ms, 62 / 4: 0.73, 48 / 5: 0.667,
+// 40 / 6: 0.669, 32 / 8: 0.70 ms.
+#ifndef SR_GATHER_AGG_MIN_BLOCKS
+#define SR_GATHER_AGG_MIN_BLOCKS 5
+#endif
 // one selective join on the selected rows: sel_in[0, *n_in) -> sel_out (appended at *counter_out)
 __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_join(const FragDev* __restrict__ fdp, int32_t j, const __grid_constant__ VTab vt,
                                                                     const SelEntry* __restrict__ sel_in, const unsigned long long* __restrict__ n_in_ptr,
@@ -496,7 +502,7 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_join(const FragDev
 // final pass: remaining joins inline, payload lookups, aggregate update.  SINGLE: no GROUP BY (its register state
 // would only cost the grouped instantiations spills).
 template <bool SMEM_AGG, bool SINGLE = false>
-__global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg(const FragDev* __restrict__ fdp, const AggDev* __restrict__ adp, const __grid_constant__ PassDev pd,
+__global__ void __launch_bounds__(GATHER_BLOCK, SR_GATHER_AGG_MIN_BLOCKS) k_frag_gather_agg(const FragDev* __restrict__ fdp, const AggDev* __restrict__ adp, const __grid_constant__ PassDev pd,
                                                                    const __grid_constant__ VTab vt, const SelEntry* __restrict__ sel_in,
                                                                    const unsigned long long* __restrict__ n_in_ptr, SelEntry* __restrict__ fail_list,
                                                                    unsigned long long* __restrict__ fail_count) {
