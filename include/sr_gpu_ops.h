@@ -398,14 +398,17 @@ typedef enum sr_agg_fn_kind {
     SR_AGG_COUNT_STAR = 3, /* COUNT(*) */
     SR_AGG_AVG = 4,
     SR_AGG_MIN = 5,
-    SR_AGG_MAX = 6
+    SR_AGG_MAX = 6,
+    /* merge phase of AVG over (sum, count) state columns: `input` = the DOUBLE sum state, `reserved` = slot id of the
+     * BIGINT count state (see sr_agg_two_phase_descs); result = total sum / total count, NULL when the count is 0 */
+    SR_AGG_AVG_MERGE = 7
 } sr_agg_fn_kind;
 
 typedef struct sr_agg_fn {
     int32_t kind;       /* sr_agg_fn_kind */
     int32_t input_type; /* sr_type of the argument (decides the result type, sum.h:24-34) */
     int32_t out_slot;   /* slot id of the result column */
-    int32_t reserved;
+    int32_t reserved;   /* SR_AGG_AVG_MERGE: slot id of the count state column; otherwise 0 */
     sr_expr input; /* argument expression over the input chunk's slots (ignored for COUNT_STAR) */
 } sr_agg_fn;
 
@@ -449,6 +452,35 @@ int32_t sr_agg_reset(sr_agg* agg);
  * distributed aggregate (AggregateFunction::merge, be/src/exprs/agg/aggregate.h:365-445).
  * Both handles must have been created from the same desc on the same context. */
 int32_t sr_agg_merge(sr_agg* agg, sr_agg* other);
+
+/* ---------------------------------------------------------------------------------------
+ * two-phase / streaming aggregation: AggregateStreamingSinkOperator
+ * (be/src/exec/pipeline/aggregate/aggregate_streaming_sink_operator.cpp:80-372) is the FIRST phase of a distributed
+ * aggregate: it pre-aggregates what it can and hands rows on in the INTERMEDIATE format (group-by columns + one state per
+ * function, AggregateFunction::convert_to_serialize_format / serialize_to_column), which the second phase merges
+ * (AggregateFunction::merge).  Here the intermediate format is a plain chunk:
+ *      SUM -> its running sum (result type, NULL while no non-NULL input was seen)      slot out_slot
+ *      COUNT / COUNT(*) -> BIGINT count                                                  slot out_slot
+ *      MIN / MAX -> the value (input type, nullable)                                     slot out_slot
+ *      AVG -> DOUBLE sum (slot out_slot) + BIGINT count (slot SR_AGG_STATE_SLOT(out_slot))
+ * sr_agg_two_phase_descs derives, from the single-phase desc of a query, the desc of the first phase (AVG split into
+ * SUM(double) + COUNT; its sr_agg_pull output IS the intermediate chunk) and of the merge phase (SUM of sums / counts,
+ * MIN of MINs, SR_AGG_AVG_MERGE), whose result equals the single-phase result.  SR_ERR_NOT_SUPPORTED when a state would be
+ * 128 bits wide (decimal / LARGEINT sums) or the first phase would need more than SR_MAX_AGG_FNS functions.
+ * sr_agg_convert_to_states is the pass-through leg (Aggregator::output_chunk_by_streaming, aggregator.cpp:1071-1120): the
+ * rows of `chunk` become intermediate rows one to one (no hash table involved); `agg` must be a first-phase handle; the
+ * output columns are device buffers owned by the handle, valid until its next call.
+ * The adaptive choice between the two legs (the AUTO state machine) lives in the operator:
+ * starrocks_b200/host/gpu/gpu_operators.h GpuAggregateStreamingSinkOperator.
+ * ------------------------------------------------------------------------------------- */
+#define SR_AGG_STATE_SLOT(out_slot) ((out_slot) | 0x40000000)
+int32_t sr_agg_two_phase_descs(const sr_agg_desc* desc, sr_agg_desc* phase1, sr_agg_desc* phase2);
+/* groups in the table right now (before sink_finish; synchronises on a counter): what the AUTO mode compares with the rows
+ * it has fed to decide whether pre-aggregation still pays (Aggregator::should_expand_preagg_hash_tables,
+ * aggregator.cpp:1241-1290).  0 for dense tables and aggregates without GROUP BY (bounded: always worth keeping);
+ * negative = sr_status. */
+int64_t sr_agg_current_groups(sr_agg* agg);
+int32_t sr_agg_convert_to_states(sr_agg* agg, const sr_chunk_view* chunk, sr_chunk_out* out);
 
 /* Element-wise mergeable view of a DENSE aggregate table (group-by columns with declared ranges, or no
  * GROUP BY): one array per state component, every array indexed by the same slot number on every

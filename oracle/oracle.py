@@ -93,6 +93,7 @@ def lib():
         "orc_agg_out_type": (i32, [vp, i32]),
         "orc_agg_num_out_cols": (i32, [vp]),
         "orc_agg_merge": (i32, [vp, vp]),
+        "orc_agg_convert_to_states": (i32, [vp, vp, vp, vp]),
         "orc_hash_partition": (i32, [vp, vp, vp, vp, vp, vp]),
         "orc_fragment_run": (i32, [vp, vp, i32, vp, vp]),
         "orc_rf_create": (vp, [i32, i64, i32]),
@@ -309,6 +310,25 @@ class Agg:
         pn = (C.c_void_p * max(1, nc))(*[x.ctypes.data for x in nulls])
         _check(lib().orc_agg_output(self.h, pd, pn))
         return list(zip(types, outs, nulls))
+
+
+def convert_to_states(first_phase_desc, chunk):
+    """pass-through leg of the streaming aggregate -> list of (slot, type, data, nulls_or_None): group-by columns of the
+    chunk as they are, then one state column per function (orc_agg_convert_to_states)"""
+    d = first_phase_desc
+    n = chunk.num_rows
+    cols = {s: (t, a, nl) for (s, a, nl), t in zip(chunk.columns(), chunk.types)}
+    res = [(d.group_slots[k],) + cols[d.group_slots[k]] for k in range(d.num_group_keys)]
+    types = [abi.agg_result_type(d.fns[f].kind, d.fns[f].input_type) for f in range(d.num_fns)]
+    outs = [_alloc_col(t, n) for t in types]
+    nulls = [np.zeros(n, dtype=np.uint8) for _ in types]
+    pd = (C.c_void_p * max(1, d.num_fns))(*[o.ctypes.data for o in outs])
+    pn = (C.c_void_p * max(1, d.num_fns))(*[x.ctypes.data for x in nulls])
+    _check(lib().orc_agg_convert_to_states(C.byref(d), chunk.ref(), pd, pn))
+    for f in range(d.num_fns):
+        countlike = d.fns[f].kind in (abi.AGG_COUNT, abi.AGG_COUNT_STAR)
+        res.append((d.fns[f].out_slot, types[f], outs[f], None if countlike else nulls[f]))
+    return res
 
 
 def hash_partition(part_desc, chunk):

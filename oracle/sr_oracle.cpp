@@ -1304,6 +1304,7 @@ static int32_t agg_result_type(const sr_agg_fn& f) {
     case SR_AGG_COUNT_STAR:
         return SR_TYPE_BIGINT;
     case SR_AGG_AVG:
+    case SR_AGG_AVG_MERGE:
         return SR_TYPE_DOUBLE; // AvgResultTrait<arithmetic> (avg.h:33-36)
     case SR_AGG_SUM:           // SumResultLT (sum.h:24-34)
         if (is_float_class(f.input_type)) return SR_TYPE_DOUBLE;
@@ -1509,6 +1510,20 @@ static int32_t agg_push_range(orc_agg* a, const sr_chunk_view* c, int64_t r0, in
         ExprVal v;
         int32_t rc = eval_expr_range(&fn.input, c, r0, n, &v);
         if (rc) return rc;
+        if (fn.kind == SR_AGG_AVG_MERGE) { // AvgAggregateFunction::merge (avg.h:105-118): sum += sum state, count += count state
+            const sr_col_view* cc = find_col(c, fn.reserved);
+            if (!cc || !v.is_double) return fail(SR_ERR_INVALID_ARGUMENT, "AVG_MERGE needs a DOUBLE sum state and a count state column");
+            for (int64_t i = 0; i < n; i++) {
+                if (v.nul[i] || (cc->nulls && cc->nulls[r0 + i])) continue;
+                const int64_t cnt = load_int(cc->data, cc->type, r0 + i);
+                if (cnt == 0) continue;
+                FnState& s = a->states[(size_t)gidx[i] * nf + f];
+                s.dsum += v.dv[i];
+                s.count += cnt;
+                s.has = true;
+            }
+            continue;
+        }
         for (int64_t i = 0; i < n; i++) {
             if (v.nul[i]) continue; // NullableAggregateFunction skips NULL inputs
             FnState& s = a->states[(size_t)gidx[i] * nf + f];
@@ -1583,7 +1598,7 @@ extern "C" int32_t orc_agg_output(orc_agg* a, void** out_data, uint8_t** out_nul
             bool nul = false;
             if (fn.kind == SR_AGG_COUNT || fn.kind == SR_AGG_COUNT_STAR) {
                 ((int64_t*)out_data[col])[g] = s.count;
-            } else if (fn.kind == SR_AGG_AVG) {
+            } else if (fn.kind == SR_AGG_AVG || fn.kind == SR_AGG_AVG_MERGE) {
                 nul = !s.has || s.count == 0;
                 ((double*)out_data[col])[g] = nul ? 0.0 : s.dsum / (double)s.count; // avg.h:218-236
             } else if (rt == SR_TYPE_DOUBLE) {
@@ -1597,6 +1612,48 @@ extern "C" int32_t orc_agg_output(orc_agg* a, void** out_data, uint8_t** out_nul
                 store_int(out_data[col], rt, g, nul ? (i128)0 : s.isum);
             }
             if (out_nulls && out_nulls[col]) out_nulls[col][g] = nul ? 1 : 0;
+        }
+    }
+    return SR_OK;
+}
+
+// Aggregator::output_chunk_by_streaming (aggregator.cpp:1071-1120) -> AggregateFunction::convert_to_serialize_format:
+// every input row becomes one intermediate row.  SUM (sum.h:118-126) / MIN / MAX (maxmin.h) states are the input value in
+// the result type (NULL stays NULL), COUNT (count.h:84-99) is 1 for a non-NULL input and 0 otherwise, COUNT(*) is 1.
+// out_data / out_nulls: one buffer per function (chunk->num_rows elements of the result type); the group-by columns are
+// the input columns themselves.
+extern "C" int32_t orc_agg_convert_to_states(const sr_agg_desc* d, const sr_chunk_view* c, void** out_data, uint8_t** out_nulls) {
+    const int64_t n = c->num_rows;
+    for (int f = 0; f < d->num_fns; f++) {
+        const sr_agg_fn& fn = d->fns[f];
+        if (fn.kind == SR_AGG_AVG || fn.kind == SR_AGG_AVG_MERGE) return fail(SR_ERR_INVALID_ARGUMENT, "first-phase desc expected (AVG is split into SUM + COUNT)");
+        const int32_t rt = agg_result_type(fn);
+        if (type_width(rt) > 8) return fail(SR_ERR_NOT_SUPPORTED, "128-bit states in the intermediate format");
+        if (fn.kind == SR_AGG_COUNT_STAR) {
+            for (int64_t i = 0; i < n; i++) ((int64_t*)out_data[f])[i] = 1;
+            continue;
+        }
+        for (int64_t r0 = 0; r0 < n; r0 += ORC_CHUNK_SIZE) {
+            const int64_t m = std::min<int64_t>(ORC_CHUNK_SIZE, n - r0);
+            ExprVal v;
+            int32_t rc = eval_expr_range(&fn.input, c, r0, m, &v);
+            if (rc) return rc;
+            for (int64_t i = 0; i < m; i++) {
+                if (fn.kind == SR_AGG_COUNT) {
+                    ((int64_t*)out_data[f])[r0 + i] = v.nul[i] ? 0 : 1;
+                    continue;
+                }
+                if (out_nulls && out_nulls[f]) out_nulls[f][r0 + i] = v.nul[i] ? 1 : 0;
+                if (v.is_double) {
+                    const double x = v.nul[i] ? 0.0 : v.dv[i];
+                    if (rt == SR_TYPE_FLOAT)
+                        ((float*)out_data[f])[r0 + i] = (float)x;
+                    else
+                        ((double*)out_data[f])[r0 + i] = x;
+                } else {
+                    store_int(out_data[f], rt, r0 + i, v.nul[i] ? (i128)0 : (i128)v.iv[i]);
+                }
+            }
         }
     }
     return SR_OK;
@@ -1619,6 +1676,7 @@ extern "C" int32_t orc_agg_merge(orc_agg* a, const orc_agg* o) {
                 r.dsum += s.dsum;
                 break;
             case SR_AGG_AVG:
+            case SR_AGG_AVG_MERGE:
                 r.dsum += s.dsum;
                 r.count += s.count;
                 break;

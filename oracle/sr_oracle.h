@@ -139,6 +139,8 @@ int32_t orc_agg_out_type(const orc_agg* a, int32_t k);
 int32_t orc_agg_num_out_cols(const orc_agg* a);
 /* AggregateFunction::merge of another aggregator's states */
 int32_t orc_agg_merge(orc_agg* a, const orc_agg* other);
+/* pass-through leg of the streaming aggregate: rows -> intermediate rows (Aggregator::output_chunk_by_streaming) */
+int32_t orc_agg_convert_to_states(const sr_agg_desc* first_phase_desc, const sr_chunk_view* chunk, void** out_data, uint8_t** out_nulls);
 
 /* ---- exchange partitioning ---------------------------------------------------------- */
 /* ExchangeSinkOperator hash + Shuffler::exchange_shuffle + counting sort

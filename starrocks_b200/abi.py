@@ -53,7 +53,7 @@ EX_EQ, EX_NE, EX_LT, EX_LE, EX_GT, EX_GE, EX_AND, EX_OR, EX_NOT, EX_IS_NULL, EX_
 JOIN_INNER, JOIN_LEFT_OUTER, JOIN_LEFT_SEMI, JOIN_LEFT_ANTI = 0, 1, 2, 3
 JOIN_METHOD_NONE, JOIN_METHOD_DIRECT_MAPPING, JOIN_METHOD_RANGE_DIRECT_MAPPING, JOIN_METHOD_LINEAR_CHAINED = 0, 1, 2, 3
 
-AGG_SUM, AGG_COUNT, AGG_COUNT_STAR, AGG_AVG, AGG_MIN, AGG_MAX = 1, 2, 3, 4, 5, 6
+AGG_SUM, AGG_COUNT, AGG_COUNT_STAR, AGG_AVG, AGG_MIN, AGG_MAX, AGG_AVG_MERGE = 1, 2, 3, 4, 5, 6, 7
 
 HASH_FNV, HASH_CRC32 = 0, 1
 REDUCE_MULHI, REDUCE_MODULO = 0, 1
@@ -346,11 +346,71 @@ def make_part_desc(part_slots, num_channels, hash_fn=HASH_FNV, reduce_op=REDUCE_
     return d
 
 
+def agg_state_slot(out_slot):
+    """SR_AGG_STATE_SLOT: slot of the second state column of a function (AVG: the count)"""
+    return out_slot | 0x40000000
+
+
+def two_phase_descs(desc):
+    """Python statement of sr_agg_two_phase_descs (include/sr_gpu_ops.h): single-phase desc -> (first phase, merge phase).
+    AVG(x) becomes SUM(double(x)) + COUNT(x) in the first phase and AVG_MERGE(sum, count) in the merge phase; counts are
+    summed, sums summed, MIN / MAX re-applied.  Raises NotImplementedError where the C function returns
+    SR_ERR_NOT_SUPPORTED (128-bit states, more than SR_MAX_AGG_FNS first-phase functions)."""
+    p1, p2 = sr_agg_desc(), sr_agg_desc()
+    C.memmove(C.byref(p1), C.byref(desc), C.sizeof(sr_agg_desc))
+    C.memmove(C.byref(p2), C.byref(desc), C.sizeof(sr_agg_desc))
+    for f in range(SR_MAX_AGG_FNS):
+        C.memset(C.byref(p1.fns[f]), 0, C.sizeof(sr_agg_fn))
+    n1 = 0
+
+    def state_col(slot):
+        e = sr_expr()
+        e.nodes[0].op, e.nodes[0].slot_id, e.num_nodes = EX_COL, slot, 1
+        return e
+    float_class = (TYPE_FLOAT, TYPE_DOUBLE)
+    for f in range(desc.num_fns):
+        fn = desc.fns[f]
+        m = sr_agg_fn()
+        m.out_slot = fn.out_slot
+        if fn.kind == AGG_AVG_MERGE:
+            raise ValueError("already a merge phase")
+        if fn.kind not in (AGG_COUNT, AGG_COUNT_STAR, AGG_AVG) and TYPE_WIDTH[agg_result_type(fn.kind, fn.input_type)] > 8:
+            raise NotImplementedError("128-bit states")
+        if n1 + (2 if fn.kind == AGG_AVG else 1) > SR_MAX_AGG_FNS:
+            raise NotImplementedError("too many first-phase functions")
+        if fn.kind == AGG_AVG:
+            C.memmove(C.byref(p1.fns[n1]), C.byref(fn), C.sizeof(sr_agg_fn))
+            s1 = p1.fns[n1]
+            s1.kind, s1.reserved = AGG_SUM, 0
+            if fn.input_type not in float_class:
+                s1.input.nodes[s1.input.num_nodes].op = EX_TO_DOUBLE
+                s1.input.num_nodes += 1
+                s1.input_type = TYPE_DOUBLE
+            C.memmove(C.byref(p1.fns[n1 + 1]), C.byref(fn), C.sizeof(sr_agg_fn))
+            c1 = p1.fns[n1 + 1]
+            c1.kind, c1.reserved, c1.out_slot = AGG_COUNT, 0, agg_state_slot(fn.out_slot)
+            n1 += 2
+            m.kind, m.input_type, m.input, m.reserved = AGG_AVG_MERGE, TYPE_DOUBLE, state_col(fn.out_slot), agg_state_slot(fn.out_slot)
+        else:
+            C.memmove(C.byref(p1.fns[n1]), C.byref(fn), C.sizeof(sr_agg_fn))
+            n1 += 1
+            m.input = state_col(fn.out_slot)
+            if fn.kind in (AGG_COUNT, AGG_COUNT_STAR):
+                m.kind, m.input_type = AGG_SUM, TYPE_BIGINT
+            elif fn.kind == AGG_SUM:
+                m.kind, m.input_type = AGG_SUM, agg_result_type(fn.kind, fn.input_type)
+            else:
+                m.kind, m.input_type = fn.kind, fn.input_type
+        C.memmove(C.byref(p2.fns[f]), C.byref(m), C.sizeof(sr_agg_fn))
+    p1.num_fns = n1
+    return p1, p2
+
+
 def agg_result_type(kind, input_type):
     """SumResultLT / AvgResultLT (be/src/exprs/agg/sum.h:24-34, avg.h:27-47)."""
     if kind in (AGG_COUNT, AGG_COUNT_STAR):
         return TYPE_BIGINT
-    if kind == AGG_AVG:
+    if kind in (AGG_AVG, AGG_AVG_MERGE):
         return TYPE_DOUBLE
     if kind == AGG_SUM:
         if input_type in (TYPE_FLOAT, TYPE_DOUBLE):

@@ -44,7 +44,7 @@ struct AggFnDev {
     int32_t in_is_double;
     int32_t track_n; // accn holds the non-null input count (else it equals cnt_star)
     int32_t result_type;
-    int32_t pad;
+    int32_t n_value_id; // SR_AGG_AVG_MERGE: value id of the count state column added to accn (-1: every non-NULL input counts 1)
     long long* acc0;
     long long* acc1;
     long long* accn;
@@ -376,12 +376,18 @@ __device__ __forceinline__ void agg_apply_row(const AggDev& a, const AccPtrs& p,
         int64_t bits;
         const bool nul = eval_expr(fn.input, ld, bits);
         if (nul) continue;
+        unsigned long long nadd = 1ull;
+        if (fn.n_value_id >= 0) { // AVG_MERGE: the state row stands for `count` inputs
+            int64_t c;
+            nadd = ld.load(fn.n_value_id, c) ? 0ull : (unsigned long long)c;
+            if (nadd == 0) continue;
+        }
         if (SHARED) {
             acc_apply_shared(fn.mode, p.acc0[f], p.acc1[f], slot, bits);
-            if (fn.track_n) red_shared_add_u64(p.accn[f] + slot, 1ull);
+            if (fn.track_n) red_shared_add_u64(p.accn[f] + slot, nadd);
         } else {
             acc_apply(fn.mode, p.acc0[f], p.acc1[f], slot, bits);
-            if (fn.track_n) atomicAdd((unsigned long long*)p.accn[f] + slot, 1ull);
+            if (fn.track_n) atomicAdd((unsigned long long*)p.accn[f] + slot, nadd);
         }
     }
 }
@@ -744,7 +750,13 @@ __device__ __forceinline__ void single_acc_row(const AggDev& a, SingleAcc& s, Lo
         if (fn.mode == M_COUNT_STAR) continue;
         int64_t bits;
         if (eval_expr(fn.input, ld, bits)) continue;
-        s.accn[f]++;
+        if (fn.n_value_id >= 0) { // AVG_MERGE
+            int64_t c;
+            if (ld.load(fn.n_value_id, c) || c == 0) continue;
+            s.accn[f] += c;
+        } else {
+            s.accn[f]++;
+        }
         switch (fn.mode) {
         case M_COUNT:
             s.acc[f]++;
@@ -963,6 +975,50 @@ __device__ __forceinline__ void store_int_typed(void* dst, int32_t width, long l
     }
 }
 
+// pass-through leg of the streaming (first-phase) aggregate: row i of the input becomes intermediate row i
+// (Aggregator::output_chunk_by_streaming -> AggregateFunction::convert_to_serialize_format): SUM / MIN / MAX states are the
+// evaluated input in the function's result type, COUNT states are 1 / 0, COUNT(*) is 1.
+struct ConvertCol {
+    void* data;
+    uint8_t* nulls;
+    int32_t width;
+    int32_t type;
+};
+struct ConvertArgs {
+    ConvertCol c[SR_MAX_AGG_FNS];
+};
+__global__ void __launch_bounds__(256) k_agg_convert_states(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, int64_t n, ConvertArgs ca) {
+    const AggDev& a = *ad;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        ChunkLoader ld{vt, row};
+#pragma unroll 1
+        for (int f = 0; f < a.num_fns; f++) {
+            const AggFnDev& fn = a.fns[f];
+            const ConvertCol& c = ca.c[f];
+            if (fn.mode == M_COUNT_STAR) {
+                ((long long*)c.data)[row] = 1;
+                continue;
+            }
+            int64_t bits;
+            const bool nul = eval_expr(fn.input, ld, bits);
+            if (fn.mode == M_COUNT) {
+                ((long long*)c.data)[row] = nul ? 0 : 1;
+                continue;
+            }
+            if (c.nulls) c.nulls[row] = nul ? 1 : 0;
+            if (nul) bits = 0;
+            if (fn.in_is_double) {
+                if (c.type == SR_TYPE_FLOAT)
+                    ((float*)c.data)[row] = (float)__longlong_as_double(bits);
+                else
+                    ((double*)c.data)[row] = __longlong_as_double(bits);
+            } else {
+                store_int_typed(c.data, c.width, row, bits);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(EMIT_BLOCK) k_agg_emit(const AggDev* __restrict__ ad, unsigned long long total, const uint64_t* __restrict__ block_offsets,
                                                           EmitArgs ea) {
     __shared__ uint32_t s_scan[EMIT_BLOCK / 32 + 1];
@@ -1078,6 +1134,7 @@ struct sr_agg {
     std::vector<PinnedBuf> host_bufs; // host-memory pull: page-locked, the D2H copies are plain DMA
     int32_t out_types[SR_MAX_GROUP_KEYS + SR_MAX_AGG_FNS];
     bool out_has_nulls[SR_MAX_GROUP_KEYS + SR_MAX_AGG_FNS];
+    std::vector<DevBuf> conv_bufs; // sr_agg_convert_to_states: (data, nulls) per function
 };
 
 static int32_t agg_result_type(const sr_agg_fn& f) {
@@ -1086,6 +1143,7 @@ static int32_t agg_result_type(const sr_agg_fn& f) {
     case SR_AGG_COUNT_STAR:
         return SR_TYPE_BIGINT;
     case SR_AGG_AVG:
+    case SR_AGG_AVG_MERGE:
         return SR_TYPE_DOUBLE;
     case SR_AGG_SUM:
         if (srd::is_float_class(f.input_type)) return SR_TYPE_DOUBLE;
@@ -1106,7 +1164,7 @@ static int32_t agg_validate_desc(sr_ctx* ctx, const sr_agg_desc* d) {
     }
     for (int f = 0; f < d->num_fns; f++) {
         const sr_agg_fn& fn = d->fns[f];
-        if (fn.kind < SR_AGG_SUM || fn.kind > SR_AGG_MAX) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "aggregate kind %d", fn.kind);
+        if (fn.kind < SR_AGG_SUM || fn.kind > SR_AGG_AVG_MERGE) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "aggregate kind %d", fn.kind);
         if (fn.kind != SR_AGG_COUNT_STAR && srd::type_width(fn.input_type) == 0) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "aggregate input type %d", fn.input_type);
         if (fn.kind == SR_AGG_AVG && (srd::is_decimal(fn.input_type) || srd::type_width(fn.input_type) > 8))
             return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "AVG on decimal / largeint");
@@ -1213,6 +1271,7 @@ static int32_t agg_compile(sr_agg* a, slot_type_fn tf, agg_nullable_fn nf, void*
         fd.kind = fn.kind;
         fd.result_type = agg_result_type(fn);
         fd.track_n = 0;
+        fd.n_value_id = -1;
         if (fn.kind == SR_AGG_COUNT_STAR) {
             fd.mode = srd::M_COUNT_STAR;
             continue;
@@ -1248,6 +1307,18 @@ static int32_t agg_compile(sr_agg* a, slot_type_fn tf, agg_nullable_fn nf, void*
                 fd.input.result_is_double = 1;
             }
             break;
+        case SR_AGG_AVG_MERGE: { // merge phase of AVG: acc0 += sum state, accn += count state (AvgAggregateFunction::merge, avg.h:105-118)
+            if (!dbl) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "fn %d: AVG_MERGE needs a DOUBLE sum state", f);
+            const int32_t ct = tf(user, fn.reserved);
+            if (ct == 0) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "fn %d: AVG_MERGE count state slot %d is not in the chunk", f, fn.reserved);
+            if (srd::is_float_class(ct) || srd::type_width(ct) > 8) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "fn %d: AVG_MERGE count state must be an integer column", f);
+            const int id = a->reg.add(fn.reserved, ct);
+            if (id >= SR_MAX_VALUES) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "too many distinct columns");
+            fd.mode = srd::M_AVG;
+            fd.n_value_id = id;
+            fd.track_n = 1;
+            break;
+        }
         case SR_AGG_MIN:
             fd.mode = dbl ? srd::M_MIN_F64 : srd::M_MIN_I64;
             break;
@@ -1528,7 +1599,9 @@ static int32_t agg_push_vtab(sr_agg* a, const VTab& vt, int64_t n) {
         const char* e_table = getenv("SR_AGG_PARTITION_MIN_TABLE_BYTES");
         const int64_t min_rows = e_rows ? atoll(e_rows) : kPartitionedMinRows;
         const uint64_t min_table = e_table ? (uint64_t)atoll(e_table) : kPartitionedTableBytes;
-        if (n >= min_rows && (h.cap + 1) * agg_slot_bytes(h) > min_table) return agg_push_partitioned(a, vt, n);
+        bool merge_fns = false; // the staged rows of the partitioned push carry one value per function, not (sum, count)
+        for (int f = 0; f < h.num_fns; f++) merge_fns |= h.fns[f].n_value_id >= 0;
+        if (!merge_fns && n >= min_rows && (h.cap + 1) * agg_slot_bytes(h) > min_table) return agg_push_partitioned(a, vt, n);
     }
     if ((uint64_t)a->ngroups_host + (uint64_t)n <= h.limit) {
         // cannot overflow: single fused pass

@@ -769,6 +769,143 @@ int32_t sr_agg_dense_state(sr_agg* a, sr_agg_state_array* arrays, int32_t max_ar
     return SR_OK;
 }
 
+// ---- two-phase / streaming aggregation ----
+int32_t sr_agg_two_phase_descs(const sr_agg_desc* d, sr_agg_desc* p1, sr_agg_desc* p2) {
+    if (!d || !p1 || !p2) return SR_ERR_INVALID_ARGUMENT;
+    if (d->num_group_keys < 0 || d->num_group_keys > SR_MAX_GROUP_KEYS || d->num_fns < 0 || d->num_fns > SR_MAX_AGG_FNS) return SR_ERR_INVALID_ARGUMENT;
+    *p1 = *d;
+    *p2 = *d;
+    p1->num_fns = 0;
+    const auto state_col = [](int32_t slot) {
+        sr_expr e;
+        memset(&e, 0, sizeof(e));
+        e.nodes[0].op = SR_EX_COL;
+        e.nodes[0].slot_id = slot;
+        e.num_nodes = 1;
+        return e;
+    };
+    for (int f = 0; f < d->num_fns; f++) {
+        const sr_agg_fn& fn = d->fns[f];
+        sr_agg_fn& m = p2->fns[f];
+        memset(&m, 0, sizeof(m));
+        m.out_slot = fn.out_slot;
+        if (fn.kind == SR_AGG_AVG_MERGE) return SR_ERR_INVALID_ARGUMENT; // already a merge phase
+        if (fn.kind != SR_AGG_COUNT && fn.kind != SR_AGG_COUNT_STAR && fn.kind != SR_AGG_AVG && srd::type_width(agg_result_type(fn)) > 8)
+            return SR_ERR_NOT_SUPPORTED; // 128-bit states (decimal / LARGEINT sums) cannot be read back as an input column yet
+        if (p1->num_fns + (fn.kind == SR_AGG_AVG ? 2 : 1) > SR_MAX_AGG_FNS) return SR_ERR_NOT_SUPPORTED;
+        if (fn.kind == SR_AGG_AVG) {
+            // first phase: SUM(double(x)) + COUNT(x)  (the two halves of AvgAggregateState, avg.h:62-66)
+            sr_agg_fn& s1 = p1->fns[p1->num_fns++];
+            s1 = fn;
+            s1.kind = SR_AGG_SUM;
+            s1.reserved = 0;
+            if (!srd::is_float_class(fn.input_type)) {
+                if (s1.input.num_nodes >= SR_MAX_EXPR_NODES) return SR_ERR_NOT_SUPPORTED;
+                s1.input.nodes[s1.input.num_nodes].op = SR_EX_TO_DOUBLE;
+                s1.input.num_nodes++;
+                s1.input_type = SR_TYPE_DOUBLE;
+            }
+            sr_agg_fn& c1 = p1->fns[p1->num_fns++];
+            c1 = fn;
+            c1.kind = SR_AGG_COUNT;
+            c1.reserved = 0;
+            c1.out_slot = SR_AGG_STATE_SLOT(fn.out_slot);
+            m.kind = SR_AGG_AVG_MERGE;
+            m.input_type = SR_TYPE_DOUBLE;
+            m.input = state_col(fn.out_slot);
+            m.reserved = SR_AGG_STATE_SLOT(fn.out_slot);
+            continue;
+        }
+        p1->fns[p1->num_fns++] = fn;
+        m.input = state_col(fn.out_slot);
+        switch (fn.kind) {
+        case SR_AGG_COUNT:
+        case SR_AGG_COUNT_STAR: // counts are summed (CountAggregateFunction::merge, count.h:60-64)
+            m.kind = SR_AGG_SUM;
+            m.input_type = SR_TYPE_BIGINT;
+            break;
+        case SR_AGG_SUM:
+            m.kind = SR_AGG_SUM;
+            m.input_type = agg_result_type(fn); // BIGINT or DOUBLE
+            break;
+        default: // MIN / MAX of the partial extrema
+            m.kind = fn.kind;
+            m.input_type = fn.input_type;
+            break;
+        }
+    }
+    for (int f = p1->num_fns; f < SR_MAX_AGG_FNS; f++) memset(&p1->fns[f], 0, sizeof(sr_agg_fn));
+    return SR_OK;
+}
+
+int64_t sr_agg_current_groups(sr_agg* a) {
+    if (!a) return SR_ERR_INVALID_ARGUMENT;
+    sr_ctx* ctx = a->ctx;
+    SR_BIND(ctx);
+    if (!a->compiled || a->host.dense || a->host.num_keys == 0) return 0;
+    uint64_t ng;
+    int32_t ovf, bad;
+    SR_TRY(agg_read_counters(a, &ng, &ovf, &bad));
+    a->ngroups_host = (int64_t)ng;
+    return (int64_t)ng;
+}
+
+int32_t sr_agg_convert_to_states(sr_agg* a, const sr_chunk_view* chunk, sr_chunk_out* out) {
+    if (!a || !chunk || !out) return SR_ERR_INVALID_ARGUMENT;
+    sr_ctx* ctx = a->ctx;
+    SR_BIND(ctx);
+    const sr_agg_desc& d = a->desc;
+    for (int f = 0; f < d.num_fns; f++)
+        if (d.fns[f].kind == SR_AGG_AVG || d.fns[f].kind == SR_AGG_AVG_MERGE)
+            return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "convert_to_states needs a first-phase desc (sr_agg_two_phase_descs): fn %d is AVG", f);
+    SR_TRY(a->staged.stage(ctx, chunk));
+    if (!a->compiled) SR_TRY(agg_compile(a, staged_slot_type, staged_slot_nullable, &a->staged));
+    VTab vt;
+    SR_TRY(bind_vtab(ctx, a->reg, a->staged, &vt));
+    SR_TRY(agg_check_nullability(a, vt));
+    const int64_t n = chunk->num_rows;
+    const srd::AggDev& h = a->host;
+    if (a->conv_bufs.size() < 2 * (size_t)SR_MAX_AGG_FNS) {
+        std::vector<DevBuf> nb(2 * (size_t)SR_MAX_AGG_FNS);
+        for (size_t i = 0; i < a->conv_bufs.size(); i++) std::swap(nb[i], a->conv_bufs[i]);
+        a->conv_bufs.swap(nb);
+    }
+    out->num_cols = d.num_group_keys + d.num_fns;
+    out->mem = SR_MEM_DEVICE;
+    out->num_rows = n;
+    for (int k = 0; k < d.num_group_keys; k++) { // group-by columns travel as they are (device copies of the staged input)
+        const int c = a->staged.find(d.group_slots[k]);
+        if (c < 0) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "chunk misses group slot %d", d.group_slots[k]);
+        out->cols[k].data = (void*)a->staged.cols[c].data;
+        out->cols[k].nulls = (uint8_t*)a->staged.cols[c].nulls;
+        out->cols[k].type = a->staged.cols[c].type;
+        out->cols[k].slot_id = d.group_slots[k];
+    }
+    srd::ConvertArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    for (int f = 0; f < d.num_fns; f++) {
+        const srd::AggFnDev& fn = h.fns[f];
+        const int32_t type = fn.result_type;
+        const int w = srd::type_width(type);
+        if (w > 8) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "fn %d: 128-bit states in the intermediate format", f);
+        const bool nullable = !(fn.mode == srd::M_COUNT || fn.mode == srd::M_COUNT_STAR);
+        SR_TRY(a->conv_bufs[2 * f].reserve(ctx, (size_t)std::max<int64_t>(n, 1) * w));
+        if (nullable) SR_TRY(a->conv_bufs[2 * f + 1].reserve(ctx, (size_t)std::max<int64_t>(n, 1)));
+        ca.c[f] = srd::ConvertCol{a->conv_bufs[2 * f].p, nullable ? (uint8_t*)a->conv_bufs[2 * f + 1].p : nullptr, w, type};
+        sr_col_out& oc = out->cols[d.num_group_keys + f];
+        oc.data = ca.c[f].data;
+        oc.nulls = ca.c[f].nulls;
+        oc.type = type;
+        oc.slot_id = d.fns[f].out_slot;
+    }
+    if (n > 0 && d.num_fns > 0) {
+        srd::k_agg_convert_states<<<std::min(grid_for(n, 256), ctx->num_sms * 8), 256, 0, ctx->stream>>>((const srd::AggDev*)a->dev.p, vt, n, ca);
+        SR_LAUNCH_CHECK(ctx);
+    }
+    if (chunk->mem != SR_MEM_DEVICE) SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // caller may free host buffers
+    return SR_OK;
+}
+
 int32_t sr_agg_merge(sr_agg* a, sr_agg* o) {
     if (!a || !o) return SR_ERR_INVALID_ARGUMENT;
     sr_ctx* ctx = a->ctx;

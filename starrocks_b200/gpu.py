@@ -88,6 +88,9 @@ def lib():
         "sr_agg_num_groups": (i64, [vp]),
         "sr_agg_pull": (i32, [vp, i64, i32, vp]),
         "sr_agg_merge": (i32, [vp, vp]),
+        "sr_agg_two_phase_descs": (i32, [vp, vp, vp]),
+        "sr_agg_convert_to_states": (i32, [vp, vp, vp]),
+        "sr_agg_current_groups": (i64, [vp]),
         "sr_agg_dense_state": (i32, [vp, vp, i32, vp]),
         "sr_agg_reset": (i32, [vp]),
         "sr_fragment_reset": (i32, [vp]),
@@ -124,7 +127,7 @@ EXPORTED_SYMBOLS = [
     "sr_scan_filter", "sr_scan_evaluate", "sr_join_create", "sr_join_destroy", "sr_join_append_build",
     "sr_join_build_finish", "sr_join_is_build_done", "sr_join_get_info", "sr_join_copy_table", "sr_join_probe",
     "sr_join_probe_indexes", "sr_join_key_hash", "sr_agg_create", "sr_agg_destroy", "sr_agg_push",
-    "sr_agg_sink_finish", "sr_agg_num_groups", "sr_agg_pull", "sr_agg_merge", "sr_agg_dense_state", "sr_agg_reset", "sr_fragment_reset", "sr_fragment_get_plan", "sr_fragment_last_pass_ms",
+    "sr_agg_sink_finish", "sr_agg_num_groups", "sr_agg_pull", "sr_agg_merge", "sr_agg_two_phase_descs", "sr_agg_convert_to_states", "sr_agg_current_groups", "sr_agg_dense_state", "sr_agg_reset", "sr_fragment_reset", "sr_fragment_get_plan", "sr_fragment_last_pass_ms",
     "sr_fragment_create",
     "sr_fragment_destroy", "sr_fragment_push", "sr_fragment_agg", "sr_fragment_rows_passed", "sr_xchg_create",
     "sr_join_build_runtime_filter", "sr_rf_create", "sr_rf_insert", "sr_rf_destroy", "sr_rf_get_info", "sr_rf_copy_directory",
@@ -366,6 +369,15 @@ class Agg:
     def reset(self):
         self.ctx.check(lib().sr_agg_reset(self.h))
 
+    def current_groups(self):
+        return self.ctx.check(lib().sr_agg_current_groups(self.h))
+
+    def convert_to_states(self, chunk):
+        """pass-through leg of the streaming aggregate: rows -> intermediate rows (device chunk owned by the handle)"""
+        out = abi.sr_chunk_out()
+        self.ctx.check(lib().sr_agg_convert_to_states(self.h, chunk.ref(), C.byref(out)))
+        return out
+
     def dense_state(self):
         """[(device_ptr, count, elem_type, reduce)] -- the element-wise mergeable arrays of a dense table"""
         n_max = 1 + 3 * abi.SR_MAX_AGG_FNS
@@ -388,6 +400,27 @@ class Agg:
         self.finish()
         out = self.pull()
         return chunk_out_to_host(self.ctx, out)
+
+
+def two_phase_descs(desc):
+    """sr_agg_two_phase_descs: (first-phase desc, merge-phase desc) of a single-phase aggregate desc"""
+    p1, p2 = abi.sr_agg_desc(), abi.sr_agg_desc()
+    rc = lib().sr_agg_two_phase_descs(C.byref(desc), C.byref(p1), C.byref(p2))
+    if rc != 0:
+        raise GpuError(rc, "sr_agg_two_phase_descs: the aggregate cannot be split into two phases (128-bit states or too many functions)")
+    return p1, p2
+
+
+def chunk_out_as_view(out):
+    """device sr_chunk_out -> abi.Chunk-like object usable as the input of another operator (no copy)"""
+    class _View:
+        pass
+    v = _View()
+    v.view = abi.sr_chunk_view(C.cast(out.cols, C.POINTER(abi.sr_col_view)), out.num_cols, out.mem, out.num_rows)
+    v.num_rows = out.num_rows
+    v._keep = out
+    v.ref = lambda: C.byref(v.view)
+    return v
 
 
 class Fragment:

@@ -452,6 +452,181 @@ private:
 };
 
 // ------------------------------------------------------------------------------------------------------------
+// streaming (first-phase) aggregate: AggregateStreamingSinkOperator / AggregateStreamingSourceOperator
+// (be/src/exec/pipeline/aggregate/aggregate_streaming_{sink,source}_operator.cpp).  The sink pre-aggregates what it can
+// and hands everything else on in the intermediate format; the source drains the chunk buffer and, once the sink is done,
+// the hash table.  The aggregator must be created from the FIRST-PHASE desc of sr_agg_two_phase_descs.
+//
+// AUTO on a GPU works on batches of kGpuBatchChunks chunks, not on single chunks, so the reference's six-state machine
+// (aggregate_streaming_sink_operator.cpp:211-355) is folded into three states driven by the same quantity, the reduction
+// rows_fed / groups (Aggregator::should_expand_preagg_hash_tables, STREAMING_HT_MIN_REDUCTION = 2.0 above 2 MB):
+//   PREAGG        push the batch into the table.  While the table is below max_ht_bytes, or the reduction since the last
+//                 flush is >= 2, stay.  Otherwise flush the table downstream (its groups are emitted as intermediate rows,
+//                 the table is reset) and go to PASS_THROUGH.
+//   PASS_THROUGH  convert batches row by row (sr_agg_convert_to_states) for `pass_through_batches` batches
+//                 (AggrAutoContext::StableLimit), then PROBE.
+//   PROBE         pre-aggregate ONE batch into the empty table (the reference's FORCE_PREAGG: "freshening the hash table
+//                 with new coming rows"): reduction >= 2 -> PREAGG, else flush and PASS_THROUGH again.
+// Dense tables and aggregates without GROUP BY are bounded: always PREAGG.
+// ------------------------------------------------------------------------------------------------------------
+enum class GpuStreamingPreaggMode { AUTO = 0, FORCE_STREAMING = 1, FORCE_PREAGGREGATION = 2 }; // TStreamingPreaggregationMode
+
+class GpuStreamingAggregator {
+public:
+    GpuStreamingAggregator(sr_ctx* ctx, const sr_agg_desc& first_phase_desc, GpuStreamingPreaggMode mode, size_t max_ht_bytes = 64u << 20,
+                           int pass_through_batches = 5)
+            : _ctx(ctx), _desc(first_phase_desc), _mode(mode), _max_ht_bytes(max_ht_bytes), _pass_through_batches(pass_through_batches) {
+        // bytes one group occupies: packed key + COUNT(*) word + one state word per function (+ null tracking)
+        _group_bytes = 16 + 8 + 16 * (size_t)_desc.num_fns;
+    }
+    ~GpuStreamingAggregator() {
+        if (_agg) sr_agg_destroy(_agg);
+    }
+    Status prepare() {
+        if (_agg) return Status::OK();
+        _agg = sr_agg_create(_ctx, &_desc);
+        return _agg ? Status::OK() : sr_to_status(_ctx, sr_last_error_code(_ctx));
+    }
+    // one batch of input rows (host chunks concatenated by the sink)
+    Status process_batch(RuntimeState* state, const sr_chunk_view& v) {
+        const bool bounded = _desc.num_group_keys == 0 || _desc.has_ranges != 0;
+        if (_mode == GpuStreamingPreaggMode::FORCE_STREAMING && !bounded) return _stream(state, v);
+        if (_mode == GpuStreamingPreaggMode::FORCE_PREAGGREGATION || bounded) return _preagg(v);
+        switch (_state) {
+        case PASS_THROUGH:
+            RETURN_IF_ERROR(_stream(state, v));
+            if (++_pass_count >= _pass_through_batches) {
+                _pass_count = 0;
+                _state = PROBE;
+            }
+            return Status::OK();
+        case PROBE:
+        case PREAGG: {
+            RETURN_IF_ERROR(_preagg(v));
+            const int64_t groups = sr_agg_current_groups(_agg);
+            if (groups < 0) return sr_to_status(_ctx, (int32_t)groups);
+            const double reduction = groups > 0 ? (double)_rows_in_table / (double)groups : 1e30;
+            const bool big = (size_t)groups * _group_bytes > _max_ht_bytes;
+            if (_state == PROBE) {
+                if (reduction >= 2.0) {
+                    _state = PREAGG;
+                    return Status::OK();
+                }
+            } else if (!big || reduction >= 2.0) {
+                return Status::OK(); // small table, or pre-aggregation still pays
+            }
+            // low reduction: emit what the table holds and stop building it for a while
+            RETURN_IF_ERROR(flush_table(state));
+            _state = PASS_THROUGH;
+            _num_flushes++;
+            return Status::OK();
+        }
+        }
+        return Status::OK();
+    }
+    // emit every group of the table as intermediate rows and clear it
+    Status flush_table(RuntimeState* state) {
+        RETURN_IF_SR_ERROR(_ctx, sr_agg_sink_finish(_agg));
+        while (true) {
+            sr_chunk_out out;
+            RETURN_IF_SR_ERROR(_ctx, sr_agg_pull(_agg, (int64_t)kGpuBatchChunks * state->chunk_size(), SR_MEM_DEVICE, &out));
+            if (out.num_rows == 0) break;
+            _rows_from_table += (size_t)out.num_rows;
+            RETURN_IF_ERROR(slice_out_to_chunks(_ctx, out, state->chunk_size(), &_buffer));
+        }
+        RETURN_IF_SR_ERROR(_ctx, sr_agg_reset(_agg));
+        _rows_in_table = 0;
+        return Status::OK();
+    }
+    std::deque<ChunkPtr>& buffer() { return _buffer; } // Aggregator::_buffer (offer_chunk_to_buffer / poll_chunk_buffer)
+    void sink_complete() { _sink_complete = true; }
+    bool is_sink_complete() const { return _sink_complete; }
+    size_t rows_streamed() const { return _rows_streamed; }
+    size_t rows_from_table() const { return _rows_from_table; }
+    int num_flushes() const { return _num_flushes; }
+
+private:
+    Status _preagg(const sr_chunk_view& v) {
+        RETURN_IF_SR_ERROR(_ctx, sr_agg_push(_agg, &v));
+        _rows_in_table += (size_t)v.num_rows;
+        return Status::OK();
+    }
+    Status _stream(RuntimeState* state, const sr_chunk_view& v) {
+        sr_chunk_out out;
+        RETURN_IF_SR_ERROR(_ctx, sr_agg_convert_to_states(_agg, &v, &out));
+        _rows_streamed += (size_t)out.num_rows;
+        return slice_out_to_chunks(_ctx, out, state->chunk_size(), &_buffer);
+    }
+    enum AutoState { PREAGG, PASS_THROUGH, PROBE };
+    sr_ctx* _ctx;
+    sr_agg_desc _desc;
+    GpuStreamingPreaggMode _mode;
+    size_t _max_ht_bytes, _group_bytes;
+    int _pass_through_batches;
+    sr_agg* _agg = nullptr;
+    AutoState _state = PREAGG;
+    int _pass_count = 0, _num_flushes = 0;
+    size_t _rows_in_table = 0, _rows_streamed = 0, _rows_from_table = 0;
+    std::deque<ChunkPtr> _buffer;
+    bool _sink_complete = false;
+};
+using GpuStreamingAggregatorPtr = std::shared_ptr<GpuStreamingAggregator>;
+
+class GpuAggregateStreamingSinkOperator final : public Operator {
+public:
+    GpuAggregateStreamingSinkOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, GpuStreamingAggregatorPtr agg)
+            : Operator(f, id, "gpu_aggregate_streaming_sink", plan_node_id, false, seq), _aggregator(std::move(agg)) {}
+    Status prepare(RuntimeState* state) override { return _aggregator->prepare(); }
+    bool has_output() const override { return false; }
+    bool need_input() const override { return !_finished; }
+    bool is_finished() const override { return _finished; }
+    StatusOr<ChunkPtr> pull_chunk(RuntimeState*) override { return Status::InternalError("pull_chunk on a sink"); }
+    Status push_chunk(RuntimeState* state, const ChunkPtr& chunk) override {
+        _batch.append(*chunk);
+        if (_batch.rows() >= (size_t)kGpuBatchChunks * state->chunk_size()) RETURN_IF_ERROR(_flush(state));
+        return Status::OK();
+    }
+    Status set_finishing(RuntimeState* state) override { // aggregate_streaming_sink_operator.cpp:43-66
+        if (_finished) return Status::OK();
+        RETURN_IF_ERROR(_flush(state));
+        RETURN_IF_ERROR(_aggregator->flush_table(state)); // the source outputs the hash table after the buffered chunks
+        _aggregator->sink_complete();
+        _finished = true;
+        return Status::OK();
+    }
+
+private:
+    Status _flush(RuntimeState* state) {
+        if (_batch.empty()) return Status::OK();
+        sr_chunk_view v = _batch.view();
+        RETURN_IF_ERROR(_aggregator->process_batch(state, v));
+        _batch.clear();
+        return Status::OK();
+    }
+    GpuStreamingAggregatorPtr _aggregator;
+    ChunkBatch _batch;
+    bool _finished = false;
+};
+
+class GpuAggregateStreamingSourceOperator final : public SourceOperator {
+public:
+    GpuAggregateStreamingSourceOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, GpuStreamingAggregatorPtr agg)
+            : SourceOperator(f, id, "gpu_aggregate_streaming_source", plan_node_id, false, seq), _aggregator(std::move(agg)) {}
+    bool has_output() const override { return !_aggregator->buffer().empty(); } // aggregate_streaming_source_operator.cpp:30-52
+    bool is_finished() const override { return _aggregator->is_sink_complete() && _aggregator->buffer().empty(); }
+    StatusOr<ChunkPtr> pull_chunk(RuntimeState* state) override {
+        auto& q = _aggregator->buffer();
+        if (q.empty()) return ChunkPtr(nullptr);
+        ChunkPtr c = q.front();
+        q.pop_front();
+        return c;
+    }
+
+private:
+    GpuStreamingAggregatorPtr _aggregator;
+};
+
+// ------------------------------------------------------------------------------------------------------------
 // fused fragment sink: [probe x N -> aggregate sink] collapsed behind one sink operator
 // ------------------------------------------------------------------------------------------------------------
 class GpuFragment {

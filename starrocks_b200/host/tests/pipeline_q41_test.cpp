@@ -11,6 +11,7 @@
 //
 // A and B must give the same groups, and both must match a straightforward row-at-a-time evaluation of the query in
 // this file (the checker).  Exit code 0 = pass.  Needs a CUDA device (run by tests/test_host_pipeline.py -m gpu).
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -378,6 +379,88 @@ int main(int argc, char** argv) {
             rc = 1;
         }
         printf("exchange sink: %zu rows over %d channels, placement and per-channel order verified\n", total, nch);
+    }
+    {
+        // ---- two-phase aggregate: GROUP BY lo_custkey, SUM(lo_revenue), AVG(lo_supplycost), COUNT(*) ----
+        //   first phase:  GpuScanOperator(lineorder) -> GpuAggregateStreamingSinkOperator | ...StreamingSourceOperator ->
+        //   merge phase:  GpuAggregateBlockingSinkOperator(merge desc)                    | ...BlockingSourceOperator -> sink
+        // in the three TStreamingPreaggregationMode settings; AUTO runs with a tiny table budget so that it flushes and
+        // passes through.  lo_custkey has 30 000 values over 1 M rows sorted by nothing: reduction ~33 per full table.
+        struct G {
+            int64_t rev = 0, cost = 0, cnt = 0;
+        };
+        const char* names[3] = {"AUTO", "FORCE_STREAMING", "FORCE_PREAGGREGATION"};
+        // (a) GROUP BY lo_custkey: 30 000 groups over 1 M rows, reduction ~33 -> AUTO keeps pre-aggregating;
+        // (b) GROUP BY lo_custkey, lo_partkey: ~1 M groups, reduction ~1 -> AUTO must flush, pass through and probe again
+        for (int run = 0; run < 4; run++) {
+            const int mode = run < 3 ? run : 0;
+            const bool two_keys = run == 3;
+            sr_agg_desc q{};
+            q.num_group_keys = two_keys ? 2 : 1;
+            q.group_slots[0] = LO_CUSTKEY;
+            q.group_slots[1] = LO_PARTKEY;
+            q.group_types[0] = q.group_types[1] = SR_TYPE_INT;
+            q.num_fns = 3;
+            q.fns[0] = sr_agg_fn{SR_AGG_SUM, SR_TYPE_INT, OUT_REV, 0, col_expr(LO_REVENUE)};
+            q.fns[1] = sr_agg_fn{SR_AGG_AVG, SR_TYPE_INT, OUT_COST, 0, col_expr(LO_SUPPLYCOST)};
+            q.fns[2] = sr_agg_fn{SR_AGG_COUNT_STAR, SR_TYPE_INT, OUT_COST + 1, 0, sr_expr{}};
+            sr_agg_desc p1{}, p2{};
+            if (sr_agg_two_phase_descs(&q, &p1, &p2) != SR_OK) {
+                fprintf(stderr, "sr_agg_two_phase_descs failed\n");
+                return 2;
+            }
+            std::map<std::pair<int32_t, int32_t>, G> want;
+            for (size_t i = 0; i < n_fact; i++) {
+                G& g = want[{lo_cust[i], two_keys ? lo_part[i] : 0}];
+                g.rev += lo_rev[i];
+                g.cost += lo_cost[i];
+                g.cnt++;
+            }
+            sr_scan_desc sd{};
+            std::vector<int32_t> outs = {LO_CUSTKEY, LO_PARTKEY, LO_REVENUE, LO_SUPPLYCOST};
+            sd.out_slots = outs.data();
+            sd.num_out_slots = (int32_t)outs.size();
+            GpuScanOperatorFactory scan_f(30, 30, ctx, sd, {split(lineorder, 4096)});
+            auto streaming = std::make_shared<GpuStreamingAggregator>(ctx, p1, (GpuStreamingPreaggMode)mode, /*max_ht_bytes=*/(size_t)256 << 10,
+                                                                       /*pass_through_batches=*/1);
+            auto final_f = std::make_shared<GpuAggregatorFactory>(ctx, p2);
+            PipelineDriver first({scan_f.create(1, 0), std::make_shared<GpuAggregateStreamingSinkOperator>(nullptr, 31, 31, 0, streaming)});
+            GpuAggregateBlockingSinkOperatorFactory merge_sink_f(33, 33, final_f);
+            PipelineDriver second({std::make_shared<GpuAggregateStreamingSourceOperator>(nullptr, 32, 32, 0, streaming), merge_sink_f.create(1, 0)});
+            run_to_finish(first, &state, "first phase");
+            run_to_finish(second, &state, "merge phase");
+            auto sink = std::make_shared<ResultSink>();
+            PipelineDriver result_driver({std::make_shared<GpuAggregateBlockingSourceOperator>(nullptr, 34, 34, 0, final_f->get_or_create(0)), sink});
+            run_to_finish(result_driver, &state, "two-phase result");
+            size_t groups = 0;
+            bool ok = true;
+            for (auto& c : sink->chunks) {
+                auto* k = (const int32_t*)c->get_column_by_slot_id(LO_CUSTKEY)->raw_data();
+                auto* k2 = two_keys ? (const int32_t*)c->get_column_by_slot_id(LO_PARTKEY)->raw_data() : nullptr;
+                auto* r = (const int64_t*)c->get_column_by_slot_id(OUT_REV)->raw_data();
+                auto* a = (const double*)c->get_column_by_slot_id(OUT_COST)->raw_data();
+                auto* n = (const int64_t*)c->get_column_by_slot_id(OUT_COST + 1)->raw_data();
+                for (size_t i = 0; i < c->num_rows(); i++, groups++) {
+                    auto it = want.find({k[i], k2 ? k2[i] : 0});
+                    const double avg = it == want.end() ? 0 : (double)it->second.cost / (double)it->second.cnt;
+                    ok = ok && it != want.end() && r[i] == it->second.rev && n[i] == it->second.cnt && std::abs(a[i] - avg) <= 1e-9 * avg;
+                }
+            }
+            if (!ok || groups != want.size()) {
+                fprintf(stderr, "two-phase aggregate (%s): %zu groups (want %zu), values %s\n", names[mode], groups, want.size(), ok ? "ok" : "WRONG");
+                rc = 1;
+            }
+            if (two_keys && (streaming->rows_streamed() == 0 || streaming->num_flushes() == 0)) {
+                fprintf(stderr, "AUTO never left pre-aggregation on a low-reduction input\n");
+                rc = 1;
+            }
+            printf("two-phase aggregate %-20s %s: %zu groups; first phase passed %zu rows through, emitted %zu pre-aggregated rows, %d table flushes\n",
+                   names[mode], two_keys ? "(2 keys, reduction ~1)" : "(1 key, reduction ~33)", groups, streaming->rows_streamed(),
+                   streaming->rows_from_table(), streaming->num_flushes());
+            result_driver.close(&state);
+            second.close(&state);
+            first.close(&state);
+        }
     }
     if (results[0] != expect) {
         fprintf(stderr, "per-operator pipeline differs from the checker (%zu vs %zu groups)\n", results[0].size(), expect.size());
