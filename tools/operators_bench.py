@@ -8,6 +8,8 @@ covered by the fused fragment) on HBM-resident chunks, one B200:
   runtime filter                      the same join with its build-side filter (min/max + bloom) attached to the scan:
                                       scan_filter(+filter) then join_probe on the survivors
   sr_agg_push                         no GROUP BY / dense (7 x 25 groups) / hash (1 M groups)
+  two-phase aggregate                 sr_agg_convert_to_states (the streaming first phase's pass-through leg) and first-phase
+                                      push + pull of the intermediate rows + merge-phase push
 Each line: milliseconds (best of N), rows/s and algorithmic GB/s (input columns read + output written).
 """
 import argparse
@@ -130,6 +132,24 @@ def main():
     agg_case("agg_push hash 1 M groups: SUM, COUNT(*)",
              abi.make_agg_desc([1], [abi.TYPE_INT], fns=[(abi.AGG_SUM, abi.TYPE_INT, 10, [("col", 3)]), (abi.AGG_COUNT_STAR, 0, 11, None)]),
              [(1, "gk"), (3, "lo_revenue")], n * 8)
+    # ---- two-phase aggregate: pass-through leg and the merge of pre-aggregated states ----
+    d1 = abi.make_agg_desc([1], [abi.TYPE_INT], fns=[(abi.AGG_SUM, abi.TYPE_INT, 10, [("col", 3)]), (abi.AGG_AVG, abi.TYPE_INT, 11, [("col", 3)]),
+                                                     (abi.AGG_COUNT_STAR, 0, 12, None)])
+    p1, p2 = gpu.two_phase_descs(d1)
+    first, final = gpu.Agg(ctx, p1), gpu.Agg(ctx, p2)
+    ch = abi.Chunk([(1, cols["gk"], None, abi.TYPE_INT), (3, cols["lo_revenue"], None, abi.TYPE_INT)], mem=abi.MEM_DEVICE)
+    report("agg_convert_to_states (pass-through leg): key + SUM, AVG, COUNT(*) states",
+           best_ms(lambda: first.convert_to_states(ch), stream, args.reps), n * 8 + n * (8 + 8 + 8 + 8))
+
+    def first_phase_then_merge():
+        first.reset()
+        first.push(ch)
+        first.finish()
+        final.reset()
+        final.push(gpu.chunk_out_as_view(first.pull(mem=abi.MEM_DEVICE)))
+    report("two-phase hash aggregate, 1 M groups: first-phase push + pull states + merge push", best_ms(first_phase_then_merge, stream, args.reps), n * 8)
+    first.close()
+    final.close()
     print(json.dumps({"rows": n, "operators": out}, indent=1))
 
 
