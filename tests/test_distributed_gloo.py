@@ -62,6 +62,60 @@ def _two_phase_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _intermediate_format_worker(rank, world, port, q):
+    """general two-phase aggregate over the intermediate format (sr_agg_two_phase_descs): AVG / MIN / MAX / COUNT of a
+    nullable column, first phase per rank (half of its rows pre-aggregated, half passed through), state chunks gathered
+    to rank 0 in one collective, merge phase there; equals the single-phase result on the whole table"""
+    from oracle import oracle
+    from starrocks_b200.distributed import all_gather_partial_states
+    from tests.helpers import assert_rows_equal, oracle_rows, rand_nulls
+    _init(rank, world, port)
+    rng = np.random.default_rng(5)
+    n = 60_000
+    key = rng.integers(0, 3000, n, dtype=np.int32)
+    v = rng.integers(-10**6, 10**6, n, dtype=np.int32)
+    vn = rand_nulls(rng, n, 0.3)
+    x = rng.normal(0, 100, n)
+    d = abi.make_agg_desc([0], [abi.TYPE_INT], fns=[(abi.AGG_AVG, abi.TYPE_INT, 10, [("col", 1)]), (abi.AGG_COUNT, abi.TYPE_INT, 11, [("col", 1)]),
+                                                    (abi.AGG_MIN, abi.TYPE_INT, 12, [("col", 1)]), (abi.AGG_MAX, abi.TYPE_DOUBLE, 13, [("col", 2)]),
+                                                    (abi.AGG_SUM, abi.TYPE_DOUBLE, 14, [("col", 2)]), (abi.AGG_COUNT_STAR, 0, 15, None)])
+    p1, p2 = abi.two_phase_descs(d)
+    mine = slice(rank, None, world)
+    k_, v_, vn_, x_ = key[mine].copy(), v[mine].copy(), vn[mine].copy(), x[mine].copy()
+    half = len(k_) // 2
+    pre = oracle.Agg(p1)
+    pre.push(Chunk([(0, k_[:half].copy(), None), (1, v_[:half].copy(), vn_[:half].copy()), (2, x_[:half].copy(), None)]))
+    slots = [p1.group_slots[0]] + [p1.fns[f].out_slot for f in range(p1.num_fns)]
+    a = [(s, t, dd, nl) for s, (t, dd, nl) in zip(slots, pre.output())]
+    b = oracle.convert_to_states(p1, Chunk([(0, k_[half:].copy(), None), (1, v_[half:].copy(), vn_[half:].copy()), (2, x_[half:].copy(), None)]))
+    # ship every column as int64 words (doubles bit-cast) plus its null bytes
+    cols = []
+    for (s, t, da, na), (_, _, db, nb) in zip(a, b):
+        data = np.concatenate([np.asarray(da), np.asarray(db)])
+        bits = data.view(np.int64) if data.dtype == np.float64 else data.astype(np.int64)
+        nul = np.concatenate([np.zeros(len(da), np.uint8) if na is None else na, np.zeros(len(db), np.uint8) if nb is None else nb])
+        cols += [torch.from_numpy(np.ascontiguousarray(bits)), torch.from_numpy(nul.astype(np.int64))]
+    packed = all_gather_partial_states(cols, max_rows=len(k_), dst=0)
+    if rank == 0:
+        final = oracle.Agg(p2)
+        chunk_cols = []
+        for i, (s, t, _, _) in enumerate(a):
+            bits = packed[2 * i].numpy()
+            data = bits.view(np.float64).copy() if t == abi.TYPE_DOUBLE else bits.astype(abi.TYPE_NUMPY[t])
+            chunk_cols.append((s, np.ascontiguousarray(data), packed[2 * i + 1].numpy().astype(np.uint8), t))
+        final.push(Chunk(chunk_cols))
+        whole = oracle.Agg(d)
+        whole.push(Chunk([(0, key, None), (1, v, vn), (2, x, None)]))
+        try:
+            assert_rows_equal(oracle_rows(final), oracle_rows(whole), float_cols=(1, 5))
+            q.put(True)
+        except AssertionError as e:
+            print(e)
+            q.put(False)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def _shuffle_worker(rank, world, port, q):
     from oracle import oracle
     from starrocks_b200.distributed import exchange_partitions, gather_partial_states
@@ -98,7 +152,7 @@ def _shuffle_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("worker", [_two_phase_worker, _shuffle_worker])
+@pytest.mark.parametrize("worker", [_two_phase_worker, _intermediate_format_worker, _shuffle_worker])
 def test_world_size_2_gloo(oracle, worker):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -103,6 +103,63 @@ def test_avg_merge_known_answer(oracle):
     assert oracle_rows(final) == [(7, 3.0, 3), (8, None, 0)]
 
 
+# be/test/exprs/agg/aggregate_test.cpp:47-59 (count), :61-83 (sum), :115-132 (avg), :669-686 (max), :705-722 (min) through
+# test_agg_function (base_aggregate_test.h:83-113,203-238): state1 = update(column1 = {0..1023, 100, 200}), state2 =
+# update(column2 = {2000..2999}), then state1 is SERIALISED and MERGED into state2.  Expected (result1, result2, merged):
+REFERENCE_MERGE_VECTORS = {
+    abi.AGG_COUNT: (1026, 1000, 2026),
+    abi.AGG_SUM: (524076, 2499500, 3023576),
+    abi.AGG_AVG: (524076 / 1026.0, 2499500 / 1000.0, 3023576 / 2026.0),
+    abi.AGG_MAX: (1023, 2999, 2999),
+    abi.AGG_MIN: (0, 2000, 0),
+}
+REFERENCE_MERGE_TYPES = [(np.int16, abi.TYPE_SMALLINT), (np.int32, abi.TYPE_INT), (np.int64, abi.TYPE_BIGINT), (np.float32, abi.TYPE_FLOAT),
+                         (np.float64, abi.TYPE_DOUBLE)]
+
+
+def _reference_merge_case(kind, dtype, typ):
+    col1 = np.concatenate([np.arange(1024), [100, 200]]).astype(dtype)
+    col2 = np.arange(2000, 3000).astype(dtype)
+    d = abi.make_agg_desc(fns=[(kind, typ, 9, [("col", 0)])])
+    return d, Chunk([(0, col1, None, typ)]), Chunk([(0, col2, None, typ)])
+
+
+@pytest.mark.parametrize("kind", sorted(REFERENCE_MERGE_VECTORS))
+@pytest.mark.parametrize("dtype,typ", REFERENCE_MERGE_TYPES)
+def test_reference_serialize_merge_vectors_oracle(oracle, kind, dtype, typ):
+    d, c1, c2 = _reference_merge_case(kind, dtype, typ)
+    r1, r2, merged = REFERENCE_MERGE_VECTORS[kind]
+    for ch, want in ((c1, r1), (c2, r2)):
+        a = oracle.Agg(d)
+        a.push(ch)
+        assert oracle_rows(a) == [(want,)]
+    p1, p2 = abi.two_phase_descs(d)
+    final = oracle.Agg(p2)
+    for ch in (c2, c1):     # state2 first, then the serialised state1 merged into it
+        final.push(_state_chunk(_oracle_states_of_preagg(oracle, p1, ch)))
+    assert oracle_rows(final) == [(merged,)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", sorted(REFERENCE_MERGE_VECTORS))
+@pytest.mark.parametrize("dtype,typ", REFERENCE_MERGE_TYPES)
+def test_reference_serialize_merge_vectors_gpu(gpu, ctx, kind, dtype, typ):
+    d, c1, c2 = _reference_merge_case(kind, dtype, typ)
+    merged = REFERENCE_MERGE_VECTORS[kind][2]
+    p1, p2 = gpu.two_phase_descs(d)
+    first, final = gpu.Agg(ctx, p1), gpu.Agg(ctx, p2)
+    try:
+        for ch in (c2, c1):
+            first.reset()
+            first.push(ch)
+            first.finish()
+            final.push(gpu.chunk_out_as_view(first.pull(mem=abi.MEM_DEVICE)))
+        assert gpu_rows(final.result()) == [(merged,)]
+    finally:
+        first.close()
+        final.close()
+
+
 @pytest.mark.parametrize("name", CASES)
 @pytest.mark.parametrize("n", [0, 1, 5000])
 def test_oracle_two_phase_equals_single_phase(oracle, name, n):
