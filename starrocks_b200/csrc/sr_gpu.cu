@@ -327,8 +327,12 @@ int32_t sr_scan_filter(sr_scan* s, const sr_chunk_view* in, sr_chunk_out* out) {
     if (total > 0 && ca.n > 0) {
         const int64_t tiles = (in->num_rows + srd::SCANW_TILE - 1) / srd::SCANW_TILE;
         const int grid = (int)std::min<int64_t>((tiles + srd::SCANW_BLOCK / 32 - 1) / (srd::SCANW_BLOCK / 32), (int64_t)ctx->num_sms * 8);
-        srd::k_scan_compact<<<grid, srd::SCANW_BLOCK, 0, ctx->stream>>>(s->mask_bits.as<uint8_t>(), s->local_excl.as<uint32_t>(), s->block_offsets.as<uint64_t>(), ca,
-                                                                         in->num_rows);
+        if (total * 8 >= in->num_rows)
+            srd::k_scan_compact<true><<<grid, srd::SCANW_BLOCK, 0, ctx->stream>>>(s->mask_bits.as<uint8_t>(), s->local_excl.as<uint32_t>(), s->block_offsets.as<uint64_t>(),
+                                                                                   ca, in->num_rows);
+        else
+            srd::k_scan_compact<false><<<grid, srd::SCANW_BLOCK, 0, ctx->stream>>>(s->mask_bits.as<uint8_t>(), s->local_excl.as<uint32_t>(), s->block_offsets.as<uint64_t>(),
+                                                                                    ca, in->num_rows);
         SR_LAUNCH_CHECK(ctx);
     }
     return SR_OK;
