@@ -65,6 +65,18 @@ __device__ __forceinline__ int4 ldg_stream_v4(const void* p) {
                  : "l"(p));
     return r;
 }
+// one 256-bit load (sm_100: LDG.E.256): a whole 32-byte sector per lane in one instruction / one L1 wavefront per line
+// instead of two 128-bit halves.  p must be 32-byte aligned.
+__device__ __forceinline__ void ldg_nc_u32x8(const void* p, uint32_t (&w)[8]) {
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void ldg_stream_u32x8(const void* p, uint32_t (&w)[8]) {
+    asm volatile("ld.global.nc" SR_LD_HINT ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(p));
+}
 __device__ __forceinline__ int32_t ldg_stream_s32(const void* p) {
     int32_t r;
     asm volatile("ld.global.nc" SR_LD_HINT ".s32 %0, [%1];" : "=r"(r) : "l"(p));

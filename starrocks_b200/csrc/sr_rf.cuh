@@ -37,9 +37,8 @@ __device__ __forceinline__ bool rf_test(const RfDev& r, long long v) {
     if (r.dir == nullptr) return true;
     const unsigned long long h = rf_value_hash(v);
     const uint32_t key = (uint32_t)(h >> r.log_buckets);
-    const uint4* b = (const uint4*)(r.dir + 8 * (h & r.dir_mask));
-    const uint4 lo = __ldg(b), hi = __ldg(b + 1);
-    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint32_t w[8];
+    ldg_nc_u32x8(r.dir + 8 * (h & r.dir_mask), w); // the bucket is one 32-byte sector: one 256-bit load
     uint32_t miss = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) miss |= ~w[i] & (1u << ((key * rf_salt(i)) >> 27));
@@ -55,26 +54,22 @@ __device__ __forceinline__ uint32_t rf_test_rows(const RfDev& rf, const long lon
 #pragma unroll
     for (int r = 0; r < R; r++) in |= (((active >> r) & 1u) && v[r] >= rf.min_value && v[r] <= rf.max_value ? 1u : 0u) << r;
     if (rf.dir == nullptr || in == 0) return in;
-    uint4 lo[R], hi[R];
+    uint32_t w[R][8];
     uint32_t key[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const unsigned long long h = rf_value_hash(v[r]);
         key[r] = (uint32_t)(h >> rf.log_buckets);
-        const uint4* b = (const uint4*)(rf.dir + 8 * (h & rf.dir_mask));
-        lo[r] = hi[r] = make_uint4(0, 0, 0, 0);
-        if ((in >> r) & 1u) {
-            lo[r] = __ldg(b);
-            hi[r] = __ldg(b + 1);
-        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[r][i] = 0;
+        if ((in >> r) & 1u) ldg_nc_u32x8(rf.dir + 8 * (h & rf.dir_mask), w[r]); // one 256-bit load per bucket (L1 tag rate bound)
     }
     uint32_t pass = 0;
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        const uint32_t w[8] = {lo[r].x, lo[r].y, lo[r].z, lo[r].w, hi[r].x, hi[r].y, hi[r].z, hi[r].w};
         uint32_t miss = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) miss |= ~w[i] & (1u << ((key[r] * rf_salt(i)) >> 27));
+        for (int i = 0; i < 8; i++) miss |= ~w[r][i] & (1u << ((key[r] * rf_salt(i)) >> 27));
         pass |= (miss == 0 ? 1u : 0u) << r;
     }
     return pass & in;

@@ -156,8 +156,10 @@ __global__ void __launch_bounds__(SCANW_BLOCK) k_scan_mask(const ScanProg* __res
                 const int32_t* col = (const int32_t*)vt.v[rt.value_id].data;
                 int32_t k[SCANW_ROWS];
                 if (t == 0 && st.vec0 && full) {
-                    const int4 a = ldg_stream_v4(col + base), b = ldg_stream_v4(col + base + 4);
-                    k[0] = a.x, k[1] = a.y, k[2] = a.z, k[3] = a.w, k[4] = b.x, k[5] = b.y, k[6] = b.z, k[7] = b.w;
+                    uint32_t w[8];
+                    ldg_stream_u32x8(col + base, w); // the lane's 8 consecutive rows = one 32-byte sector = one 256-bit load
+#pragma unroll
+                    for (int r = 0; r < SCANW_ROWS; r++) k[r] = (int32_t)w[r];
                 } else {
 #pragma unroll
                     for (int r = 0; r < SCANW_ROWS; r++) k[r] = ldg_stream_s32_pred(col + base + r, (m >> r) & 1u);
@@ -195,9 +197,11 @@ __global__ void __launch_bounds__(SCANW_BLOCK) k_scan_mask(const ScanProg* __res
                 uint32_t nulls = 0;
                 long long v[SCANW_ROWS];
                 const int32_t* c32 = (const int32_t*)vt.v[rf.value_id].data;
-                if (vt.plain32 && m == 0xFFu && (((uintptr_t)c32) & 15) == 0) { // whole tile alive: two 128-bit loads
-                    const int4 a = ldg_stream_v4(c32 + base), b = ldg_stream_v4(c32 + base + 4);
-                    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+                if (vt.plain32 && m == 0xFFu && (((uintptr_t)c32) & 31) == 0) { // whole tile alive: one 256-bit load
+                    uint32_t w[8];
+                    ldg_stream_u32x8(c32 + base, w);
+#pragma unroll
+                    for (int r = 0; r < SCANW_ROWS; r++) v[r] = (int32_t)w[r];
                 } else {
 #pragma unroll
                     for (int r = 0; r < SCANW_ROWS; r++) {
@@ -255,8 +259,8 @@ __device__ __forceinline__ void compact_rows(const void* __restrict__ src, void*
 }
 // dense tile, 4-byte column: the lane's 8 consecutive values by two 128-bit loads instead of up to 8 scalar ones
 __device__ __forceinline__ void compact_rows_vec32(const void* __restrict__ src, void* __restrict__ dst, int64_t base, uint32_t m, uint64_t out_pos) {
-    const int4 a = ldg_stream_v4((const uint32_t*)src + base), b = ldg_stream_v4((const uint32_t*)src + base + 4);
-    const uint32_t v[SCANW_ROWS] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w, (uint32_t)b.x, (uint32_t)b.y, (uint32_t)b.z, (uint32_t)b.w};
+    uint32_t v[SCANW_ROWS];
+    ldg_stream_u32x8((const uint32_t*)src + base, v);
     uint32_t* d = (uint32_t*)dst + out_pos;
     uint32_t q = 0;
 #pragma unroll
@@ -273,8 +277,8 @@ __device__ __forceinline__ void compact_rows_staged(const void* __restrict__ src
     const T* s = (const T*)src + base;
     uint32_t q = my_off;
     if (sizeof(T) == 4 && vec) {
-        const int4 a = ldg_stream_v4(s), b = ldg_stream_v4((const uint32_t*)s + 4);
-        const uint32_t v[SCANW_ROWS] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w, (uint32_t)b.x, (uint32_t)b.y, (uint32_t)b.z, (uint32_t)b.w};
+        uint32_t v[SCANW_ROWS];
+        ldg_stream_u32x8(s, v);
 #pragma unroll
         for (int r = 0; r < SCANW_ROWS; r++)
             if ((m >> r) & 1u) ((uint32_t*)stage)[q++] = v[r];
@@ -317,7 +321,7 @@ __global__ void __launch_bounds__(SCANW_BLOCK) k_scan_compact(const uint8_t* __r
             for (int c = 0; c < args.n; c++) {
                 const CompactCol col = args.c[c];
                 if (col.width == 4)
-                    compact_rows_staged<uint32_t>(col.src, col.dst, base, m, dense && (((uintptr_t)col.src) & 15) == 0, (uint32_t*)stage, incl - cnt, tile_total, tile_out);
+                    compact_rows_staged<uint32_t>(col.src, col.dst, base, m, dense && (((uintptr_t)col.src) & 31) == 0, (uint32_t*)stage, incl - cnt, tile_total, tile_out);
                 else if (col.width == 8)
                     compact_rows_staged<unsigned long long>(col.src, col.dst, base, m, false, stage, incl - cnt, tile_total, tile_out);
                 else if (col.width == 1)
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(SCANW_BLOCK) k_scan_compact(const uint8_t* __r
                 compact_rows<uint16_t>(col.src, col.dst, base, m, out_pos);
                 break;
             case 4:
-                if (dense && (((uintptr_t)col.src) & 15) == 0)
+                if (dense && (((uintptr_t)col.src) & 31) == 0)
                     compact_rows_vec32(col.src, col.dst, base, m, out_pos);
                 else
                     compact_rows<uint32_t>(col.src, col.dst, base, m, out_pos);
@@ -574,7 +578,7 @@ static int32_t scan_select(sr_scan* s, const sr_chunk_view* in, bool want_counts
     srd::ScanTests tests = s->tests;
     for (int t = 0; t < tests.num_tests; t++)
         if (vt.v[tests.t[t].value_id].nulls != nullptr) tests.num_tests = 0;
-    tests.vec0 = tests.num_tests > 0 && (((uintptr_t)vt.v[tests.t[0].value_id].data) & 15) == 0 ? 1 : 0;
+    tests.vec0 = tests.num_tests > 0 && (((uintptr_t)vt.v[tests.t[0].value_id].data) & 31) == 0 ? 1 : 0;
     tests.num_rfs = (int32_t)s->rfs.size();
     for (size_t f = 0; f < s->rfs.size(); f++) {
         SR_TRY(rf_device_desc(s->rfs[f].first, &tests.rfs[f])); // reads min/max once the build side is complete
