@@ -33,48 +33,6 @@ struct ScanProg {
     CExpr exprs[8];
 };
 
-constexpr int SCAN_BLOCK = 256;
-constexpr int SCAN_ITEMS = 4;
-constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
-
-// selection[i] = all conjuncts true-and-not-null.  block_counts[b] = survivors of tile b.
-__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_select(const ScanProg* __restrict__ prog, const __grid_constant__ VTab vt, int64_t n,
-                                                             uint8_t* __restrict__ sel, uint32_t* __restrict__ block_counts) {
-    __shared__ uint32_t s_cnt[SCAN_BLOCK / 32];
-    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
-    uint32_t mine = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        const int64_t row = base + k * SCAN_BLOCK + threadIdx.x;
-        if (row < n) {
-            ChunkLoader ld{vt, row};
-            bool pass = true;
-            for (int p = 0; p < prog->num_preds && pass; p++) {
-                int64_t bits;
-                const bool nul = ld.load(prog->preds[p].value_id, bits);
-                pass = eval_pred(prog->preds[p], bits, nul);
-            }
-            for (int e = 0; e < prog->num_exprs && pass; e++) {
-                int64_t bits;
-                const bool nul = eval_expr(prog->exprs[e], ld, bits);
-                pass = !nul && bits != 0;
-            }
-            sel[row] = pass ? 1 : 0;
-            mine += pass ? 1u : 0u;
-        }
-    }
-    if (block_counts) {
-        mine = warp_sum(mine);
-        if (lane_id() == 0) s_cnt[threadIdx.x >> 5] = mine;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t t = 0;
-            for (int w = 0; w < SCAN_BLOCK / 32; w++) t += s_cnt[w];
-            block_counts[blockIdx.x] = t;
-        }
-    }
-}
-
 // single-block exclusive scan of `n` uint32 counts into uint64 offsets; total -> *total
 __global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t* __restrict__ counts, int64_t n, uint64_t* __restrict__ offsets,
                                                        uint64_t* __restrict__ total) {
@@ -365,43 +323,6 @@ __device__ __forceinline__ void copy_elem(const void* src, void* dst, int64_t s,
     ((T*)dst)[d] = ((const T*)src)[s];
 }
 
-// grid = (tiles, columns).  Keeps input order: out position = tile offset + rank inside tile.
-__global__ void __launch_bounds__(SCAN_BLOCK) k_compact(const uint8_t* __restrict__ sel, const uint64_t* __restrict__ tile_offsets,
-                                                         CompactArgs args, int64_t n) {
-    __shared__ uint32_t s_scan[SCAN_BLOCK / 32 + 1];
-    const CompactCol col = args.c[blockIdx.y];
-    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
-    uint64_t out = tile_offsets[blockIdx.x];
-#pragma unroll 1
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        const int64_t row = base + k * SCAN_BLOCK + threadIdx.x;
-        const uint32_t keep = (row < n && sel[row]) ? 1u : 0u;
-        uint32_t tot;
-        const uint32_t rank = block_excl_scan<SCAN_BLOCK>(keep, s_scan, &tot);
-        if (keep) {
-            const int64_t d = (int64_t)(out + rank);
-            switch (col.width) {
-            case 1:
-                copy_elem<uint8_t>(col.src, col.dst, row, d);
-                break;
-            case 2:
-                copy_elem<uint16_t>(col.src, col.dst, row, d);
-                break;
-            case 4:
-                copy_elem<uint32_t>(col.src, col.dst, row, d);
-                break;
-            case 8:
-                copy_elem<uint64_t>(col.src, col.dst, row, d);
-                break;
-            default:
-                copy_elem<int4>(col.src, col.dst, row, d);
-                break;
-            }
-        }
-        out += tot;
-    }
-}
-
 // K11: dst[j] = src[index[j]] (Column::append_selective); index 0 of a build column is the
 // sentinel row.  null_out (optional): 1 when index == 0 (outer join miss) or src null.
 struct GatherCol {
@@ -486,7 +407,7 @@ struct sr_scan {
     VReg reg;
     DevBuf prog;
     Staged staged;
-    DevBuf sel, block_counts, tile_offsets;
+    DevBuf sel;
     // warp-tile scan (k_scan_mask / k_scan_lvl1 / k_scan_compact)
     DevBuf mask_bits, tile_counts, local_excl, block_sums, block_offsets;
     srd::ScanTests tests; // range form of the conjuncts (num_tests == 0: generic evaluation)
