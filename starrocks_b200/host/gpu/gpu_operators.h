@@ -862,4 +862,52 @@ private:
     GpuAggregatorFactoryPtr _f;
 };
 
+// AggregateStreamingNode::decompose_to_pipeline (be/src/exec/aggregate/aggregate_streaming_node.cpp:39-50): one aggregator
+// factory shared by the sink operator factory (end of the upstream pipeline) and the source operator factory (head of the
+// downstream one); one aggregator per driver sequence
+class GpuStreamingAggregatorFactory {
+public:
+    GpuStreamingAggregatorFactory(sr_ctx* ctx, sr_agg_desc first_phase_desc, GpuStreamingPreaggMode mode, size_t max_ht_bytes = 64u << 20,
+                                  int pass_through_batches = 5)
+            : _ctx(ctx), _desc(first_phase_desc), _mode(mode), _max_ht_bytes(max_ht_bytes), _pass_through_batches(pass_through_batches) {}
+    GpuStreamingAggregatorPtr get_or_create(size_t seq) {
+        if (_aggs.size() <= seq) _aggs.resize(seq + 1);
+        if (!_aggs[seq]) _aggs[seq] = std::make_shared<GpuStreamingAggregator>(_ctx, _desc, _mode, _max_ht_bytes, _pass_through_batches);
+        return _aggs[seq];
+    }
+
+private:
+    sr_ctx* _ctx;
+    sr_agg_desc _desc;
+    GpuStreamingPreaggMode _mode;
+    size_t _max_ht_bytes;
+    int _pass_through_batches;
+    std::vector<GpuStreamingAggregatorPtr> _aggs;
+};
+using GpuStreamingAggregatorFactoryPtr = std::shared_ptr<GpuStreamingAggregatorFactory>;
+
+class GpuAggregateStreamingSinkOperatorFactory final : public OperatorFactory {
+public:
+    GpuAggregateStreamingSinkOperatorFactory(int32_t id, int32_t plan_node_id, GpuStreamingAggregatorFactoryPtr f)
+            : OperatorFactory(id, "gpu_aggregate_streaming_sink", plan_node_id), _f(std::move(f)) {}
+    OperatorPtr create(int32_t dop, int32_t seq) override {
+        return std::make_shared<GpuAggregateStreamingSinkOperator>(this, _id, _plan_node_id, seq, _f->get_or_create(seq));
+    }
+
+private:
+    GpuStreamingAggregatorFactoryPtr _f;
+};
+
+class GpuAggregateStreamingSourceOperatorFactory final : public SourceOperatorFactory {
+public:
+    GpuAggregateStreamingSourceOperatorFactory(int32_t id, int32_t plan_node_id, GpuStreamingAggregatorFactoryPtr f)
+            : SourceOperatorFactory(id, "gpu_aggregate_streaming_source", plan_node_id), _f(std::move(f)) {}
+    OperatorPtr create(int32_t dop, int32_t seq) override {
+        return std::make_shared<GpuAggregateStreamingSourceOperator>(this, _id, _plan_node_id, seq, _f->get_or_create(seq));
+    }
+
+private:
+    GpuStreamingAggregatorFactoryPtr _f;
+};
+
 } // namespace starrocks::pipeline

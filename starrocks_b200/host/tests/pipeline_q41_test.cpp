@@ -421,12 +421,15 @@ int main(int argc, char** argv) {
             sd.out_slots = outs.data();
             sd.num_out_slots = (int32_t)outs.size();
             GpuScanOperatorFactory scan_f(30, 30, ctx, sd, {split(lineorder, 4096)});
-            auto streaming = std::make_shared<GpuStreamingAggregator>(ctx, p1, (GpuStreamingPreaggMode)mode, /*max_ht_bytes=*/(size_t)256 << 10,
-                                                                       /*pass_through_batches=*/1);
+            auto streaming_f = std::make_shared<GpuStreamingAggregatorFactory>(ctx, p1, (GpuStreamingPreaggMode)mode, /*max_ht_bytes=*/(size_t)256 << 10,
+                                                                               /*pass_through_batches=*/1);
+            auto streaming = streaming_f->get_or_create(0);
             auto final_f = std::make_shared<GpuAggregatorFactory>(ctx, p2);
-            PipelineDriver first({scan_f.create(1, 0), std::make_shared<GpuAggregateStreamingSinkOperator>(nullptr, 31, 31, 0, streaming)});
+            GpuAggregateStreamingSinkOperatorFactory stream_sink_f(31, 31, streaming_f);
+            GpuAggregateStreamingSourceOperatorFactory stream_source_f(32, 32, streaming_f);
+            PipelineDriver first({scan_f.create(1, 0), stream_sink_f.create(1, 0)});
             GpuAggregateBlockingSinkOperatorFactory merge_sink_f(33, 33, final_f);
-            PipelineDriver second({std::make_shared<GpuAggregateStreamingSourceOperator>(nullptr, 32, 32, 0, streaming), merge_sink_f.create(1, 0)});
+            PipelineDriver second({stream_source_f.create(1, 0), merge_sink_f.create(1, 0)});
             run_to_finish(first, &state, "first phase");
             run_to_finish(second, &state, "merge phase");
             auto sink = std::make_shared<ResultSink>();
