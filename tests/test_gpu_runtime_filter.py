@@ -186,3 +186,18 @@ def test_runtime_filter_errors_are_loud(gpu, ctx):
         scan.add_runtime_filter(rf, 0)
     scan.close()
     rf.close()
+
+
+def test_reference_evaluate_and_fill_vectors(gpu, ctx):
+    # the known answers of runtime_filter_core_test.cpp:125-163,227-263 through the CUDA path
+    from tests.test_oracle_golden import _rf_reference_evaluate_vectors
+    made = []
+
+    def make(n):
+        made.append(gpu.RuntimeFilter(ctx, abi.TYPE_INT, n))
+        return made[-1]
+    try:
+        _rf_reference_evaluate_vectors(make)
+    finally:
+        for f in made:
+            f.close()

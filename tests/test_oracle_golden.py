@@ -433,3 +433,35 @@ def test_runtime_bloom_filter_values(oracle):
     inside = np.setdiff1d(np.arange(-10**6, 10**6, 7, dtype=np.int32), keys)[:20000]
     fp = rf.evaluate(Chunk([(0, inside, None)]), 0).mean()
     assert fp < 0.05                                                           # 8 bits per key, 8 probes in one block
+
+
+def _rf_reference_evaluate_vectors(make_filter):
+    """runtime_filter_core_test.cpp:125-163 RuntimeBloomFilterEvaluateConstAndNullableColumns and :227-263
+    RuntimeFilterBuilderFill{OnNullableColumn,WithEqNull}: known answers of evaluate() on const / NULL / nullable columns.
+    `make_filter(expected_rows)` -> object with insert(chunk, slot, insert_nulls) / evaluate(chunk, slot)."""
+    i32 = lambda xs: np.array(xs, dtype=np.int32)  # noqa: E731
+    rf = make_filter(100)
+    rf.insert(Chunk([(0, i32([10, 20]), None)]), 0)
+    assert rf.evaluate(Chunk([(0, i32([10] * 8), None)]), 0).tolist() == [1] * 8           # const hit
+    assert rf.evaluate(Chunk([(0, i32([11] * 8), None)]), 0).tolist() == [0] * 8           # const miss INSIDE [min, max]: the bloom part
+    all_null = Chunk([(0, i32([0] * 8), np.ones(8, dtype=np.uint8))])
+    assert rf.evaluate(all_null, 0).tolist() == [0] * 8                                    # const NULL, filter has no NULL
+    nullable = Chunk([(0, i32([10, 11, 20, 21, 0, 0]), np.array([0, 0, 0, 0, 1, 1], dtype=np.uint8))])
+    assert rf.evaluate(nullable, 0).tolist() == [1, 0, 1, 0, 0, 0]
+    rf.insert(Chunk([(0, i32([0]), np.ones(1, dtype=np.uint8))]), 0, insert_nulls=True)   # insert_null()
+    assert rf.evaluate(all_null, 0).tolist() == [1] * 8
+    assert rf.evaluate(nullable, 0).tolist() == [1, 0, 1, 0, 1, 1]
+    # RuntimeFilterBuilder::fill on a nullable column: eq_null = false skips the NULL, eq_null = true records it
+    build = Chunk([(0, i32([10, 20, 0]), np.array([0, 0, 1], dtype=np.uint8))])
+    plain, eq_null = make_filter(64), make_filter(64)
+    plain.insert(build, 0, insert_nulls=False)
+    eq_null.insert(build, 0, insert_nulls=True)
+    assert plain.info().has_null == 0 and eq_null.info().has_null == 1
+    assert plain.evaluate(Chunk([(0, i32([10, 20]), None)]), 0).tolist() == [1, 1]
+    three_nulls = Chunk([(0, i32([0, 0, 0]), np.ones(3, dtype=np.uint8))])
+    assert eq_null.evaluate(three_nulls, 0).tolist() == [1, 1, 1]
+    assert plain.evaluate(three_nulls, 0).tolist() == [0, 0, 0]
+
+
+def test_runtime_bloom_filter_evaluate_and_fill_golden(oracle):
+    _rf_reference_evaluate_vectors(lambda n: oracle.RuntimeFilter(abi.TYPE_INT, n))
