@@ -110,6 +110,33 @@ def all_reduce_dense_state(arrays, device):
         k += len(group)
 
 
+def all_reduce_runtime_filter(directory, min_value, max_value, num_inserted, has_null):
+    """Global runtime filter (the RuntimeFilterMerger of be/src/runtime/runtime_filter_worker.cpp, every fragment instance
+    ships its PARTIAL filter of a partitioned join's build side and the merged filter goes to the probe-side scans): the
+    partial SimdBlockFilter directories -- all sized for the GLOBAL build row count, so they have the same shape -- are
+    gathered in one collective and OR-ed (SimdBlockFilter::merge is a bitwise OR), min / max / has_null / counts are
+    reduced alongside.  directory: 1-D int32 tensor aliasing or holding the 32-byte buckets (device tensor under NCCL,
+    host tensor under gloo), modified in place.  Returns (min, max, num_inserted, has_null) of the merged filter; feed
+    them with the directory to sr_rf_merge_directory of an EMPTY filter (or overwrite this rank's own)."""
+    dev = directory.device
+    if directory.numel():
+        # NCCL has no bitwise-OR reduction: gather the partial directories (a filter is at most a few MB) and OR them here;
+        # a BE would hand each gathered slice to sr_rf_merge_directory (k_or_u32) instead of the torch op
+        world = dist.get_world_size()
+        flat = torch.empty(world * directory.numel(), dtype=directory.dtype, device=dev)
+        dist.all_gather_into_tensor(flat, directory.contiguous())
+        parts = flat.view(world, directory.numel())
+        for r in range(world):
+            directory.bitwise_or_(parts[r])
+    lo = torch.tensor([min_value], dtype=torch.int64, device=dev)
+    hi = torch.tensor([max_value, 1 if has_null else 0], dtype=torch.int64, device=dev)
+    cnt = torch.tensor([num_inserted], dtype=torch.int64, device=dev)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    return int(lo[0]), int(hi[0]), int(cnt[0]), bool(int(hi[1]))
+
+
 def exchange_partitions(cols, channel_offsets):
     """HASH_PARTITIONED exchange.  cols: list of 1-D tensors already reordered so that the rows of channel c occupy
     [channel_offsets[c], channel_offsets[c+1]) (what sr_xchg_partition / the reference's counting sort produce);

@@ -116,6 +116,41 @@ def _intermediate_format_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _global_runtime_filter_worker(rank, world, port, q):
+    """partitioned join: each rank builds the PARTIAL filter of its build-side shard (sized for the global row count),
+    the directories are OR-ed and min / max / has_null reduced across ranks; the merged filter equals the filter built
+    from the whole build side, byte for byte"""
+    from oracle import oracle
+    from starrocks_b200.distributed import all_reduce_runtime_filter
+    from tests.helpers import rand_nulls
+    _init(rank, world, port)
+    rng = np.random.default_rng(3)
+    n = 50_000
+    keys = rng.integers(-10**7, 10**7, n, dtype=np.int64)
+    nulls = rand_nulls(rng, n, 0.01)
+    part = oracle.RuntimeFilter(abi.TYPE_BIGINT, n)                      # expected_rows = GLOBAL build rows
+    part.insert(Chunk([(0, keys[rank::world].copy(), nulls[rank::world].copy())]), 0, insert_nulls=(rank == 1))
+    inf = part.info()
+    directory = torch.from_numpy(part.directory().view(np.int32).copy())
+    mn, mx, cnt, has_null = all_reduce_runtime_filter(directory, inf.min_value, inf.max_value, inf.num_inserted, inf.has_null != 0)
+    whole = oracle.RuntimeFilter(abi.TYPE_BIGINT, n)
+    whole.insert(Chunk([(0, keys, nulls)]), 0, insert_nulls=True)
+    w = whole.info()
+    ok = np.array_equal(directory.numpy().view(np.uint32), whole.directory())
+    # rank 0 inserted no NULLs, rank 1 did: the union has them; counts add up to the non-NULL keys
+    ok = ok and (mn, mx, cnt, has_null) == (w.min_value, w.max_value, w.num_inserted, True)
+    # and the merged bytes fed into an empty filter evaluate like the whole-side filter
+    merged = oracle.RuntimeFilter(abi.TYPE_BIGINT, n)
+    other = oracle.RuntimeFilter(abi.TYPE_BIGINT, n)
+    other.insert(Chunk([(0, keys, nulls)]), 0, insert_nulls=True)
+    merged.merge(other)
+    probe = Chunk([(0, rng.integers(-10**7, 10**7, 20_000, dtype=np.int64), rand_nulls(rng, 20_000, 0.02))])
+    ok = ok and np.array_equal(merged.evaluate(probe, 0), whole.evaluate(probe, 0)) and np.array_equal(merged.directory(), directory.numpy().view(np.uint32))
+    q.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def _shuffle_worker(rank, world, port, q):
     from oracle import oracle
     from starrocks_b200.distributed import exchange_partitions, gather_partial_states
@@ -152,7 +187,7 @@ def _shuffle_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("worker", [_two_phase_worker, _intermediate_format_worker, _shuffle_worker])
+@pytest.mark.parametrize("worker", [_two_phase_worker, _intermediate_format_worker, _global_runtime_filter_worker, _shuffle_worker])
 def test_world_size_2_gloo(oracle, worker):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
