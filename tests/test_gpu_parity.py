@@ -789,3 +789,20 @@ def test_errors_are_loud(gpu, ctx):
             s.filter(Chunk([(0, np.arange(4, dtype=np.int32), None)]))   # slot 5 does not exist
     finally:
         s.close()
+
+
+def test_agg_compressed_key_sql_goldens_gpu(gpu, ctx):
+    # test/sql/test_agg/R/test_agg_compressed_key through the dense (range-declared) CUDA aggregate, in two pushes
+    from tests.test_oracle_golden import _compressed_key_check
+
+    def run(d, chunk):
+        a = gpu.Agg(ctx, d)
+        try:
+            n = chunk.num_rows
+            cols = chunk.columns()
+            for lo, hi in ((0, n // 3), (n // 3, n)):
+                a.push(Chunk([(s, arr[lo:hi].copy(), None if nl is None else nl[lo:hi].copy(), t) for (s, arr, nl), t in zip(cols, chunk.types)]))
+            return gpu_rows(a.result())
+        finally:
+            a.close()
+    _compressed_key_check(run)

@@ -465,3 +465,56 @@ def _rf_reference_evaluate_vectors(make_filter):
 
 def test_runtime_bloom_filter_evaluate_and_fill_golden(oracle):
     _rf_reference_evaluate_vectors(lambda n: oracle.RuntimeFilter(abi.TYPE_INT, n))
+
+
+# ---- test/sql/test_agg/R/test_agg_compressed_key: the compressed-key (range-declared) aggregator on nullable keys -------
+def _compressed_key_table():
+    """all_t0 of the SQL test, integer columns only: x = 1..30000; c1 tinyint = x % 200 (128..199 overflow the TINYINT and
+    load as NULL, which is what the goldens show), c2 smallint / c3 int / c4 bigint = x % 200, c13 tinyint / c14 smallint
+    = x % 8, c15 int = x % 16, c16 bigint = x % 200 (NOT NULL columns), plus the two literal rows."""
+    x = np.arange(1, 30001)
+    m = x % 200
+    c1, c1n = np.where(m < 128, m, 0), (m >= 128).astype(np.uint8)
+    cols = {1: (np.concatenate([c1, [0, -1]]).astype(np.int8), np.concatenate([c1n, [1, 0]]).astype(np.uint8), abi.TYPE_TINYINT),
+            2: (np.concatenate([m, [0, -2]]).astype(np.int16), np.array([0] * 30000 + [1, 0], dtype=np.uint8), abi.TYPE_SMALLINT),
+            3: (np.concatenate([m, [0, -3]]).astype(np.int32), np.array([0] * 30000 + [1, 0], dtype=np.uint8), abi.TYPE_INT),
+            4: (np.concatenate([m, [0, 0]]).astype(np.int64), np.array([0] * 30000 + [1, 1], dtype=np.uint8), abi.TYPE_BIGINT),
+            13: (np.concatenate([x % 8, [-1, -1]]).astype(np.int8), None, abi.TYPE_TINYINT),
+            14: (np.concatenate([x % 8, [-2, -2]]).astype(np.int16), None, abi.TYPE_SMALLINT),
+            16: (np.concatenate([m, [-4, -4]]).astype(np.int64), None, abi.TYPE_BIGINT)}
+    return cols
+
+
+COMPRESSED_KEY_RANGES = {1: (-1, 127), 2: (-2, 199), 3: (-3, 199), 4: (0, 199), 13: (-1, 7), 14: (-2, 7), 16: (-4, 199)}
+# (group-by columns) -> {position in ORDER BY keys ASC NULLS FIRST: expected row}; "last" = ORDER BY keys DESC LIMIT 1
+COMPRESSED_KEY_GOLDENS = [
+    ((1,), {0: (None, None), 1: (-1, -1), 2: (0, 0)}),                                   # :159-164
+    ((1, 2), {0: (None, None, None), 1: (None, 128, None), 2: (None, 129, None)}),       # :165-170
+    ((2,), {3: (1, 150), "last": (199, None)}), ((3,), {3: (1, 150), "last": (199, None)}),
+    ((4,), {3: (2, 300), "last": (199, None)}), ((13,), {3: (2, 148800), "last": (7, 160800)}),
+    ((14,), {3: (2, 148800), "last": (7, 160800)}), ((16,), {3: (2, 300), "last": (199, None)}),
+    ((3, 4), {30: (28, 28, 4200)}),                                                       # :262-265
+]
+
+
+def _compressed_key_check(run_agg):
+    """run_agg(desc, chunk) -> sorted rows (None first).  Every query is SUM(c1) GROUP BY the listed columns with the
+    min/max statistics the FE would pass (the compressed-key variants, aggregator.cpp:1516-1566)."""
+    cols = _compressed_key_table()
+    for keys, expect in COMPRESSED_KEY_GOLDENS:
+        d = abi.make_agg_desc(list(keys), [cols[k][2] for k in keys], fns=[(abi.AGG_SUM, abi.TYPE_TINYINT, 100, [("col", 1)])],
+                              ranges=[COMPRESSED_KEY_RANGES[k] for k in keys], group_nullable=[1 if cols[k][1] is not None else 0 for k in keys])
+        need = sorted(set(keys) | {1})
+        rows = run_agg(d, Chunk([(k, cols[k][0], cols[k][1], cols[k][2]) for k in need]))
+        for pos, want in expect.items():
+            assert rows[-1 if pos == "last" else pos] == want, (keys, pos)
+
+
+def test_agg_compressed_key_sql_goldens(oracle):
+    from tests.helpers import oracle_rows
+
+    def run(d, chunk):
+        a = oracle.Agg(d)
+        a.push(chunk)
+        return oracle_rows(a)
+    _compressed_key_check(run)
