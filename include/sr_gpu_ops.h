@@ -299,6 +299,11 @@ typedef struct sr_join_desc {
     /* session switch enable_hash_join_range_direct_mapping_opt (join_hash_table.cpp:259) */
     int32_t enable_range_direct_mapping;
     int32_t reserved;
+    /* sr_type of every build_out_slot (0 = take it from the appended chunks).  The reference knows the build side's
+     * schema from the plan (HashJoinerParam::_build_row_descriptor, exec/hash_joiner.h:66-133) even when no build chunk
+     * ever arrives -- a dimension scan that filters everything out; with the types declared here such a join probes to
+     * zero rows (INNER / SEMI) or to NULL-padded rows (LEFT OUTER) instead of failing. */
+    int32_t build_out_types[SR_MAX_JOIN_OUT];
 } sr_join_desc;
 
 typedef struct sr_join sr_join;

@@ -416,6 +416,12 @@ static int32_t eval_expr_range(const sr_expr* e, const sr_chunk_view* in, int64_
                 for (int64_t i = 0; i < n; i++) {
                     const double x = a.dv[i], y = b.dv[i];
                     r.dv[i] = nd.op == SR_EX_ADD ? x + y : nd.op == SR_EX_SUB ? x - y : nd.op == SR_EX_MUL ? x * y : x / y;
+                    // VectorizedDiv runs under ArithmeticRightZeroCheck (be/src/exprs/arithmetic_operation.h:638,
+                    // arithmetic_expr.cpp VectorizedDivArithmeticExpr): a zero divisor yields NULL, for DOUBLE too
+                    if (nd.op == SR_EX_DIV && y == 0.0) {
+                        r.nul[i] = 1;
+                        r.dv[i] = 0.0;
+                    }
                 }
             } else {
                 r.iv.resize(n);

@@ -114,7 +114,8 @@ class sr_join_desc(C.Structure):
                 ("key_types", C.c_int32 * SR_MAX_JOIN_KEYS),
                 ("num_build_out", C.c_int32), ("build_out_slots", C.c_int32 * SR_MAX_JOIN_OUT),
                 ("num_probe_out", C.c_int32), ("probe_out_slots", C.c_int32 * SR_MAX_JOIN_OUT),
-                ("enable_range_direct_mapping", C.c_int32), ("reserved", C.c_int32)]
+                ("enable_range_direct_mapping", C.c_int32), ("reserved", C.c_int32),
+                ("build_out_types", C.c_int32 * SR_MAX_JOIN_OUT)]
 
 
 class sr_join_info(C.Structure):
@@ -297,7 +298,7 @@ class ScanDesc:
         return C.byref(self.desc)
 
 
-def make_join_desc(join_type, build_keys, probe_keys, key_types, build_out=(), probe_out=(), enable_rdm=True):
+def make_join_desc(join_type, build_keys, probe_keys, key_types, build_out=(), probe_out=(), enable_rdm=True, build_out_types=()):
     d = sr_join_desc()
     d.join_type = join_type
     d.num_keys = len(build_keys)
@@ -312,6 +313,8 @@ def make_join_desc(join_type, build_keys, probe_keys, key_types, build_out=(), p
     for k, s in enumerate(probe_out):
         d.probe_out_slots[k] = s
     d.enable_range_direct_mapping = 1 if enable_rdm else 0
+    for k, t in enumerate(build_out_types):
+        d.build_out_types[k] = t
     return d
 
 

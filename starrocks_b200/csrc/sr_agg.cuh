@@ -68,6 +68,12 @@ struct AggDev {
     unsigned long long cap; // slots (hash: power of two, plus one special slot at index cap)
     unsigned long long mask;
     unsigned long long limit; // admission limit for new groups
+    // hash tables: a probe sequence never leaves the aligned SLICE of slice_mask + 1 slots its home slot lies in (it wraps
+    // inside the slice).  A slice with all its state arrays fits the shared memory of one CTA, which is what lets the
+    // radix-partitioned push (sr_agg_part.cuh) aggregate a whole slice on chip and write it back once.
+    unsigned long long slice_mask;
+    int32_t slice_log2;
+    int32_t pad0;
     unsigned long long* hkeys;
     long long* cnt_star;
     unsigned long long* ngroups;
@@ -239,7 +245,8 @@ __device__ __forceinline__ long long agg_find_slot_key(const AggDev& a, const HK
     inserted = false;
     if (hkey_is_empty(a, key)) return (long long)a.cap; // only possible for full 8- / 16-byte keys: the special slot
     unsigned long long s = hkey_hash(a, key) & a.mask;
-    for (unsigned long long tries = 0; tries <= a.mask; tries++) {
+    const unsigned long long sb = s & ~a.slice_mask;
+    for (unsigned long long tries = 0; tries <= a.slice_mask; tries++) {
         HKey cur = hkey_load(a, s);
         if (hkey_eq(a, cur, key)) return (long long)s;
         if (hkey_is_empty(a, cur)) {
@@ -254,7 +261,7 @@ __device__ __forceinline__ long long agg_find_slot_key(const AggDev& a, const HK
             }
             if (hkey_eq(a, cur, key)) return (long long)s;
         }
-        s = (s + 1) & a.mask;
+        s = sb | ((s + 1) & a.slice_mask);
     }
     a.flags[0] = 1;
     return -1;
@@ -498,233 +505,8 @@ __global__ void __launch_bounds__(AGG_BLOCK, AGG_MIN_BLOCKS) k_agg_push(const Ag
     }
 }
 
-// ---- radix-partitioned push: hash tables far larger than L2 -------------------------------------------------
-// A row of a high-cardinality group-by touches one random sector per state array; with a multi-GB table every one
-// of them is a DRAM read-modify-write.  The partitioned push first scatters the batch by the TOP bits of each
-// row's home slot (packed key + evaluated function inputs, staged in HBM), then applies the staged rows bucket by
-// bucket: while a bucket is processed the slice of the table it maps to (a few tens of MB) stays in L2, and the
-// find / claim / accumulate traffic is served there.  Cost: one extra write + read of ~17..33 staged bytes per row.
-constexpr int AGGP_BLOCK = 512;
-constexpr int AGGP_MAX_PARTS = 1024;
-
-struct PartStage {
-    unsigned long long* key_lo;
-    unsigned long long* key_hi;      // wide keys only
-    long long* val[SR_MAX_AGG_FNS];  // evaluated input of each function (nullptr: COUNT(*))
-    uint8_t* nulls;                  // bit f: the input of function f is NULL for this row
-};
-
-// contiguous row range of the calling CTA (the histogram and the scatter pass must agree on it)
-__device__ __forceinline__ void aggp_cta_range(int64_t n, int64_t& begin, int64_t& end) {
-    int64_t per = (n + gridDim.x - 1) / gridDim.x;
-    per = (per + AGGP_BLOCK - 1) / AGGP_BLOCK * AGGP_BLOCK;
-    begin = (int64_t)blockIdx.x * per;
-    if (begin > n) begin = n;
-    end = begin + per < n ? begin + per : n;
-}
-
-__global__ void __launch_bounds__(AGGP_BLOCK) k_agg_part_hist(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, int64_t row_base, int64_t n,
-                                                               int log2p, int shift, uint32_t* __restrict__ hist) {
-    __shared__ uint32_t s_h[AGGP_MAX_PARTS];
-    const AggDev& a = *ad;
-    const int P = 1 << log2p;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) s_h[i] = 0;
-    __syncthreads();
-    int64_t b, e;
-    aggp_cta_range(n, b, e);
-    for (int64_t row = b + threadIdx.x; row < e; row += blockDim.x) {
-        ChunkLoader ld{vt, row_base + row};
-        HKey key;
-        agg_pack_key(a, ld, key);
-        atomicAdd(&s_h[(uint32_t)((hkey_hash(a, key) & a.mask) >> shift)], 1u);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < P; i += blockDim.x) hist[(size_t)i * gridDim.x + blockIdx.x] = s_h[i]; // bucket-major
-}
-
-// Scatter pass.  A direct per-row scatter writes 8 bytes to a different bucket for every lane (measured: 81 ms per
-// 1e9 rows, all of it partial-sector write traffic), so each CTA first counting-sorts a tile of AGGP_TILE rows by
-// bucket in shared memory and then writes every staged array in sorted order: consecutive threads write consecutive
-// addresses inside each bucket's run.
-constexpr int AGGP_RPT = 4;                      // rows per thread and tile (8 needs 128 registers: one CTA per SM)
-constexpr int AGGP_TILE = AGGP_BLOCK * AGGP_RPT; // rows per tile
-constexpr size_t AGGP_SCATTER_SMEM = (size_t)AGGP_TILE * 8 + (size_t)AGGP_MAX_PARTS * (8 + 4 + 4 + 4) + (size_t)AGGP_TILE * 2;
-
-__global__ void __launch_bounds__(AGGP_BLOCK, 2) k_agg_part_scatter(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, int64_t row_base, int64_t n,
-                                                                  int log2p, int shift, const uint64_t* __restrict__ offs, PartStage st) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ uint32_t s_scan[AGGP_BLOCK / 32 + 1];
-    unsigned long long* s_val = (unsigned long long*)s_raw;              // one staged array of the tile, in sorted order
-    unsigned long long* s_gbase = s_val + AGGP_TILE;                     // first staged row of (bucket, this CTA)
-    uint32_t* s_hist = (uint32_t*)(s_gbase + AGGP_MAX_PARTS);            // rows of the tile per bucket
-    uint32_t* s_start = s_hist + AGGP_MAX_PARTS;                         // first sorted position of the bucket in the tile
-    uint32_t* s_done = s_start + AGGP_MAX_PARTS;                         // rows this CTA has already written per bucket
-    uint16_t* s_bkt = (uint16_t*)(s_done + AGGP_MAX_PARTS);              // bucket of every sorted position
-    const AggDev& a = *ad;
-    const int P = 1 << log2p;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < P; i += AGGP_BLOCK) {
-        s_gbase[i] = offs[(size_t)i * gridDim.x + blockIdx.x];
-        s_done[i] = 0;
-    }
-    int64_t b, e;
-    aggp_cta_range(n, b, e);
-    const int per = (P + AGGP_BLOCK - 1) / AGGP_BLOCK; // histogram entries each thread scans
-    for (int64_t tile0 = b; tile0 < e; tile0 += AGGP_TILE) {
-        const int tile_n = (int)(e - tile0 < AGGP_TILE ? e - tile0 : AGGP_TILE);
-        for (int i = tid; i < P; i += AGGP_BLOCK) s_hist[i] = 0;
-        __syncthreads();
-        HKey keys[AGGP_RPT];
-        uint32_t bk[AGGP_RPT], dst[AGGP_RPT];
-#pragma unroll
-        for (int k = 0; k < AGGP_RPT; k++) {
-            const int q = k * AGGP_BLOCK + tid;
-            bk[k] = 0;
-            dst[k] = 0;
-            if (q < tile_n) {
-                ChunkLoader ld{vt, row_base + tile0 + q};
-                agg_pack_key(a, ld, keys[k]);
-                bk[k] = (uint32_t)((hkey_hash(a, keys[k]) & a.mask) >> shift);
-                dst[k] = atomicAdd(&s_hist[bk[k]], 1u); // rank inside the bucket, for now
-            }
-        }
-        __syncthreads();
-        {   // exclusive scan of the histogram -> first sorted position of every bucket
-            uint32_t local = 0;
-            for (int i = 0; i < per; i++) {
-                const int idx = tid * per + i;
-                if (idx < P) local += s_hist[idx];
-            }
-            uint32_t tot;
-            uint32_t run = block_excl_scan<AGGP_BLOCK>(local, s_scan, &tot);
-            for (int i = 0; i < per; i++) {
-                const int idx = tid * per + i;
-                if (idx < P) {
-                    s_start[idx] = run;
-                    run += s_hist[idx];
-                }
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < AGGP_RPT; k++) {
-            if (k * AGGP_BLOCK + tid < tile_n) {
-                dst[k] += s_start[bk[k]];
-                s_bkt[dst[k]] = (uint16_t)bk[k];
-            }
-        }
-        // sorted position j of the tile -> staged row
-        auto staged_pos = [&](int j) {
-            const uint32_t q = s_bkt[j];
-            return s_gbase[q] + s_done[q] + (unsigned long long)(j - s_start[q]);
-        };
-        // packed key, low word
-#pragma unroll
-        for (int k = 0; k < AGGP_RPT; k++)
-            if (k * AGGP_BLOCK + tid < tile_n) s_val[dst[k]] = keys[k].lo;
-        __syncthreads();
-        for (int j = tid; j < tile_n; j += AGGP_BLOCK) st.key_lo[staged_pos(j)] = s_val[j];
-        __syncthreads();
-        if (a.wide) {
-#pragma unroll
-            for (int k = 0; k < AGGP_RPT; k++)
-                if (k * AGGP_BLOCK + tid < tile_n) s_val[dst[k]] = keys[k].hi;
-            __syncthreads();
-            for (int j = tid; j < tile_n; j += AGGP_BLOCK) st.key_hi[staged_pos(j)] = s_val[j];
-            __syncthreads();
-        }
-        // evaluated function inputs, one array at a time through the same buffer
-        uint32_t nm[AGGP_RPT];
-#pragma unroll
-        for (int k = 0; k < AGGP_RPT; k++) nm[k] = 0;
-#pragma unroll 1
-        for (int f = 0; f < a.num_fns; f++) {
-            if (a.fns[f].mode == M_COUNT_STAR) continue;
-#pragma unroll
-            for (int k = 0; k < AGGP_RPT; k++) {
-                const int q = k * AGGP_BLOCK + tid;
-                if (q < tile_n) {
-                    ChunkLoader ld{vt, row_base + tile0 + q};
-                    int64_t bits;
-                    const bool nul = eval_expr(a.fns[f].input, ld, bits);
-                    s_val[dst[k]] = (unsigned long long)bits;
-                    nm[k] |= (nul ? 1u : 0u) << f;
-                }
-            }
-            __syncthreads();
-            long long* out = st.val[f];
-            for (int j = tid; j < tile_n; j += AGGP_BLOCK) out[staged_pos(j)] = (long long)s_val[j];
-            __syncthreads();
-        }
-        uint8_t* s_nul = (uint8_t*)s_val;
-#pragma unroll
-        for (int k = 0; k < AGGP_RPT; k++)
-            if (k * AGGP_BLOCK + tid < tile_n) s_nul[dst[k]] = (uint8_t)nm[k];
-        __syncthreads();
-        for (int j = tid; j < tile_n; j += AGGP_BLOCK) st.nulls[staged_pos(j)] = s_nul[j];
-        __syncthreads();
-        for (int i = tid; i < P; i += AGGP_BLOCK) s_done[i] += s_hist[i];
-        // (the next iteration starts with a barrier after clearing s_hist -- s_done is only read after it)
-        __syncthreads();
-    }
-}
-
-// first staged row of every bucket (+ the total), compacted for the host
-__global__ void k_agg_part_bounds(const uint64_t* __restrict__ offs, int P, int grid, uint64_t total, uint64_t* __restrict__ bounds) {
-    for (int b = threadIdx.x; b <= P; b += blockDim.x) bounds[b] = b < P ? offs[(size_t)b * grid] : total;
-}
-
-// Apply the staged rows [r0, r1) -- one bucket, or `list` (rows that could not be placed before a growth).
-// The bucket's table slice [s_lo, s_hi) is requested into L2 up front with full-line prefetches, so that the random
-// find / claim / accumulate accesses that follow hit L2 instead of fetching one DRAM sector each.
-__global__ void __launch_bounds__(AGG_BLOCK) k_agg_part_apply(const AggDev* __restrict__ ad, int64_t r0, int64_t r1, const uint32_t* __restrict__ list,
-                                                               unsigned long long s_lo, unsigned long long s_hi, PartStage st,
-                                                               uint32_t* __restrict__ fail_list, unsigned long long* __restrict__ fail_count) {
-    const AggDev& a = *ad;
-    AccPtrs p;
-    acc_ptrs_global(a, p);
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-    if (s_hi > s_lo) {
-        const unsigned long long lines = ((s_hi - s_lo) * 8 + 127) / 128; // 8-byte state words, 128-byte lines
-        for (unsigned long long l = (unsigned long long)tid; l < lines; l += (unsigned long long)nth) {
-            const unsigned long long w = s_lo + l * 16;
-            if (a.wide) {
-                prefetch_l2(a.hkeys + 2 * w);
-                prefetch_l2(a.hkeys + 2 * w + 16);
-            } else {
-                prefetch_l2(a.hkeys + w);
-            }
-            prefetch_l2(p.cnt + w);
-            for (int f = 0; f < a.num_fns; f++) {
-                if (p.acc0[f]) prefetch_l2(p.acc0[f] + w);
-                if (p.acc1[f]) prefetch_l2(p.acc1[f] + w);
-                if (p.accn[f]) prefetch_l2(p.accn[f] + w);
-            }
-        }
-    }
-    unsigned long long known_groups = *(volatile unsigned long long*)a.ngroups;
-    for (int64_t q = r0 + tid; q < r1; q += nth) {
-        const int64_t i = list ? (int64_t)list[q] : q;
-        const HKey key{st.key_lo[i], a.wide ? st.key_hi[i] : 0ull};
-        bool inserted;
-        const long long slot = agg_find_slot_key(a, key, inserted, known_groups);
-        agg_count_new_groups(a, inserted, known_groups);
-        if (slot < 0) { // table full: remember the row, the host grows the table and re-applies the list
-            fail_list[atomicAdd(fail_count, 1ull)] = (uint32_t)i;
-            continue;
-        }
-        atomicAdd((unsigned long long*)p.cnt + slot, 1ull);
-        const uint32_t nm = st.nulls[i];
-#pragma unroll 1
-        for (int f = 0; f < a.num_fns; f++) {
-            const AggFnDev& fn = a.fns[f];
-            if (fn.mode == M_COUNT_STAR || ((nm >> f) & 1u)) continue;
-            acc_apply(fn.mode, p.acc0[f], p.acc1[f], slot, st.val[f][i]);
-            if (fn.track_n) atomicAdd((unsigned long long*)p.accn[f] + slot, 1ull);
-        }
-    }
-}
+// ---- radix-partitioned push (hash tables larger than one shared-memory slice, large batches): sr_agg_part.cuh,
+// included at the end of the device section
 
 // no GROUP BY: every thread keeps the single state in registers over its rows, a warp reduction and one atomic per
 // warp follow at the end (update_batch_single_state).  Used by the standalone push and by the fragment's final pass --
@@ -860,10 +642,19 @@ __global__ void __launch_bounds__(256) k_agg_rehash(const AggDev* __restrict__ o
             const HKey key = hkey_load(o, s);
             if (hkey_is_empty(o, key)) continue;
             t = hkey_hash(a, key) & a.mask;
-            while (true) {
+            const unsigned long long tb = t & ~a.slice_mask;
+            bool placed = false;
+            for (unsigned long long tries = 0; tries <= a.slice_mask; tries++) {
                 const HKey cur = hkey_claim(a, t, key);
-                if (hkey_is_empty(a, cur)) break;
-                t = (t + 1) & a.mask;
+                if (hkey_is_empty(a, cur)) {
+                    placed = true;
+                    break;
+                }
+                t = tb | ((t + 1) & a.slice_mask);
+            }
+            if (!placed) { // cannot happen when the new table is at least as large as the old one (a slice only splits)
+                a.flags[0] = 1;
+                continue;
             }
         }
         a.cnt_star[t] = o.cnt_star[s];
@@ -891,8 +682,9 @@ __global__ void __launch_bounds__(256) k_agg_merge(const AggDev* __restrict__ od
         } else {
             const HKey key = hkey_load(o, s);
             unsigned long long q = hkey_hash(a, key) & a.mask;
+            const unsigned long long qb = q & ~a.slice_mask;
             t = -1;
-            for (unsigned long long tries = 0; tries <= a.mask; tries++) {
+            for (unsigned long long tries = 0; tries <= a.slice_mask; tries++) {
                 HKey cur = hkey_load(a, q);
                 if (hkey_is_empty(a, cur)) {
                     cur = hkey_claim(a, q, key);
@@ -905,7 +697,7 @@ __global__ void __launch_bounds__(256) k_agg_merge(const AggDev* __restrict__ od
                     t = (long long)q;
                     break;
                 }
-                q = (q + 1) & a.mask;
+                q = qb | ((q + 1) & a.slice_mask);
             }
             if (t < 0) {
                 a.flags[0] = 1;
@@ -1105,6 +897,8 @@ __global__ void __launch_bounds__(EMIT_BLOCK) k_agg_emit(const AggDev* __restric
 
 } // namespace srd
 
+#include "sr_agg_part.cuh"
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -1119,9 +913,11 @@ struct sr_agg {
     DevBuf hkeys, cnt_star, counters /* ngroups + flags */;
     DevBuf acc0[SR_MAX_AGG_FNS], acc1[SR_MAX_AGG_FNS], accn[SR_MAX_AGG_FNS];
     DevBuf slots_tmp;
-    // radix-partitioned push (tables far larger than L2): histogram, offsets, staged rows
-    DevBuf part_hist, part_offs, part_bounds, part_fail, part_fail2, part_key_lo, part_key_hi, part_nulls, part_val[SR_MAX_AGG_FNS];
+    // radix-partitioned push (sr_agg_part.cuh): bucket histogram / bases / cursors, tile list, staged records, retry lists
+    DevBuf part_hist, part_base, part_cursor, part_tiles, part_rec[2], part_fail, part_fail64, part_fail64b;
     int64_t partitioned_pushes = 0;
+    int slice_log2_max = 12;    // slots per probing slice (fixed when the plan is compiled, see agg_compile)
+    bool table_touched = false; // some kernel may have created groups since the table was allocated / reset
     Staged staged;
     int64_t ngroups_host = 0; // hash mode: groups after the last synchronising push
     size_t smem_bytes = 0;    // > 0: dense table accumulated in shared memory
@@ -1190,7 +986,16 @@ static int32_t agg_alloc_tables(sr_agg* a, srd::AggDev* h, uint64_t cap, DevBuf*
     const int grid = std::min(grid_for((int64_t)total, 256), ctx->num_sms * 8);
     h->cap = cap;
     h->mask = cap - 1;
-    h->limit = hash ? cap / 2 : ~0ull;
+    h->limit = hash ? cap / 4 * 3 : ~0ull;
+    if (hash) {
+        int log2cap = 0;
+        while ((1ull << log2cap) < cap) log2cap++;
+        h->slice_log2 = std::min(a->slice_log2_max, log2cap);
+        h->slice_mask = (1ull << h->slice_log2) - 1;
+    } else {
+        h->slice_log2 = 0;
+        h->slice_mask = 0;
+    }
     if (hash) {
         const uint64_t kwords = total * (h->wide ? 2 : 1);
         SR_TRY(hkeys->reserve(ctx, sizeof(uint64_t) * kwords));
@@ -1223,6 +1028,16 @@ static int32_t agg_alloc_tables(sr_agg* a, srd::AggDev* h, uint64_t cap, DevBuf*
         }
     }
     return SR_OK;
+}
+
+// bytes of table state one group slot owns (keys + COUNT(*) + every accumulator array)
+static uint64_t agg_slot_bytes(const srd::AggDev& h) {
+    uint64_t b = 8 * (h.wide ? 2 : 1) + 8;
+    for (int f = 0; f < h.num_fns; f++) {
+        if (h.fns[f].mode == srd::M_COUNT_STAR) continue;
+        b += 8 + (h.fns[f].mode == srd::M_SUM_I128 ? 8 : 0) + (h.fns[f].track_n ? 8 : 0);
+    }
+    return b;
 }
 
 typedef int32_t (*agg_type_fn)(void* user, int32_t slot);
@@ -1358,8 +1173,15 @@ static int32_t agg_compile(sr_agg* a, slot_type_fn tf, agg_nullable_fn nf, void*
     if (!h.dense) {
         if (h.key_bytes > 16) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "packed group-by key of %d bytes (> 16) without usable ranges", h.key_bytes);
         cap = 1ull << 21;
-        const uint64_t want = d.expected_groups > 0 ? (uint64_t)d.expected_groups * 2 : 0;
+        const uint64_t want = d.expected_groups > 0 ? (uint64_t)d.expected_groups / 3 * 4 + 4 : 0; // load <= 3/4
         while (cap < want) cap <<= 1;
+        // probing slice: the largest power of two of slots whose keys + states fit 96 KB of shared memory (two CTAs per
+        // SM in k_aggp_apply_smem).  The slice size is part of the table's probing rule and cannot change once groups
+        // exist: when a column turns nullable later (one more state array per function), the slices may no longer fit and
+        // the partitioned push falls back to its global-atomics apply.
+        const uint64_t slot_bytes = agg_slot_bytes(h);
+        a->slice_log2_max = 12;
+        while (a->slice_log2_max > 6 && (slot_bytes << a->slice_log2_max) > 96 * 1024) a->slice_log2_max--;
     }
     SR_TRY(a->counters.reserve(ctx, 64));
     SR_CUDA(ctx, cudaMemsetAsync(a->counters.p, 0, 64, ctx->stream));
@@ -1452,129 +1274,14 @@ static int32_t agg_check_nullability(sr_agg* a, const VTab& vt) {
     return SR_OK;
 }
 
-// push rows described by vt (already bound) -- shared by sr_agg_push and the unfused paths
-// bytes of table state one group slot owns (keys + COUNT(*) + every accumulator array)
-static uint64_t agg_slot_bytes(const srd::AggDev& h) {
-    uint64_t b = 8 * (h.wide ? 2 : 1) + 8;
-    for (int f = 0; f < h.num_fns; f++) {
-        if (h.fns[f].mode == srd::M_COUNT_STAR) continue;
-        b += 8 + (h.fns[f].mode == srd::M_SUM_I128 ? 8 : 0) + (h.fns[f].track_n ? 8 : 0);
-    }
-    return b;
-}
-
-static const uint64_t kPartitionedTableBytes = 256ull << 20; // tables beyond this no longer live in the 126 MB L2
-static const uint64_t kPartitionSliceBytes = 32ull << 20;    // table slice one bucket maps to
-static const int64_t kPartitionedMinRows = 4 << 20;
-static const int64_t kPartitionedMaxRows = 1ll << 30; // staged rows per round (8..33 B each)
-
-// hash table much larger than L2 and a large batch: scatter by home-slot range, then apply bucket by bucket
-static int32_t agg_push_partitioned(sr_agg* a, const VTab& vt, int64_t n) {
-    sr_ctx* ctx = a->ctx;
-    int64_t done = 0;
-    const bool trace = getenv("SR_AGG_TRACE") != nullptr; // phase times (CUDA events) on stderr
-    cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (trace)
-        for (auto& e : tev) SR_CUDA(ctx, cudaEventCreate(&e));
-    while (done < n) {
-        const srd::AggDev& h = a->host;
-        const int64_t m = std::min<int64_t>(n - done, kPartitionedMaxRows); // bounded by the staging buffers
-        int log2cap = 0;
-        while ((1ull << log2cap) < h.cap) log2cap++;
-        const uint64_t table_bytes = (h.cap + 1) * agg_slot_bytes(h);
-        const char* e_slice = getenv("SR_AGG_PARTITION_SLICE_BYTES"); // tuning knob
-        const uint64_t slice_bytes = e_slice ? (uint64_t)atoll(e_slice) : kPartitionSliceBytes;
-        int log2p = 1;
-        while (log2p < 10 && (table_bytes >> log2p) > slice_bytes) log2p++;
-        if (log2p > log2cap) log2p = log2cap;
-        const int shift = log2cap - log2p;
-        const int P = 1 << log2p;
-        // one wave of resident CTAs (the scatter pass is barrier-heavy: it needs every CTA slot the SM offers)
-        SR_CUDA(ctx, cudaFuncSetAttribute(srd::k_agg_part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)srd::AGGP_SCATTER_SMEM));
-        int occ = 0;
-        SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, srd::k_agg_part_scatter, srd::AGGP_BLOCK, srd::AGGP_SCATTER_SMEM));
-        const int grid = ctx->num_sms * std::max(occ, 1);
-        SR_TRY(a->part_hist.reserve(ctx, sizeof(uint32_t) * (size_t)P * grid));
-        SR_TRY(a->part_offs.reserve(ctx, sizeof(uint64_t) * (size_t)P * grid));
-        SR_TRY(a->part_key_lo.reserve(ctx, sizeof(uint64_t) * (size_t)m));
-        if (h.wide) SR_TRY(a->part_key_hi.reserve(ctx, sizeof(uint64_t) * (size_t)m));
-        SR_TRY(a->part_nulls.reserve(ctx, (size_t)m));
-        srd::PartStage st;
-        memset(&st, 0, sizeof(st));
-        st.key_lo = a->part_key_lo.as<unsigned long long>();
-        st.key_hi = h.wide ? a->part_key_hi.as<unsigned long long>() : nullptr;
-        st.nulls = a->part_nulls.as<uint8_t>();
-        for (int f = 0; f < h.num_fns; f++) {
-            if (h.fns[f].mode == srd::M_COUNT_STAR) continue;
-            SR_TRY(a->part_val[f].reserve(ctx, sizeof(int64_t) * (size_t)m));
-            st.val[f] = a->part_val[f].as<long long>();
-        }
-        const srd::AggDev* dev = (const srd::AggDev*)a->dev.p;
-        if (trace) SR_CUDA(ctx, cudaEventRecord(tev[0], ctx->stream));
-        srd::k_agg_part_hist<<<grid, srd::AGGP_BLOCK, 0, ctx->stream>>>(dev, vt, done, m, log2p, shift, a->part_hist.as<uint32_t>());
-        SR_LAUNCH_CHECK(ctx);
-        if (trace) SR_CUDA(ctx, cudaEventRecord(tev[1], ctx->stream));
-        SR_TRY(scan_counts(ctx, &a->scan_scratch, a->part_hist.as<uint32_t>(), (int64_t)P * grid, a->part_offs.as<uint64_t>()));
-        if (trace) SR_CUDA(ctx, cudaEventRecord(tev[2], ctx->stream));
-        srd::k_agg_part_scatter<<<grid, srd::AGGP_BLOCK, srd::AGGP_SCATTER_SMEM, ctx->stream>>>(dev, vt, done, m, log2p, shift, a->part_offs.as<uint64_t>(), st);
-        SR_LAUNCH_CHECK(ctx);
-        if (trace) SR_CUDA(ctx, cudaEventRecord(tev[3], ctx->stream));
-        // bucket boundaries to the host: one launch per bucket, each with its own table slice to prefetch
-        SR_TRY(a->part_bounds.reserve(ctx, sizeof(uint64_t) * (size_t)(P + 1)));
-        srd::k_agg_part_bounds<<<1, 256, 0, ctx->stream>>>(a->part_offs.as<uint64_t>(), P, grid, (uint64_t)m, a->part_bounds.as<uint64_t>());
-        SR_LAUNCH_CHECK(ctx);
-        std::vector<uint64_t> bounds((size_t)P + 1);
-        SR_CUDA(ctx, cudaMemcpyAsync(bounds.data(), a->part_bounds.p, sizeof(uint64_t) * (size_t)(P + 1), cudaMemcpyDeviceToHost, ctx->stream));
-        SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        SR_TRY(a->part_fail.reserve(ctx, sizeof(uint32_t) * (size_t)m));
-        unsigned long long* fail_count = a->counters.as<unsigned long long>() + 4;
-        SR_CUDA(ctx, cudaMemsetAsync(fail_count, 0, 8, ctx->stream));
-        for (int b = 0; b < P; b++) {
-            const int64_t r0 = (int64_t)bounds[b], r1 = (int64_t)bounds[b + 1];
-            if (r1 <= r0) continue;
-            const int agrid = std::min(grid_for(r1 - r0, srd::AGG_BLOCK), ctx->num_sms * 8);
-            srd::k_agg_part_apply<<<agrid, srd::AGG_BLOCK, 0, ctx->stream>>>(dev, r0, r1, nullptr, (unsigned long long)b << shift,
-                                                                              (unsigned long long)(b + 1) << shift, st, a->part_fail.as<uint32_t>(), fail_count);
-            SR_LAUNCH_CHECK(ctx);
-        }
-        if (trace) {
-            SR_CUDA(ctx, cudaEventRecord(tev[4], ctx->stream));
-            SR_CUDA(ctx, cudaEventSynchronize(tev[4]));
-            float t[4];
-            for (int k = 0; k < 4; k++) cudaEventElapsedTime(&t[k], tev[k], tev[k + 1]);
-            fprintf(stderr, "[sr_agg partitioned push] rows %lld, %d buckets (table %.1f MB): histogram %.3f ms, scan %.3f ms, scatter %.3f ms, apply %.3f ms\n",
-                    (long long)m, P, table_bytes / 1048576.0, t[0], t[1], t[2], t[3]);
-        }
-        // rows refused by the admission limit: grow, re-apply them (they are few when expected_groups was honest)
-        while (true) {
-            SR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned + 8, a->counters.p, 48, cudaMemcpyDeviceToHost, ctx->stream));
-            SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            a->ngroups_host = (int64_t)ctx->pinned[8];
-            const uint64_t failed = ctx->pinned[8 + 4];
-            if (failed == 0) break;
-            if (a->host.cap >= (1ull << 33)) return sr_fail(ctx, SR_ERR_OUT_OF_MEMORY, "aggregate table would exceed 2^33 slots");
-            SR_CUDA(ctx, cudaMemsetAsync((uint8_t*)a->counters.p + 8, 0, 8, ctx->stream)); // overflow / range flags
-            SR_CUDA(ctx, cudaMemsetAsync(fail_count, 0, 8, ctx->stream));
-            SR_TRY(agg_grow(a, a->host.cap * 2));
-            SR_TRY(a->part_fail2.reserve(ctx, sizeof(uint32_t) * (size_t)failed));
-            const int agrid = std::min(grid_for((int64_t)failed, srd::AGG_BLOCK), ctx->num_sms * 8);
-            srd::k_agg_part_apply<<<agrid, srd::AGG_BLOCK, 0, ctx->stream>>>((const srd::AggDev*)a->dev.p, 0, (int64_t)failed, a->part_fail.as<uint32_t>(), 0, 0, st,
-                                                                              a->part_fail2.as<uint32_t>(), fail_count);
-            SR_LAUNCH_CHECK(ctx);
-            std::swap(a->part_fail, a->part_fail2);
-        }
-        a->partitioned_pushes++;
-        done += m;
-    }
-    if (trace)
-        for (auto& e : tev) cudaEventDestroy(e);
-    return SR_OK;
-}
+#include "sr_agg_part_host.cuh"
 
 static int32_t agg_push_vtab(sr_agg* a, const VTab& vt, int64_t n) {
     sr_ctx* ctx = a->ctx;
     if (n <= 0) return SR_OK;
     SR_TRY(agg_check_nullability(a, vt));
+    const bool fresh = !a->table_touched; // no kernel has created a group since the table was allocated / reset
+    a->table_touched = true;
     const srd::AggDev& h = a->host;
     const srd::AggDev* dev = (const srd::AggDev*)a->dev.p;
     const int grid = std::min(grid_for(n, srd::AGG_BLOCK), ctx->num_sms * 8);
@@ -1598,10 +1305,10 @@ static int32_t agg_push_vtab(sr_agg* a, const VTab& vt, int64_t n) {
         const char* e_rows = getenv("SR_AGG_PARTITION_MIN_ROWS");
         const char* e_table = getenv("SR_AGG_PARTITION_MIN_TABLE_BYTES");
         const int64_t min_rows = e_rows ? atoll(e_rows) : kPartitionedMinRows;
-        const uint64_t min_table = e_table ? (uint64_t)atoll(e_table) : kPartitionedTableBytes;
-        bool merge_fns = false; // the staged rows of the partitioned push carry one value per function, not (sum, count)
+        (void)e_table;
+        bool merge_fns = false; // the staged records of the partitioned push carry one value per function, not (sum, count)
         for (int f = 0; f < h.num_fns; f++) merge_fns |= h.fns[f].n_value_id >= 0;
-        if (!merge_fns && n >= min_rows && (h.cap + 1) * agg_slot_bytes(h) > min_table) return agg_push_partitioned(a, vt, n);
+        if (!merge_fns && n >= min_rows && h.cap > h.slice_mask + 1) return agg_push_partitioned(a, vt, n, fresh);
     }
     if ((uint64_t)a->ngroups_host + (uint64_t)n <= h.limit) {
         // cannot overflow: single fused pass

@@ -404,7 +404,8 @@ __device__ __forceinline__ bool eval_expr(const CExpr& e, Loader& ld, int64_t& o
             }
             sp--;
             st[sp - 1] = r;
-            nu[sp - 1] = nu[sp - 1] || nu[sp];
+            // a zero divisor yields NULL (ArithmeticRightZeroCheck, be/src/exprs/arithmetic_operation.h:638), DOUBLE included
+            nu[sp - 1] = nu[sp - 1] || nu[sp] || (nd.op == C_DIV_D && y == 0.0);
             break;
         }
         }

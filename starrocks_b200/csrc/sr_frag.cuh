@@ -444,6 +444,7 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
     SR_TRY(agg_check_nullability(f->agg, vt));
     if (f->agg->smem_bytes == 0 && f->smem_agg) f->smem_agg = false; // a nullability change forced global accumulation
     sr_agg* a = f->agg;
+    a->table_touched = true;
     const srd::AggDev& ah = a->host;
     const bool hash = !ah.dense && ah.num_keys > 0;
     if (hash) {

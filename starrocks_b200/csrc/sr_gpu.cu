@@ -230,6 +230,7 @@ void sr_ctx_destroy(sr_ctx* ctx) {
 
 int32_t sr_ctx_sync(sr_ctx* ctx) {
     if (!ctx) return SR_ERR_INVALID_ARGUMENT;
+    SR_LOCK(ctx);
     SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SR_OK;
 }
@@ -252,11 +253,11 @@ void* sr_ctx_stream(sr_ctx* ctx) {
     return ctx ? (void*)ctx->stream : nullptr;
 }
 
-#define SR_BIND(ctx)                                \
-    do {                                            \
-        if (!(ctx)) return SR_ERR_INVALID_ARGUMENT; \
-        cudaSetDevice((ctx)->device);               \
-    } while (0)
+// validates the context, takes its lock for the rest of the calling function and makes its device current
+#define SR_BIND(ctx)                            \
+    if (!(ctx)) return SR_ERR_INVALID_ARGUMENT; \
+    SR_LOCK(ctx);                               \
+    cudaSetDevice((ctx)->device)
 
 // ------------------------------------------------------------------ scan
 sr_scan* sr_scan_create(sr_ctx* ctx, const sr_scan_desc* desc) {
@@ -275,6 +276,7 @@ sr_scan* sr_scan_create(sr_ctx* ctx, const sr_scan_desc* desc) {
 
 void sr_scan_destroy(sr_scan* scan) {
     if (!scan) return;
+    SR_LOCK(scan->ctx);
     cudaSetDevice(scan->ctx->device);
     cudaStreamSynchronize(scan->ctx->stream);
     delete scan;
@@ -350,6 +352,7 @@ sr_join* sr_join_create(sr_ctx* ctx, const sr_join_desc* desc) {
 
 void sr_join_destroy(sr_join* join) {
     if (!join) return;
+    SR_LOCK(join->ctx);
     cudaSetDevice(join->ctx->device);
     cudaStreamSynchronize(join->ctx->stream);
     delete join;
@@ -401,7 +404,9 @@ int32_t sr_join_probe(sr_join* join, int32_t prober_id, const sr_chunk_view* pro
 }
 
 int32_t sr_join_probe_indexes(sr_join* join, int32_t prober_id, const uint32_t** probe_index_dev, const uint32_t** build_index_dev) {
-    if (!join || prober_id < 0 || prober_id >= (int)join->probers.size()) return SR_ERR_INVALID_ARGUMENT;
+    if (!join) return SR_ERR_INVALID_ARGUMENT;
+    SR_LOCK(join->ctx);
+    if (prober_id < 0 || prober_id >= (int)join->probers.size()) return SR_ERR_INVALID_ARGUMENT;
     if (probe_index_dev) *probe_index_dev = join->probers[prober_id]->probe_index.as<uint32_t>();
     if (build_index_dev) *build_index_dev = join->probers[prober_id]->build_index.as<uint32_t>();
     return SR_OK;
@@ -432,6 +437,7 @@ sr_rf* sr_rf_create(sr_ctx* ctx, int32_t key_type, int64_t expected_rows, int32_
 
 void sr_rf_destroy(sr_rf* rf) {
     if (!rf) return;
+    SR_LOCK(rf->ctx);
     cudaSetDevice(rf->ctx->device);
     cudaStreamSynchronize(rf->ctx->stream);
     delete rf;
@@ -453,6 +459,7 @@ int32_t sr_rf_insert(sr_rf* rf, const sr_chunk_view* in, int32_t slot_id, int32_
 sr_rf* sr_join_build_runtime_filter(sr_join* join, int32_t key_index, int32_t with_bloom, int32_t insert_nulls) {
     if (!join) return nullptr;
     sr_ctx* ctx = join->ctx;
+    SR_LOCK(ctx);
     cudaSetDevice(ctx->device);
     if (!join->built) {
         sr_fail(ctx, SR_ERR_STATE, "build_runtime_filter before build_finish");
@@ -568,6 +575,7 @@ int32_t sr_rf_evaluate(sr_rf* rf, const sr_chunk_view* in, int32_t slot_id, uint
 int32_t sr_scan_add_runtime_filter(sr_scan* scan, sr_rf* rf, int32_t probe_slot) {
     if (!scan || !rf) return SR_ERR_INVALID_ARGUMENT;
     sr_ctx* ctx = scan->ctx;
+    SR_LOCK(ctx);
     if (rf->ctx != ctx) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "runtime filter belongs to another context");
     if (scan->rfs.size() >= SR_MAX_SCAN_RFS) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "more than %d runtime filters on one scan", SR_MAX_SCAN_RFS);
     scan->rfs.emplace_back(rf, probe_slot);
@@ -612,6 +620,7 @@ sr_agg* sr_agg_create(sr_ctx* ctx, const sr_agg_desc* desc) {
 
 void sr_agg_destroy(sr_agg* agg) {
     if (!agg) return;
+    SR_LOCK(agg->ctx);
     cudaSetDevice(agg->ctx->device);
     cudaStreamSynchronize(agg->ctx->stream);
     delete agg;
@@ -693,6 +702,7 @@ static int32_t agg_reset_impl(sr_agg* a) {
     a->out_rows = -1;
     a->cursor = 0;
     a->ngroups_host = 0;
+    a->table_touched = false;
     if (!a->compiled) return SR_OK;
     srd::AggDev& h = a->host;
     const bool hash = !h.dense && h.num_keys > 0;
@@ -954,6 +964,7 @@ int32_t sr_agg_merge(sr_agg* a, sr_agg* o) {
         while ((uint64_t)a->ngroups_host + ng_o > a->host.limit) SR_TRY(agg_grow(a, a->host.cap * 4));
     }
     const uint64_t total_o = (!oh.dense && oh.num_keys > 0) ? oh.cap + 1 : oh.cap;
+    a->table_touched = true;
     srd::k_agg_merge<<<std::min(grid_for((int64_t)total_o, 256), ctx->num_sms * 16), 256, 0, ctx->stream>>>((const srd::AggDev*)o->dev.p,
                                                                                                             (const srd::AggDev*)a->dev.p);
     SR_LAUNCH_CHECK(ctx);
@@ -970,6 +981,7 @@ int32_t sr_agg_merge(sr_agg* a, sr_agg* o) {
 // ------------------------------------------------------------------ fragment
 sr_fragment* sr_fragment_create(sr_ctx* ctx, const sr_fragment_desc* desc) {
     if (!ctx || !desc) return nullptr;
+    SR_LOCK(ctx);
     cudaSetDevice(ctx->device);
     if (desc->num_joins < 0 || desc->num_joins > SR_MAX_FRAG_JOINS || desc->scan.num_preds < 0 || desc->scan.num_filter_exprs < 0) {
         sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "fragment desc counts");
@@ -1023,6 +1035,7 @@ sr_fragment* sr_fragment_create(sr_ctx* ctx, const sr_fragment_desc* desc) {
 
 void sr_fragment_destroy(sr_fragment* frag) {
     if (!frag) return;
+    SR_LOCK(frag->ctx);
     cudaSetDevice(frag->ctx->device);
     cudaStreamSynchronize(frag->ctx->stream);
     delete frag->agg;
@@ -1041,6 +1054,7 @@ sr_agg* sr_fragment_agg(sr_fragment* frag) {
 
 int32_t sr_fragment_get_plan(sr_fragment* frag, sr_fragment_plan* plan) {
     if (!frag || !plan) return SR_ERR_INVALID_ARGUMENT;
+    SR_LOCK(frag->ctx);
     if (!frag->compiled) return sr_fail(frag->ctx, SR_ERR_STATE, "the fragment plans on its first push");
     memset(plan, 0, sizeof(*plan));
     plan->num_joins = frag->num_joins;
@@ -1110,6 +1124,7 @@ sr_xchg* sr_xchg_create(sr_ctx* ctx, const sr_part_desc* desc) {
 
 void sr_xchg_destroy(sr_xchg* x) {
     if (!x) return;
+    SR_LOCK(x->ctx);
     cudaSetDevice(x->ctx->device);
     cudaStreamSynchronize(x->ctx->stream);
     delete x;

@@ -28,7 +28,13 @@ struct sr_ctx {
     uint64_t* dscratch = nullptr; // 64 x u64 on device
     void* l2_flush = nullptr;
     size_t l2_flush_bytes = 0;
+    // Every entry point that enqueues work or touches the context's scratch (pinned / dscratch counters, err, launches,
+    // dev_bytes, the per-handle prober list) holds this lock for its whole duration: handles of one context may be driven
+    // from several pipeline-driver threads (build thread, N prober threads, the poller), but all their work goes to the one
+    // stream anyway, so serialising the host side costs nothing and keeps the shared scratch slots private to a call.
+    std::recursive_mutex mu;
 };
+#define SR_LOCK(ctx) std::lock_guard<std::recursive_mutex> _sr_lock((ctx)->mu)
 
 static thread_local std::string g_create_err;
 

@@ -374,7 +374,7 @@ struct sr_join {
     int32_t has_dup = 0;
     int64_t min_value = 0, max_value = 0, bucket_size = 0, null_keys = 0;
     uint32_t hmask = 0, hlog = 0;
-    DevBuf keys, knulls, first, next, hkeys, bitmap, flags;
+    DevBuf keys, knulls, first, next, hkeys, bitmap, flags, zero_row;
     Staged staged_build;
     std::vector<ProberState*> probers;
     ~sr_join() {
@@ -707,15 +707,27 @@ static int32_t join_probe(sr_join* j, int32_t prober_id, const sr_chunk_view* pr
         } else {
             slot = j->desc.build_out_slots[k - np];
             const BuildCol* bc = j->find_col(slot);
-            if (!bc) {
-                if (j->cols.empty()) return sr_fail(ctx, SR_ERR_STATE, "build side is empty and its column types are unknown (slot %d)", slot);
+            if (bc) {
+                g.src = bc->data.p;
+                g.src_nulls = bc->nullable ? (const uint8_t*)bc->nulls.p : nullptr;
+                g.width = bc->width;
+                type = bc->type;
+            } else if (j->cols.empty() && j->desc.build_out_types[k - np] != 0) {
+                // no build chunk ever arrived (a dimension scan that filtered everything out): the schema comes from the
+                // desc; INNER probes to zero rows, LEFT OUTER to one all-NULL build row per probe row (index 0 = "no row")
+                type = j->desc.build_out_types[k - np];
+                g.width = srd::type_width(type);
+                if (g.width == 0) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "build_out_types[%d] = %d is not a type", k - np, type);
+                SR_TRY(j->zero_row.reserve(ctx, 16));
+                SR_CUDA(ctx, cudaMemsetAsync(j->zero_row.p, 0, 16, ctx->stream));
+                g.src = j->zero_row.p;
+                g.src_nulls = nullptr;
+            } else {
+                if (j->cols.empty())
+                    return sr_fail(ctx, SR_ERR_STATE, "build side is empty and the type of slot %d is unknown: declare it in sr_join_desc.build_out_types", slot);
                 return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "build chunk misses output slot %d", slot);
             }
-            g.src = bc->data.p;
-            g.src_nulls = bc->nullable ? (const uint8_t*)bc->nulls.p : nullptr;
-            g.width = bc->width;
             g.zero_is_null = outer ? 1 : 0;
-            type = bc->type;
         }
         const bool need_nulls = g.src_nulls != nullptr || g.zero_is_null;
         SR_TRY(ps.out_bufs[2 * k].reserve(ctx, (size_t)std::max<int64_t>(total, 1) * g.width));

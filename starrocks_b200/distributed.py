@@ -11,10 +11,30 @@ import torch
 import torch.distributed as dist
 
 
+def _to_i64_bits(c):
+    """a state column as int64 WORDS: integers by value, floating-point states bit for bit (a DOUBLE sum must not be
+    rounded to an integer on its way through the packed int64 exchange buffer)"""
+    if c.dtype == torch.float64:
+        return c.contiguous().view(torch.int64)
+    if c.dtype == torch.float32:
+        return c.to(torch.float64).view(torch.int64)      # exact; _from_i64_bits narrows it back
+    if c.dtype.is_floating_point:
+        raise TypeError(f"state column of dtype {c.dtype}")
+    return c.to(torch.int64)
+
+
+def _from_i64_bits(t, dtype):
+    if dtype == torch.float64:
+        return t.contiguous().view(torch.float64)
+    if dtype == torch.float32:
+        return t.contiguous().view(torch.float64).to(torch.float32)
+    return t.to(dtype)
+
+
 def gather_partial_states(cols, max_rows, dst=0):
-    """cols: list of 1-D integer tensors (same length g <= max_rows) holding a rank's partial aggregate rows
-    (group keys and states).  Returns on `dst` a list (one entry per rank) of lists of tensors trimmed to each
-    rank's row count; None elsewhere."""
+    """cols: list of 1-D tensors (same length g <= max_rows) holding a rank's partial aggregate rows (group keys and
+    states; integer or floating point, every rank passes the same dtypes).  Returns on `dst` a list (one entry per rank)
+    of lists of tensors of the same dtypes trimmed to each rank's row count; None elsewhere."""
     world, rank = dist.get_world_size(), dist.get_rank()
     g = int(cols[0].numel())
     if g > max_rows:
@@ -22,7 +42,7 @@ def gather_partial_states(cols, max_rows, dst=0):
     dev = cols[0].device
     part = torch.zeros((len(cols), max_rows), dtype=torch.int64, device=dev)
     for k, c in enumerate(cols):
-        part[k, :g] = c.to(torch.int64)
+        part[k, :g] = _to_i64_bits(c)
     cnt = torch.tensor([g], dtype=torch.int64, device=dev)
     parts = [torch.empty_like(part) for _ in range(world)] if rank == dst else None
     cnts = [torch.empty_like(cnt) for _ in range(world)] if rank == dst else None
@@ -33,7 +53,7 @@ def gather_partial_states(cols, max_rows, dst=0):
     out = []
     for p, c in zip(parts, cnts):
         gg = int(c.item())
-        out.append([p[k, :gg].contiguous() for k in range(len(cols))])
+        out.append([_from_i64_bits(p[k, :gg], cols[k].dtype) for k in range(len(cols))])
     return out
 
 
@@ -53,8 +73,9 @@ def device_view(ptr, n, width, device):
 
 def all_gather_partial_states(cols, max_rows, dst=0):
     """Same exchange as gather_partial_states in ONE collective and one host sync: every rank contributes a packed
-    [len(cols) * max_rows + 1] int64 buffer (last word = its row count); `dst` returns one concatenated int64 tensor
-    per column (rank 0's rows first), the others return None without waiting."""
+    [len(cols) * max_rows + 1] int64 buffer (last word = its row count; floating-point states travel bit for bit); `dst`
+    returns one concatenated tensor per column in the column's own dtype (rank 0's rows first), the others return None
+    without waiting."""
     world, rank = dist.get_world_size(), dist.get_rank()
     g = int(cols[0].numel())
     if g > max_rows:
@@ -63,7 +84,7 @@ def all_gather_partial_states(cols, max_rows, dst=0):
     nc = len(cols)
     packed = torch.zeros(nc * max_rows + 1, dtype=torch.int64, device=dev)
     for k, c in enumerate(cols):
-        packed[k * max_rows:k * max_rows + g] = c
+        packed[k * max_rows:k * max_rows + g] = _to_i64_bits(c)
     packed[-1] = g
     flat = torch.empty(world * (nc * max_rows + 1), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(flat, packed)
@@ -71,7 +92,7 @@ def all_gather_partial_states(cols, max_rows, dst=0):
         return None
     out = flat.view(world, nc * max_rows + 1)
     counts = [int(x) for x in out[:, -1].tolist()]
-    return [torch.cat([out[r, k * max_rows:k * max_rows + counts[r]] for r in range(world)]) for k in range(nc)]
+    return [_from_i64_bits(torch.cat([out[r, k * max_rows:k * max_rows + counts[r]] for r in range(world)]), cols[k].dtype) for k in range(nc)]
 
 
 _REDUCE_OPS = {0: "SUM", 1: "MIN", 2: "MAX"}

@@ -249,6 +249,65 @@ def test_join_empty_sides(gpu, ctx):
         j.close()
 
 
+@pytest.mark.parametrize("join_type", [abi.JOIN_INNER, abi.JOIN_LEFT_OUTER, abi.JOIN_LEFT_SEMI, abi.JOIN_LEFT_ANTI])
+def test_join_build_side_never_appended(gpu, ctx, join_type):
+    # A dimension scan that filters everything out hands the build operator no chunk at all: build_finish without any
+    # append.  With the build schema declared in the desc (the reference knows it from the plan's row descriptor,
+    # exec/hash_joiner.h:66-133) the probe returns zero rows (INNER / SEMI), every probe row (ANTI), or every probe row
+    # padded with typed NULL build columns (LEFT OUTER) -- not an error.
+    d = abi.make_join_desc(join_type, [1], [0], [abi.TYPE_INT], build_out=[1, 2], probe_out=[0],
+                           build_out_types=[abi.TYPE_INT, abi.TYPE_BIGINT])
+    j = gpu.Join(ctx, d)
+    try:
+        j.build_finish()
+        keys = np.arange(10, dtype=np.int32)
+        out = j.probe(Chunk([(0, keys, None)]))
+        semi = join_type in (abi.JOIN_LEFT_SEMI, abi.JOIN_LEFT_ANTI)
+        assert out.num_rows == (0 if join_type in (abi.JOIN_INNER, abi.JOIN_LEFT_SEMI) else 10)
+        assert out.num_cols == (1 if semi else 3)
+        got = gpu.chunk_out_to_host(ctx, out)
+        if not semi:
+            assert [g[1] for g in got] == [abi.TYPE_INT, abi.TYPE_INT, abi.TYPE_BIGINT]
+        if join_type == abi.JOIN_LEFT_OUTER:
+            assert got[0][2].tolist() == keys.tolist()
+            assert got[1][3].tolist() == [1] * 10 and got[2][3].tolist() == [1] * 10      # NULL-padded build columns
+        if join_type == abi.JOIN_LEFT_ANTI:
+            assert got[0][2].tolist() == keys.tolist()
+    finally:
+        j.close()
+    # without declared types the old, loud failure stays
+    j = gpu.Join(ctx, abi.make_join_desc(abi.JOIN_LEFT_OUTER, [1], [0], [abi.TYPE_INT], build_out=[1], probe_out=[0]))
+    try:
+        j.build_finish()
+        with pytest.raises(gpu.GpuError) as ei:
+            j.probe(Chunk([(0, np.arange(4, dtype=np.int32), None)]))
+        assert ei.value.code == abi.SR_ERR_STATE
+    finally:
+        j.close()
+
+
+def test_divide_by_zero_is_null_gpu(gpu, ctx, oracle):
+    # ArithmeticRightZeroCheck (be/src/exprs/arithmetic_operation.h:638): x / 0 -> NULL, skipped by SUM / COUNT / MIN
+    rng = np.random.default_rng(3)
+    n = 100_003
+    a = rng.integers(-50, 50, n, dtype=np.int64)
+    b = rng.integers(-3, 4, n, dtype=np.int64)
+    g = rng.integers(0, 7, n, dtype=np.int32)
+    q = [("col", 0), ("col", 1), "/"]
+    d = abi.make_agg_desc([2], [abi.TYPE_INT], fns=[(abi.AGG_SUM, abi.TYPE_DOUBLE, 10, q), (abi.AGG_COUNT, abi.TYPE_DOUBLE, 11, q),
+                                                     (abi.AGG_MIN, abi.TYPE_DOUBLE, 12, q), (abi.AGG_COUNT_STAR, 0, 13, None)], ranges=[(0, 6)])
+    ch = Chunk([(0, a, None), (1, b, None), (2, g, None)])
+    ga, oa = gpu.Agg(ctx, d), oracle.Agg(d)
+    try:
+        ga.push(ch)
+        oa.push(ch)
+        rows = gpu_rows(ga.result())
+        assert_rows_equal(rows, oracle_rows(oa), float_cols=(1,))
+        assert sum(r[2] for r in rows) == int((b != 0).sum())      # COUNT(a / b) counts the rows with a non-zero divisor
+    finally:
+        ga.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # hash aggregate (K13-K17)
 # ---------------------------------------------------------------------------------------------
@@ -412,18 +471,23 @@ def test_agg_hash_growth_two_pass(gpu, ctx, oracle):
         ga.close()
 
 
-@pytest.mark.parametrize("wide,expected,nkeys,n", [(False, 0, 300_000, 700_000), (True, 0, 300_000, 700_000),
-                                                    (False, 0, 5_000_000, 1_700_000), (False, 16_000_000, 3_000_000, 5_000_000)])
-def test_agg_partitioned_push_parity(gpu, ctx, oracle, monkeypatch, wide, expected, nkeys, n):
-    # Tables far larger than L2 take the radix-partitioned push (scatter by home-slot range, apply bucket by bucket
-    # with the table slice prefetched into L2); the thresholds are lowered through the library's tuning knobs so that
-    # small inputs reach it.  A following small batch takes the direct path.  Third case: more groups than the table
-    # admits (2^21 slots, limit 2^20) -> refused rows are re-applied after a growth.  Fourth: default thresholds.
-    if expected == 0:
-        monkeypatch.setenv("SR_AGG_PARTITION_MIN_ROWS", "100000")
-        monkeypatch.setenv("SR_AGG_PARTITION_MIN_TABLE_BYTES", str(1 << 20))
+@pytest.mark.parametrize("wide,expected,nkeys,n,force_l2", [(False, 0, 300_000, 700_000, False), (True, 0, 300_000, 700_000, False),
+                                                             (False, 0, 5_000_000, 1_700_000, False), (False, 16_000_000, 3_000_000, 5_000_000, False),
+                                                             (False, 0, 40_000_000, 6_000_000, False), (True, 0, 300_000, 700_000, True),
+                                                             (False, 0, 5_000_000, 1_700_000, True)])
+def test_agg_partitioned_push_parity(gpu, ctx, oracle, monkeypatch, wide, expected, nkeys, n, force_l2):
+    # Large batches into a hash table of more than one slice take the radix-partitioned push (sr_agg_part.cuh: bucket
+    # histogram, one or two scatter levels, one CTA per table slice applying its bucket in shared memory); the row
+    # threshold is lowered through the library's tuning knob so that small inputs reach it.  A following small batch takes
+    # the direct path.  Fourth case: 2^15 buckets -> two scatter levels.  Fifth: ~5.6 M groups into the initial 2^21-slot
+    # table: every slice overflows, the buckets are re-applied with global atomics after a growth.  force_l2: the fallback
+    # for tables of more than 2^15 slices (buckets of several slices, global atomics on an L2-prefetched range).
+    monkeypatch.setenv("SR_AGG_PARTITION_MIN_ROWS", "100000")
+    if force_l2:
+        monkeypatch.setenv("SR_AGG_PARTITION_FORCE_L2", "1")
     rng = np.random.default_rng(21)
     k64 = rng.integers(0, nkeys, n, dtype=np.int64) * 1_000_003 - 7
+    k64[::1000] = -1            # the table's empty marker as a legal key (special slot)
     k32 = rng.integers(0, 3, n, dtype=np.int32)
     v = rng.integers(-1000, 1000, n, dtype=np.int64)
     vn = rand_nulls(rng, n, 0.1)
@@ -438,11 +502,48 @@ def test_agg_partitioned_push_parity(gpu, ctx, oracle, monkeypatch, wide, expect
     ga, oa = gpu.Agg(ctx, d), oracle.Agg(d)
     try:
         launches0 = ctx.launches
-        for lo, hi in ((0, n - 50_000), (n - 50_000, n)):
+        for lo, hi in ((0, n // 2), (n // 2, n - 50_000), (n - 50_000, n)):   # fresh table, loaded slices, direct push
             ga.push(sub(lo, hi))
             oa.push(sub(lo, hi))
-        assert ctx.launches - launches0 >= 8          # histogram + scan + scatter + bounds + one apply per bucket
+        assert ctx.launches - launches0 >= 9          # 2 x (histogram + prepare + scatter + apply) + the direct push
         assert_rows_equal(gpu_rows(ga.result()), oracle_rows(oa))
+    finally:
+        ga.close()
+
+
+@pytest.mark.parametrize("shape", ["sum_count", "count_only", "decimal128", "double_minmax"])
+def test_agg_partitioned_push_shapes(gpu, ctx, oracle, monkeypatch, shape):
+    # record shapes of the partitioned push: the SIMPLE plan (one plain key, plain column inputs: the 1e9-row / 1e8-key
+    # config of BASELINE.json), a key-only record, 128-bit sums (multi-word shared-memory adds with carries) and
+    # double SUM / MIN / MAX (CAS-loop shared atomics); int32 key -> masked to its width in the record
+    monkeypatch.setenv("SR_AGG_PARTITION_MIN_ROWS", "100000")
+    rng = np.random.default_rng(5)
+    n = 900_000
+    k64 = rng.integers(0, 200_000, n, dtype=np.int64) * 7919 - 3
+    k32 = rng.integers(-100_000, 100_000, n, dtype=np.int32)
+    v = rng.integers(-(1 << 40), 1 << 40, n, dtype=np.int64)
+    dv = rng.normal(0, 1e6, n)
+    if shape == "sum_count":
+        d = abi.make_agg_desc([0], [abi.TYPE_BIGINT], fns=[(abi.AGG_SUM, abi.TYPE_BIGINT, 10, [("col", 2)]), (abi.AGG_COUNT_STAR, 0, 11, None)])
+        cols = [(0, k64, None), (2, v, None)]
+    elif shape == "count_only":
+        d = abi.make_agg_desc([1], [abi.TYPE_INT], fns=[(abi.AGG_COUNT_STAR, 0, 11, None)])
+        cols = [(1, k32, None)]
+    elif shape == "decimal128":
+        d = abi.make_agg_desc([1], [abi.TYPE_INT], fns=[(abi.AGG_SUM, abi.TYPE_DECIMAL64, 10, [("col", 2)]), (abi.AGG_COUNT_STAR, 0, 11, None)])
+        cols = [(1, k32, None), (2, v, None, abi.TYPE_DECIMAL64)]
+    else:
+        d = abi.make_agg_desc([0], [abi.TYPE_BIGINT], fns=[(abi.AGG_SUM, abi.TYPE_DOUBLE, 10, [("col", 3)]), (abi.AGG_MIN, abi.TYPE_DOUBLE, 11, [("col", 3)]),
+                                                            (abi.AGG_MAX, abi.TYPE_DOUBLE, 12, [("col", 3)]), (abi.AGG_AVG, abi.TYPE_BIGINT, 13, [("col", 2)])])
+        cols = [(0, k64, None), (2, v >> 20, None), (3, dv, None)]
+    ga, oa = gpu.Agg(ctx, d), oracle.Agg(d)
+    try:
+        half = n // 2
+        for lo, hi in ((0, half), (half, n)):
+            ch = Chunk([(c[0], c[1][lo:hi].copy(), None) + tuple(c[3:]) for c in cols])
+            ga.push(ch)
+            oa.push(ch)
+        assert_rows_equal(gpu_rows(ga.result()), oracle_rows(oa), float_cols=(1, 4) if shape == "double_minmax" else ())
     finally:
         ga.close()
 

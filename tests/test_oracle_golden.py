@@ -518,3 +518,23 @@ def test_agg_compressed_key_sql_goldens(oracle):
         a.push(chunk)
         return oracle_rows(a)
     _compressed_key_check(run)
+
+
+def test_divide_by_zero_is_null(oracle):
+    # VectorizedDiv runs under ArithmeticRightZeroCheck (be/src/exprs/arithmetic_operation.h:638): x / 0 is NULL, for
+    # DOUBLE as well as for integers cast to DOUBLE; SUM / COUNT over the quotient skip those rows
+    a = np.array([6, 7, 8, 9], dtype=np.int64)
+    b = np.array([3, 0, 2, 0], dtype=np.int64)
+    vals, nul = oracle.eval_expr(abi.make_expr([("col", 0), ("col", 1), "/"]), Chunk([(0, a, None), (1, b, None)]))
+    assert nul.tolist() == [0, 1, 0, 1]
+    assert vals[0] == 2.0 and vals[2] == 4.0
+    x = np.array([1.5, -2.0, 0.0], dtype=np.float64)
+    y = np.array([0.0, 0.5, 0.0], dtype=np.float64)
+    vals, nul = oracle.eval_expr(abi.make_expr([("col", 0), ("col", 1), "/"]), Chunk([(0, x, None), (1, y, None)]))
+    assert nul.tolist() == [1, 0, 1] and vals[1] == -4.0
+    d = abi.make_agg_desc(fns=[(abi.AGG_SUM, abi.TYPE_DOUBLE, 10, [("col", 0), ("col", 1), "/"]),
+                               (abi.AGG_COUNT, abi.TYPE_DOUBLE, 11, [("col", 0), ("col", 1), "/"])])
+    ag = oracle.Agg(d)
+    ag.push(Chunk([(0, a, None), (1, b, None)]))
+    out = ag.output()
+    assert out[0][1][0] == 6.0 and out[1][1][0] == 2          # 6/3 + 8/2, two non-NULL quotients

@@ -36,7 +36,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=1_000_000_000)
     ap.add_argument("--keys", type=int, default=100_000_000)
-    ap.add_argument("--morsel", type=int, default=100_000_000)
+    ap.add_argument("--morsel", type=int, default=1_000_000_000)
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
