@@ -193,7 +193,17 @@ __device__ __forceinline__ void hkey_or(HKey& k, unsigned long long bits, int sh
 __device__ __forceinline__ unsigned long long hkey_bits(const HKey& k, int shift) { return shift < 64 ? k.lo >> shift : k.hi >> (shift - 64); }
 __device__ __forceinline__ bool hkey_is_empty(const AggDev& a, const HKey& k) { return k.lo == SR_AGG_EMPTY && (!a.wide || k.hi == SR_AGG_EMPTY); }
 __device__ __forceinline__ bool hkey_eq(const AggDev& a, const HKey& x, const HKey& y) { return x.lo == y.lo && (!a.wide || x.hi == y.hi); }
-__device__ __forceinline__ unsigned long long hkey_hash(const AggDev& a, const HKey& k) { return a.wide ? mix64(k.lo ^ mix64(k.hi + 0x9e3779b97f4a7c15ull)) : mix64(k.lo); }
+// xorshift - multiply - xorshift: half the instructions of the murmur finaliser (mix64), and the radix-partitioned push
+// hashes every row three times.  The leading fold keeps keys that differ only in their high bits (ids shifted left, packed
+// second columns) apart in the LOW bits, which pick the slot inside a 256-slot probing slice.
+__device__ __forceinline__ unsigned long long agg_hash64(unsigned long long x) {
+    x ^= x >> 32;
+    x *= 0x9E3779B97F4A7C15ull;
+    return x ^ (x >> 29);
+}
+__device__ __forceinline__ unsigned long long hkey_hash(const AggDev& a, const HKey& k) {
+    return a.wide ? agg_hash64(k.lo ^ (agg_hash64(k.hi) + 0x632BE59BD9B4E019ull)) : agg_hash64(k.lo);
+}
 __device__ __forceinline__ HKey hkey_load(const AggDev& a, unsigned long long s) {
     if (!a.wide) return HKey{a.hkeys[s], 0};
     HKey v; // ONE 16-byte access: a claim publishes both words at once, a split load could pair an old lo with a new hi
@@ -914,9 +924,8 @@ struct sr_agg {
     DevBuf acc0[SR_MAX_AGG_FNS], acc1[SR_MAX_AGG_FNS], accn[SR_MAX_AGG_FNS];
     DevBuf slots_tmp;
     // radix-partitioned push (sr_agg_part.cuh): bucket histogram / bases / cursors, tile list, staged records, retry lists
-    DevBuf part_hist, part_base, part_cursor, part_tiles, part_rec[2], part_fail, part_fail64, part_fail64b;
+    DevBuf part_cursor, part_tiles, part_rec[2], part_ovf, part_fail, part_fail64, part_fail64b;
     int64_t partitioned_pushes = 0;
-    int slice_log2_max = 12;    // slots per probing slice (fixed when the plan is compiled, see agg_compile)
     bool table_touched = false; // some kernel may have created groups since the table was allocated / reset
     Staged staged;
     int64_t ngroups_host = 0; // hash mode: groups after the last synchronising push
@@ -986,11 +995,11 @@ static int32_t agg_alloc_tables(sr_agg* a, srd::AggDev* h, uint64_t cap, DevBuf*
     const int grid = std::min(grid_for((int64_t)total, 256), ctx->num_sms * 8);
     h->cap = cap;
     h->mask = cap - 1;
-    h->limit = hash ? cap / 4 * 3 : ~0ull;
+    h->limit = hash ? cap / 2 : ~0ull;
     if (hash) {
         int log2cap = 0;
         while ((1ull << log2cap) < cap) log2cap++;
-        h->slice_log2 = std::min(a->slice_log2_max, log2cap);
+        h->slice_log2 = std::min((int)srd::AGGP_SLICE_LOG2, log2cap);
         h->slice_mask = (1ull << h->slice_log2) - 1;
     } else {
         h->slice_log2 = 0;
@@ -1031,14 +1040,7 @@ static int32_t agg_alloc_tables(sr_agg* a, srd::AggDev* h, uint64_t cap, DevBuf*
 }
 
 // bytes of table state one group slot owns (keys + COUNT(*) + every accumulator array)
-static uint64_t agg_slot_bytes(const srd::AggDev& h) {
-    uint64_t b = 8 * (h.wide ? 2 : 1) + 8;
-    for (int f = 0; f < h.num_fns; f++) {
-        if (h.fns[f].mode == srd::M_COUNT_STAR) continue;
-        b += 8 + (h.fns[f].mode == srd::M_SUM_I128 ? 8 : 0) + (h.fns[f].track_n ? 8 : 0);
-    }
-    return b;
-}
+static uint64_t agg_slot_bytes(const srd::AggDev& h) { return (uint64_t)srd::agg_slot_bytes_of(h); }
 
 typedef int32_t (*agg_type_fn)(void* user, int32_t slot);
 typedef bool (*agg_nullable_fn)(void* user, int32_t slot);
@@ -1173,15 +1175,8 @@ static int32_t agg_compile(sr_agg* a, slot_type_fn tf, agg_nullable_fn nf, void*
     if (!h.dense) {
         if (h.key_bytes > 16) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "packed group-by key of %d bytes (> 16) without usable ranges", h.key_bytes);
         cap = 1ull << 21;
-        const uint64_t want = d.expected_groups > 0 ? (uint64_t)d.expected_groups / 3 * 4 + 4 : 0; // load <= 3/4
+        const uint64_t want = d.expected_groups > 0 ? (uint64_t)d.expected_groups * 2 : 0; // load <= 1/2: a probe sequence stays in its 256-slot slice
         while (cap < want) cap <<= 1;
-        // probing slice: the largest power of two of slots whose keys + states fit 96 KB of shared memory (two CTAs per
-        // SM in k_aggp_apply_smem).  The slice size is part of the table's probing rule and cannot change once groups
-        // exist: when a column turns nullable later (one more state array per function), the slices may no longer fit and
-        // the partitioned push falls back to its global-atomics apply.
-        const uint64_t slot_bytes = agg_slot_bytes(h);
-        a->slice_log2_max = 12;
-        while (a->slice_log2_max > 6 && (slot_bytes << a->slice_log2_max) > 96 * 1024) a->slice_log2_max--;
     }
     SR_TRY(a->counters.reserve(ctx, 64));
     SR_CUDA(ctx, cudaMemsetAsync(a->counters.p, 0, 64, ctx->stream));
@@ -1308,7 +1303,7 @@ static int32_t agg_push_vtab(sr_agg* a, const VTab& vt, int64_t n) {
         (void)e_table;
         bool merge_fns = false; // the staged records of the partitioned push carry one value per function, not (sum, count)
         for (int f = 0; f < h.num_fns; f++) merge_fns |= h.fns[f].n_value_id >= 0;
-        if (!merge_fns && n >= min_rows && h.cap > h.slice_mask + 1) return agg_push_partitioned(a, vt, n, fresh);
+        if (!merge_fns && n >= min_rows) return agg_push_partitioned(a, vt, n, fresh);
     }
     if ((uint64_t)a->ngroups_host + (uint64_t)n <= h.limit) {
         // cannot overflow: single fused pass

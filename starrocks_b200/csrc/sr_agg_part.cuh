@@ -3,31 +3,32 @@
 // Replaces, for large batches, the row-at-a-time lazy_emplace + update of
 //   AggHashMap*::compute_agg_states            be/src/exec/aggregate/agg_hash_map.h:303-361
 //   Aggregator::compute_batch_agg_states       be/src/exec/aggregator.cpp:1616-1640
-// whose GPU transcription (k_agg_push) pays one L2 atomic transaction per row and state word (measured round 1:
-// ~60-90 G atomics/s whatever the table size).  Here the batch is first moved next to the table slice it will update:
+// whose GPU transcription (k_agg_push) pays one L2 atomic transaction per row and state word (measured: 60-90 G
+// atomics/s whatever the table size).  Here the batch is first moved next to the table slices it updates:
 //
-//   k_aggp_hist      one pass over the key columns: rows per BUCKET (bucket = top bits of the row's home slot)
-//   k_aggp_prepare   exclusive scan -> bucket bases, write cursors, tile list of the second scatter level
-//   k_aggp_scatter   packed RECORDS (key, evaluated function inputs, null mask; W 8-byte words) are counting-sorted by
-//                    bucket inside a shared-memory tile, then every bucket's run is copied out contiguously (space
-//                    reserved with ONE atomicAdd per (tile, bucket) on the bucket cursor).  Up to 2^9 buckets take one
-//                    level; up to 2^15 take two (fan-out <= 2^8 each, so runs stay >= 16 records long)
-//   k_aggp_apply_smem one CTA per bucket = per table SLICE: the slice's key / state arrays are loaded into shared
-//                    memory (or initialised there when the table is still empty), the bucket's records are applied with
-//                    shared-memory atomics (64-bit CAS claim, 32-bit adds with carry), the slice is written back with
-//                    coalesced stores.  HBM traffic per row: W*8 bytes x (1 write + 1 read) per level + the table once.
-//   k_aggp_apply_l2  fallback when a bucket spans more than one slice (tables beyond 2^15 slices) and for the records of
-//                    slices that overflowed: global atomics on the L2-prefetched table range, as in round 1.
+//   k_aggp_scatter   packed RECORDS (key, evaluated function inputs, null mask; W 8-byte words) are partitioned by the
+//                    top bits of their home slot.  Inside a tile every warp ranks its rows with match.any + a warp-private
+//                    counter per bucket (no atomics), the counters are scanned, the tile is copied out bucket by bucket
+//                    into the buckets' regions (ONE global atomicAdd per tile and non-empty bucket reserves the run).
+//                    Regions have a fixed capacity (mean + 6 sigma of a uniform hash); what does not fit goes to an
+//                    overflow list -- no histogram pass.  Fan-out <= 2^9 per level, two levels for up to 2^18 buckets.
+//   k_aggp_tiles     tile list of the second level from the first level's counts
+//   k_aggp_apply     one CTA per bucket (a few 256-slot probing slices of the table, 48 KB of keys + states): the slices are
+//                    loaded / initialised in shared memory, the bucket's records are applied with shared-memory atomics,
+//                    the slices are written back with coalesced stores.
+//   k_aggp_apply_l2  global-atomics apply for the overflow list, for slices that filled up, and for tables of more
+//                    than 2^18 buckets (buckets of several CTA-loads: table range prefetched into L2, as in round 1).
 #pragma once
 
 namespace srd {
 
-constexpr int AGGP_BLOCK = 512;
-constexpr int AGGP_MAX_BITS = 15;       // buckets of one push: the histogram of 2^15 counters lives in shared memory
-constexpr int AGGP_ONE_LEVEL_BITS = 9;  // up to 2^9 buckets are scattered in one level
-constexpr int AGGP_THREAD_WORDS = 16;   // record words a thread keeps in registers per tile
+constexpr int AGGP_BLOCK = 256;          // scatter CTA: 8 warps, four CTAs per SM
+constexpr int AGGP_WARPS = AGGP_BLOCK / 32;
+constexpr int AGGP_MAX_FAN_BITS = 9;     // fan-out of one scatter level
+constexpr int AGGP_MAX_FAN = 1 << AGGP_MAX_FAN_BITS;
 constexpr int AGGP_MAX_WORDS = 2 + SR_MAX_AGG_FNS + 1;
-constexpr int AGGP_MAX_FAN = 512;    // fan-out of one scatter level
+constexpr int AGGP_SLICE_LOG2 = 8;       // slots of one probing slice (owned by one warp in k_aggp_apply)
+constexpr int AGGP_MAX_APPLY_SLICES = 8; // probing slices per bucket (one apply CTA loads a bucket's slices)
 
 enum PartWordKind : int32_t { WK_KEY_LO = 0, WK_KEY_HI = 1, WK_VALUE = 2, WK_NULLS = 3 };
 
@@ -37,160 +38,106 @@ struct PartPlan {
     int32_t bucket_shift; // bucket = (hash & mask) >> bucket_shift
     int32_t words;        // W: 8-byte words per record
     int32_t null_word;    // word holding the null mask (bit f: input of function f is NULL), -1: no input is nullable
-    int32_t pad;
+    int32_t apply_slices; // probing slices per bucket (k_aggp_apply)
     int32_t word_kind[AGGP_MAX_WORDS];
     int32_t word_fn[AGGP_MAX_WORDS];
     int32_t val_word[SR_MAX_AGG_FNS]; // word of function f's input, -1 for COUNT(*)
     // SIMPLE plans (one non-nullable group-by column of <= 8 bytes, every function input a plain non-nullable column):
     // word 0 = the key column's value & simple_key_mask, word w = value id word_vid[w]; no expression interpreter
     int32_t simple;
-    int32_t word_vid[AGGP_MAX_WORDS];
+    int32_t word_w8[4];        // SIMPLE: 1 = the word's column holds 8-byte values, 0 = 4-byte signed integers
+    const void* word_ptr[4];   // SIMPLE: the word's column
     unsigned long long simple_key_mask;
+    unsigned long long cap1, cap2; // records a first-level / final bucket region can take
 };
 
-__host__ __device__ constexpr int aggp_row_group(int W) { return W <= 2 ? 4 : (W <= 4 ? 2 : 1); } // rows produced together
-__host__ __device__ constexpr int aggp_rows_per_thread(int W) {
-    return AGGP_THREAD_WORDS / W / aggp_row_group(W) > 0 ? AGGP_THREAD_WORDS / W / aggp_row_group(W) * aggp_row_group(W) : aggp_row_group(W);
-}
+// rows per thread and tile: 8 for records of <= 2 words (tile = 4096 rows = 64 KB), fewer for wider records
+__host__ __device__ constexpr int aggp_rows_per_thread(int W) { return W <= 2 ? 8 : (W <= 4 ? 4 : (W <= 8 ? 2 : 1)); }
 
 __device__ __forceinline__ uint32_t aggp_bucket(const AggDev& a, const PartPlan& pl, const HKey& key) {
     return (uint32_t)((hkey_hash(a, key) & a.mask) >> pl.bucket_shift);
 }
 
-// ---- histogram --------------------------------------------------------------------------------------------------
-constexpr int AGGP_HIST_ROWS = 8; // key loads in flight per thread
-__global__ void __launch_bounds__(AGGP_BLOCK, 1) k_aggp_hist(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, const __grid_constant__ PartPlan pl,
-                                                              int64_t row_base, int64_t n, uint32_t* __restrict__ hist) {
-    extern __shared__ uint32_t s_h[];
-    const AggDev& a = *ad;
-    const int P = 1 << pl.bits;
-    for (int i = threadIdx.x; i < P; i += AGGP_BLOCK) s_h[i] = 0;
-    __syncthreads();
-    const int64_t tile = (int64_t)AGGP_BLOCK * AGGP_HIST_ROWS;
-    const int64_t ntiles = (n + tile - 1) / tile;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t r0 = t * tile + threadIdx.x;
-        HKey key[AGGP_HIST_ROWS];
+// lanes of the warp holding the same NBITS-bit value as the caller (among the lanes with valid set; an invalid lane gets
+// the mask of the invalid lanes).  One ballot per bit: MATCH.ANY walks the distinct values one after the other and takes
+// hundreds of cycles when nearly every lane holds a different value.
+template <int NBITS>
+__device__ __forceinline__ uint32_t warp_peers(uint32_t v, bool valid) {
+    uint32_t peers = __ballot_sync(SR_FULL_MASK, valid);
+    if (!valid) peers = ~peers;
 #pragma unroll
-        for (int k = 0; k < AGGP_HIST_ROWS; k++) {
-            const int64_t r = r0 + (int64_t)k * AGGP_BLOCK;
-            key[k].lo = key[k].hi = SR_AGG_EMPTY;
-            if (r < n) {
-                ChunkLoader ld{vt, row_base + r};
-                agg_pack_key(a, ld, key[k]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < AGGP_HIST_ROWS; k++) {
-            const int64_t r = r0 + (int64_t)k * AGGP_BLOCK;
-            // rows whose packed key equals the empty marker live in the table's special slot: the scatter pass applies
-            // them directly, they are not staged
-            if (r < n && !hkey_is_empty(a, key[k])) atomicAdd(&s_h[aggp_bucket(a, pl, key[k])], 1u);
-        }
+    for (int b = 0; b < NBITS; b++) {
+        const uint32_t sgn = 0u - ((v >> b) & 1u);
+        const uint32_t m = __ballot_sync(SR_FULL_MASK, sgn != 0u);
+        peers &= ~(m ^ sgn);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < P; i += AGGP_BLOCK) {
-        const uint32_t c = s_h[i];
-        if (c) atomicAdd(&hist[i], c);
-    }
+    return peers;
 }
 
-// ---- bucket bases, cursors, tile list of the second level (one CTA) -------------------------------------------------
-__global__ void __launch_bounds__(1024) k_aggp_prepare(const uint32_t* __restrict__ hist, int bits, int bits2, int tile_rows, uint64_t* __restrict__ base,
-                                                        unsigned long long* __restrict__ cursor, unsigned long long* __restrict__ cursor1,
-                                                        uint32_t* __restrict__ tile_start) {
-    __shared__ uint32_t s_scan[1024 / 32 + 1];
-    __shared__ uint64_t s_running;
-    const int P = 1 << bits;
-    if (threadIdx.x == 0) s_running = 0;
-    __syncthreads();
-    for (int b0 = 0; b0 < P; b0 += 1024) {
-        const int i = b0 + threadIdx.x;
-        const uint32_t v = i < P ? hist[i] : 0;
-        uint32_t tot;
-        const uint32_t ex = block_excl_scan<1024>(v, s_scan, &tot);
-        const uint64_t run = s_running;
-        if (i < P) {
-            base[i] = run + ex;
-            cursor[i] = run + ex;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) s_running = run + tot;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) base[P] = s_running;
-    if (bits2 == 0) return;
-    __syncthreads(); // base[] written by this block is visible to it after the barrier
-    const int F1 = 1 << (bits - bits2);
-    if (threadIdx.x == 0) s_running = 0;
-    __syncthreads();
-    for (int b0 = 0; b0 < F1; b0 += 1024) { // F1 <= 1024: one iteration
-        const int i = b0 + threadIdx.x;
-        uint32_t tiles = 0;
-        if (i < F1) {
-            const uint64_t lo = base[(size_t)i << bits2], hi = base[(size_t)(i + 1) << bits2];
-            cursor1[i] = lo;
-            tiles = (uint32_t)((hi - lo + (uint64_t)tile_rows - 1) / (uint64_t)tile_rows);
-        }
-        uint32_t tot;
-        const uint32_t ex = block_excl_scan<1024>(tiles, s_scan, &tot);
-        const uint64_t run = s_running;
-        if (i < F1) tile_start[i] = (uint32_t)run + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) s_running = run + tot;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) tile_start[F1] = (uint32_t)s_running;
+// rank of the calling lane among the rows of its warp that went to the same bucket so far (warp-private counters, no
+// atomics): every lane passes its bucket `l` < 2^NBITS (ignored when !valid); returns the rank for valid lanes.  All 32
+// lanes must call.
+template <int NBITS>
+__device__ __forceinline__ uint32_t aggp_warp_rank(uint16_t* wh, uint32_t l, bool valid) {
+    const uint32_t peers = warp_peers<NBITS>(l, valid);
+    uint32_t prev = 0;
+    if (valid) prev = wh[l];
+    __syncwarp();
+    if (valid && (peers & lanemask_lt()) == 0) wh[l] = (uint16_t)(prev + __popc(peers));
+    __syncwarp();
+    return prev + __popc(peers & lanemask_lt());
 }
 
 // ---- scatter ----------------------------------------------------------------------------------------------------
 struct ScatterArgs {
-    int64_t row_base, n;                 // FROM_CHUNK: rows [row_base, row_base + n) of the bound chunk
-    const unsigned long long* src;       // !FROM_CHUNK: records sorted by first-level bucket
-    const uint64_t* base;                // bucket bases (2^bits + 1)
-    const uint32_t* tile_start;          // !FROM_CHUNK: first tile of every first-level bucket (+ total)
-    unsigned long long* cursor;          // write cursors of the destination buckets
-    unsigned long long* dst;             // destination records
+    int64_t row_base, n;                 // from a chunk: rows [row_base, row_base + n) of the bound chunk
+    const unsigned long long* src;       // from records: the first level's regions
+    const uint32_t* src_count;           //   records in every first-level region (may exceed cap1: capped)
+    const uint32_t* tile_start;          //   first tile of every first-level bucket (+ total)
+    uint32_t* cursor;                    // records reserved so far per destination bucket
+    unsigned long long* dst;             // destination regions (bucket b at b * dst_cap records)
+    unsigned long long dst_cap;
+    unsigned long long* ovf;             // overflow list (records) + its counter
+    unsigned long long* ovf_count;
+    unsigned long long ovf_cap;
     int32_t fan_bits;                    // log2 of this level's fan-out
     int32_t local_shift;                 // local bucket = (bucket >> local_shift) & (fan - 1)
 };
 
-template <int W>
-__device__ __forceinline__ void aggp_make_record(const AggDev& a, const PartPlan& pl, const VTab& vt, int64_t row, unsigned long long (&rec)[W], HKey& key) {
-    ChunkLoader ld{vt, row};
+// general plans: build the record of `row` straight into shared memory (one out-of-line copy of the key packing and of the
+// expression interpreter for all record widths); returns the row's bucket, or 0xFFFFFFFF when the packed key equals the
+// table's empty marker -- such rows live in the special slot and are applied here, exactly once, never staged
+__device__ __noinline__ uint32_t aggp_stage_row(const AggDev* ad, const PartPlan* plp, const VTab* vtp, int64_t row, unsigned long long* dst) {
+    const AggDev& a = *ad;
+    const PartPlan& pl = *plp;
+    ChunkLoader ld{*vtp, row};
+    HKey key;
     agg_pack_key(a, ld, key);
+    if (hkey_is_empty(a, key)) {
+        AccPtrs gp;
+        acc_ptrs_global(a, gp);
+        agg_apply_row<false>(a, gp, (long long)a.cap, ld);
+        return 0xFFFFFFFFu;
+    }
     unsigned long long nm = 0;
-#pragma unroll
-    for (int w = 0; w < W; w++) {
+#pragma unroll 1
+    for (int w = 0; w < pl.words; w++) {
         const int kind = pl.word_kind[w];
         if (kind == WK_KEY_LO) {
-            rec[w] = key.lo;
+            dst[w] = key.lo;
         } else if (kind == WK_KEY_HI) {
-            rec[w] = key.hi;
+            dst[w] = key.hi;
         } else if (kind == WK_NULLS) {
-            rec[w] = nm; // the null word is the last one: every function has been evaluated
+            dst[w] = nm; // the null word is the last one: every function has been evaluated
         } else {
             const int f = pl.word_fn[w];
             int64_t bits;
             const bool nul = eval_expr(a.fns[f].input, ld, bits);
-            rec[w] = nul ? 0ull : (unsigned long long)bits;
+            dst[w] = nul ? 0ull : (unsigned long long)bits;
             nm |= (nul ? 1ull : 0ull) << f;
         }
     }
-}
-
-template <int W>
-__device__ __forceinline__ void aggp_make_record_simple(const PartPlan& pl, const VTab& vt, int64_t row, unsigned long long (&rec)[W], HKey& key) {
-    ChunkLoader ld{vt, row};
-#pragma unroll
-    for (int w = 0; w < W; w++) {
-        int64_t bits;
-        ld.load(pl.word_vid[w], bits);
-        rec[w] = (unsigned long long)bits;
-    }
-    rec[0] &= pl.simple_key_mask;
-    key.lo = rec[0];
-    key.hi = 0;
+    return aggp_bucket(a, pl, key);
 }
 
 template <int W>
@@ -216,144 +163,246 @@ __device__ __forceinline__ void aggp_store_record(unsigned long long* p, const u
 
 template <int W>
 constexpr size_t aggp_scatter_smem() {
-    return (size_t)AGGP_BLOCK * aggp_rows_per_thread(W) * (W * 8 + 6) + (size_t)AGGP_MAX_FAN * 20;
+    // records + (perm, bucket) per position + warp counters / offsets + bucket start / run base
+    return (size_t)AGGP_BLOCK * aggp_rows_per_thread(W) * (W * 8 + 4) + (size_t)AGGP_WARPS * AGGP_MAX_FAN * 2 + (size_t)(AGGP_MAX_FAN + 1) * 8 + 16;
 }
 
-// One tile = T consecutive rows (first level: of the input chunk; second level: of one first-level bucket).  The tile's
-// records go to shared memory in ROW order as they are produced (a few rows per thread at a time, so that their loads are
-// in flight together and nothing has to stay in registers across the barriers), the tile histogram is scanned, every
-// row claims a position inside its bucket's run, and the copy-out walks the tile in BUCKET order through the inverse
-// permutation: consecutive threads write consecutive records of a bucket's run.
 enum ScatterMode { SCATTER_RECORDS = 0, SCATTER_CHUNK = 1, SCATTER_CHUNK_SIMPLE = 2 };
+
+// One tile = T consecutive rows (first level: of the input chunk; second level: of one first-level region).  Warp w takes
+// rows [w * 32 R, (w + 1) * 32 R) of the tile, 32 consecutive rows per step: the record goes to shared memory in row
+// order, the row's rank inside (warp, bucket) comes from aggp_warp_rank.  After a barrier the (warp, bucket) counters are
+// scanned into tile positions and every non-empty bucket reserves its run in the destination region; a second pass over
+// the rows fills the inverse permutation; the copy-out walks the tile in bucket order: consecutive threads write
+// consecutive records of a run.
 template <int W, int MODE>
-__global__ void __launch_bounds__(AGGP_BLOCK, 2) k_aggp_scatter(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, const __grid_constant__ PartPlan pl,
+__global__ void __launch_bounds__(AGGP_BLOCK, 4) k_aggp_scatter(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, const __grid_constant__ PartPlan pl,
                                                                  const __grid_constant__ ScatterArgs sa) {
     constexpr int R = aggp_rows_per_thread(W);
-    constexpr int G = aggp_row_group(W);
     constexpr int T = AGGP_BLOCK * R;
+    constexpr int WR = 32 * R; // rows of one warp
     constexpr bool FROM_CHUNK = MODE != SCATTER_RECORDS;
-    static_assert(R % G == 0, "row groups");
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ uint32_t s_scan[AGGP_BLOCK / 32 + 1];
-    unsigned long long* s_rec = (unsigned long long*)s_raw;              // T records in row order
-    unsigned long long* s_gbase = s_rec + (size_t)T * W;                  // destination of the bucket's run
-    uint32_t* s_hist = (uint32_t*)(s_gbase + AGGP_MAX_FAN);               // records of the tile per bucket
-    uint32_t* s_start = s_hist + AGGP_MAX_FAN;                            // first sorted position of the bucket
-    uint32_t* s_cur = s_start + AGGP_MAX_FAN;                             // next free sorted position of the bucket
-    uint16_t* s_lb = (uint16_t*)(s_cur + AGGP_MAX_FAN);                   // row -> bucket (0xFFFF: no record)
-    uint16_t* s_perm = s_lb + T;                                          // sorted position -> row of the tile
-    uint16_t* s_bkt = s_perm + T;                                         // sorted position -> bucket
+    unsigned long long* s_rec = (unsigned long long*)s_raw;                  // T records in row order
+    uint32_t* s_start = (uint32_t*)(s_rec + (size_t)T * W);                   // first tile position of the bucket (+ total)
+    uint32_t* s_gbase = s_start + AGGP_MAX_FAN + 1;                           // first record of the bucket's reserved run
+    uint16_t* s_wh = (uint16_t*)(s_gbase + AGGP_MAX_FAN + 1);                 // [warp][bucket] rows so far, then the warp's offset inside the bucket
+    uint16_t* s_perm = s_wh + AGGP_WARPS * AGGP_MAX_FAN;                      // tile position -> row of the tile
+    uint16_t* s_bkt = s_perm + T;                                             // tile position -> bucket
     const AggDev& a = *ad;
     const int tid = threadIdx.x;
+    const int wid = tid >> 5, lane = tid & 31;
     const int F = 1 << sa.fan_bits;
     const uint32_t fmask = (uint32_t)F - 1;
-    const int per = (F + AGGP_BLOCK - 1) / AGGP_BLOCK;
+    uint16_t* const my_wh = s_wh + wid * F;
+    for (int i = tid; i < AGGP_WARPS * F; i += AGGP_BLOCK) s_wh[i] = 0;
     const int64_t ntiles = FROM_CHUNK ? (sa.n + T - 1) / T : (int64_t)sa.tile_start[1 << (pl.bits - pl.bits2)];
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int64_t row0;        // first row / record of the tile
         int tile_n;
-        uint32_t cbase = 0;  // cursor index of local bucket 0
+        uint32_t cbase = 0;  // destination bucket of local bucket 0
         if (FROM_CHUNK) {
             row0 = tile * T;
             tile_n = (int)(sa.n - row0 < T ? sa.n - row0 : T);
         } else {
-            // first-level bucket b1 owning this tile: last entry of tile_start <= tile
+            // first-level bucket owning this tile: last entry of tile_start <= tile
             const int F1 = 1 << (pl.bits - pl.bits2);
             int lo = 0, hi = F1;
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
                 if (__ldg(sa.tile_start + mid) <= (uint32_t)tile) lo = mid; else hi = mid;
             }
-            const uint64_t pb = sa.base[(size_t)lo << pl.bits2], pe = sa.base[(size_t)(lo + 1) << pl.bits2];
-            row0 = (int64_t)pb + (tile - (int64_t)__ldg(sa.tile_start + lo)) * T;
-            tile_n = (int)((int64_t)pe - row0 < T ? (int64_t)pe - row0 : T);
+            const unsigned long long cnt = min((unsigned long long)__ldg(sa.src_count + lo), pl.cap1);
+            const int64_t off = (tile - (int64_t)__ldg(sa.tile_start + lo)) * T;
+            row0 = (int64_t)((unsigned long long)lo * pl.cap1) + off;
+            tile_n = (int)((int64_t)cnt - off < T ? (int64_t)cnt - off : T);
             cbase = (uint32_t)lo << pl.bits2;
         }
-        for (int i = tid; i < F; i += AGGP_BLOCK) s_hist[i] = 0;
-        __syncthreads();
-#pragma unroll 1
-        for (int k0 = 0; k0 < R; k0 += G) {
-            unsigned long long rec[G][W];
-            HKey key[G];
+        __syncthreads(); // s_wh is clear (initial clear, or the copy-out phase of the previous tile); s_rec / s_perm are free
+        uint32_t lr[R];  // bucket << 16 | rank inside (warp, bucket); 0xFFFFFFFF: no record
+        // first the loads of all R rows (issued back to back: the compiler does not move the volatile streaming loads
+        // across the shared-memory stores of a fused loop, which left ONE load in flight per thread -- eight serial DRAM
+        // latencies per tile), then the staging + bucket of every row, then the warp-synchronous ranking
+        if (MODE == SCATTER_CHUNK) {
 #pragma unroll
-            for (int g = 0; g < G; g++) {
-                const int q = (k0 + g) * AGGP_BLOCK + tid;
+            for (int k = 0; k < R; k++) {
+                const int q = wid * WR + k * 32 + lane;
+                lr[k] = 0xFFFFFFFFu;
                 if (q < tile_n) {
-                    if (MODE == SCATTER_CHUNK_SIMPLE) {
-                        aggp_make_record_simple<W>(pl, vt, sa.row_base + row0 + q, rec[g], key[g]);
-                    } else if (MODE == SCATTER_CHUNK) {
-                        aggp_make_record<W>(a, pl, vt, sa.row_base + row0 + q, rec[g], key[g]);
-                    } else {
-                        aggp_load_record<W>(sa.src + (size_t)(row0 + q) * W, rec[g]);
-                        key[g].lo = rec[g][0];
-                        key[g].hi = a.wide ? rec[g][W > 1 ? 1 : 0] : 0ull;
-                    }
+                    const uint32_t bk = aggp_stage_row(ad, &pl, &vt, sa.row_base + row0 + q, s_rec + (size_t)q * W);
+                    if (bk != 0xFFFFFFFFu) lr[k] = (bk >> sa.local_shift) & fmask;
                 }
             }
+        } else {
+            constexpr int G = R < 4 ? R : 4; // rows whose loads are in flight together (registers: G * W words)
 #pragma unroll
-            for (int g = 0; g < G; g++) {
-                const int q = (k0 + g) * AGGP_BLOCK + tid;
-                if (q < tile_n) {
-                    uint32_t l = 0xFFFFu;
-                    if (FROM_CHUNK && hkey_is_empty(a, key[g])) { // the table's special slot: applied here, exactly once, never staged
-                        AccPtrs gp;
-                        acc_ptrs_global(a, gp);
-                        ChunkLoader ld{vt, sa.row_base + row0 + q};
-                        agg_apply_row<false>(a, gp, (long long)a.cap, ld);
-                    } else {
-                        aggp_store_record<W>(s_rec + (size_t)q * W, rec[g]);
-                        l = (aggp_bucket(a, pl, key[g]) >> sa.local_shift) & fmask;
-                        atomicAdd(&s_hist[l], 1u);
+            for (int k0 = 0; k0 < R; k0 += G) {
+                unsigned long long rec[G][W];
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const int q = wid * WR + (k0 + g) * 32 + lane;
+                    if (q < tile_n) {
+                        if (MODE == SCATTER_CHUNK_SIMPLE) {
+#pragma unroll
+                            for (int w = 0; w < W; w++) {
+                                if (pl.word_w8[w])
+                                    rec[g][w] = (unsigned long long)ldg_stream_s64((const int64_t*)pl.word_ptr[w] + sa.row_base + row0 + q);
+                                else
+                                    rec[g][w] = (unsigned long long)(int64_t)ldg_stream_s32((const int32_t*)pl.word_ptr[w] + sa.row_base + row0 + q);
+                            }
+                        } else {
+                            aggp_load_record<W>(sa.src + (size_t)(row0 + q) * W, rec[g]);
+                        }
                     }
-                    s_lb[q] = (uint16_t)l;
+                }
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const int k = k0 + g;
+                    const int q = wid * WR + k * 32 + lane;
+                    lr[k] = 0xFFFFFFFFu;
+                    if (q < tile_n) {
+                        HKey key;
+                        if (MODE == SCATTER_CHUNK_SIMPLE) rec[g][0] &= pl.simple_key_mask;
+                        key.lo = rec[g][0];
+                        key.hi = (MODE == SCATTER_RECORDS && a.wide) ? rec[g][W > 1 ? 1 : 0] : 0ull;
+                        if (MODE == SCATTER_CHUNK_SIMPLE && key.lo == SR_AGG_EMPTY) {
+                            (void)aggp_stage_row(ad, &pl, &vt, sa.row_base + row0 + q, s_rec + (size_t)q * W); // the special slot's row: applied, not staged
+                        } else {
+                            aggp_store_record<W>(s_rec + (size_t)q * W, rec[g]);
+                            lr[k] = (aggp_bucket(a, pl, key) >> sa.local_shift) & fmask;
+                        }
+                    }
                 }
             }
         }
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            const bool valid = lr[k] != 0xFFFFFFFFu;
+            const uint32_t rank = aggp_warp_rank<AGGP_MAX_FAN_BITS>(my_wh, lr[k], valid);
+            if (valid) lr[k] = lr[k] << 16 | rank;
+        }
         __syncthreads();
-        {   // exclusive scan of the tile histogram; reserve the destination runs
-            uint32_t local = 0;
-            for (int i = 0; i < per; i++) {
-                const int idx = tid * per + i;
-                if (idx < F) local += s_hist[idx];
+        {   // (warp, bucket) counters -> offsets; exclusive scan over the buckets; reserve the destination runs
+            constexpr int PER = (AGGP_MAX_FAN + AGGP_BLOCK - 1) / AGGP_BLOCK; // buckets per thread (consecutive)
+            uint32_t tot_l[PER];
+            uint32_t mine = 0;
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int l = tid * PER + i;
+                tot_l[i] = 0;
+                if (l < F) {
+#pragma unroll
+                    for (int w = 0; w < AGGP_WARPS; w++) {
+                        const uint32_t c = s_wh[w * F + l];
+                        s_wh[w * F + l] = (uint16_t)tot_l[i]; // count -> offset, in place
+                        tot_l[i] += c;
+                    }
+                }
+                mine += tot_l[i];
             }
             uint32_t tot;
-            uint32_t run = block_excl_scan<AGGP_BLOCK>(local, s_scan, &tot);
-            for (int i = 0; i < per; i++) {
-                const int idx = tid * per + i;
-                if (idx < F) {
-                    const uint32_t c = s_hist[idx];
-                    s_start[idx] = run;
-                    s_cur[idx] = run;
-                    run += c;
-                    if (c) s_gbase[idx] = atomicAdd(sa.cursor + cbase + idx, (unsigned long long)c);
+            uint32_t run = block_excl_scan<AGGP_BLOCK>(mine, s_scan, &tot);
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int l = tid * PER + i;
+                if (l < F) {
+                    s_start[l] = run;
+                    if (tot_l[i]) s_gbase[l] = atomicAdd(sa.cursor + cbase + l, tot_l[i]);
+                    run += tot_l[i];
                 }
             }
+            if (tid == 0) s_start[F] = tot;
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < R; k++) {
-            const int q = k * AGGP_BLOCK + tid;
-            if (q < tile_n) {
-                const uint32_t l = s_lb[q];
-                if (l != 0xFFFFu) {
-                    const uint32_t pos = atomicAdd(&s_cur[l], 1u);
-                    s_perm[pos] = (uint16_t)q;
-                    s_bkt[pos] = (uint16_t)l;
-                }
+            if (lr[k] != 0xFFFFFFFFu) {
+                const uint32_t l = lr[k] >> 16;
+                const uint32_t pos = s_start[l] + s_wh[wid * F + l] + (lr[k] & 0xFFFFu);
+                s_perm[pos] = (uint16_t)(wid * WR + k * 32 + lane);
+                s_bkt[pos] = (uint16_t)l;
             }
         }
         __syncthreads();
-        const int staged = (int)s_cur[F - 1]; // records of the tile (rows of the special slot dropped out)
+        for (int i = tid; i < AGGP_WARPS * F; i += AGGP_BLOCK) s_wh[i] = 0; // counters of the next tile
+        const int staged = (int)s_start[F]; // records of the tile (rows of the special slot dropped out)
         for (int pos = tid; pos < staged; pos += AGGP_BLOCK) {
             const uint32_t l = s_bkt[pos];
-            const unsigned long long d = s_gbase[l] + (unsigned long long)(pos - s_start[l]);
-            aggp_store_record<W>(sa.dst + d * W, s_rec + (size_t)s_perm[pos] * W);
+            const unsigned long long d = (unsigned long long)s_gbase[l] + (unsigned long long)(pos - s_start[l]);
+            const unsigned long long* src = s_rec + (size_t)s_perm[pos] * W;
+            if (d < sa.dst_cap) {
+                aggp_store_record<W>(sa.dst + ((unsigned long long)(cbase + l) * sa.dst_cap + d) * W, src);
+            } else { // the bucket's region is full (skewed input): the record goes to the overflow list
+                const unsigned long long o = atomicAdd(sa.ovf_count, 1ull);
+                if (o < sa.ovf_cap) aggp_store_record<W>(sa.ovf + o * W, src);
+            }
         }
-        __syncthreads();
     }
 }
 
-// ---- apply: shared-memory slices ------------------------------------------------------------------------------------
+// first tile of every first-level region for the second level (one CTA)
+__global__ void __launch_bounds__(1024) k_aggp_tiles(const uint32_t* __restrict__ count1, int f1, unsigned long long cap1, int tile_rows, uint32_t* __restrict__ tile_start) {
+    __shared__ uint32_t s_scan[1024 / 32 + 1];
+    const int i = threadIdx.x; // f1 <= 512
+    uint32_t tiles = 0;
+    if (i < f1) {
+        const unsigned long long c = min((unsigned long long)count1[i], cap1);
+        tiles = (uint32_t)((c + (unsigned long long)tile_rows - 1) / (unsigned long long)tile_rows);
+    }
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan<1024>(tiles, s_scan, &tot);
+    if (i < f1) tile_start[i] = ex;
+    if (i == 0) tile_start[f1] = tot;
+}
+
+// ---- apply ----------------------------------------------------------------------------------------------------------
+// bytes of table state one group slot owns (keys + COUNT(*) + every accumulator array)
+__host__ __device__ inline size_t agg_slot_bytes_of(const AggDev& h) {
+    size_t b = 8 * (h.wide ? 2 : 1) + 8;
+    for (int f = 0; f < h.num_fns; f++) {
+        if (h.fns[f].mode == M_COUNT_STAR) continue;
+        b += 8 + (h.fns[f].mode == M_SUM_I128 ? 8 : 0) + (h.fns[f].track_n ? 8 : 0);
+    }
+    return b;
+}
+
+// shared-memory image of a bucket's slices: [keys | cnt | per fn: acc0, acc1?, accn?], S slots each
+__device__ __forceinline__ void aggp_slice_ptrs(const AggDev& a, unsigned char* smem, int S, unsigned long long*& keys, AccPtrs& p) {
+    keys = (unsigned long long*)smem;
+    long long* q = (long long*)(keys + (size_t)S * (a.wide ? 2 : 1));
+    p.cnt = q;
+    q += S;
+    for (int f = 0; f < SR_MAX_AGG_FNS; f++) {
+        p.acc0[f] = p.acc1[f] = p.accn[f] = nullptr;
+        if (f < a.num_fns && a.fns[f].mode != M_COUNT_STAR) {
+            p.acc0[f] = q;
+            q += S;
+            if (a.fns[f].mode == M_SUM_I128) {
+                p.acc1[f] = q;
+                q += S;
+            }
+            if (a.fns[f].track_n) {
+                p.accn[f] = q;
+                q += S;
+            }
+        }
+    }
+}
+
+struct ApplyArgs {
+    const unsigned long long* rec;  // final regions (bucket b at b * cap2 records)
+    const uint32_t* count;          // records reserved per bucket (may exceed cap2: capped)
+    uint32_t num_buckets;
+    int32_t fresh; // the table holds no group yet: slices are initialised in shared memory instead of loaded
+    uint32_t* fail_list;            // buckets with a slice that filled up (their records are re-applied by k_aggp_apply_l2)
+    unsigned long long* fail_count;
+};
+
+struct ApplyFn {
+    int32_t mode, val_word, track_n, fn;
+};
+
 // multi-word add into shared memory through native 32-bit atomics: every carry out of a word is seen by exactly one
 // adder (atom returns the old value) and forwarded as a +1 to the next word.  Readers look at the words after a barrier.
 __device__ __forceinline__ void smem_add_i128(long long* lo, long long* hi, long long v) {
@@ -381,72 +430,50 @@ __device__ __forceinline__ void acc_apply_slice(int32_t mode, long long* a0, lon
         acc_apply_shared(mode, a0, a1, slot, bits);
 }
 
-// shared-memory image of one slice: [keys | cnt | per fn: acc0, acc1?, accn?], S slots each
-__device__ __forceinline__ void aggp_slice_ptrs(const AggDev& a, unsigned char* smem, int S, unsigned long long*& keys, AccPtrs& p) {
-    keys = (unsigned long long*)smem;
-    long long* q = (long long*)(keys + (size_t)S * (a.wide ? 2 : 1));
-    p.cnt = q;
-    q += S;
-    for (int f = 0; f < SR_MAX_AGG_FNS; f++) {
-        p.acc0[f] = p.acc1[f] = p.accn[f] = nullptr;
-        if (f < a.num_fns && a.fns[f].mode != M_COUNT_STAR) {
-            p.acc0[f] = q;
-            q += S;
-            if (a.fns[f].mode == M_SUM_I128) {
-                p.acc1[f] = q;
-                q += S;
-            }
-            if (a.fns[f].track_n) {
-                p.accn[f] = q;
-                q += S;
-            }
-        }
-    }
-}
-
-struct ApplyArgs {
-    const unsigned long long* rec;
-    const uint64_t* base;
-    uint32_t num_buckets;
-    int32_t fresh; // the table holds no group yet: slices are initialised in shared memory instead of loaded
-    uint32_t* fail_list;            // buckets whose slice overflowed (their records are re-applied by k_aggp_apply_l2)
-    unsigned long long* fail_count;
-};
-
-__global__ void __launch_bounds__(AGGP_BLOCK, 2) k_aggp_apply_smem(const AggDev* __restrict__ ad, const __grid_constant__ PartPlan pl, const __grid_constant__ ApplyArgs aa) {
+constexpr int AGGP_APPLY_BLOCK = 256;
+// One CTA per bucket (= pl.apply_slices probing slices): the slices' key / state arrays are loaded into shared memory (or
+// initialised there while the table is still empty), every thread takes records straight from the bucket's region: probe
+// (64-bit / 128-bit CAS claims an empty slot), then shared-memory atomics on the state words (64-bit adds as 32-bit adds
+// with carry); the slices are written back with coalesced stores.  48 KB of slices per CTA -> four CTAs per SM.
+__global__ void __launch_bounds__(AGGP_APPLY_BLOCK, 4) k_aggp_apply(const AggDev* __restrict__ ad, const __grid_constant__ PartPlan pl, const __grid_constant__ ApplyArgs aa) {
     extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ AccPtrs sp;
+    __shared__ ApplyFn s_fn[SR_MAX_AGG_FNS];
+    __shared__ int s_nfn;
+    __shared__ unsigned long long* s_keys_p;
     __shared__ int s_fail;
-    __shared__ uint32_t s_new[AGGP_BLOCK / 32];
+    __shared__ uint32_t s_new[AGGP_APPLY_BLOCK / 32];
     const AggDev& a = *ad;
-    const int S = 1 << a.slice_log2;
-    const uint32_t smask = (uint32_t)S - 1;
+    const int S = pl.apply_slices << AGGP_SLICE_LOG2;
     const int W = pl.words;
     const int tid = threadIdx.x;
-    // the per-function array pointers are indexed by a run-time function number: kept in shared memory (a local array
-    // would live in local memory)
-    __shared__ AccPtrs sp, gp;
-    __shared__ unsigned long long* s_keys_p;
+    const int kw = a.wide ? 2 : 1;
     if (tid == 0) {
         unsigned long long* kp;
         AccPtrs t;
         aggp_slice_ptrs(a, s_raw, S, kp, t);
         sp = t;
         s_keys_p = kp;
-        acc_ptrs_global(a, t);
-        gp = t;
+        int n = 0;
+        for (int f = 0; f < a.num_fns; f++)
+            if (a.fns[f].mode != M_COUNT_STAR) s_fn[n++] = ApplyFn{a.fns[f].mode, pl.val_word[f], a.fns[f].track_n, f};
+        s_nfn = n;
     }
     __syncthreads();
     unsigned long long* const s_keys = s_keys_p;
-    const bool fast2 = W == 2 && !a.wide; // (key, one value)
-    const int kw = a.wide ? 2 : 1;
+    const bool fast2 = W == 2 && !a.wide;
+    const bool sumcount = fast2 && s_nfn == 1 && s_fn[0].mode == M_SUM_I64 && !s_fn[0].track_n && pl.null_word < 0;
+    long long* const cnt_p = sp.cnt;
+    long long* const sum_p = s_nfn > 0 ? sp.acc0[s_fn[0].fn] : nullptr;
     for (uint32_t b = blockIdx.x; b < aa.num_buckets; b += gridDim.x) {
-        const int64_t r0 = (int64_t)aa.base[b], r1 = (int64_t)aa.base[b + 1];
-        if (r1 <= r0) continue;
-        const size_t g0 = (size_t)b << a.slice_log2; // first slot of the slice
+        const int64_t nrec = (int64_t)min((unsigned long long)aa.count[b], pl.cap2);
+        if (nrec <= 0) continue;
+        const unsigned long long* const brec = aa.rec + (unsigned long long)b * pl.cap2 * W;
+        const size_t g0 = (size_t)b * S;
         if (tid == 0) s_fail = 0;
         if (aa.fresh) {
-            for (int i = tid; i < S * kw; i += AGGP_BLOCK) s_keys[i] = SR_AGG_EMPTY;
-            for (int i = tid; i < S; i += AGGP_BLOCK) {
+            for (int i = tid; i < S * kw; i += AGGP_APPLY_BLOCK) s_keys[i] = SR_AGG_EMPTY;
+            for (int i = tid; i < S; i += AGGP_APPLY_BLOCK) {
                 sp.cnt[i] = 0;
                 for (int f = 0; f < a.num_fns; f++) {
                     if (sp.acc0[f]) sp.acc0[f][i] = acc_init_value(a.fns[f].mode);
@@ -455,24 +482,24 @@ __global__ void __launch_bounds__(AGGP_BLOCK, 2) k_aggp_apply_smem(const AggDev*
                 }
             }
         } else {
-            for (int i = tid; i < S * kw; i += AGGP_BLOCK) s_keys[i] = a.hkeys[g0 * kw + i];
-            for (int i = tid; i < S; i += AGGP_BLOCK) sp.cnt[i] = gp.cnt[g0 + i];
+            for (int i = tid; i < S * kw; i += AGGP_APPLY_BLOCK) s_keys[i] = a.hkeys[g0 * kw + i];
+            for (int i = tid; i < S; i += AGGP_APPLY_BLOCK) sp.cnt[i] = a.cnt_star[g0 + i];
             for (int f = 0; f < a.num_fns; f++) {
                 if (sp.acc0[f])
-                    for (int i = tid; i < S; i += AGGP_BLOCK) sp.acc0[f][i] = gp.acc0[f][g0 + i];
+                    for (int i = tid; i < S; i += AGGP_APPLY_BLOCK) sp.acc0[f][i] = a.fns[f].acc0[g0 + i];
                 if (sp.acc1[f])
-                    for (int i = tid; i < S; i += AGGP_BLOCK) sp.acc1[f][i] = gp.acc1[f][g0 + i];
+                    for (int i = tid; i < S; i += AGGP_APPLY_BLOCK) sp.acc1[f][i] = a.fns[f].acc1[g0 + i];
                 if (sp.accn[f])
-                    for (int i = tid; i < S; i += AGGP_BLOCK) sp.accn[f][i] = gp.accn[f][g0 + i];
+                    for (int i = tid; i < S; i += AGGP_APPLY_BLOCK) sp.accn[f][i] = a.fns[f].accn[g0 + i];
             }
         }
         __syncthreads();
         uint32_t my_new = 0;
-        for (int64_t q = r0 + tid; q < r1; q += AGGP_BLOCK) {
-            const unsigned long long* rp = aa.rec + (size_t)q * W;
+        for (int64_t q = tid; q < nrec; q += AGGP_APPLY_BLOCK) {
+            const unsigned long long* rp = brec + (size_t)q * W;
             HKey key;
             unsigned long long w1 = 0;
-            if (fast2) { // one 16-byte load
+            if (fast2) {
                 const ulonglong2 v = __ldg((const ulonglong2*)rp);
                 key.lo = v.x;
                 w1 = v.y;
@@ -481,24 +508,26 @@ __global__ void __launch_bounds__(AGGP_BLOCK, 2) k_aggp_apply_smem(const AggDev*
                 key.lo = __ldg(rp);
                 key.hi = a.wide ? __ldg(rp + 1) : 0ull;
             }
-            uint32_t s = (uint32_t)hkey_hash(a, key) & smask; // slice_log2 <= log2(cap): the low bits of the home slot
-            long long slot = -1;
-            for (int tries = 0; tries < S; tries++) {
+            const uint32_t home = (uint32_t)hkey_hash(a, key) & (uint32_t)(S - 1);
+            const uint32_t sbase = home & ~((1u << AGGP_SLICE_LOG2) - 1);
+            uint32_t s = home & ((1u << AGGP_SLICE_LOG2) - 1);
+            int slot = -1;
+            for (int tries = 0; tries < (1 << AGGP_SLICE_LOG2); tries++) {
                 if (!a.wide) {
-                    unsigned long long cur = *(volatile unsigned long long*)(s_keys + s);
+                    unsigned long long cur = *(volatile unsigned long long*)(s_keys + sbase + s);
                     if (cur == SR_AGG_EMPTY) {
-                        cur = atomicCAS(s_keys + s, SR_AGG_EMPTY, key.lo);
+                        cur = atomicCAS(s_keys + sbase + s, SR_AGG_EMPTY, key.lo);
                         if (cur == SR_AGG_EMPTY) {
                             my_new++;
                             cur = key.lo;
                         }
                     }
                     if (cur == key.lo) {
-                        slot = s;
+                        slot = (int)(sbase + s);
                         break;
                     }
                 } else {
-                    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(s_keys + 2 * s);
+                    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(s_keys + 2 * (sbase + s));
                     HKey cur;
                     asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(cur.lo), "=l"(cur.hi) : "r"(addr) : "memory");
                     if (cur.lo == SR_AGG_EMPTY && cur.hi == SR_AGG_EMPTY) {
@@ -517,48 +546,50 @@ __global__ void __launch_bounds__(AGGP_BLOCK, 2) k_aggp_apply_smem(const AggDev*
                         }
                     }
                     if (cur.lo == key.lo && cur.hi == key.hi) {
-                        slot = s;
+                        slot = (int)(sbase + s);
                         break;
                     }
                 }
-                s = (s + 1) & smask;
+                s = (s + 1) & ((1u << AGGP_SLICE_LOG2) - 1);
             }
             if (slot < 0) {
                 s_fail = 1;
                 continue;
             }
-            smem_add_u64(sp.cnt + slot, 1ull);
-            const unsigned long long nm = pl.null_word >= 0 ? __ldg(rp + pl.null_word) : 0ull;
+            smem_add_u64(cnt_p + slot, 1ull);
+            if (sumcount) {
+                smem_add_u64(sum_p + slot, w1);
+            } else {
+                const unsigned long long nm = pl.null_word >= 0 ? __ldg(rp + pl.null_word) : 0ull;
 #pragma unroll 1
-            for (int f = 0; f < a.num_fns; f++) {
-                const AggFnDev& fn = a.fns[f];
-                if (fn.mode == M_COUNT_STAR || ((nm >> f) & 1ull)) continue;
-                const long long bits = (long long)(fast2 ? w1 : __ldg(rp + pl.val_word[f]));
-                acc_apply_slice(fn.mode, sp.acc0[f], sp.acc1[f], slot, bits);
-                if (fn.track_n) smem_add_u64(sp.accn[f] + slot, 1ull);
+                for (int i = 0; i < s_nfn; i++) {
+                    const ApplyFn fn = s_fn[i];
+                    if ((nm >> fn.fn) & 1ull) continue;
+                    acc_apply_slice(fn.mode, sp.acc0[fn.fn], sp.acc1[fn.fn], slot, (long long)__ldg(rp + fn.val_word));
+                    if (fn.track_n) smem_add_u64(sp.accn[fn.fn] + slot, 1ull);
+                }
             }
         }
         __syncthreads();
         if (s_fail) {
-            // the slice cannot take every group of its bucket: leave the table untouched, hand the bucket back
             if (tid == 0) aa.fail_list[atomicAdd(aa.fail_count, 1ull)] = b;
         } else {
-            for (int i = tid; i < S * kw; i += AGGP_BLOCK) a.hkeys[g0 * kw + i] = s_keys[i];
-            for (int i = tid; i < S; i += AGGP_BLOCK) gp.cnt[g0 + i] = sp.cnt[i];
+            for (int i = tid; i < S * kw; i += AGGP_APPLY_BLOCK) a.hkeys[g0 * kw + i] = s_keys[i];
+            for (int i = tid; i < S; i += AGGP_APPLY_BLOCK) a.cnt_star[g0 + i] = sp.cnt[i];
             for (int f = 0; f < a.num_fns; f++) {
                 if (sp.acc0[f])
-                    for (int i = tid; i < S; i += AGGP_BLOCK) gp.acc0[f][g0 + i] = sp.acc0[f][i];
+                    for (int i = tid; i < S; i += AGGP_APPLY_BLOCK) a.fns[f].acc0[g0 + i] = sp.acc0[f][i];
                 if (sp.acc1[f])
-                    for (int i = tid; i < S; i += AGGP_BLOCK) gp.acc1[f][g0 + i] = sp.acc1[f][i];
+                    for (int i = tid; i < S; i += AGGP_APPLY_BLOCK) a.fns[f].acc1[g0 + i] = sp.acc1[f][i];
                 if (sp.accn[f])
-                    for (int i = tid; i < S; i += AGGP_BLOCK) gp.accn[f][g0 + i] = sp.accn[f][i];
+                    for (int i = tid; i < S; i += AGGP_APPLY_BLOCK) a.fns[f].accn[g0 + i] = sp.accn[f][i];
             }
             const uint32_t wn = warp_sum(my_new);
-            if (lane_id() == 0) s_new[tid >> 5] = wn;
+            if ((tid & 31) == 0) s_new[tid >> 5] = wn;
             __syncthreads();
             if (tid == 0) {
                 unsigned long long t = 0;
-                for (int w = 0; w < AGGP_BLOCK / 32; w++) t += s_new[w];
+                for (int w = 0; w < AGGP_APPLY_BLOCK / 32; w++) t += s_new[w];
                 if (t) atomicAdd(a.ngroups, t);
             }
         }
@@ -567,8 +598,8 @@ __global__ void __launch_bounds__(AGGP_BLOCK, 2) k_aggp_apply_smem(const AggDev*
 }
 
 // ---- apply: global atomics on an L2-prefetched table range ----------------------------------------------------------
-// records [r0, r1), or the records named by `list` (refused by the admission limit before a growth).  [s_lo, s_hi): the
-// slots the records map to, requested into L2 with full-line prefetches up front.
+// records [r0, r1) of `rec`, or the records named by `list` (refused by the admission limit before a growth).
+// [s_lo, s_hi): the slots the records map to, requested into L2 with full-line prefetches up front.
 __global__ void __launch_bounds__(AGG_BLOCK) k_aggp_apply_l2(const AggDev* __restrict__ ad, const __grid_constant__ PartPlan pl, const unsigned long long* __restrict__ rec,
                                                               int64_t r0, int64_t r1, const uint64_t* __restrict__ list, unsigned long long s_lo, unsigned long long s_hi,
                                                               uint64_t* __restrict__ fail_list, unsigned long long* __restrict__ fail_count) {
