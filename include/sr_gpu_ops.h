@@ -626,6 +626,24 @@ int32_t sr_abi_sizeof(int32_t which);
  * own (the ctypes tests, a JNI shim) read the device buffers handed back in sr_chunk_out. */
 int32_t sr_memcpy(sr_ctx* ctx, void* dst, const void* src, int64_t bytes, int32_t kind);
 
+/* ---------------------------------------------------------------------------------------
+ * plumbing for asynchronous adapters.  Operator::push_chunk must not block (be/src/exec/pipeline/operator.h:100-118: the
+ * driver polls need_input / has_output / pending_finish instead), so an adapter hands a batch of page-locked columns to
+ * the library, records an event behind the work it queued and re-uses the batch only once the event has completed.
+ *   sr_host_alloc / sr_host_free: page-locked, device-mapped host memory (what a cudaHostRegister-ed ColumnAllocator
+ *     pool would provide, be/src/common/memory/column_allocator.h:23-54); valid as SR_MEM_HOST_PINNED columns.
+ *   sr_event_*: a marker on the context's stream.  record: after everything queued so far; query: 1 = reached,
+ *     0 = still pending (never blocks), < 0 = sr_status; sync: block until reached.
+ * ------------------------------------------------------------------------------------- */
+int32_t sr_host_alloc(sr_ctx* ctx, int64_t bytes, void** ptr);
+int32_t sr_host_free(sr_ctx* ctx, void* ptr);
+typedef struct sr_event sr_event;
+sr_event* sr_event_create(sr_ctx* ctx);
+void sr_event_destroy(sr_event* ev);
+int32_t sr_event_record(sr_event* ev);
+int32_t sr_event_query(sr_event* ev);
+int32_t sr_event_sync(sr_event* ev);
+
 /* measurement aid: read-only 128-bit-load bandwidth kernel over `bytes` of device memory
  * (SURVEY.md section 8d "measure the achievable peak"); returns the xor checksum through
  * *checksum_host after syncing. */

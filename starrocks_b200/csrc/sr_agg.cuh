@@ -1014,6 +1014,39 @@ static int32_t agg_alloc_tables(sr_agg* a, srd::AggDev* h, uint64_t cap, DevBuf*
     } else {
         h->hkeys = nullptr;
     }
+    if (!hash) {
+        // dense tables: ONE slab holds every state array back to back (cnt | per fn: acc0, acc1?, accn?), so that the
+        // element-wise merge of the partial tables of several GPUs (sr_agg_dense_state + all-reduce) is one in-place
+        // collective over one contiguous range per (operator, element type) instead of a cat / copy per array
+        size_t words = 1;
+        for (int f = 0; f < h->num_fns; f++)
+            if (h->fns[f].mode != srd::M_COUNT_STAR) words += 1 + (h->fns[f].mode == srd::M_SUM_I128 ? 1 : 0) + (h->fns[f].track_n ? 1 : 0);
+        SR_TRY(cnt->reserve(ctx, sizeof(int64_t) * total * words));
+        SR_CUDA(ctx, cudaMemsetAsync(cnt->p, 0, sizeof(int64_t) * total * words, ctx->stream));
+        long long* q = cnt->as<long long>();
+        h->cnt_star = q;
+        q += total;
+        for (int f = 0; f < h->num_fns; f++) {
+            srd::AggFnDev& fn = h->fns[f];
+            fn.acc0 = fn.acc1 = fn.accn = nullptr;
+            if (fn.mode == srd::M_COUNT_STAR) continue;
+            fn.acc0 = q;
+            q += total;
+            if (srd::acc_init_value(fn.mode) != 0) {
+                srd::k_fill_i64<<<grid, 256, 0, ctx->stream>>>(fn.acc0, (int64_t)total, srd::acc_init_value(fn.mode));
+                SR_LAUNCH_CHECK(ctx);
+            }
+            if (fn.mode == srd::M_SUM_I128) {
+                fn.acc1 = q;
+                q += total;
+            }
+            if (fn.track_n) {
+                fn.accn = q;
+                q += total;
+            }
+        }
+        return SR_OK;
+    }
     SR_TRY(cnt->reserve(ctx, sizeof(int64_t) * total));
     SR_CUDA(ctx, cudaMemsetAsync(cnt->p, 0, sizeof(int64_t) * total, ctx->stream));
     h->cnt_star = cnt->as<long long>();
@@ -1257,7 +1290,7 @@ static int32_t agg_check_nullability(sr_agg* a, const VTab& vt) {
                 const uint64_t total = (!h.dense && h.num_keys > 0) ? h.cap + 1 : h.cap;
                 SR_TRY(a->accn[f].reserve(a->ctx, sizeof(int64_t) * total));
                 srd::k_copy_i64<<<std::min(grid_for((int64_t)total, 256), a->ctx->num_sms * 8), 256, 0, a->ctx->stream>>>(
-                        a->accn[f].as<long long>(), a->cnt_star.as<long long>(), (int64_t)total);
+                        a->accn[f].as<long long>(), a->host.cnt_star, (int64_t)total);
                 SR_LAUNCH_CHECK(a->ctx);
                 hf.accn = a->accn[f].as<long long>();
                 hf.track_n = 1;

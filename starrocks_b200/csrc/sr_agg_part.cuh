@@ -7,8 +7,8 @@
 // atomics/s whatever the table size).  Here the batch is first moved next to the table slices it updates:
 //
 //   k_aggp_scatter   packed RECORDS (key, evaluated function inputs, null mask; W 8-byte words) are partitioned by the
-//                    top bits of their home slot.  Inside a tile every warp ranks its rows with match.any + a warp-private
-//                    counter per bucket (no atomics), the counters are scanned, the tile is copied out bucket by bucket
+//                    top bits of their home slot.  Inside a tile every row takes its rank in its bucket with one shared-memory
+//                    atomic, the counters are scanned, the tile is copied out bucket by bucket
 //                    into the buckets' regions (ONE global atomicAdd per tile and non-empty bucket reserves the run).
 //                    Regions have a fixed capacity (mean + 6 sigma of a uniform hash); what does not fit goes to an
 //                    overflow list -- no histogram pass.  Fan-out <= 2^9 per level, two levels for up to 2^18 buckets.
@@ -22,7 +22,10 @@
 
 namespace srd {
 
-constexpr int AGGP_BLOCK = 256;          // scatter CTA: 8 warps, four CTAs per SM
+#ifndef SR_AGGP_BLOCK
+#define SR_AGGP_BLOCK 512
+#endif
+constexpr int AGGP_BLOCK = SR_AGGP_BLOCK; // scatter CTA: 16 warps (tile of 4096 two-word records), two CTAs per SM
 constexpr int AGGP_WARPS = AGGP_BLOCK / 32;
 constexpr int AGGP_MAX_FAN_BITS = 9;     // fan-out of one scatter level
 constexpr int AGGP_MAX_FAN = 1 << AGGP_MAX_FAN_BITS;
@@ -56,36 +59,6 @@ __host__ __device__ constexpr int aggp_rows_per_thread(int W) { return W <= 2 ? 
 
 __device__ __forceinline__ uint32_t aggp_bucket(const AggDev& a, const PartPlan& pl, const HKey& key) {
     return (uint32_t)((hkey_hash(a, key) & a.mask) >> pl.bucket_shift);
-}
-
-// lanes of the warp holding the same NBITS-bit value as the caller (among the lanes with valid set; an invalid lane gets
-// the mask of the invalid lanes).  One ballot per bit: MATCH.ANY walks the distinct values one after the other and takes
-// hundreds of cycles when nearly every lane holds a different value.
-template <int NBITS>
-__device__ __forceinline__ uint32_t warp_peers(uint32_t v, bool valid) {
-    uint32_t peers = __ballot_sync(SR_FULL_MASK, valid);
-    if (!valid) peers = ~peers;
-#pragma unroll
-    for (int b = 0; b < NBITS; b++) {
-        const uint32_t sgn = 0u - ((v >> b) & 1u);
-        const uint32_t m = __ballot_sync(SR_FULL_MASK, sgn != 0u);
-        peers &= ~(m ^ sgn);
-    }
-    return peers;
-}
-
-// rank of the calling lane among the rows of its warp that went to the same bucket so far (warp-private counters, no
-// atomics): every lane passes its bucket `l` < 2^NBITS (ignored when !valid); returns the rank for valid lanes.  All 32
-// lanes must call.
-template <int NBITS>
-__device__ __forceinline__ uint32_t aggp_warp_rank(uint16_t* wh, uint32_t l, bool valid) {
-    const uint32_t peers = warp_peers<NBITS>(l, valid);
-    uint32_t prev = 0;
-    if (valid) prev = wh[l];
-    __syncwarp();
-    if (valid && (peers & lanemask_lt()) == 0) wh[l] = (uint16_t)(prev + __popc(peers));
-    __syncwarp();
-    return prev + __popc(peers & lanemask_lt());
 }
 
 // ---- scatter ----------------------------------------------------------------------------------------------------
@@ -164,7 +137,7 @@ __device__ __forceinline__ void aggp_store_record(unsigned long long* p, const u
 template <int W>
 constexpr size_t aggp_scatter_smem() {
     // records + (perm, bucket) per position + warp counters / offsets + bucket start / run base
-    return (size_t)AGGP_BLOCK * aggp_rows_per_thread(W) * (W * 8 + 4) + (size_t)AGGP_WARPS * AGGP_MAX_FAN * 2 + (size_t)(AGGP_MAX_FAN + 1) * 8 + 16;
+    return (size_t)AGGP_BLOCK * aggp_rows_per_thread(W) * (W * 8 + 4) + (size_t)AGGP_MAX_FAN * 4 + (size_t)(AGGP_MAX_FAN + 1) * 8 + 16;
 }
 
 enum ScatterMode { SCATTER_RECORDS = 0, SCATTER_CHUNK = 1, SCATTER_CHUNK_SIMPLE = 2 };
@@ -176,7 +149,7 @@ enum ScatterMode { SCATTER_RECORDS = 0, SCATTER_CHUNK = 1, SCATTER_CHUNK_SIMPLE 
 // the rows fills the inverse permutation; the copy-out walks the tile in bucket order: consecutive threads write
 // consecutive records of a run.
 template <int W, int MODE>
-__global__ void __launch_bounds__(AGGP_BLOCK, 4) k_aggp_scatter(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, const __grid_constant__ PartPlan pl,
+__global__ void __launch_bounds__(AGGP_BLOCK, 1024 / AGGP_BLOCK) k_aggp_scatter(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, const __grid_constant__ PartPlan pl,
                                                                  const __grid_constant__ ScatterArgs sa) {
     constexpr int R = aggp_rows_per_thread(W);
     constexpr int T = AGGP_BLOCK * R;
@@ -187,16 +160,15 @@ __global__ void __launch_bounds__(AGGP_BLOCK, 4) k_aggp_scatter(const AggDev* __
     unsigned long long* s_rec = (unsigned long long*)s_raw;                  // T records in row order
     uint32_t* s_start = (uint32_t*)(s_rec + (size_t)T * W);                   // first tile position of the bucket (+ total)
     uint32_t* s_gbase = s_start + AGGP_MAX_FAN + 1;                           // first record of the bucket's reserved run
-    uint16_t* s_wh = (uint16_t*)(s_gbase + AGGP_MAX_FAN + 1);                 // [warp][bucket] rows so far, then the warp's offset inside the bucket
-    uint16_t* s_perm = s_wh + AGGP_WARPS * AGGP_MAX_FAN;                      // tile position -> row of the tile
+    uint32_t* s_hist = s_gbase + AGGP_MAX_FAN + 1;                            // rows of the tile per bucket
+    uint16_t* s_perm = (uint16_t*)(s_hist + AGGP_MAX_FAN);                    // tile position -> row of the tile
     uint16_t* s_bkt = s_perm + T;                                             // tile position -> bucket
     const AggDev& a = *ad;
     const int tid = threadIdx.x;
     const int wid = tid >> 5, lane = tid & 31;
     const int F = 1 << sa.fan_bits;
     const uint32_t fmask = (uint32_t)F - 1;
-    uint16_t* const my_wh = s_wh + wid * F;
-    for (int i = tid; i < AGGP_WARPS * F; i += AGGP_BLOCK) s_wh[i] = 0;
+    for (int i = tid; i < F; i += AGGP_BLOCK) s_hist[i] = 0;
     const int64_t ntiles = FROM_CHUNK ? (sa.n + T - 1) / T : (int64_t)sa.tile_start[1 << (pl.bits - pl.bits2)];
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int64_t row0;        // first row / record of the tile
@@ -219,7 +191,7 @@ __global__ void __launch_bounds__(AGGP_BLOCK, 4) k_aggp_scatter(const AggDev* __
             tile_n = (int)((int64_t)cnt - off < T ? (int64_t)cnt - off : T);
             cbase = (uint32_t)lo << pl.bits2;
         }
-        __syncthreads(); // s_wh is clear (initial clear, or the copy-out phase of the previous tile); s_rec / s_perm are free
+        __syncthreads(); // s_hist is clear (initial clear, or the scan of the previous tile); s_rec / s_perm are free
         uint32_t lr[R];  // bucket << 16 | rank inside (warp, bucket); 0xFFFFFFFF: no record
         // first the loads of all R rows (issued back to back: the compiler does not move the volatile streaming loads
         // across the shared-memory stores of a fused loop, which left ONE load in flight per thread -- eight serial DRAM
@@ -236,6 +208,7 @@ __global__ void __launch_bounds__(AGGP_BLOCK, 4) k_aggp_scatter(const AggDev* __
             }
         } else {
             constexpr int G = R < 4 ? R : 4; // rows whose loads are in flight together (registers: G * W words)
+            uint32_t special = 0;
 #pragma unroll
             for (int k0 = 0; k0 < R; k0 += G) {
                 unsigned long long rec[G][W];
@@ -267,7 +240,7 @@ __global__ void __launch_bounds__(AGGP_BLOCK, 4) k_aggp_scatter(const AggDev* __
                         key.lo = rec[g][0];
                         key.hi = (MODE == SCATTER_RECORDS && a.wide) ? rec[g][W > 1 ? 1 : 0] : 0ull;
                         if (MODE == SCATTER_CHUNK_SIMPLE && key.lo == SR_AGG_EMPTY) {
-                            (void)aggp_stage_row(ad, &pl, &vt, sa.row_base + row0 + q, s_rec + (size_t)q * W); // the special slot's row: applied, not staged
+                            special |= 1u << k; // the special slot's row: applied below (out of line), not staged
                         } else {
                             aggp_store_record<W>(s_rec + (size_t)q * W, rec[g]);
                             lr[k] = (aggp_bucket(a, pl, key) >> sa.local_shift) & fmask;
@@ -275,13 +248,20 @@ __global__ void __launch_bounds__(AGGP_BLOCK, 4) k_aggp_scatter(const AggDev* __
                     }
                 }
             }
+            if (MODE == SCATTER_CHUNK_SIMPLE && special) {
+#pragma unroll 1
+                for (int k = 0; k < R; k++)
+                    if ((special >> k) & 1u) {
+                        const int q = wid * WR + k * 32 + lane;
+                        (void)aggp_stage_row(ad, &pl, &vt, sa.row_base + row0 + q, s_rec + (size_t)q * W);
+                    }
+            }
         }
+        // rank inside (tile, bucket): one shared-memory atomic per row.  (Measured against a ballot-per-bit match with
+        // warp-private counters, which needs no atomic: 14.4 / 11.1 ms vs 13.3 / 8.7 ms per 1e9 rows for the two levels.)
 #pragma unroll
-        for (int k = 0; k < R; k++) {
-            const bool valid = lr[k] != 0xFFFFFFFFu;
-            const uint32_t rank = aggp_warp_rank<AGGP_MAX_FAN_BITS>(my_wh, lr[k], valid);
-            if (valid) lr[k] = lr[k] << 16 | rank;
-        }
+        for (int k = 0; k < R; k++)
+            if (lr[k] != 0xFFFFFFFFu) lr[k] = lr[k] << 16 | atomicAdd(&s_hist[lr[k]], 1u);
         __syncthreads();
         {   // (warp, bucket) counters -> offsets; exclusive scan over the buckets; reserve the destination runs
             constexpr int PER = (AGGP_MAX_FAN + AGGP_BLOCK - 1) / AGGP_BLOCK; // buckets per thread (consecutive)
@@ -292,12 +272,8 @@ __global__ void __launch_bounds__(AGGP_BLOCK, 4) k_aggp_scatter(const AggDev* __
                 const int l = tid * PER + i;
                 tot_l[i] = 0;
                 if (l < F) {
-#pragma unroll
-                    for (int w = 0; w < AGGP_WARPS; w++) {
-                        const uint32_t c = s_wh[w * F + l];
-                        s_wh[w * F + l] = (uint16_t)tot_l[i]; // count -> offset, in place
-                        tot_l[i] += c;
-                    }
+                    tot_l[i] = s_hist[l];
+                    s_hist[l] = 0; // the next tile's counter
                 }
                 mine += tot_l[i];
             }
@@ -319,13 +295,12 @@ __global__ void __launch_bounds__(AGGP_BLOCK, 4) k_aggp_scatter(const AggDev* __
         for (int k = 0; k < R; k++) {
             if (lr[k] != 0xFFFFFFFFu) {
                 const uint32_t l = lr[k] >> 16;
-                const uint32_t pos = s_start[l] + s_wh[wid * F + l] + (lr[k] & 0xFFFFu);
+                const uint32_t pos = s_start[l] + (lr[k] & 0xFFFFu);
                 s_perm[pos] = (uint16_t)(wid * WR + k * 32 + lane);
                 s_bkt[pos] = (uint16_t)l;
             }
         }
         __syncthreads();
-        for (int i = tid; i < AGGP_WARPS * F; i += AGGP_BLOCK) s_wh[i] = 0; // counters of the next tile
         const int staged = (int)s_start[F]; // records of the tile (rows of the special slot dropped out)
         for (int pos = tid; pos < staged; pos += AGGP_BLOCK) {
             const uint32_t l = s_bkt[pos];

@@ -166,6 +166,7 @@ static int32_t agg_push_partitioned(sr_agg* a, const VTab& vt, int64_t n, bool f
             pl.bucket_shift = log2cap - log2p;
         }
         pl.bits2 = pl.bits > srd::AGGP_MAX_FAN_BITS ? pl.bits / 2 : 0;
+        if (pl.bits2 && getenv("SR_AGG_BITS2")) pl.bits2 = std::min(std::max(atoi(getenv("SR_AGG_BITS2")), pl.bits - srd::AGGP_MAX_FAN_BITS), srd::AGGP_MAX_FAN_BITS); // tuning knob
         const int P = 1 << pl.bits;
         const int F1 = 1 << (pl.bits - pl.bits2);
         pl.cap2 = aggp_region_cap((double)m / P);

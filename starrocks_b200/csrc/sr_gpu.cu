@@ -259,6 +259,78 @@ void* sr_ctx_stream(sr_ctx* ctx) {
     SR_LOCK(ctx);                               \
     cudaSetDevice((ctx)->device)
 
+// ------------------------------------------------------------------ pinned host memory + events (asynchronous adapters)
+int32_t sr_host_alloc(sr_ctx* ctx, int64_t bytes, void** ptr) {
+    SR_BIND(ctx);
+    if (!ptr || bytes <= 0) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "sr_host_alloc(%lld)", (long long)bytes);
+    *ptr = nullptr;
+    const cudaError_t e = cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return sr_fail(ctx, SR_ERR_OUT_OF_MEMORY, "cudaHostAlloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+    }
+    return SR_OK;
+}
+
+int32_t sr_host_free(sr_ctx* ctx, void* ptr) {
+    SR_BIND(ctx);
+    if (ptr) SR_CUDA(ctx, cudaFreeHost(ptr));
+    return SR_OK;
+}
+
+struct sr_event {
+    sr_ctx* ctx = nullptr;
+    cudaEvent_t ev = nullptr;
+    bool recorded = false;
+};
+
+sr_event* sr_event_create(sr_ctx* ctx) {
+    if (!ctx) return nullptr;
+    SR_LOCK(ctx);
+    cudaSetDevice(ctx->device);
+    sr_event* e = new sr_event();
+    e->ctx = ctx;
+    if (cudaEventCreateWithFlags(&e->ev, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        sr_fail(ctx, SR_ERR_CUDA, "cudaEventCreate failed");
+        delete e;
+        return nullptr;
+    }
+    return e;
+}
+
+void sr_event_destroy(sr_event* e) {
+    if (!e) return;
+    SR_LOCK(e->ctx);
+    cudaSetDevice(e->ctx->device);
+    cudaEventDestroy(e->ev);
+    delete e;
+}
+
+int32_t sr_event_record(sr_event* e) {
+    if (!e) return SR_ERR_INVALID_ARGUMENT;
+    SR_BIND(e->ctx);
+    SR_CUDA(e->ctx, cudaEventRecord(e->ev, e->ctx->stream));
+    e->recorded = true;
+    return SR_OK;
+}
+
+// no lock: polled from the driver / poller thread while other threads are inside library calls (cudaEventQuery is thread-safe)
+int32_t sr_event_query(sr_event* e) {
+    if (!e) return SR_ERR_INVALID_ARGUMENT;
+    if (!e->recorded) return 1;
+    const cudaError_t r = cudaEventQuery(e->ev);
+    if (r == cudaSuccess) return 1;
+    if (r == cudaErrorNotReady) return 0;
+    return SR_ERR_CUDA;
+}
+
+int32_t sr_event_sync(sr_event* e) {
+    if (!e) return SR_ERR_INVALID_ARGUMENT;
+    if (!e->recorded) return SR_OK;
+    return cudaEventSynchronize(e->ev) == cudaSuccess ? SR_OK : SR_ERR_CUDA;
+}
+
 // ------------------------------------------------------------------ scan
 sr_scan* sr_scan_create(sr_ctx* ctx, const sr_scan_desc* desc) {
     if (!ctx || !desc) return nullptr;
@@ -712,8 +784,26 @@ static int32_t agg_reset_impl(sr_agg* a) {
         srd::k_fill_u64<<<grid, 256, 0, ctx->stream>>>(a->hkeys.as<unsigned long long>(), (int64_t)(total * (h.wide ? 2 : 1)), SR_AGG_EMPTY);
         SR_LAUNCH_CHECK(ctx);
     }
-    SR_CUDA(ctx, cudaMemsetAsync(a->cnt_star.p, 0, sizeof(int64_t) * total, ctx->stream));
     SR_CUDA(ctx, cudaMemsetAsync(a->counters.p, 0, 64, ctx->stream));
+    if (!hash) {
+        // dense tables live in one slab (agg_alloc_tables): when every array follows the previous one and starts from
+        // zero, the whole reset is ONE memset (the per-step reset of the fused fragment's 175-slot table was 4 launches)
+        long long* end = h.cnt_star + total;
+        bool one = true;
+        for (int f = 0; f < h.num_fns && one; f++) {
+            const srd::AggFnDev& fn = h.fns[f];
+            for (long long* p : {fn.acc0, fn.acc1, fn.accn}) {
+                if (!p) continue;
+                if (p != end || (p == fn.acc0 && srd::acc_init_value(fn.mode) != 0)) one = false;
+                end = p + total;
+            }
+        }
+        if (one) {
+            SR_CUDA(ctx, cudaMemsetAsync(h.cnt_star, 0, sizeof(int64_t) * (size_t)(end - h.cnt_star), ctx->stream));
+            return SR_OK;
+        }
+    }
+    SR_CUDA(ctx, cudaMemsetAsync(h.cnt_star, 0, sizeof(int64_t) * total, ctx->stream));
     for (int f = 0; f < h.num_fns; f++) {
         const srd::AggFnDev& fn = h.fns[f];
         if (fn.acc0) {
@@ -949,7 +1039,7 @@ int32_t sr_agg_merge(sr_agg* a, sr_agg* o) {
             const uint64_t total = hash ? a->host.cap + 1 : a->host.cap;
             SR_TRY(a->accn[f].reserve(ctx, sizeof(int64_t) * total));
             srd::k_copy_i64<<<std::min(grid_for((int64_t)total, 256), ctx->num_sms * 8), 256, 0, ctx->stream>>>(a->accn[f].as<long long>(),
-                                                                                                               a->cnt_star.as<long long>(), (int64_t)total);
+                                                                                                               a->host.cnt_star, (int64_t)total);
             SR_LAUNCH_CHECK(ctx);
             a->host.fns[f].accn = a->accn[f].as<long long>();
             a->host.fns[f].track_n = 1;

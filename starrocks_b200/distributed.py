@@ -110,25 +110,41 @@ def dense_state_views(arrays, device):
 def all_reduce_dense_state(arrays, device):
     """In-place merge of dense aggregate tables across ranks (all-reduce on the enumerable slot array).
     arrays: what sr_agg_dense_state returned on this rank -- [(device_ptr, count, elem_type, reduce)]; every rank
-    passes the same list shape.  Afterwards every rank's table holds the final states."""
-    views = [(t, getattr(dist.ReduceOp, _REDUCE_OPS[reduce])) for t, reduce in dense_state_views(arrays, device)]
-    # adjacent arrays with the same operator and dtype travel in one collective
-    k = 0
-    while k < len(views):
-        t, op = views[k]
-        group = [t]
-        while k + len(group) < len(views) and views[k + len(group)][1] == op and views[k + len(group)][0].dtype == t.dtype:
-            group.append(views[k + len(group)][0])
-        if len(group) == 1:
-            dist.all_reduce(t, op=op)
+    passes the same list shape.  Afterwards every rank's table holds the final states.
+    The library keeps the arrays of a dense table back to back in one slab, so neighbouring arrays with the same operator
+    and element type are ONE contiguous range: they travel in one in-place collective, no cat / copy around it (Q4.1:
+    COUNT(*) + two int64 sums = one all-reduce over 3 x 175 int64).  The ranks first agree on the list shape -- a mismatch
+    (a column that turned nullable on one rank only) would otherwise hang the collective: MIN / MAX all-reduces of the
+    list's description, once per distinct list."""
+    runs = []   # [ptr, count, elem_type, reduce]
+    for ptr, count, elem_type, reduce in arrays:
+        if runs and runs[-1][2] == elem_type and runs[-1][3] == reduce and runs[-1][0] + 8 * runs[-1][1] == ptr:
+            runs[-1][1] += count
         else:
-            flat = torch.cat(group)
-            dist.all_reduce(flat, op=op)
-            off = 0
-            for g in group:
-                g.copy_(flat[off:off + g.numel()])
-                off += g.numel()
-        k += len(group)
+            runs.append([ptr, count, elem_type, reduce])
+    key = tuple([len(runs)] + [x for r in runs for x in (r[1], r[2], r[3])])
+    if dist.get_world_size() > 1 and key not in _CHECKED_SHAPES:   # a property of the plan: checked the first time it is seen
+        shape = torch.tensor(key, dtype=torch.int64, device=device)
+        n = torch.tensor([len(key)], dtype=torch.int64, device=device)
+        nlo, nhi = n.clone(), n.clone()
+        dist.all_reduce(nlo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(nhi, op=dist.ReduceOp.MAX)
+        ok = int(nlo) == int(nhi)
+        if ok:
+            lo, hi = shape.clone(), shape.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            ok = torch.equal(lo, hi)
+        if not ok:
+            raise RuntimeError("all_reduce_dense_state: the ranks expose different state array lists (a column nullable on some ranks only?)")
+        _CHECKED_SHAPES.add(key)
+    for ptr, count, elem_type, reduce in runs:
+        typestr = "<f8" if elem_type == 8 else "<i8"
+        t = torch.as_tensor(_DevicePtr(ptr, count, typestr), device=device)
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, _REDUCE_OPS[reduce]))
+
+
+_CHECKED_SHAPES = set()
 
 
 def all_reduce_runtime_filter(directory, min_value, max_value, num_inserted, has_null):
@@ -162,19 +178,37 @@ def exchange_partitions(cols, channel_offsets):
     """HASH_PARTITIONED exchange.  cols: list of 1-D tensors already reordered so that the rows of channel c occupy
     [channel_offsets[c], channel_offsets[c+1]) (what sr_xchg_partition / the reference's counting sort produce);
     channel c is rank c.  Returns the list of received columns (rows from rank 0 first, then rank 1, ... -- each
-    sender's rows keep their order, like the reference's per-sender queues)."""
-    world = dist.get_world_size()
+    sender's rows keep their order, like the reference's per-sender queues).
+    One small all-to-all carries the per-channel row counts (the receive sizes must be known to the host: one sync, the
+    only one), then ALL columns travel in ONE grouped NCCL operation (ncclGroupStart .. ncclSend/ncclRecv per column and
+    peer .. ncclGroupEnd via batch_isend_irecv); a rank's own channel is a device-to-device copy."""
+    world, rank = dist.get_world_size(), dist.get_rank()
     if len(channel_offsets) != world + 1:
         raise ValueError("one channel per rank expected")
     dev = cols[0].device
-    send_counts = torch.tensor([int(channel_offsets[c + 1] - channel_offsets[c]) for c in range(world)], dtype=torch.int64, device=dev)
+    send_list = [int(channel_offsets[c + 1] - channel_offsets[c]) for c in range(world)]
+    send_counts = torch.tensor(send_list, dtype=torch.int64, device=dev)
     recv_counts = torch.empty_like(send_counts)
     dist.all_to_all_single(recv_counts, send_counts)
-    send_list = [int(x) for x in send_counts.tolist()]
     recv_list = [int(x) for x in recv_counts.tolist()]
-    out = []
-    for c in cols:
-        r = torch.empty(sum(recv_list), dtype=c.dtype, device=dev)
-        dist.all_to_all_single(r, c.contiguous(), output_split_sizes=recv_list, input_split_sizes=send_list)
-        out.append(r)
+    send_off = [int(x) for x in channel_offsets]
+    recv_off = [0]
+    for x in recv_list:
+        recv_off.append(recv_off[-1] + x)
+    out = [torch.empty(recv_off[-1], dtype=c.dtype, device=dev) for c in cols]
+    ops = []
+    for c, r in zip(cols, out):
+        c = c.contiguous()
+        for p in range(world):
+            if p == rank:
+                if send_list[p]:
+                    r[recv_off[p]:recv_off[p + 1]].copy_(c[send_off[p]:send_off[p + 1]])
+                continue
+            if send_list[p]:
+                ops.append(dist.P2POp(dist.isend, c[send_off[p]:send_off[p + 1]], p))
+            if recv_list[p]:
+                ops.append(dist.P2POp(dist.irecv, r[recv_off[p]:recv_off[p + 1]], p))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
     return out

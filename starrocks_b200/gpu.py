@@ -110,6 +110,13 @@ def lib():
         "sr_abi_sizeof": (i32, [i32]),
         "sr_bandwidth_probe": (i32, [vp, vp, i64, vp]),
         "sr_flush_l2": (i32, [vp]),
+        "sr_host_alloc": (i32, [vp, i64, vp]),
+        "sr_host_free": (i32, [vp, vp]),
+        "sr_event_create": (vp, [vp]),
+        "sr_event_destroy": (None, [vp]),
+        "sr_event_record": (i32, [vp]),
+        "sr_event_query": (i32, [vp]),
+        "sr_event_sync": (i32, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -133,6 +140,7 @@ EXPORTED_SYMBOLS = [
     "sr_join_build_runtime_filter", "sr_rf_create", "sr_rf_insert", "sr_rf_destroy", "sr_rf_get_info", "sr_rf_copy_directory",
     "sr_rf_merge_directory", "sr_rf_evaluate", "sr_scan_add_runtime_filter",
     "sr_xchg_destroy", "sr_xchg_partition", "sr_xchg_hash", "sr_gather", "sr_memcpy", "sr_abi_sizeof", "sr_bandwidth_probe", "sr_flush_l2",
+    "sr_host_alloc", "sr_host_free", "sr_event_create", "sr_event_destroy", "sr_event_record", "sr_event_query", "sr_event_sync",
 ]
 
 

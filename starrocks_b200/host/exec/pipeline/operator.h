@@ -9,7 +9,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdint>
+#include <map>
 #include <memory>
 #include <set>
 #include <string>
@@ -77,6 +79,80 @@ private:
     bool _cancelled = false;
 };
 
+// RuntimeProfile, the part the operators use (be/src/common/runtime_profile.h): named counters with a unit, created
+// once (add_counter) and bumped with COUNTER_UPDATE / SCOPED_TIMER.  Operator owns two of them, like the reference
+// (be/src/exec/pipeline/operator.h:296-335): _common_metrics (filled by the driver: rows pushed / pulled, operator
+// time) and _unique_metrics (the operator's own: BuildHashTableTime, SearchHashTableTime, AggComputeTime, ...).
+enum class TUnit { UNIT, TIME_NS, BYTES };
+class RuntimeProfile {
+public:
+    struct Counter {
+        TUnit unit;
+        std::atomic<int64_t> v{0};
+        void update(int64_t d) { v.fetch_add(d, std::memory_order_relaxed); }
+        void set(int64_t x) { v.store(x, std::memory_order_relaxed); }
+        int64_t value() const { return v.load(std::memory_order_relaxed); }
+    };
+    explicit RuntimeProfile(std::string name) : _name(std::move(name)) {}
+    Counter* add_counter(const std::string& name, TUnit unit) {
+        auto& c = _counters[name];
+        if (!c) {
+            c = std::make_unique<Counter>();
+            c->unit = unit;
+        }
+        return c.get();
+    }
+    Counter* get_counter(const std::string& name) const {
+        auto it = _counters.find(name);
+        return it == _counters.end() ? nullptr : it->second.get();
+    }
+    const std::string& name() const { return _name; }
+    std::string to_string() const {
+        std::string out = _name + ":";
+        for (auto& kv : _counters) {
+            const int64_t v = kv.second->value();
+            out += " " + kv.first + "=";
+            if (kv.second->unit == TUnit::TIME_NS)
+                out += std::to_string(v / 1000) + "us";
+            else
+                out += std::to_string(v);
+        }
+        return out;
+    }
+
+private:
+    std::string _name;
+    std::map<std::string, std::unique_ptr<Counter>> _counters;
+};
+#define ADD_COUNTER(profile, name, unit) (profile)->add_counter(name, unit)
+#define ADD_TIMER(profile, name) (profile)->add_counter(name, TUnit::TIME_NS)
+#define COUNTER_UPDATE(c, v) (c)->update(v)
+#define COUNTER_SET(c, v) (c)->set(v)
+class ScopedTimer {
+public:
+    explicit ScopedTimer(RuntimeProfile::Counter* c) : _c(c), _t0(std::chrono::steady_clock::now()) {}
+    ~ScopedTimer() { _c->update(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - _t0).count()); }
+
+private:
+    RuntimeProfile::Counter* _c;
+    std::chrono::steady_clock::time_point _t0;
+};
+#define SR_CONCAT_(a, b) a##b
+#define SR_CONCAT(a, b) SR_CONCAT_(a, b)
+#define SCOPED_TIMER(c) ScopedTimer SR_CONCAT(_scoped_timer_, __LINE__)(c)
+
+// MemTracker, the part an operator touches (be/src/runtime/mem_tracker.h: consume / release / consumption)
+class MemTracker {
+public:
+    void consume(int64_t b) { _bytes.fetch_add(b, std::memory_order_relaxed); }
+    void release(int64_t b) { _bytes.fetch_sub(b, std::memory_order_relaxed); }
+    void set(int64_t b) { _bytes.store(b, std::memory_order_relaxed); }
+    int64_t consumption() const { return _bytes.load(std::memory_order_relaxed); }
+
+private:
+    std::atomic<int64_t> _bytes{0};
+};
+
 namespace pipeline {
 
 class OperatorFactory;
@@ -86,10 +162,24 @@ public:
     Operator(OperatorFactory* factory, int32_t id, std::string name, int32_t plan_node_id, bool is_subordinate, int32_t driver_sequence)
             : _factory(factory), _id(id), _name(std::move(name)), _plan_node_id(plan_node_id), _driver_sequence(driver_sequence) {
         (void)is_subordinate;
+        const std::string label = _name + " (plan_node_id=" + std::to_string(_plan_node_id) + ")";
+        _runtime_profile = std::make_shared<RuntimeProfile>(label);
+        _common_metrics = std::make_shared<RuntimeProfile>("CommonMetrics");
+        _unique_metrics = std::make_shared<RuntimeProfile>("UniqueMetrics");
+        _mem_tracker = std::make_shared<MemTracker>();
+        _push_chunk_num_counter = ADD_COUNTER(_common_metrics.get(), "PushChunkNum", TUnit::UNIT);
+        _push_row_num_counter = ADD_COUNTER(_common_metrics.get(), "PushRowNum", TUnit::UNIT);
+        _pull_chunk_num_counter = ADD_COUNTER(_common_metrics.get(), "PullChunkNum", TUnit::UNIT);
+        _pull_row_num_counter = ADD_COUNTER(_common_metrics.get(), "PullRowNum", TUnit::UNIT);
+        _total_timer = ADD_TIMER(_common_metrics.get(), "OperatorTotalTime");
     }
     virtual ~Operator() = default;
 
     virtual Status prepare(RuntimeState* state) { return Status::OK(); }
+    // be/src/exec/pipeline/operator.h:60-66: per-driver state that must be created on the driver's own thread
+    virtual Status prepare_local_state(RuntimeState* state) { return Status::OK(); }
+    // be/src/exec/pipeline/operator.h:143: make the operator reusable (multi-cast / cache operators call it)
+    virtual Status reset_state(RuntimeState* state, const std::vector<ChunkPtr>& refill_chunks) { return Status::OK(); }
     virtual Status set_finishing(RuntimeState* state) { return Status::OK(); }
     virtual Status set_finished(RuntimeState* state) { return Status::OK(); }
     virtual Status set_cancelled(RuntimeState* state) { return Status::OK(); }
@@ -105,6 +195,20 @@ public:
 
     int32_t get_id() const { return _id; }
     int32_t get_plan_node_id() const { return _plan_node_id; }
+    RuntimeProfile* runtime_profile() { return _runtime_profile.get(); }
+    RuntimeProfile* common_metrics() { return _common_metrics.get(); }
+    RuntimeProfile* unique_metrics() { return _unique_metrics.get(); }
+    MemTracker* mem_tracker() const { return _mem_tracker.get(); }
+    // PipelineDriver is the one filling the common metrics (pipeline_driver.cpp:340-420)
+    void update_push_metrics(int64_t rows) {
+        COUNTER_UPDATE(_push_chunk_num_counter, 1);
+        COUNTER_UPDATE(_push_row_num_counter, rows);
+    }
+    void update_pull_metrics(int64_t rows) {
+        COUNTER_UPDATE(_pull_chunk_num_counter, 1);
+        COUNTER_UPDATE(_pull_row_num_counter, rows);
+    }
+    RuntimeProfile::Counter* total_timer() { return _total_timer; }
     std::string get_raw_name() const { return _name; }
     std::string get_name() const { return _name + "_" + std::to_string(_plan_node_id) + (is_finished() ? "(X)" : "(O)"); }
 
@@ -114,6 +218,9 @@ protected:
     const std::string _name;
     const int32_t _plan_node_id;
     const int32_t _driver_sequence;
+    std::shared_ptr<RuntimeProfile> _runtime_profile, _common_metrics, _unique_metrics;
+    std::shared_ptr<MemTracker> _mem_tracker;
+    RuntimeProfile::Counter *_push_chunk_num_counter, *_push_row_num_counter, *_pull_chunk_num_counter, *_pull_row_num_counter, *_total_timer;
 };
 using OperatorPtr = std::shared_ptr<Operator>;
 using Operators = std::vector<OperatorPtr>;
@@ -208,10 +315,11 @@ private:
 class PipelineDriver {
 public:
     explicit PipelineDriver(Operators ops) : _operators(std::move(ops)), _finishing_sent(_operators.size(), false) {}
-    enum State { READY, PRECONDITION_BLOCK, FINISH };
+    enum State { READY, PRECONDITION_BLOCK, PENDING_FINISH, FINISH };
 
     Status prepare(RuntimeState* state) {
         for (auto& op : _operators) RETURN_IF_ERROR(op->prepare(state));
+        for (auto& op : _operators) RETURN_IF_ERROR(op->prepare_local_state(state));
         return Status::OK();
     }
 
@@ -235,13 +343,21 @@ public:
                 auto& curr = _operators[i];
                 auto& next = _operators[i + 1];
                 if (curr->has_output() && next->need_input() && !next->is_finished()) {
-                    StatusOr<ChunkPtr> maybe = curr->pull_chunk(state);
+                    StatusOr<ChunkPtr> maybe = [&]() {
+                        SCOPED_TIMER(curr->total_timer());
+                        return curr->pull_chunk(state);
+                    }();
                     if (!maybe.ok() && !maybe.status().is_end_of_file()) return maybe.status();
                     if (maybe.ok() && maybe.value() != nullptr && maybe.value()->num_rows() > 0) {
                         if ((int)maybe.value()->num_rows() > state->chunk_size())
                             return Status::InternalError("Intermediate chunk size must not be greater than " + std::to_string(state->chunk_size()) +
                                                          ", actually " + std::to_string(maybe.value()->num_rows()) + " after " + curr->get_name());
-                        RETURN_IF_ERROR(next->push_chunk(state, maybe.value()));
+                        curr->update_pull_metrics((int64_t)maybe.value()->num_rows());
+                        next->update_push_metrics((int64_t)maybe.value()->num_rows());
+                        {
+                            SCOPED_TIMER(next->total_timer());
+                            RETURN_IF_ERROR(next->push_chunk(state, maybe.value()));
+                        }
                         _rows_moved += maybe.value()->num_rows();
                     }
                     progressed = true;
@@ -255,6 +371,9 @@ public:
             while (_first_unfinished + 1 < n && _operators[_first_unfinished]->is_finished() && _finishing_sent[_first_unfinished + 1])
                 _first_unfinished++;
             if (_operators.back()->is_finished()) {
+                // PENDING_FINISH (pipeline_driver.cpp:880-905): asynchronous work queued by an operator must drain first
+                for (auto& op : _operators)
+                    if (op->pending_finish()) return PENDING_FINISH;
                 for (auto& op : _operators) RETURN_IF_ERROR(op->set_finished(state));
                 return FINISH;
             }

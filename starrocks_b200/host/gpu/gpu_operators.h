@@ -22,6 +22,7 @@
 #include <deque>
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -102,6 +103,105 @@ private:
     size_t _rows = 0;
 };
 
+// The same accumulation into PAGE-LOCKED, device-mapped buffers of a fixed row capacity (sr_host_alloc: what a
+// cudaHostRegister-ed ColumnAllocator pool would be in the BE).  The library reads such a batch in place over PCIe
+// (SR_MEM_HOST_PINNED) or DMA-copies it without a staging bounce; the operator may refill it only after the event it
+// recorded behind the push has completed.  Non-nullable fixed-length columns (the fact tables of the hot path).
+class PinnedChunkBatch {
+public:
+    PinnedChunkBatch() = default;
+    PinnedChunkBatch(const PinnedChunkBatch&) = delete;
+    PinnedChunkBatch& operator=(const PinnedChunkBatch&) = delete;
+    ~PinnedChunkBatch() { release(); }
+    Status init(sr_ctx* ctx, const Chunk& schema, size_t capacity_rows) {
+        _ctx = ctx;
+        _cap = capacity_rows;
+        for (size_t i = 0; i < schema.num_columns(); i++) {
+            const Column& col = *schema.get_column_by_index(i);
+            if (col.is_nullable()) return Status::NotSupported("PinnedChunkBatch: nullable column (slot " + std::to_string(schema.slot_of_index(i)) + ")");
+            Col c{schema.slot_of_index(i), col.logical_type(), col.type_size(), nullptr};
+            void* p = nullptr;
+            RETURN_IF_SR_ERROR(ctx, sr_host_alloc(ctx, (int64_t)(capacity_rows * c.width), &p));
+            c.data = (uint8_t*)p;
+            _cols.push_back(c);
+        }
+        _event = sr_event_create(ctx);
+        return _event ? Status::OK() : sr_to_status(ctx, sr_last_error_code(ctx));
+    }
+    bool initialised() const { return _event != nullptr; }
+    void release() {
+        for (auto& c : _cols)
+            if (c.data) sr_host_free(_ctx, c.data);
+        _cols.clear();
+        if (_event) sr_event_destroy(_event);
+        _event = nullptr;
+    }
+    size_t rows() const { return _rows; }
+    size_t room() const { return _cap - _rows; }
+    size_t bytes() const {
+        size_t b = 0;
+        for (auto& c : _cols) b += _rows * c.width;
+        return b;
+    }
+    void append(const Chunk& c, size_t from = 0) { // rows [from, from + min(room, rest)) of the chunk
+        const size_t n = std::min(room(), c.num_rows() - from);
+        for (auto& dst : _cols) memcpy(dst.data + _rows * dst.width, c.get_column_by_slot_id(dst.slot)->raw_data() + from * dst.width, n * dst.width);
+        _rows += n;
+    }
+    sr_chunk_view view() {
+        _views.clear();
+        for (auto& c : _cols) _views.push_back(sr_col_view{c.data, nullptr, c.type, c.slot});
+        return sr_chunk_view{_views.data(), (int32_t)_views.size(), SR_MEM_HOST_PINNED, (int64_t)_rows};
+    }
+    // in flight: handed to the library, the event behind that work has not completed yet
+    Status mark_submitted() {
+        RETURN_IF_SR_ERROR(_ctx, sr_event_record(_event));
+        _in_flight = true;
+        return Status::OK();
+    }
+    bool busy() { // non-blocking
+        if (_in_flight && sr_event_query(_event) != 0) {
+            _in_flight = false;
+            _rows = 0;
+        }
+        return _in_flight;
+    }
+    void wait() {
+        if (_in_flight) sr_event_sync(_event);
+        _in_flight = false;
+        _rows = 0;
+    }
+
+private:
+    struct Col {
+        SlotId slot;
+        int32_t type;
+        size_t width;
+        uint8_t* data;
+    };
+    sr_ctx* _ctx = nullptr;
+    std::vector<Col> _cols;
+    std::vector<sr_col_view> _views;
+    sr_event* _event = nullptr;
+    size_t _cap = 0, _rows = 0;
+    bool _in_flight = false;
+};
+
+// counters every GPU operator keeps in its _unique_metrics, sampled from the context at the operator's life-cycle points
+struct GpuOpCounters {
+    RuntimeProfile::Counter* launches = nullptr;
+    RuntimeProfile::Counter* device_bytes = nullptr;
+    void init(RuntimeProfile* p) {
+        launches = ADD_COUNTER(p, "GpuKernelLaunches", TUnit::UNIT);
+        device_bytes = ADD_COUNTER(p, "GpuDeviceBytes", TUnit::BYTES);
+    }
+    void sample(sr_ctx* ctx, MemTracker* tracker) { // context-wide totals: the context is shared by the operators of a fragment
+        COUNTER_SET(launches, sr_ctx_kernel_launches(ctx));
+        COUNTER_SET(device_bytes, sr_ctx_device_bytes(ctx));
+        if (tracker) tracker->set(sr_ctx_device_bytes(ctx));
+    }
+};
+
 // device (or host) sr_chunk_out -> host Chunks of <= chunk_size rows appended to `queue`
 inline Status slice_out_to_chunks(sr_ctx* ctx, const sr_chunk_out& out, int chunk_size, std::deque<ChunkPtr>* queue) {
     const int64_t n = out.num_rows;
@@ -177,7 +277,13 @@ public:
     // operator owns predicate evaluation + Chunk::filter on the device.
     GpuScanOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, sr_ctx* ctx, const sr_scan_desc& desc,
                     std::vector<ChunkPtr> morsel)
-            : SourceOperator(f, id, "gpu_olap_scan", plan_node_id, false, seq), _ctx(ctx), _desc(desc), _morsel(std::move(morsel)) {}
+            : SourceOperator(f, id, "gpu_olap_scan", plan_node_id, false, seq), _ctx(ctx), _desc(desc), _morsel(std::move(morsel)) {
+        // the names of ScanOperator / OlapChunkSource's profile (olap_chunk_source.cpp:93-140)
+        _expr_filter_timer = ADD_TIMER(_unique_metrics.get(), "ExprFilterTime");
+        _rows_read_counter = ADD_COUNTER(_unique_metrics.get(), "RawRowsRead", TUnit::UNIT);
+        _rows_out_counter = ADD_COUNTER(_unique_metrics.get(), "RowsRead", TUnit::UNIT);
+        _gpu.init(_unique_metrics.get());
+    }
     ~GpuScanOperator() override {
         if (_scan) sr_scan_destroy(_scan);
     }
@@ -206,7 +312,13 @@ public:
             for (int k = 0; k < kGpuBatchChunks && _next < _morsel.size(); k++) _batch.append(*_morsel[_next++]);
             sr_chunk_view v = _batch.view();
             sr_chunk_out out;
-            RETURN_IF_SR_ERROR(_ctx, sr_scan_filter(_scan, &v, &out));
+            {
+                SCOPED_TIMER(_expr_filter_timer);
+                RETURN_IF_SR_ERROR(_ctx, sr_scan_filter(_scan, &v, &out));
+            }
+            COUNTER_UPDATE(_rows_read_counter, (int64_t)_batch.rows());
+            COUNTER_UPDATE(_rows_out_counter, out.num_rows);
+            _gpu.sample(_ctx, _mem_tracker.get());
             _rows_out += out.num_rows;
             RETURN_IF_ERROR(slice_out_to_chunks(_ctx, out, state->chunk_size(), &_out));
         }
@@ -235,6 +347,8 @@ private:
     std::vector<GpuRuntimeFilterProbeDesc> _rf_probes;
     bool _rf_attached = false;
     int64_t _rows_out = 0;
+    RuntimeProfile::Counter *_expr_filter_timer, *_rows_read_counter, *_rows_out_counter;
+    GpuOpCounters _gpu;
     std::vector<ChunkPtr> _morsel;
     size_t _next = 0;
     ChunkBatch _batch;
@@ -269,7 +383,15 @@ using GpuHashJoinerPtr = std::shared_ptr<GpuHashJoiner>;
 class GpuHashJoinBuildOperator final : public Operator {
 public:
     GpuHashJoinBuildOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, GpuHashJoinerPtr joiner)
-            : Operator(f, id, "gpu_hash_join_build", plan_node_id, false, seq), _joiner(std::move(joiner)) {}
+            : Operator(f, id, "gpu_hash_join_build", plan_node_id, false, seq), _joiner(std::move(joiner)) {
+        // HashJoiner's build metrics (be/src/exec/hash_joiner.h:161-188)
+        _copy_right_table_timer = ADD_TIMER(_unique_metrics.get(), "CopyRightTableChunkTime");
+        _build_ht_timer = ADD_TIMER(_unique_metrics.get(), "BuildHashTableTime");
+        _rf_build_timer = ADD_TIMER(_unique_metrics.get(), "RuntimeFilterBuildTime");
+        _build_rows_counter = ADD_COUNTER(_unique_metrics.get(), "HashTableBuildRows", TUnit::UNIT);
+        _rf_num_counter = ADD_COUNTER(_unique_metrics.get(), "RuntimeFilterNum", TUnit::UNIT);
+        _gpu.init(_unique_metrics.get());
+    }
     Status prepare(RuntimeState* state) override { return _joiner->prepare(); }
     // what HashJoinNode hands the build operator factory: the filters to build and the hub that carries them
     void set_runtime_filters(RuntimeFilterHub* hub, std::vector<GpuRuntimeFilterBuildDesc> descs) {
@@ -288,16 +410,24 @@ public:
     Status set_finishing(RuntimeState* state) override { // build_ht + enter_probe_phase (hash_join_build_operator.cpp:86-220)
         if (_finished) return Status::OK();
         RETURN_IF_ERROR(_flush());
-        RETURN_IF_SR_ERROR(_joiner->ctx(), sr_join_build_finish(_joiner->join()));
-        if (_hub) { // create_runtime_filters + set_collector (hash_join_build_operator.cpp:100-215): publish even when empty
+        {
+            SCOPED_TIMER(_build_ht_timer);
+            RETURN_IF_SR_ERROR(_joiner->ctx(), sr_join_build_finish(_joiner->join()));
+        }
+        sr_join_info info;
+        if (sr_join_get_info(_joiner->join(), &info) == SR_OK) COUNTER_SET(_build_rows_counter, info.build_rows);
+        if (_hub) {
+            SCOPED_TIMER(_rf_build_timer); // create_runtime_filters + set_collector (hash_join_build_operator.cpp:100-215): publish even when empty
             auto collector = std::make_shared<GpuRuntimeFilterCollector>();
             for (auto& d : _rf_descs) {
                 sr_rf* rf = sr_join_build_runtime_filter(_joiner->join(), d.key_index, d.with_bloom ? 1 : 0, d.insert_nulls ? 1 : 0);
                 if (!rf) return sr_to_status(_joiner->ctx(), sr_last_error_code(_joiner->ctx()));
                 collector->add(d.filter_id, rf);
+                COUNTER_UPDATE(_rf_num_counter, 1);
             }
             _hub->set_collector(_plan_node_id, collector);
         }
+        _gpu.sample(_joiner->ctx(), _mem_tracker.get());
         _finished = true;
         return Status::OK();
     }
@@ -306,6 +436,7 @@ private:
     Status _flush() {
         if (_batch.empty()) return Status::OK();
         sr_chunk_view v = _batch.view();
+        SCOPED_TIMER(_copy_right_table_timer);
         RETURN_IF_SR_ERROR(_joiner->ctx(), sr_join_append_build(_joiner->join(), &v));
         _batch.clear();
         return Status::OK();
@@ -313,6 +444,8 @@ private:
     GpuHashJoinerPtr _joiner;
     ChunkBatch _batch;
     bool _finished = false;
+    RuntimeProfile::Counter *_copy_right_table_timer, *_build_ht_timer, *_rf_build_timer, *_build_rows_counter, *_rf_num_counter;
+    GpuOpCounters _gpu;
     RuntimeFilterHub* _hub = nullptr;
     std::vector<GpuRuntimeFilterBuildDesc> _rf_descs;
 };
@@ -320,7 +453,13 @@ private:
 class GpuHashJoinProbeOperator final : public OperatorWithDependency {
 public:
     GpuHashJoinProbeOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, GpuHashJoinerPtr joiner)
-            : OperatorWithDependency(f, id, "gpu_hash_join_probe", plan_node_id, false, seq), _joiner(std::move(joiner)), _prober_id(seq) {}
+            : OperatorWithDependency(f, id, "gpu_hash_join_probe", plan_node_id, false, seq), _joiner(std::move(joiner)), _prober_id(seq) {
+        _search_ht_timer = ADD_TIMER(_unique_metrics.get(), "SearchHashTableTime"); // probe + both output gathers: one library call
+        _output_timer = ADD_TIMER(_unique_metrics.get(), "OutputChunkTime");        // D2H + slicing into <= chunk_size chunks
+        _probe_rows_counter = ADD_COUNTER(_unique_metrics.get(), "ProbeRows", TUnit::UNIT);
+        _output_rows_counter = ADD_COUNTER(_unique_metrics.get(), "OutputRows", TUnit::UNIT);
+        _gpu.init(_unique_metrics.get());
+    }
     Status prepare(RuntimeState* state) override { return _joiner->prepare(); }
     bool is_ready() const override { return _joiner->is_build_done(); } // hash_join_probe_operator.cpp:75-77
     bool has_output() const override { return !_out.empty(); }
@@ -347,12 +486,23 @@ private:
         if (_batch.empty()) return Status::OK();
         sr_chunk_view v = _batch.view();
         sr_chunk_out out;
-        RETURN_IF_SR_ERROR(_joiner->ctx(), sr_join_probe(_joiner->join(), _prober_id, &v, &out));
-        RETURN_IF_ERROR(slice_out_to_chunks(_joiner->ctx(), out, state->chunk_size(), &_out));
+        {
+            SCOPED_TIMER(_search_ht_timer);
+            RETURN_IF_SR_ERROR(_joiner->ctx(), sr_join_probe(_joiner->join(), _prober_id, &v, &out));
+        }
+        COUNTER_UPDATE(_probe_rows_counter, (int64_t)_batch.rows());
+        COUNTER_UPDATE(_output_rows_counter, out.num_rows);
+        {
+            SCOPED_TIMER(_output_timer);
+            RETURN_IF_ERROR(slice_out_to_chunks(_joiner->ctx(), out, state->chunk_size(), &_out));
+        }
+        _gpu.sample(_joiner->ctx(), _mem_tracker.get());
         _batch.clear();
         return Status::OK();
     }
     GpuHashJoinerPtr _joiner;
+    RuntimeProfile::Counter *_search_ht_timer, *_output_timer, *_probe_rows_counter, *_output_rows_counter;
+    GpuOpCounters _gpu;
     int32_t _prober_id;
     ChunkBatch _batch;
     std::deque<ChunkPtr> _out;
@@ -395,7 +545,11 @@ using GpuAggregatorPtr = std::shared_ptr<GpuAggregator>;
 class GpuAggregateBlockingSinkOperator final : public Operator {
 public:
     GpuAggregateBlockingSinkOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, GpuAggregatorPtr agg)
-            : Operator(f, id, "gpu_aggregate_blocking_sink", plan_node_id, false, seq), _aggregator(std::move(agg)) {}
+            : Operator(f, id, "gpu_aggregate_blocking_sink", plan_node_id, false, seq), _aggregator(std::move(agg)) {
+        _agg_compute_timer = ADD_TIMER(_unique_metrics.get(), "AggComputeTime"); // aggregator.h: AggComputeTime
+        _input_rows_counter = ADD_COUNTER(_unique_metrics.get(), "InputRowCount", TUnit::UNIT);
+        _gpu.init(_unique_metrics.get());
+    }
     Status prepare(RuntimeState* state) override { return _aggregator->prepare(); }
     bool has_output() const override { return false; }
     bool need_input() const override { return !_finished; }
@@ -419,13 +573,20 @@ private:
     Status _flush() {
         if (_batch.empty()) return Status::OK();
         sr_chunk_view v = _batch.view();
-        RETURN_IF_SR_ERROR(_aggregator->ctx(), sr_agg_push(_aggregator->agg(), &v));
+        {
+            SCOPED_TIMER(_agg_compute_timer);
+            RETURN_IF_SR_ERROR(_aggregator->ctx(), sr_agg_push(_aggregator->agg(), &v));
+        }
+        COUNTER_UPDATE(_input_rows_counter, (int64_t)_batch.rows());
+        _gpu.sample(_aggregator->ctx(), _mem_tracker.get());
         _batch.clear();
         return Status::OK();
     }
     GpuAggregatorPtr _aggregator;
     ChunkBatch _batch;
     bool _finished = false;
+    RuntimeProfile::Counter *_agg_compute_timer, *_input_rows_counter;
+    GpuOpCounters _gpu;
 };
 
 class GpuAggregateBlockingSourceOperator final : public SourceOperator {
@@ -641,7 +802,8 @@ public:
             if (!j->is_build_done()) return false;
         return true;
     }
-    Status prepare() { // needs the builds: called lazily from the first push
+    Status prepare() { // needs the builds: called lazily from the first push (of any of the sinks sharing the fragment)
+        std::lock_guard<std::mutex> lk(_mu);
         if (_frag) return Status::OK();
         for (size_t k = 0; k < _joiners.size(); k++) _desc.joins[k].join = _joiners[k]->join();
         _frag = sr_fragment_create(_ctx, &_desc);
@@ -652,6 +814,16 @@ public:
     sr_ctx* ctx() const { return _ctx; }
     sr_fragment* frag() const { return _frag; }
     GpuAggregatorPtr aggregator() const { return _aggregator; }
+    // the sinks of all pipeline drivers feed the one fragment; the aggregate is complete when the last of them finishes
+    // (the reference counts the sink operators of a shared Aggregator the same way, aggregator.h ref / unref)
+    void add_sink() { _open_sinks.fetch_add(1); }
+    Status sink_finished() {
+        if (_open_sinks.fetch_sub(1) != 1) return Status::OK();
+        RETURN_IF_ERROR(prepare());
+        RETURN_IF_SR_ERROR(_ctx, sr_agg_sink_finish(sr_fragment_agg(_frag)));
+        _aggregator->sink_complete();
+        return Status::OK();
+    }
 
 private:
     sr_ctx* _ctx;
@@ -659,47 +831,97 @@ private:
     std::vector<GpuHashJoinerPtr> _joiners;
     sr_fragment* _frag = nullptr;
     GpuAggregatorPtr _aggregator;
+    std::mutex _mu;
+    std::atomic<int> _open_sinks{0};
 };
 using GpuFragmentPtr = std::shared_ptr<GpuFragment>;
 
+// The fused sink.  push_chunk never waits for the GPU: chunks are copied into one of two page-locked batches (the copy a
+// ColumnAllocator-backed scan would not even need); a full batch is handed to sr_fragment_push, which only queues work
+// (the fragment kernels read the batch IN PLACE over PCIe), an event is recorded behind it and the operator switches to
+// the other batch.  need_input() turns false only while BOTH batches are in flight -- polled by the driver, no blocking
+// call (operator.h:100-118) -- and pending_finish() keeps the driver from finishing until the queued work has drained.
 class GpuFragmentSinkOperator final : public OperatorWithDependency {
 public:
     GpuFragmentSinkOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, GpuFragmentPtr frag, size_t batch_rows = 1 << 22)
-            : OperatorWithDependency(f, id, "gpu_fragment_sink", plan_node_id, false, seq), _frag(std::move(frag)), _batch_rows(batch_rows) {}
+            : OperatorWithDependency(f, id, "gpu_fragment_sink", plan_node_id, false, seq), _frag(std::move(frag)), _batch_rows(batch_rows) {
+        _append_timer = ADD_TIMER(_unique_metrics.get(), "AppendChunkTime");
+        _push_timer = ADD_TIMER(_unique_metrics.get(), "FragmentPushTime"); // host time of the (asynchronous) library call
+        _batches_counter = ADD_COUNTER(_unique_metrics.get(), "FragmentBatches", TUnit::UNIT);
+        _bytes_counter = ADD_COUNTER(_unique_metrics.get(), "PinnedBatchBytes", TUnit::BYTES);
+        _no_buffer_counter = ADD_COUNTER(_unique_metrics.get(), "NeedInputFalseBothBatchesInFlight", TUnit::UNIT);
+        _gpu.init(_unique_metrics.get());
+        _frag->add_sink();
+    }
     bool is_ready() const override { return _frag->builds_done(); }
     bool has_output() const override { return false; }
-    bool need_input() const override { return !_finished; }
+    bool need_input() const override {
+        if (_finished) return false;
+        auto* self = const_cast<GpuFragmentSinkOperator*>(this);
+        if (!_batch[_cur].initialised()) return true;
+        if (_batch[_cur].room() > 0 && !self->_batch[_cur].busy()) return true;
+        const bool ok = !self->_batch[_cur ^ 1].busy(); // the current batch is full: the other one must be free to switch
+        if (!ok) COUNTER_UPDATE(self->_no_buffer_counter, 1);
+        return ok;
+    }
     bool is_finished() const override { return _finished; }
+    bool pending_finish() const override {
+        auto* self = const_cast<GpuFragmentSinkOperator*>(this);
+        return _finished && (self->_batch[0].busy() || self->_batch[1].busy());
+    }
     StatusOr<ChunkPtr> pull_chunk(RuntimeState*) override { return Status::InternalError("pull_chunk on a sink"); }
     Status push_chunk(RuntimeState* state, const ChunkPtr& chunk) override {
-        _batch.append(*chunk);
-        if (_batch.rows() >= _batch_rows) RETURN_IF_ERROR(_flush());
+        if (!_batch[0].initialised()) {
+            RETURN_IF_ERROR(_frag->prepare());
+            for (auto& b : _batch) RETURN_IF_ERROR(b.init(_frag->ctx(), *chunk, _batch_rows));
+        }
+        size_t from = 0;
+        while (from < chunk->num_rows()) {
+            if (_batch[_cur].room() == 0) {
+                RETURN_IF_ERROR(_submit());
+                if (_batch[_cur].busy()) _batch[_cur].wait(); // cannot happen under the driver's need_input() protocol
+            }
+            const size_t before = _batch[_cur].rows();
+            {
+                SCOPED_TIMER(_append_timer);
+                _batch[_cur].append(*chunk, from);
+            }
+            from += _batch[_cur].rows() - before;
+        }
         return Status::OK();
     }
     Status set_finishing(RuntimeState* state) override {
         if (_finished) return Status::OK();
         RETURN_IF_ERROR(_frag->prepare());
-        RETURN_IF_ERROR(_flush());
-        RETURN_IF_SR_ERROR(_frag->ctx(), sr_agg_sink_finish(sr_fragment_agg(_frag->frag())));
-        _frag->aggregator()->sink_complete();
+        if (_batch[_cur].initialised() && _batch[_cur].rows() > 0) RETURN_IF_ERROR(_submit());
         _finished = true;
+        return _frag->sink_finished();
+    }
+    Status set_finished(RuntimeState* state) override { // every driver's sink has drained (pending_finish was false)
+        _gpu.sample(_frag->ctx(), _mem_tracker.get());
         return Status::OK();
     }
 
 private:
-    Status _flush() {
-        if (_batch.empty()) return Status::OK();
-        RETURN_IF_ERROR(_frag->prepare());
-        sr_chunk_view v = _batch.view();
-        RETURN_IF_SR_ERROR(_frag->ctx(), sr_fragment_push(_frag->frag(), &v));
-        RETURN_IF_SR_ERROR(_frag->ctx(), sr_ctx_sync(_frag->ctx())); // the host batch is reused
-        _batch.clear();
+    Status _submit() { // hand the current batch over, continue with the other one
+        sr_chunk_view v = _batch[_cur].view();
+        {
+            SCOPED_TIMER(_push_timer);
+            RETURN_IF_SR_ERROR(_frag->ctx(), sr_fragment_push(_frag->frag(), &v));
+        }
+        COUNTER_UPDATE(_batches_counter, 1);
+        COUNTER_UPDATE(_bytes_counter, (int64_t)_batch[_cur].bytes());
+        RETURN_IF_ERROR(_batch[_cur].mark_submitted());
+        _cur ^= 1;
         return Status::OK();
     }
     GpuFragmentPtr _frag;
     size_t _batch_rows;
-    ChunkBatch _batch;
+    PinnedChunkBatch _batch[2];
+    int _cur = 0;
     bool _finished = false;
+    RuntimeProfile::Counter *_append_timer, *_push_timer, *_batches_counter, *_bytes_counter, *_no_buffer_counter;
+    GpuOpCounters _gpu;
 };
 
 // ------------------------------------------------------------------------------------------------------------

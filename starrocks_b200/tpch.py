@@ -124,3 +124,107 @@ def q3_build_oracle(oracle, tables):
     j2.append_build(o_j)
     j2.build()
     return j2, [j1, o_f, o_j]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Shardable generator (SF300 on 8 GPUs: no rank ever holds a whole table).  Every column value is a pure function of the
+# row's logical index: counter-based hashing (splitmix64 of index and column id) instead of a sequential RNG, so that any
+# rank can produce any slice on its own device, the ranks need not agree on anything but (sf, world), and the host can
+# reproduce the same tables with numpy for the oracle check.  Same shapes / distributions as gen_tables above.
+# ---------------------------------------------------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+def _sm64_np(x):
+    """splitmix64 output function on uint64 numpy arrays (wrapping)"""
+    with np.errstate(over="ignore"):
+        z = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)).astype(np.uint64)
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)).astype(np.uint64)
+        return z ^ (z >> np.uint64(31))
+
+
+def _sm64_torch(x):
+    """the same on int64 torch tensors (two's complement wrapping; logical shifts emulated by masking)"""
+    z = x + (-7046029254386353131)
+    z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * (-4658895280553007687)
+    z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * (-7723592293110705685)
+    return z ^ ((z >> 31) & ((1 << 33) - 1))
+
+
+class HashGen:
+    """column values as functions of the row index.  xp = "np" (host, oracle check) or a torch device."""
+
+    def __init__(self, sf, device=None):
+        self.nc = max(3, int(150_000 * sf))
+        self.no = self.nc * 10
+        self.dev = device
+
+    def _h(self, col, idx):
+        """63-bit non-negative hash of (column id, index)"""
+        if self.dev is None:
+            return (_sm64_np(idx.astype(np.uint64) * np.uint64(16) + np.uint64(col)) >> np.uint64(1)).astype(np.int64)
+        return (_sm64_torch(idx * 16 + col) >> 1) & ((1 << 62) - 1 | (1 << 62))
+
+    def _arange(self, lo, hi):
+        if self.dev is None:
+            return np.arange(lo, hi, dtype=np.int64)
+        import torch
+        return torch.arange(lo, hi, dtype=torch.int64, device=self.dev)
+
+    def _i32(self, x):
+        return x.astype(np.int32) if self.dev is None else x.to(dtype=__import__("torch").int32)
+
+    def customer(self, lo=0, hi=None):
+        hi = self.nc if hi is None else hi
+        i = self._arange(lo, hi)
+        return {"c_custkey": self._i32(i + 1), "c_mktsegment": self._i32(self._h(1, i) % 5)}
+
+    def order_cols(self, i):
+        """columns of the orders with logical indexes `i` (int64 array / tensor)"""
+        okey = (i // 8) * 32 + (i % 8) + 1
+        ck = 1 + self._h(2, i) % self.nc
+        if self.dev is None:
+            ck = np.where(ck % 3 == 0, np.maximum(ck - 1, 1), ck)       # a third of the customers place no order
+        else:
+            import torch
+            ck = torch.where(ck % 3 == 0, torch.clamp(ck - 1, min=1), ck)
+        odate = JULIAN_1992_01_01 + self._h(3, i) % ORDERDATE_SPAN
+        return okey, ck, odate
+
+    def orders(self, idx):
+        okey, ck, odate = self.order_cols(idx)
+        zeros = np.zeros(len(idx), dtype=np.int32) if self.dev is None else __import__("torch").zeros(idx.numel(), dtype=__import__("torch").int32, device=self.dev)
+        return {"o_orderkey": self._i32(okey), "o_custkey": self._i32(ck), "o_orderdate": self._i32(odate), "o_shippriority": zeros}
+
+    def lineitem_of_orders(self, lo, hi):
+        """the line items of the orders with logical indexes [lo, hi): 1..7 per order"""
+        i = self._arange(lo, hi)
+        per = 1 + self._h(4, i) % 7
+        okey, _, odate = self.order_cols(i)
+        if self.dev is None:
+            rep = np.repeat(np.arange(hi - lo, dtype=np.int64), per)
+            first = np.cumsum(per) - per
+            line = np.arange(len(rep), dtype=np.int64) - first[rep]
+        else:
+            import torch
+            rep = torch.repeat_interleave(torch.arange(hi - lo, dtype=torch.int64, device=self.dev), per)
+            first = torch.cumsum(per, 0) - per
+            line = torch.arange(rep.numel(), dtype=torch.int64, device=self.dev) - first[rep]
+        key = (i[rep]) * 8 + line
+        price = 90_000 + self._h(5, key) % (10_494_951 - 90_000)
+        disc = self._h(6, key) % 11
+        ship = odate[rep] + 1 + self._h(7, key) % 121
+        return {"l_orderkey": self._i32(okey[rep]), "l_extendedprice": price, "l_discount": disc, "l_shipdate": self._i32(ship)}
+
+    def order_qualifies(self, i):
+        """Q3's build-side conditions for the orders with logical indexes i: o_orderdate < cutoff and the customer's segment"""
+        _, ck, odate = self.order_cols(i)
+        seg = self._h(1, ck - 1) % 5
+        return (odate < CUTOFF) & (seg == BUILDING)
+
+
+def gen_tables_hashed(sf):
+    """the whole tables on the host from HashGen (for the oracle check of the sharded runs)"""
+    g = HashGen(sf)
+    return {"customer": g.customer(), "orders": g.orders(np.arange(g.no, dtype=np.int64)), "lineitem": g.lineitem_of_orders(0, g.no)}
