@@ -582,13 +582,16 @@ int64_t sr_fragment_rows_passed(sr_fragment* frag);
  * 242-244).  The transport itself (NCCL all-to-all in place of brpc transmit_chunk) is
  * driven by the host with the per-channel counts this call produces.
  * ------------------------------------------------------------------------------------- */
-typedef enum sr_hash_fn { SR_HASH_FNV = 0, SR_HASH_CRC32 = 1 } sr_hash_fn;
+/* SR_HASH_XXH3: the exchange hash of exchange_hash_function_version = 1 (exchange_sink_operator.cpp:597-601): every
+ * partition column feeds XXH3_64bits_withSeed(value bytes, width, seed = the row's 32-bit hash so far) truncated to 32 bits,
+ * starting from HashUtil::XXH3_SEED_32 (ColumnHashVisitor<XXHash3>, column_hash.cpp:64-68). */
+typedef enum sr_hash_fn { SR_HASH_FNV = 0, SR_HASH_CRC32 = 1, SR_HASH_XXH3 = 2 } sr_hash_fn;
 typedef enum sr_reduce_op { SR_REDUCE_MULHI = 0 /* ReduceOp */, SR_REDUCE_MODULO = 1 /* ModuloOp */ } sr_reduce_op;
 
 #define SR_MAX_PART_KEYS 4
 
 typedef struct sr_part_desc {
-    int32_t hash_fn;   /* sr_hash_fn: FNV for HASH_PARTITIONED, CRC32 for BUCKET_SHUFFLE */
+    int32_t hash_fn;   /* sr_hash_fn: FNV (or XXH3, hash function version 1) for HASH_PARTITIONED, CRC32 for BUCKET_SHUFFLE */
     int32_t reduce_op; /* sr_reduce_op */
     int32_t num_channels;
     int32_t num_part_slots;

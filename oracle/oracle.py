@@ -43,8 +43,21 @@ DENSE_RANGE_DIRECT_MAPPING, LINEAR_CHAINED, LINEAR_CHAINED_SET = 5, 6, 7
 
 
 def build():
-    """compile oracle/libsr_oracle.so (g++, seconds)."""
+    """compile oracle/libsr_oracle.so (g++, seconds) and, where the reference tree is present, oracle/_ref (the pieces of the
+    path that compile from the reference's own sources: the vendored xxHash)."""
     subprocess.check_call(["make", "-C", _HERE, "-s"])
+    subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+
+
+def ref_xxh3():
+    """oracle/_ref/libxxh3_ref.so (HashUtil::xx_hash3_64 from the reference's own header), or None when it was never built"""
+    path = os.path.join(_HERE, "_ref", "libxxh3_ref.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.ref_xx_hash3_64.restype = C.c_uint64
+    L.ref_xx_hash3_64.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+    return L
 
 
 def lib():
@@ -65,6 +78,7 @@ def lib():
         "orc_crc_hash_32": (u32, [vp, i32, u32]),
         "orc_zlib_crc32": (u32, [vp, i32, u32]),
         "orc_fnv_hash": (u32, [vp, i32, u32]),
+        "orc_xxh3_64": (C.c_uint64, [vp, i32, C.c_uint64]),
         "orc_xorshift32": (u32, [u32]),
         "orc_reduce_op": (u32, [u32, u32]),
         "orc_filter_range": (i64, [vp, vp, i32, i64, i64]),

@@ -1710,13 +1710,72 @@ extern "C" int32_t orc_agg_merge(orc_agg* a, const orc_agg* o) {
 }
 
 // ---------------------------------------------------------------------------------------
+// XXH3 64-bit, short inputs (be/src/base/hash/xxhash.h: XXH3_len_1to3_64b, XXH3_len_4to8_64b, XXH3_len_9to16_64b,
+// XXH3_rrmxmx, XXH3_avalanche, XXH64_avalanche, kSecret)
+// ---------------------------------------------------------------------------------------
+static const uint8_t kXxh3Secret[64] = {0xb8, 0xfe, 0x6c, 0x39, 0x23, 0xa4, 0x4b, 0xbe, 0x7c, 0x01, 0x81, 0x2c, 0xf7, 0x21, 0xad, 0x1c,
+                                         0xde, 0xd4, 0x6d, 0xe9, 0x83, 0x90, 0x97, 0xdb, 0x72, 0x40, 0xa4, 0xa4, 0xb7, 0xb3, 0x67, 0x1f,
+                                         0xcb, 0x79, 0xe6, 0x4e, 0xcc, 0xc0, 0xe5, 0x78, 0x82, 0x5a, 0xd0, 0x7d, 0xcc, 0xff, 0x72, 0x21,
+                                         0xb8, 0x08, 0x46, 0x74, 0xf7, 0x43, 0x24, 0x8e, 0xe0, 0x35, 0x90, 0xe6, 0x81, 0x3a, 0x26, 0x4c};
+static inline uint64_t xxh_r64(const uint8_t* p) {
+    uint64_t v;
+    memcpy(&v, p, 8);
+    return v;
+}
+static inline uint32_t xxh_r32(const uint8_t* p) {
+    uint32_t v;
+    memcpy(&v, p, 4);
+    return v;
+}
+static inline uint64_t xxh_rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+extern "C" uint64_t orc_xxh3_64(const void* data, int32_t bytes, uint64_t seed) {
+    const uint8_t* in = (const uint8_t*)data;
+    const uint64_t len = (uint64_t)bytes;
+    if (bytes >= 1 && bytes <= 3) {
+        const uint32_t combined = ((uint32_t)in[0] << 16) | ((uint32_t)in[bytes >> 1] << 24) | (uint32_t)in[bytes - 1] | ((uint32_t)bytes << 8);
+        const uint64_t bitflip = (uint64_t)(xxh_r32(kXxh3Secret) ^ xxh_r32(kXxh3Secret + 4)) + seed;
+        uint64_t h = (uint64_t)combined ^ bitflip; // XXH64_avalanche
+        h ^= h >> 33;
+        h *= 0xC2B2AE3D27D4EB4FULL;
+        h ^= h >> 29;
+        h *= 0x165667B19E3779F9ULL;
+        h ^= h >> 32;
+        return h;
+    }
+    if (bytes >= 4 && bytes <= 8) {
+        seed ^= (uint64_t)__builtin_bswap32((uint32_t)seed) << 32;
+        const uint32_t in1 = xxh_r32(in), in2 = xxh_r32(in + bytes - 4);
+        const uint64_t bitflip = (xxh_r64(kXxh3Secret + 8) ^ xxh_r64(kXxh3Secret + 16)) - seed;
+        uint64_t h = ((uint64_t)in2 + ((uint64_t)in1 << 32)) ^ bitflip; // XXH3_rrmxmx
+        h ^= xxh_rotl64(h, 49) ^ xxh_rotl64(h, 24);
+        h *= 0x9FB21C651E98DF25ULL;
+        h ^= (h >> 35) + len;
+        h *= 0x9FB21C651E98DF25ULL;
+        return h ^ (h >> 28);
+    }
+    if (bytes >= 9 && bytes <= 16) {
+        const uint64_t bitflip1 = (xxh_r64(kXxh3Secret + 24) ^ xxh_r64(kXxh3Secret + 32)) + seed;
+        const uint64_t bitflip2 = (xxh_r64(kXxh3Secret + 40) ^ xxh_r64(kXxh3Secret + 48)) - seed;
+        const uint64_t lo = xxh_r64(in) ^ bitflip1, hi = xxh_r64(in + bytes - 8) ^ bitflip2;
+        const unsigned __int128 prod = (unsigned __int128)lo * hi;
+        uint64_t h = len + __builtin_bswap64(lo) + hi + ((uint64_t)prod ^ (uint64_t)(prod >> 64)); // XXH3_avalanche
+        h ^= h >> 37;
+        h *= 0x165667919E3779F9ULL;
+        h ^= h >> 32;
+        return h;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // exchange partitioning: exchange_sink_operator.cpp:586-637, shuffler.h:72-89,
 // column_hash.cpp:138-300 (per-type byte feeding, NULL mixing)
 // ---------------------------------------------------------------------------------------
 extern "C" int32_t orc_hash_partition(const sr_part_desc* d, const sr_chunk_view* in, uint32_t* hash_values,
                                       uint32_t* channel_ids, uint32_t* row_indexes, int64_t* channel_starts) {
     const int64_t n = in->num_rows;
-    const uint32_t seed = d->hash_fn == SR_HASH_FNV ? 0x811C9DC5u : 0u;
+    // seeds: HashUtil::FNV_SEED / XXH3_SEED_32 (exchange_sink_operator.cpp:597-606), 0 for the CRC32 bucket shuffle
+    const uint32_t seed = d->hash_fn == SR_HASH_FNV ? 0x811C9DC5u : d->hash_fn == SR_HASH_XXH3 ? 0x9E3779B1u : 0u;
     for (int64_t i = 0; i < n; i++) hash_values[i] = seed;
     for (int k = 0; k < d->num_part_slots; k++) {
         const sr_col_view* c = find_col(in, d->part_slots[k]);
@@ -1733,7 +1792,7 @@ extern "C" int32_t orc_hash_partition(const sr_part_desc* d, const sr_chunk_view
                 }
             } else {
                 const uint8_t* p = (const uint8_t*)c->data + i * w;
-                h = d->hash_fn == SR_HASH_FNV ? orc_fnv_hash(p, w, h) : orc_zlib_crc32(p, w, h);
+                h = d->hash_fn == SR_HASH_FNV ? orc_fnv_hash(p, w, h) : d->hash_fn == SR_HASH_XXH3 ? (uint32_t)orc_xxh3_64(p, w, h) : orc_zlib_crc32(p, w, h);
             }
             hash_values[i] = h;
         }

@@ -40,6 +40,11 @@ uint32_t orc_crc_hash_32(const void* data, int32_t bytes, uint32_t seed);
 uint32_t orc_zlib_crc32(const void* data, int32_t bytes, uint32_t seed);
 /* HashUtil::fnv_hash (be/src/base/hash/hash_util.hpp:127-134) */
 uint32_t orc_fnv_hash(const void* data, int32_t bytes, uint32_t seed);
+/* HashUtil::xx_hash3_64 = XXH3_64bits_withSeed of the vendored xxHash (be/src/base/hash/hash_util.cpp:100-102,
+ * be/src/base/hash/xxhash.h XXH3_len_1to3 / 4to8 / 9to16_64b) for inputs of 1..16 bytes -- every fixed-width value.
+ * Pinned by HashFunctionsTest.test_xx_hash3_64 (be/test/exprs/hash_functions_test.cpp:85-118) and, where the reference tree
+ * is present, cross-checked against the real header compiled into oracle/_ref/libxxh3_ref.so. returns 0 for other lengths. */
+uint64_t orc_xxh3_64(const void* data, int32_t bytes, uint64_t seed);
 /* HashUtil::xorshift32 (:223-228) */
 uint32_t orc_xorshift32(uint32_t x);
 /* ReduceOp / ModuloOp (:236-244) */

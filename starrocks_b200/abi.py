@@ -55,7 +55,7 @@ JOIN_METHOD_NONE, JOIN_METHOD_DIRECT_MAPPING, JOIN_METHOD_RANGE_DIRECT_MAPPING, 
 
 AGG_SUM, AGG_COUNT, AGG_COUNT_STAR, AGG_AVG, AGG_MIN, AGG_MAX, AGG_AVG_MERGE = 1, 2, 3, 4, 5, 6, 7
 
-HASH_FNV, HASH_CRC32 = 0, 1
+HASH_FNV, HASH_CRC32, HASH_XXH3 = 0, 1, 2
 REDUCE_MULHI, REDUCE_MODULO = 0, 1
 
 SR_MAX_OUT_COLS = 32

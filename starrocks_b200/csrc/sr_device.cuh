@@ -192,6 +192,38 @@ __device__ __forceinline__ uint32_t zlib_crc32_bytes(uint64_t lo, uint64_t hi, i
     }
     return c ^ 0xFFFFFFFFu;
 }
+// HashUtil::xx_hash3_64 = XXH3_64bits_withSeed (be/src/base/hash/xxhash.h) of one fixed-width value of 1..16 bytes held in
+// (lo, hi): XXH3_len_1to3_64b / XXH3_len_4to8_64b / XXH3_len_9to16_64b with the default secret.  The secret words are the
+// little-endian reads of kSecret at the offsets the three routines use.
+__device__ __forceinline__ uint64_t xxh3_64_value(uint64_t lo, uint64_t hi, int width, uint64_t seed) {
+    if (width <= 2) { // (width 3 does not occur: fixed-width types are 1, 2, 4, 8, 16 bytes)
+        const uint32_t b0 = (uint32_t)lo & 0xFFu, bm = (uint32_t)(lo >> (8 * (width >> 1))) & 0xFFu, bl = (uint32_t)(lo >> (8 * (width - 1))) & 0xFFu;
+        const uint32_t combined = (b0 << 16) | (bm << 24) | bl | ((uint32_t)width << 8);
+        uint64_t h = (uint64_t)combined ^ ((uint64_t)(0x396cfeb8u ^ 0xbe4ba423u) + seed); // secret[0..3] ^ secret[4..7]
+        h ^= h >> 33;
+        h *= 0xC2B2AE3D27D4EB4Full;
+        h ^= h >> 29;
+        h *= 0x165667B19E3779F9ull;
+        return h ^ (h >> 32);
+    }
+    if (width <= 8) {
+        seed ^= (uint64_t)__byte_perm((uint32_t)seed, 0, 0x0123) << 32;
+        const uint32_t in1 = (uint32_t)lo, in2 = (uint32_t)(lo >> (8 * (width - 4)));
+        uint64_t h = ((uint64_t)in2 + ((uint64_t)in1 << 32)) ^ ((0x1cad21f72c81017cull ^ 0xdb979083e96dd4deull) - seed); // secret[8..15] ^ secret[16..23]
+        h ^= ((h << 49) | (h >> 15)) ^ ((h << 24) | (h >> 40));
+        h *= 0x9FB21C651E98DF25ull;
+        h ^= (h >> 35) + (uint64_t)width;
+        h *= 0x9FB21C651E98DF25ull;
+        return h ^ (h >> 28);
+    }
+    const uint64_t l = lo ^ ((0x1f67b3b7a4a44072ull ^ 0x78e5c0cc4ee679cbull) + seed); // secret[24..31] ^ secret[32..39]
+    const uint64_t r = hi ^ ((0x2172ffcc7dd05a82ull ^ 0x8e2443f7744608b8ull) - seed); // secret[40..47] ^ secret[48..55]   (width 16: the last 8 bytes)
+    const uint64_t sw = ((uint64_t)__byte_perm((uint32_t)l, 0, 0x0123) << 32) | (uint64_t)__byte_perm((uint32_t)(l >> 32), 0, 0x0123);
+    uint64_t h = (uint64_t)width + sw + r + ((l * r) ^ __umul64hi(l, r));
+    h ^= h >> 37;
+    h *= 0x165667919E3779F9ull;
+    return h ^ (h >> 32);
+}
 // ReduceOp: hash_util.hpp:242-244
 __host__ __device__ __forceinline__ uint32_t reduce_op(uint32_t l, uint32_t r) {
     return (uint32_t)(((uint64_t)l * (uint64_t)r) >> 32);

@@ -18,7 +18,7 @@ struct PartCols {
 };
 
 __device__ __forceinline__ uint32_t part_hash_row(const PartCols& pc, int64_t row) {
-    uint32_t h = pc.hash_fn == SR_HASH_FNV ? 0x811C9DC5u : 0u;
+    uint32_t h = pc.hash_fn == SR_HASH_FNV ? 0x811C9DC5u : pc.hash_fn == SR_HASH_XXH3 ? 0x9E3779B1u : 0u; // FNV_SEED / XXH3_SEED_32
     for (int k = 0; k < pc.n; k++) {
         const DCol& c = pc.c[k];
         if (c.nulls && c.nulls[row]) {
@@ -47,7 +47,9 @@ __device__ __forceinline__ uint32_t part_hash_row(const PartCols& pc, int64_t ro
             hi = ((const uint64_t*)c.data)[2 * row + 1];
             break;
         }
-        h = pc.hash_fn == SR_HASH_FNV ? fnv_hash_bytes(lo, hi, c.width, h) : zlib_crc32_bytes(lo, hi, c.width, h);
+        h = pc.hash_fn == SR_HASH_FNV    ? fnv_hash_bytes(lo, hi, c.width, h)
+            : pc.hash_fn == SR_HASH_XXH3 ? (uint32_t)xxh3_64_value(lo, hi, c.width, (uint64_t)h)
+                                         : zlib_crc32_bytes(lo, hi, c.width, h);
     }
     return h;
 }
@@ -1202,7 +1204,7 @@ int64_t sr_fragment_rows_passed(sr_fragment* frag) {
 sr_xchg* sr_xchg_create(sr_ctx* ctx, const sr_part_desc* desc) {
     if (!ctx || !desc) return nullptr;
     if (desc->num_channels < 1 || desc->num_channels > srd::PART_MAX_CH || desc->num_part_slots < 1 || desc->num_part_slots > SR_MAX_PART_KEYS ||
-        (desc->hash_fn != SR_HASH_FNV && desc->hash_fn != SR_HASH_CRC32) || (desc->reduce_op != SR_REDUCE_MULHI && desc->reduce_op != SR_REDUCE_MODULO)) {
+        (desc->hash_fn != SR_HASH_FNV && desc->hash_fn != SR_HASH_CRC32 && desc->hash_fn != SR_HASH_XXH3) || (desc->reduce_op != SR_REDUCE_MULHI && desc->reduce_op != SR_REDUCE_MODULO)) {
         sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "partition desc (channels 1..%d, 1..%d slots)", srd::PART_MAX_CH, SR_MAX_PART_KEYS);
         return nullptr;
     }

@@ -9,15 +9,17 @@
 //                          RuntimeFilterHub and the lineorder scan consuming them (local_rf_block until they are ready)
 //   result pipeline:       GpuAggregateBlockingSourceOperator -> ResultSink (collects rows)
 //
-// A and B must give the same groups, and both must match a straightforward row-at-a-time evaluation of the query in
-// this file (the checker).  Exit code 0 = pass.  Needs a CUDA device (run by tests/test_host_pipeline.py -m gpu).
+// A, B and C must give the groups of the CPU ORACLE (oracle/sr_oracle.cpp: the restatement of the reference's operators)
+// run on the same chunks -- dimension scans + join builds + the chunk-at-a-time probe / aggregate pipeline
+// (orc_fragment_run); a row-at-a-time evaluation of the query in this file cross-checks the oracle.  Exit code 0 = pass.  Needs a CUDA device (run by tests/test_host_pipeline.py -m gpu).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <tuple>
 
-#include "../gpu/gpu_operators.h"
+#include "../../oracle/sr_oracle.h"
+#include "../../starrocks_b200/host/gpu/gpu_operators.h"
 
 using namespace starrocks;
 using namespace starrocks::pipeline;
@@ -212,6 +214,85 @@ int main(int argc, char** argv) {
     agg_desc.fns[0] = sr_agg_fn{SR_AGG_SUM, SR_TYPE_INT, OUT_REV, 0, col_expr(LO_REVENUE)};
     agg_desc.fns[1] = sr_agg_fn{SR_AGG_SUM, SR_TYPE_INT, OUT_COST, 0, col_expr(LO_SUPPLYCOST)};
 
+    // ---- the oracle: the same plan through the CPU restatement of the reference's operators ----
+    Groups oracle_groups;
+    {
+        std::vector<orc_join*> ojoins;
+        orc_fragment_desc ofd{};
+        ofd.num_joins = (int32_t)dims.size();
+        ofd.agg = agg_desc;
+        for (size_t k = 0; k < dims.size(); k++) {
+            Dim& dm = dims[k];
+            std::vector<int32_t> outs = {dm.key_slot};
+            for (int32_t p : dm.payload) outs.push_back(p);
+            sr_scan_desc sd{};
+            sd.preds = dm.pred;
+            sd.num_preds = dm.pred ? 1 : 0;
+            sd.out_slots = outs.data();
+            sd.num_out_slots = (int32_t)outs.size();
+            std::vector<sr_col_view> views;
+            sr_chunk_view tv = make_chunk_view(*dm.table, &views);
+            std::vector<std::vector<int32_t>> kept(outs.size(), std::vector<int32_t>(dm.table->num_rows()));
+            std::vector<void*> od(outs.size());
+            std::vector<uint8_t*> on(outs.size(), nullptr);
+            for (size_t c = 0; c < outs.size(); c++) od[c] = kept[c].data();
+            const int64_t rows = orc_scan_filter(&sd, &tv, od.data(), on.data());
+            if (rows < 0) {
+                fprintf(stderr, "oracle scan failed: %s\n", orc_last_error());
+                return 2;
+            }
+            sr_join_desc jd{};
+            jd.join_type = SR_JOIN_INNER;
+            jd.num_keys = 1;
+            jd.build_key_slots[0] = dm.key_slot;
+            jd.probe_key_slots[0] = dm.probe_slot;
+            jd.key_types[0] = SR_TYPE_INT;
+            jd.enable_range_direct_mapping = 1;
+            jd.num_build_out = (int32_t)dm.payload.size();
+            for (size_t p = 0; p < dm.payload.size(); p++) jd.build_out_slots[p] = dm.payload[p];
+            orc_join_options opt{1, 1, 1 << 20, 32 << 20, 0, 0};
+            orc_join* oj = orc_join_create(&jd, &opt);
+            std::vector<sr_col_view> bcols;
+            for (size_t c = 0; c < outs.size(); c++) bcols.push_back(sr_col_view{kept[c].data(), nullptr, SR_TYPE_INT, outs[c]});
+            sr_chunk_view bv{bcols.data(), (int32_t)bcols.size(), SR_MEM_HOST, rows};
+            if (!oj || orc_join_append_build(oj, &bv) != SR_OK || orc_join_build(oj) != SR_OK) {
+                fprintf(stderr, "oracle join build failed: %s\n", orc_last_error());
+                return 2;
+            }
+            ojoins.push_back(oj);
+            ofd.joins[k].join = oj;
+            ofd.joins[k].probe_key_slot = dm.probe_slot;
+            ofd.joins[k].num_payload = (int32_t)dm.payload.size();
+            for (size_t p = 0; p < dm.payload.size(); p++) ofd.joins[k].payload_build_slots[p] = dm.payload[p];
+        }
+        std::vector<sr_col_view> fviews;
+        sr_chunk_view fv = make_chunk_view(*lineorder, &fviews);
+        orc_agg* oresult = orc_agg_create(&agg_desc);
+        int64_t passed = 0;
+        if (!oresult || orc_fragment_run(&ofd, &fv, 4, oresult, &passed) != SR_OK) {
+            fprintf(stderr, "oracle fragment run failed: %s\n", orc_last_error());
+            return 2;
+        }
+        const int64_t g = orc_agg_num_groups(oresult);
+        std::vector<int32_t> oy((size_t)g), on_((size_t)g);
+        std::vector<int64_t> orv((size_t)g), oc((size_t)g);
+        std::vector<uint8_t> nul0((size_t)g), nul1((size_t)g), nul2((size_t)g), nul3((size_t)g);
+        void* od[4] = {oy.data(), on_.data(), orv.data(), oc.data()};
+        uint8_t* onl[4] = {nul0.data(), nul1.data(), nul2.data(), nul3.data()};
+        if (orc_agg_output(oresult, od, onl) != SR_OK) {
+            fprintf(stderr, "oracle output failed: %s\n", orc_last_error());
+            return 2;
+        }
+        for (int64_t i = 0; i < g; i++) oracle_groups[{oy[(size_t)i], on_[(size_t)i]}] = {orv[(size_t)i], oc[(size_t)i]};
+        orc_agg_destroy(oresult);
+        for (auto* oj : ojoins) orc_join_destroy(oj);
+        if (oracle_groups != expect) {
+            fprintf(stderr, "the oracle (%zu groups) and the row-at-a-time evaluation (%zu groups) disagree\n", oracle_groups.size(), expect.size());
+            return 2;
+        }
+        printf("oracle: %zu groups from %lld joined rows (equal to the row-at-a-time evaluation)\n", oracle_groups.size(), (long long)passed);
+    }
+
     Groups results[3];
     size_t rows_after_scan[3] = {0, 0, 0};
     for (int variant = 0; variant < 3; variant++) {
@@ -333,6 +414,7 @@ int main(int argc, char** argv) {
         printf("%s path: %zu groups, %zu rows left the scan, %zu rows moved between operators\n",
                fused ? "fused fragment" : with_rf ? "per-operator + runtime filters" : "per-operator", results[variant].size(), rows_after_scan[variant],
                probe_driver.rows_moved());
+        for (auto& op : ops) printf("    %s | %s | %s\n", op->runtime_profile()->name().c_str(), op->common_metrics()->to_string().c_str(), op->unique_metrics()->to_string().c_str());
         ops.clear(); // scans go before the hub that owns their filters
     }
     int rc = 0;
@@ -465,12 +547,12 @@ int main(int argc, char** argv) {
             first.close(&state);
         }
     }
-    if (results[0] != expect) {
-        fprintf(stderr, "per-operator pipeline differs from the checker (%zu vs %zu groups)\n", results[0].size(), expect.size());
+    if (results[0] != oracle_groups) {
+        fprintf(stderr, "per-operator pipeline differs from the oracle (%zu vs %zu groups)\n", results[0].size(), expect.size());
         rc = 1;
     }
-    if (results[2] != expect) {
-        fprintf(stderr, "per-operator pipeline with runtime filters differs from the checker (%zu vs %zu groups)\n", results[2].size(), expect.size());
+    if (results[2] != oracle_groups) {
+        fprintf(stderr, "per-operator pipeline with runtime filters differs from the oracle (%zu vs %zu groups)\n", results[2].size(), expect.size());
         rc = 1;
     }
     {
@@ -485,8 +567,8 @@ int main(int argc, char** argv) {
         }
         printf("runtime filters: scan output %zu -> %zu rows (%zu rows join)\n", rows_after_scan[0], rows_after_scan[2], joined);
     }
-    if (results[1] != expect) {
-        fprintf(stderr, "fused pipeline differs from the checker (%zu vs %zu groups)\n", results[1].size(), expect.size());
+    if (results[1] != oracle_groups) {
+        fprintf(stderr, "fused pipeline differs from the oracle (%zu vs %zu groups)\n", results[1].size(), expect.size());
         rc = 1;
     }
     printf("kernel launches: %lld\n", (long long)sr_ctx_kernel_launches(ctx));

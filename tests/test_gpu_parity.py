@@ -807,7 +807,7 @@ def test_fragment_rejects_duplicate_build_keys(gpu, ctx):
 # ---------------------------------------------------------------------------------------------
 # exchange partitioning (K18)
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("hash_fn,reduce_op", [(abi.HASH_FNV, abi.REDUCE_MULHI), (abi.HASH_CRC32, abi.REDUCE_MODULO)])
+@pytest.mark.parametrize("hash_fn,reduce_op", [(abi.HASH_FNV, abi.REDUCE_MULHI), (abi.HASH_CRC32, abi.REDUCE_MODULO), (abi.HASH_XXH3, abi.REDUCE_MULHI)])
 @pytest.mark.parametrize("nch", [1, 8, 37])
 @pytest.mark.parametrize("n", [0, 1, 1023, 50_001])
 def test_xchg_partition_parity(gpu, ctx, oracle, hash_fn, reduce_op, nch, n):
@@ -830,6 +830,27 @@ def test_xchg_partition_parity(gpu, ctx, oracle, hash_fn, reduce_op, nch, n):
             assert np.array_equal(got[0][3], chunk._keep[0][1][ori])
     finally:
         x.close()
+
+
+def test_xchg_xxh3_all_widths(gpu, ctx, oracle):
+    # exchange_hash_function_version = 1 (XXH3) over every fixed width: 1 / 2 bytes take XXH3_len_1to3_64b, 4 / 8 bytes
+    # XXH3_len_4to8_64b, 16 bytes (decimal128) XXH3_len_9to16_64b -- the oracle is pinned by the reference's goldens and by
+    # the reference's own xxhash.h (tests/test_oracle_golden.py)
+    rng = np.random.default_rng(23)
+    n = 20_011
+    dec = rng.integers(0, 256, (n, 16), dtype=np.uint8)
+    chunk = Chunk([(0, rng.integers(-128, 128, n, dtype=np.int8), None), (1, rng.integers(-30000, 30000, n, dtype=np.int16), rand_nulls(rng, n, 0.1)),
+                   (2, rng.integers(-10**9, 10**9, n, dtype=np.int32), None), (3, rng.integers(-10**17, 10**17, n, dtype=np.int64), None),
+                   (4, dec.reshape(-1).view(np.dtype((np.void, 16))), None, abi.TYPE_DECIMAL128)])
+    for slots in ([0], [1], [2], [3], [4], [0, 1, 2, 3, 4]):
+        d = abi.make_part_desc(slots, 8, hash_fn=abi.HASH_XXH3)
+        x = gpu.Xchg(ctx, d)
+        try:
+            ohv, och, _, _ = oracle.hash_partition(d, chunk)
+            hv, ch = x.hash(chunk)
+            assert np.array_equal(hv, ohv) and np.array_equal(ch, och), slots
+        finally:
+            x.close()
 
 
 def test_large_batches_take_the_two_level_scan(gpu, ctx, oracle):

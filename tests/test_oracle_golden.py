@@ -538,3 +538,52 @@ def test_divide_by_zero_is_null(oracle):
     ag.push(Chunk([(0, a, None), (1, b, None)]))
     out = ag.output()
     assert out[0][1][0] == 6.0 and out[1][1][0] == 2          # 6/3 + 8/2, two non-NULL quotients
+
+
+def test_xxh3_64_reference_goldens(oracle):
+    # HashFunctionsTest.test_xx_hash3_64 (be/test/exprs/hash_functions_test.cpp:85-118): xx_hash3_64('hello') and
+    # ('starrocks') with XXHASH3_64_SEED = 0; two columns chain the first hash as the seed of the second.  5 bytes take
+    # XXH3_len_4to8_64b, 9 bytes XXH3_len_9to16_64b.
+    L = oracle.lib()
+
+    def h(b, seed):
+        buf = np.frombuffer(b, dtype=np.uint8).copy()
+        v = L.orc_xxh3_64(buf.ctypes.data, len(b), seed)
+        return v - (1 << 64) if v >= 1 << 63 else v
+    assert h(b"hello", 0) == -7685981735718036227
+    assert h(b"starrocks", 0) == 6573472450560322992
+    assert h(b"world", h(b"hello", 0) & ((1 << 64) - 1)) == 7001965798170371843
+    assert h(b"starrocks", h(b"hello", 0) & ((1 << 64) - 1)) == 2803320466222626098
+
+
+def test_xxh3_64_against_the_reference_header(oracle):
+    # oracle/_ref/libxxh3_ref.so = the reference's vendored xxhash.h compiled where it lies (`make -C oracle ref`): every
+    # length 1..16, random bytes and seeds, must agree with the restatement
+    ref = oracle.ref_xxh3()
+    if ref is None:
+        pytest.skip("oracle/_ref/libxxh3_ref.so was not built (no reference tree on this machine)")
+    L = oracle.lib()
+    rng = np.random.default_rng(11)
+    for n in range(1, 17):
+        for _ in range(200):
+            buf = rng.integers(0, 256, n, dtype=np.uint8)
+            seed = int(rng.integers(0, 1 << 63)) * 2 + int(rng.integers(0, 2))
+            if _ % 2:
+                seed &= 0xFFFFFFFF          # the exchange feeds 32-bit seeds
+            assert L.orc_xxh3_64(buf.ctypes.data, n, seed) == ref.ref_xx_hash3_64(buf.ctypes.data, n, seed), (n, seed)
+
+
+def test_hash_partition_xxh3_matches_value_hash(oracle):
+    # exchange_hash_function_version = 1: per partition column hash = (uint32) xx_hash3_64(value, width, seed = hash so far),
+    # from XXH3_SEED_32 = 0x9E3779B1 (exchange_sink_operator.cpp:597-601); channel = ReduceOp(hash, n)
+    rng = np.random.default_rng(12)
+    a = rng.integers(-10**9, 10**9, 1000, dtype=np.int32)
+    b = rng.integers(-10**15, 10**15, 1000, dtype=np.int64)
+    d = abi.make_part_desc([0, 1], 7, hash_fn=abi.HASH_XXH3)
+    hv, ch, ri, st = oracle.hash_partition(d, Chunk([(0, a, None), (1, b, None)]))
+    L = oracle.lib()
+    for i in (0, 1, 500, 999):
+        h = 0x9E3779B1
+        h = L.orc_xxh3_64(a[i:i + 1].ctypes.data, 4, h) & 0xFFFFFFFF
+        h = L.orc_xxh3_64(b[i:i + 1].ctypes.data, 8, h) & 0xFFFFFFFF
+        assert hv[i] == h and ch[i] == (h * 7) >> 32
