@@ -610,6 +610,43 @@ int32_t sr_xchg_partition(sr_xchg* x, const sr_chunk_view* in, sr_chunk_out* out
 int32_t sr_xchg_hash(sr_xchg* x, const sr_chunk_view* in, uint32_t* hash_values, uint32_t* channel_ids, int32_t mem);
 
 /* ---------------------------------------------------------------------------------------
+ * exchange wire format: the bytes of ChunkPB.data as ProtobufChunkSerde::serialize_without_meta writes
+ * them (be/src/serde/protobuf_serde.cpp:88-140) with encode level 0 and no compression:
+ *      fixed32 version = 1 | fixed32 num_rows | columns in chunk order
+ *      FixedLengthColumn<T>:  fixed32 byte size | raw little-endian values      (column_array_serde.cpp:214-255)
+ *      NullableColumn:        the null column (a uint8 FixedLengthColumn) | the data column          (:759-782)
+ * so a channel slice produced by sr_xchg_partition can be handed to the unchanged brpc sender (ExchangeSinkOperator::
+ * Channel::send_one_chunk, exchange_sink_operator.cpp) and a ChunkPB received from a CPU BE can be consumed on the device.
+ * The protobuf envelope itself (slot_id_map, is_nulls, is_consts, serialized_size, uncompressed_size, compress_type) stays
+ * host code; sr_chunk_pb_meta carries what it needs.  Fixed-length and nullable fixed-length columns; the integer
+ * (streamvbyte) encodings of encode_level > 0 and var-length columns are not produced.
+ * ------------------------------------------------------------------------------------- */
+typedef struct sr_chunk_pb_meta {
+    int64_t serialized_size; /* bytes of ChunkPB.data = ChunkPB.serialized_size = uncompressed_size (no padding at level 0) */
+    int64_t num_rows;
+    int32_t num_cols;
+    int32_t reserved;
+    int32_t slot_ids[SR_MAX_OUT_COLS];  /* slot_id_map: slot id -> column index, in column order */
+    int32_t types[SR_MAX_OUT_COLS];     /* sr_type of every column (the receiver knows it from its RowDescriptor) */
+    uint8_t is_nulls[SR_MAX_OUT_COLS];  /* ChunkPB.is_nulls */
+    uint8_t is_consts[SR_MAX_OUT_COLS]; /* ChunkPB.is_consts: always 0 here */
+} sr_chunk_pb_meta;
+/* bytes rows [row_begin, row_end) of `chunk` serialize to */
+int64_t sr_chunk_serialized_size(const sr_chunk_view* chunk, int64_t row_begin, int64_t row_end);
+/* Serialize rows [row_begin, row_end) of `chunk` (host or device columns) into dst (dst_mem: SR_MEM_HOST -- a page-locked
+ * buffer makes it one DMA per column -- or SR_MEM_DEVICE); dst_capacity >= sr_chunk_serialized_size.  Queued on the context's
+ * stream; synchronises when dst is host memory. */
+int32_t sr_chunk_serialize(sr_ctx* ctx, const sr_chunk_view* chunk, int64_t row_begin, int64_t row_end, void* dst, int64_t dst_capacity,
+                           int32_t dst_mem, sr_chunk_pb_meta* meta);
+/* Parse ChunkPB.data (src in src_mem) described by `meta` (num_cols, slot_ids, types, is_nulls) into device columns owned by
+ * `handle` (valid until its next deserialize / destroy); checks version, sizes and bounds like the reference's
+ * deserialize (SR_ERR_INVALID_ARGUMENT on a malformed payload). */
+typedef struct sr_serde sr_serde;
+sr_serde* sr_serde_create(sr_ctx* ctx);
+void sr_serde_destroy(sr_serde* handle);
+int32_t sr_chunk_deserialize(sr_serde* handle, const void* src, int64_t bytes, int32_t src_mem, const sr_chunk_pb_meta* meta, sr_chunk_out* out);
+
+/* ---------------------------------------------------------------------------------------
  * K11: Column::append_selective gather (be/src/column/fixed_length_column_base.cpp:54):
  * dst[j] = src[index[j]] for one column; all pointers in `mem`.
  * ------------------------------------------------------------------------------------- */

@@ -79,6 +79,7 @@ def lib():
         "orc_zlib_crc32": (u32, [vp, i32, u32]),
         "orc_fnv_hash": (u32, [vp, i32, u32]),
         "orc_xxh3_64": (C.c_uint64, [vp, i32, C.c_uint64]),
+        "orc_chunk_serialize": (C.c_int64, [vp, C.c_int64, C.c_int64, vp, C.c_int64]),
         "orc_xorshift32": (u32, [u32]),
         "orc_reduce_op": (u32, [u32, u32]),
         "orc_filter_range": (i64, [vp, vp, i32, i64, i64]),
@@ -401,6 +402,18 @@ class RuntimeFilter:
 
 def value_hash(v):
     return int(lib().orc_rf_value_hash(int(v)))
+
+
+def chunk_serialize(chunk, row_begin=0, row_end=None):
+    """ChunkPB.data bytes (encode level 0) of rows [row_begin, row_end) -> uint8 ndarray"""
+    row_end = chunk.num_rows if row_end is None else row_end
+    n = lib().orc_chunk_serialize(chunk.ref(), row_begin, row_end, None, 0)
+    if n < 0:
+        _check(int(n))
+    buf = np.zeros(n, dtype=np.uint8)
+    n2 = lib().orc_chunk_serialize(chunk.ref(), row_begin, row_end, buf.ctypes.data, n)
+    assert n2 == n
+    return buf
 
 
 def fragment_run(scan_desc, joins, agg_desc, fact_chunk, num_threads=1):

@@ -1710,6 +1710,38 @@ extern "C" int32_t orc_agg_merge(orc_agg* a, const orc_agg* o) {
 }
 
 // ---------------------------------------------------------------------------------------
+// exchange wire format: protobuf_serde.cpp:88-140 (encode_fixed32_le(buff, 1); encode_fixed32_le(buff + 4, num_rows);
+// columns), column_array_serde.cpp:228-238 (write_little_endian_32(size) + write_raw), :768-772 (null column, data column)
+// ---------------------------------------------------------------------------------------
+extern "C" int64_t orc_chunk_serialize(const sr_chunk_view* c, int64_t r0, int64_t r1, uint8_t* dst, int64_t cap) {
+    if (r0 < 0 || r1 < r0 || r1 > c->num_rows) return fail(SR_ERR_INVALID_ARGUMENT, "row range");
+    const int64_t rows = r1 - r0;
+    int64_t total = 8;
+    for (int k = 0; k < c->num_cols; k++) total += (c->cols[k].nulls ? 4 + rows : 0) + 4 + rows * type_width(c->cols[k].type);
+    if (!dst) return total;
+    if (total > cap) return fail(SR_ERR_INVALID_ARGUMENT, "serialize: destination too small");
+    uint8_t* p = dst;
+    auto put32 = [&](uint32_t v) {
+        for (int b = 0; b < 4; b++) *p++ = (uint8_t)(v >> (8 * b));
+    };
+    put32(1);
+    put32((uint32_t)rows);
+    for (int k = 0; k < c->num_cols; k++) {
+        const sr_col_view& col = c->cols[k];
+        const int w = type_width(col.type);
+        if (col.nulls) {
+            put32((uint32_t)rows);
+            memcpy(p, col.nulls + r0, (size_t)rows);
+            p += rows;
+        }
+        put32((uint32_t)(rows * w));
+        memcpy(p, (const uint8_t*)col.data + r0 * w, (size_t)(rows * w));
+        p += rows * w;
+    }
+    return total;
+}
+
+// ---------------------------------------------------------------------------------------
 // XXH3 64-bit, short inputs (be/src/base/hash/xxhash.h: XXH3_len_1to3_64b, XXH3_len_4to8_64b, XXH3_len_9to16_64b,
 // XXH3_rrmxmx, XXH3_avalanche, XXH64_avalanche, kSecret)
 // ---------------------------------------------------------------------------------------

@@ -156,6 +156,13 @@ int32_t orc_agg_convert_to_states(const sr_agg_desc* first_phase_desc, const sr_
 int32_t orc_hash_partition(const sr_part_desc* desc, const sr_chunk_view* in, uint32_t* hash_values,
                            uint32_t* channel_ids, uint32_t* row_indexes, int64_t* channel_starts);
 
+/* ---- exchange wire format -------------------------------------------------------------- */
+/* ChunkPB.data at encode level 0 (ProtobufChunkSerde::serialize_without_meta, be/src/serde/protobuf_serde.cpp:88-140;
+ * FixedLengthColumnSerde / NullableColumnSerde, column_array_serde.cpp:214-255,759-782): fixed32 version 1, fixed32 rows, per
+ * column [null column: fixed32 n + n bytes] fixed32 byte size + raw values.  rows [row_begin, row_end).  returns the number of
+ * bytes written (dst may be NULL to size the buffer), < 0 on error. */
+int64_t orc_chunk_serialize(const sr_chunk_view* chunk, int64_t row_begin, int64_t row_end, uint8_t* dst, int64_t cap);
+
 /* ---- whole pipeline (CPU BE stand-in) ------------------------------------------------ */
 typedef struct orc_frag_join {
     orc_join* join;

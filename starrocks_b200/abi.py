@@ -118,6 +118,12 @@ class sr_join_desc(C.Structure):
                 ("build_out_types", C.c_int32 * SR_MAX_JOIN_OUT)]
 
 
+class sr_chunk_pb_meta(C.Structure):
+    _fields_ = [("serialized_size", C.c_int64), ("num_rows", C.c_int64), ("num_cols", C.c_int32), ("reserved", C.c_int32),
+                ("slot_ids", C.c_int32 * SR_MAX_OUT_COLS), ("types", C.c_int32 * SR_MAX_OUT_COLS),
+                ("is_nulls", C.c_uint8 * SR_MAX_OUT_COLS), ("is_consts", C.c_uint8 * SR_MAX_OUT_COLS)]
+
+
 class sr_join_info(C.Structure):
     _fields_ = [("method", C.c_int32), ("has_duplicates", C.c_int32), ("build_rows", C.c_int64),
                 ("bucket_size", C.c_int64), ("min_value", C.c_int64), ("max_value", C.c_int64)]

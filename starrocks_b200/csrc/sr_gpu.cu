@@ -2,6 +2,7 @@
 // code lives in the headers included below.  sm_100a only; there is no CPU fallback: without a
 // CUDA device every entry point fails with SR_ERR_NO_DEVICE / SR_ERR_CUDA.
 #include "sr_frag.cuh"
+#include "sr_serde.cuh"
 
 // ---------------------------------------------------------------------------------------
 // exchange: hash partition (K18).  exchange_sink_operator.cpp:586-637, shuffler.h:72-89,
@@ -1398,6 +1399,40 @@ int32_t sr_bandwidth_probe(sr_ctx* ctx, const void* dev_ptr, int64_t bytes, uint
         *checksum_host = ctx->pinned[32];
     }
     return SR_OK;
+}
+
+// ------------------------------------------------------------------ exchange wire format (ChunkPB.data)
+int64_t sr_chunk_serialized_size(const sr_chunk_view* chunk, int64_t row_begin, int64_t row_end) {
+    if (!chunk || row_begin < 0 || row_end < row_begin) return SR_ERR_INVALID_ARGUMENT;
+    return serde_size(chunk, row_end - row_begin);
+}
+
+int32_t sr_chunk_serialize(sr_ctx* ctx, const sr_chunk_view* chunk, int64_t row_begin, int64_t row_end, void* dst, int64_t dst_capacity, int32_t dst_mem,
+                           sr_chunk_pb_meta* meta) {
+    SR_BIND(ctx);
+    if (!chunk || !dst) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "sr_chunk_serialize: null argument");
+    return serde_serialize(ctx, chunk, row_begin, row_end, dst, dst_capacity, dst_mem, meta);
+}
+
+sr_serde* sr_serde_create(sr_ctx* ctx) {
+    if (!ctx) return nullptr;
+    sr_serde* h = new sr_serde();
+    h->ctx = ctx;
+    return h;
+}
+
+void sr_serde_destroy(sr_serde* h) {
+    if (!h) return;
+    SR_LOCK(h->ctx);
+    cudaSetDevice(h->ctx->device);
+    cudaStreamSynchronize(h->ctx->stream);
+    delete h;
+}
+
+int32_t sr_chunk_deserialize(sr_serde* h, const void* src, int64_t bytes, int32_t src_mem, const sr_chunk_pb_meta* meta, sr_chunk_out* out) {
+    if (!h || !src || !meta || !out) return SR_ERR_INVALID_ARGUMENT;
+    SR_BIND(h->ctx);
+    return serde_deserialize(h, src, bytes, src_mem, meta, out);
 }
 
 int32_t sr_flush_l2(sr_ctx* ctx) {

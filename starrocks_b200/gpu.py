@@ -110,6 +110,11 @@ def lib():
         "sr_abi_sizeof": (i32, [i32]),
         "sr_bandwidth_probe": (i32, [vp, vp, i64, vp]),
         "sr_flush_l2": (i32, [vp]),
+        "sr_chunk_serialized_size": (i64, [vp, i64, i64]),
+        "sr_chunk_serialize": (i32, [vp, vp, i64, i64, vp, i64, i32, vp]),
+        "sr_serde_create": (vp, [vp]),
+        "sr_serde_destroy": (None, [vp]),
+        "sr_chunk_deserialize": (i32, [vp, vp, i64, i32, vp, vp]),
         "sr_host_alloc": (i32, [vp, i64, vp]),
         "sr_host_free": (i32, [vp, vp]),
         "sr_event_create": (vp, [vp]),
@@ -140,6 +145,7 @@ EXPORTED_SYMBOLS = [
     "sr_join_build_runtime_filter", "sr_rf_create", "sr_rf_insert", "sr_rf_destroy", "sr_rf_get_info", "sr_rf_copy_directory",
     "sr_rf_merge_directory", "sr_rf_evaluate", "sr_scan_add_runtime_filter",
     "sr_xchg_destroy", "sr_xchg_partition", "sr_xchg_hash", "sr_gather", "sr_memcpy", "sr_abi_sizeof", "sr_bandwidth_probe", "sr_flush_l2",
+    "sr_chunk_serialized_size", "sr_chunk_serialize", "sr_serde_create", "sr_serde_destroy", "sr_chunk_deserialize",
     "sr_host_alloc", "sr_host_free", "sr_event_create", "sr_event_destroy", "sr_event_record", "sr_event_query", "sr_event_sync",
 ]
 
@@ -488,6 +494,35 @@ class Fragment:
     @property
     def rows_passed(self):
         return self.ctx.check(lib().sr_fragment_rows_passed(self.h))
+
+
+def chunk_serialize(ctx, chunk, row_begin=0, row_end=None):
+    """ChunkPB.data bytes of rows [row_begin, row_end) of `chunk` (host or device columns) -> (uint8 ndarray, sr_chunk_pb_meta)"""
+    row_end = chunk.num_rows if row_end is None else row_end
+    n = ctx.check(lib().sr_chunk_serialized_size(chunk.ref(), row_begin, row_end))
+    buf = np.zeros(n, dtype=np.uint8)
+    meta = abi.sr_chunk_pb_meta()
+    ctx.check(lib().sr_chunk_serialize(ctx.h, chunk.ref(), row_begin, row_end, buf.ctypes.data, n, abi.MEM_HOST, C.byref(meta)))
+    return buf, meta
+
+
+class Serde:
+    """sr_serde: owner of the device columns a ChunkPB.data payload deserialises into"""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.h = lib().sr_serde_create(ctx.h)
+
+    def close(self):
+        if self.h:
+            lib().sr_serde_destroy(self.h)
+            self.h = None
+
+    def deserialize(self, payload, meta):
+        out = abi.sr_chunk_out()
+        payload = np.ascontiguousarray(payload, dtype=np.uint8)
+        self.ctx.check(lib().sr_chunk_deserialize(self.h, payload.ctypes.data, payload.nbytes, abi.MEM_HOST, C.byref(meta), C.byref(out)))
+        return out
 
 
 class Xchg:

@@ -853,6 +853,45 @@ def test_xchg_xxh3_all_widths(gpu, ctx, oracle):
             x.close()
 
 
+@pytest.mark.parametrize("n", [0, 1, 4096, 70_001])
+@pytest.mark.parametrize("device_columns", [False, True])
+def test_chunk_wire_format_parity(gpu, ctx, oracle, n, device_columns):
+    # ChunkPB.data: the device serialiser must produce the oracle's bytes (slices of a partitioned chunk are
+    # what the exchange ships per channel), and deserialising them gives the columns back
+    rng = np.random.default_rng(31)
+    dec = rng.integers(0, 256, (n, 16), dtype=np.uint8)
+    cols = [(3, rng.integers(-10**9, 10**9, n, dtype=np.int32), rand_nulls(rng, n, 0.2)), (4, rng.integers(-10**17, 10**17, n, dtype=np.int64), None),
+            (5, rng.integers(-100, 100, n, dtype=np.int8), rand_nulls(rng, n, 0.5)), (6, rng.normal(size=n), None),
+            (7, dec.reshape(-1).view(np.dtype((np.void, 16))), None, abi.TYPE_DECIMAL128)]
+    host = Chunk(cols)
+    src = host
+    keep = []
+    if device_columns and n > 0:          # run the columns through the partition step: its output lives on the device
+        x = gpu.Xchg(ctx, abi.make_part_desc([3], 1))
+        out, _ = x.partition(host)
+        src = gpu.chunk_out_as_view(out)
+        keep.append(x)
+    try:
+        for lo, hi in ((0, n), (n // 3, n - n // 4)):
+            payload, meta = gpu.chunk_serialize(ctx, src, lo, hi)
+            assert payload.tobytes() == oracle.chunk_serialize(host, lo, hi).tobytes()
+            assert meta.serialized_size == payload.nbytes and meta.num_rows == hi - lo and list(meta.is_nulls[:5]) == [1, 0, 1, 0, 0]
+            sd = gpu.Serde(ctx)
+            try:
+                back = gpu.chunk_out_to_host(ctx, sd.deserialize(payload, meta))
+                for k, c in enumerate(cols):
+                    assert np.array_equal(back[k][2].view(np.uint8), c[1][lo:hi].view(np.uint8)) and back[k][0] == c[0]
+                    assert (back[k][3] is None) == (c[2] is None) and (c[2] is None or np.array_equal(back[k][3], c[2][lo:hi]))
+                if hi - lo > 0:            # a truncated payload must be refused, not read out of bounds
+                    with pytest.raises(gpu.GpuError):
+                        sd.deserialize(payload[:-3], meta)
+            finally:
+                sd.close()
+    finally:
+        for x in keep:
+            x.close()
+
+
 def test_large_batches_take_the_two_level_scan(gpu, ctx, oracle):
     # 5 M-row probe (19.5 K block counts) and a 37-channel partition of 3 M rows (> 16 K tile x channel counts): the
     # exclusive scans behind the ordered outputs switch from the single-block walk to the two-level form

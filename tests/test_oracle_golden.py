@@ -587,3 +587,18 @@ def test_hash_partition_xxh3_matches_value_hash(oracle):
         h = L.orc_xxh3_64(a[i:i + 1].ctypes.data, 4, h) & 0xFFFFFFFF
         h = L.orc_xxh3_64(b[i:i + 1].ctypes.data, 8, h) & 0xFFFFFFFF
         assert hv[i] == h and ch[i] == (h * 7) >> 32
+
+
+def test_chunk_wire_format_bytes(oracle):
+    # ChunkPB.data at encode level 0 (protobuf_serde.cpp:88-140, column_array_serde.cpp:228-238,768-772), written out by hand:
+    # version 1, 3 rows; nullable int32 column = null column (uint8 x 3) then data column; int64 column
+    a = np.array([7, -1, 300], dtype=np.int32)
+    an = np.array([0, 1, 0], dtype=np.uint8)
+    b = np.array([1, 2, -3], dtype=np.int64)
+    got = oracle.chunk_serialize(Chunk([(5, a, an), (9, b, None)]))
+    import struct
+    want = struct.pack("<II", 1, 3) + struct.pack("<I", 3) + bytes([0, 1, 0]) + struct.pack("<I", 12) + struct.pack("<iii", 7, -1, 300) \
+        + struct.pack("<I", 24) + struct.pack("<qqq", 1, 2, -3)
+    assert got.tobytes() == want
+    assert oracle.chunk_serialize(Chunk([(5, a, an), (9, b, None)]), 1, 2).tobytes() == \
+        struct.pack("<II", 1, 1) + struct.pack("<I", 1) + bytes([1]) + struct.pack("<Ii", 4, -1) + struct.pack("<Iq", 8, 2)
