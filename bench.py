@@ -47,6 +47,10 @@ def parse_args():
     ap.add_argument("--sf", type=float, default=100.0, help="SSB scale factor per GPU (weak scaling)")
     ap.add_argument("--rows", type=int, default=0, help="override fact rows per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-morsel-rows", type=int, default=1 << 22,
+                    help="e2e: the host columns are pushed in morsels of this many rows (measured: 4 M-row morsels 170.6 ms per 600 M rows, "
+                         "one 600 M-row batch 197 ms; tools/e2e_batches.py)")
+    ap.add_argument("--no-operator-e2e", action="store_true", help="skip e2e.operator_api (the C++ operator path, starrocks_b200/host/bench)")
     ap.add_argument("--cpu-sample-rows", type=int, default=0, help="rows of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -425,14 +429,22 @@ def run_gpu(args):
             e2e = {"value": None, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                    "error": f"pinned host allocation failed: {ex}"}
     def run_e2e(mem):
-        hchunk = abi.Chunk([(ssb.LO_SLOTS[nm], host_cols[nm].data_ptr(), None, abi.TYPE_INT) for nm in ssb.Q41_FACT_COLS],
-                           num_rows=n, mem=mem)
-        r0 = step(hchunk)  # warm-up (allocates the staging buffers)
+        morsel = max(1, args.e2e_morsel_rows)
+
+        def e2e_step():
+            """one pass over the HOST columns in morsels (what a scan hands over), merge, result to the host"""
+            frag.reset()
+            for lo in range(0, n, morsel):
+                hi = min(n, lo + morsel)
+                frag.push(abi.Chunk([(ssb.LO_SLOTS[nm], host_cols[nm][lo:hi].data_ptr(), None, abi.TYPE_INT) for nm in ssb.Q41_FACT_COLS],
+                                    num_rows=hi - lo, mem=mem))
+            return finish_step()
+        r0 = e2e_step()  # warm-up (allocates the staging buffers)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.e2e_steps):
-            r0 = step(hchunk)
+            r0 = e2e_step()
         e1.record(stream)
         barrier()
         ems = e0.elapsed_time(e1) / args.e2e_steps
@@ -445,7 +457,7 @@ def run_gpu(args):
             from starrocks_b200.rows import gpu_rows
             assert gpu_rows(r0) == gpu_rows(result), "e2e (host buffers) result differs from the HBM-resident result"
         return {"value": n * world / (ems / 1000.0), "unit": "rows/s", "d2h_bytes_per_step": d2h, "ms_per_step": ems,
-                "steps": args.e2e_steps}
+                "steps": args.e2e_steps, "morsel_rows": morsel}
 
     if host_cols is not None:
         # (1) the columns are read IN PLACE from pinned host memory (SR_MEM_HOST_PINNED): the streaming pass pulls its
@@ -459,6 +471,26 @@ def run_gpu(args):
         full = run_e2e(abi.MEM_HOST)
         full["h2d_bytes_per_step"] = n * ALGO_BYTES_PER_ROW * world
         e2e["staged_copy"] = full
+        # (3) the C++ OPERATOR path: DOP pipeline drivers on host threads pull 4096-row chunks and push them into
+        #     GpuFragmentSinkOperators sharing one fragment (page-locked double-buffered batches, no blocking call)
+        op_bin = os.path.join(ROOT, "starrocks_b200", "host", "bench", "operator_e2e_bench")
+        if rank == 0 and world == 1 and not args.no_operator_e2e and os.path.exists(op_bin):
+            eff, _ = host_cores()
+            dop = max(1, min(8, eff))
+            try:
+                # frees nothing of ours: the binary creates its own context next to this process's (HBM has room for both)
+                r = subprocess.run([op_bin, str(n), str(dop)], capture_output=True, text=True, timeout=600)
+                line = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else None
+                e2e["operator_api"] = ({"value": line["rows_per_s"], "unit": "rows/s", "seconds": line["seconds"], "dop": line["dop"],
+                                        "matches_row_at_a_time_evaluation": line["matches_row_at_a_time_evaluation"],
+                                        "fragment_batches": line["fragment_batches"], "h2d_bytes_offered": line["h2d_bytes_offered"],
+                                        "d2h_bytes": line["d2h_bytes"], "append_chunk_cpu_seconds_all_threads": line["append_chunk_cpu_seconds_all_threads"],
+                                        "need_input_false_polls": line["need_input_false_polls"], "path": line["path"],
+                                        "note": "own synthetic SSB-shaped data (same distributions), generated outside the timed region; the timed region holds "
+                                                "the 4096-row chunk materialisation of the source, the copies into pinned batches, PCIe and the result D2H"}
+                                       if line else {"value": None, "error": (r.stderr or r.stdout)[-300:]})
+            except Exception as ex:  # noqa: BLE001
+                e2e["operator_api"] = {"value": None, "error": str(ex)}
 
     # ---- CPU baseline + parity on rank 0 (N = 1 only): the oracle on a bounded sample of the same rows ----
     cpu = None

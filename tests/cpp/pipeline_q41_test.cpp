@@ -343,6 +343,7 @@ int main(int argc, char** argv) {
                 PipelineDriver build_driver({build_ops[k].first, build_ops[k].second});
                 run_to_finish(build_driver, &state, dims[k].name);
                 build_driver.close(&state);
+                printf("    %s | %s\n", build_ops[k].second->runtime_profile()->name().c_str(), build_ops[k].second->unique_metrics()->to_string().c_str());
             }
         };
         if (!with_rf) run_builds();
