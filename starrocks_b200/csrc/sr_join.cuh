@@ -292,6 +292,10 @@ __global__ void __launch_bounds__(PROBE_BLOCK) k_probe_count(JoinDev j, KeyCols 
     }
 }
 
+// (Measured and rejected, round 2: ONE kernel for unique build keys -- lookup, block ranking, a decoupled look-back over
+// per-tile status words for the global offset, ordered pair write; no heads[] round trip, no separate scan.  200 M probe
+// rows, 20 % match: 4.37 ms against 1.87 ms for the two passes below -- with four rows per thread a tile is too little
+// work to hide the serial look-back chain of 195 K tiles.)
 // pass 2: write (probe_index, build_index) pairs in probe order
 __global__ void __launch_bounds__(PROBE_BLOCK) k_probe_write(JoinDev j, int32_t join_type, int64_t n, const uint32_t* __restrict__ heads,
                                                               const uint64_t* __restrict__ block_offsets, uint32_t* __restrict__ probe_index,
@@ -332,96 +336,6 @@ __global__ void __launch_bounds__(PROBE_BLOCK) k_probe_write(JoinDev j, int32_t 
             o++;
             b = j.has_dup ? __ldg(j.next + b) : 0u;
         }
-    }
-}
-
-// Single-pass probe for build sides WITHOUT duplicate keys (every probe row yields at most one output row, so n entries
-// bound the output): lookup, block-local ranking and the global offset -- a decoupled look-back over per-tile status
-// words (aggregate / inclusive prefix, tiles taken in ticket order so that a tile only ever waits for tiles that are
-// already running) -- and the ordered pair write happen in ONE kernel: the heads[] round trip through HBM (8 bytes per probe
-// row) and the separate scan of the two-pass form are gone.  status[tile] = flag << 62 | value; flag 1 = the tile's own
-// count, 2 = inclusive prefix.  The grand total lands in *total.
-__global__ void __launch_bounds__(PROBE_BLOCK) k_probe_fused(JoinDev j, KeyCols kc, int32_t join_type, int64_t n, int32_t vec_keys, unsigned long long* __restrict__ status,
-                                                              uint32_t* __restrict__ ticket, uint32_t* __restrict__ probe_index, uint32_t* __restrict__ build_index,
-                                                              unsigned long long* __restrict__ total) {
-    __shared__ uint32_t s_scan[PROBE_BLOCK / 32 + 1];
-    __shared__ uint32_t s_tile;
-    __shared__ unsigned long long s_base;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const int64_t base = ((int64_t)tile * PROBE_BLOCK + threadIdx.x) * PROBE_ROWS;
-    int64_t key[PROBE_ROWS];
-    uint32_t live = 0; // bit r: row exists and its key is not NULL
-    const bool full = base + PROBE_ROWS <= n;
-    if (vec_keys && full) {
-        const int4 v = ldg_stream_v4((const int32_t*)kc.c[0].data + base);
-        key[0] = v.x, key[1] = v.y, key[2] = v.z, key[3] = v.w;
-        live = (1u << PROBE_ROWS) - 1;
-    } else {
-#pragma unroll
-        for (int r = 0; r < PROBE_ROWS; r++) {
-            key[r] = 0;
-            if (base + r < n && !pack_key(kc, base + r, key[r])) live |= 1u << r;
-        }
-    }
-    uint32_t head[PROBE_ROWS];
-    if (j.method == SR_JOIN_METHOD_LINEAR_CHAINED) {
-#pragma unroll
-        for (int r = 0; r < PROBE_ROWS; r++) head[r] = (live >> r) & 1u ? join_lookup(j, key[r]) : 0u;
-    } else {
-        uint32_t word[PROBE_ROWS];
-#pragma unroll
-        for (int r = 0; r < PROBE_ROWS; r++) {
-            const bool in = ((live >> r) & 1u) && key[r] >= j.min_value && key[r] <= j.max_value;
-            if (!in) live &= ~(1u << r);
-            word[r] = in ? __ldg(j.bitmap + ((uint64_t)(key[r] - j.min_value) >> 5)) : 0u;
-        }
-#pragma unroll
-        for (int r = 0; r < PROBE_ROWS; r++) {
-            const uint64_t off = (uint64_t)(key[r] - j.min_value);
-            head[r] = (((live >> r) & 1u) && ((word[r] >> (off & 31)) & 1u)) ? __ldg(j.first + off) : 0u;
-        }
-    }
-    uint32_t emit = 0, mine = 0; // bit r: row r produces its (single) output row
-#pragma unroll
-    for (int r = 0; r < PROBE_ROWS; r++) {
-        if (base + r < n && probe_row_count(j, join_type, head[r])) {
-            emit |= 1u << r;
-            mine++;
-        }
-    }
-    uint32_t tot;
-    const uint32_t ex = block_excl_scan<PROBE_BLOCK>(mine, s_scan, &tot);
-    if (threadIdx.x == 0) {
-        unsigned long long excl = 0;
-        if (tile > 0) {
-            // publish the tile's own count, then walk back until an inclusive prefix is found
-            atomicExch(status + tile, (1ull << 62) | (unsigned long long)tot);
-            for (int64_t p = (int64_t)tile - 1; p >= 0; p--) {
-                unsigned long long st;
-                do {
-                    st = *(volatile unsigned long long*)(status + p);
-                } while ((st >> 62) == 0);
-                excl += st & ((1ull << 62) - 1);
-                if ((st >> 62) == 2) break;
-            }
-        }
-        __threadfence();
-        atomicExch(status + tile, (2ull << 62) | (excl + tot));
-        s_base = excl;
-        if ((int64_t)(tile + 1) * PROBE_TILE >= n) *total = excl + tot; // the last tile
-    }
-    __syncthreads();
-    if (mine == 0) return;
-    uint64_t o = s_base + ex;
-    const bool no_build = join_type == SR_JOIN_LEFT_SEMI || join_type == SR_JOIN_LEFT_ANTI;
-#pragma unroll
-    for (int r = 0; r < PROBE_ROWS; r++) {
-        if (!((emit >> r) & 1u)) continue;
-        probe_index[o] = (uint32_t)(base + r);
-        build_index[o] = no_build ? 0u : head[r];
-        o++;
     }
 }
 
@@ -744,22 +658,7 @@ static int32_t join_probe(sr_join* j, int32_t prober_id, const sr_chunk_view* pr
                                      ? 1
                                      : 0;
     int64_t total = 0;
-    const bool single_pass = n > 0 && !j->has_dup && !getenv("SR_JOIN_TWO_PASS_PROBE");
-    if (single_pass) {
-        // unique build keys: at most one output row per probe row, so n entries bound the index pairs and the probe is
-        // one kernel (k_probe_fused); the only synchronisation left is the read-back of the row count the caller needs
-        SR_TRY(ps.probe_index.reserve(ctx, sizeof(uint32_t) * (size_t)n));
-        SR_TRY(ps.build_index.reserve(ctx, sizeof(uint32_t) * (size_t)n));
-        SR_TRY(ps.block_offsets.reserve(ctx, sizeof(uint64_t) * ((size_t)blocks + 2)));
-        SR_CUDA(ctx, cudaMemsetAsync(ps.block_offsets.p, 0, sizeof(uint64_t) * ((size_t)blocks + 2), ctx->stream));
-        unsigned long long* status = ps.block_offsets.as<unsigned long long>();
-        srd::k_probe_fused<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, kc, j->desc.join_type, n, vec_keys, status, (uint32_t*)(status + blocks),
-                                                                        ps.probe_index.as<uint32_t>(), ps.build_index.as<uint32_t>(), status + blocks + 1);
-        SR_LAUNCH_CHECK(ctx);
-        SR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, status + blocks + 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        total = (int64_t)ctx->pinned[0];
-    } else if (n > 0) {
+    if (n > 0) {
         SR_TRY(ps.heads.reserve(ctx, sizeof(uint32_t) * (size_t)n));
         SR_TRY(ps.block_counts.reserve(ctx, sizeof(uint32_t) * (size_t)blocks));
         SR_TRY(ps.block_offsets.reserve(ctx, sizeof(uint64_t) * (size_t)blocks));
@@ -772,11 +671,9 @@ static int32_t join_probe(sr_join* j, int32_t prober_id, const sr_chunk_view* pr
         total = (int64_t)ctx->pinned[0];
     }
     if (total >= 0xFFFFFFF0ll) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "join output of more than 2^32 rows in one batch; probe in smaller batches");
-    if (!single_pass) {
-        SR_TRY(ps.probe_index.reserve(ctx, sizeof(uint32_t) * (size_t)std::max<int64_t>(total, 1)));
-        SR_TRY(ps.build_index.reserve(ctx, sizeof(uint32_t) * (size_t)std::max<int64_t>(total, 1)));
-    }
-    if (total > 0 && !single_pass) {
+    SR_TRY(ps.probe_index.reserve(ctx, sizeof(uint32_t) * (size_t)std::max<int64_t>(total, 1)));
+    SR_TRY(ps.build_index.reserve(ctx, sizeof(uint32_t) * (size_t)std::max<int64_t>(total, 1)));
+    if (total > 0) {
         srd::k_probe_write<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, j->desc.join_type, n, ps.heads.as<uint32_t>(),
                                                                         ps.block_offsets.as<uint64_t>(), ps.probe_index.as<uint32_t>(),
                                                                         ps.build_index.as<uint32_t>());
