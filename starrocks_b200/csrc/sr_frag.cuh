@@ -483,7 +483,16 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
             const VDesc& d = vt.v[pass.tests[t].value_id];
             if (d.nulls != nullptr || (t < pass.num_vec && (((uintptr_t)d.data) & 15) != 0)) tests = false;
         }
-        if (tests) {
+        static const bool use_tma = getenv("SR_FRAG_STREAM_TMA") != nullptr; // experiment: TMA-staged vector columns
+        if (tests && use_tma && !pass.host_input) {
+            const uint32_t bitmap_bytes = (uint32_t)((f->stream_smem + 127) / 128 * 128);
+            const size_t sm = bitmap_bytes + srd::STREAM_TMA_SMEM;
+            SR_CUDA(ctx, cudaFuncSetAttribute(srd::k_frag_stream_tests_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            int per_sm = 1;
+            SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, srd::k_frag_stream_tests_tma<false>, srd::STREAM_BLOCK, sm));
+            const int tgrid = (int)std::min<int64_t>((int64_t)std::max(per_sm, 1) * ctx->num_sms, (n + srd::STREAM_TILE - 1) / srd::STREAM_TILE);
+            srd::k_frag_stream_tests_tma<false><<<tgrid, srd::STREAM_BLOCK, sm, ctx->stream>>>(fdev, pass, vt, n, bitmap_bytes, f->sel[0].as<srd::SelEntry>(), cnt);
+        } else if (tests) {
             if (carry)
                 srd::k_frag_stream_tests<true><<<sgrid, srd::STREAM_BLOCK, f->stream_smem, ctx->stream>>>(fdev, pass, vt, n, f->sel[0].as<srd::SelEntry>(), cnt);
             else
