@@ -237,7 +237,7 @@ constexpr int PROBE_TILE = PROBE_BLOCK * PROBE_ROWS;
 // first[], L1/L2 resident) first, so only matching rows gather from first[].
 __global__ void __launch_bounds__(PROBE_BLOCK) k_probe_count(JoinDev j, KeyCols kc, int32_t join_type, int64_t n, int32_t vec_keys, uint32_t* __restrict__ heads,
                                                               uint32_t* __restrict__ block_counts) {
-    __shared__ uint32_t s_cnt[PROBE_BLOCK / 32];
+    __shared__ unsigned long long s_cnt[PROBE_BLOCK / 32];
     const int64_t base = ((int64_t)blockIdx.x * PROBE_BLOCK + threadIdx.x) * PROBE_ROWS;
     int64_t key[PROBE_ROWS];
     uint32_t live = 0; // bit r: row exists and its key is not NULL
@@ -271,7 +271,10 @@ __global__ void __launch_bounds__(PROBE_BLOCK) k_probe_count(JoinDev j, KeyCols 
             head[r] = (((live >> r) & 1u) && ((word[r] >> (off & 31)) & 1u)) ? __ldg(j.first + off) : 0u;
         }
     }
-    uint32_t cnt = 0;
+    // 64-bit while summing: a chain may be as long as the build side, a block's total is stored saturated (the host
+    // refuses outputs of >= 2^32 - 16 rows per batch, so a saturated block makes the whole probe fail loudly instead of
+    // wrapping and under-sizing the index buffers)
+    unsigned long long cnt = 0;
 #pragma unroll
     for (int r = 0; r < PROBE_ROWS; r++)
         if (base + r < n) cnt += probe_row_count(j, join_type, head[r]);
@@ -286,9 +289,9 @@ __global__ void __launch_bounds__(PROBE_BLOCK) k_probe_count(JoinDev j, KeyCols 
     if (lane_id() == 0) s_cnt[threadIdx.x >> 5] = cnt;
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t t = 0;
+        unsigned long long t = 0;
         for (int w = 0; w < PROBE_BLOCK / 32; w++) t += s_cnt[w];
-        block_counts[blockIdx.x] = t;
+        block_counts[blockIdx.x] = t > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)t;
     }
 }
 
@@ -600,6 +603,7 @@ static int32_t join_finish(sr_join* j) {
     const int64_t rows = j->rows;
     if (hd && rows > 0) {
         // duplicate build keys: put every chain into the reference's order (descending build index)
+        if (rows > 0x7FFFFFFFll) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "join build side of %lld rows with duplicate keys (the chain relink sorts int-indexed items)", (long long)rows);
         const uint64_t nb = (uint64_t)j->bucket_size;
         if (nb >= 0xFFFFFFFFull) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "join table of %llu buckets with duplicate keys", (unsigned long long)nb);
         const uint32_t invalid = (uint32_t)nb; // sorts after every real bucket
