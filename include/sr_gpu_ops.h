@@ -406,7 +406,14 @@ typedef enum sr_agg_fn_kind {
     SR_AGG_MAX = 6,
     /* merge phase of AVG over (sum, count) state columns: `input` = the DOUBLE sum state, `reserved` = slot id of the
      * BIGINT count state (see sr_agg_two_phase_descs); result = total sum / total count, NULL when the count is 0 */
-    SR_AGG_AVG_MERGE = 7
+    SR_AGG_AVG_MERGE = 7,
+    /* COUNT(DISTINCT col): `input` must be a single column reference of an integer-class type (<= 8 bytes; group keys +
+     * value + null flags <= 16 bytes).  Reference: DistinctAggregateFunction / multi_distinct_count,
+     * be/src/exprs/agg/distinct.h:48-300 -- a hash set per group state.  Here ONE second-level hash set keyed
+     * (group keys, value) for the whole operator, folded into the group states at sink_finish.  NULL values are not
+     * counted; the result is BIGINT, never NULL.  Single-phase only (sr_agg_merge / *_states / two_phase_descs and
+     * the fused fragment answer SR_ERR_NOT_SUPPORTED: shuffle on the distinct column's group instead). */
+    SR_AGG_COUNT_DISTINCT = 8
 } sr_agg_fn_kind;
 
 typedef struct sr_agg_fn {

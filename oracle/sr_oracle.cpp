@@ -14,6 +14,7 @@
 #include <memory>
 #include <string>
 #include <thread>
+#include <unordered_set>
 #include <vector>
 
 typedef __int128 i128;
@@ -1292,6 +1293,9 @@ struct orc_agg {
     // state arena in insertion order (aggregator.cpp:57-87,1718-1724)
     std::vector<Key128> group_keys;
     std::vector<FnState> states; // group * num_fns + f
+    // COUNT(DISTINCT) states: DistinctAggregateState<LT>::set (distinct.h:51-62), one hash set per (group, function)
+    std::vector<std::unordered_set<int64_t>> dsets; // group * num_fns + f; sized only when the desc has such a function
+    bool has_distinct = false;
     int64_t num_groups = 0;
 };
 
@@ -1308,6 +1312,7 @@ static int32_t agg_result_type(const sr_agg_fn& f) {
     switch (f.kind) {
     case SR_AGG_COUNT:
     case SR_AGG_COUNT_STAR:
+    case SR_AGG_COUNT_DISTINCT: // TDistinctAggregateFunction<..., AggDistinctType::COUNT>::finalize_to_column (distinct.h:590-594)
         return SR_TYPE_BIGINT;
     case SR_AGG_AVG:
     case SR_AGG_AVG_MERGE:
@@ -1354,6 +1359,7 @@ extern "C" orc_agg* orc_agg_create(const sr_agg_desc* desc) {
             fail(SR_ERR_NOT_SUPPORTED, "avg on decimal/largeint");
             return nullptr;
         }
+        if (fn.kind == SR_AGG_COUNT_DISTINCT) a->has_distinct = true;
     }
     a->slot_key.assign(1024, Key128());
     a->slot_group.assign(1024, -1);
@@ -1362,6 +1368,7 @@ extern "C" orc_agg* orc_agg_create(const sr_agg_desc* desc) {
         a->num_groups = 1;
         a->group_keys.push_back(Key128());
         a->states.resize(std::max(1, desc->num_fns));
+        if (a->has_distinct) a->dsets.resize(a->states.size());
     }
     return a;
 }
@@ -1398,6 +1405,7 @@ static inline int32_t agg_find_or_insert(orc_agg* a, const Key128& k) {
     a->slot_key[s] = k;
     a->group_keys.push_back(k);
     a->states.resize((size_t)a->num_groups * std::max(1, a->desc.num_fns));
+    if (a->has_distinct) a->dsets.resize(a->states.size());
     if ((uint64_t)a->num_groups * 2 > a->cap_mask) agg_grow(a);
     return g;
 }
@@ -1530,6 +1538,15 @@ static int32_t agg_push_range(orc_agg* a, const sr_chunk_view* c, int64_t r0, in
             }
             continue;
         }
+        if (fn.kind == SR_AGG_COUNT_DISTINCT) { // TDistinctAggregateFunction::update -> set.insert(key) (distinct.h:56,417-424)
+            if (v.is_double) return fail(SR_ERR_NOT_SUPPORTED, "COUNT(DISTINCT) on a floating type");
+            for (int64_t i = 0; i < n; i++) {
+                if (v.nul[i]) continue;
+                a->dsets[(size_t)gidx[i] * nf + f].insert(v.iv[i]);
+                a->states[(size_t)gidx[i] * nf + f].has = true;
+            }
+            continue;
+        }
         for (int64_t i = 0; i < n; i++) {
             if (v.nul[i]) continue; // NullableAggregateFunction skips NULL inputs
             FnState& s = a->states[(size_t)gidx[i] * nf + f];
@@ -1604,6 +1621,8 @@ extern "C" int32_t orc_agg_output(orc_agg* a, void** out_data, uint8_t** out_nul
             bool nul = false;
             if (fn.kind == SR_AGG_COUNT || fn.kind == SR_AGG_COUNT_STAR) {
                 ((int64_t*)out_data[col])[g] = s.count;
+            } else if (fn.kind == SR_AGG_COUNT_DISTINCT) { // distinct_count() = set.size() (distinct.h:62,593)
+                ((int64_t*)out_data[col])[g] = (int64_t)a->dsets[(size_t)g * nf + f].size();
             } else if (fn.kind == SR_AGG_AVG || fn.kind == SR_AGG_AVG_MERGE) {
                 nul = !s.has || s.count == 0;
                 ((double*)out_data[col])[g] = nul ? 0.0 : s.dsum / (double)s.count; // avg.h:218-236
@@ -1675,6 +1694,12 @@ extern "C" int32_t orc_agg_merge(orc_agg* a, const orc_agg* o) {
             FnState& r = a->states[(size_t)t * nf + f];
             if (!s.has) continue;
             const sr_agg_fn& fn = d.fns[f];
+            if (fn.kind == SR_AGG_COUNT_DISTINCT) { // merge = insert the other state's keys (distinct.h:64-75 deserialize_and_merge)
+                const auto& os = o->dsets[(size_t)g * nf + f];
+                a->dsets[(size_t)t * nf + f].insert(os.begin(), os.end());
+                r.has = true;
+                continue;
+            }
             const bool dbl = is_float_class(fn.input_type);
             switch (fn.kind) {
             case SR_AGG_SUM:

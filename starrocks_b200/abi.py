@@ -53,7 +53,7 @@ EX_EQ, EX_NE, EX_LT, EX_LE, EX_GT, EX_GE, EX_AND, EX_OR, EX_NOT, EX_IS_NULL, EX_
 JOIN_INNER, JOIN_LEFT_OUTER, JOIN_LEFT_SEMI, JOIN_LEFT_ANTI = 0, 1, 2, 3
 JOIN_METHOD_NONE, JOIN_METHOD_DIRECT_MAPPING, JOIN_METHOD_RANGE_DIRECT_MAPPING, JOIN_METHOD_LINEAR_CHAINED = 0, 1, 2, 3
 
-AGG_SUM, AGG_COUNT, AGG_COUNT_STAR, AGG_AVG, AGG_MIN, AGG_MAX, AGG_AVG_MERGE = 1, 2, 3, 4, 5, 6, 7
+AGG_SUM, AGG_COUNT, AGG_COUNT_STAR, AGG_AVG, AGG_MIN, AGG_MAX, AGG_AVG_MERGE, AGG_COUNT_DISTINCT = 1, 2, 3, 4, 5, 6, 7, 8
 
 HASH_FNV, HASH_CRC32, HASH_XXH3 = 0, 1, 2
 REDUCE_MULHI, REDUCE_MODULO = 0, 1
@@ -383,6 +383,8 @@ def two_phase_descs(desc):
         m.out_slot = fn.out_slot
         if fn.kind == AGG_AVG_MERGE:
             raise ValueError("already a merge phase")
+        if fn.kind == AGG_COUNT_DISTINCT:
+            raise NotImplementedError("COUNT(DISTINCT) is single-phase: shuffle on the group keys")
         if fn.kind not in (AGG_COUNT, AGG_COUNT_STAR, AGG_AVG) and TYPE_WIDTH[agg_result_type(fn.kind, fn.input_type)] > 8:
             raise NotImplementedError("128-bit states")
         if n1 + (2 if fn.kind == AGG_AVG else 1) > SR_MAX_AGG_FNS:
@@ -417,7 +419,7 @@ def two_phase_descs(desc):
 
 def agg_result_type(kind, input_type):
     """SumResultLT / AvgResultLT (be/src/exprs/agg/sum.h:24-34, avg.h:27-47)."""
-    if kind in (AGG_COUNT, AGG_COUNT_STAR):
+    if kind in (AGG_COUNT, AGG_COUNT_STAR, AGG_COUNT_DISTINCT):
         return TYPE_BIGINT
     if kind in (AGG_AVG, AGG_AVG_MERGE):
         return TYPE_DOUBLE

@@ -749,6 +749,45 @@ __global__ void __launch_bounds__(EMIT_BLOCK) k_agg_count(const AggDev* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// COUNT(DISTINCT): fold the second-level set keyed (group keys, value) into the group states
+// ---------------------------------------------------------------------------------------
+// One occupied slot of the set = one distinct (group, value) pair.  The loader hands the PARENT's group-by values back
+// out of the set's packed key (the set's first keys are the parent's keys, in order), so the parent's own slot lookup --
+// dense index, hash probe or the single state -- finds the group.
+struct DistinctKeyLoader {
+    const AggDev& p;
+    const AggDev& c;
+    HKey key;
+    __device__ __forceinline__ bool load(int id, int64_t& bits) const {
+        bits = 0;
+        for (int k = 0; k < p.num_keys; k++) {
+            if (p.key_value_id[k] != id) continue;
+            const int w = c.key_width[k];
+            const unsigned long long m = w == 8 ? ~0ull : ((1ull << (8 * w)) - 1);
+            const unsigned long long raw = hkey_bits(key, c.key_shift[k]) & m;
+            long long v = (long long)raw;
+            if (w < 8 && c.key_type[k] != SR_TYPE_BOOLEAN) v = (long long)(raw << (64 - 8 * w)) >> (64 - 8 * w);
+            bits = v;
+            return c.key_nullable[k] && (hkey_bits(key, c.null_shift + k) & 1ull);
+        }
+        return false;
+    }
+};
+
+__global__ void __launch_bounds__(256) k_agg_distinct_fold(const AggDev* __restrict__ cd, const AggDev* __restrict__ pd, int32_t f) {
+    const AggDev& c = *cd;
+    const AggDev& p = *pd;
+    const int vk = c.num_keys - 1; // the value column is the set's last key
+    for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s <= c.cap; s += (unsigned long long)gridDim.x * blockDim.x) {
+        if (c.cnt_star[s] == 0) continue;
+        DistinctKeyLoader ld{p, c, s == c.cap ? HKey{SR_AGG_EMPTY, SR_AGG_EMPTY} : hkey_load(c, s)};
+        if (c.key_nullable[vk] && (hkey_bits(ld.key, c.null_shift + vk) & 1ull)) continue; // COUNT(DISTINCT) skips NULL
+        const long long slot = agg_find_slot(p, ld);
+        if (slot >= 0) atomicAdd((unsigned long long*)p.fns[f].acc0 + slot, 1ull);
+    }
+}
+
 struct EmitCol {
     void* data;
     uint8_t* nulls;
@@ -940,12 +979,21 @@ struct sr_agg {
     int32_t out_types[SR_MAX_GROUP_KEYS + SR_MAX_AGG_FNS];
     bool out_has_nulls[SR_MAX_GROUP_KEYS + SR_MAX_AGG_FNS];
     std::vector<DevBuf> conv_bufs; // sr_agg_convert_to_states: (data, nulls) per function
+    // COUNT(DISTINCT) functions: one (group keys, value) set each -- an aggregate of its own with no functions, fed the
+    // same chunks; agg_finish_output folds it into acc0 of the function (which until then holds COUNT(value))
+    sr_agg* distinct[SR_MAX_AGG_FNS] = {};
+    bool has_distinct = false;
+    bool distinct_folded = false;
+    ~sr_agg() {
+        for (sr_agg* c : distinct) delete c;
+    }
 };
 
 static int32_t agg_result_type(const sr_agg_fn& f) {
     switch (f.kind) {
     case SR_AGG_COUNT:
     case SR_AGG_COUNT_STAR:
+    case SR_AGG_COUNT_DISTINCT:
         return SR_TYPE_BIGINT;
     case SR_AGG_AVG:
     case SR_AGG_AVG_MERGE:
@@ -969,7 +1017,14 @@ static int32_t agg_validate_desc(sr_ctx* ctx, const sr_agg_desc* d) {
     }
     for (int f = 0; f < d->num_fns; f++) {
         const sr_agg_fn& fn = d->fns[f];
-        if (fn.kind < SR_AGG_SUM || fn.kind > SR_AGG_AVG_MERGE) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "aggregate kind %d", fn.kind);
+        if (fn.kind < SR_AGG_SUM || fn.kind > SR_AGG_COUNT_DISTINCT) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "aggregate kind %d", fn.kind);
+        if (fn.kind == SR_AGG_COUNT_DISTINCT) {
+            if (fn.input.num_nodes != 1 || fn.input.nodes[0].op != SR_EX_COL)
+                return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "COUNT(DISTINCT) takes a column reference (fn %d)", f);
+            if (srd::type_width(fn.input_type) > 8 || srd::is_float_class(fn.input_type))
+                return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "COUNT(DISTINCT) on type %d (fn %d)", fn.input_type, f);
+            if (d->num_group_keys + 1 > SR_MAX_GROUP_KEYS) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "COUNT(DISTINCT) with %d group keys", d->num_group_keys);
+        }
         if (fn.kind != SR_AGG_COUNT_STAR && srd::type_width(fn.input_type) == 0) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "aggregate input type %d", fn.input_type);
         if (fn.kind == SR_AGG_AVG && (srd::is_decimal(fn.input_type) || srd::type_width(fn.input_type) > 8))
             return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "AVG on decimal / largeint");
@@ -1136,6 +1191,7 @@ static int32_t agg_compile(sr_agg* a, slot_type_fn tf, agg_nullable_fn nf, void*
         const bool dbl = fd.in_is_double != 0;
         switch (fn.kind) {
         case SR_AGG_COUNT:
+        case SR_AGG_COUNT_DISTINCT: // COUNT(value) while rows arrive; replaced by the folded set at sink_finish
             fd.mode = srd::M_COUNT;
             fd.track_n = 0;
             break;
@@ -1231,6 +1287,26 @@ static int32_t agg_compile(sr_agg* a, slot_type_fn tf, agg_nullable_fn nf, void*
     }
     SR_TRY(agg_upload(a));
     a->compiled = true;
+    // COUNT(DISTINCT value): the (group keys, value) set, an aggregate without functions over the same input
+    for (int f = 0; f < d.num_fns; f++) {
+        if (d.fns[f].kind != SR_AGG_COUNT_DISTINCT) continue;
+        a->has_distinct = true;
+        if (a->distinct[f]) continue; // recompiled after a reset: the set keeps its tables
+        sr_agg* c = new sr_agg();
+        a->distinct[f] = c;
+        c->ctx = ctx;
+        memset(&c->desc, 0, sizeof(c->desc));
+        c->desc.num_group_keys = d.num_group_keys + 1;
+        for (int k = 0; k < d.num_group_keys; k++) {
+            c->desc.group_slots[k] = d.group_slots[k];
+            c->desc.group_types[k] = d.group_types[k];
+            c->desc.group_nullable[k] = d.group_nullable[k];
+        }
+        c->desc.group_slots[d.num_group_keys] = d.fns[f].input.nodes[0].slot_id;
+        c->desc.group_types[d.num_group_keys] = d.fns[f].input_type;
+        c->desc.expected_groups = d.expected_groups;
+        SR_TRY(agg_compile(c, tf, nf, user));
+    }
     return SR_OK;
 }
 
@@ -1394,6 +1470,19 @@ static int32_t agg_finish_output(sr_agg* a) {
     }
     const srd::AggDev& h = a->host;
     const uint64_t total = (!h.dense && h.num_keys > 0) ? h.cap + 1 : h.cap;
+    if (a->has_distinct && !a->distinct_folded) {
+        for (int f = 0; f < d.num_fns; f++) {
+            sr_agg* c = a->distinct[f];
+            if (!c) continue;
+            // acc0 held COUNT(value) so far (the state every push path maintains); from here on the distinct count
+            SR_CUDA(ctx, cudaMemsetAsync(h.fns[f].acc0, 0, sizeof(int64_t) * total, ctx->stream));
+            if (!c->compiled) continue;
+            srd::k_agg_distinct_fold<<<std::min(grid_for((int64_t)c->host.cap + 1, 256), ctx->num_sms * 16), 256, 0, ctx->stream>>>(
+                    (const srd::AggDev*)c->dev.p, (const srd::AggDev*)a->dev.p, f);
+            SR_LAUNCH_CHECK(ctx);
+        }
+        a->distinct_folded = true;
+    }
     const int blocks = grid_for((int64_t)total, srd::EMIT_BLOCK);
     SR_TRY(a->block_counts.reserve(ctx, sizeof(uint32_t) * (size_t)blocks));
     SR_TRY(a->block_offsets.reserve(ctx, sizeof(uint64_t) * (size_t)blocks));

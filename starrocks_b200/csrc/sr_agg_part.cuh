@@ -75,7 +75,17 @@ struct ScatterArgs {
     unsigned long long ovf_cap;
     int32_t fan_bits;                    // log2 of this level's fan-out
     int32_t local_shift;                 // local bucket = (bucket >> local_shift) & (fan - 1)
+    int32_t l2_prefetch;                 // request the CTA's NEXT tile into L2 while this one is ranked and copied out
+    int32_t pad;
 };
+
+// ask L2 for the 128-byte lines of [p, p + bytes): one line per thread and step (sequential input only -- a prefetch
+// fetches whole lines)
+__device__ __forceinline__ void aggp_prefetch_l2(const void* p, size_t bytes, int tid, int nthreads) {
+    const char* c = (const char*)((uintptr_t)p & ~(uintptr_t)127);
+    const size_t lines = (((uintptr_t)p & 127) + bytes + 127) >> 7;
+    for (size_t i = (size_t)tid; i < lines; i += (size_t)nthreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + (i << 7)));
+}
 
 // general plans: build the record of `row` straight into shared memory (one out-of-line copy of the key packing and of the
 // expression interpreter for all record widths); returns the row's bucket, or 0xFFFFFFFF when the packed key equals the
@@ -170,10 +180,9 @@ __global__ void __launch_bounds__(AGGP_BLOCK, 1024 / AGGP_BLOCK) k_aggp_scatter(
     const uint32_t fmask = (uint32_t)F - 1;
     for (int i = tid; i < F; i += AGGP_BLOCK) s_hist[i] = 0;
     const int64_t ntiles = FROM_CHUNK ? (sa.n + T - 1) / T : (int64_t)sa.tile_start[1 << (pl.bits - pl.bits2)];
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int64_t row0;        // first row / record of the tile
-        int tile_n;
-        uint32_t cbase = 0;  // destination bucket of local bucket 0
+    // first row / record of a tile, its length, and the destination bucket of its local bucket 0
+    auto locate = [&](int64_t tile, int64_t& row0, int& tile_n, uint32_t& cbase) {
+        cbase = 0;
         if (FROM_CHUNK) {
             row0 = tile * T;
             tile_n = (int)(sa.n - row0 < T ? sa.n - row0 : T);
@@ -190,6 +199,30 @@ __global__ void __launch_bounds__(AGGP_BLOCK, 1024 / AGGP_BLOCK) k_aggp_scatter(
             row0 = (int64_t)((unsigned long long)lo * pl.cap1) + off;
             tile_n = (int)((int64_t)cnt - off < T ? (int64_t)cnt - off : T);
             cbase = (uint32_t)lo << pl.bits2;
+        }
+    };
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int64_t row0;
+        int tile_n;
+        uint32_t cbase;
+        locate(tile, row0, tile_n, cbase);
+        if (sa.l2_prefetch && MODE != SCATTER_CHUNK && tile + gridDim.x < ntiles) {
+            // the tile's loads are one DRAM round trip per batch of rows with nothing else in flight (ncu: 42 % of the
+            // level-1 kernel's stall samples sit on the first use of the loaded words); the next tile's lines are
+            // requested now and arrive in L2 while this tile is ranked, scanned and copied out
+            int64_t nrow0;
+            int ntile_n;
+            uint32_t ncbase;
+            locate(tile + gridDim.x, nrow0, ntile_n, ncbase);
+            if (MODE == SCATTER_CHUNK_SIMPLE) {
+#pragma unroll
+                for (int w = 0; w < W; w++) {
+                    const int wb = pl.word_w8[w] ? 8 : 4;
+                    aggp_prefetch_l2((const char*)pl.word_ptr[w] + (size_t)(sa.row_base + nrow0) * wb, (size_t)ntile_n * wb, tid, AGGP_BLOCK);
+                }
+            } else {
+                aggp_prefetch_l2(sa.src + (size_t)nrow0 * W, (size_t)ntile_n * W * 8, tid, AGGP_BLOCK);
+            }
         }
         __syncthreads(); // s_hist is clear (initial clear, or the scan of the previous tile); s_rec / s_perm are free
         uint32_t lr[R];  // bucket << 16 | rank inside (warp, bucket); 0xFFFFFFFF: no record
@@ -372,6 +405,8 @@ struct ApplyArgs {
     int32_t fresh; // the table holds no group yet: slices are initialised in shared memory instead of loaded
     uint32_t* fail_list;            // buckets with a slice that filled up (their records are re-applied by k_aggp_apply_l2)
     unsigned long long* fail_count;
+    int32_t l2_prefetch;            // request the CTA's next bucket into L2 while this one is applied
+    int32_t pad;
 };
 
 struct ApplyFn {
@@ -446,6 +481,11 @@ __global__ void __launch_bounds__(AGGP_APPLY_BLOCK, 4) k_aggp_apply(const AggDev
         const unsigned long long* const brec = aa.rec + (unsigned long long)b * pl.cap2 * W;
         const size_t g0 = (size_t)b * S;
         if (tid == 0) s_fail = 0;
+        if (aa.l2_prefetch && b + gridDim.x < aa.num_buckets) {
+            const uint32_t nb = b + gridDim.x;
+            const unsigned long long nn = min((unsigned long long)aa.count[nb], pl.cap2);
+            aggp_prefetch_l2(aa.rec + (unsigned long long)nb * pl.cap2 * W, (size_t)nn * W * 8, tid, AGGP_APPLY_BLOCK);
+        }
         if (aa.fresh) {
             for (int i = tid; i < S * kw; i += AGGP_APPLY_BLOCK) s_keys[i] = SR_AGG_EMPTY;
             for (int i = tid; i < S; i += AGGP_APPLY_BLOCK) {

@@ -196,6 +196,9 @@ static int32_t agg_push_partitioned(sr_agg* a, const VTab& vt, int64_t n, bool f
         sa.ovf = a->part_ovf.as<unsigned long long>();
         sa.ovf_count = ovf_count;
         sa.ovf_cap = (unsigned long long)m;
+        static const bool no_prefetch = getenv("SR_AGG_NO_L2_PREFETCH") != nullptr; // A/B switch of the next-tile L2 prefetch
+        sa.l2_prefetch = no_prefetch ? 0 : 1;
+        sa.pad = 0;
         if (pl.bits2 == 0) {
             sa.cursor = cursor;
             sa.dst = rec_final;
@@ -235,6 +238,8 @@ static int32_t agg_push_partitioned(sr_agg* a, const VTab& vt, int64_t n, bool f
             aa.fresh = fresh ? 1 : 0;
             aa.fail_list = a->part_fail.as<uint32_t>();
             aa.fail_count = fail_count;
+            aa.l2_prefetch = sa.l2_prefetch;
+            aa.pad = 0;
             SR_CUDA(ctx, cudaFuncSetAttribute(srd::k_aggp_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem));
             int occ = 1;
             SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, srd::k_aggp_apply, srd::AGGP_APPLY_BLOCK, apply_smem));

@@ -60,6 +60,7 @@ struct sr_fragment {
     // selective mode (sr_frag_pass.cuh): streaming pass -> gather passes -> final pass
     int force_mode = 0; // 0 = choose from the sampled pass rates, 1 = fused cascade kernel, 2 = selection-vector passes
     bool selective = false;
+    bool expand = false; // some INNER join has duplicate build keys: selection-vector passes + k_frag_gather_agg_expand
     srd::PassDev pass;
     std::vector<int> gather_joins; // probe positions that get a pass of their own
     DevBuf sel[2], pass_counters;
@@ -160,7 +161,9 @@ static int32_t frag_compile(sr_fragment* f) {
         h.joins[j].smem_off = -1;
         h.joins[j].use_bitmap = jn->method != SR_JOIN_METHOD_LINEAR_CHAINED ? 1 : 0;
         h.joins[j].bitmap_words = (int32_t)((std::max<int64_t>(jn->bucket_size, 1) + 31) / 32);
-        h.joins[j].need_head = 0;
+        // one-to-many INNER join: the final pass walks the build chain of every surviving row
+        h.joins[j].expand = (jn->has_dup && jn->desc.join_type == SR_JOIN_INNER) ? 1 : 0;
+        h.joins[j].need_head = h.joins[j].expand;
         h.joins[j].idx32 = (h.joins[j].use_bitmap && jn->min_value >= INT32_MIN && jn->max_value <= INT32_MAX && jn->max_value >= jn->min_value) ? 1 : 0;
         f->order[j] = j;
     }
@@ -254,7 +257,7 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
     double total_rate = f->pred_rate;
     for (int q = 0; q < f->num_joins; q++) total_rate *= f->pass_rate[ord[q]];
     f->est_rate = total_rate;
-    f->selective = f->force_mode == 2 || (f->force_mode == 0 && total_rate < 0.25 && n >= (1 << 16));
+    f->selective = f->expand || f->force_mode == 2 || (f->force_mode == 0 && total_rate < 0.25 && n >= (1 << 16));
     if (f->selective) {
         // joins whose key column is streamed: the first one, and the second when >= 8 % of the rows reach it
         int ns = f->num_joins > 0 ? 1 : 0;
@@ -356,9 +359,9 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
         for (int q = 0; q < f->num_joins; q++) {
             srd::FragJoinDev& fj = h.joins[q];
             fj.smem_off = -1;
-            if (q < ns && fj.use_bitmap && sw + (size_t)fj.bitmap_words <= sbudget) {
+            if (q < ns && fj.use_bitmap && sw + (size_t)fj.bitmap_words + 1 <= sbudget) {
                 fj.smem_off = (int32_t)sw;
-                sw += ((size_t)fj.bitmap_words + 3) & ~(size_t)3;
+                sw += ((size_t)fj.bitmap_words + 1 + 3) & ~(size_t)3; // + one zero guard word (stream_test_reg kind 1)
             }
         }
         f->stream_smem = sw * 4;
@@ -378,7 +381,9 @@ static int32_t frag_plan(sr_fragment* f, const VTab& vt, int64_t n) {
         // gather passes: exactly one wave of resident CTAs (grid-stride loops; a partial second wave only adds a tail)
         int gj = 0, ga = 0;
         SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gj, srd::k_frag_gather_join, srd::GATHER_BLOCK, 0));
-        if (f->agg->host.num_keys == 0)
+        if (f->expand)
+            SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ga, srd::k_frag_gather_agg_expand, srd::GATHER_BLOCK, 0));
+        else if (f->agg->host.num_keys == 0)
             SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ga, srd::k_frag_gather_agg<false, true>, srd::GATHER_BLOCK, 0));
         else if (f->smem_agg)
             SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ga, srd::k_frag_gather_agg<true>, srd::GATHER_BLOCK, f->agg->smem_bytes));
@@ -517,7 +522,10 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
         if (hash) SR_TRY(f->sel[cur ^ 1].reserve(ctx, sizeof(srd::SelEntry) * ((size_t)n + slack)));
         srd::SelEntry* fail_list = hash ? f->sel[cur ^ 1].as<srd::SelEntry>() : nullptr;
         unsigned long long* fail_count = cnt + 8;
-        if (ah.num_keys == 0)
+        if (f->expand)
+            srd::k_frag_gather_agg_expand<<<f->final_grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, pass, vt,
+                                                                                       f->sel[cur].as<srd::SelEntry>(), cnt + k, fail_list, fail_count);
+        else if (ah.num_keys == 0)
             srd::k_frag_gather_agg<false, true><<<f->final_grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, pass, vt,
                                                                                               f->sel[cur].as<srd::SelEntry>(), cnt + k, nullptr, nullptr);
         else if (f->smem_agg)
@@ -541,16 +549,23 @@ static int32_t frag_push(sr_fragment* f, const sr_chunk_view* fact) {
                 if (failed == 0) break;
                 // grow so that the refused rows fit even if each of them is a new group, then re-apply them
                 SR_CUDA(ctx, cudaMemsetAsync((uint8_t*)a->counters.p + 8, 0, 8, ctx->stream)); // overflow / range flags
-                uint64_t cap = a->host.cap;
-                while ((uint64_t)a->ngroups_host + failed > cap / 2) cap *= 4;
+                // (always at least doubled: a refused row of a one-to-many join may bring several new groups, and a
+                // full 256-slot slice refuses rows below the admission limit)
+                uint64_t cap = a->host.cap * 2;
+                while ((uint64_t)a->ngroups_host + failed > cap / 2) cap *= 2;
                 if (cap > (1ull << 33)) return sr_fail(ctx, SR_ERR_OUT_OF_MEMORY, "aggregate table would exceed 2^33 slots; push smaller batches");
                 SR_TRY(agg_grow(a, cap));
                 cur ^= 1; // the fail list becomes the input, the old input buffer the new fail list
                 const int nfc = fc == 8 ? 9 : 8;
                 SR_CUDA(ctx, cudaMemsetAsync(cnt + nfc, 0, 8, ctx->stream));
-                srd::k_frag_gather_agg<false><<<f->final_grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, pass, vt,
-                                                                                            f->sel[cur].as<srd::SelEntry>(), cnt + fc,
-                                                                                            f->sel[cur ^ 1].as<srd::SelEntry>(), cnt + nfc);
+                if (f->expand)
+                    srd::k_frag_gather_agg_expand<<<f->final_grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, pass, vt,
+                                                                                               f->sel[cur].as<srd::SelEntry>(), cnt + fc,
+                                                                                               f->sel[cur ^ 1].as<srd::SelEntry>(), cnt + nfc);
+                else
+                    srd::k_frag_gather_agg<false><<<f->final_grid, srd::GATHER_BLOCK, 0, ctx->stream>>>(fdev, (const srd::AggDev*)a->dev.p, pass, vt,
+                                                                                                f->sel[cur].as<srd::SelEntry>(), cnt + fc,
+                                                                                                f->sel[cur ^ 1].as<srd::SelEntry>(), cnt + nfc);
                 SR_LAUNCH_CHECK(ctx);
                 fc = nfc;
             }

@@ -13,6 +13,8 @@ struct FragJoinDev {
     int32_t use_bitmap; // range-mapped table: test the bitmap; otherwise probe the hash table
     int32_t need_head;  // a payload column of this join is read downstream
     int32_t idx32;      // bitmap join whose [min, max] fits int32: 32-bit index arithmetic is exact
+    int32_t expand;     // INNER join whose build side has duplicate keys: a probe row is emitted once per chain entry
+    int32_t pad;
 };
 
 struct FragDev {

@@ -344,6 +344,80 @@ __device__ __forceinline__ uint32_t stream_test(const StreamTest& st, const Frag
     return join_test_batch<N>(s_joins[st.join], smem, k, alive);
 }
 
+// The two vector-column tests of k_frag_stream_tests with their parameters held in REGISTERS for the whole kernel.  ncu
+// (profiles/r2_notes.md) showed that kernel issue bound at 47.8 instructions per row, 6.4 of them re-reading the
+// warp-uniform test descriptors from shared memory on every call (the compiler cannot hoist them over the selection-vector
+// stores) and 13.5 in the shared-memory bitmap test.  kind: 0 = range conjunct, 1 = bitmap in shared memory (int32 index
+// arithmetic, zero GUARD bit at index span + 1: an out-of-range key is clamped onto it, so the test needs neither a
+// predicate nor a select), 2 = bitmap in global memory (predicated word fetches, issued back to back), 3 = anything else
+// (falls back to stream_test).
+struct TestReg {
+    uint32_t kind;
+    uint32_t lo, span;
+    const uint32_t* bm;
+};
+
+__device__ __forceinline__ TestReg make_test_reg(const StreamTest& st, const FragJoinDev* s_joins, const uint32_t* smem) {
+    TestReg t;
+    t.kind = 3;
+    t.lo = st.lo;
+    t.span = st.span;
+    t.bm = nullptr;
+    if (st.kind == 0) {
+        t.kind = 0;
+    } else {
+        const FragJoinDev& fj = s_joins[st.join];
+        if (fj.use_bitmap && fj.idx32) {
+            t.lo = (uint32_t)(int32_t)fj.j.min_value;
+            t.span = (uint32_t)(fj.j.max_value - fj.j.min_value);
+            if (fj.smem_off >= 0 && t.span != 0xFFFFFFFFu) {
+                t.kind = 1;
+                t.bm = smem + fj.smem_off;
+            } else {
+                t.kind = 2;
+                t.bm = fj.j.bitmap;
+            }
+        }
+    }
+    return t;
+}
+
+template <int N>
+__device__ __forceinline__ uint32_t stream_test_reg(const TestReg& t, const StreamTest& st, const FragJoinDev* s_joins, const uint32_t* smem,
+                                                    const int32_t (&k)[N], uint32_t alive) {
+    uint32_t out = 0;
+    if (t.kind == 1) {
+        const uint32_t guard = t.span + 1u;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const uint32_t idx = min((uint32_t)k[i] - t.lo, guard);
+            const uint32_t word = t.bm[idx >> 5];
+            out |= __funnelshift_r(word, word, idx - (uint32_t)i) & (1u << i);
+        }
+        return out & alive;
+    }
+    if (t.kind == 2) {
+        uint32_t words[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const uint32_t idx = (uint32_t)k[i] - t.lo;
+            words[i] = ldg_u32_pred(t.bm + (idx >> 5), ((alive >> i) & 1u) && idx <= t.span);
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const uint32_t idx = (uint32_t)k[i] - t.lo;
+            out |= __funnelshift_r(words[i], words[i], idx - (uint32_t)i) & (1u << i);
+        }
+        return out;
+    }
+    if (t.kind == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i++) out |= ((uint32_t)k[i] - t.lo <= t.span ? 1u : 0u) << i;
+        return out & alive;
+    }
+    return stream_test<N>(st, s_joins, smem, k, alive);
+}
+
 template <bool CARRY>
 __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream_tests(const FragDev* __restrict__ fdp, PassDev pd, const __grid_constant__ VTab vt, int64_t n,
                                                                        SelEntry* __restrict__ sel_out, unsigned long long* __restrict__ counter) {
@@ -358,10 +432,14 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream_tests(const Fra
     for (int i = threadIdx.x; i < (int)(sizeof(StreamTest) / 4) * NT; i += blockDim.x) ((uint32_t*)s_tests)[i] = ((const uint32_t*)pd.tests)[i];
     for (int j = 0; j < SJ; j++) {
         const FragJoinDev& fj = fd.joins[j];
-        if (fj.smem_off >= 0)
-            for (int w = threadIdx.x; w < fj.bitmap_words; w += blockDim.x) smem[fj.smem_off + w] = fj.j.bitmap[w];
+        if (fj.smem_off >= 0) // + the zero guard word behind the copy (frag_plan reserves it)
+            for (int w = threadIdx.x; w <= fj.bitmap_words; w += blockDim.x) smem[fj.smem_off + w] = w < fj.bitmap_words ? fj.j.bitmap[w] : 0u;
     }
     __syncthreads();
+    const TestReg t0 = make_test_reg(s_tests[0], s_joins, smem);
+    const TestReg t1 = make_test_reg(s_tests[NV > 1 ? 1 : 0], s_joins, smem);
+    const bool carry0 = CARRY && s_tests[0].kind == 1 && s_tests[0].join == pd.carry_join;
+    const bool carry1 = CARRY && NV > 1 && s_tests[1].kind == 1 && s_tests[1].join == pd.carry_join;
     const int32_t* col0 = (const int32_t*)vt.v[pd.tests[0].value_id].data;
     const int32_t* col1 = NV > 1 ? (const int32_t*)vt.v[pd.tests[1].value_id].data : nullptr;
     const int64_t num_tiles = (n + STREAM_TILE - 1) / STREAM_TILE;
@@ -405,14 +483,14 @@ __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream_tests(const Fra
             const int32_t k0[8] = {pk[0][0].x, pk[0][0].y, pk[0][0].z, pk[0][0].w, pk[0][1].x, pk[0][1].y, pk[0][1].z, pk[0][1].w};
             const int32_t k1[8] = {pk[1][0].x, pk[1][0].y, pk[1][0].z, pk[1][0].w, pk[1][1].x, pk[1][1].y, pk[1][1].z, pk[1][1].w};
             prefetch(tile + 1); // the next tile's vector columns stay in flight while this tile is tested
-            a8 = stream_test<8>(s_tests[0], s_joins, smem, k0, 0xFFu);
-            if (CARRY && s_tests[0].kind == 1 && s_tests[0].join == pd.carry_join) {
+            a8 = stream_test_reg<8>(t0, s_tests[0], s_joins, smem, k0, 0xFFu);
+            if (carry0) {
 #pragma unroll
                 for (int i = 0; i < 8; i++) carry[i] = k0[i];
             }
             if (NV > 1) {
-                a8 = stream_test<8>(s_tests[1], s_joins, smem, k1, a8);
-                if (CARRY && s_tests[1].kind == 1 && s_tests[1].join == pd.carry_join) {
+                a8 = stream_test_reg<8>(t1, s_tests[1], s_joins, smem, k1, a8);
+                if (carry1) {
 #pragma unroll
                     for (int i = 0; i < 8; i++) carry[i] = k1[i];
                 }
@@ -741,6 +819,113 @@ __global__ void __launch_bounds__(GATHER_BLOCK, SR_GATHER_AGG_MIN_BLOCKS) k_frag
         __syncthreads();
         acc_smem_flush(ad, acc);
     }
+    passed = warp_sum(passed);
+    if (lane_id() == 0 && passed) atomicAdd(fd.rows_passed, passed);
+}
+
+// Final pass of a fragment with one-to-many joins (reference: JoinHashMap::_probe_from_ht one-to-many walk,
+// be/src/exec/join/join_hash_map.hpp:718-795 -- every probe row is emitted once per entry of the build chain of its
+// key).  The probe output is never materialised: the thread that owns a surviving fact row walks the chains of its
+// expanding joins like an odometer (last join fastest) and applies the aggregate once per combination, reading the
+// payload columns at the current chain entries.  Hash-table aggregate: a first walk only finds / inserts the group
+// slots; when the table refuses one, nothing of the row has been applied yet and the row goes to the retry list
+// (a row is either applied with all its combinations or not at all).
+__global__ void __launch_bounds__(GATHER_BLOCK) k_frag_gather_agg_expand(const FragDev* __restrict__ fdp, const AggDev* __restrict__ adp, const __grid_constant__ PassDev pd,
+                                                                          const __grid_constant__ VTab vt, const SelEntry* __restrict__ sel_in,
+                                                                          const unsigned long long* __restrict__ n_in_ptr, SelEntry* __restrict__ fail_list,
+                                                                          unsigned long long* __restrict__ fail_count) {
+    __shared__ FragJoinDev s_joins[SR_MAX_FRAG_JOINS];
+    const FragDev& fd = *fdp;
+    const AggDev& ad = *adp;
+    const int S = fd.num_joins;
+    const bool single = ad.num_keys == 0;
+    const bool hash_table = !ad.dense && ad.num_keys > 0;
+    unsigned long long known_groups = hash_table && fail_list ? *(volatile unsigned long long*)ad.ngroups : 0ull;
+    for (int i = threadIdx.x; i < (int)(sizeof(FragJoinDev) / 4) * S; i += blockDim.x) ((uint32_t*)s_joins)[i] = ((const uint32_t*)fd.joins)[i];
+    AccPtrs acc;
+    acc_ptrs_global(ad, acc);
+    __syncthreads();
+    const unsigned long long n_in = *n_in_ptr;
+    unsigned long long passed = 0;
+    SingleAcc sacc;
+    if (single) single_acc_init(ad, sacc);
+    unsigned long long w_begin, w_end;
+    warp_sel_range(n_in, w_begin, w_end);
+    for (unsigned long long i = w_begin + lane_id(); i < w_end; i += 32) {
+        const SelEntry entry = sel_in[i];
+        const uint32_t row = sel_row(entry);
+        if (row == SEL_INVALID) continue;
+        FragLoader ld{vt, (int64_t)row, {0, 0, 0, 0, 0, 0}, pd.carry_join >= 0 ? (int32_t)pd.carry_value_id : -1, sel_carry(entry)};
+        uint32_t head[SR_MAX_FRAG_JOINS];
+        bool ok = true;
+#pragma unroll 1
+        for (int j = 0; j < S && ok; j++) {
+            const FragJoinDev& fj = s_joins[j];
+            head[j] = 0;
+            const bool test = j >= pd.final_first_join;
+            if (!test && !fj.need_head) continue;
+            int64_t key;
+            const bool nul = ld.load(fj.key_value_id, key);
+            if (test && nul) {
+                ok = false;
+                break;
+            }
+            if (fj.need_head || !fj.use_bitmap) {
+                head[j] = join_lookup(fj.j, key);
+                ld.bidx[j] = head[j];
+                if (test && head[j] == 0) ok = false;
+            } else if (test) {
+                if (!join_hit_global(fj, key)) ok = false;
+            }
+        }
+        if (!ok) continue;
+        bool refused = false;
+#pragma unroll 1
+        for (int phase = hash_table ? 0 : 1; phase < 2 && !refused; phase++) {
+            while (true) {
+                if (single) {
+                    single_acc_row(ad, sacc, ld);
+                } else if (hash_table) {
+                    HKey key;
+                    agg_pack_key(ad, ld, key);
+                    bool inserted;
+                    const long long slot = agg_find_slot_key(ad, key, inserted, known_groups);
+                    agg_count_new_groups(ad, inserted, known_groups);
+                    if (slot < 0) {
+                        refused = true;
+                        break;
+                    }
+                    if (phase == 1) agg_apply_row<false>(ad, acc, slot, ld);
+                } else {
+                    const long long slot = agg_find_slot(ad, ld);
+                    if (slot >= 0) agg_apply_row<false>(ad, acc, slot, ld);
+                }
+                if (phase == 1) passed++;
+                // next combination: advance the last expanding join, carry into the one before it when its chain ends
+                int j = S - 1;
+#pragma unroll 1
+                for (; j >= 0; j--) {
+                    if (!s_joins[j].expand) continue;
+                    const uint32_t nx = __ldg(s_joins[j].j.next + ld.bidx[j]);
+                    if (nx) {
+                        ld.bidx[j] = nx;
+                        break;
+                    }
+                    ld.bidx[j] = head[j];
+                }
+                if (j < 0) break;
+            }
+            if (refused) {
+                // phase 0 only (phase 1 finds the slots phase 0 created; tables never shrink in between)
+                if (fail_list) fail_list[atomicAdd(fail_count, 1ull)] = entry;
+            } else if (phase == 0) {
+#pragma unroll 1
+                for (int j = 0; j < S; j++) ld.bidx[j] = head[j]; // the odometer ends on the heads anyway; keeps the second walk independent of that
+            }
+        }
+    }
+    __syncwarp();
+    if (single) single_acc_flush(ad, sacc);
     passed = warp_sum(passed);
     if (lane_id() == 0 && passed) atomicAdd(fd.rows_passed, passed);
 }

@@ -684,6 +684,12 @@ int32_t sr_join_key_hash(sr_ctx* ctx, const void* keys, int32_t key_type, int64_
 }
 
 // ------------------------------------------------------------------ aggregate
+static bool desc_has_distinct(const sr_agg_desc* d) {
+    for (int f = 0; f < d->num_fns; f++)
+        if (d->fns[f].kind == SR_AGG_COUNT_DISTINCT) return true;
+    return false;
+}
+
 sr_agg* sr_agg_create(sr_ctx* ctx, const sr_agg_desc* desc) {
     if (!ctx || !desc) return nullptr;
     if (agg_validate_desc(ctx, desc) != SR_OK) return nullptr;
@@ -710,7 +716,14 @@ int32_t sr_agg_push(sr_agg* a, const sr_chunk_view* chunk) {
     if (!a->compiled) SR_TRY(agg_compile(a, staged_slot_type, staged_slot_nullable, &a->staged));
     VTab vt;
     SR_TRY(bind_vtab(ctx, a->reg, a->staged, &vt));
-    return agg_push_vtab(a, vt, chunk->num_rows);
+    SR_TRY(agg_push_vtab(a, vt, chunk->num_rows));
+    for (sr_agg* c : a->distinct) { // COUNT(DISTINCT) sets see the same (already staged) columns
+        if (!c) continue;
+        VTab cvt;
+        SR_TRY(bind_vtab(ctx, c->reg, a->staged, &cvt));
+        SR_TRY(agg_push_vtab(c, cvt, chunk->num_rows));
+    }
+    return SR_OK;
 }
 
 int32_t sr_agg_sink_finish(sr_agg* a) {
@@ -778,6 +791,9 @@ static int32_t agg_reset_impl(sr_agg* a) {
     a->cursor = 0;
     a->ngroups_host = 0;
     a->table_touched = false;
+    a->distinct_folded = false;
+    for (sr_agg* c : a->distinct)
+        if (c) SR_TRY(agg_reset_impl(c));
     if (!a->compiled) return SR_OK;
     srd::AggDev& h = a->host;
     const bool hash = !h.dense && h.num_keys > 0;
@@ -836,6 +852,7 @@ int32_t sr_agg_dense_state(sr_agg* a, sr_agg_state_array* arrays, int32_t max_ar
     SR_BIND(ctx);
     *num_arrays = 0;
     if (a->out_rows >= 0) return sr_fail(ctx, SR_ERR_STATE, "dense state requested after the output was materialised");
+    if (a->has_distinct) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "COUNT(DISTINCT) states are not element-wise mergeable");
     if (!a->compiled) return sr_fail(ctx, SR_ERR_STATE, "dense state requested before any input was pushed");
     const srd::AggDev& h = a->host;
     if (!h.dense && h.num_keys > 0) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "hash aggregate tables have no element-wise mergeable layout");
@@ -880,6 +897,7 @@ int32_t sr_agg_dense_state(sr_agg* a, sr_agg_state_array* arrays, int32_t max_ar
 int32_t sr_agg_two_phase_descs(const sr_agg_desc* d, sr_agg_desc* p1, sr_agg_desc* p2) {
     if (!d || !p1 || !p2) return SR_ERR_INVALID_ARGUMENT;
     if (d->num_group_keys < 0 || d->num_group_keys > SR_MAX_GROUP_KEYS || d->num_fns < 0 || d->num_fns > SR_MAX_AGG_FNS) return SR_ERR_INVALID_ARGUMENT;
+    if (desc_has_distinct(d)) return SR_ERR_NOT_SUPPORTED; // plan it as GROUP BY (keys, value) below a COUNT, like the reference's FE does
     *p1 = *d;
     *p2 = *d;
     p1->num_fns = 0;
@@ -962,6 +980,7 @@ int32_t sr_agg_convert_to_states(sr_agg* a, const sr_chunk_view* chunk, sr_chunk
     sr_ctx* ctx = a->ctx;
     SR_BIND(ctx);
     const sr_agg_desc& d = a->desc;
+    if (desc_has_distinct(&d)) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "COUNT(DISTINCT) has no intermediate state column");
     for (int f = 0; f < d.num_fns; f++)
         if (d.fns[f].kind == SR_AGG_AVG || d.fns[f].kind == SR_AGG_AVG_MERGE)
             return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "convert_to_states needs a first-phase desc (sr_agg_two_phase_descs): fn %d is AVG", f);
@@ -1019,6 +1038,7 @@ int32_t sr_agg_merge(sr_agg* a, sr_agg* o) {
     SR_BIND(ctx);
     if (o->ctx != ctx) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "merge across contexts");
     if (a->finished) return sr_fail(ctx, SR_ERR_STATE, "merge into a finished aggregate");
+    if (desc_has_distinct(&a->desc)) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "COUNT(DISTINCT) states do not merge; shuffle on the group keys instead");
     if (!o->compiled) return SR_OK; // nothing was pushed into `other`
     if (memcmp(&a->desc, &o->desc, sizeof(sr_agg_desc)) != 0) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "merge needs identical descriptors");
     if (!a->compiled) {
@@ -1098,10 +1118,6 @@ sr_fragment* sr_fragment_create(sr_ctx* ctx, const sr_fragment_desc* desc) {
             sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "fused fragment supports single-column join keys (join %d)", j);
             return nullptr;
         }
-        if (fj.join->has_dup && fj.join->desc.join_type == SR_JOIN_INNER) {
-            sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "fused fragment needs unique build keys (join %d has duplicates); use the per-operator path", j);
-            return nullptr;
-        }
         if (fj.num_payload < 0 || fj.num_payload > SR_MAX_FRAG_PAYLOAD || (fj.num_payload > 0 && fj.join->desc.join_type != SR_JOIN_INNER)) {
             sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "fragment join %d payload", j);
             return nullptr;
@@ -1113,13 +1129,21 @@ sr_fragment* sr_fragment_create(sr_ctx* ctx, const sr_fragment_desc* desc) {
             }
     }
     if (agg_validate_desc(ctx, &desc->agg) != SR_OK) return nullptr;
+    if (desc_has_distinct(&desc->agg)) {
+        sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "COUNT(DISTINCT) inside the fused fragment; aggregate the probe output with sr_agg_push");
+        return nullptr;
+    }
     sr_fragment* f = new sr_fragment();
     f->ctx = ctx;
     f->preds.assign(desc->scan.preds, desc->scan.preds + desc->scan.num_preds);
     f->exprs.assign(desc->scan.filter_exprs, desc->scan.filter_exprs + desc->scan.num_filter_exprs);
     f->num_joins = desc->num_joins;
     f->force_mode = (desc->mode_hint == 1 || desc->mode_hint == 2) ? desc->mode_hint : 0;
-    for (int j = 0; j < desc->num_joins; j++) f->joins[j] = desc->joins[j];
+    for (int j = 0; j < desc->num_joins; j++) {
+        f->joins[j] = desc->joins[j];
+        // one-to-many INNER join (duplicate build keys): always the selection-vector passes, whose final pass expands
+        if (desc->joins[j].join->has_dup && desc->joins[j].join->desc.join_type == SR_JOIN_INNER) f->expand = true;
+    }
     f->agg = new sr_agg();
     f->agg->ctx = ctx;
     f->agg->desc = desc->agg;

@@ -401,6 +401,69 @@ def test_agg_parity(gpu, ctx, oracle, name, n):
         ga.close()
 
 
+@pytest.mark.parametrize("shape", ["nogroup", "dense", "hash", "hash_nullkey", "wide"])
+@pytest.mark.parametrize("n", [0, 1, 5000, 400_001, 2_500_000])
+def test_agg_count_distinct_parity(gpu, ctx, oracle, shape, n):
+    # COUNT(DISTINCT col) next to ordinary functions (reference: distinct.h:48-62,410-424,590-594: a hash set per group
+    # state, NULL inputs skipped, result = set size).  2.5 M rows: the (group, value) set is filled by the
+    # radix-partitioned push; two COUNT(DISTINCT)s of different widths share one operator.
+    rng = np.random.default_rng(77)
+    cols = [(0, rng.integers(0, 40, n, dtype=np.int32), rand_nulls(rng, n, 0.03) if shape == "hash_nullkey" else None),
+            (1, rng.integers(-3000, 3000, n, dtype=np.int64), rand_nulls(rng, n, 0.1)),
+            (2, rng.integers(0, 1 << 40, n, dtype=np.int64) >> rng.integers(0, 30, n), None),
+            (3, rng.integers(0, 2000, n, dtype=np.int16), None),
+            (4, rng.integers(0, 100_000, n, dtype=np.int32), None)]
+    fns = [(abi.AGG_COUNT_DISTINCT, abi.TYPE_BIGINT, 20, [("col", 1)]), (abi.AGG_SUM, abi.TYPE_BIGINT, 21, [("col", 1)]),
+           (abi.AGG_COUNT_STAR, 0, 22, None), (abi.AGG_COUNT_DISTINCT, abi.TYPE_SMALLINT, 23, [("col", 3)]),
+           (abi.AGG_COUNT, abi.TYPE_BIGINT, 24, [("col", 1)])]
+    if shape == "nogroup":
+        d = abi.make_agg_desc(fns=fns)
+    elif shape == "dense":
+        d = abi.make_agg_desc([0], [abi.TYPE_INT], fns=fns, ranges=[(0, 39)])
+    elif shape == "wide":    # 4 + 4 key bytes + 8 value bytes = a 16-byte set key
+        d = abi.make_agg_desc([0, 4], [abi.TYPE_INT, abi.TYPE_INT], fns=[(abi.AGG_COUNT_DISTINCT, abi.TYPE_BIGINT, 20, [("col", 2)]), (abi.AGG_COUNT_STAR, 0, 22, None)])
+    else:
+        d = abi.make_agg_desc([0], [abi.TYPE_INT], fns=fns, group_nullable=[1 if shape == "hash_nullkey" else 0])
+    ga, oa = gpu.Agg(ctx, d), oracle.Agg(d)
+    try:
+        for lo, hi in ((0, n // 3), (n // 3, n)):
+            ch = Chunk([(c[0], c[1][lo:hi].copy(), None if c[2] is None else c[2][lo:hi].copy()) for c in cols])
+            ga.push(ch)
+            oa.push(ch)
+        got = gpu_rows(ga.result())
+        assert_rows_equal(got, oracle_rows(oa))
+        if shape == "nogroup" and n >= 5000:
+            v = cols[1][1][cols[1][2] == 0]
+            assert got[0][0] == len(np.unique(v)) and got[0][4] == len(v)
+        # reset -> same operator, same answer (the sets are reset with it)
+        ga.reset()
+        ch = Chunk([(c[0], c[1], c[2]) for c in cols])
+        ga.push(ch)
+        assert_rows_equal(gpu_rows(ga.result()), oracle_rows(oa))
+    finally:
+        ga.close()
+
+
+def test_agg_count_distinct_unsupported_forms(gpu, ctx):
+    fn = [(abi.AGG_COUNT_DISTINCT, abi.TYPE_BIGINT, 20, [("col", 1), ("i", 1), "+"])]          # expression argument
+    with pytest.raises(gpu.GpuError) as ei:
+        gpu.Agg(ctx, abi.make_agg_desc(fns=fn))
+    assert ei.value.code == abi.SR_ERR_NOT_SUPPORTED
+    d = abi.make_agg_desc([0], [abi.TYPE_INT], fns=[(abi.AGG_COUNT_DISTINCT, abi.TYPE_BIGINT, 20, [("col", 1)])])
+    a, b = gpu.Agg(ctx, d), gpu.Agg(ctx, d)
+    try:
+        ch = Chunk([(0, np.arange(10, dtype=np.int32), None), (1, np.arange(10, dtype=np.int64), None)])
+        a.push(ch)
+        b.push(ch)
+        b.finish()
+        with pytest.raises(gpu.GpuError) as ei:
+            a.merge(b)
+        assert ei.value.code == abi.SR_ERR_NOT_SUPPORTED
+    finally:
+        a.close()
+        b.close()
+
+
 @pytest.mark.parametrize("name", ["dense_b", "nogroup_b"])
 def test_agg_dense_state_elementwise_merge(gpu, ctx, oracle, name):
     # two "fragment instances" aggregate disjoint halves; their dense tables are merged in place by the element-wise
@@ -791,17 +854,91 @@ def test_fragment_hash_table_grows_when_the_sampled_estimate_is_wrong(gpu, ctx, 
         frag.close()
 
 
-def test_fragment_rejects_duplicate_build_keys(gpu, ctx):
-    d = abi.make_join_desc(abi.JOIN_INNER, [10], [0], [abi.TYPE_INT])
-    j = gpu.Join(ctx, d)
+@pytest.mark.parametrize("shape", ["hash_group", "no_group", "dense_group", "two_expanding", "grow"])
+def test_fragment_one_to_many_join(gpu, ctx, oracle, shape):
+    # duplicate build keys (reference: the one-to-many walk of JoinHashMap::_probe_from_ht, join_hash_map.hpp:718-795):
+    # a probe row counts once per build row of its key; payload columns come from every chain entry in turn
+    rng = np.random.default_rng(91)
+    n = 300_000 if shape != "grow" else 1_200_000
+    nb = 40_000
+    fact = Chunk([(0, rng.integers(0, 20_000, n, dtype=np.int32), rand_nulls(rng, n, 0.01)), (1, rng.integers(0, 3000, n, dtype=np.int32), None),
+                  (2, rng.integers(-1000, 1000, n, dtype=np.int64), None), (3, rng.integers(0, 50, n, dtype=np.int32), None)])
+    # build 1: keys 0..9999 with 0-7 rows each (skewed), payload differs per row; a few NULL keys that never match
+    k1 = np.repeat(np.arange(10_000, dtype=np.int32), rng.integers(0, 8, 10_000))
+    rng.shuffle(k1)
+    dim1 = Chunk([(10, k1, rand_nulls(rng, len(k1), 0.01)), (11, rng.integers(0, 200, len(k1), dtype=np.int32), None),
+                  (12, rng.integers(-5, 5, len(k1), dtype=np.int64), rand_nulls(rng, len(k1), 0.05))])
+    k2 = rng.integers(0, 2500, nb // 8, dtype=np.int32)            # build 2: ~2 rows per key, sparse domain -> may be a hash table
+    dim2 = Chunk([(20, k2 * 7, None), (21, rng.integers(0, 30, len(k2), dtype=np.int32), None)])
+    d1 = abi.make_join_desc(abi.JOIN_INNER, [10], [0], [abi.TYPE_INT], build_out=[11, 12])
+    d2 = abi.make_join_desc(abi.JOIN_INNER, [20], [1], [abi.TYPE_INT], build_out=[21])
+    sd = abi.ScanDesc(preds=[abi.make_pred(3, abi.PRED_LT, 40)])
+    fns = [(abi.AGG_SUM, abi.TYPE_BIGINT, 30, [("col", 2), ("col", 12), "*"]), (abi.AGG_COUNT_STAR, 0, 31, None), (abi.AGG_COUNT, abi.TYPE_BIGINT, 32, [("col", 12)]),
+           (abi.AGG_MIN, abi.TYPE_INT, 33, [("col", 11)])]
+    if shape == "no_group":
+        agg_desc = abi.make_agg_desc(fns=fns)
+    elif shape == "dense_group":
+        agg_desc = abi.make_agg_desc([11], [abi.TYPE_INT], fns=fns, ranges=[(0, 199)])
+    elif shape == "grow":
+        # the 64 K-row sample sees no survivor (conjunct on the row number), the rest survive and nearly every
+        # (fact value, payload) pair is a new group -> refused rows are replayed whole after the table has grown
+        fact = Chunk([(0, fact.columns()[0][1], None), (1, fact.columns()[1][1], None), (2, np.arange(n, dtype=np.int64), None),
+                      (3, np.where(np.arange(n) < 70_000, 45, 1).astype(np.int32), None)])
+        agg_desc = abi.make_agg_desc([2, 11], [abi.TYPE_BIGINT, abi.TYPE_INT], fns=fns[1:])
+    else:
+        agg_desc = abi.make_agg_desc([11, 3], [abi.TYPE_INT, abi.TYPE_INT], fns=fns)
+    two = shape == "two_expanding"
+    gj1, gj2 = gpu.Join(ctx, d1), gpu.Join(ctx, d2)
+    oj1, oj2 = oracle.Join(d1), oracle.Join(d2)
+    frag = None
     try:
-        j.append_build(Chunk([(10, np.array([1, 1, 2], dtype=np.int32), None)]))
-        j.build_finish()
-        with pytest.raises(gpu.GpuError) as ei:
-            gpu.Fragment(ctx, abi.ScanDesc(), [(j, 0, [])], abi.make_agg_desc(fns=[(abi.AGG_COUNT_STAR, 0, 1, None)]))
-        assert ei.value.code == abi.SR_ERR_NOT_SUPPORTED    # caller must take the per-operator GPU path; no CPU fallback
+        for j, ch in ((gj1, dim1), (gj2, dim2), (oj1, dim1), (oj2, dim2)):
+            j.append_build(ch)
+        gj1.build_finish()
+        gj2.build_finish()
+        oj1.build()
+        oj2.build()
+        assert gj1.info().has_duplicates and gj2.info().has_duplicates
+        gjoins = [(gj1, 0, [11, 12])] + ([(gj2, 1, [21])] if two else [])
+        ojoins = [(oj1, 0, [11, 12])] + ([(oj2, 1, [21])] if two else [])
+        if two:
+            agg_desc = abi.make_agg_desc([11, 21], [abi.TYPE_INT, abi.TYPE_INT], fns=fns)
+        frag = gpu.Fragment(ctx, sd, gjoins, agg_desc)
+        half = n // 2 + 13
+        for lo, hi in ((0, half), (half, n)):
+            frag.push(Chunk([(sl, d[lo:hi], None if nl is None else nl[lo:hi]) for sl, d, nl in fact.columns()]))
+        got = gpu_rows(frag.agg.result())
+        ores, opassed = oracle.fragment_run(sd, ojoins, agg_desc, fact, num_threads=3)
+        assert opassed > (n // 2 if not two else 50_000)   # the expansion really happened (about 3.5 build rows per matching key)
+        assert frag.rows_passed == opassed
+        assert_rows_equal(got, oracle_rows(ores))
     finally:
-        j.close()
+        if frag:
+            frag.close()
+        gj1.close()
+        gj2.close()
+
+
+def test_q95_plan_parity(gpu, ctx, oracle):
+    # BASELINE config 4's shape on one GPU: the same plan (starrocks_b200.tpcds.q95_local_plan) through the CUDA operators and
+    # through the oracle -- one-to-many self join with an other-conjunct filter, GROUP BY dedup, four IN / dimension semi
+    # joins, COUNT(DISTINCT) + SUMs -- must give the same three numbers and the same intermediate row counts
+    from starrocks_b200 import tpcds
+    g = tpcds.Q95Gen(1.0)
+    ws, wr = g.web_sales_of_orders(0, g.n_orders), g.web_returns_of_orders(0, g.n_orders)
+    def dims(mem):
+        return {"date": Chunk([(tpcds.D_DATE_SK, g.date_keys(), None)]), "addr": Chunk([(tpcds.CA_ADDRESS_SK, g.address_keys(), None)]),
+                "site": Chunk([(tpcds.WEB_SITE_SK, g.site_keys(), None)])}
+    ws_chunk, wr_chunk = tpcds.table_chunk(ws, tpcds.WS_COLS), Chunk([(tpcds.WS_ORDER, wr["wr_order_number"], None)])
+    ores, ost = tpcds.q95_local_plan(tpcds.OracleEngine(oracle), ws_chunk, wr_chunk, dims(0), morsel_rows=200_000)
+    eng = tpcds.GpuEngine(gpu, ctx)
+    eng.mem = abi.MEM_HOST               # host chunks in: the operators stage them
+    try:
+        gres, gst = tpcds.q95_local_plan(eng, ws_chunk, wr_chunk, dims(0), morsel_rows=200_000, expected_orders=g.n_orders)
+    finally:
+        eng.close()
+    assert gres == ores == g.expected(0, g.n_orders)
+    assert gst == ost and gres[0] > 50
 
 
 # ---------------------------------------------------------------------------------------------

@@ -326,6 +326,30 @@ def test_count_avg_minmax_goldens(oracle):
     assert out[2][1][0] == 1023 and out[3][1][0] == 0 and out[4][1][0] == 1026
 
 
+@pytest.mark.parametrize("typ,dt", [(abi.TYPE_SMALLINT, np.int16), (abi.TYPE_INT, np.int32), (abi.TYPE_BIGINT, np.int64)])
+def test_count_distinct_goldens(oracle, typ, dt):
+    # aggregate_test.cpp:752-760 test_count_distinct: multi_distinct_count over gen_input_column1 (0..1023, 100, 200) = 1024,
+    # over gen_input_column2 (2000..2999) = 1000, merged = 2024 (base_aggregate_test.h:83-112,203-237)
+    col1 = np.array(list(range(1024)) + [100, 200], dtype=dt)
+    col2 = np.arange(2000, 3000, dtype=dt)
+    d = abi.make_agg_desc(fns=[(abi.AGG_COUNT_DISTINCT, typ, 10, [("col", 0)])])
+    a, b = oracle.Agg(d), oracle.Agg(d)
+    a.push(Chunk([(0, col1, None)]))
+    b.push(Chunk([(0, col2, None)]))
+    assert a.output()[0][1][0] == 1024
+    assert b.output()[0][1][0] == 1000
+    b.merge(a)
+    assert b.output()[0][1][0] == 2024
+    # grouped, with NULL inputs: NULLs are not counted, an all-NULL group reports 0
+    g = np.array([0, 0, 0, 1, 1, 2], dtype=np.int32)
+    v = np.array([5, 5, 7, 9, 9, 4], dtype=dt)
+    nl = np.array([0, 0, 0, 0, 1, 1], dtype=np.uint8)
+    c = oracle.Agg(abi.make_agg_desc([1], [abi.TYPE_INT], fns=[(abi.AGG_COUNT_DISTINCT, typ, 10, [("col", 0)])]))
+    c.push(Chunk([(0, v, nl), (1, g, None)]))
+    out = c.output()
+    assert sorted(zip(out[0][1].tolist(), out[1][1].tolist())) == [(0, 2), (1, 1), (2, 0)]
+
+
 def test_sum_nullable_all_null_is_null(oracle):
     # test_sum_nullable (aggregate_test.cpp:962): NULL inputs are skipped, all-NULL -> NULL result
     d = abi.make_agg_desc(fns=[(abi.AGG_SUM, abi.TYPE_INT, 10, [("col", 0)])])
@@ -602,3 +626,17 @@ def test_chunk_wire_format_bytes(oracle):
     assert got.tobytes() == want
     assert oracle.chunk_serialize(Chunk([(5, a, an), (9, b, None)]), 1, 2).tobytes() == \
         struct.pack("<II", 1, 1) + struct.pack("<I", 1) + bytes([1]) + struct.pack("<Ii", 4, -1) + struct.pack("<Iq", 8, 2)
+
+
+def test_q95_plan_equals_join_free_evaluation(oracle):
+    # TPC-DS Q95 shape (one-to-many self join, other conjunct, IN-subqueries, COUNT DISTINCT) through the oracle's operators
+    # against the query evaluated without joins over the generator functions
+    from starrocks_b200 import tpcds
+    g = tpcds.Q95Gen(0.3)
+    ws, wr = g.web_sales_of_orders(0, g.n_orders), g.web_returns_of_orders(0, g.n_orders)
+    dims = {"date": Chunk([(tpcds.D_DATE_SK, g.date_keys(), None)]), "addr": Chunk([(tpcds.CA_ADDRESS_SK, g.address_keys(), None)]),
+            "site": Chunk([(tpcds.WEB_SITE_SK, g.site_keys(), None)])}
+    res, st = tpcds.q95_local_plan(tpcds.OracleEngine(oracle), tpcds.table_chunk(ws, tpcds.WS_COLS), Chunk([(tpcds.WS_ORDER, wr["wr_order_number"], None)]),
+                                   dims, morsel_rows=50_000)
+    assert res == g.expected(0, g.n_orders) and res[0] > 10
+    assert st["self_join_rows"] > 10 * len(ws["ws_order_number"])          # the join really is one-to-many
