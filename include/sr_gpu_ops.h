@@ -617,6 +617,35 @@ int32_t sr_xchg_partition(sr_xchg* x, const sr_chunk_view* in, sr_chunk_out* out
 int32_t sr_xchg_hash(sr_xchg* x, const sr_chunk_view* in, uint32_t* hash_values, uint32_t* channel_ids, int32_t mem);
 
 /* ---------------------------------------------------------------------------------------
+ * Segment data pages decoded on the device -- the column a scan would otherwise get from the CPU page
+ * decoders.  Replaces, for 4- and 8-byte integer-class columns (INT, BIGINT, DATE, DATETIME, DECIMAL32/64):
+ *   FrameOfReferencePageDecoder::next_batch  be/src/storage/rowset/frame_of_reference_page.h:113-222
+ *       (ForDecoder, be/src/util/frame_of_reference_coding.cpp:246-352)
+ *   PlainPageDecoder::next_batch             be/src/storage/rowset/plain_page.h:135-260
+ * `pages`: the BODIES of consecutive data pages of one column (after the page's checksum / null-map handling of
+ * page_io.cpp), all in `mem`: SR_MEM_DEVICE, SR_MEM_HOST_PINNED (page-locked mapped memory, e.g. a registered page cache:
+ * read in place over PCIe, the decode is the transfer) or SR_MEM_HOST (pageable: staged page by page).  The values of page
+ * k follow those of page k - 1 in `out` (device memory, room for out_capacity values); *out_rows receives the total.
+ * SR_ERR_INVALID_ARGUMENT for a page that is not well formed (sizes, frame table, bit widths).  Asynchronous on the context
+ * stream except for one small read-back of the per-page counts.  BIT_SHUFFLE (bitshuffle + LZ4), RLE and dictionary pages
+ * are not covered: SR_ERR_NOT_SUPPORTED. */
+typedef enum sr_page_encoding {
+    SR_PAGE_PLAIN = 0, /* EncodingTypePB::PLAIN_ENCODING */
+    SR_PAGE_FOR = 1    /* EncodingTypePB::FOR_ENCODING */
+} sr_page_encoding;
+
+typedef struct sr_page_view {
+    const void* data;
+    int64_t size;
+} sr_page_view;
+
+typedef struct sr_page_decoder sr_page_decoder;
+sr_page_decoder* sr_page_decoder_create(sr_ctx* ctx);
+void sr_page_decoder_destroy(sr_page_decoder* dec);
+int32_t sr_pages_decode(sr_page_decoder* dec, int32_t encoding, int32_t type, const sr_page_view* pages, int32_t num_pages, int32_t mem, void* out,
+                        int64_t out_capacity, int64_t* out_rows);
+
+/* ---------------------------------------------------------------------------------------
  * exchange wire format: the bytes of ChunkPB.data as ProtobufChunkSerde::serialize_without_meta writes
  * them (be/src/serde/protobuf_serde.cpp:88-140) with encode level 0 and no compression:
  *      fixed32 version = 1 | fixed32 num_rows | columns in chunk order

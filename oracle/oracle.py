@@ -44,7 +44,7 @@ DENSE_RANGE_DIRECT_MAPPING, LINEAR_CHAINED, LINEAR_CHAINED_SET = 5, 6, 7
 
 def build():
     """compile oracle/libsr_oracle.so (g++, seconds) and, where the reference tree is present, oracle/_ref (the pieces of the
-    path that compile from the reference's own sources: the vendored xxHash)."""
+    path that compile from the reference's own sources: the vendored xxHash, the frame-of-reference page codec)."""
     subprocess.check_call(["make", "-C", _HERE, "-s"])
     subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
 
@@ -414,6 +414,63 @@ def chunk_serialize(chunk, row_begin=0, row_end=None):
     n2 = lib().orc_chunk_serialize(chunk.ref(), row_begin, row_end, buf.ctypes.data, n)
     assert n2 == n
     return buf
+
+
+def ref_for():
+    """oracle/_ref/libfor_ref.so (the reference's own ForEncoder / ForDecoder), or None when it was never built"""
+    path = os.path.join(_HERE, "_ref", "libfor_ref.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    for nm in ("ref_for_encode_i32", "ref_for_encode_i64", "ref_for_decode_i32", "ref_for_decode_i64"):
+        getattr(L, nm).restype = C.c_longlong
+        getattr(L, nm).argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong]
+    return L
+
+
+def _page_call(fn, elem_size, src, n_or_len, out_dtype, cap_guess):
+    cap = cap_guess
+    while True:
+        out = np.zeros(max(cap, 1), dtype=out_dtype)
+        r = fn(elem_size, src.ctypes.data if src.size else None, n_or_len, out.ctypes.data, cap)
+        if r >= 0:
+            return out[:r]
+        if r == -1:
+            raise OracleError("corrupt page")
+        cap = int(-r)
+
+
+def for_encode(values):
+    """frame-of-reference page bytes of an int32 / int64 array (FrameOfReferencePageBuilder::finish)"""
+    v = np.ascontiguousarray(values)
+    L = lib()
+    L.orc_for_encode.restype = C.c_int64
+    L.orc_for_encode.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+    return _page_call(L.orc_for_encode, v.dtype.itemsize, v, len(v), np.uint8, len(v) * (v.dtype.itemsize + 1) + 64)
+
+
+def for_decode(page, dtype):
+    p = np.ascontiguousarray(page, dtype=np.uint8)
+    L = lib()
+    L.orc_for_decode.restype = C.c_int64
+    L.orc_for_decode.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+    return _page_call(L.orc_for_decode, np.dtype(dtype).itemsize, p, len(p), dtype, 1024)
+
+
+def plain_encode(values):
+    v = np.ascontiguousarray(values)
+    L = lib()
+    L.orc_plain_encode.restype = C.c_int64
+    L.orc_plain_encode.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+    return _page_call(L.orc_plain_encode, v.dtype.itemsize, v, len(v), np.uint8, 4 + v.nbytes)
+
+
+def plain_decode(page, dtype):
+    p = np.ascontiguousarray(page, dtype=np.uint8)
+    L = lib()
+    L.orc_plain_decode.restype = C.c_int64
+    L.orc_plain_decode.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+    return _page_call(L.orc_plain_decode, np.dtype(dtype).itemsize, p, len(p), dtype, 1024)
 
 
 def fragment_run(scan_desc, joins, agg_desc, fact_chunk, num_threads=1):

@@ -14,6 +14,7 @@
 #include <memory>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <unordered_set>
 #include <vector>
 
@@ -2244,4 +2245,169 @@ extern "C" int32_t orc_rf_get_info(const orc_rf* rf, sr_rf_info* info) {
 extern "C" const void* orc_rf_directory(const orc_rf* rf, int64_t* bytes) {
     *bytes = (int64_t)rf->directory.size() * 4;
     return rf->directory.data();
+}
+
+// ---------------------------------------------------------------------------------------
+// segment pages: frame of reference + plain
+// ---------------------------------------------------------------------------------------
+namespace {
+constexpr int FOR_FRAME = 128; // ForEncoder::FRAME_VALUE_NUM (frame_of_reference_coding.h:135)
+
+template <typename T>
+int for_bits(T v) { // bits() / bits_less_than_64 (frame_of_reference_coding.h:49-70): sign-extended to 64 bits first
+    const uint64_t u = (uint64_t)(int64_t)v;
+    return u == 0 ? 0 : 64 - __builtin_clzll(u);
+}
+
+// bit_pack (frame_of_reference_coding.cpp:96-118): value i occupies bits [i*bw, (i+1)*bw) of the stream, most significant
+// bit first inside the value and inside every byte
+template <typename T>
+void for_bit_pack(const T* in, int n, int bw, uint8_t* out) {
+    typedef typename std::make_unsigned<T>::type U;
+    size_t bit = 0;
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < bw; k++, bit++) {
+            if ((bit & 7) == 0) out[bit >> 3] = 0;
+            if (((U)in[i] >> (bw - 1 - k)) & 1) out[bit >> 3] |= (uint8_t)(0x80u >> (bit & 7));
+        }
+}
+
+template <typename T>
+void for_put_le(std::vector<uint8_t>& b, T v) {
+    for (size_t i = 0; i < sizeof(T); i++) b.push_back((uint8_t)((typename std::make_unsigned<T>::type)v >> (8 * i)));
+}
+
+// bit_packing_one_frame_value (frame_of_reference_coding.cpp:120-211)
+template <typename T>
+void for_encode_frame(const T* in, int n, std::vector<uint8_t>& buf, std::vector<uint8_t>& formats, std::vector<uint8_t>& widths) {
+    T mn = in[0], mx = in[0];
+    bool ascending = true, keep = false;
+    int bw = 0;
+    const T half_max = std::numeric_limits<T>::max() >> 1;
+    for (int i = 1; i < n; i++) {
+        if (ascending) {
+            if (in[i] < in[i - 1]) {
+                ascending = false;
+            } else if ((T)((in[i] >> 1) - (in[i - 1] >> 1)) > half_max) {
+                keep = true;
+            } else {
+                bw = std::max(bw, for_bits((T)(in[i] - in[i - 1])));
+            }
+        }
+        if (in[i] < mn) {
+            mn = in[i];
+            continue;
+        }
+        if (in[i] > mx) mx = in[i];
+    }
+    if (!ascending && (T)((mx >> 1) - (mn >> 1)) > half_max) keep = true;
+    for_put_le(buf, mn);
+    T delta[FOR_FRAME];
+    const T* packed = delta;
+    if (keep) {
+        bw = 8 * (int)sizeof(T);
+        packed = in;
+    } else if (ascending) {
+        delta[0] = 0;
+        for (int i = 1; i < n; i++) delta[i] = (T)(in[i] - in[i - 1]);
+    } else {
+        bw = for_bits((T)(mx - mn));
+        for (int i = 0; i < n; i++) delta[i] = (T)(in[i] - mn);
+    }
+    // (the keep-original branch sizes its buffer in bits, frame_of_reference_coding.cpp:172-176: n * bit_width BYTES are
+    // appended, of which bit_pack fills the first n * bit_width / 8)
+    const size_t len = keep ? (size_t)n * bw : ((size_t)n * bw + 7) / 8;
+    const size_t at = buf.size();
+    buf.resize(at + len, 0);
+    if (bw > 0) for_bit_pack(packed, n, bw, buf.data() + at);
+    formats.push_back(keep ? 2 : (ascending ? 1 : 0));
+    widths.push_back((uint8_t)bw);
+}
+
+template <typename T>
+int64_t for_encode(const T* v, int64_t n, uint8_t* out, int64_t cap) {
+    std::vector<uint8_t> buf, formats, widths;
+    for (int64_t i = 0; i < n; i += FOR_FRAME) for_encode_frame(v + i, (int)std::min<int64_t>(FOR_FRAME, n - i), buf, formats, widths);
+    for (size_t f = 0; f < formats.size(); f++) { // flush (frame_of_reference_coding.cpp:213-233)
+        buf.push_back(formats[f]);
+        buf.push_back(widths[f]);
+    }
+    buf.push_back((uint8_t)FOR_FRAME);
+    for_put_le(buf, (uint32_t)n);
+    if ((int64_t)buf.size() > cap) return -(int64_t)buf.size();
+    memcpy(out, buf.data(), buf.size());
+    return (int64_t)buf.size();
+}
+
+// ForDecoder::init + decode_current_frame (frame_of_reference_coding.cpp:246-352)
+template <typename T>
+int64_t for_decode(const uint8_t* p, int64_t len, T* out, int64_t cap) {
+    typedef typename std::make_unsigned<T>::type U;
+    if (len < 5) return -1;
+    const int frame = p[len - 5];
+    uint32_t n;
+    memcpy(&n, p + len - 4, 4);
+    if (frame == 0) return n == 0 ? 0 : -1;
+    const int64_t frames = (n + frame - 1) / frame;
+    const int64_t meta = len - 5 - frames * 2;
+    if (meta < 0) return -1;
+    if ((int64_t)n > cap) return -(int64_t)n;
+    int64_t off = 0;
+    for (int64_t f = 0; f < frames; f++) {
+        const int fmt = p[meta + 2 * f], bw = p[meta + 2 * f + 1];
+        const int cnt = (int)std::min<int64_t>(frame, (int64_t)n - f * frame);
+        if (off + (int64_t)sizeof(T) > meta) return -1;
+        U mn = 0;
+        for (size_t i = 0; i < sizeof(T); i++) mn |= (U)p[off + i] << (8 * i);
+        const uint8_t* bits = p + off + sizeof(T);
+        U prev = mn;
+        for (int i = 0; i < cnt; i++) { // bit_unpack (frame_of_reference_coding.cpp:283-300)
+            U v = 0;
+            const size_t b0 = (size_t)i * bw;
+            for (int k = 0; k < bw; k++) {
+                const size_t bit = b0 + k;
+                v = (U)(v << 1) | ((bits[bit >> 3] >> (7 - (bit & 7))) & 1u);
+            }
+            if (fmt == 2) {
+                out[f * frame + i] = (T)v;
+            } else if (fmt == 1) {
+                prev = (U)(prev + v);
+                out[f * frame + i] = (T)prev;
+            } else {
+                out[f * frame + i] = (T)(U)(v + mn);
+            }
+        }
+        off += (int64_t)bw * frame / 8 + (int64_t)sizeof(T); // ForDecoder::init's frame offsets: full frames
+    }
+    return (int64_t)n;
+}
+} // namespace
+
+extern "C" int64_t orc_for_encode(int32_t elem_size, const void* values, int64_t n, uint8_t* out, int64_t cap) {
+    if (elem_size == 4) return for_encode((const int32_t*)values, n, out, cap);
+    if (elem_size == 8) return for_encode((const int64_t*)values, n, out, cap);
+    return fail(SR_ERR_NOT_SUPPORTED, "frame-of-reference element size");
+}
+extern "C" int64_t orc_for_decode(int32_t elem_size, const uint8_t* page, int64_t len, void* out, int64_t cap) {
+    if (elem_size == 4) return for_decode(page, len, (int32_t*)out, cap);
+    if (elem_size == 8) return for_decode(page, len, (int64_t*)out, cap);
+    return fail(SR_ERR_NOT_SUPPORTED, "frame-of-reference element size");
+}
+// PlainPageBuilder::finish / PlainPageDecoder::init (plain_page.h:82-98,146-165): uint32 count, then the values
+extern "C" int64_t orc_plain_encode(int32_t elem_size, const void* values, int64_t n, uint8_t* out, int64_t cap) {
+    const int64_t need = 4 + n * elem_size;
+    if (need > cap) return -need;
+    const uint32_t c = (uint32_t)n;
+    memcpy(out, &c, 4);
+    memcpy(out + 4, values, (size_t)(n * elem_size));
+    return need;
+}
+extern "C" int64_t orc_plain_decode(int32_t elem_size, const uint8_t* page, int64_t len, void* out, int64_t cap) {
+    if (len < 4) return -1;
+    uint32_t c;
+    memcpy(&c, page, 4);
+    if (len != 4 + (int64_t)c * elem_size) return -1;
+    if ((int64_t)c > cap) return -(int64_t)c;
+    memcpy(out, page + 4, (size_t)c * elem_size);
+    return (int64_t)c;
 }

@@ -202,6 +202,17 @@ int32_t orc_rf_evaluate(const orc_rf* rf, const sr_chunk_view* in, int32_t slot_
 int32_t orc_rf_get_info(const orc_rf* rf, sr_rf_info* info);
 const void* orc_rf_directory(const orc_rf* rf, int64_t* bytes);
 
+/* ---- segment pages: frame-of-reference pages (be/src/util/frame_of_reference_coding.{h,cpp}:
+ * ForEncoder::put_batch / bit_packing_one_frame_value / flush, ForDecoder::init / decode_current_frame; page wrapper
+ * be/src/storage/rowset/frame_of_reference_page.h) and plain pages (plain_page.h:51-158).  elem_size 4 or 8 (signed
+ * integers, like the CppType of TYPE_INT / TYPE_BIGINT / TYPE_DATE).  Pinned byte for byte against the reference's own codec
+ * compiled into oracle/_ref/libfor_ref.so.  encode: returns the page size, or -needed when cap is too small.
+ * decode: returns the number of values, -1 for a corrupt page, -n when cap < n. */
+int64_t orc_for_encode(int32_t elem_size, const void* values, int64_t n, uint8_t* out, int64_t cap);
+int64_t orc_for_decode(int32_t elem_size, const uint8_t* page, int64_t len, void* out, int64_t cap);
+int64_t orc_plain_encode(int32_t elem_size, const void* values, int64_t n, uint8_t* out, int64_t cap);
+int64_t orc_plain_decode(int32_t elem_size, const uint8_t* page, int64_t len, void* out, int64_t cap);
+
 const char* orc_last_error(void);
 
 #ifdef __cplusplus

@@ -118,6 +118,13 @@ class sr_join_desc(C.Structure):
                 ("build_out_types", C.c_int32 * SR_MAX_JOIN_OUT)]
 
 
+PAGE_PLAIN, PAGE_FOR = 0, 1
+
+
+class sr_page_view(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("size", C.c_int64)]
+
+
 class sr_chunk_pb_meta(C.Structure):
     _fields_ = [("serialized_size", C.c_int64), ("num_rows", C.c_int64), ("num_cols", C.c_int32), ("reserved", C.c_int32),
                 ("slot_ids", C.c_int32 * SR_MAX_OUT_COLS), ("types", C.c_int32 * SR_MAX_OUT_COLS),

@@ -75,7 +75,7 @@ struct ScatterArgs {
     unsigned long long ovf_cap;
     int32_t fan_bits;                    // log2 of this level's fan-out
     int32_t local_shift;                 // local bucket = (bucket >> local_shift) & (fan - 1)
-    int32_t l2_prefetch;                 // request the CTA's NEXT tile into L2 while this one is ranked and copied out
+    int32_t l2_prefetch;                 // level 1 from plain columns: request the CTA's NEXT tile into L2 meanwhile
     int32_t pad;
 };
 
@@ -206,22 +206,20 @@ __global__ void __launch_bounds__(AGGP_BLOCK, 1024 / AGGP_BLOCK) k_aggp_scatter(
         int tile_n;
         uint32_t cbase;
         locate(tile, row0, tile_n, cbase);
-        if (sa.l2_prefetch && MODE != SCATTER_CHUNK && tile + gridDim.x < ntiles) {
-            // the tile's loads are one DRAM round trip per batch of rows with nothing else in flight (ncu: 42 % of the
-            // level-1 kernel's stall samples sit on the first use of the loaded words); the next tile's lines are
-            // requested now and arrive in L2 while this tile is ranked, scanned and copied out
+        if (sa.l2_prefetch && MODE == SCATTER_CHUNK_SIMPLE && tile + gridDim.x < ntiles) {
+            // the input columns of the CTA's NEXT tile are requested into L2 while this tile is ranked, scanned and copied
+            // out.  Measured per 1e9 rows (SR_AGG_NO_L2_PREFETCH=1 switches it off): level 1 11.90 -> 11.47 ms.  The same
+            // prefetch on the record tiles of level 2 and on the next bucket of the apply pass cost 0.5 ms each (8.09 ->
+            // 8.65, 9.94 -> 10.40 ms: their input was written by the previous kernel and is largely L2-resident already,
+            // the prefetch instructions only compete for issue slots) and is not done.
             int64_t nrow0;
             int ntile_n;
             uint32_t ncbase;
             locate(tile + gridDim.x, nrow0, ntile_n, ncbase);
-            if (MODE == SCATTER_CHUNK_SIMPLE) {
 #pragma unroll
-                for (int w = 0; w < W; w++) {
-                    const int wb = pl.word_w8[w] ? 8 : 4;
-                    aggp_prefetch_l2((const char*)pl.word_ptr[w] + (size_t)(sa.row_base + nrow0) * wb, (size_t)ntile_n * wb, tid, AGGP_BLOCK);
-                }
-            } else {
-                aggp_prefetch_l2(sa.src + (size_t)nrow0 * W, (size_t)ntile_n * W * 8, tid, AGGP_BLOCK);
+            for (int w = 0; w < W; w++) {
+                const int wb = pl.word_w8[w] ? 8 : 4;
+                aggp_prefetch_l2((const char*)pl.word_ptr[w] + (size_t)(sa.row_base + nrow0) * wb, (size_t)ntile_n * wb, tid, AGGP_BLOCK);
             }
         }
         __syncthreads(); // s_hist is clear (initial clear, or the scan of the previous tile); s_rec / s_perm are free
@@ -405,8 +403,6 @@ struct ApplyArgs {
     int32_t fresh; // the table holds no group yet: slices are initialised in shared memory instead of loaded
     uint32_t* fail_list;            // buckets with a slice that filled up (their records are re-applied by k_aggp_apply_l2)
     unsigned long long* fail_count;
-    int32_t l2_prefetch;            // request the CTA's next bucket into L2 while this one is applied
-    int32_t pad;
 };
 
 struct ApplyFn {
@@ -481,11 +477,6 @@ __global__ void __launch_bounds__(AGGP_APPLY_BLOCK, 4) k_aggp_apply(const AggDev
         const unsigned long long* const brec = aa.rec + (unsigned long long)b * pl.cap2 * W;
         const size_t g0 = (size_t)b * S;
         if (tid == 0) s_fail = 0;
-        if (aa.l2_prefetch && b + gridDim.x < aa.num_buckets) {
-            const uint32_t nb = b + gridDim.x;
-            const unsigned long long nn = min((unsigned long long)aa.count[nb], pl.cap2);
-            aggp_prefetch_l2(aa.rec + (unsigned long long)nb * pl.cap2 * W, (size_t)nn * W * 8, tid, AGGP_APPLY_BLOCK);
-        }
         if (aa.fresh) {
             for (int i = tid; i < S * kw; i += AGGP_APPLY_BLOCK) s_keys[i] = SR_AGG_EMPTY;
             for (int i = tid; i < S; i += AGGP_APPLY_BLOCK) {

@@ -238,8 +238,6 @@ static int32_t agg_push_partitioned(sr_agg* a, const VTab& vt, int64_t n, bool f
             aa.fresh = fresh ? 1 : 0;
             aa.fail_list = a->part_fail.as<uint32_t>();
             aa.fail_count = fail_count;
-            aa.l2_prefetch = sa.l2_prefetch;
-            aa.pad = 0;
             SR_CUDA(ctx, cudaFuncSetAttribute(srd::k_aggp_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem));
             int occ = 1;
             SR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, srd::k_aggp_apply, srd::AGGP_APPLY_BLOCK, apply_smem));

@@ -3,6 +3,7 @@
 // CUDA device every entry point fails with SR_ERR_NO_DEVICE / SR_ERR_CUDA.
 #include "sr_frag.cuh"
 #include "sr_serde.cuh"
+#include "sr_page.cuh"
 
 // ---------------------------------------------------------------------------------------
 // exchange: hash partition (K18).  exchange_sink_operator.cpp:586-637, shuffler.h:72-89,
@@ -1457,6 +1458,33 @@ int32_t sr_chunk_deserialize(sr_serde* h, const void* src, int64_t bytes, int32_
     if (!h || !src || !meta || !out) return SR_ERR_INVALID_ARGUMENT;
     SR_BIND(h->ctx);
     return serde_deserialize(h, src, bytes, src_mem, meta, out);
+}
+
+struct sr_page_decoder {
+    sr_ctx* ctx = nullptr;
+    PageScratch scratch;
+};
+
+sr_page_decoder* sr_page_decoder_create(sr_ctx* ctx) {
+    if (!ctx) return nullptr;
+    sr_page_decoder* d = new sr_page_decoder();
+    d->ctx = ctx;
+    return d;
+}
+
+void sr_page_decoder_destroy(sr_page_decoder* d) {
+    if (!d) return;
+    SR_LOCK(d->ctx);
+    cudaSetDevice(d->ctx->device);
+    cudaStreamSynchronize(d->ctx->stream);
+    delete d;
+}
+
+int32_t sr_pages_decode(sr_page_decoder* d, int32_t encoding, int32_t type, const sr_page_view* pages, int32_t num_pages, int32_t mem, void* out,
+                        int64_t out_capacity, int64_t* out_rows) {
+    if (!d || !out_rows) return SR_ERR_INVALID_ARGUMENT;
+    SR_BIND(d->ctx);
+    return pages_decode(d->ctx, &d->scratch, encoding, type, pages, num_pages, mem, out, out_capacity, out_rows);
 }
 
 int32_t sr_flush_l2(sr_ctx* ctx) {

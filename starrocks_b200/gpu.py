@@ -122,6 +122,9 @@ def lib():
         "sr_event_record": (i32, [vp]),
         "sr_event_query": (i32, [vp]),
         "sr_event_sync": (i32, [vp]),
+        "sr_page_decoder_create": (vp, [vp]),
+        "sr_page_decoder_destroy": (None, [vp]),
+        "sr_pages_decode": (i32, [vp, i32, i32, vp, i32, i32, vp, i64, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -147,6 +150,7 @@ EXPORTED_SYMBOLS = [
     "sr_xchg_destroy", "sr_xchg_partition", "sr_xchg_hash", "sr_gather", "sr_memcpy", "sr_abi_sizeof", "sr_bandwidth_probe", "sr_flush_l2",
     "sr_chunk_serialized_size", "sr_chunk_serialize", "sr_serde_create", "sr_serde_destroy", "sr_chunk_deserialize",
     "sr_host_alloc", "sr_host_free", "sr_event_create", "sr_event_destroy", "sr_event_record", "sr_event_query", "sr_event_sync",
+    "sr_page_decoder_create", "sr_page_decoder_destroy", "sr_pages_decode",
 ]
 
 
@@ -504,6 +508,34 @@ def chunk_serialize(ctx, chunk, row_begin=0, row_end=None):
     meta = abi.sr_chunk_pb_meta()
     ctx.check(lib().sr_chunk_serialize(ctx.h, chunk.ref(), row_begin, row_end, buf.ctypes.data, n, abi.MEM_HOST, C.byref(meta)))
     return buf, meta
+
+
+class PageDecoder:
+    """sr_page_decoder: frame-of-reference / plain data pages -> a device column"""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.h = lib().sr_page_decoder_create(ctx.h)
+
+    def close(self):
+        if self.h:
+            lib().sr_page_decoder_destroy(self.h)
+            self.h = None
+
+    def decode(self, encoding, typ, pages, out_ptr, out_capacity, mem=abi.MEM_HOST):
+        """pages: list of uint8 numpy arrays (host) or (pointer, size) pairs; out_ptr: device pointer.  -> rows"""
+        views = (abi.sr_page_view * max(1, len(pages)))()
+        keep = []
+        for k, pg in enumerate(pages):
+            if isinstance(pg, tuple):
+                views[k].data, views[k].size = pg
+            else:
+                a = np.ascontiguousarray(pg, dtype=np.uint8)
+                keep.append(a)
+                views[k].data, views[k].size = (a.ctypes.data if a.size else None), a.size
+        rows = C.c_int64(0)
+        self.ctx.check(lib().sr_pages_decode(self.h, encoding, typ, views, len(pages), mem, out_ptr, out_capacity, C.byref(rows)))
+        return rows.value
 
 
 class Serde:

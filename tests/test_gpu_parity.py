@@ -1104,3 +1104,98 @@ def test_agg_compressed_key_sql_goldens_gpu(gpu, ctx):
         finally:
             a.close()
     _compressed_key_check(run)
+
+
+# ---------------------------------------------------------------------------------------------
+# segment data pages decoded on the device
+# ---------------------------------------------------------------------------------------------
+def _page_columns(dt, rng):
+    info = np.iinfo(dt)
+    yield "ssb_keys_22bit", rng.integers(1, 3_000_000, 100_003).astype(dt)
+    yield "dates_ascending", np.sort(rng.integers(19920101, 19981231, 70_000)).astype(dt)          # format 1 frames
+    yield "constant", np.full(1000, 42, dtype=dt)                                                     # bit width 0
+    yield "negative_mixed", rng.integers(-10**6, 10**6, 12_345).astype(dt)
+    yield "wide", rng.integers(info.min // 2 + 1, info.max // 2, 5000, dtype=dt)                      # widths 31 / 63
+    yield "one_value", np.array([7], dtype=dt)
+    yield "empty", np.zeros(0, dtype=dt)
+    yield "original_values_single_frame", np.array([info.min, info.max, -1, 0, 1] * 20, dtype=dt)     # format 2 (see test_oracle_golden)
+
+
+@pytest.mark.parametrize("dt,typ", [(np.int32, abi.TYPE_INT), (np.int64, abi.TYPE_BIGINT)])
+@pytest.mark.parametrize("page_rows", [128, 1000, 65_536])
+@pytest.mark.parametrize("mem", ["host", "device"])
+def test_for_pages_decode_parity(gpu, ctx, oracle, dt, typ, page_rows, mem):
+    # pages written by the (reference-pinned) oracle encoder, decoded by k_for_frames / k_for_decode: bit-exact with
+    # ForDecoder as restated in the oracle; pages of one column are concatenated in order
+    import torch
+    rng = np.random.default_rng(5)
+    dec = gpu.PageDecoder(ctx)
+    try:
+        for name, v in _page_columns(dt, rng):
+            pages = [oracle.for_encode(v[lo:lo + page_rows]) for lo in range(0, max(len(v), 1), page_rows)]
+            for pg, lo in zip(pages, range(0, max(len(v), 1), page_rows)):
+                assert (oracle.for_decode(pg, dt) == v[lo:lo + page_rows]).all(), name
+            out = torch.full((len(v) + 8,), -77, dtype=torch.int32 if dt == np.int32 else torch.int64, device="cuda")
+            if mem == "device":
+                blobs = [torch.from_numpy(np.concatenate([np.zeros(k % 4, dtype=np.uint8), pg])).cuda() for k, pg in enumerate(pages)]   # odd alignments
+                views = [(b.data_ptr() + k % 4, len(pg)) for k, (b, pg) in enumerate(zip(blobs, pages))]
+                rows = dec.decode(abi.PAGE_FOR, typ, views, out.data_ptr(), len(v), mem=abi.MEM_DEVICE)
+            else:
+                rows = dec.decode(abi.PAGE_FOR, typ, pages, out.data_ptr(), len(v))
+            ctx.sync()
+            assert rows == len(v), name
+            got = out.cpu().numpy()
+            assert (got[:len(v)] == v).all(), name
+            assert (got[len(v):] == -77).all(), name            # nothing written past the column
+    finally:
+        dec.close()
+
+
+def test_plain_pages_and_malformed_pages(gpu, ctx, oracle):
+    import torch
+    rng = np.random.default_rng(6)
+    dec = gpu.PageDecoder(ctx)
+    try:
+        v = rng.integers(-10**9, 10**9, 10_001).astype(np.int64)
+        pages = [oracle.plain_encode(v[lo:lo + 999]) for lo in range(0, len(v), 999)]
+        out = torch.zeros(len(v), dtype=torch.int64, device="cuda")
+        assert dec.decode(abi.PAGE_PLAIN, abi.TYPE_BIGINT, pages, out.data_ptr(), len(v)) == len(v)
+        ctx.sync()
+        assert (out.cpu().numpy() == v).all()
+        good = oracle.for_encode(v[:300])
+        for bad in (good[:3], np.concatenate([good[:-4], np.array([255, 255, 0, 0], dtype=np.uint8)]),     # too short; value count beyond the page
+                    np.concatenate([good[:-7], np.array([0, 200], dtype=np.uint8), good[-5:]])):            # bit width 200
+            with pytest.raises(gpu.GpuError) as ei:
+                dec.decode(abi.PAGE_FOR, abi.TYPE_BIGINT, [bad], out.data_ptr(), len(v))
+            assert ei.value.code == abi.SR_ERR_INVALID_ARGUMENT
+        with pytest.raises(gpu.GpuError) as ei:                                                               # output too small
+            dec.decode(abi.PAGE_FOR, abi.TYPE_BIGINT, [good], out.data_ptr(), 100)
+        assert ei.value.code == abi.SR_ERR_INVALID_ARGUMENT
+        with pytest.raises(gpu.GpuError) as ei:
+            dec.decode(abi.PAGE_FOR, abi.TYPE_DOUBLE, [good], out.data_ptr(), len(v))
+        assert ei.value.code == abi.SR_ERR_NOT_SUPPORTED
+    finally:
+        dec.close()
+
+
+def test_for_pages_feed_the_scan(gpu, ctx, oracle):
+    # the decoded column is an ordinary device column: scan + filter over it equals the oracle's scan over the raw values
+    import torch
+    rng = np.random.default_rng(8)
+    n = 200_000
+    key = rng.integers(0, 1000, n).astype(np.int32)
+    val = rng.integers(0, 10**6, n).astype(np.int64)
+    dec = gpu.PageDecoder(ctx)
+    try:
+        dk, dv = torch.empty(n, dtype=torch.int32, device="cuda"), torch.empty(n, dtype=torch.int64, device="cuda")
+        dec.decode(abi.PAGE_FOR, abi.TYPE_INT, [oracle.for_encode(key[lo:lo + 50_000]) for lo in range(0, n, 50_000)], dk.data_ptr(), n)
+        dec.decode(abi.PAGE_FOR, abi.TYPE_BIGINT, [oracle.for_encode(val[lo:lo + 30_000]) for lo in range(0, n, 30_000)], dv.data_ptr(), n)
+        sd = abi.ScanDesc(preds=[abi.make_pred(0, abi.PRED_LT, 100)], out_slots=[0, 1])
+        sc = gpu.Scan(ctx, sd)
+        got = gpu.chunk_out_to_host(ctx, sc.filter(Chunk([(0, dk, None), (1, dv, None)], num_rows=n, mem=abi.MEM_DEVICE)))
+        rows, ores = oracle.scan_filter(sd, Chunk([(0, key, None), (1, val, None)]))
+        gcols = {s: d for s, _, d, _ in got}
+        assert len(gcols[0]) == rows and (gcols[0] == ores[0][0]).all() and (gcols[1] == ores[1][0]).all()
+        sc.close()
+    finally:
+        dec.close()

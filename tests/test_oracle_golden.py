@@ -640,3 +640,67 @@ def test_q95_plan_equals_join_free_evaluation(oracle):
                                    dims, morsel_rows=50_000)
     assert res == g.expected(0, g.n_orders) and res[0] > 10
     assert st["self_join_rows"] > 10 * len(ws["ws_order_number"])          # the join really is one-to-many
+
+
+def _for_cases(dt):
+    rng = np.random.default_rng(17)
+    info = np.iinfo(dt)
+    yield "empty", np.zeros(0, dtype=dt)
+    yield "one", np.array([2019], dtype=dt)
+    yield "half_frame", np.arange(64, dtype=dt)                              # TestHalfFrame / TestOneFrame / TestTwoFrame ...
+    yield "one_frame", np.arange(128, dtype=dt)
+    yield "two_half_frames", np.arange(320, dtype=dt)
+    yield "constant", np.full(300, 7, dtype=dt)
+    yield "random_small_range", rng.integers(1000, 1000 + (1 << 22), 5000).astype(dt)      # SSB key columns: 22-bit deltas
+    # delta overflow -> original values (storage format 2).  Single-frame pages only: the reference WRITER appends
+    # n * bit_width BYTES for such a frame (frame_of_reference_coding.cpp:172-176, a bit count used as a byte count; the
+    # tail is uninitialised memory) while its READER steps bit_width * 128 / 8 bytes (:266-272), so the reference cannot
+    # read back its own page when another frame follows one of these.  Both restatements follow the reference as it is.
+    yield "random_full_range", rng.integers(info.min, info.max, 100, dtype=dt)
+    yield "negative", rng.integers(-500, 500, 777).astype(dt)
+    yield "ascending_big_steps", np.cumsum(rng.integers(0, 1 << 20, 1000)).astype(dt)
+    yield "ascending_then_not", np.concatenate([np.arange(128), rng.integers(0, 50, 128), np.arange(40)]).astype(dt)
+    yield "extremes", np.array([info.min, info.max, 0, -1, 1, info.min, info.max] * 18, dtype=dt)
+    yield "ascending_overflow", np.array([info.min, info.max] + [info.max] * 126, dtype=dt)
+
+
+@pytest.mark.parametrize("dt", [np.int32, np.int64])
+def test_for_page_codec_matches_the_reference_codec(oracle, dt):
+    # frame_of_reference_coding.cpp compiled from the reference tree (oracle/_ref/libfor_ref.so) against the restatement:
+    # the encoded page bytes are identical, each side decodes the other's pages (cases follow
+    # be/test/util/frame_of_reference_coding_test.cpp: half / one / two / two-and-a-half frames, int64, min value, zero values)
+    ref = oracle.ref_for()
+    if ref is None:
+        pytest.skip("oracle/_ref/libfor_ref.so not built (no reference tree on this machine)")
+    enc, dec = (ref.ref_for_encode_i32, ref.ref_for_decode_i32) if dt == np.int32 else (ref.ref_for_encode_i64, ref.ref_for_decode_i64)
+    for name, v in _for_cases(dt):
+        mine = oracle.for_encode(v)
+        buf = np.zeros(len(v) * (v.dtype.itemsize * 8 + 2) + 64, dtype=np.uint8)
+        n = enc(v.ctypes.data if len(v) else None, len(v), buf.ctypes.data, len(buf))
+        assert n > 0 and n == len(mine), name
+        if name in ("random_full_range", "extremes", "ascending_overflow"):   # format 2: compare the defined bytes only
+            used = v.dtype.itemsize * (1 + len(v))
+            assert mine[-7:].tobytes() == bytes([2, 8 * v.dtype.itemsize, 128]) + len(v).to_bytes(4, "little"), name
+            assert mine[:used].tobytes() == buf[:used].tobytes() and mine[-7:].tobytes() == buf[n - 7:n].tobytes(), name
+        else:
+            assert mine.tobytes() == buf[:n].tobytes(), name
+        out = np.zeros(max(len(v), 1), dtype=dt)
+        assert dec(mine.ctypes.data, len(mine), out.ctypes.data, len(out)) == len(v), name
+        assert (out[:len(v)] == v).all(), name
+        assert (oracle.for_decode(buf[:n], dt) == v).all(), name
+
+
+@pytest.mark.parametrize("dt", [np.int32, np.int64])
+def test_for_page_known_answers(oracle, dt):
+    # frame_of_reference_coding_test.cpp TestZeroValue: an empty page is the 5-byte footer; the format itself
+    # (frame_of_reference_coding.h:96-118): min, MSB-first deltas, (format, width) per frame, frame size 128, value count
+    assert oracle.for_encode(np.zeros(0, dtype=dt)).tobytes() == bytes([128, 0, 0, 0, 0])
+    page = oracle.for_encode(np.array([1, 2, 4, 8], dtype=dt) + 100)
+    w = np.dtype(dt).itemsize
+    # ascending -> deltas vs the predecessor 0,1,2,4 in 3 bits: 000 001 010 100 -> 0000 0101 0100 (0000)
+    assert page.tobytes() == (101).to_bytes(w, "little") + bytes([0b00000101, 0b01000000]) + bytes([1, 3]) + bytes([128]) + (4).to_bytes(4, "little")
+    assert (oracle.for_decode(page, dt) == np.array([101, 102, 104, 108], dtype=dt)).all()
+    for name, v in _for_cases(dt):
+        assert (oracle.for_decode(oracle.for_encode(v), dt) == v).all(), name
+        assert (oracle.plain_decode(oracle.plain_encode(v), dt) == v).all(), name
+    assert oracle.plain_encode(np.array([5, 6], dtype=np.int32)).tobytes() == bytes([2, 0, 0, 0, 5, 0, 0, 0, 6, 0, 0, 0])   # plain_page.h:82-86
