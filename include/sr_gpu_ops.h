@@ -270,7 +270,18 @@ typedef enum sr_join_type {
     SR_JOIN_INNER = 0,
     SR_JOIN_LEFT_OUTER = 1,
     SR_JOIN_LEFT_SEMI = 2,
-    SR_JOIN_LEFT_ANTI = 3
+    SR_JOIN_LEFT_ANTI = 3,
+    /* Joins that emit build rows after the probe phase (HashJoiner's POST_PROBE phase, exec/hash_joiner.h:161-188,314-329;
+     * JoinHashMap::probe_remain / _search_ht_remain, join_hash_map.hpp:136-143,420-457).  Every probe marks the build rows
+     * it matched (HashTableProbeState::build_match_index); after the last probe sr_join_probe_remain emits, in build
+     * order, the rows that were never matched (RIGHT OUTER, FULL OUTER, RIGHT ANTI; build rows with a NULL key never
+     * match) or that were matched (RIGHT SEMI).  Probe-phase output: RIGHT OUTER = INNER, FULL OUTER = LEFT OUTER, RIGHT
+     * SEMI / ANTI nothing.  (The reference emits RIGHT SEMI rows during the probe, at their first match,
+     * join_hash_map.hpp:1405-1440; here they come out of the remain call in build order -- the same rows.) */
+    SR_JOIN_RIGHT_OUTER = 4,
+    SR_JOIN_RIGHT_SEMI = 5,
+    SR_JOIN_RIGHT_ANTI = 6,
+    SR_JOIN_FULL_OUTER = 7
 } sr_join_type;
 
 /* table layout chosen at build_finish; mirrors JoinHashMapMethodType
@@ -304,6 +315,9 @@ typedef struct sr_join_desc {
      * ever arrives -- a dimension scan that filters everything out; with the types declared here such a join probes to
      * zero rows (INNER / SEMI) or to NULL-padded rows (LEFT OUTER) instead of failing. */
     int32_t build_out_types[SR_MAX_JOIN_OUT];
+    /* sr_type of every probe_out_slot (0 = take it from the probed chunks): sr_join_probe_remain pads the probe columns
+     * of RIGHT / FULL OUTER rows with NULLs and needs their types even when no probe chunk ever arrived */
+    int32_t probe_out_types[SR_MAX_JOIN_OUT];
 } sr_join_desc;
 
 typedef struct sr_join sr_join;
@@ -333,6 +347,11 @@ int32_t sr_join_copy_table(sr_join* join, uint32_t* first_host, uint32_t* next_h
  * (probe_index, build_index) pairs of HashTableProbeState
  * (be/src/exec/join/join_hash_table_descriptor.h:207-330). */
 int32_t sr_join_probe(sr_join* join, int32_t prober_id, const sr_chunk_view* probe, sr_chunk_out* out);
+/* POST_PROBE phase of SR_JOIN_RIGHT_* / SR_JOIN_FULL_OUTER (see sr_join_type): call once, after every prober's last
+ * sr_join_probe has returned (the reference lets the last HashJoinProbeOperator to finish do this, hash_joiner.cpp:315-327).
+ * All rows come in one chunk -- probe_out columns first (all NULL; absent for RIGHT SEMI / ANTI), then the build_out columns --
+ * in DEVICE buffers owned by the join (valid until the next call on this join); the adapter slices it into chunk_size pieces. */
+int32_t sr_join_probe_remain(sr_join* join, sr_chunk_out* out);
 /* device pointers to the index pairs of the last probe of prober_id (num = out->num_rows). */
 int32_t sr_join_probe_indexes(sr_join* join, int32_t prober_id, const uint32_t** probe_index_dev,
                               const uint32_t** build_index_dev);

@@ -100,6 +100,8 @@ def lib():
         "orc_join_probe_chunk": (i32, [vp, vp, i32, vp, vp, vp]),
         "orc_join_probe_all": (i64, [vp, vp, vp, vp, i64]),
         "orc_join_output": (i32, [vp, vp, i64, vp, vp, vp, vp]),
+        "orc_join_probe_remain": (i64, [vp, vp, i64]),
+        "orc_join_output_remain": (i32, [vp, i64, vp, vp, vp, vp]),
         "orc_agg_create": (vp, [vp]),
         "orc_agg_destroy": (None, [vp]),
         "orc_agg_push": (i32, [vp, vp]),
@@ -289,6 +291,32 @@ class Join:
         pi = np.ascontiguousarray(pi, dtype=np.uint32)
         bi = np.ascontiguousarray(bi, dtype=np.uint32)
         _check(lib().orc_join_output(self.h, chunk.ref(), n, _np_ptr(pi), _np_ptr(bi), pd, pn))
+        return list(zip(slots, outs, nulls))
+
+
+    def probe_remain(self, probe_types=()):
+        """POST_PROBE rows of a RIGHT / FULL join -> list of (slot, data, nulls): NULL probe_out columns (types given), then build_out"""
+        d = self.desc
+        cap = self.build_rows + 1
+        bi = np.zeros(cap, dtype=np.uint32)
+        n = _check(lib().orc_join_probe_remain(self.h, _np_ptr(bi), cap))
+        bi = bi[:n]
+        with_probe = d.join_type in (abi.JOIN_RIGHT_OUTER, abi.JOIN_FULL_OUTER)
+        slots, outs, nulls = [], [], []
+        if with_probe:
+            for k in range(d.num_probe_out):
+                slots.append(d.probe_out_slots[k])
+                outs.append(_alloc_col(probe_types[k], n))
+                nulls.append(np.zeros(n, dtype=np.uint8))
+        for k in range(d.num_build_out):
+            s = d.build_out_slots[k]
+            slots.append(s)
+            outs.append(_alloc_col(self.build_types[s], n))
+            nulls.append(np.zeros(n, dtype=np.uint8))
+        pd = (C.c_void_p * max(1, len(outs)))(*[o.ctypes.data for o in outs])
+        pn = (C.c_void_p * max(1, len(outs)))(*[x.ctypes.data for x in nulls])
+        pt = (C.c_int32 * max(1, len(probe_types)))(*probe_types)
+        _check(lib().orc_join_output_remain(self.h, n, _np_ptr(bi), pt, pd, pn))
         return list(zip(slots, outs, nulls))
 
 

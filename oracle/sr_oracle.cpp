@@ -576,6 +576,9 @@ struct orc_join {
     std::vector<DenseGroup> dense_groups;
     bool built = false;
     ProbeState ps; // the builder's own probe state; probers of a fragment clone one each
+    // HashTableProbeState::build_match_index (join_hash_map.hpp:47-48): 1 = the build row found a probe partner.  Index 0 is
+    // the sentinel row, always 1.  One array for the whole join: the reference merges the probers' arrays before POST_PROBE.
+    mutable std::vector<uint8_t> build_match;
 };
 
 static const int FP_BITS = 7; // join_hash_map_method.h:137-147
@@ -914,6 +917,8 @@ extern "C" int32_t orc_join_build(orc_join* j) {
         return fail(SR_ERR_INVALID_ARGUMENT, "bad join method");
     }
     j->ps.prepare(j->chunk_size);
+    j->build_match.assign((size_t)j->row_count + 1, 0);
+    j->build_match[0] = 1;
     j->built = true;
     return SR_OK;
 }
@@ -1071,7 +1076,18 @@ static int32_t probe_chunk_impl(const orc_join* j, ProbeState& ps, const int32_t
         ps.cur_row_match_count = 0;
     };
     const int32_t jt = j->desc.join_type;
-    if (jt == SR_JOIN_LEFT_SEMI || jt == SR_JOIN_LEFT_ANTI) {
+    // joins with a POST_PROBE phase mark every build row they match (join_hash_map.hpp:1352 right outer, :1492 right anti,
+    // :1600 full outer)
+    const bool marks = jt == SR_JOIN_RIGHT_OUTER || jt == SR_JOIN_FULL_OUTER || jt == SR_JOIN_RIGHT_SEMI || jt == SR_JOIN_RIGHT_ANTI;
+    if (jt == SR_JOIN_RIGHT_SEMI || jt == SR_JOIN_RIGHT_ANTI) {
+        // _probe_from_ht_for_right_anti_join (join_hash_map.hpp:1480-1500): mark, emit nothing.  RIGHT SEMI marks the same
+        // way here and emits its (matched) build rows from probe_remain in build order; the reference emits each of them
+        // during the probe at its first match (:1405-1440) -- the same rows in another order.
+        for (uint32_t i = 0; i < n; i++)
+            for (uint32_t b = ps.p_next[i]; b != 0; b = j->next[b])
+                if (j->keys[b] == ps.p_keys[i]) j->build_match[b] = 1;
+        over();
+    } else if (jt == SR_JOIN_LEFT_SEMI || jt == SR_JOIN_LEFT_ANTI) {
         // _probe_from_ht_for_left_semi_join / left_anti_join: join_hash_map.hpp:1186-1255
         for (uint32_t i = 0; i < n; i++) {
             const bool c = contains_probe_row(j, ps, i);
@@ -1090,7 +1106,9 @@ static int32_t probe_chunk_impl(const orc_join* j, ProbeState& ps, const int32_t
         // INNER: _probe_from_ht (join_hash_map.hpp:718-795); LEFT OUTER:
         // _probe_from_ht_for_left_outer_join (:950-1030).  Chunk-full resume via
         // RETURN_IF_CHUNK_FULL2 (:593-602).
-        const bool outer = jt == SR_JOIN_LEFT_OUTER;
+        // RIGHT OUTER probes like INNER, FULL OUTER like LEFT OUTER (_probe_from_ht_for_right_outer_join :1330-1375,
+        // _probe_from_ht_for_full_outer_join :1560-1640), both marking the build rows they emit
+        const bool outer = jt == SR_JOIN_LEFT_OUTER || jt == SR_JOIN_FULL_OUTER;
         size_t i = ps.cur_probe_index;
         if (!first_probe) {
             probe_index[0] = ps.cur_probe_index;
@@ -1127,6 +1145,7 @@ static int32_t probe_chunk_impl(const orc_join* j, ProbeState& ps, const int32_t
                 if (j->keys[b] == ps.p_keys[i]) {
                     probe_index[match_count] = (uint32_t)i;
                     build_index[match_count] = b;
+                    if (marks) j->build_match[b] = 1;
                     match_count++;
                     if (first_probe || outer) cur_row_match_count++;
                     if (first_probe && !outer) ps.p_match_filter[i] = 1;
@@ -1256,6 +1275,38 @@ static int32_t join_output_slots(orc_join* j, const sr_chunk_view* probe, int64_
         }
     }
     return SR_OK;
+}
+
+// POST_PROBE: _search_ht_remain (join_hash_map.hpp:420-457) -- build rows in order whose mark is 0 (RIGHT OUTER, FULL OUTER,
+// RIGHT ANTI) or 1 (RIGHT SEMI, see probe_chunk_impl).  Returns the number of rows (negated when cap is too small).
+extern "C" int64_t orc_join_probe_remain(orc_join* j, uint32_t* build_index, int64_t cap) {
+    if (!j->built) return fail(SR_ERR_STATE, "probe_remain before build");
+    const int32_t jt = j->desc.join_type;
+    if (jt != SR_JOIN_RIGHT_OUTER && jt != SR_JOIN_FULL_OUTER && jt != SR_JOIN_RIGHT_SEMI && jt != SR_JOIN_RIGHT_ANTI)
+        return fail(SR_ERR_INVALID_ARGUMENT, "join type has no post-probe phase");
+    const uint8_t want = jt == SR_JOIN_RIGHT_SEMI ? 1 : 0;
+    int64_t n = 0;
+    for (uint32_t i = 1; i <= j->row_count; i++)
+        if (j->build_match[i] == want) {
+            if (n < cap) build_index[n] = i;
+            n++;
+        }
+    return n > cap ? -n : n;
+}
+
+// output of the POST_PROBE rows: probe_out columns all NULL (_probe_null_output, join_hash_map.hpp:206-232; absent for RIGHT
+// SEMI / ANTI), then the build_out columns gathered by build_index.  probe_types: sr_type of every probe_out slot.
+extern "C" int32_t orc_join_output_remain(orc_join* j, int64_t n, const uint32_t* build_index, const int32_t* probe_types, void** out_data,
+                                          uint8_t** out_nulls) {
+    const int32_t jt = j->desc.join_type;
+    const int np = (jt == SR_JOIN_RIGHT_OUTER || jt == SR_JOIN_FULL_OUTER) ? j->desc.num_probe_out : 0;
+    for (int k = 0; k < np; k++) {
+        memset(out_data[k], 0, (size_t)n * type_width(probe_types[k]));
+        if (out_nulls && out_nulls[k]) memset(out_nulls[k], 1, (size_t)n);
+    }
+    sr_chunk_view none{nullptr, 0, SR_MEM_HOST, 0};
+    return join_output_slots(j, &none, n, nullptr, build_index, nullptr, 0, j->desc.build_out_slots, j->desc.num_build_out, out_data + np,
+                             out_nulls ? out_nulls + np : nullptr);
 }
 
 extern "C" int32_t orc_join_output(orc_join* j, const sr_chunk_view* probe, int64_t n, const uint32_t* probe_index,

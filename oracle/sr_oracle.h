@@ -125,6 +125,9 @@ int64_t orc_join_probe_all(orc_join* j, const sr_chunk_view* probe, uint32_t* pr
 /* _probe_output / _build_output (join_hash_map.hpp:163-269): materialise the join output
  * columns for n index pairs: probe_out_slots then build_out_slots of the desc.
  * out_nulls[k] must be non-NULL for build columns of a LEFT OUTER join. */
+/* POST_PROBE phase of RIGHT / FULL joins (join_hash_map.hpp:136-143,420-457) */
+int64_t orc_join_probe_remain(orc_join* j, uint32_t* build_index, int64_t cap);
+int32_t orc_join_output_remain(orc_join* j, int64_t n, const uint32_t* build_index, const int32_t* probe_types, void** out_data, uint8_t** out_nulls);
 int32_t orc_join_output(orc_join* j, const sr_chunk_view* probe, int64_t n, const uint32_t* probe_index,
                         const uint32_t* build_index, void** out_data, uint8_t** out_nulls);
 

@@ -51,6 +51,7 @@ EX_COL, EX_ICONST, EX_DCONST, EX_ADD, EX_SUB, EX_MUL, EX_TO_DOUBLE = 1, 2, 3, 4,
 EX_EQ, EX_NE, EX_LT, EX_LE, EX_GT, EX_GE, EX_AND, EX_OR, EX_NOT, EX_IS_NULL, EX_DIV = 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18
 
 JOIN_INNER, JOIN_LEFT_OUTER, JOIN_LEFT_SEMI, JOIN_LEFT_ANTI = 0, 1, 2, 3
+JOIN_RIGHT_OUTER, JOIN_RIGHT_SEMI, JOIN_RIGHT_ANTI, JOIN_FULL_OUTER = 4, 5, 6, 7
 JOIN_METHOD_NONE, JOIN_METHOD_DIRECT_MAPPING, JOIN_METHOD_RANGE_DIRECT_MAPPING, JOIN_METHOD_LINEAR_CHAINED = 0, 1, 2, 3
 
 AGG_SUM, AGG_COUNT, AGG_COUNT_STAR, AGG_AVG, AGG_MIN, AGG_MAX, AGG_AVG_MERGE, AGG_COUNT_DISTINCT = 1, 2, 3, 4, 5, 6, 7, 8
@@ -115,7 +116,7 @@ class sr_join_desc(C.Structure):
                 ("num_build_out", C.c_int32), ("build_out_slots", C.c_int32 * SR_MAX_JOIN_OUT),
                 ("num_probe_out", C.c_int32), ("probe_out_slots", C.c_int32 * SR_MAX_JOIN_OUT),
                 ("enable_range_direct_mapping", C.c_int32), ("reserved", C.c_int32),
-                ("build_out_types", C.c_int32 * SR_MAX_JOIN_OUT)]
+                ("build_out_types", C.c_int32 * SR_MAX_JOIN_OUT), ("probe_out_types", C.c_int32 * SR_MAX_JOIN_OUT)]
 
 
 PAGE_PLAIN, PAGE_FOR = 0, 1
@@ -311,7 +312,7 @@ class ScanDesc:
         return C.byref(self.desc)
 
 
-def make_join_desc(join_type, build_keys, probe_keys, key_types, build_out=(), probe_out=(), enable_rdm=True, build_out_types=()):
+def make_join_desc(join_type, build_keys, probe_keys, key_types, build_out=(), probe_out=(), enable_rdm=True, build_out_types=(), probe_out_types=()):
     d = sr_join_desc()
     d.join_type = join_type
     d.num_keys = len(build_keys)
@@ -328,6 +329,8 @@ def make_join_desc(join_type, build_keys, probe_keys, key_types, build_out=(), p
     d.enable_range_direct_mapping = 1 if enable_rdm else 0
     for k, t in enumerate(build_out_types):
         d.build_out_types[k] = t
+    for k, t in enumerate(probe_out_types):
+        d.probe_out_types[k] = t
     return d
 
 

@@ -479,6 +479,12 @@ int32_t sr_join_probe(sr_join* join, int32_t prober_id, const sr_chunk_view* pro
     return join_probe(join, prober_id, probe, out);
 }
 
+int32_t sr_join_probe_remain(sr_join* join, sr_chunk_out* out) {
+    if (!join || !out) return SR_ERR_INVALID_ARGUMENT;
+    SR_BIND(join->ctx);
+    return join_probe_remain(join, out);
+}
+
 int32_t sr_join_probe_indexes(sr_join* join, int32_t prober_id, const uint32_t** probe_index_dev, const uint32_t** build_index_dev) {
     if (!join) return SR_ERR_INVALID_ARGUMENT;
     SR_LOCK(join->ctx);

@@ -200,29 +200,67 @@ __global__ void __launch_bounds__(256) k_fill_u64(unsigned long long* p, int64_t
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-// number of output rows a probe row produces for the join type, given its chain head
-__device__ __forceinline__ uint32_t probe_row_count(const JoinDev& j, int32_t join_type, uint32_t head) {
+// number of output rows a probe row produces for the join type, given its chain head.  `match` (joins with a POST_PROBE
+// phase only): every build row of the chain is marked as matched (HashTableProbeState::build_match_index,
+// join_hash_map.hpp:1352,1492 -- plain byte stores of 1, any number of probers may race on them).
+__device__ __forceinline__ uint32_t probe_row_count(const JoinDev& j, int32_t join_type, uint32_t head, uint8_t* __restrict__ match = nullptr) {
     uint32_t cnt = 0;
     if (head != 0) {
         cnt = 1;
+        if (match) match[head] = 1;
         if (j.has_dup) {
             uint32_t b = __ldg(j.next + head);
             while (b != 0) {
                 cnt++;
+                if (match) match[b] = 1;
                 b = __ldg(j.next + b);
             }
         }
     }
     switch (join_type) {
     case SR_JOIN_INNER:
+    case SR_JOIN_RIGHT_OUTER:
         return cnt;
     case SR_JOIN_LEFT_OUTER:
+    case SR_JOIN_FULL_OUTER:
         return cnt ? cnt : 1;
     case SR_JOIN_LEFT_SEMI:
         return cnt ? 1 : 0;
+    case SR_JOIN_RIGHT_SEMI:
+    case SR_JOIN_RIGHT_ANTI:
+        return 0;
     default:
         return cnt ? 0 : 1;
     }
+}
+
+// POST_PROBE: build rows 1..rows whose mark equals `want`, in build order (_search_ht_remain, join_hash_map.hpp:420-457)
+constexpr int REMAIN_BLOCK = 256;
+__global__ void __launch_bounds__(REMAIN_BLOCK) k_remain_count(const uint8_t* __restrict__ match, int64_t rows, uint8_t want, uint32_t* __restrict__ block_counts) {
+    __shared__ uint32_t s_cnt[REMAIN_BLOCK / 32];
+    const int64_t i = 1 + (int64_t)blockIdx.x * REMAIN_BLOCK + threadIdx.x;
+    uint32_t c = (i <= rows && (match[i] != 0) == (want != 0)) ? 1u : 0u;
+    c = warp_sum(c);
+    if (lane_id() == 0) s_cnt[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < REMAIN_BLOCK / 32; w++) t += s_cnt[w];
+        block_counts[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(REMAIN_BLOCK) k_remain_write(const uint8_t* __restrict__ match, int64_t rows, uint8_t want, const uint64_t* __restrict__ block_offsets,
+                                                                uint32_t* __restrict__ build_index) {
+    __shared__ uint32_t s_scan[REMAIN_BLOCK / 32 + 1];
+    const int64_t i = 1 + (int64_t)blockIdx.x * REMAIN_BLOCK + threadIdx.x;
+    const uint32_t c = (i <= rows && (match[i] != 0) == (want != 0)) ? 1u : 0u;
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan<REMAIN_BLOCK>(c, s_scan, &tot);
+    if (c) build_index[block_offsets[blockIdx.x] + ex] = (uint32_t)i;
+}
+// a column of n NULLs (data zeroed: what Column::append_nulls leaves)
+__global__ void __launch_bounds__(256) k_fill_u8(uint8_t* p, int64_t n, uint8_t v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
 constexpr int PROBE_BLOCK = 256;
@@ -235,7 +273,7 @@ constexpr int PROBE_TILE = PROBE_BLOCK * PROBE_ROWS;
 // PROBE_ROWS consecutive rows: one 128-bit key load when the key is a plain int32 column, then all bitmap words, then
 // all first[] words of the rows whose bit is set -- range methods read the 1-bit-per-key bitmap (32x denser than
 // first[], L1/L2 resident) first, so only matching rows gather from first[].
-__global__ void __launch_bounds__(PROBE_BLOCK) k_probe_count(JoinDev j, KeyCols kc, int32_t join_type, int64_t n, int32_t vec_keys, uint32_t* __restrict__ heads,
+__global__ void __launch_bounds__(PROBE_BLOCK) k_probe_count(JoinDev j, KeyCols kc, int32_t join_type, int64_t n, int32_t vec_keys, uint8_t* __restrict__ match, uint32_t* __restrict__ heads,
                                                               uint32_t* __restrict__ block_counts) {
     __shared__ unsigned long long s_cnt[PROBE_BLOCK / 32];
     const int64_t base = ((int64_t)blockIdx.x * PROBE_BLOCK + threadIdx.x) * PROBE_ROWS;
@@ -277,7 +315,7 @@ __global__ void __launch_bounds__(PROBE_BLOCK) k_probe_count(JoinDev j, KeyCols 
     unsigned long long cnt = 0;
 #pragma unroll
     for (int r = 0; r < PROBE_ROWS; r++)
-        if (base + r < n) cnt += probe_row_count(j, join_type, head[r]);
+        if (base + r < n) cnt += probe_row_count(j, join_type, head[r], match);
     if (full) {
         *(uint4*)(heads + base) = make_uint4(head[0], head[1], head[2], head[3]);
     } else {
@@ -382,6 +420,12 @@ struct sr_join {
     int64_t min_value = 0, max_value = 0, bucket_size = 0, null_keys = 0;
     uint32_t hmask = 0, hlog = 0;
     DevBuf keys, knulls, first, next, hkeys, bitmap, flags, zero_row;
+    // POST_PROBE phase (RIGHT / FULL joins): one mark byte per build row, written by every probe
+    DevBuf match, remain_counts, remain_offsets, remain_index;
+    bool match_ready = false;
+    int32_t probe_types_seen[SR_MAX_JOIN_OUT] = {}; // types of the probe_out columns, from the first probed chunk
+    ScanScratch remain_scan;
+    std::vector<DevBuf> remain_bufs;
     Staged staged_build;
     std::vector<ProberState*> probers;
     ~sr_join() {
@@ -411,7 +455,7 @@ struct sr_join {
 
 static int32_t join_validate_desc(sr_ctx* ctx, const sr_join_desc* d) {
     if (d->num_keys < 1 || d->num_keys > SR_MAX_JOIN_KEYS) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "num_keys %d", d->num_keys);
-    if (d->join_type < SR_JOIN_INNER || d->join_type > SR_JOIN_LEFT_ANTI) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "join type %d", d->join_type);
+    if (d->join_type < SR_JOIN_INNER || d->join_type > SR_JOIN_FULL_OUTER) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "join type %d", d->join_type);
     int total = 0;
     for (int k = 0; k < d->num_keys; k++) {
         const int w = srd::type_width(d->key_types[k]);
@@ -643,6 +687,110 @@ static int32_t join_key_cols(sr_join* j, const Staged& st, srd::KeyCols* kc) {
     return SR_OK;
 }
 
+static bool join_has_post_probe(int32_t jt) {
+    return jt == SR_JOIN_RIGHT_OUTER || jt == SR_JOIN_RIGHT_SEMI || jt == SR_JOIN_RIGHT_ANTI || jt == SR_JOIN_FULL_OUTER;
+}
+
+static int32_t join_match_array(sr_join* j) {
+    if (j->match_ready) return SR_OK;
+    sr_ctx* ctx = j->ctx;
+    SR_TRY(j->match.reserve(ctx, (size_t)j->rows + 16));
+    SR_CUDA(ctx, cudaMemsetAsync(j->match.p, 0, (size_t)j->rows + 16, ctx->stream));
+    j->match_ready = true;
+    return SR_OK;
+}
+
+// POST_PROBE: JoinHashMap::probe_remain (join_hash_map.hpp:136-143) -> _search_ht_remain + _probe_null_output / _build_output
+static int32_t join_probe_remain(sr_join* j, sr_chunk_out* out) {
+    sr_ctx* ctx = j->ctx;
+    if (!j->built) return sr_fail(ctx, SR_ERR_STATE, "probe_remain before build_finish");
+    const int32_t jt = j->desc.join_type;
+    if (!join_has_post_probe(jt)) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "join type %d has no post-probe phase", jt);
+    SR_TRY(join_match_array(j)); // never probed: every build row is unmatched
+    const bool with_probe_cols = jt == SR_JOIN_RIGHT_OUTER || jt == SR_JOIN_FULL_OUTER;
+    const uint8_t want = jt == SR_JOIN_RIGHT_SEMI ? 1 : 0;
+    const int64_t rows = j->rows;
+    int64_t total = 0;
+    const int blocks = grid_for(std::max<int64_t>(rows, 1), srd::REMAIN_BLOCK);
+    if (rows > 0) {
+        SR_TRY(j->remain_counts.reserve(ctx, sizeof(uint32_t) * (size_t)blocks));
+        SR_TRY(j->remain_offsets.reserve(ctx, sizeof(uint64_t) * (size_t)blocks));
+        srd::k_remain_count<<<blocks, srd::REMAIN_BLOCK, 0, ctx->stream>>>((const uint8_t*)j->match.p, rows, want, j->remain_counts.as<uint32_t>());
+        SR_LAUNCH_CHECK(ctx);
+        SR_TRY(scan_counts(ctx, &j->remain_scan, j->remain_counts.as<uint32_t>(), blocks, j->remain_offsets.as<uint64_t>()));
+        SR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->dscratch, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        total = (int64_t)ctx->pinned[0];
+    }
+    SR_TRY(j->remain_index.reserve(ctx, sizeof(uint32_t) * (size_t)std::max<int64_t>(total, 1)));
+    if (total > 0) {
+        srd::k_remain_write<<<blocks, srd::REMAIN_BLOCK, 0, ctx->stream>>>((const uint8_t*)j->match.p, rows, want, j->remain_offsets.as<uint64_t>(),
+                                                                           j->remain_index.as<uint32_t>());
+        SR_LAUNCH_CHECK(ctx);
+    }
+    const int np = with_probe_cols ? j->desc.num_probe_out : 0, nb = j->desc.num_build_out;
+    if (np + nb > SR_MAX_OUT_COLS) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "too many join output columns");
+    if ((int)j->remain_bufs.size() < 2 * (np + nb)) {
+        std::vector<DevBuf> nbv(2 * (np + nb));
+        for (size_t i = 0; i < j->remain_bufs.size(); i++) std::swap(nbv[i], j->remain_bufs[i]);
+        j->remain_bufs.swap(nbv);
+    }
+    out->num_cols = np + nb;
+    out->mem = SR_MEM_DEVICE;
+    out->num_rows = total;
+    srd::GatherArgs ga;
+    ga.n = 0;
+    const size_t cap = (size_t)std::max<int64_t>(total, 1);
+    for (int k = 0; k < np + nb; k++) {
+        if (k < np) { // probe side: NULL (_probe_null_output, join_hash_map.hpp:206-232)
+            const int32_t type = j->desc.probe_out_types[k] ? j->desc.probe_out_types[k] : j->probe_types_seen[k];
+            const int w = srd::type_width(type);
+            if (w == 0)
+                return sr_fail(ctx, SR_ERR_STATE, "type of probe output slot %d is unknown (never probed): declare it in sr_join_desc.probe_out_types", j->desc.probe_out_slots[k]);
+            SR_TRY(j->remain_bufs[2 * k].reserve(ctx, cap * w));
+            SR_TRY(j->remain_bufs[2 * k + 1].reserve(ctx, cap));
+            if (total > 0) {
+                SR_CUDA(ctx, cudaMemsetAsync(j->remain_bufs[2 * k].p, 0, (size_t)total * w, ctx->stream));
+                SR_CUDA(ctx, cudaMemsetAsync(j->remain_bufs[2 * k + 1].p, 1, (size_t)total, ctx->stream));
+            }
+            out->cols[k].data = j->remain_bufs[2 * k].p;
+            out->cols[k].nulls = (uint8_t*)j->remain_bufs[2 * k + 1].p;
+            out->cols[k].type = type;
+            out->cols[k].slot_id = j->desc.probe_out_slots[k];
+            continue;
+        }
+        const int32_t slot = j->desc.build_out_slots[k - np];
+        const BuildCol* bc = j->find_col(slot);
+        if (!bc) {
+            if (total > 0 || j->desc.build_out_types[k - np] == 0) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "build chunk misses output slot %d", slot);
+            out->cols[k].data = nullptr; // empty build side: zero rows of the declared type
+            out->cols[k].nulls = nullptr;
+            out->cols[k].type = j->desc.build_out_types[k - np];
+            out->cols[k].slot_id = slot;
+            continue;
+        }
+        srd::GatherCol g;
+        g.src = bc->data.p;
+        g.src_nulls = bc->nullable ? (const uint8_t*)bc->nulls.p : nullptr;
+        g.width = bc->width;
+        g.zero_is_null = 0;
+        SR_TRY(j->remain_bufs[2 * k].reserve(ctx, cap * g.width));
+        if (g.src_nulls) SR_TRY(j->remain_bufs[2 * k + 1].reserve(ctx, cap));
+        g.dst = j->remain_bufs[2 * k].p;
+        g.dst_nulls = g.src_nulls ? (uint8_t*)j->remain_bufs[2 * k + 1].p : nullptr;
+        out->cols[k].data = g.dst;
+        out->cols[k].nulls = g.dst_nulls;
+        out->cols[k].type = bc->type;
+        out->cols[k].slot_id = slot;
+        ga.c[ga.n++] = g;
+    }
+    if (total > 0 && ga.n > 0) {
+        srd::k_gather<<<dim3(std::min(grid_for(total, 256), ctx->num_sms * 16), ga.n), 256, 0, ctx->stream>>>(j->remain_index.as<uint32_t>(), total, ga);
+        SR_LAUNCH_CHECK(ctx);
+    }
+    return SR_OK;
+}
+
 static int32_t join_probe(sr_join* j, int32_t prober_id, const sr_chunk_view* probe, sr_chunk_out* out) {
     sr_ctx* ctx = j->ctx;
     if (!j->built) return sr_fail(ctx, SR_ERR_STATE, "probe before build_finish");
@@ -661,12 +809,21 @@ static int32_t join_probe(sr_join* j, int32_t prober_id, const sr_chunk_view* pr
                                              (((uintptr_t)kc.c[0].data) & 15) == 0
                                      ? 1
                                      : 0;
+    uint8_t* match = nullptr;
+    if (join_has_post_probe(j->desc.join_type)) {
+        SR_TRY(join_match_array(j));
+        match = (uint8_t*)j->match.p;
+        for (int k = 0; k < j->desc.num_probe_out; k++) { // remembered for the NULL padding of sr_join_probe_remain
+            const int c = ps.staged.find(j->desc.probe_out_slots[k]);
+            if (c >= 0) j->probe_types_seen[k] = ps.staged.cols[c].type;
+        }
+    }
     int64_t total = 0;
     if (n > 0) {
         SR_TRY(ps.heads.reserve(ctx, sizeof(uint32_t) * (size_t)n));
         SR_TRY(ps.block_counts.reserve(ctx, sizeof(uint32_t) * (size_t)blocks));
         SR_TRY(ps.block_offsets.reserve(ctx, sizeof(uint64_t) * (size_t)blocks));
-        srd::k_probe_count<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, kc, j->desc.join_type, n, vec_keys, ps.heads.as<uint32_t>(),
+        srd::k_probe_count<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, kc, j->desc.join_type, n, vec_keys, match, ps.heads.as<uint32_t>(),
                                                                         ps.block_counts.as<uint32_t>());
         SR_LAUNCH_CHECK(ctx);
         SR_TRY(scan_counts(ctx, &ps.scan_scratch, ps.block_counts.as<uint32_t>(), blocks, ps.block_offsets.as<uint64_t>()));
@@ -685,9 +842,11 @@ static int32_t join_probe(sr_join* j, int32_t prober_id, const sr_chunk_view* pr
     }
     ps.last_count = total;
     // materialise output columns: probe_out_slots (gather by probe_index) then build_out_slots
-    const bool semi = j->desc.join_type == SR_JOIN_LEFT_SEMI || j->desc.join_type == SR_JOIN_LEFT_ANTI;
-    const bool outer = j->desc.join_type == SR_JOIN_LEFT_OUTER;
-    const int np = j->desc.num_probe_out, nb = semi ? 0 : j->desc.num_build_out;
+    const int32_t jt = j->desc.join_type;
+    const bool semi = jt == SR_JOIN_LEFT_SEMI || jt == SR_JOIN_LEFT_ANTI;
+    const bool outer = jt == SR_JOIN_LEFT_OUTER || jt == SR_JOIN_FULL_OUTER;
+    const bool right_only = jt == SR_JOIN_RIGHT_SEMI || jt == SR_JOIN_RIGHT_ANTI; // no probe column in the output, no probe-phase rows
+    const int np = right_only ? 0 : j->desc.num_probe_out, nb = semi ? 0 : j->desc.num_build_out;
     if (np + nb > SR_MAX_OUT_COLS) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "too many join output columns");
     if ((int)ps.out_bufs.size() < 2 * (np + nb)) {
         std::vector<DevBuf> nbv(2 * (np + nb));

@@ -70,6 +70,7 @@ def lib():
         "sr_join_get_info": (i32, [vp, vp]),
         "sr_join_copy_table": (i32, [vp, vp, vp]),
         "sr_join_probe": (i32, [vp, i32, vp, vp]),
+        "sr_join_probe_remain": (i32, [vp, vp]),
         "sr_join_probe_indexes": (i32, [vp, i32, vp, vp]),
         "sr_join_key_hash": (i32, [vp, vp, i32, i64, u32, vp, i32]),
         "sr_join_build_runtime_filter": (vp, [vp, i32, i32, i32]),
@@ -140,7 +141,7 @@ EXPORTED_SYMBOLS = [
     "sr_abi_version", "sr_type_width", "sr_ctx_create", "sr_ctx_destroy", "sr_ctx_sync", "sr_last_error", "sr_last_error_code",
     "sr_ctx_kernel_launches", "sr_ctx_device_bytes", "sr_ctx_stream", "sr_scan_create", "sr_scan_destroy",
     "sr_scan_filter", "sr_scan_evaluate", "sr_join_create", "sr_join_destroy", "sr_join_append_build",
-    "sr_join_build_finish", "sr_join_is_build_done", "sr_join_get_info", "sr_join_copy_table", "sr_join_probe",
+    "sr_join_build_finish", "sr_join_is_build_done", "sr_join_get_info", "sr_join_copy_table", "sr_join_probe", "sr_join_probe_remain",
     "sr_join_probe_indexes", "sr_join_key_hash", "sr_agg_create", "sr_agg_destroy", "sr_agg_push",
     "sr_agg_sink_finish", "sr_agg_num_groups", "sr_agg_pull", "sr_agg_merge", "sr_agg_two_phase_descs", "sr_agg_convert_to_states", "sr_agg_current_groups", "sr_agg_dense_state", "sr_agg_reset", "sr_fragment_reset", "sr_fragment_get_plan", "sr_fragment_last_pass_ms",
     "sr_fragment_create",
@@ -349,6 +350,12 @@ class Join:
     def probe(self, chunk, prober_id=0):
         out = abi.sr_chunk_out()
         self.ctx.check(lib().sr_join_probe(self.h, prober_id, chunk.ref(), C.byref(out)))
+        return out
+
+    def probe_remain(self):
+        """POST_PROBE rows of a RIGHT / FULL join (device chunk owned by the join)"""
+        out = abi.sr_chunk_out()
+        self.ctx.check(lib().sr_join_probe_remain(self.h, C.byref(out)))
         return out
 
     def probe_indexes(self, n, prober_id=0):

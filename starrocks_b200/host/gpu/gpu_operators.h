@@ -19,6 +19,7 @@
 // back into <= chunk_size chunks.  need_input() / has_output() expose exactly that buffering to the driver.
 #pragma once
 
+#include <atomic>
 #include <deque>
 #include <functional>
 #include <memory>
@@ -372,11 +373,21 @@ public:
     sr_ctx* ctx() const { return _ctx; }
     sr_join* join() const { return _join; }
     bool is_build_done() const { return _join != nullptr && sr_join_is_build_done(_join) != 0; } // HashJoiner::is_build_done
+    // POST_PROBE phase of RIGHT / FULL joins (HashJoiner::_phase, exec/hash_joiner.h:161-188): every prober registers, the
+    // LAST one to finish its probe input emits the unmatched build rows (hash_join_probe_operator.cpp set_finishing ->
+    // HashJoiner::enter_post_probe_phase, hash_joiner.cpp:315-327)
+    bool has_post_probe() const {
+        return _desc.join_type == SR_JOIN_RIGHT_OUTER || _desc.join_type == SR_JOIN_RIGHT_SEMI || _desc.join_type == SR_JOIN_RIGHT_ANTI ||
+               _desc.join_type == SR_JOIN_FULL_OUTER;
+    }
+    void add_prober() { _active_probers.fetch_add(1); }
+    bool prober_finished_is_last() { return _active_probers.fetch_sub(1) == 1; }
 
 private:
     sr_ctx* _ctx;
     sr_join_desc _desc;
     sr_join* _join = nullptr;
+    std::atomic<int> _active_probers{0};
 };
 using GpuHashJoinerPtr = std::shared_ptr<GpuHashJoiner>;
 
@@ -454,6 +465,7 @@ class GpuHashJoinProbeOperator final : public OperatorWithDependency {
 public:
     GpuHashJoinProbeOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, GpuHashJoinerPtr joiner)
             : OperatorWithDependency(f, id, "gpu_hash_join_probe", plan_node_id, false, seq), _joiner(std::move(joiner)), _prober_id(seq) {
+        _joiner->add_prober();
         _search_ht_timer = ADD_TIMER(_unique_metrics.get(), "SearchHashTableTime"); // probe + both output gathers: one library call
         _output_timer = ADD_TIMER(_unique_metrics.get(), "OutputChunkTime");        // D2H + slicing into <= chunk_size chunks
         _probe_rows_counter = ADD_COUNTER(_unique_metrics.get(), "ProbeRows", TUnit::UNIT);
@@ -477,8 +489,17 @@ public:
         return c;
     }
     Status set_finishing(RuntimeState* state) override {
+        if (_finishing) return Status::OK();
         _finishing = true;
-        return _probe(state);
+        RETURN_IF_ERROR(_probe(state));
+        if (_joiner->has_post_probe() && _joiner->prober_finished_is_last()) { // probe_remain (hash_joiner.cpp:315-327)
+            sr_chunk_out out;
+            RETURN_IF_SR_ERROR(_joiner->ctx(), sr_join_probe_remain(_joiner->join(), &out));
+            COUNTER_UPDATE(_output_rows_counter, out.num_rows);
+            SCOPED_TIMER(_output_timer);
+            RETURN_IF_ERROR(slice_out_to_chunks(_joiner->ctx(), out, state->chunk_size(), &_out));
+        }
+        return Status::OK();
     }
 
 private:

@@ -106,11 +106,31 @@ def _join_pairs(gpu, ctx, oracle, desc, build_chunks, probe_chunk, expect_method
         # exactly the reference's pair sequence: probe order, and inside a duplicate chain descending build index
         assert np.array_equal(gpi, opi) and np.array_equal(gbi, obi)
         gout = gpu.chunk_out_to_host(ctx, out)
-        oout = oj.output(probe_chunk, opi, obi)
-        assert [s for s, _, _, _ in gout] == [s for s, _, _ in oout]
-        grow = rows_sorted([col_to_py(t, d, nl) for _, t, d, nl in gout])
-        orow = rows_sorted([col_to_py(desc_type(desc, oj, probe_chunk, s), d, nl) for s, d, nl in oout])
-        assert grow == orow
+        if desc.join_type in (abi.JOIN_RIGHT_SEMI, abi.JOIN_RIGHT_ANTI):
+            assert n == 0 and len(opi) == 0          # these emit build rows only, all of them in the POST_PROBE phase
+        else:
+            oout = oj.output(probe_chunk, opi, obi)
+            assert [s for s, _, _, _ in gout] == [s for s, _, _ in oout]
+            grow = rows_sorted([col_to_py(t, d, nl) for _, t, d, nl in gout])
+            orow = rows_sorted([col_to_py(desc_type(desc, oj, probe_chunk, s), d, nl) for s, d, nl in oout])
+            assert grow == orow
+        if desc.join_type in POST_PROBE_JOIN_TYPES:
+            # a second prober marks more build rows, then POST_PROBE: never-matched (RIGHT SEMI: matched) build rows in
+            # build order, probe columns NULL (probe_remain, join_hash_map.hpp:136-143,420-457)
+            half = probe_chunk.num_rows // 2
+            tail = Chunk([(sl, d[half:].copy(), None if nl is None else nl[half:].copy()) for sl, d, nl in probe_chunk.columns()])
+            gj.probe(tail, prober_id=1)
+            oj.probe_all(tail, cap=max(1024, 4 * tail.num_rows + 16))
+            ptypes = [probe_chunk.types[probe_chunk.slots.index(desc.probe_out_slots[k])] for k in range(desc.num_probe_out)]
+            grem = gpu.chunk_out_to_host(ctx, gj.probe_remain())
+            orem = oj.probe_remain(ptypes)
+            assert [s for s, _, _, _ in grem] == [s for s, _, _ in orem]
+            for (gs, gt, gd, gn), (os_, od, on) in zip(grem, orem):
+                exp_null = on if gn is not None else None
+                assert col_to_py(gt, gd, gn) == col_to_py(gt, od, exp_null), f"remain slot {gs}"      # same rows, same (build) order
+                if gn is None:
+                    assert not on.any()
+            assert len(grem[0][2]) > 0                                                              # the case has unmatched (matched) build rows
         return gj.info(), n
     finally:
         gj.close()
@@ -122,7 +142,8 @@ def desc_type(desc, oj, probe_chunk, slot):
     return oj.build_types[slot]
 
 
-JOIN_TYPES = [abi.JOIN_INNER, abi.JOIN_LEFT_OUTER, abi.JOIN_LEFT_SEMI, abi.JOIN_LEFT_ANTI]
+POST_PROBE_JOIN_TYPES = (abi.JOIN_RIGHT_OUTER, abi.JOIN_RIGHT_SEMI, abi.JOIN_RIGHT_ANTI, abi.JOIN_FULL_OUTER)
+JOIN_TYPES = [abi.JOIN_INNER, abi.JOIN_LEFT_OUTER, abi.JOIN_LEFT_SEMI, abi.JOIN_LEFT_ANTI] + list(POST_PROBE_JOIN_TYPES)
 
 
 @pytest.mark.parametrize("join_type", JOIN_TYPES)

@@ -704,3 +704,27 @@ def test_for_page_known_answers(oracle, dt):
         assert (oracle.for_decode(oracle.for_encode(v), dt) == v).all(), name
         assert (oracle.plain_decode(oracle.plain_encode(v), dt) == v).all(), name
     assert oracle.plain_encode(np.array([5, 6], dtype=np.int32)).tobytes() == bytes([2, 0, 0, 0, 5, 0, 0, 0, 6, 0, 0, 0])   # plain_page.h:82-86
+
+
+def test_right_and_full_join_post_probe_known_answers(oracle):
+    # build keys 1, 2, 2, 3, NULL (rows 1..5); probe keys 2, 4.  POST_PROBE (join_hash_map.hpp:420-457): build rows whose
+    # build_match_index stayed 0, in build order; a NULL build key never matches
+    bkey = np.array([1, 2, 2, 3, 0], dtype=np.int32)
+    bnul = np.array([0, 0, 0, 0, 1], dtype=np.uint8)
+    bpay = np.array([10, 20, 21, 30, 40], dtype=np.int32)
+    build = Chunk([(10, bkey, bnul), (11, bpay, None)])
+    probe = Chunk([(0, np.array([2, 4], dtype=np.int32), None), (1, np.array([100, 400], dtype=np.int64), None)])
+    exp = {abi.JOIN_RIGHT_OUTER: ([(0, 3), (0, 2)], [10, 30, 40]), abi.JOIN_FULL_OUTER: ([(0, 3), (0, 2), (1, 0)], [10, 30, 40]),
+           abi.JOIN_RIGHT_ANTI: ([], [10, 30, 40]), abi.JOIN_RIGHT_SEMI: ([], [20, 21])}
+    for jt, (pairs, remain_pay) in exp.items():
+        j = oracle.Join(abi.make_join_desc(jt, [10], [0], [abi.TYPE_INT], build_out=[11], probe_out=[1]))
+        j.append_build(build)
+        j.build()
+        pi, bi = j.probe_all(probe)
+        assert list(zip(pi.tolist(), bi.tolist())) == pairs, jt          # chain order: descending build index, like INNER
+        rem = j.probe_remain([abi.TYPE_BIGINT])
+        assert rem[-1][1].tolist() == remain_pay, jt
+        if jt in (abi.JOIN_RIGHT_OUTER, abi.JOIN_FULL_OUTER):
+            assert rem[0][0] == 1 and rem[0][2].tolist() == [1] * len(remain_pay)      # probe column: all NULL
+        else:
+            assert len(rem) == 1
