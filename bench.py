@@ -36,10 +36,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
-    ap.add_argument("--workload", default="q41", choices=["q41", "groupby", "q3"],
+    ap.add_argument("--workload", default="q41", choices=["q41", "groupby", "q3", "q95"],
                     help="q41: SSB SF100 Q4.1 (BASELINE.json's metric; the default).  groupby: BASELINE.json config 5, 1e9 rows / 1e8 "
                          "distinct int64 keys, SUM + COUNT, on one B200 (N > 1: one independent key range per GPU, no exchange).  "
-                         "q3: BASELINE.json config 3, TPC-H Q3 with the NCCL hash shuffle (tools/q3_distributed.py; --sf = TPC-H scale)")
+                         "q3: BASELINE.json config 3, TPC-H Q3 with the NCCL hash shuffle (tools/q3_distributed.py; --sf = TPC-H scale).  "
+                         "q95: BASELINE.json config 4, the TPC-DS Q95 shape (tools/q95_distributed.py; --sf = TPC-DS scale, default 1000 / 8 per GPU)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="q41 with N > 1: weak = --sf per GPU (default), strong = --sf split over the N GPUs")
     ap.add_argument("--groupby-rows", type=int, default=1_000_000_000)
@@ -869,6 +870,15 @@ if __name__ == "__main__":
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import q3_distributed
             q3_distributed.main(q3_distributed.parse(["--sf", str(a.sf if a.sf != 100.0 else 300.0), "--steps", str(a.steps), "--warmup", str(a.warmup)]))
+    elif a.workload == "q95":
+        if a.impl == "reference":
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the CPU arm of the Q95 workload is the oracle check inside tools/q95_distributed.py (--check oracle)"}))
+        else:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import q95_distributed
+            world = int(os.environ.get("WORLD_SIZE", "1"))
+            q95_distributed.main(q95_distributed.parse(["--sf", str(a.sf if a.sf != 100.0 else 125.0 * world), "--steps", str(a.steps), "--warmup", str(a.warmup)]))
     elif a.workload == "groupby":
         run_reference_groupby(a) if a.impl == "reference" else run_gpu_groupby(a)
     elif a.impl == "reference":

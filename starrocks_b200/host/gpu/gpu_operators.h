@@ -20,11 +20,13 @@
 #pragma once
 
 #include <atomic>
+#include <condition_variable>
 #include <deque>
 #include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../exec/pipeline/operator.h"
@@ -272,23 +274,108 @@ constexpr int kGpuBatchChunks = 64; // ScanOperator::_buffer_size / io task batc
 // ------------------------------------------------------------------------------------------------------------
 // scan
 // ------------------------------------------------------------------------------------------------------------
+// The IO side of the scan (reference: ScanOperator::_trigger_next_scan submits a ScanTask to the workgroup's ScanExecutor,
+// the task runs ChunkSource::buffer_next_batch_chunks_blocking and fills the operator's BalancedChunkBuffer;
+// scan_operator.cpp:328-515, chunk_source.cpp:60-120, exec/workgroup/scan_executor.h).  Here the "IO" of a task is one
+// sr_scan_filter call over a batch of the morsel's chunks plus the D2H slicing of its output -- the part that takes time --
+// so the pipeline driver that owns the operator never waits for the GPU: pull_chunk only triggers tasks and pops the buffer.
+class GpuScanExecutor {
+public:
+    explicit GpuScanExecutor(int threads) {
+        for (int t = 0; t < std::max(1, threads); t++) _workers.emplace_back([this] { _run(); });
+    }
+    ~GpuScanExecutor() {
+        {
+            std::lock_guard<std::mutex> l(_mu);
+            _stop = true;
+        }
+        _cv.notify_all();
+        for (auto& w : _workers) w.join();
+    }
+    void submit(std::function<void()> task) {
+        {
+            std::lock_guard<std::mutex> l(_mu);
+            _tasks.push_back(std::move(task));
+        }
+        _cv.notify_one();
+    }
+    int64_t tasks_run() const { return _tasks_run.load(); }
+
+private:
+    void _run() {
+        while (true) {
+            std::function<void()> task;
+            {
+                std::unique_lock<std::mutex> l(_mu);
+                _cv.wait(l, [this] { return _stop || !_tasks.empty(); });
+                if (_tasks.empty()) return; // stop requested and drained
+                task = std::move(_tasks.front());
+                _tasks.pop_front();
+            }
+            task();
+            _tasks_run.fetch_add(1);
+        }
+    }
+    std::mutex _mu;
+    std::condition_variable _cv;
+    std::deque<std::function<void()>> _tasks;
+    std::vector<std::thread> _workers;
+    std::atomic<int64_t> _tasks_run{0};
+    bool _stop = false;
+};
+using GpuScanExecutorPtr = std::shared_ptr<GpuScanExecutor>;
+
+// the operator's chunk buffer (BalancedChunkBuffer, exec/pipeline/scan/balanced_chunk_buffer.h): filled by IO tasks, drained by
+// pull_chunk; `limit` chunks bound what a scan may run ahead of its consumer (ScanOperator::_buffer_size)
+class GpuChunkBuffer {
+public:
+    explicit GpuChunkBuffer(size_t limit) : _limit(limit) {}
+    void put(std::deque<ChunkPtr>&& chunks) {
+        std::lock_guard<std::mutex> l(_mu);
+        for (auto& c : chunks) _q.push_back(std::move(c));
+        _size.store(_q.size());
+    }
+    ChunkPtr try_get() {
+        std::lock_guard<std::mutex> l(_mu);
+        if (_q.empty()) return ChunkPtr(nullptr);
+        ChunkPtr c = std::move(_q.front());
+        _q.pop_front();
+        _size.store(_q.size());
+        return c;
+    }
+    bool empty() const { return _size.load() == 0; }
+    bool has_room() const { return _size.load() < _limit; }
+
+private:
+    mutable std::mutex _mu;
+    std::deque<ChunkPtr> _q;
+    std::atomic<size_t> _size{0};
+    size_t _limit;
+};
+
 class GpuScanOperator final : public SourceOperator {
 public:
     // `morsel`: the decoded chunks the storage layer would hand over (TabletReader -> ChunkIterator::get_next); the
-    // operator owns predicate evaluation + Chunk::filter on the device.
+    // operator owns predicate evaluation + Chunk::filter on the device.  With an executor the scan is asynchronous (the
+    // reference's shape); without one every pull_chunk runs its batch inline (kept for single-threaded tests).
     GpuScanOperator(OperatorFactory* f, int32_t id, int32_t plan_node_id, int32_t seq, sr_ctx* ctx, const sr_scan_desc& desc,
-                    std::vector<ChunkPtr> morsel)
-            : SourceOperator(f, id, "gpu_olap_scan", plan_node_id, false, seq), _ctx(ctx), _desc(desc), _morsel(std::move(morsel)) {
+                    std::vector<ChunkPtr> morsel, GpuScanExecutorPtr executor = nullptr)
+            : SourceOperator(f, id, "gpu_olap_scan", plan_node_id, false, seq), _ctx(ctx), _desc(desc), _morsel(std::move(morsel)),
+              _executor(std::move(executor)), _buffer(2 * kGpuBatchChunks) {
         // the names of ScanOperator / OlapChunkSource's profile (olap_chunk_source.cpp:93-140)
         _expr_filter_timer = ADD_TIMER(_unique_metrics.get(), "ExprFilterTime");
         _rows_read_counter = ADD_COUNTER(_unique_metrics.get(), "RawRowsRead", TUnit::UNIT);
         _rows_out_counter = ADD_COUNTER(_unique_metrics.get(), "RowsRead", TUnit::UNIT);
+        _io_task_counter = ADD_COUNTER(_unique_metrics.get(), "SubmitTaskCount", TUnit::UNIT);           // scan_operator.cpp: _submit_task_counter
+        _buffer_empty_counter = ADD_COUNTER(_unique_metrics.get(), "PullChunkBufferEmpty", TUnit::UNIT); // pulls that found the buffer empty
         _gpu.init(_unique_metrics.get());
     }
     ~GpuScanOperator() override {
+        _wait_io();
         if (_scan) sr_scan_destroy(_scan);
     }
     Status prepare(RuntimeState* state) override {
+        _chunk_size = state->chunk_size();
         _scan = sr_scan_create(_ctx, &_desc);
         return _scan ? Status::OK() : sr_to_status(_ctx, sr_last_error_code(_ctx));
     }
@@ -303,33 +390,82 @@ public:
         for (auto& p : _rf_probes) ids.insert(p.build_plan_node_id);
         return _hub ? _hub->gather_holders(ids) : std::vector<RuntimeFilterHolder*>();
     }
-    int64_t rows_after_scan() const { return _rows_out; }
-    bool has_output() const override { return !_out.empty() || _next < _morsel.size(); }
-    bool is_finished() const override { return _out.empty() && _next >= _morsel.size(); }
+    int64_t rows_after_scan() const { return _rows_out.load(); }
+    // ScanOperator::has_output (scan_operator.cpp:130-175): a buffered chunk, or an IO task could be submitted -- the
+    // driver then calls pull_chunk, which submits it and returns nothing yet
+    bool has_output() const override {
+        if (!_buffer.empty() || _io_failed.load()) return true;
+        return _running.load() == 0 && _next.load() < _morsel.size();
+    }
+    bool is_finished() const override { return _buffer.empty() && _running.load() == 0 && _next.load() >= _morsel.size() && !_io_failed.load(); }
+    bool pending_finish() const override { return _running.load() > 0; } // ScanOperator::pending_finish: IO tasks still hold the operator
+    Status set_finished(RuntimeState* state) override {
+        _cancelled.store(true);
+        return Status::OK();
+    }
     StatusOr<ChunkPtr> pull_chunk(RuntimeState* state) override {
         if (!_rf_attached) RETURN_IF_ERROR(_attach_runtime_filters());
-        if (_out.empty() && _next < _morsel.size()) {
-            _batch.clear();
-            for (int k = 0; k < kGpuBatchChunks && _next < _morsel.size(); k++) _batch.append(*_morsel[_next++]);
-            sr_chunk_view v = _batch.view();
-            sr_chunk_out out;
-            {
-                SCOPED_TIMER(_expr_filter_timer);
-                RETURN_IF_SR_ERROR(_ctx, sr_scan_filter(_scan, &v, &out));
-            }
-            COUNTER_UPDATE(_rows_read_counter, (int64_t)_batch.rows());
-            COUNTER_UPDATE(_rows_out_counter, out.num_rows);
-            _gpu.sample(_ctx, _mem_tracker.get());
-            _rows_out += out.num_rows;
-            RETURN_IF_ERROR(slice_out_to_chunks(_ctx, out, state->chunk_size(), &_out));
+        if (_io_failed.load()) {
+            std::lock_guard<std::mutex> l(_status_mu);
+            return _io_status;
         }
-        if (_out.empty()) return ChunkPtr(nullptr);
-        ChunkPtr c = _out.front();
-        _out.pop_front();
+        if (_executor) {
+            _try_to_trigger_next_scan();
+        } else if (_buffer.empty() && _next.load() < _morsel.size()) {
+            _io_task(); // synchronous form
+        }
+        ChunkPtr c = _buffer.try_get();
+        if (!c) COUNTER_UPDATE(_buffer_empty_counter, 1);
         return c;
     }
 
 private:
+    // one IO task per operator at a time (its chunks stay in morsel order); DOP operators give DOP concurrent tasks
+    void _try_to_trigger_next_scan() {
+        if (_next.load() >= _morsel.size() || !_buffer.has_room() || _cancelled.load()) return;
+        int expected = 0;
+        if (!_running.compare_exchange_strong(expected, 1)) return;
+        COUNTER_UPDATE(_io_task_counter, 1);
+        _executor->submit([this] {
+            _io_task();
+            _running.store(0);
+        });
+    }
+    // ChunkSource::buffer_next_batch_chunks_blocking: read a batch, filter it on the device, buffer the output chunks
+    void _io_task() {
+        size_t next = _next.load();
+        ChunkBatch batch;
+        for (int k = 0; k < kGpuBatchChunks && next < _morsel.size(); k++) batch.append(*_morsel[next++]);
+        sr_chunk_view v = batch.view();
+        sr_chunk_out out;
+        Status st = Status::OK();
+        std::deque<ChunkPtr> chunks;
+        {
+            SCOPED_TIMER(_expr_filter_timer);
+            const int32_t rc = sr_scan_filter(_scan, &v, &out);
+            if (rc != SR_OK) st = sr_to_status(_ctx, rc);
+        }
+        if (st.ok()) st = slice_out_to_chunks(_ctx, out, _chunk_size, &chunks);
+        if (!st.ok()) {
+            {
+                std::lock_guard<std::mutex> l(_status_mu);
+                _io_status = st;
+            }
+            _io_failed.store(true);
+            _next.store(_morsel.size());
+            return;
+        }
+        COUNTER_UPDATE(_rows_read_counter, (int64_t)batch.rows());
+        COUNTER_UPDATE(_rows_out_counter, out.num_rows);
+        _gpu.sample(_ctx, _mem_tracker.get());
+        _rows_out.fetch_add(out.num_rows);
+        _buffer.put(std::move(chunks));
+        _next.store(next); // published after the chunks: is_finished() never sees "exhausted" with the last batch still on its way
+    }
+    void _wait_io() {
+        _cancelled.store(true);
+        while (_running.load() > 0) std::this_thread::yield();
+    }
     Status _attach_runtime_filters() {
         _rf_attached = true;
         for (auto& p : _rf_probes) {
@@ -347,13 +483,18 @@ private:
     RuntimeFilterHub* _hub = nullptr;
     std::vector<GpuRuntimeFilterProbeDesc> _rf_probes;
     bool _rf_attached = false;
-    int64_t _rows_out = 0;
-    RuntimeProfile::Counter *_expr_filter_timer, *_rows_read_counter, *_rows_out_counter;
+    int _chunk_size = 4096;
+    std::atomic<int64_t> _rows_out{0};
+    RuntimeProfile::Counter *_expr_filter_timer, *_rows_read_counter, *_rows_out_counter, *_io_task_counter, *_buffer_empty_counter;
     GpuOpCounters _gpu;
     std::vector<ChunkPtr> _morsel;
-    size_t _next = 0;
-    ChunkBatch _batch;
-    std::deque<ChunkPtr> _out;
+    std::atomic<size_t> _next{0};
+    GpuScanExecutorPtr _executor;
+    GpuChunkBuffer _buffer;
+    std::atomic<int> _running{0};
+    std::atomic<bool> _io_failed{false}, _cancelled{false};
+    std::mutex _status_mu;
+    Status _io_status;
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1021,18 +1162,24 @@ private:
 // ------------------------------------------------------------------------------------------------------------
 class GpuScanOperatorFactory final : public SourceOperatorFactory {
 public:
-    GpuScanOperatorFactory(int32_t id, int32_t plan_node_id, sr_ctx* ctx, sr_scan_desc desc, std::vector<std::vector<ChunkPtr>> morsels)
-            : SourceOperatorFactory(id, "gpu_olap_scan", plan_node_id), _ctx(ctx), _desc(desc), _morsels(std::move(morsels)) {
+    // `io_threads` > 0: the scan operators share a ScanExecutor of that many IO threads (the asynchronous form); 0: every
+    // pull_chunk filters its batch inline
+    GpuScanOperatorFactory(int32_t id, int32_t plan_node_id, sr_ctx* ctx, sr_scan_desc desc, std::vector<std::vector<ChunkPtr>> morsels,
+                           int io_threads = 2)
+            : SourceOperatorFactory(id, "gpu_olap_scan", plan_node_id), _ctx(ctx), _desc(desc), _morsels(std::move(morsels)),
+              _executor(io_threads > 0 ? std::make_shared<GpuScanExecutor>(io_threads) : nullptr) {
         set_degree_of_parallelism(_morsels.size());
     }
     OperatorPtr create(int32_t dop, int32_t seq) override {
-        return std::make_shared<GpuScanOperator>(this, _id, _plan_node_id, seq, _ctx, _desc, _morsels[seq]);
+        return std::make_shared<GpuScanOperator>(this, _id, _plan_node_id, seq, _ctx, _desc, _morsels[seq], _executor);
     }
+    GpuScanExecutorPtr executor() const { return _executor; }
 
 private:
     sr_ctx* _ctx;
     sr_scan_desc _desc;
     std::vector<std::vector<ChunkPtr>> _morsels;
+    GpuScanExecutorPtr _executor;
 };
 
 class GpuHashJoinerFactory { // HashJoinerFactory (hashjoin/hash_joiner_factory.cpp:57-79): prober i uses builder i % builder_dop
