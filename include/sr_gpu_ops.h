@@ -293,12 +293,13 @@ typedef enum sr_join_method {
     SR_JOIN_METHOD_LINEAR_CHAINED = 3        /* open addressing, chain of equal keys in next[]  */
 } sr_join_method;
 
-#define SR_MAX_JOIN_KEYS 2
+#define SR_MAX_JOIN_KEYS 4
 #define SR_MAX_JOIN_OUT 16
 
 typedef struct sr_join_desc {
     int32_t join_type; /* sr_join_type */
-    int32_t num_keys;  /* 1..SR_MAX_JOIN_KEYS; packed key must fit 8 bytes */
+    int32_t num_keys;  /* 1..SR_MAX_JOIN_KEYS; the packed key must fit 16 bytes (<= 8: SERIALIZED_FIXED_SIZE_INT / BIGINT, 9..16:
+                        * SERIALIZED_FIXED_SIZE_LARGEINT, join_hash_table.cpp:221-250) */
     int32_t build_key_slots[SR_MAX_JOIN_KEYS];
     int32_t probe_key_slots[SR_MAX_JOIN_KEYS];
     int32_t key_types[SR_MAX_JOIN_KEYS]; /* sr_type, integer class */

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <memory>
 #include <string>
 #include <thread>
@@ -579,6 +580,8 @@ struct orc_join {
     // HashTableProbeState::build_match_index (join_hash_map.hpp:47-48): 1 = the build row found a probe partner.  Index 0 is
     // the sentinel row, always 1.  One array for the whole join: the reference merges the probers' arrays before POST_PROBE.
     mutable std::vector<uint8_t> build_match;
+    bool wide = false;
+    std::map<std::pair<uint64_t, uint64_t>, int64_t> wide_ids; // 128-bit build key -> id
 };
 
 static const int FP_BITS = 7; // join_hash_map_method.h:137-147
@@ -604,12 +607,13 @@ extern "C" orc_join* orc_join_create(const sr_join_desc* desc, const orc_join_op
         }
         total += type_width(desc->key_types[k]);
     }
-    if (total > 8) {
-        fail(SR_ERR_NOT_SUPPORTED, "packed join key wider than 8 bytes");
+    if (total > 16) {
+        fail(SR_ERR_NOT_SUPPORTED, "packed join key wider than 16 bytes");
         return nullptr;
     }
     auto* j = new orc_join();
     j->desc = *desc;
+    j->wide = total > 8;
     if (opt) {
         j->opt = *opt;
     } else {
@@ -624,6 +628,9 @@ extern "C" orc_join* orc_join_create(const sr_join_desc* desc, const orc_join_op
     // ONE_KEY keeps the native width; several keys are serialized into the smallest of
     // int32/int64 that fits (SERIALIZED_FIXED_SIZE_INT/BIGINT, join_hash_table.cpp:225-250)
     j->key_bytes = desc->num_keys == 1 ? type_width(desc->key_types[0]) : (total <= 4 ? 4 : 8);
+    // 9..16 bytes: SERIALIZED_FIXED_SIZE_LARGEINT (join_hash_table.cpp:221-222).  The table machinery below works on 64-bit
+    // keys; a 128-bit key is INTERNED -- every distinct build key gets the next id, the id is the table key.  The pair
+    // sequence of a probe (probe order, chain by descending build index) does not depend on which hash placed the key.
     j->keys.push_back(0);
     j->key_nulls.push_back(0);
     return j;
@@ -635,9 +642,46 @@ extern "C" void orc_join_destroy(orc_join* j) {
 // pack key columns of `c` rows [r0,r0+n) into int64 (little-endian concatenation, the
 // SERIALIZED_FIXED_SIZE layout, join_key_constructor.hpp) + null flags.
 static int32_t pack_keys(const orc_join* j, const sr_chunk_view* c, const int32_t* slots, int64_t r0, int64_t n,
-                         int64_t* out, uint8_t* out_null, bool* any_null) {
+                         int64_t* out, uint8_t* out_null, bool* any_null, std::map<std::pair<uint64_t, uint64_t>, int64_t>* intern = nullptr) {
     const sr_join_desc& d = j->desc;
     *any_null = false;
+    if (j->wide) {
+        std::vector<uint64_t> lo(n, 0), hi(n, 0);
+        for (int64_t i = 0; i < n; i++) out_null[i] = 0;
+        int shift = 0;
+        for (int k = 0; k < d.num_keys; k++) {
+            const sr_col_view* col = find_col(c, slots[k]);
+            if (!col) return fail(SR_ERR_INVALID_ARGUMENT, "join key slot not in chunk");
+            const int w = type_width(col->type);
+            const uint64_t mask = w == 8 ? ~0ull : ((1ull << (8 * w)) - 1);
+            for (int64_t i = 0; i < n; i++) {
+                const uint64_t v = (uint64_t)load_int(col->data, col->type, r0 + i) & mask;
+                if (shift < 64) {
+                    lo[i] |= v << shift;
+                    if (shift + 8 * w > 64) hi[i] |= v >> (64 - shift);
+                } else {
+                    hi[i] |= v << (shift - 64);
+                }
+                if (col->nulls && col->nulls[r0 + i]) {
+                    out_null[i] = 1;
+                    *any_null = true;
+                }
+            }
+            shift += 8 * w;
+        }
+        for (int64_t i = 0; i < n; i++) {
+            const auto key = std::make_pair(lo[i], hi[i]);
+            if (intern) { // build side: a new key gets the next id
+                auto it = intern->find(key);
+                if (it == intern->end()) it = intern->emplace(key, (int64_t)intern->size()).first;
+                out[i] = it->second;
+            } else { // probe side: a key the build side never had gets an id no build row carries
+                auto it = j->wide_ids.find(key);
+                out[i] = it == j->wide_ids.end() ? -1 - i : it->second;
+            }
+        }
+        return SR_OK;
+    }
     if (d.num_keys == 1) {
         const sr_col_view* col = find_col(c, slots[0]);
         if (!col) return fail(SR_ERR_INVALID_ARGUMENT, "join key slot not in chunk");
@@ -710,7 +754,7 @@ extern "C" int32_t orc_join_append_build(orc_join* j, const sr_chunk_view* chunk
     j->keys.resize(oldk + n);
     j->key_nulls.resize(oldk + n);
     bool any = false;
-    int32_t rc = pack_keys(j, chunk, j->desc.build_key_slots, 0, n, j->keys.data() + oldk, j->key_nulls.data() + oldk, &any);
+    int32_t rc = pack_keys(j, chunk, j->desc.build_key_slots, 0, n, j->keys.data() + oldk, j->key_nulls.data() + oldk, &any, j->wide ? &j->wide_ids : nullptr);
     if (rc) return rc;
     j->keys_have_null |= any;
     j->row_count += (uint32_t)n;

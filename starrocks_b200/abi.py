@@ -62,7 +62,7 @@ REDUCE_MULHI, REDUCE_MODULO = 0, 1
 SR_MAX_OUT_COLS = 32
 SR_MAX_IN_LIST = 16
 SR_MAX_EXPR_NODES = 24
-SR_MAX_JOIN_KEYS = 2
+SR_MAX_JOIN_KEYS = 4
 SR_MAX_JOIN_OUT = 16
 SR_MAX_GROUP_KEYS = 4
 SR_MAX_AGG_FNS = 8

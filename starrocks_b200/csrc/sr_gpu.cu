@@ -423,6 +423,9 @@ sr_join* sr_join_create(sr_ctx* ctx, const sr_join_desc* desc) {
     sr_join* j = new sr_join();
     j->ctx = ctx;
     j->desc = *desc;
+    int total = 0;
+    for (int k = 0; k < desc->num_keys; k++) total += srd::type_width(desc->key_types[k]);
+    j->wide = total > 8; // SERIALIZED_FIXED_SIZE_LARGEINT (join_hash_table.cpp:221-222)
     return j;
 }
 

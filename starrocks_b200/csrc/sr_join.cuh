@@ -36,7 +36,28 @@ struct JoinDev {
     uint32_t hmask;
     uint32_t hlog;
     const uint32_t* bitmap; // range methods: bit (key - min) set when a build row has the key
+    // packed keys of 9..16 bytes (SERIALIZED_FIXED_SIZE_LARGEINT, join_hash_table.cpp:221-222): the table is keyed by a
+    // 64-bit FINGERPRINT of the 128-bit key -- a chain then holds every build row with that fingerprint, and every walk
+    // compares the full key of each entry (wide_lo / wide_hi, one pair per build row) with the probe row's
+    int32_t wide;
+    int32_t pad;
+    const unsigned long long* wide_lo;
+    const unsigned long long* wide_hi;
 };
+
+struct WideKey {
+    unsigned long long lo, hi;
+};
+__device__ __forceinline__ int64_t wide_fingerprint(const WideKey& k) {
+    unsigned long long x = k.lo ^ (k.hi * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull);
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32;
+    return (int64_t)x;
+}
+__device__ __forceinline__ bool wide_equal(const JoinDev& j, uint32_t b, const WideKey& k) {
+    return __ldg(j.wide_lo + b) == k.lo && __ldg(j.wide_hi + b) == k.hi;
+}
 
 struct KeyCols {
     DCol c[SR_MAX_JOIN_KEYS];
@@ -67,6 +88,30 @@ __device__ __forceinline__ bool pack_key(const KeyCols& kc, int64_t row, int64_t
     return nul;
 }
 
+// the same for packed keys of 9..16 bytes: little-endian concatenation of the columns into 128 bits
+__device__ __forceinline__ bool pack_key_wide(const KeyCols& kc, int64_t row, WideKey& key) {
+    key.lo = key.hi = 0;
+    int shift = 0;
+    bool nul = false;
+#pragma unroll
+    for (int q = 0; q < SR_MAX_JOIN_KEYS; q++) {
+        if (q < kc.n) {
+            const int w = kc.c[q].width;
+            const unsigned long long mask = w == 8 ? ~0ull : ((1ull << (8 * w)) - 1);
+            const unsigned long long v = (unsigned long long)load_int(kc.c[q].data, kc.c[q].type, row) & mask;
+            if (shift < 64) {
+                key.lo |= v << shift;
+                if (shift + 8 * w > 64) key.hi |= v >> (64 - shift);
+            } else {
+                key.hi |= v << (shift - 64);
+            }
+            shift += 8 * w;
+            nul |= kc.c[q].nulls != nullptr && kc.c[q].nulls[row] != 0;
+        }
+    }
+    return nul;
+}
+
 __device__ __forceinline__ uint32_t hash_slot(int64_t key, uint32_t hlog) {
     return join_key_hash64((uint64_t)key, hlog);
 }
@@ -89,11 +134,21 @@ __device__ __forceinline__ uint32_t join_lookup(const JoinDev& j, int64_t key) {
 
 // pack build keys (rows 1..n) and reduce min / max / null count
 __global__ void __launch_bounds__(256) k_join_pack_keys(KeyCols kc, int64_t n_plus1, long long* __restrict__ keys, uint8_t* __restrict__ knulls,
-                                                         long long* __restrict__ minmax /* [min, max, nulls] */) {
+                                                         long long* __restrict__ minmax /* [min, max, nulls] */, unsigned long long* __restrict__ wide_lo,
+                                                         unsigned long long* __restrict__ wide_hi) {
     long long mn = 0x7fffffffffffffffll, mx = (long long)0x8000000000000000ll, nn = 0;
     for (int64_t i = 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_plus1; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t key;
-        const bool nul = pack_key(kc, i, key);
+        bool nul;
+        if (wide_lo) { // 9..16-byte key: the table key is its fingerprint
+            WideKey wk;
+            nul = pack_key_wide(kc, i, wk);
+            wide_lo[i] = wk.lo;
+            wide_hi[i] = wk.hi;
+            key = wide_fingerprint(wk);
+        } else {
+            nul = pack_key(kc, i, key);
+        }
         keys[i] = key;
         if (knulls) knulls[i] = nul ? 1 : 0;
         if (!nul) {
@@ -203,9 +258,17 @@ __global__ void __launch_bounds__(256) k_fill_u64(unsigned long long* p, int64_t
 // number of output rows a probe row produces for the join type, given its chain head.  `match` (joins with a POST_PROBE
 // phase only): every build row of the chain is marked as matched (HashTableProbeState::build_match_index,
 // join_hash_map.hpp:1352,1492 -- plain byte stores of 1, any number of probers may race on them).
-__device__ __forceinline__ uint32_t probe_row_count(const JoinDev& j, int32_t join_type, uint32_t head, uint8_t* __restrict__ match = nullptr) {
+__device__ __forceinline__ uint32_t probe_row_count(const JoinDev& j, int32_t join_type, uint32_t head, uint8_t* __restrict__ match = nullptr,
+                                                    const WideKey* wk = nullptr) {
     uint32_t cnt = 0;
-    if (head != 0) {
+    if (wk) { // fingerprint chain: only the entries whose full key equals the probe row's count
+        for (uint32_t b = head; b != 0; b = __ldg(j.next + b)) {
+            if (wide_equal(j, b, *wk)) {
+                cnt++;
+                if (match) match[b] = 1;
+            }
+        }
+    } else if (head != 0) {
         cnt = 1;
         if (match) match[head] = 1;
         if (j.has_dup) {
@@ -380,6 +443,77 @@ __global__ void __launch_bounds__(PROBE_BLOCK) k_probe_write(JoinDev j, int32_t 
     }
 }
 
+// ---- the two probe passes for packed keys of 9..16 bytes (JoinDev::wide) -----------------------------------------------
+// Same tile geometry and output contract as k_probe_count / k_probe_write.  heads[] holds the head of the FINGERPRINT chain;
+// both passes pack the probe row's 128-bit key again and only count / emit the chain entries whose full key equals it.
+__global__ void __launch_bounds__(PROBE_BLOCK) k_probe_count_wide(JoinDev j, KeyCols kc, int32_t join_type, int64_t n, uint8_t* __restrict__ match,
+                                                                   uint32_t* __restrict__ heads, uint32_t* __restrict__ block_counts) {
+    __shared__ unsigned long long s_cnt[PROBE_BLOCK / 32];
+    const int64_t base = ((int64_t)blockIdx.x * PROBE_BLOCK + threadIdx.x) * PROBE_ROWS;
+    unsigned long long cnt = 0;
+#pragma unroll
+    for (int r = 0; r < PROBE_ROWS; r++) {
+        if (base + r >= n) continue;
+        WideKey wk;
+        uint32_t head = 0;
+        if (!pack_key_wide(kc, base + r, wk)) head = join_lookup(j, wide_fingerprint(wk));
+        heads[base + r] = head;
+        cnt += probe_row_count(j, join_type, head, match, &wk);
+    }
+    cnt = warp_sum(cnt);
+    if (lane_id() == 0) s_cnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < PROBE_BLOCK / 32; w++) t += s_cnt[w];
+        block_counts[blockIdx.x] = t > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)t;
+    }
+}
+
+__global__ void __launch_bounds__(PROBE_BLOCK) k_probe_write_wide(JoinDev j, KeyCols kc, int32_t join_type, int64_t n, const uint32_t* __restrict__ heads,
+                                                                   const uint64_t* __restrict__ block_offsets, uint32_t* __restrict__ probe_index,
+                                                                   uint32_t* __restrict__ build_index) {
+    __shared__ uint32_t s_scan[PROBE_BLOCK / 32 + 1];
+    const int64_t base = ((int64_t)blockIdx.x * PROBE_BLOCK + threadIdx.x) * PROBE_ROWS;
+    uint32_t head[PROBE_ROWS], cnt[PROBE_ROWS], mine = 0;
+    WideKey wk[PROBE_ROWS];
+#pragma unroll
+    for (int r = 0; r < PROBE_ROWS; r++) {
+        head[r] = cnt[r] = 0;
+        wk[r].lo = wk[r].hi = 0;
+        if (base + r < n) {
+            head[r] = heads[base + r];
+            if (head[r] != 0) (void)pack_key_wide(kc, base + r, wk[r]); // head != 0: no key column was NULL
+            cnt[r] = probe_row_count(j, join_type, head[r], nullptr, &wk[r]);
+        }
+        mine += cnt[r];
+    }
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan<PROBE_BLOCK>(mine, s_scan, &tot);
+    if (mine == 0) return;
+    uint64_t o = block_offsets[blockIdx.x] + ex;
+    const bool no_build = join_type == SR_JOIN_LEFT_SEMI || join_type == SR_JOIN_LEFT_ANTI;
+#pragma unroll
+    for (int r = 0; r < PROBE_ROWS; r++) {
+        if (cnt[r] == 0) continue;
+        uint32_t emitted = 0;
+        if (!no_build) {
+            for (uint32_t b = head[r]; b != 0; b = __ldg(j.next + b)) {
+                if (!wide_equal(j, b, wk[r])) continue;
+                probe_index[o] = (uint32_t)(base + r);
+                build_index[o] = b;
+                o++;
+                emitted++;
+            }
+        }
+        if (emitted == 0) { // semi / anti rows, and the NULL-padded row of an outer join
+            probe_index[o] = (uint32_t)(base + r);
+            build_index[o] = 0;
+            o++;
+        }
+    }
+}
+
 // K5 exposed for golden-vector pinning
 __global__ void __launch_bounds__(256) k_join_key_hash(const void* __restrict__ keys, int32_t type, int64_t n, uint32_t log_buckets,
                                                         uint32_t* __restrict__ out) {
@@ -419,7 +553,8 @@ struct sr_join {
     int32_t has_dup = 0;
     int64_t min_value = 0, max_value = 0, bucket_size = 0, null_keys = 0;
     uint32_t hmask = 0, hlog = 0;
-    DevBuf keys, knulls, first, next, hkeys, bitmap, flags, zero_row;
+    DevBuf keys, knulls, first, next, hkeys, bitmap, flags, zero_row, wide_lo, wide_hi;
+    bool wide = false; // packed key of 9..16 bytes
     // POST_PROBE phase (RIGHT / FULL joins): one mark byte per build row, written by every probe
     DevBuf match, remain_counts, remain_offsets, remain_index;
     bool match_ready = false;
@@ -441,6 +576,10 @@ struct sr_join {
         d.first = first.as<uint32_t>();
         d.next = next.as<uint32_t>();
         d.hkeys = hkeys.as<unsigned long long>();
+        d.wide = wide ? 1 : 0;
+        d.pad = 0;
+        d.wide_lo = wide_lo.as<unsigned long long>();
+        d.wide_hi = wide_hi.as<unsigned long long>();
         d.hmask = hmask;
         d.hlog = hlog;
         d.bitmap = bitmap.as<uint32_t>();
@@ -462,7 +601,7 @@ static int32_t join_validate_desc(sr_ctx* ctx, const sr_join_desc* d) {
         if (w == 0 || w > 8 || srd::is_float_class(d->key_types[k])) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "join key type %d", d->key_types[k]);
         total += w;
     }
-    if (total > 8) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "packed join key wider than 8 bytes");
+    if (total > 16) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "packed join key wider than 16 bytes (serialized var-length keys are not implemented)");
     if (d->num_build_out < 0 || d->num_build_out > SR_MAX_JOIN_OUT || d->num_probe_out < 0 || d->num_probe_out > SR_MAX_JOIN_OUT)
         return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "output slot count");
     return SR_OK;
@@ -568,15 +707,22 @@ static int32_t join_finish(sr_join* j) {
     SR_CUDA(ctx, cudaMemcpyAsync(j->flags.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     SR_CUDA(ctx, cudaMemsetAsync(j->keys.p, 0, 8, ctx->stream));
     const int grid = std::min(grid_for(j->rows, 256), ctx->num_sms * 8);
+    if (j->wide) {
+        SR_TRY(j->wide_lo.reserve(ctx, sizeof(uint64_t) * (size_t)n1));
+        SR_TRY(j->wide_hi.reserve(ctx, sizeof(uint64_t) * (size_t)n1));
+        SR_CUDA(ctx, cudaMemsetAsync(j->wide_lo.p, 0, 8, ctx->stream));
+        SR_CUDA(ctx, cudaMemsetAsync(j->wide_hi.p, 0, 8, ctx->stream));
+    }
     srd::k_join_pack_keys<<<grid, 256, 0, ctx->stream>>>(kc, n1, j->keys.as<long long>(), any_nullable ? j->knulls.as<uint8_t>() : nullptr,
-                                                        j->flags.as<long long>());
+                                                        j->flags.as<long long>(), j->wide ? j->wide_lo.as<unsigned long long>() : nullptr,
+                                                        j->wide ? j->wide_hi.as<unsigned long long>() : nullptr);
     SR_LAUNCH_CHECK(ctx);
     long long mm[4];
     SR_CUDA(ctx, cudaMemcpyAsync(mm, j->flags.p, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
     SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     j->null_keys = mm[2];
     const int64_t valid = j->rows - j->null_keys;
-    const bool one_key = j->desc.num_keys == 1;
+    const bool one_key = j->desc.num_keys == 1 && !j->wide;
     const int kw = srd::type_width(j->desc.key_types[0]);
     // --- method selection (JoinHashMapSelector::_determine_hash_map_method, join_hash_table.cpp:225-350,
     // with the CPU L2/L3 thresholds replaced by an HBM/L2 budget: a direct table is used while it
@@ -823,8 +969,12 @@ static int32_t join_probe(sr_join* j, int32_t prober_id, const sr_chunk_view* pr
         SR_TRY(ps.heads.reserve(ctx, sizeof(uint32_t) * (size_t)n));
         SR_TRY(ps.block_counts.reserve(ctx, sizeof(uint32_t) * (size_t)blocks));
         SR_TRY(ps.block_offsets.reserve(ctx, sizeof(uint64_t) * (size_t)blocks));
-        srd::k_probe_count<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, kc, j->desc.join_type, n, vec_keys, match, ps.heads.as<uint32_t>(),
-                                                                        ps.block_counts.as<uint32_t>());
+        if (j->wide)
+            srd::k_probe_count_wide<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, kc, j->desc.join_type, n, match, ps.heads.as<uint32_t>(),
+                                                                                 ps.block_counts.as<uint32_t>());
+        else
+            srd::k_probe_count<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, kc, j->desc.join_type, n, vec_keys, match, ps.heads.as<uint32_t>(),
+                                                                            ps.block_counts.as<uint32_t>());
         SR_LAUNCH_CHECK(ctx);
         SR_TRY(scan_counts(ctx, &ps.scan_scratch, ps.block_counts.as<uint32_t>(), blocks, ps.block_offsets.as<uint64_t>()));
         SR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->dscratch, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -835,9 +985,14 @@ static int32_t join_probe(sr_join* j, int32_t prober_id, const sr_chunk_view* pr
     SR_TRY(ps.probe_index.reserve(ctx, sizeof(uint32_t) * (size_t)std::max<int64_t>(total, 1)));
     SR_TRY(ps.build_index.reserve(ctx, sizeof(uint32_t) * (size_t)std::max<int64_t>(total, 1)));
     if (total > 0) {
-        srd::k_probe_write<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, j->desc.join_type, n, ps.heads.as<uint32_t>(),
-                                                                        ps.block_offsets.as<uint64_t>(), ps.probe_index.as<uint32_t>(),
-                                                                        ps.build_index.as<uint32_t>());
+        if (j->wide)
+            srd::k_probe_write_wide<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, kc, j->desc.join_type, n, ps.heads.as<uint32_t>(),
+                                                                                 ps.block_offsets.as<uint64_t>(), ps.probe_index.as<uint32_t>(),
+                                                                                 ps.build_index.as<uint32_t>());
+        else
+            srd::k_probe_write<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, j->desc.join_type, n, ps.heads.as<uint32_t>(),
+                                                                            ps.block_offsets.as<uint64_t>(), ps.probe_index.as<uint32_t>(),
+                                                                            ps.build_index.as<uint32_t>());
         SR_LAUNCH_CHECK(ctx);
     }
     ps.last_count = total;

@@ -26,10 +26,9 @@ struct PageDesc {
 };
 
 struct FrameDesc {
-    const uint8_t* bits; // first byte after the frame's min value
-    long long row;       // output row of the frame's first value
-    unsigned long long min_value;
-    uint32_t count;      // values in the frame (<= 128)
+    const uint8_t* frame; // the frame's min value (4 / 8 bytes LE), followed by the packed deltas
+    long long row;        // output row of the frame's first value
+    uint32_t count;       // values in the frame (<= 128)
     uint16_t format;
     uint16_t bit_width;
 };
@@ -101,21 +100,16 @@ __global__ void __launch_bounds__(FOR_FRAMES_BLOCK) k_for_frames(const PageDesc*
         if (f < nf) {
             const uint32_t cnt = f + 1 < nf ? 128u : n - f * 128u;
             FrameDesc d;
-            d.bits = pg.data + off + sizeof(T);
+            d.frame = pg.data + off;
             d.row = pg.row_off + (long long)f * 128;
             d.count = cnt;
             d.format = (uint16_t)fmt;
             d.bit_width = (uint16_t)bw;
-            d.min_value = 0;
             // the bytes this frame really holds must lie in front of the frame table
             const unsigned long long used = off + sizeof(T) + ((unsigned long long)cnt * bw + 7) / 8;
             if (fmt > 2 || bw > 8 * sizeof(T) || (long long)used > meta) {
                 atomicOr(flags, 1);
                 d.count = 0;
-            } else {
-                unsigned long long mn = 0;
-                for (int i = 0; i < (int)sizeof(T); i++) mn |= (unsigned long long)pg.data[off + i] << (8 * i);
-                d.min_value = mn;
             }
             frames[pg.frame_off + f] = d;
         }
@@ -127,7 +121,7 @@ __global__ void __launch_bounds__(FOR_FRAMES_BLOCK) k_for_frames(const PageDesc*
 
 constexpr int FOR_DECODE_BLOCK = 256;
 constexpr int FOR_DECODE_WARPS = FOR_DECODE_BLOCK / 32;
-constexpr int FOR_FRAME_WORDS = 128 * 8 / 4 + 4; // a frame's packed bits: at most 128 x 64 bits, + the words a 96-bit window may touch
+constexpr int FOR_FRAME_WORDS = 128 * 8 / 4 + 8; // a frame: min value + at most 128 x 64 bits, + the words a 96-bit window may touch
 
 // bits [b, b + bw) of the big-endian bit string in `words` (shared memory, 32-bit words as loaded from little-endian memory)
 __device__ __forceinline__ unsigned long long for_extract(const uint32_t* words, uint32_t b, uint32_t bw) {
@@ -151,24 +145,28 @@ __global__ void __launch_bounds__(FOR_DECODE_BLOCK) k_for_decode(const FrameDesc
         const uint32_t bw = d.bit_width, cnt = d.count;
         if (cnt == 0) continue; // (warp-uniform)
         U v[4] = {0, 0, 0, 0};
+        // the frame (min value + packed bytes) -> shared memory.  It starts at any byte: fetch whole words from the aligned
+        // address below it and remember the byte skew.  (The min value is read from this copy too: a separate read of it in
+        // k_for_frames cost one extra DRAM sector -- or PCIe request -- per frame.)
+        const uint32_t nbytes = (uint32_t)sizeof(T) + (cnt * bw + 7) / 8;
+        const uintptr_t a0 = (uintptr_t)d.frame & ~(uintptr_t)3;
+        const uint32_t skew = (uint32_t)((uintptr_t)d.frame - a0);
+        const uint32_t nwords = (skew + nbytes + 3) / 4;
+        __syncwarp();
+        for (uint32_t i = lane; i < nwords; i += 32) words[i] = (uint32_t)ldg_stream_s32((const uint32_t*)a0 + i);
+        for (uint32_t i = nwords + lane; i < nwords + 3; i += 32) words[i] = 0;
+        __syncwarp();
         if (bw > 0) {
-            // the frame's packed bytes -> shared memory.  The bit string starts at any byte: fetch whole words from the
-            // aligned address below it and remember the byte skew.
-            const uint32_t nbytes = (cnt * bw + 7) / 8;
-            const uintptr_t a0 = (uintptr_t)d.bits & ~(uintptr_t)3;
-            const uint32_t skew = (uint32_t)((uintptr_t)d.bits - a0);
-            const uint32_t nwords = (skew + nbytes + 3) / 4;
-            __syncwarp();
-            for (uint32_t i = lane; i < nwords; i += 32) words[i] = (uint32_t)ldg_stream_s32((const uint32_t*)a0 + i);
-            for (uint32_t i = nwords + lane; i < nwords + 3; i += 32) words[i] = 0;
-            __syncwarp();
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const uint32_t i = 4 * lane + j;
-                if (i < cnt) v[j] = (U)for_extract(words, 8 * skew + i * bw, bw);
+                if (i < cnt) v[j] = (U)for_extract(words, 8 * (skew + (uint32_t)sizeof(T)) + i * bw, bw);
             }
         }
-        const U mn = (U)d.min_value;
+        // the min value: sizeof(T) little-endian bytes at byte `skew` of the copy = a byte-swapped big-endian extraction
+        const unsigned long long mn_be = for_extract(words, 8 * skew, 8 * (uint32_t)sizeof(T));
+        const U mn = sizeof(T) == 4 ? (U)__byte_perm((uint32_t)mn_be, 0, 0x0123)
+                                    : (U)(((unsigned long long)__byte_perm((uint32_t)mn_be, 0, 0x0123) << 32) | __byte_perm((uint32_t)(mn_be >> 32), 0, 0x0123));
         if (d.format == 1) {
             // ascending: value i = min + delta_0 + ... + delta_i (decode_current_frame, frame_of_reference_coding.cpp:338-345)
             v[1] += v[0];
