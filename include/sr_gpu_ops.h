@@ -319,6 +319,14 @@ typedef struct sr_join_desc {
     /* sr_type of every probe_out_slot (0 = take it from the probed chunks): sr_join_probe_remain pads the probe columns
      * of RIGHT / FULL OUTER rows with NULLs and needs their types even when no probe chunk ever arrived */
     int32_t probe_out_types[SR_MAX_JOIN_OUT];
+    /* other-join conjunct (HashJoiner::_other_join_conjunct_ctxs, exec/hash_joiner.h:314-329; applied by
+     * JoinHashMap / HashJoinProber after the key match, hash_joiner.cpp `_process_other_conjunct`,
+     * `_process_outer_join_with_other_conjunct`, `_process_semi_join_with_other_conjunct`, ...): a boolean expression over
+     * slots of the PROBE chunk and of the BUILD chunk (slot ids of the two sides are distinct, as in the output chunk).
+     * num_nodes = 0: none.  A key-matched pair only counts when the conjunct is true (NULL = false): INNER / RIGHT OUTER
+     * emit the passing pairs, LEFT / FULL OUTER pad probe rows without a passing pair, LEFT SEMI / ANTI test "some pair
+     * passes", RIGHT / FULL joins mark build rows by passing pairs only.  Output keeps probe order. */
+    sr_expr other_conjunct;
 } sr_join_desc;
 
 typedef struct sr_join sr_join;

@@ -891,7 +891,9 @@ static int32_t select_method(orc_join* j) {
         }
         return j->opt.force_method;
     }
-    const bool semi_anti = j->desc.join_type == SR_JOIN_LEFT_SEMI || j->desc.join_type == SR_JOIN_LEFT_ANTI;
+    // the key-set methods keep no build rows: they are only chosen when no other-join conjunct has to read them
+    // (JoinHashTableItems::with_other_conjunct, join_hash_table.cpp:259-300)
+    const bool semi_anti = (j->desc.join_type == SR_JOIN_LEFT_SEMI || j->desc.join_type == SR_JOIN_LEFT_ANTI) && j->desc.other_conjunct.num_nodes == 0;
     const bool one_key = j->desc.num_keys == 1;
     if (one_key && j->key_bytes <= 2) return ORC_DIRECT_MAPPING;
     if (one_key && j->opt.enable_range_direct_mapping && j->row_count > 0) {
@@ -1089,7 +1091,7 @@ static inline bool contains_probe_row(const orc_join* j, const ProbeState& ps, u
 
 static int32_t probe_chunk_impl(const orc_join* j, ProbeState& ps, const int32_t* probe_key_slots,
                                 const sr_chunk_view* probe, int32_t first_probe, uint32_t* probe_index,
-                                uint32_t* build_index, orc_probe_result* res) {
+                                uint32_t* build_index, orc_probe_result* res, int32_t join_type_override = -1) {
     if (!j->built) return fail(SR_ERR_STATE, "probe before build");
     if (probe->num_rows > j->chunk_size) return fail(SR_ERR_INVALID_ARGUMENT, "probe chunk larger than chunk_size");
     const uint32_t chunk_size = j->chunk_size;
@@ -1119,7 +1121,7 @@ static int32_t probe_chunk_impl(const orc_join* j, ProbeState& ps, const int32_t
         res->count = (int64_t)match_count;
         ps.cur_row_match_count = 0;
     };
-    const int32_t jt = j->desc.join_type;
+    const int32_t jt = join_type_override >= 0 ? join_type_override : j->desc.join_type;
     // joins with a POST_PROBE phase mark every build row they match (join_hash_map.hpp:1352 right outer, :1492 right anti,
     // :1600 full outer)
     const bool marks = jt == SR_JOIN_RIGHT_OUTER || jt == SR_JOIN_FULL_OUTER || jt == SR_JOIN_RIGHT_SEMI || jt == SR_JOIN_RIGHT_ANTI;
@@ -1254,8 +1256,117 @@ extern "C" int32_t orc_join_probe_chunk(orc_join* j, const sr_chunk_view* probe,
     return probe_chunk_impl(j, j->ps, j->desc.probe_key_slots, probe, first_probe, probe_index, build_index, res);
 }
 
+// Other-join conjunct (HashJoiner::_other_join_conjunct_ctxs, exec/hash_joiner.h:314-329; hash_joiner.cpp
+// _process_other_conjunct / _process_outer_join_with_other_conjunct / _process_semi_join_with_other_conjunct /
+// _process_right_anti_join_with_other_conjunct ...): the key match yields candidate pairs (the INNER probe), the conjunct
+// is evaluated over each pair's probe row and build row, and the join type decides what a probe row emits: its passing
+// pairs (INNER, RIGHT OUTER), those or one NULL-padded row when none passes (LEFT / FULL OUTER), itself once when some /
+// no pair passes (LEFT SEMI / ANTI), nothing (RIGHT SEMI / ANTI); RIGHT / FULL joins mark the build rows of passing pairs.
+static int64_t probe_all_with_conjunct(orc_join* j, const sr_chunk_view* probe, uint32_t* probe_index, uint32_t* build_index, int64_t cap) {
+    std::vector<uint32_t> cpi, cbi;
+    {
+        std::vector<uint32_t> pi(j->chunk_size + 8), bi(j->chunk_size + 8);
+        std::vector<sr_col_view> cols(probe->num_cols);
+        for (int64_t r0 = 0; r0 < probe->num_rows; r0 += j->chunk_size) {
+            const int64_t n = std::min<int64_t>(j->chunk_size, probe->num_rows - r0);
+            for (int k = 0; k < probe->num_cols; k++) {
+                cols[k] = probe->cols[k];
+                cols[k].data = (const uint8_t*)cols[k].data + r0 * type_width(cols[k].type);
+                if (cols[k].nulls) cols[k].nulls += r0;
+            }
+            sr_chunk_view sub{cols.data(), probe->num_cols, SR_MEM_HOST, n};
+            int32_t first = 1;
+            while (true) {
+                orc_probe_result res{};
+                int32_t rc = probe_chunk_impl(j, j->ps, j->desc.probe_key_slots, &sub, first, pi.data(), bi.data(), &res, SR_JOIN_INNER);
+                if (rc) return rc;
+                for (int64_t q = 0; q < res.count; q++) {
+                    cpi.push_back((uint32_t)(pi[q] + r0));
+                    cbi.push_back(bi[q]);
+                }
+                if (!res.has_remain) break;
+                first = 0;
+            }
+        }
+    }
+    const int64_t nc = (int64_t)cpi.size();
+    // the candidate pairs as a chunk of the columns the conjunct reads
+    const sr_expr& e = j->desc.other_conjunct;
+    std::vector<std::vector<uint8_t>> data, nulls;
+    std::vector<sr_col_view> pcols;
+    for (int k = 0; k < e.num_nodes; k++) {
+        if (e.nodes[k].op != SR_EX_COL) continue;
+        const int32_t slot = e.nodes[k].slot_id;
+        bool seen = false;
+        for (auto& c : pcols) seen |= c.slot_id == slot;
+        if (seen) continue;
+        const sr_col_view* pc = find_col(probe, slot);
+        const OwnedCol* oc = nullptr;
+        for (auto& c : j->build_cols)
+            if (c.slot == slot) oc = &c;
+        if (!pc && !oc) return fail(SR_ERR_INVALID_ARGUMENT, "other-join conjunct slot is in neither chunk");
+        const int32_t type = pc ? pc->type : oc->type;
+        const int w = type_width(type);
+        data.emplace_back((size_t)std::max<int64_t>(nc, 1) * w);
+        nulls.emplace_back((size_t)std::max<int64_t>(nc, 1), 0);
+        for (int64_t c = 0; c < nc; c++) {
+            if (pc) {
+                memcpy(data.back().data() + c * w, (const uint8_t*)pc->data + (size_t)cpi[c] * w, w);
+                nulls.back()[c] = pc->nulls ? pc->nulls[cpi[c]] : 0;
+            } else {
+                memcpy(data.back().data() + c * w, oc->data.data() + (size_t)cbi[c] * w, w);
+                nulls.back()[c] = oc->nullable ? oc->nulls[cbi[c]] : 0;
+            }
+        }
+        sr_col_view v;
+        v.data = nullptr; // set below: the vectors may still move
+        v.nulls = nullptr;
+        v.type = type;
+        v.slot_id = slot;
+        pcols.push_back(v);
+    }
+    for (size_t k = 0; k < pcols.size(); k++) {
+        pcols[k].data = data[k].data();
+        pcols[k].nulls = nulls[k].data();
+    }
+    std::vector<uint8_t> pass((size_t)nc, 0);
+    if (nc > 0) {
+        sr_chunk_view pairs{pcols.data(), (int32_t)pcols.size(), SR_MEM_HOST, nc};
+        ExprVal v;
+        int32_t rc = eval_expr_range(&e, &pairs, 0, nc, &v);
+        if (rc) return rc;
+        if (v.is_double) return fail(SR_ERR_INVALID_ARGUMENT, "the other-join conjunct is not boolean");
+        for (int64_t c = 0; c < nc; c++) pass[c] = !v.nul[c] && v.iv[c] != 0;
+    }
+    const int32_t jt = j->desc.join_type;
+    const bool marks = jt == SR_JOIN_RIGHT_OUTER || jt == SR_JOIN_FULL_OUTER || jt == SR_JOIN_RIGHT_SEMI || jt == SR_JOIN_RIGHT_ANTI;
+    const bool pairs_out = jt == SR_JOIN_INNER || jt == SR_JOIN_LEFT_OUTER || jt == SR_JOIN_RIGHT_OUTER || jt == SR_JOIN_FULL_OUTER;
+    int64_t total = 0;
+    auto emit = [&](uint32_t p, uint32_t b) {
+        if (total < cap) {
+            probe_index[total] = p;
+            build_index[total] = b;
+        }
+        total++;
+    };
+    int64_t c = 0;
+    for (int64_t i = 0; i < probe->num_rows; i++) {
+        bool any = false;
+        for (; c < nc && (int64_t)cpi[c] == i; c++) {
+            if (!pass[c]) continue;
+            any = true;
+            if (marks) j->build_match[cbi[c]] = 1;
+            if (pairs_out) emit((uint32_t)i, cbi[c]);
+        }
+        if ((jt == SR_JOIN_LEFT_OUTER || jt == SR_JOIN_FULL_OUTER || jt == SR_JOIN_LEFT_ANTI) && !any) emit((uint32_t)i, 0);
+        if (jt == SR_JOIN_LEFT_SEMI && any) emit((uint32_t)i, 0);
+    }
+    return total > cap ? -total : total;
+}
+
 extern "C" int64_t orc_join_probe_all(orc_join* j, const sr_chunk_view* probe, uint32_t* probe_index,
                                       uint32_t* build_index, int64_t cap) {
+    if (j->desc.other_conjunct.num_nodes > 0) return probe_all_with_conjunct(j, probe, probe_index, build_index, cap);
     std::vector<uint32_t> pi(j->chunk_size + 8), bi(j->chunk_size + 8);
     std::vector<sr_col_view> cols(probe->num_cols);
     int64_t total = 0;

@@ -116,7 +116,8 @@ class sr_join_desc(C.Structure):
                 ("num_build_out", C.c_int32), ("build_out_slots", C.c_int32 * SR_MAX_JOIN_OUT),
                 ("num_probe_out", C.c_int32), ("probe_out_slots", C.c_int32 * SR_MAX_JOIN_OUT),
                 ("enable_range_direct_mapping", C.c_int32), ("reserved", C.c_int32),
-                ("build_out_types", C.c_int32 * SR_MAX_JOIN_OUT), ("probe_out_types", C.c_int32 * SR_MAX_JOIN_OUT)]
+                ("build_out_types", C.c_int32 * SR_MAX_JOIN_OUT), ("probe_out_types", C.c_int32 * SR_MAX_JOIN_OUT),
+                ("other_conjunct", sr_expr)]
 
 
 PAGE_PLAIN, PAGE_FOR = 0, 1
@@ -312,7 +313,8 @@ class ScanDesc:
         return C.byref(self.desc)
 
 
-def make_join_desc(join_type, build_keys, probe_keys, key_types, build_out=(), probe_out=(), enable_rdm=True, build_out_types=(), probe_out_types=()):
+def make_join_desc(join_type, build_keys, probe_keys, key_types, build_out=(), probe_out=(), enable_rdm=True, build_out_types=(), probe_out_types=(),
+                   other_conjunct=None):
     d = sr_join_desc()
     d.join_type = join_type
     d.num_keys = len(build_keys)
@@ -331,6 +333,8 @@ def make_join_desc(join_type, build_keys, probe_keys, key_types, build_out=(), p
         d.build_out_types[k] = t
     for k, t in enumerate(probe_out_types):
         d.probe_out_types[k] = t
+    if other_conjunct is not None:
+        d.other_conjunct = make_expr(other_conjunct)
     return d
 
 

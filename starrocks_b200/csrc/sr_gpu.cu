@@ -1124,6 +1124,10 @@ sr_fragment* sr_fragment_create(sr_ctx* ctx, const sr_fragment_desc* desc) {
             sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "fused fragment supports INNER / LEFT SEMI joins (join %d is type %d)", j, fj.join->desc.join_type);
             return nullptr;
         }
+        if (fj.join->desc.other_conjunct.num_nodes > 0) {
+            sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "fused fragment: join %d has an other-join conjunct; use the per-operator path", j);
+            return nullptr;
+        }
         if (fj.join->desc.num_keys != 1) {
             sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "fused fragment supports single-column join keys (join %d)", j);
             return nullptr;

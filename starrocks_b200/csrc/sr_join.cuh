@@ -18,6 +18,8 @@
 //    atomicCAS on the key word; the multiplicative JoinKeyHash picks the start slot.
 #pragma once
 
+#include <cub/device/device_scan.cuh>       // prefix sums of the other-join-conjunct emit flags
+#include <cub/iterator/transform_input_iterator.cuh>
 #include <cub/device/device_radix_sort.cuh> // stable (bucket, row) sort for the deterministic-chain pass of the build (cold path)
 
 #include "sr_scan.cuh"
@@ -514,6 +516,85 @@ __global__ void __launch_bounds__(PROBE_BLOCK) k_probe_write_wide(JoinDev j, Key
     }
 }
 
+// ---- other-join conjunct ------------------------------------------------------------------------------------------------
+// (HashJoiner::_other_join_conjunct_ctxs, exec/hash_joiner.h:314-329.)  The key match produces CANDIDATE pairs (the INNER
+// form of the two passes above, in probe order); the conjunct is evaluated per candidate over the probe row and the build
+// row; what is emitted then depends on the join type (see sr_join_desc.other_conjunct).
+struct PairLoader {
+    const VTab& vt;
+    int64_t prow, brow;
+    __device__ __forceinline__ bool load(int id, int64_t& bits) const {
+        const VDesc& d = vt.v[id];
+        const int64_t row = d.src < 0 ? prow : brow;
+        const bool nul = d.nulls != nullptr && d.nulls[row] != 0;
+        bits = is_float_class(d.type) ? __double_as_longlong(load_double(d.data, d.type, row)) : load_int(d.data, d.type, row);
+        return nul;
+    }
+};
+
+// keep[c] = the conjunct holds for candidate c; probe_any[i] = some candidate of probe row i passed; match[b] (RIGHT / FULL
+// joins) = build row b has a passing partner
+__global__ void __launch_bounds__(256) k_conj_eval(const __grid_constant__ VTab vt, const __grid_constant__ CExpr conj, const uint32_t* __restrict__ pi,
+                                                    const uint32_t* __restrict__ bi, int64_t ncand, uint8_t* __restrict__ keep, uint8_t* __restrict__ probe_any,
+                                                    uint8_t* __restrict__ match) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncand; c += (int64_t)gridDim.x * blockDim.x) {
+        PairLoader ld{vt, (int64_t)pi[c], (int64_t)bi[c]};
+        int64_t bits;
+        const bool nul = eval_expr(conj, ld, bits);
+        const bool pass = !nul && bits != 0;
+        keep[c] = pass ? 1 : 0;
+        if (pass) {
+            probe_any[pi[c]] = 1;
+            if (match) match[bi[c]] = 1;
+        }
+    }
+}
+// which candidates and which probe rows appear in the output
+__global__ void __launch_bounds__(256) k_conj_flags(int32_t join_type, int64_t ncand, int64_t n, uint8_t* __restrict__ keep /* in: passed, out: emit */,
+                                                     uint8_t* __restrict__ probe_any /* in: any passed, out: emit the row by itself */) {
+    const bool pairs = join_type == SR_JOIN_INNER || join_type == SR_JOIN_LEFT_OUTER || join_type == SR_JOIN_RIGHT_OUTER || join_type == SR_JOIN_FULL_OUTER;
+    const bool row_if_none = join_type == SR_JOIN_LEFT_OUTER || join_type == SR_JOIN_FULL_OUTER || join_type == SR_JOIN_LEFT_ANTI;
+    const bool row_if_any = join_type == SR_JOIN_LEFT_SEMI;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncand + n + 2; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i <= ncand) {
+            keep[i] = (i < ncand && pairs) ? keep[i] : 0; // entry ncand: the scan's total lands behind it
+        } else {
+            const int64_t r = i - ncand - 1;
+            const uint8_t any = r < n ? probe_any[r] : 0;
+            probe_any[r] = (r < n && ((row_if_none && !any) || (row_if_any && any))) ? 1 : 0;
+        }
+    }
+}
+// ordered merge of the kept candidates and the stand-alone probe rows: a kept candidate c lands behind the kept candidates
+// before it (K[c]) and the stand-alone rows of smaller probe index (U[pi[c]]); a stand-alone row i behind the kept
+// candidates of smaller probe index (K[first candidate with probe index >= i]) and the stand-alone rows before it (U[i])
+__global__ void __launch_bounds__(256) k_conj_emit(const uint8_t* __restrict__ keep, const uint8_t* __restrict__ row_emit, const uint32_t* __restrict__ K,
+                                                    const uint32_t* __restrict__ U, const uint32_t* __restrict__ pi, const uint32_t* __restrict__ bi, int64_t ncand,
+                                                    int64_t n, uint32_t* __restrict__ out_pi, uint32_t* __restrict__ out_bi) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncand + n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < ncand) {
+            if (!keep[i]) continue;
+            const uint64_t o = (uint64_t)K[i] + U[pi[i]];
+            out_pi[o] = pi[i];
+            out_bi[o] = bi[i];
+        } else {
+            const int64_t r = i - ncand;
+            if (!row_emit[r]) continue;
+            int64_t lo = 0, hi = ncand; // first candidate whose probe index is >= r
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if ((int64_t)pi[mid] < r) lo = mid + 1; else hi = mid;
+            }
+            const uint64_t o = (uint64_t)K[lo] + U[r];
+            out_pi[o] = (uint32_t)r;
+            out_bi[o] = 0;
+        }
+    }
+}
+struct U8ToU32 {
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint8_t& v) const { return v; }
+};
+
 // K5 exposed for golden-vector pinning
 __global__ void __launch_bounds__(256) k_join_key_hash(const void* __restrict__ keys, int32_t type, int64_t n, uint32_t log_buckets,
                                                         uint32_t* __restrict__ out) {
@@ -537,6 +618,7 @@ struct BuildCol {
 struct ProberState {
     Staged staged;
     DevBuf heads, block_counts, block_offsets, probe_index, build_index;
+    DevBuf conj_keep, conj_any, conj_k, conj_u, conj_tmp, conj_pi, conj_bi; // other-join conjunct: flags, their prefix sums, final pairs
     ScanScratch scan_scratch;
     std::vector<DevBuf> out_bufs;
     int64_t last_count = 0;
@@ -555,6 +637,9 @@ struct sr_join {
     uint32_t hmask = 0, hlog = 0;
     DevBuf keys, knulls, first, next, hkeys, bitmap, flags, zero_row, wide_lo, wide_hi;
     bool wide = false; // packed key of 9..16 bytes
+    bool conj_compiled = false;
+    VReg conj_reg;
+    srd::CExpr conj;
     // POST_PROBE phase (RIGHT / FULL joins): one mark byte per build row, written by every probe
     DevBuf match, remain_counts, remain_offsets, remain_index;
     bool match_ready = false;
@@ -937,6 +1022,86 @@ static int32_t join_probe_remain(sr_join* j, sr_chunk_out* out) {
     return SR_OK;
 }
 
+struct ConjTypeCtx {
+    sr_join* j;
+    const Staged* probe;
+};
+static int32_t conj_slot_type(void* user, int32_t slot) {
+    ConjTypeCtx* t = (ConjTypeCtx*)user;
+    const int c = t->probe->find(slot);
+    if (c >= 0) return t->probe->cols[c].type;
+    const BuildCol* bc = t->j->find_col(slot);
+    return bc ? bc->type : 0;
+}
+
+// candidates (ps.probe_index / ps.build_index, `*total` of them, probe order) -> the join type's output pairs
+static int32_t join_apply_conjunct(sr_join* j, ProberState& ps, int64_t n, int64_t* total, uint8_t* match) {
+    sr_ctx* ctx = j->ctx;
+    const int64_t ncand = *total;
+    ConjTypeCtx tc{j, &ps.staged};
+    if (!j->conj_compiled) {
+        j->conj_reg = VReg();
+        SR_TRY(compile_expr(ctx, &j->desc.other_conjunct, &j->conj_reg, conj_slot_type, &tc, &j->conj));
+        if (j->conj.result_is_double) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "the other-join conjunct is not boolean");
+        if (j->conj_reg.slots.size() > SR_MAX_VALUES) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "other-join conjunct over too many columns");
+        j->conj_compiled = true;
+    }
+    VTab vt;
+    memset(&vt, 0, sizeof(vt));
+    vt.n = (int32_t)j->conj_reg.slots.size();
+    for (size_t k = 0; k < j->conj_reg.slots.size(); k++) {
+        const int32_t slot = j->conj_reg.slots[k];
+        const int c = ps.staged.find(slot);
+        if (c >= 0) {
+            vt.v[k] = VDesc{ps.staged.cols[c].data, ps.staged.cols[c].nulls, ps.staged.cols[c].type, -1};
+        } else {
+            const BuildCol* bc = j->find_col(slot);
+            if (!bc) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "other-join conjunct: slot %d is in neither chunk", slot);
+            vt.v[k] = VDesc{bc->data.p, bc->nullable ? (const uint8_t*)bc->nulls.p : nullptr, bc->type, 0};
+        }
+        if (vt.v[k].type != j->conj_reg.types[k]) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "other-join conjunct: slot %d changed type", slot);
+    }
+    SR_TRY(ps.conj_keep.reserve(ctx, (size_t)ncand + 16));
+    SR_TRY(ps.conj_any.reserve(ctx, (size_t)n + 16));
+    SR_TRY(ps.conj_k.reserve(ctx, sizeof(uint32_t) * ((size_t)ncand + 2)));
+    SR_TRY(ps.conj_u.reserve(ctx, sizeof(uint32_t) * ((size_t)n + 2)));
+    SR_CUDA(ctx, cudaMemsetAsync(ps.conj_any.p, 0, (size_t)n + 16, ctx->stream));
+    const int grid = std::min(grid_for(std::max<int64_t>(ncand + n + 2, 1), 256), ctx->num_sms * 16);
+    if (ncand > 0) {
+        srd::k_conj_eval<<<grid, 256, 0, ctx->stream>>>(vt, j->conj, ps.probe_index.as<uint32_t>(), ps.build_index.as<uint32_t>(), ncand, ps.conj_keep.as<uint8_t>(),
+                                                       ps.conj_any.as<uint8_t>(), match);
+        SR_LAUNCH_CHECK(ctx);
+    }
+    srd::k_conj_flags<<<grid, 256, 0, ctx->stream>>>(j->desc.join_type, ncand, n, ps.conj_keep.as<uint8_t>(), ps.conj_any.as<uint8_t>());
+    SR_LAUNCH_CHECK(ctx);
+    // exclusive prefix sums over ncand + 1 / n + 1 flags (the last flag is 0: its sum is the total)
+    cub::TransformInputIterator<uint32_t, srd::U8ToU32, const uint8_t*> kin(ps.conj_keep.as<uint8_t>(), srd::U8ToU32()), uin(ps.conj_any.as<uint8_t>(), srd::U8ToU32());
+    size_t tb1 = 0, tb2 = 0;
+    SR_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb1, kin, ps.conj_k.as<uint32_t>(), (int)(ncand + 1), ctx->stream));
+    SR_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb2, uin, ps.conj_u.as<uint32_t>(), (int)(n + 1), ctx->stream));
+    SR_TRY(ps.conj_tmp.reserve(ctx, std::max<size_t>(std::max(tb1, tb2), 16)));
+    SR_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ps.conj_tmp.p, tb1, kin, ps.conj_k.as<uint32_t>(), (int)(ncand + 1), ctx->stream));
+    SR_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ps.conj_tmp.p, tb2, uin, ps.conj_u.as<uint32_t>(), (int)(n + 1), ctx->stream));
+    uint32_t* pin = (uint32_t*)ctx->pinned;
+    SR_CUDA(ctx, cudaMemcpyAsync(pin, ps.conj_k.as<uint32_t>() + ncand, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SR_CUDA(ctx, cudaMemcpyAsync(pin + 1, ps.conj_u.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t out_total = (int64_t)pin[0] + (int64_t)pin[1];
+    if (out_total >= 0xFFFFFFF0ll) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "join output of more than 2^32 rows in one batch; probe in smaller batches");
+    SR_TRY(ps.conj_pi.reserve(ctx, sizeof(uint32_t) * (size_t)std::max<int64_t>(out_total, 1)));
+    SR_TRY(ps.conj_bi.reserve(ctx, sizeof(uint32_t) * (size_t)std::max<int64_t>(out_total, 1)));
+    if (out_total > 0) {
+        srd::k_conj_emit<<<grid, 256, 0, ctx->stream>>>(ps.conj_keep.as<uint8_t>(), ps.conj_any.as<uint8_t>(), ps.conj_k.as<uint32_t>(), ps.conj_u.as<uint32_t>(),
+                                                       ps.probe_index.as<uint32_t>(), ps.build_index.as<uint32_t>(), ncand, n, ps.conj_pi.as<uint32_t>(),
+                                                       ps.conj_bi.as<uint32_t>());
+        SR_LAUNCH_CHECK(ctx);
+    }
+    std::swap(ps.probe_index, ps.conj_pi);
+    std::swap(ps.build_index, ps.conj_bi);
+    *total = out_total;
+    return SR_OK;
+}
+
 static int32_t join_probe(sr_join* j, int32_t prober_id, const sr_chunk_view* probe, sr_chunk_out* out) {
     sr_ctx* ctx = j->ctx;
     if (!j->built) return sr_fail(ctx, SR_ERR_STATE, "probe before build_finish");
@@ -964,16 +1129,21 @@ static int32_t join_probe(sr_join* j, int32_t prober_id, const sr_chunk_view* pr
             if (c >= 0) j->probe_types_seen[k] = ps.staged.cols[c].type;
         }
     }
+    // with an other-join conjunct the two passes produce the key-matched CANDIDATES (INNER form, nothing marked); the
+    // conjunct pass below turns them into the join type's output
+    const bool has_conj = j->desc.other_conjunct.num_nodes > 0;
+    const int32_t jt_run = has_conj ? (int32_t)SR_JOIN_INNER : j->desc.join_type;
+    uint8_t* const match_run = has_conj ? nullptr : match;
     int64_t total = 0;
     if (n > 0) {
         SR_TRY(ps.heads.reserve(ctx, sizeof(uint32_t) * (size_t)n));
         SR_TRY(ps.block_counts.reserve(ctx, sizeof(uint32_t) * (size_t)blocks));
         SR_TRY(ps.block_offsets.reserve(ctx, sizeof(uint64_t) * (size_t)blocks));
         if (j->wide)
-            srd::k_probe_count_wide<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, kc, j->desc.join_type, n, match, ps.heads.as<uint32_t>(),
+            srd::k_probe_count_wide<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, kc, jt_run, n, match_run, ps.heads.as<uint32_t>(),
                                                                                  ps.block_counts.as<uint32_t>());
         else
-            srd::k_probe_count<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, kc, j->desc.join_type, n, vec_keys, match, ps.heads.as<uint32_t>(),
+            srd::k_probe_count<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, kc, jt_run, n, vec_keys, match_run, ps.heads.as<uint32_t>(),
                                                                             ps.block_counts.as<uint32_t>());
         SR_LAUNCH_CHECK(ctx);
         SR_TRY(scan_counts(ctx, &ps.scan_scratch, ps.block_counts.as<uint32_t>(), blocks, ps.block_offsets.as<uint64_t>()));
@@ -986,15 +1156,16 @@ static int32_t join_probe(sr_join* j, int32_t prober_id, const sr_chunk_view* pr
     SR_TRY(ps.build_index.reserve(ctx, sizeof(uint32_t) * (size_t)std::max<int64_t>(total, 1)));
     if (total > 0) {
         if (j->wide)
-            srd::k_probe_write_wide<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, kc, j->desc.join_type, n, ps.heads.as<uint32_t>(),
+            srd::k_probe_write_wide<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, kc, jt_run, n, ps.heads.as<uint32_t>(),
                                                                                  ps.block_offsets.as<uint64_t>(), ps.probe_index.as<uint32_t>(),
                                                                                  ps.build_index.as<uint32_t>());
         else
-            srd::k_probe_write<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, j->desc.join_type, n, ps.heads.as<uint32_t>(),
+            srd::k_probe_write<<<blocks, srd::PROBE_BLOCK, 0, ctx->stream>>>(jd, jt_run, n, ps.heads.as<uint32_t>(),
                                                                             ps.block_offsets.as<uint64_t>(), ps.probe_index.as<uint32_t>(),
                                                                             ps.build_index.as<uint32_t>());
         SR_LAUNCH_CHECK(ctx);
     }
+    if (has_conj) SR_TRY(join_apply_conjunct(j, ps, n, &total, match));
     ps.last_count = total;
     // materialise output columns: probe_out_slots (gather by probe_index) then build_out_slots
     const int32_t jt = j->desc.join_type;

@@ -140,8 +140,13 @@ __global__ void __launch_bounds__(FOR_DECODE_BLOCK) k_for_decode(const FrameDesc
     typedef typename std::make_unsigned<T>::type U;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t* words = s_words[wid];
-    for (long long f = (long long)blockIdx.x * FOR_DECODE_WARPS + wid; f < num_frames; f += (long long)gridDim.x * FOR_DECODE_WARPS) {
-        const FrameDesc d = frames[f];
+    const long long stride = (long long)gridDim.x * FOR_DECODE_WARPS;
+    long long f = (long long)blockIdx.x * FOR_DECODE_WARPS + wid;
+    FrameDesc nd;
+    if (f < num_frames) nd = frames[f];
+    for (; f < num_frames; f += stride) {
+        const FrameDesc d = nd;
+        if (f + stride < num_frames) nd = frames[f + stride]; // the next descriptor travels while this frame is decoded
         const uint32_t bw = d.bit_width, cnt = d.count;
         if (cnt == 0) continue; // (warp-uniform)
         U v[4] = {0, 0, 0, 0};

@@ -225,6 +225,32 @@ def test_join_parity(gpu, ctx, oracle, join_type, kind):
     _join_pairs(gpu, ctx, oracle, d, builds, probe, expect_method=expect)
 
 
+@pytest.mark.parametrize("join_type", JOIN_TYPES)
+@pytest.mark.parametrize("shape", ["dups_int", "nullable_mixed_types"])
+def test_join_other_conjunct_parity(gpu, ctx, oracle, join_type, shape):
+    # other-join conjunct (exec/hash_joiner.h:314-329): key-matched pairs only count when the expression over the probe row
+    # and the build row is true; every join type, duplicate chains, NULLs on either side of the expression (NULL = false)
+    rng = np.random.default_rng(41)
+    nb, npr = 3000, 15_001
+    bkey = rng.integers(0, 500, nb, dtype=np.int32)
+    pkey = rng.integers(-20, 560, npr, dtype=np.int32)
+    if shape == "dups_int":
+        bval, pval = rng.integers(0, 100, nb, dtype=np.int32), rng.integers(0, 100, npr, dtype=np.int32)
+        bvn = pvn = None
+        conj = [("col", 1), ("col", 11), "<"]
+    else:
+        bval, pval = rng.normal(size=nb), rng.integers(-3, 3, npr, dtype=np.int64)
+        bvn, pvn = rand_nulls(rng, nb, 0.1), rand_nulls(rng, npr, 0.1)
+        conj = [("col", 1), "todouble", ("col", 11), ">", ("col", 0), ("i", 100), "<", "or"]
+    d = abi.make_join_desc(join_type, [10], [0], [abi.TYPE_INT], build_out=[11, 10], probe_out=[0, 1], other_conjunct=conj)
+    builds = [Chunk([(10, bkey[:1000].copy(), None), (11, bval[:1000].copy(), None if bvn is None else bvn[:1000].copy())]),
+              Chunk([(10, bkey[1000:].copy(), None), (11, bval[1000:].copy(), None if bvn is None else bvn[1000:].copy())])]
+    probe = Chunk([(0, pkey, rand_nulls(rng, npr, 0.02)), (1, pval, pvn)])
+    _, n = _join_pairs(gpu, ctx, oracle, d, builds, probe)
+    if join_type in (abi.JOIN_INNER, abi.JOIN_LEFT_OUTER, abi.JOIN_LEFT_SEMI, abi.JOIN_LEFT_ANTI, abi.JOIN_FULL_OUTER):
+        assert n > 0
+
+
 def test_join_one_key_golden(gpu, ctx):
     # be/test/exec/join_hash_map_test.cpp:2042-2088 OneKeyJoinHashTable through the CUDA path
     d = abi.make_join_desc(abi.JOIN_INNER, [3], [0], [abi.TYPE_INT], build_out=[3, 4, 5], probe_out=[0, 1, 2])

@@ -728,3 +728,23 @@ def test_right_and_full_join_post_probe_known_answers(oracle):
             assert rem[0][0] == 1 and rem[0][2].tolist() == [1] * len(remain_pay)      # probe column: all NULL
         else:
             assert len(rem) == 1
+
+
+def test_other_join_conjunct_known_answers(oracle):
+    # build (key, b): (1, 5) (1, 9) (2, 7) (3, 1); probe (key, a): (1, 6) (2, 8) (4, 0) (3, 0).  Conjunct a < b.
+    # candidates by key: p0-{b2 (9), b1 (5)}, p1-{b3 (7)}, p3-{b4 (1)}; passing: p0-b2 (6 < 9) and p3-b4 (0 < 1).
+    build = Chunk([(10, np.array([1, 1, 2, 3], dtype=np.int32), None), (11, np.array([5, 9, 7, 1], dtype=np.int32), None)])
+    probe = Chunk([(0, np.array([1, 2, 4, 3], dtype=np.int32), None), (1, np.array([6, 8, 0, 0], dtype=np.int32), None)])
+    conj = [("col", 1), ("col", 11), "<"]
+    exp = {abi.JOIN_INNER: [(0, 2), (3, 4)], abi.JOIN_LEFT_OUTER: [(0, 2), (1, 0), (2, 0), (3, 4)], abi.JOIN_LEFT_SEMI: [(0, 0), (3, 0)],
+           abi.JOIN_LEFT_ANTI: [(1, 0), (2, 0)], abi.JOIN_RIGHT_OUTER: [(0, 2), (3, 4)], abi.JOIN_FULL_OUTER: [(0, 2), (1, 0), (2, 0), (3, 4)],
+           abi.JOIN_RIGHT_ANTI: [], abi.JOIN_RIGHT_SEMI: []}
+    remain = {abi.JOIN_RIGHT_OUTER: [5, 7], abi.JOIN_FULL_OUTER: [5, 7], abi.JOIN_RIGHT_ANTI: [5, 7], abi.JOIN_RIGHT_SEMI: [9, 1]}
+    for jt, pairs in exp.items():
+        j = oracle.Join(abi.make_join_desc(jt, [10], [0], [abi.TYPE_INT], build_out=[11], probe_out=[1], other_conjunct=conj))
+        j.append_build(build)
+        j.build()
+        pi, bi = j.probe_all(probe)
+        assert list(zip(pi.tolist(), bi.tolist())) == pairs, jt
+        if jt in remain:
+            assert j.probe_remain([abi.TYPE_INT])[-1][1].tolist() == remain[jt], jt
