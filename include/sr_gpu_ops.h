@@ -521,6 +521,12 @@ int32_t sr_agg_two_phase_descs(const sr_agg_desc* desc, sr_agg_desc* phase1, sr_
  * negative = sr_status. */
 int64_t sr_agg_current_groups(sr_agg* agg);
 int32_t sr_agg_convert_to_states(sr_agg* agg, const sr_chunk_view* chunk, sr_chunk_out* out);
+/* SELECTIVE_PREAGG leg (AggregateStreamingSinkOperator::_push_chunk_by_selective_preaggregation,
+ * aggregate_streaming_sink_operator.cpp:173-210: build_hash_map_with_selection, compute_batch_agg_states_with_selection,
+ * output_chunk_by_streaming_with_selection): rows whose group is already in the table are aggregated into it; the others
+ * create no group and come back in `out` as intermediate rows (the format of sr_agg_convert_to_states), in input order.
+ * `out` is owned by the aggregate (valid until its next call). */
+int32_t sr_agg_push_selective(sr_agg* agg, const sr_chunk_view* chunk, sr_chunk_out* out);
 
 /* Element-wise mergeable view of a DENSE aggregate table (group-by columns with declared ranges, or no
  * GROUP BY): one array per state component, every array indexed by the same slot number on every

@@ -338,6 +338,15 @@ class Agg:
     def merge(self, other):
         _check(lib().orc_agg_merge(self.h, other.h))
 
+    def streaming_selection(self, chunk):
+        """build_hash_map_with_selection: uint8 per row, 1 = the row's group is not in the table"""
+        sel = np.zeros(chunk.num_rows, dtype=np.uint8)
+        L = lib()
+        L.orc_agg_streaming_selection.restype = C.c_int32
+        L.orc_agg_streaming_selection.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _check(L.orc_agg_streaming_selection(self.h, chunk.ref(), sel.ctypes.data if sel.size else None))
+        return sel
+
     @property
     def num_groups(self):
         return lib().orc_agg_num_groups(self.h)

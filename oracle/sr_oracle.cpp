@@ -1766,6 +1766,42 @@ static int32_t agg_push_range(orc_agg* a, const sr_chunk_view* c, int64_t r0, in
     return SR_OK;
 }
 
+// Aggregator::build_hash_map_with_selection (aggregator.cpp, agg_hash_map.h:303-361 compute_agg_states with
+// allocate_and_compute_state = false): selection[i] = 1 when row i's group is NOT in the hash map (the row will be streamed),
+// 0 when it is; the map is not changed.
+extern "C" int32_t orc_agg_streaming_selection(const orc_agg* a, const sr_chunk_view* c, uint8_t* selection) {
+    const sr_agg_desc& d = a->desc;
+    const sr_col_view* kc[SR_MAX_GROUP_KEYS];
+    for (int k = 0; k < d.num_group_keys; k++) {
+        kc[k] = find_col(c, d.group_slots[k]);
+        if (!kc[k]) return fail(SR_ERR_INVALID_ARGUMENT, "group slot not in chunk");
+    }
+    for (int64_t i = 0; i < c->num_rows; i++) {
+        if (d.num_group_keys == 0) {
+            selection[i] = 0;
+            continue;
+        }
+        Key128 key;
+        for (int k = 0; k < d.num_group_keys; k++) {
+            if (kc[k]->nulls && kc[k]->nulls[i])
+                key_set_null(&key, k);
+            else
+                key_put(&key, a->key_off_bits[k], a->key_width[k], (uint64_t)load_int(kc[k]->data, kc[k]->type, i));
+        }
+        uint64_t s = mix64(key.lo ^ mix64(key.hi + key.nul)) & a->cap_mask;
+        bool found = false;
+        while (a->slot_group[s] >= 0) {
+            if (a->slot_key[s] == key) {
+                found = true;
+                break;
+            }
+            s = (s + 1) & a->cap_mask;
+        }
+        selection[i] = found ? 0 : 1;
+    }
+    return SR_OK;
+}
+
 extern "C" int32_t orc_agg_push(orc_agg* a, const sr_chunk_view* chunk) {
     std::vector<int32_t> gidx;
     for (int64_t r0 = 0; r0 < chunk->num_rows; r0 += ORC_CHUNK_SIZE) {

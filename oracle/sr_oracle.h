@@ -216,6 +216,9 @@ int64_t orc_for_decode(int32_t elem_size, const uint8_t* page, int64_t len, void
 int64_t orc_plain_encode(int32_t elem_size, const void* values, int64_t n, uint8_t* out, int64_t cap);
 int64_t orc_plain_decode(int32_t elem_size, const uint8_t* page, int64_t len, void* out, int64_t cap);
 
+/* Aggregator::build_hash_map_with_selection (SELECTIVE_PREAGG): selection[i] = 1 when row i's group is not in the table */
+int32_t orc_agg_streaming_selection(const orc_agg* a, const sr_chunk_view* chunk, uint8_t* selection);
+
 const char* orc_last_error(void);
 
 #ifdef __cplusplus

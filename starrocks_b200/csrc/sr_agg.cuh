@@ -515,6 +515,41 @@ __global__ void __launch_bounds__(AGG_BLOCK, AGG_MIN_BLOCKS) k_agg_push(const Ag
     }
 }
 
+// SELECTIVE_PREAGG (Aggregator::build_hash_map_with_selection + compute_batch_agg_states_with_selection,
+// aggregate_streaming_sink_operator.cpp:173-210): a row whose group is already in the table is aggregated into it, a row
+// whose group is not there creates NO group -- streaming_selection[row] = 1 sends it out as an intermediate row instead.
+__device__ __forceinline__ long long agg_lookup_slot_key(const AggDev& a, const HKey& key) {
+    if (hkey_is_empty(a, key)) return a.cnt_star[a.cap] != 0 ? (long long)a.cap : -1; // the special slot holds this key's group, if any
+    unsigned long long s = hkey_hash(a, key) & a.mask;
+    const unsigned long long sb = s & ~a.slice_mask;
+    for (unsigned long long tries = 0; tries <= a.slice_mask; tries++) {
+        const HKey cur = hkey_load(a, s);
+        if (hkey_eq(a, cur, key)) return (long long)s;
+        if (hkey_is_empty(a, cur)) return -1;
+        s = sb | ((s + 1) & a.slice_mask);
+    }
+    return -1;
+}
+__global__ void __launch_bounds__(AGG_BLOCK, AGG_MIN_BLOCKS) k_agg_push_existing(const AggDev* __restrict__ ad, const __grid_constant__ VTab vt, int64_t n,
+                                                                                  uint8_t* __restrict__ selection) {
+    const AggDev& a = *ad;
+    AccPtrs p;
+    acc_ptrs_global(a, p);
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        ChunkLoader ld{vt, row};
+        HKey key;
+        agg_pack_key(a, ld, key);
+        const long long slot = agg_lookup_slot_key(a, key);
+        selection[row] = slot < 0 ? 1 : 0;
+        if (slot >= 0) agg_apply_row<false>(a, p, slot, ld);
+    }
+}
+// positions of the set selection bytes, in row order (prefix sums by cub)
+__global__ void __launch_bounds__(256) k_selection_index(const uint8_t* __restrict__ selection, const uint32_t* __restrict__ pos, int64_t n, uint32_t* __restrict__ index) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (selection[i]) index[pos[i]] = (uint32_t)i;
+}
+
 // ---- radix-partitioned push (hash tables larger than one shared-memory slice, large batches): sr_agg_part.cuh,
 // included at the end of the device section
 
@@ -979,6 +1014,8 @@ struct sr_agg {
     int32_t out_types[SR_MAX_GROUP_KEYS + SR_MAX_AGG_FNS];
     bool out_has_nulls[SR_MAX_GROUP_KEYS + SR_MAX_AGG_FNS];
     std::vector<DevBuf> conv_bufs; // sr_agg_convert_to_states: (data, nulls) per function
+    DevBuf sel_flags, sel_pos, sel_index, sel_tmp; // sr_agg_push_selective: streaming selection, its prefix sums, the streamed rows
+    std::vector<DevBuf> sel_bufs;                  //   compacted (data, nulls) per output column
     // COUNT(DISTINCT) functions: one (group keys, value) set each -- an aggregate of its own with no functions, fed the
     // same chunks; agg_finish_output folds it into acc0 of the function (which until then holds COUNT(value))
     sr_agg* distinct[SR_MAX_AGG_FNS] = {};

@@ -985,10 +985,9 @@ int64_t sr_agg_current_groups(sr_agg* a) {
     return (int64_t)ng;
 }
 
-int32_t sr_agg_convert_to_states(sr_agg* a, const sr_chunk_view* chunk, sr_chunk_out* out) {
-    if (!a || !chunk || !out) return SR_ERR_INVALID_ARGUMENT;
+// the body of sr_agg_convert_to_states; *vt_out receives the bound value table of the staged chunk
+static int32_t agg_convert_impl(sr_agg* a, const sr_chunk_view* chunk, sr_chunk_out* out, VTab* vt_out) {
     sr_ctx* ctx = a->ctx;
-    SR_BIND(ctx);
     const sr_agg_desc& d = a->desc;
     if (desc_has_distinct(&d)) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "COUNT(DISTINCT) has no intermediate state column");
     for (int f = 0; f < d.num_fns; f++)
@@ -999,6 +998,7 @@ int32_t sr_agg_convert_to_states(sr_agg* a, const sr_chunk_view* chunk, sr_chunk
     VTab vt;
     SR_TRY(bind_vtab(ctx, a->reg, a->staged, &vt));
     SR_TRY(agg_check_nullability(a, vt));
+    if (vt_out) *vt_out = vt;
     const int64_t n = chunk->num_rows;
     const srd::AggDev& h = a->host;
     if (a->conv_bufs.size() < 2 * (size_t)SR_MAX_AGG_FNS) {
@@ -1038,7 +1038,81 @@ int32_t sr_agg_convert_to_states(sr_agg* a, const sr_chunk_view* chunk, sr_chunk
         srd::k_agg_convert_states<<<std::min(grid_for(n, 256), ctx->num_sms * 8), 256, 0, ctx->stream>>>((const srd::AggDev*)a->dev.p, vt, n, ca);
         SR_LAUNCH_CHECK(ctx);
     }
+    return SR_OK;
+}
+
+int32_t sr_agg_convert_to_states(sr_agg* a, const sr_chunk_view* chunk, sr_chunk_out* out) {
+    if (!a || !chunk || !out) return SR_ERR_INVALID_ARGUMENT;
+    sr_ctx* ctx = a->ctx;
+    SR_BIND(ctx);
+    SR_TRY(agg_convert_impl(a, chunk, out, nullptr));
     if (chunk->mem != SR_MEM_DEVICE) SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // caller may free host buffers
+    return SR_OK;
+}
+
+// SELECTIVE_PREAGG leg of the streaming aggregate (aggregate_streaming_sink_operator.cpp:173-210)
+int32_t sr_agg_push_selective(sr_agg* a, const sr_chunk_view* chunk, sr_chunk_out* out) {
+    if (!a || !chunk || !out) return SR_ERR_INVALID_ARGUMENT;
+    sr_ctx* ctx = a->ctx;
+    SR_BIND(ctx);
+    if (a->finished) return sr_fail(ctx, SR_ERR_STATE, "push after sink_finish");
+    VTab vt;
+    SR_TRY(agg_convert_impl(a, chunk, out, &vt)); // every row's intermediate form; compacted to the streamed rows below
+    const int64_t n = chunk->num_rows;
+    const srd::AggDev& h = a->host;
+    if (h.dense || h.num_keys == 0) { // every group of a range-declared (or single-state) table exists: plain pre-aggregation
+        SR_TRY(agg_push_vtab(a, vt, n));
+        out->num_rows = 0;
+        return SR_OK;
+    }
+    if (n == 0) return SR_OK;
+    if (n >= 0xFFFFFFF0ll) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "selective push of more than 2^32 rows");
+    SR_TRY(a->sel_flags.reserve(ctx, (size_t)n + 16));
+    SR_TRY(a->sel_pos.reserve(ctx, sizeof(uint32_t) * ((size_t)n + 2)));
+    SR_CUDA(ctx, cudaMemsetAsync((uint8_t*)a->sel_flags.p + n, 0, 1, ctx->stream)); // flag n = 0: its prefix sum is the total
+    a->table_touched = true;
+    srd::k_agg_push_existing<<<std::min(grid_for(n, srd::AGG_BLOCK), ctx->num_sms * 8), srd::AGG_BLOCK, 0, ctx->stream>>>((const srd::AggDev*)a->dev.p, vt, n,
+                                                                                                                       a->sel_flags.as<uint8_t>());
+    SR_LAUNCH_CHECK(ctx);
+    cub::TransformInputIterator<uint32_t, srd::U8ToU32, const uint8_t*> fin(a->sel_flags.as<uint8_t>(), srd::U8ToU32());
+    size_t tb = 0;
+    SR_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, fin, a->sel_pos.as<uint32_t>(), (int)(n + 1), ctx->stream));
+    SR_TRY(a->sel_tmp.reserve(ctx, std::max<size_t>(tb, 16)));
+    SR_CUDA(ctx, cub::DeviceScan::ExclusiveSum(a->sel_tmp.p, tb, fin, a->sel_pos.as<uint32_t>(), (int)(n + 1), ctx->stream));
+    uint32_t* pin = (uint32_t*)ctx->pinned;
+    SR_CUDA(ctx, cudaMemcpyAsync(pin, a->sel_pos.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t m = (int64_t)pin[0];
+    out->num_rows = m;
+    if (m == 0 || m == n) return SR_OK; // nothing streamed, or everything: `out` already holds exactly those rows
+    SR_TRY(a->sel_index.reserve(ctx, sizeof(uint32_t) * (size_t)m));
+    srd::k_selection_index<<<std::min(grid_for(n, 256), ctx->num_sms * 8), 256, 0, ctx->stream>>>(a->sel_flags.as<uint8_t>(), a->sel_pos.as<uint32_t>(), n,
+                                                                                                 a->sel_index.as<uint32_t>());
+    SR_LAUNCH_CHECK(ctx);
+    if (a->sel_bufs.size() < 2 * (size_t)out->num_cols) {
+        std::vector<DevBuf> nb(2 * (size_t)out->num_cols);
+        for (size_t i = 0; i < a->sel_bufs.size(); i++) std::swap(nb[i], a->sel_bufs[i]);
+        a->sel_bufs.swap(nb);
+    }
+    srd::GatherArgs ga;
+    ga.n = 0;
+    for (int k = 0; k < out->num_cols; k++) {
+        srd::GatherCol g;
+        g.src = out->cols[k].data;
+        g.src_nulls = out->cols[k].nulls;
+        g.width = srd::type_width(out->cols[k].type);
+        g.zero_is_null = 0;
+        SR_TRY(a->sel_bufs[2 * k].reserve(ctx, (size_t)m * g.width));
+        if (g.src_nulls) SR_TRY(a->sel_bufs[2 * k + 1].reserve(ctx, (size_t)m));
+        g.dst = a->sel_bufs[2 * k].p;
+        g.dst_nulls = g.src_nulls ? (uint8_t*)a->sel_bufs[2 * k + 1].p : nullptr;
+        out->cols[k].data = g.dst;
+        out->cols[k].nulls = g.dst_nulls;
+        ga.c[ga.n++] = g;
+    }
+    srd::k_gather<<<dim3(std::min(grid_for(m, 256), ctx->num_sms * 16), ga.n), 256, 0, ctx->stream>>>(a->sel_index.as<uint32_t>(), m, ga);
+    SR_LAUNCH_CHECK(ctx);
+    if (chunk->mem != SR_MEM_DEVICE) SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SR_OK;
 }
 

@@ -91,6 +91,7 @@ def lib():
         "sr_agg_merge": (i32, [vp, vp]),
         "sr_agg_two_phase_descs": (i32, [vp, vp, vp]),
         "sr_agg_convert_to_states": (i32, [vp, vp, vp]),
+        "sr_agg_push_selective": (i32, [vp, vp, vp]),
         "sr_agg_current_groups": (i64, [vp]),
         "sr_agg_dense_state": (i32, [vp, vp, i32, vp]),
         "sr_agg_reset": (i32, [vp]),
@@ -143,7 +144,7 @@ EXPORTED_SYMBOLS = [
     "sr_scan_filter", "sr_scan_evaluate", "sr_join_create", "sr_join_destroy", "sr_join_append_build",
     "sr_join_build_finish", "sr_join_is_build_done", "sr_join_get_info", "sr_join_copy_table", "sr_join_probe", "sr_join_probe_remain",
     "sr_join_probe_indexes", "sr_join_key_hash", "sr_agg_create", "sr_agg_destroy", "sr_agg_push",
-    "sr_agg_sink_finish", "sr_agg_num_groups", "sr_agg_pull", "sr_agg_merge", "sr_agg_two_phase_descs", "sr_agg_convert_to_states", "sr_agg_current_groups", "sr_agg_dense_state", "sr_agg_reset", "sr_fragment_reset", "sr_fragment_get_plan", "sr_fragment_last_pass_ms",
+    "sr_agg_sink_finish", "sr_agg_num_groups", "sr_agg_pull", "sr_agg_merge", "sr_agg_two_phase_descs", "sr_agg_convert_to_states", "sr_agg_push_selective", "sr_agg_current_groups", "sr_agg_dense_state", "sr_agg_reset", "sr_fragment_reset", "sr_fragment_get_plan", "sr_fragment_last_pass_ms",
     "sr_fragment_create",
     "sr_fragment_destroy", "sr_fragment_push", "sr_fragment_agg", "sr_fragment_rows_passed", "sr_xchg_create",
     "sr_join_build_runtime_filter", "sr_rf_create", "sr_rf_insert", "sr_rf_destroy", "sr_rf_get_info", "sr_rf_copy_directory",
@@ -401,6 +402,12 @@ class Agg:
         """pass-through leg of the streaming aggregate: rows -> intermediate rows (device chunk owned by the handle)"""
         out = abi.sr_chunk_out()
         self.ctx.check(lib().sr_agg_convert_to_states(self.h, chunk.ref(), C.byref(out)))
+        return out
+
+    def push_selective(self, chunk):
+        """SELECTIVE_PREAGG: aggregate the rows whose group exists, return the others as intermediate rows (sr_chunk_out)"""
+        out = abi.sr_chunk_out()
+        self.ctx.check(lib().sr_agg_push_selective(self.h, chunk.ref(), C.byref(out)))
         return out
 
     def dense_state(self):

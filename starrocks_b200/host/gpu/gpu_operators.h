@@ -792,7 +792,9 @@ private:
 //                 with new coming rows"): reduction >= 2 -> PREAGG, else flush and PASS_THROUGH again.
 // Dense tables and aggregates without GROUP BY are bounded: always PREAGG.
 // ------------------------------------------------------------------------------------------------------------
-enum class GpuStreamingPreaggMode { AUTO = 0, FORCE_STREAMING = 1, FORCE_PREAGGREGATION = 2 }; // TStreamingPreaggregationMode
+// TStreamingPreaggregationMode (+ LIMITED_MEM, aggregate_streaming_sink_operator.cpp:362-372: AUTO until the table holds
+// limited_memory_size bytes, FORCE_STREAMING from then on)
+enum class GpuStreamingPreaggMode { AUTO = 0, FORCE_STREAMING = 1, FORCE_PREAGGREGATION = 2, LIMITED_MEM = 3 };
 
 class GpuStreamingAggregator {
 public:
@@ -815,7 +817,22 @@ public:
         const bool bounded = _desc.num_group_keys == 0 || _desc.has_ranges != 0;
         if (_mode == GpuStreamingPreaggMode::FORCE_STREAMING && !bounded) return _stream(state, v);
         if (_mode == GpuStreamingPreaggMode::FORCE_PREAGGREGATION || bounded) return _preagg(v);
+        if (_mode == GpuStreamingPreaggMode::LIMITED_MEM) { // LimitedMemAggState::has_limited (aggregator.h:639-641)
+            const int64_t groups = _agg_groups();
+            if (groups < 0) return sr_to_status(_ctx, (int32_t)groups);
+            if ((size_t)groups * _group_bytes >= _max_ht_bytes) {
+                _limited = true;
+                return _stream(state, v);
+            }
+        }
         switch (_state) {
+        case SELECTIVE: // SELECTIVE_PREAGG for continuous_limit batches, then back to ADJUST (aggregate_streaming_sink_operator.cpp:225-228)
+            RETURN_IF_ERROR(_selective(state, v));
+            if (++_pass_count >= _pass_through_batches) {
+                _pass_count = 0;
+                _state = PROBE;
+            }
+            return Status::OK();
         case PASS_THROUGH:
             RETURN_IF_ERROR(_stream(state, v));
             if (++_pass_count >= _pass_through_batches) {
@@ -837,6 +854,13 @@ public:
                 }
             } else if (!big || reduction >= 2.0) {
                 return Status::OK(); // small table, or pre-aggregation still pays
+            }
+            if (reduction >= 1.25) {
+                // middling reduction ("middle cases", :194-208): keep the table, aggregate the rows of known groups into it
+                // and stream the rest, so it stops growing without losing the groups that do repeat
+                _state = SELECTIVE;
+                _num_selective_phases++;
+                return Status::OK();
             }
             // low reduction: emit what the table holds and stop building it for a while
             RETURN_IF_ERROR(flush_table(state));
@@ -865,6 +889,9 @@ public:
     void sink_complete() { _sink_complete = true; }
     bool is_sink_complete() const { return _sink_complete; }
     size_t rows_streamed() const { return _rows_streamed; }
+    size_t rows_selected_into_table() const { return _rows_selected; }
+    int num_selective_phases() const { return _num_selective_phases; }
+    bool memory_limited() const { return _limited; }
     size_t rows_from_table() const { return _rows_from_table; }
     int num_flushes() const { return _num_flushes; }
 
@@ -874,13 +901,22 @@ private:
         _rows_in_table += (size_t)v.num_rows;
         return Status::OK();
     }
+    int64_t _agg_groups() { return _rows_in_table == 0 ? 0 : sr_agg_current_groups(_agg); }
+    Status _selective(RuntimeState* state, const sr_chunk_view& v) {
+        sr_chunk_out out;
+        RETURN_IF_SR_ERROR(_ctx, sr_agg_push_selective(_agg, &v, &out));
+        _rows_streamed += (size_t)out.num_rows;
+        _rows_selected += (size_t)(v.num_rows - out.num_rows);
+        _rows_in_table += (size_t)(v.num_rows - out.num_rows);
+        return slice_out_to_chunks(_ctx, out, state->chunk_size(), &_buffer);
+    }
     Status _stream(RuntimeState* state, const sr_chunk_view& v) {
         sr_chunk_out out;
         RETURN_IF_SR_ERROR(_ctx, sr_agg_convert_to_states(_agg, &v, &out));
         _rows_streamed += (size_t)out.num_rows;
         return slice_out_to_chunks(_ctx, out, state->chunk_size(), &_buffer);
     }
-    enum AutoState { PREAGG, PASS_THROUGH, PROBE };
+    enum AutoState { PREAGG, PASS_THROUGH, PROBE, SELECTIVE };
     sr_ctx* _ctx;
     sr_agg_desc _desc;
     GpuStreamingPreaggMode _mode;
@@ -888,8 +924,9 @@ private:
     int _pass_through_batches;
     sr_agg* _agg = nullptr;
     AutoState _state = PREAGG;
-    int _pass_count = 0, _num_flushes = 0;
-    size_t _rows_in_table = 0, _rows_streamed = 0, _rows_from_table = 0;
+    int _pass_count = 0, _num_flushes = 0, _num_selective_phases = 0;
+    size_t _rows_in_table = 0, _rows_streamed = 0, _rows_from_table = 0, _rows_selected = 0;
+    bool _limited = false;
     std::deque<ChunkPtr> _buffer;
     bool _sink_complete = false;
 };

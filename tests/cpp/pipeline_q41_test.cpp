@@ -478,12 +478,21 @@ int main(int argc, char** argv) {
         struct G {
             int64_t rev = 0, cost = 0, cnt = 0;
         };
-        const char* names[3] = {"AUTO", "FORCE_STREAMING", "FORCE_PREAGGREGATION"};
+        const char* names[4] = {"AUTO", "FORCE_STREAMING", "FORCE_PREAGGREGATION", "LIMITED_MEM"};
+        // run 5's second key: lo_partkey folded to 13 values -> 390 000 groups over 1 M rows, a middling reduction (~1.4 on the
+        // first batch) that sends AUTO into SELECTIVE_PREAGG
+        std::vector<int32_t> lo_part13(n_fact);
+        for (size_t i = 0; i < n_fact; i++) lo_part13[i] = lo_part[i] % 13;
+        ChunkPtr lineorder13 = make_chunk({{LO_CUSTKEY, lo_cust}, {LO_PARTKEY, lo_part13}, {LO_REVENUE, lo_rev}, {LO_SUPPLYCOST, lo_cost}});
         // (a) GROUP BY lo_custkey: 30 000 groups over 1 M rows, reduction ~33 -> AUTO keeps pre-aggregating;
         // (b) GROUP BY lo_custkey, lo_partkey: ~1 M groups, reduction ~1 -> AUTO must flush, pass through and probe again
-        for (int run = 0; run < 4; run++) {
-            const int mode = run < 3 ? run : 0;
-            const bool two_keys = run == 3;
+        // (c) LIMITED_MEM on the low-reduction input: streams as soon as the table reaches its byte limit;
+        // (d) AUTO on the middling-reduction input: SELECTIVE_PREAGG (known groups aggregated, the rest streamed)
+        for (int run = 0; run < 6; run++) {
+            const int mode = run < 3 ? run : run == 4 ? 3 : 0;
+            const bool two_keys = run >= 3;
+            const bool folded = run == 5;
+            const std::vector<int32_t>& key2 = folded ? lo_part13 : lo_part;
             sr_agg_desc q{};
             q.num_group_keys = two_keys ? 2 : 1;
             q.group_slots[0] = LO_CUSTKEY;
@@ -500,7 +509,7 @@ int main(int argc, char** argv) {
             }
             std::map<std::pair<int32_t, int32_t>, G> want;
             for (size_t i = 0; i < n_fact; i++) {
-                G& g = want[{lo_cust[i], two_keys ? lo_part[i] : 0}];
+                G& g = want[{lo_cust[i], two_keys ? key2[i] : 0}];
                 g.rev += lo_rev[i];
                 g.cost += lo_cost[i];
                 g.cnt++;
@@ -509,7 +518,7 @@ int main(int argc, char** argv) {
             std::vector<int32_t> outs = {LO_CUSTKEY, LO_PARTKEY, LO_REVENUE, LO_SUPPLYCOST};
             sd.out_slots = outs.data();
             sd.num_out_slots = (int32_t)outs.size();
-            GpuScanOperatorFactory scan_f(30, 30, ctx, sd, {split(lineorder, 4096)});
+            GpuScanOperatorFactory scan_f(30, 30, ctx, sd, {split(folded ? lineorder13 : lineorder, 4096)});
             auto streaming_f = std::make_shared<GpuStreamingAggregatorFactory>(ctx, p1, (GpuStreamingPreaggMode)mode, /*max_ht_bytes=*/(size_t)256 << 10,
                                                                                /*pass_through_batches=*/1);
             auto streaming = streaming_f->get_or_create(0);
@@ -542,13 +551,24 @@ int main(int argc, char** argv) {
                 fprintf(stderr, "two-phase aggregate (%s): %zu groups (want %zu), values %s\n", names[mode], groups, want.size(), ok ? "ok" : "WRONG");
                 rc = 1;
             }
-            if (two_keys && (streaming->rows_streamed() == 0 || streaming->num_flushes() == 0)) {
+            if (run == 3 && (streaming->rows_streamed() == 0 || streaming->num_flushes() == 0)) {
                 fprintf(stderr, "AUTO never left pre-aggregation on a low-reduction input\n");
                 rc = 1;
             }
-            printf("two-phase aggregate %-20s %s: %zu groups; first phase passed %zu rows through, emitted %zu pre-aggregated rows, %d table flushes\n",
-                   names[mode], two_keys ? "(2 keys, reduction ~1)" : "(1 key, reduction ~33)", groups, streaming->rows_streamed(),
-                   streaming->rows_from_table(), streaming->num_flushes());
+            if (run == 4 && (!streaming->memory_limited() || streaming->rows_streamed() == 0)) {
+                fprintf(stderr, "LIMITED_MEM never hit its limit / never streamed\n");
+                rc = 1;
+            }
+            if (run == 5 && (streaming->num_selective_phases() == 0 || streaming->rows_selected_into_table() == 0 || streaming->rows_streamed() == 0)) {
+                fprintf(stderr, "AUTO never took the SELECTIVE_PREAGG leg on a middling-reduction input (%d phases, %zu rows into the table, %zu streamed)\n",
+                        streaming->num_selective_phases(), streaming->rows_selected_into_table(), streaming->rows_streamed());
+                rc = 1;
+            }
+            printf("two-phase aggregate %-20s %s: %zu groups; first phase passed %zu rows through, emitted %zu pre-aggregated rows, %d table flushes, "
+                   "%d selective phases (%zu rows aggregated into known groups)\n",
+                   names[mode], folded ? "(2 keys, reduction ~2.5)" : two_keys ? "(2 keys, reduction ~1)" : "(1 key, reduction ~33)", groups,
+                   streaming->rows_streamed(), streaming->rows_from_table(), streaming->num_flushes(), streaming->num_selective_phases(),
+                   streaming->rows_selected_into_table());
             result_driver.close(&state);
             second.close(&state);
             first.close(&state);

@@ -239,6 +239,60 @@ def test_gpu_two_phase_equals_oracle_single_phase(gpu, ctx, oracle, name, n):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("n", [1000, 150_001])
+def test_gpu_selective_preaggregation(gpu, ctx, oracle, name, n):
+    # SELECTIVE_PREAGG (aggregate_streaming_sink_operator.cpp:173-210): after a warm-up batch has filled the table, every
+    # further batch is split by build_hash_map_with_selection -- rows of known groups are aggregated in place, the others
+    # are streamed out in the intermediate format.  (1) the streamed rows are exactly the oracle's selection (bytes of the
+    # oracle's convert_to_states at those rows, in order); (2) table + streamed rows merged = the single-phase result.
+    rng = np.random.default_rng(31 + n)
+    d, cols, fl = _case(name, n, rng)
+    single = oracle.Agg(d)
+    single.push(_sub(cols, 0, n))
+    p1, p2 = gpu.two_phase_descs(d)
+    first, final, ofirst = gpu.Agg(ctx, p1), gpu.Agg(ctx, p2), oracle.Agg(p1)
+    try:
+        warm = n // 5
+        first.push(_sub(cols, 0, warm))
+        ofirst.push(_sub(cols, 0, warm))
+        streamed = 0
+        for lo, hi in ((warm, n // 2), (n // 2, n)):
+            ch = _sub(cols, lo, hi)
+            sel = ofirst.streaming_selection(ch)
+            exp = oracle.convert_to_states(p1, ch)
+            out = first.push_selective(ch)
+            assert out.num_rows == int(sel.sum())
+            got = gpu.chunk_out_to_host(ctx, out)
+            for (gs, gt, gd, gn), (es, et, ed, en) in zip(got, exp):
+                assert (gs, gt) == (es, et)
+                keep = sel == 1
+                if en is not None:
+                    assert np.array_equal(gn, en[keep])
+                    ok = en[keep] == 0
+                    assert np.array_equal(np.asarray(gd)[ok], np.asarray(ed)[keep][ok])
+                else:
+                    assert np.array_equal(np.asarray(gd), np.asarray(ed)[keep])
+            # the oracle's table takes the rows of known groups (what compute_batch_agg_states_with_selection does)
+            known = sel == 0
+            if known.any():
+                ofirst.push(Chunk([(c[0], c[1][lo:hi][known].copy(), None if c[2] is None else c[2][lo:hi][known].copy()) + tuple(c[3:]) for c in cols]))
+            if out.num_rows:
+                final.push(gpu.chunk_out_as_view(out))
+            streamed += out.num_rows
+        if p1.num_group_keys > 0 and not name.startswith("dense"):
+            assert streamed > 0                     # the hash cases really stream rows of unseen groups
+        first.finish()
+        tab = first.pull(mem=abi.MEM_DEVICE)
+        if tab.num_rows:
+            final.push(gpu.chunk_out_as_view(tab))
+        assert_rows_equal(gpu_rows(final.result()), oracle_rows(single), float_cols=fl)
+    finally:
+        first.close()
+        final.close()
+
+
+@pytest.mark.gpu
 def test_avg_merge_errors_are_loud(gpu, ctx):
     bad = abi.make_agg_desc(fns=[(abi.AGG_AVG_MERGE, abi.TYPE_DOUBLE, 9, [("col", 1)])])
     bad.fns[0].reserved = 77      # count state slot that is not in the chunk
