@@ -817,10 +817,10 @@ public:
         const bool bounded = _desc.num_group_keys == 0 || _desc.has_ranges != 0;
         if (_mode == GpuStreamingPreaggMode::FORCE_STREAMING && !bounded) return _stream(state, v);
         if (_mode == GpuStreamingPreaggMode::FORCE_PREAGGREGATION || bounded) return _preagg(v);
-        if (_mode == GpuStreamingPreaggMode::LIMITED_MEM) { // LimitedMemAggState::has_limited (aggregator.h:639-641)
-            const int64_t groups = _agg_groups();
-            if (groups < 0) return sr_to_status(_ctx, (int32_t)groups);
-            if ((size_t)groups * _group_bytes >= _max_ht_bytes) {
+        if (_mode == GpuStreamingPreaggMode::LIMITED_MEM) {
+            // LimitedMemAggState::has_limited (aggregator.h:639-641): Aggregator::memory_usage() >= limited_memory_size.  The
+            // table's memory does not shrink when its groups are flushed, so the peak size counts
+            if (_limited || _peak_table_bytes >= _max_ht_bytes) {
                 _limited = true;
                 return _stream(state, v);
             }
@@ -847,6 +847,7 @@ public:
             if (groups < 0) return sr_to_status(_ctx, (int32_t)groups);
             const double reduction = groups > 0 ? (double)_rows_in_table / (double)groups : 1e30;
             const bool big = (size_t)groups * _group_bytes > _max_ht_bytes;
+            _peak_table_bytes = std::max(_peak_table_bytes, (size_t)groups * _group_bytes);
             if (_state == PROBE) {
                 if (reduction >= 2.0) {
                     _state = PREAGG;
@@ -901,7 +902,6 @@ private:
         _rows_in_table += (size_t)v.num_rows;
         return Status::OK();
     }
-    int64_t _agg_groups() { return _rows_in_table == 0 ? 0 : sr_agg_current_groups(_agg); }
     Status _selective(RuntimeState* state, const sr_chunk_view& v) {
         sr_chunk_out out;
         RETURN_IF_SR_ERROR(_ctx, sr_agg_push_selective(_agg, &v, &out));
@@ -927,6 +927,7 @@ private:
     int _pass_count = 0, _num_flushes = 0, _num_selective_phases = 0;
     size_t _rows_in_table = 0, _rows_streamed = 0, _rows_from_table = 0, _rows_selected = 0;
     bool _limited = false;
+    size_t _peak_table_bytes = 0;
     std::deque<ChunkPtr> _buffer;
     bool _sink_complete = false;
 };
