@@ -387,8 +387,13 @@ typedef struct sr_rf_info {
     int32_t has_null;             /* a NULL key was inserted (null-safe joins) */
     int32_t log_num_buckets;      /* directory = 2^log_num_buckets buckets of 32 bytes; 0: no bloom part */
     int32_t key_type;
-    int32_t reserved;
+    int32_t num_in_values;        /* runtime IN filter: distinct keys held (exact membership); -1: no IN part (more than
+                                   * SR_RF_IN_FILTER_ROW_LIMIT rows were inserted) */
 } sr_rf_info;
+/* HashJoiner::runtime_in_filter_row_limit / max_pushdown_conditions_per_column (hash_joiner.h:270, hash_joiner.cpp:563-575):
+ * membership filters (with_bloom != 0) over at most this many build rows also carry their distinct keys; membership is
+ * then tested exactly */
+#define SR_RF_IN_FILTER_ROW_LIMIT 1024
 /* Build from key number `key_index` of a finished join build side.  with_bloom = 0 builds the min/max part only.
  * insert_nulls != 0 records NULL build keys (has_null) -- the reference does so for null-safe equal joins. */
 sr_rf* sr_join_build_runtime_filter(sr_join* join, int32_t key_index, int32_t with_bloom, int32_t insert_nulls);
@@ -396,6 +401,10 @@ sr_rf* sr_join_build_runtime_filter(sr_join* join, int32_t key_index, int32_t wi
  * exactly like SimdBlockFilter::init(expected_rows). */
 sr_rf* sr_rf_create(sr_ctx* ctx, int32_t key_type, int64_t expected_rows, int32_t with_bloom);
 int32_t sr_rf_insert(sr_rf* rf, const sr_chunk_view* in, int32_t slot_id, int32_t insert_nulls);
+/* the IN part: copy the sorted distinct keys out (returns their number, or -1 when the filter has no IN part); merge the keys
+ * of a partial filter in (n = -1: the partial filter has no IN part, so the merged one has none either) */
+int32_t sr_rf_copy_in_values(sr_rf* rf, int64_t* values_host, int32_t capacity);
+int32_t sr_rf_merge_in_values(sr_rf* rf, const int64_t* values_host, int32_t n);
 void sr_rf_destroy(sr_rf* rf);
 int32_t sr_rf_get_info(sr_rf* rf, sr_rf_info* info);
 /* bloom directory: copy out (bytes = 32 << log_num_buckets) / merge another filter in: OR of the directories
@@ -410,7 +419,18 @@ int32_t sr_rf_evaluate(sr_rf* rf, const sr_chunk_view* in, int32_t slot_id, uint
  * the conjuncts (the ScanOperator side of runtime filters, scan_operator.h:212-225).  At most SR_MAX_SCAN_RFS per scan;
  * the filter must outlive the scan. */
 #define SR_MAX_SCAN_RFS 4
+/* Use of runtime filter `index` (order of sr_scan_add_runtime_filter) by sr_scan_filter so far.  Like
+ * RuntimeFilterProbeCollector (runtime_filter_probe.cpp:203-262,408-480) the scan measures every filter's selectivity (rows
+ * passed / rows tested) and stops evaluating a filter that lets more than half of its rows through for the next 31 batches,
+ * then samples it again.  adaptive = 0 in sr_scan_set_rf_adaptive evaluates every filter on every batch. */
+typedef struct sr_scan_rf_stats {
+    int64_t rows_tested, rows_passed; /* over the batches that evaluated the filter */
+    int64_t batches_skipped;          /* batches on which it was switched off */
+    double last_selectivity;
+} sr_scan_rf_stats;
 int32_t sr_scan_add_runtime_filter(sr_scan* scan, sr_rf* rf, int32_t probe_slot);
+int32_t sr_scan_get_rf_stats(sr_scan* scan, int32_t index, sr_scan_rf_stats* stats);
+int32_t sr_scan_set_rf_adaptive(sr_scan* scan, int32_t adaptive);
 
 /* ---------------------------------------------------------------------------------------
  * hash aggregate.  One sr_agg is shared by the sink and source operators, like Aggregator

@@ -13,6 +13,7 @@
 #include <limits>
 #include <map>
 #include <memory>
+#include <set>
 #include <string>
 #include <thread>
 #include <type_traits>
@@ -2388,6 +2389,11 @@ struct orc_rf {
     int64_t min_value = INT64_MAX, max_value = INT64_MIN;
     int64_t num_inserted = 0;
     bool has_null = false;
+    // runtime IN filter (HashJoiner::_create_runtime_in_filters, hash_joiner.cpp:563-609): build sides of at most
+    // max_pushdown_conditions_per_column = 1024 rows publish their distinct keys as an IN predicate -- exact membership
+    bool in_enabled = false;
+    int64_t in_rows = 0;
+    std::set<int64_t> in_values;
 };
 
 extern "C" orc_rf* orc_rf_create(int32_t key_type, int64_t expected_rows, int32_t with_bloom) {
@@ -2397,6 +2403,7 @@ extern "C" orc_rf* orc_rf_create(int32_t key_type, int64_t expected_rows, int32_
     }
     auto* rf = new orc_rf();
     rf->key_type = key_type;
+    rf->in_enabled = with_bloom && expected_rows <= SR_RF_IN_FILTER_ROW_LIMIT; // a pure MinMaxRuntimeFilter (with_bloom = 0) stays a range test
     if (with_bloom) { // SimdBlockFilter::init
         const uint64_t nums = (uint64_t)std::max<int64_t>(1, expected_rows);
         const int log_heap_space = (int)std::ceil(std::log2((double)nums));
@@ -2437,12 +2444,20 @@ extern "C" int32_t orc_rf_insert(orc_rf* rf, const sr_chunk_view* in, int32_t sl
     const sr_col_view* c = find_col(in, slot_id);
     if (!c) return fail(SR_ERR_INVALID_ARGUMENT, "runtime filter slot not in chunk");
     if (type_width(c->type) != type_width(rf->key_type) || is_float_class(c->type)) return fail(SR_ERR_INVALID_ARGUMENT, "runtime filter key type differs");
+    if (rf->in_enabled && in->num_rows > 0) {
+        rf->in_rows += in->num_rows;
+        if (rf->in_rows > SR_RF_IN_FILTER_ROW_LIMIT) {
+            rf->in_enabled = false;
+            rf->in_values.clear();
+        }
+    }
     for (int64_t i = 0; i < in->num_rows; i++) {
         if (c->nulls && c->nulls[i]) {
             if (insert_nulls) rf->has_null = true;
             continue;
         }
         const int64_t v = load_int(c->data, c->type, i);
+        if (rf->in_enabled) rf->in_values.insert(v);
         rf->min_value = std::min(rf->min_value, v);
         rf->max_value = std::max(rf->max_value, v);
         rf->num_inserted++;
@@ -2457,6 +2472,15 @@ extern "C" int32_t orc_rf_merge(orc_rf* rf, const orc_rf* other) {
     rf->max_value = std::max(rf->max_value, other->max_value);
     rf->num_inserted += other->num_inserted;
     rf->has_null = rf->has_null || other->has_null;
+    if (rf->in_enabled) { // the total filter keeps an IN part only when every partial one has it and the union stays small
+        if (!other->in_enabled) {
+            rf->in_enabled = false;
+        } else {
+            rf->in_values.insert(other->in_values.begin(), other->in_values.end());
+            if ((int64_t)rf->in_values.size() > SR_RF_IN_FILTER_ROW_LIMIT) rf->in_enabled = false;
+        }
+        if (!rf->in_enabled) rf->in_values.clear();
+    }
     return SR_OK;
 }
 extern "C" int32_t orc_rf_evaluate(const orc_rf* rf, const sr_chunk_view* in, int32_t slot_id, uint8_t* selection, int32_t merge_and) {
@@ -2468,7 +2492,8 @@ extern "C" int32_t orc_rf_evaluate(const orc_rf* rf, const sr_chunk_view* in, in
             pass = rf->has_null ? 1 : 0;
         } else {
             const int64_t v = load_int(c->data, c->type, i);
-            pass = v >= rf->min_value && v <= rf->max_value && orc_rf_test_hash(rf, orc_rf_value_hash(v));
+            pass = v >= rf->min_value && v <= rf->max_value &&
+                   (rf->in_enabled && !rf->in_values.empty() ? rf->in_values.count(v) != 0 : orc_rf_test_hash(rf, orc_rf_value_hash(v)) != 0);
         }
         selection[i] = merge_and ? (uint8_t)(selection[i] && pass) : pass;
     }
@@ -2481,7 +2506,7 @@ extern "C" int32_t orc_rf_get_info(const orc_rf* rf, sr_rf_info* info) {
     info->has_null = rf->has_null ? 1 : 0;
     info->log_num_buckets = rf->log_num_buckets;
     info->key_type = rf->key_type;
-    info->reserved = 0;
+    info->num_in_values = rf->in_enabled ? (int32_t)rf->in_values.size() : -1;
     return SR_OK;
 }
 extern "C" const void* orc_rf_directory(const orc_rf* rf, int64_t* bytes) {

@@ -177,7 +177,14 @@ class sr_part_desc(C.Structure):
 
 class sr_rf_info(C.Structure):
     _fields_ = [("min_value", C.c_int64), ("max_value", C.c_int64), ("num_inserted", C.c_int64), ("has_null", C.c_int32),
-                ("log_num_buckets", C.c_int32), ("key_type", C.c_int32), ("reserved", C.c_int32)]
+                ("log_num_buckets", C.c_int32), ("key_type", C.c_int32), ("num_in_values", C.c_int32)]
+
+
+class sr_scan_rf_stats(C.Structure):
+    _fields_ = [("rows_tested", C.c_int64), ("rows_passed", C.c_int64), ("batches_skipped", C.c_int64), ("last_selectivity", C.c_double)]
+
+
+RF_IN_FILTER_ROW_LIMIT = 1024
 
 
 STATE_REDUCE_SUM, STATE_REDUCE_MIN, STATE_REDUCE_MAX = 0, 1, 2

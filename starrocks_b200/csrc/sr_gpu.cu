@@ -506,6 +506,38 @@ static int32_t rf_insert_dcol(sr_rf* rf, const srd::DCol& col, int64_t n, int32_
     srd::k_rf_insert_col<<<std::min(grid_for(n, 256), ctx->num_sms * 8), 256, 0, ctx->stream>>>(col, n, rf->log_num_buckets ? rf->dir.as<uint32_t>() : nullptr, rf->dir_mask,
                                                                                                  rf->log_num_buckets, insert_nulls ? 1 : 0, rf->stats.as<long long>());
     SR_LAUNCH_CHECK(ctx);
+    // the IN part: while the build side stays within the row limit its keys are also kept as a sorted distinct list
+    if (rf->in_enabled) {
+        rf->in_rows += n;
+        if (rf->in_rows > SR_RF_IN_FILTER_ROW_LIMIT) {
+            rf->in_enabled = false;
+            rf->in_host.clear();
+        } else {
+            const int w = srd::type_width(col.type);
+            std::vector<uint8_t> raw((size_t)n * w), nul(col.nulls ? (size_t)n : 0);
+            SR_CUDA(ctx, cudaMemcpyAsync(raw.data(), col.data, raw.size(), cudaMemcpyDeviceToHost, ctx->stream));
+            if (col.nulls) SR_CUDA(ctx, cudaMemcpyAsync(nul.data(), col.nulls, nul.size(), cudaMemcpyDeviceToHost, ctx->stream));
+            SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int64_t i = 0; i < n; i++) {
+                if (col.nulls && nul[i]) continue;
+                long long v = 0;
+                if (col.type == SR_TYPE_BOOLEAN)
+                    v = raw[i];
+                else if (w == 1)
+                    v = (int8_t)raw[i];
+                else if (w == 2)
+                    v = ((const int16_t*)raw.data())[i];
+                else if (w == 4)
+                    v = ((const int32_t*)raw.data())[i];
+                else
+                    v = ((const long long*)raw.data())[i];
+                rf->in_host.push_back(v);
+            }
+            std::sort(rf->in_host.begin(), rf->in_host.end());
+            rf->in_host.erase(std::unique(rf->in_host.begin(), rf->in_host.end()), rf->in_host.end());
+            rf->in_dirty = true;
+        }
+    }
     return SR_OK;
 }
 
@@ -585,7 +617,7 @@ int32_t sr_rf_get_info(sr_rf* rf, sr_rf_info* info) {
     info->has_null = rf->hstats[3] != 0;
     info->log_num_buckets = rf->log_num_buckets;
     info->key_type = rf->key_type;
-    info->reserved = 0;
+    info->num_in_values = rf->in_enabled ? (int32_t)rf->in_host.size() : -1;
     return SR_OK;
 }
 
@@ -596,6 +628,36 @@ int32_t sr_rf_copy_directory(sr_rf* rf, void* dst, int64_t bytes, int32_t mem) {
     if (bytes != (int64_t)rf->dir_bytes()) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "directory is %zu bytes, caller passed %lld", rf->dir_bytes(), (long long)bytes);
     SR_TRY(copy_out(ctx, dst, rf->dir.p, (size_t)bytes, mem));
     SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SR_OK;
+}
+
+int32_t sr_rf_copy_in_values(sr_rf* rf, int64_t* values_host, int32_t capacity) {
+    if (!rf) return SR_ERR_INVALID_ARGUMENT;
+    SR_LOCK(rf->ctx);
+    if (!rf->in_enabled) return -1;
+    const int32_t n = (int32_t)rf->in_host.size();
+    if (n > capacity || (n > 0 && !values_host)) return sr_fail(rf->ctx, SR_ERR_INVALID_ARGUMENT, "IN list of %d values, capacity %d", n, capacity);
+    for (int32_t i = 0; i < n; i++) values_host[i] = rf->in_host[i];
+    return n;
+}
+
+int32_t sr_rf_merge_in_values(sr_rf* rf, const int64_t* values_host, int32_t n) {
+    if (!rf || (n > 0 && !values_host)) return SR_ERR_INVALID_ARGUMENT;
+    SR_LOCK(rf->ctx);
+    if (!rf->in_enabled) return SR_OK;
+    if (n < 0) { // PartialRuntimeFilterMerger: one partial filter without an IN part -> the total has none
+        rf->in_enabled = false;
+        rf->in_host.clear();
+        return SR_OK;
+    }
+    for (int32_t i = 0; i < n; i++) rf->in_host.push_back(values_host[i]);
+    std::sort(rf->in_host.begin(), rf->in_host.end());
+    rf->in_host.erase(std::unique(rf->in_host.begin(), rf->in_host.end()), rf->in_host.end());
+    if ((int64_t)rf->in_host.size() > SR_RF_IN_FILTER_ROW_LIMIT) {
+        rf->in_enabled = false;
+        rf->in_host.clear();
+    }
+    rf->in_dirty = true;
     return SR_OK;
 }
 
@@ -665,6 +727,28 @@ int32_t sr_scan_add_runtime_filter(sr_scan* scan, sr_rf* rf, int32_t probe_slot)
     if (scan->rfs.size() >= SR_MAX_SCAN_RFS) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "more than %d runtime filters on one scan", SR_MAX_SCAN_RFS);
     scan->rfs.emplace_back(rf, probe_slot);
     scan->compiled = false; // the probe column joins the value table at the next batch
+    return SR_OK;
+}
+
+int32_t sr_scan_get_rf_stats(sr_scan* scan, int32_t index, sr_scan_rf_stats* stats) {
+    if (!scan || !stats) return SR_ERR_INVALID_ARGUMENT;
+    SR_LOCK(scan->ctx);
+    if (index < 0 || index >= (int32_t)scan->rfs.size()) return sr_fail(scan->ctx, SR_ERR_INVALID_ARGUMENT, "runtime filter index %d", index);
+    memset(stats, 0, sizeof(*stats));
+    if ((size_t)index < scan->rf_use.size()) {
+        const sr_scan::RfUse& u = scan->rf_use[index];
+        stats->rows_tested = (int64_t)u.tested;
+        stats->rows_passed = (int64_t)u.passed;
+        stats->batches_skipped = u.batches_skipped;
+        stats->last_selectivity = u.last_selectivity;
+    }
+    return SR_OK;
+}
+
+int32_t sr_scan_set_rf_adaptive(sr_scan* scan, int32_t adaptive) {
+    if (!scan) return SR_ERR_INVALID_ARGUMENT;
+    SR_LOCK(scan->ctx);
+    scan->rf_adaptive = adaptive != 0;
     return SR_OK;
 }
 

@@ -20,7 +20,8 @@ struct RfDev {
     int32_t log_buckets;
     int32_t has_null;
     int32_t value_id; // column the scan tests (scan integration only)
-    int32_t pad;
+    int32_t in_count; // > 0: runtime IN filter -- the sorted distinct build keys; membership is EXACT and replaces the bloom test
+    const long long* in_values;
 };
 
 __device__ __forceinline__ unsigned long long rf_value_hash(long long v) {
@@ -32,8 +33,19 @@ __device__ __forceinline__ uint32_t rf_salt(int i) {
     return SALT[i];
 }
 // membership test of a non-NULL value: range first (free), then the 8 bits of its bucket
+// runtime IN filter (HashJoiner::_create_runtime_in_filters, hash_joiner.cpp:563-609: at most
+// max_pushdown_conditions_per_column = 1024 build rows): binary search in the sorted key list (<= 8 KB, L1 / L2 resident)
+__device__ __forceinline__ bool rf_in_list(const RfDev& r, long long v) {
+    int lo = 0, hi = r.in_count;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(r.in_values + mid) < v) lo = mid + 1; else hi = mid;
+    }
+    return lo < r.in_count && __ldg(r.in_values + lo) == v;
+}
 __device__ __forceinline__ bool rf_test(const RfDev& r, long long v) {
     if (v < r.min_value || v > r.max_value) return false;
+    if (r.in_count > 0) return rf_in_list(r, v);
     if (r.dir == nullptr) return true;
     const unsigned long long h = rf_value_hash(v);
     const uint32_t key = (uint32_t)(h >> r.log_buckets);
@@ -53,6 +65,13 @@ __device__ __forceinline__ uint32_t rf_test_rows(const RfDev& rf, const long lon
     uint32_t in = 0;
 #pragma unroll
     for (int r = 0; r < R; r++) in |= (((active >> r) & 1u) && v[r] >= rf.min_value && v[r] <= rf.max_value ? 1u : 0u) << r;
+    if (rf.in_count > 0) {
+        uint32_t pass = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            if ((in >> r) & 1u) pass |= (rf_in_list(rf, v[r]) ? 1u : 0u) << r;
+        return pass;
+    }
     if (rf.dir == nullptr || in == 0) return in;
     uint32_t w[R][8];
     uint32_t key[R];
@@ -153,6 +172,11 @@ struct sr_rf {
     uint64_t dir_mask = 0;
     DevBuf dir, stats;
     Staged staged;
+    // runtime IN filter: the distinct non-NULL keys while at most SR_RF_IN_FILTER_ROW_LIMIT rows were inserted
+    bool in_enabled = false, in_dirty = false;
+    int64_t in_rows = 0;
+    std::vector<long long> in_host; // sorted, distinct
+    DevBuf in_dev;
     // host copy of the stats, refreshed lazily
     bool stats_valid = false;
     long long hstats[4] = {0, 0, 0, 0};
@@ -168,6 +192,8 @@ static int32_t rf_init(sr_rf* rf, sr_ctx* ctx, int32_t key_type, int64_t expecte
     const long long init[4] = {0x7fffffffffffffffll, (long long)0x8000000000000000ll, 0, 0};
     SR_CUDA(ctx, cudaMemcpyAsync(rf->stats.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // `init` is a stack buffer
+    // runtime_in_filter_row_limit (hash_joiner.h:270); a pure MinMaxRuntimeFilter (with_bloom = 0) stays a range test
+    rf->in_enabled = with_bloom && expected_rows <= SR_RF_IN_FILTER_ROW_LIMIT;
     if (with_bloom) { // SimdBlockFilter::init
         const uint64_t nums = (uint64_t)std::max<int64_t>(1, expected_rows);
         int log_heap_space = 0;
@@ -198,6 +224,18 @@ static int32_t rf_device_desc(sr_rf* rf, srd::RfDev* d) {
     d->log_buckets = rf->log_num_buckets;
     d->has_null = rf->hstats[3] != 0;
     d->value_id = -1;
-    d->pad = 0;
+    d->in_count = 0;
+    d->in_values = nullptr;
+    if (rf->in_enabled && !rf->in_host.empty()) {
+        sr_ctx* ctx = rf->ctx;
+        if (rf->in_dirty) {
+            SR_TRY(rf->in_dev.reserve(ctx, sizeof(long long) * rf->in_host.size()));
+            SR_CUDA(ctx, cudaMemcpyAsync(rf->in_dev.p, rf->in_host.data(), sizeof(long long) * rf->in_host.size(), cudaMemcpyHostToDevice, ctx->stream));
+            SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            rf->in_dirty = false;
+        }
+        d->in_count = (int32_t)rf->in_host.size();
+        d->in_values = rf->in_dev.as<long long>();
+    }
     return SR_OK;
 }

@@ -91,6 +91,10 @@ struct ScanTests {
     int32_t num_rfs;
     int32_t pad;
     RfDev rfs[SR_MAX_SCAN_RFS];
+    // per filter: rows tested / rows passed in this batch (nullptr: not counted) -- what RuntimeFilterProbeCollector::
+    // update_selectivity measures (runtime_filter_probe.cpp:408-480)
+    unsigned long long* rf_stats;
+    int32_t rf_stat_index[SR_MAX_SCAN_RFS]; // slot of filter f in rf_stats (the scan's own numbering)
 };
 
 template <bool FAST, bool RF>
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(SCANW_BLOCK) k_scan_mask(const ScanProg* __res
             // RuntimeFilterProbeCollector::evaluate: every filter ANDs into the selection; a NULL probe value passes
             // only a filter that saw a NULL build key.  Only surviving rows pay the bucket read (one 32-byte sector).
 #pragma unroll 1
-            for (int f = 0; f < st.num_rfs && m != 0; f++) {
+            for (int f = 0; f < st.num_rfs && (st.rf_stats ? __any_sync(SR_FULL_MASK, m != 0) : m != 0); f++) {
                 const RfDev& rf = st.rfs[f];
                 uint32_t nulls = 0;
                 long long v[SCANW_ROWS];
@@ -172,6 +176,13 @@ __global__ void __launch_bounds__(SCANW_BLOCK) k_scan_mask(const ScanProg* __res
                 const long long va[4] = {v[0], v[1], v[2], v[3]}, vb[4] = {v[4], v[5], v[6], v[7]};
                 const uint32_t test = m & ~nulls;
                 const uint32_t pass = rf_test_rows<4>(rf, va, test & 15u) | (rf_test_rows<4>(rf, vb, test >> 4) << 4);
+                if (st.rf_stats) { // one pair of atomics per warp, tile and filter
+                    const uint32_t tested = warp_sum((uint32_t)__popc(m)), passed = warp_sum((uint32_t)__popc(pass | (rf.has_null ? m & nulls : 0u)));
+                    if (lane == 0 && tested) {
+                        atomicAdd(st.rf_stats + 2 * st.rf_stat_index[f], (unsigned long long)tested);
+                        atomicAdd(st.rf_stats + 2 * st.rf_stat_index[f] + 1, (unsigned long long)passed);
+                    }
+                }
                 m = pass | (rf.has_null ? m & nulls : 0u);
             }
         }
@@ -413,6 +424,18 @@ struct sr_scan {
     srd::ScanTests tests; // range form of the conjuncts (num_tests == 0: generic evaluation)
     std::vector<std::pair<sr_rf*, int32_t>> rfs; // runtime filters (filter, probe slot)
     std::vector<int32_t> rf_value_ids;
+    // adaptive use of the filters (RuntimeFilterProbeCollector::do_evaluate / update_selectivity, runtime_filter_probe.cpp:
+    // 203-262,408-480): a filter that let more than half of the rows it tested through is not evaluated for the next 31
+    // batches, then sampled again; the reference does the same per 32 chunks
+    struct RfUse {
+        unsigned long long tested = 0, passed = 0; // totals over all batches that evaluated it
+        double last_selectivity = 0.0;
+        int skip_batches = 0;
+        int64_t batches_skipped = 0;
+    };
+    std::vector<RfUse> rf_use;
+    DevBuf rf_stats; // 2 counters per filter, cleared per batch
+    bool rf_adaptive = true;
     std::vector<DevBuf> out_bufs; // 2 per out slot
 };
 
@@ -500,10 +523,25 @@ static int32_t scan_select(sr_scan* s, const sr_chunk_view* in, bool want_counts
     for (int t = 0; t < tests.num_tests; t++)
         if (vt.v[tests.t[t].value_id].nulls != nullptr) tests.num_tests = 0;
     tests.vec0 = tests.num_tests > 0 && (((uintptr_t)vt.v[tests.t[0].value_id].data) & 31) == 0 ? 1 : 0;
-    tests.num_rfs = (int32_t)s->rfs.size();
+    tests.num_rfs = 0;
+    tests.rf_stats = nullptr;
+    if (s->rf_use.size() != s->rfs.size()) s->rf_use.assign(s->rfs.size(), sr_scan::RfUse());
+    const bool count_rf = want_counts && s->rf_adaptive && !s->rfs.empty(); // the compacting call synchronises anyway: read the counters with it
+    if (count_rf) {
+        SR_TRY(s->rf_stats.reserve(ctx, sizeof(unsigned long long) * 2 * SR_MAX_SCAN_RFS));
+        SR_CUDA(ctx, cudaMemsetAsync(s->rf_stats.p, 0, sizeof(unsigned long long) * 2 * SR_MAX_SCAN_RFS, ctx->stream));
+        tests.rf_stats = s->rf_stats.as<unsigned long long>();
+    }
     for (size_t f = 0; f < s->rfs.size(); f++) {
-        SR_TRY(rf_device_desc(s->rfs[f].first, &tests.rfs[f])); // reads min/max once the build side is complete
-        tests.rfs[f].value_id = s->rf_value_ids[f];
+        if (count_rf && s->rf_use[f].skip_batches > 0) { // unselective at its last sample: skipped for now
+            s->rf_use[f].skip_batches--;
+            s->rf_use[f].batches_skipped++;
+            continue;
+        }
+        const int k = tests.num_rfs++;
+        SR_TRY(rf_device_desc(s->rfs[f].first, &tests.rfs[k])); // reads min/max once the build side is complete
+        tests.rfs[k].value_id = s->rf_value_ids[f];
+        tests.rf_stat_index[k] = (int32_t)f;
     }
     if (n > 0) {
         const int grid = (int)std::min<int64_t>((tiles + srd::SCANW_BLOCK / 32 - 1) / (srd::SCANW_BLOCK / 32), (int64_t)ctx->num_sms * 8);
@@ -530,8 +568,20 @@ static int32_t scan_select(sr_scan* s, const sr_chunk_view* in, bool want_counts
             srd::k_scan_counts<<<1, 1024, 0, ctx->stream>>>(s->block_sums.as<uint32_t>(), nblk, s->block_offsets.as<uint64_t>(), ctx->dscratch);
             SR_LAUNCH_CHECK(ctx);
             SR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->dscratch, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            if (count_rf) SR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned + 8, s->rf_stats.p, sizeof(unsigned long long) * 2 * SR_MAX_SCAN_RFS, cudaMemcpyDeviceToHost, ctx->stream));
             SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             *total_out = (int64_t)ctx->pinned[0];
+            if (count_rf) {
+                for (size_t f = 0; f < s->rfs.size(); f++) {
+                    const unsigned long long tested = ctx->pinned[8 + 2 * f], passed = ctx->pinned[8 + 2 * f + 1];
+                    if (tested == 0) continue;
+                    sr_scan::RfUse& u = s->rf_use[f];
+                    u.tested += tested;
+                    u.passed += passed;
+                    u.last_selectivity = (double)passed / (double)tested;
+                    if (u.last_selectivity > 0.5) u.skip_batches = 31; // "useful filter": selectivity <= 0.5 (runtime_filter_probe.cpp:449)
+                }
+            }
         } else {
             *total_out = 0;
         }

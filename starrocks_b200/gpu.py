@@ -82,6 +82,10 @@ def lib():
         "sr_rf_merge_directory": (i32, [vp, vp, i64, i32, vp]),
         "sr_rf_evaluate": (i32, [vp, vp, i32, vp, i32, i32]),
         "sr_scan_add_runtime_filter": (i32, [vp, vp, i32]),
+        "sr_scan_get_rf_stats": (i32, [vp, i32, vp]),
+        "sr_scan_set_rf_adaptive": (i32, [vp, i32]),
+        "sr_rf_copy_in_values": (i32, [vp, vp, i32]),
+        "sr_rf_merge_in_values": (i32, [vp, vp, i32]),
         "sr_agg_create": (vp, [vp, vp]),
         "sr_agg_destroy": (None, [vp]),
         "sr_agg_push": (i32, [vp, vp]),
@@ -148,7 +152,7 @@ EXPORTED_SYMBOLS = [
     "sr_fragment_create",
     "sr_fragment_destroy", "sr_fragment_push", "sr_fragment_agg", "sr_fragment_rows_passed", "sr_xchg_create",
     "sr_join_build_runtime_filter", "sr_rf_create", "sr_rf_insert", "sr_rf_destroy", "sr_rf_get_info", "sr_rf_copy_directory",
-    "sr_rf_merge_directory", "sr_rf_evaluate", "sr_scan_add_runtime_filter",
+    "sr_rf_merge_directory", "sr_rf_evaluate", "sr_scan_add_runtime_filter", "sr_scan_get_rf_stats", "sr_scan_set_rf_adaptive", "sr_rf_copy_in_values", "sr_rf_merge_in_values",
     "sr_xchg_destroy", "sr_xchg_partition", "sr_xchg_hash", "sr_gather", "sr_memcpy", "sr_abi_sizeof", "sr_bandwidth_probe", "sr_flush_l2",
     "sr_chunk_serialized_size", "sr_chunk_serialize", "sr_serde_create", "sr_serde_destroy", "sr_chunk_deserialize",
     "sr_host_alloc", "sr_host_free", "sr_event_create", "sr_event_destroy", "sr_event_record", "sr_event_query", "sr_event_sync",
@@ -268,6 +272,14 @@ class Scan:
         self.ctx.check(lib().sr_scan_filter(self.h, chunk.ref(), C.byref(out)))
         return out
 
+    def rf_stats(self, index):
+        st = abi.sr_scan_rf_stats()
+        self.ctx.check(lib().sr_scan_get_rf_stats(self.h, index, C.byref(st)))
+        return st
+
+    def set_rf_adaptive(self, on):
+        self.ctx.check(lib().sr_scan_set_rf_adaptive(self.h, 1 if on else 0))
+
     def add_runtime_filter(self, rf, probe_slot):
         self.ctx.check(lib().sr_scan_add_runtime_filter(self.h, rf.h, probe_slot))
         self._rfs = getattr(self, "_rfs", []) + [rf]  # the filter must outlive the scan
@@ -305,6 +317,24 @@ class RuntimeFilter:
         out = np.zeros((8 << logb) if logb else 0, dtype=np.uint32)
         self.ctx.check(lib().sr_rf_copy_directory(self.h, out.ctypes.data, out.nbytes, abi.MEM_HOST))
         return out
+
+    def in_values(self):
+        """sorted distinct keys of the IN part (int64 array), or None when the filter has none"""
+        out = np.zeros(abi.RF_IN_FILTER_ROW_LIMIT, dtype=np.int64)
+        n = lib().sr_rf_copy_in_values(self.h, out.ctypes.data, len(out))
+        if n == -1:
+            return None
+        if n < 0:
+            self.ctx.check(n)
+        return out[:n].copy()
+
+    def merge_in_values(self, values):
+        """values: int64 array of the other filter's IN part, or None when it has none"""
+        if values is None:
+            self.ctx.check(lib().sr_rf_merge_in_values(self.h, None, -1))
+        else:
+            v = np.ascontiguousarray(values, dtype=np.int64)
+            self.ctx.check(lib().sr_rf_merge_in_values(self.h, v.ctypes.data if v.size else None, len(v)))
 
     def merge(self, directory, info):
         """directory: uint32 array (host) of the other filter, info: its sr_rf_info"""

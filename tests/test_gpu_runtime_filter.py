@@ -22,7 +22,7 @@ KEY_CASES = [
 
 
 def _same_info(a, b):
-    for f in ("min_value", "max_value", "num_inserted", "has_null", "log_num_buckets", "key_type"):
+    for f in ("min_value", "max_value", "num_inserted", "has_null", "log_num_buckets", "key_type", "num_in_values"):
         assert getattr(a, f) == getattr(b, f), f
 
 
@@ -167,6 +167,92 @@ def test_scan_applies_attached_runtime_filters(gpu, ctx, oracle, fast, n):
                 assert np.array_equal(nulls, nl[keep])
         if n:  # the filters do drop rows the conjuncts keep
             assert expect.sum() < oracle.scan_evaluate(sd, chunk).sum()
+    finally:
+        scan.close()
+        g1.close()
+        g2.close()
+
+
+@pytest.mark.parametrize("dtype,typ,lo,hi", KEY_CASES)
+@pytest.mark.parametrize("n", [1, 40, 1024, 1025])
+def test_runtime_in_filter(gpu, ctx, oracle, dtype, typ, lo, hi, n):
+    # runtime IN filter (HashJoiner::_create_runtime_in_filters, hash_joiner.cpp:563-609; row limit 1024): a small build side
+    # also publishes its distinct keys, membership becomes EXACT (no bloom false positive); beyond the limit the IN part is gone
+    rng = np.random.default_rng(61 + n)
+    keys = rng.integers(lo, hi, n).astype(dtype)
+    half = n // 2
+    g, o = gpu.RuntimeFilter(ctx, typ, n), oracle.RuntimeFilter(typ, n)
+    try:
+        for f in (g, o):
+            f.insert(Chunk([(0, keys[:half], rand_nulls(rng, half, 0.1) if half > 3 else None, typ)]), 0)
+            f.insert(Chunk([(0, keys[half:], None, typ)]), 0)
+        _same_info(g.info(), o.info())
+        vals = g.in_values()
+        if n <= abi.RF_IN_FILTER_ROW_LIMIT:
+            assert vals is not None and len(vals) == g.info().num_in_values and (np.diff(vals) > 0).all()
+        else:
+            assert vals is None and g.info().num_in_values == -1
+        probe = np.concatenate([keys, rng.integers(lo, hi, 50_000).astype(dtype)])
+        pc = Chunk([(3, probe, rand_nulls(rng, len(probe), 0.02), typ)])
+        sel = g.evaluate(pc, 3)
+        assert np.array_equal(sel, o.evaluate(pc, 3))
+        if vals is not None:      # exact: a row passes iff its value is one of the inserted keys
+            nn = pc.columns()[0][2] == 0
+            assert np.array_equal(sel[nn].astype(bool), np.isin(probe[nn].astype(np.int64), vals))
+    finally:
+        g.close()
+
+
+def test_runtime_in_filter_merge(gpu, ctx, oracle):
+    a, b, c = (gpu.RuntimeFilter(ctx, abi.TYPE_INT, 100) for _ in range(3))
+    big = gpu.RuntimeFilter(ctx, abi.TYPE_INT, 5000)
+    try:
+        a.insert(Chunk([(0, np.arange(0, 600, dtype=np.int32), None)]), 0)
+        b.insert(Chunk([(0, np.arange(500, 900, dtype=np.int32), None)]), 0)
+        a.merge_in_values(b.in_values())
+        assert np.array_equal(a.in_values(), np.arange(0, 900))
+        c.insert(Chunk([(0, np.arange(2000, 2300, dtype=np.int32), None)]), 0)
+        a.merge_in_values(c.in_values())          # 1200 distinct keys: over the limit -> no IN part
+        assert a.in_values() is None
+        big.insert(Chunk([(0, np.arange(5000, dtype=np.int32), None)]), 0)
+        assert big.in_values() is None
+        b.merge_in_values(big.in_values())        # a partial filter without an IN part -> the total has none
+        assert b.in_values() is None
+    finally:
+        for f in (a, b, c, big):
+            f.close()
+
+
+def test_scan_stops_evaluating_an_unselective_filter(gpu, ctx, oracle):
+    # RuntimeFilterProbeCollector::update_selectivity (runtime_filter_probe.cpp:408-480): a filter that lets more than half of
+    # its rows through is switched off for the next 31 batches; the result is the same set of rows a plan without that
+    # filter plus the join would keep, so parity here is against the oracle WITH the filters for the batches that used
+    # them and the bookkeeping is checked through sr_scan_get_rf_stats
+    rng = np.random.default_rng(71)
+    n = 200_000
+    useful = rng.choice(100_000, 5_000, replace=False).astype(np.int32)        # ~5 % of the probe keys
+    useless = np.arange(0, 95_000, dtype=np.int32)                              # ~95 % of the probe keys
+    chunk = Chunk([(0, rng.integers(0, 100_000, n, dtype=np.int32), None), (1, rng.integers(0, 100_000, n, dtype=np.int32), None)])
+    sd = abi.ScanDesc(out_slots=[0, 1])
+    g1, g2 = gpu.RuntimeFilter(ctx, abi.TYPE_INT, len(useful)), gpu.RuntimeFilter(ctx, abi.TYPE_INT, len(useless))
+    o1, o2 = oracle.RuntimeFilter(abi.TYPE_INT, len(useful)), oracle.RuntimeFilter(abi.TYPE_INT, len(useless))
+    for f, keys in ((g1, useful), (o1, useful), (g2, useless), (o2, useless)):
+        f.insert(Chunk([(0, keys, None)]), 0)
+    scan = gpu.Scan(ctx, sd)
+    try:
+        scan.add_runtime_filter(g1, 0)
+        scan.add_runtime_filter(g2, 1)
+        both = o2.evaluate(chunk, 1, o1.evaluate(chunk, 0)).astype(bool)
+        only1 = o1.evaluate(chunk, 0).astype(bool)
+        rows = [gpu.chunk_out_to_host(ctx, scan.filter(chunk))[0][2] for _ in range(4)]
+        assert np.array_equal(rows[0], chunk.columns()[0][1][both])               # batch 0 samples both filters
+        for r in rows[1:]:
+            assert np.array_equal(r, chunk.columns()[0][1][only1])                # the unselective one is off afterwards
+        s1, s2 = scan.rf_stats(0), scan.rf_stats(1)
+        assert s1.batches_skipped == 0 and s1.rows_tested == 4 * n and s1.last_selectivity < 0.1
+        assert s2.batches_skipped == 3 and s2.last_selectivity > 0.9 and s2.rows_tested == s1.rows_passed // 4
+        scan.set_rf_adaptive(False)                                               # every filter on every batch again
+        assert np.array_equal(gpu.chunk_out_to_host(ctx, scan.filter(chunk))[0][2], chunk.columns()[0][1][both])
     finally:
         scan.close()
         g1.close()
