@@ -174,6 +174,20 @@ def all_reduce_runtime_filter(directory, min_value, max_value, num_inserted, has
     return int(lo[0]), int(hi[0]), int(cnt[0]), bool(int(hi[1]))
 
 
+def all_gather_in_values(values, row_limit=1024):
+    """the IN part of a global runtime filter (PartialRuntimeFilterMerger: the total filter keeps its IN list only when every
+    partial filter has one and the union stays within the row limit).  values: sorted int64 numpy array of this rank's IN
+    part or None.  Returns the merged array (the same on every rank) or None."""
+    import numpy as np
+    world = dist.get_world_size()
+    parts = [None] * world
+    dist.all_gather_object(parts, None if values is None else np.asarray(values, dtype=np.int64).tolist())
+    if any(p is None for p in parts):
+        return None
+    merged = np.unique(np.concatenate([np.asarray(p, dtype=np.int64) for p in parts])) if parts else np.zeros(0, dtype=np.int64)
+    return None if len(merged) > row_limit else merged
+
+
 def exchange_partitions(cols, channel_offsets):
     """HASH_PARTITIONED exchange.  cols: list of 1-D tensors already reordered so that the rows of channel c occupy
     [channel_offsets[c], channel_offsets[c+1]) (what sr_xchg_partition / the reference's counting sort produce);

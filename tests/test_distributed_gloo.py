@@ -146,6 +146,14 @@ def _global_runtime_filter_worker(rank, world, port, q):
     merged.merge(other)
     probe = Chunk([(0, rng.integers(-10**7, 10**7, 20_000, dtype=np.int64), rand_nulls(rng, 20_000, 0.02))])
     ok = ok and np.array_equal(merged.evaluate(probe, 0), whole.evaluate(probe, 0)) and np.array_equal(merged.directory(), directory.numpy().view(np.uint32))
+    # the IN part of a global filter: the union of the partial key lists, gone as soon as one partial filter has none or the
+    # union exceeds the row limit
+    from starrocks_b200.distributed import all_gather_in_values
+    small = np.arange(rank * 300, rank * 300 + 400, dtype=np.int64)         # overlapping ranges: 700 distinct keys over 2 ranks
+    got = all_gather_in_values(small)
+    ok = ok and got is not None and np.array_equal(got, np.arange(0, 300 * (world - 1) + 400))
+    ok = ok and all_gather_in_values(small if rank == 0 else None) is None
+    ok = ok and all_gather_in_values(np.arange(rank * 1000, rank * 1000 + 600, dtype=np.int64)) is None
     q.put(bool(ok))
     dist.barrier()
     dist.destroy_process_group()
