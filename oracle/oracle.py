@@ -42,11 +42,37 @@ BUCKET_CHAINED, DIRECT_MAPPING, RANGE_DIRECT_MAPPING, RANGE_DIRECT_MAPPING_SET =
 DENSE_RANGE_DIRECT_MAPPING, LINEAR_CHAINED, LINEAR_CHAINED_SET = 5, 6, 7
 
 
+def _source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("sr_oracle.cpp", "sr_oracle.h", os.path.join("..", "include", "sr_gpu_ops.h")):
+        with open(os.path.join(_HERE, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def _recorded_hash():
+    try:
+        with open(os.path.join(_HERE, "libsr_oracle.so.srchash")) as fh:
+            return fh.read().strip()
+    except OSError:
+        return None
+
+
 def build():
     """compile oracle/libsr_oracle.so (g++, seconds) and, where the reference tree is present, oracle/_ref (the pieces of the
     path that compile from the reference's own sources: the vendored xxHash, the frame-of-reference page codec)."""
-    subprocess.check_call(["make", "-C", _HERE, "-s"])
-    subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+    import fcntl
+    with open(os.path.join(_HERE, "libsr_oracle.so.lock"), "w") as lock:      # the ranks of a torchrun job may all land here
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not (os.path.exists(os.path.join(_HERE, "libsr_oracle.so")) and _recorded_hash() == _source_hash()):
+                subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libsr_oracle.so"])
+                with open(os.path.join(_HERE, "libsr_oracle.so.srchash"), "w") as fh:
+                    fh.write(_source_hash())
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 def ref_xxh3():
@@ -65,7 +91,8 @@ def lib():
     if _LIB is not None:
         return _LIB
     path = os.path.join(_HERE, "libsr_oracle.so")
-    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(_HERE, "sr_oracle.cpp")):
+    # stale = the sources' content differs from what the library was built from (file times do not survive a copy of the tree)
+    if not os.path.exists(path) or _recorded_hash() != _source_hash():
         build()
     L = C.CDLL(path)
     u32, i32, i64, vp = C.c_uint32, C.c_int32, C.c_int64, C.c_void_p

@@ -576,7 +576,8 @@ constexpr size_t STREAM_TMA_SMEM = (size_t)STREAM_TMA_STAGES * 2 * STREAM_TILE *
 template <bool CARRY>
 __global__ void __launch_bounds__(STREAM_BLOCK, 2) k_frag_stream_tests_tma(const FragDev* __restrict__ fdp, PassDev pd, const __grid_constant__ VTab vt, int64_t n,
                                                                            uint32_t bitmap_bytes, SelEntry* __restrict__ sel_out, unsigned long long* __restrict__ counter) {
-    extern __shared__ __align__(128) uint32_t smem[];
+    extern __shared__ __align__(128) uint32_t smem_tma[];
+    uint32_t* const smem = smem_tma;
     __shared__ FragJoinDev s_joins[STREAM_MAX_JOINS];
     __shared__ StreamTest s_tests[SR_MAX_STREAM_TESTS];
     __shared__ __align__(8) uint64_t s_full[STREAM_TMA_STAGES], s_empty[STREAM_TMA_STAGES];

@@ -1158,7 +1158,7 @@ int32_t sr_agg_push_selective(sr_agg* a, const sr_chunk_view* chunk, sr_chunk_ou
     srd::k_agg_push_existing<<<std::min(grid_for(n, srd::AGG_BLOCK), ctx->num_sms * 8), srd::AGG_BLOCK, 0, ctx->stream>>>((const srd::AggDev*)a->dev.p, vt, n,
                                                                                                                        a->sel_flags.as<uint8_t>());
     SR_LAUNCH_CHECK(ctx);
-    cub::TransformInputIterator<uint32_t, srd::U8ToU32, const uint8_t*> fin(a->sel_flags.as<uint8_t>(), srd::U8ToU32());
+    auto fin = thrust::make_transform_iterator((const uint8_t*)a->sel_flags.as<uint8_t>(), srd::U8ToU32());
     size_t tb = 0;
     SR_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, fin, a->sel_pos.as<uint32_t>(), (int)(n + 1), ctx->stream));
     SR_TRY(a->sel_tmp.reserve(ctx, std::max<size_t>(tb, 16)));

@@ -19,7 +19,7 @@
 #pragma once
 
 #include <cub/device/device_scan.cuh>       // prefix sums of the other-join-conjunct emit flags
-#include <cub/iterator/transform_input_iterator.cuh>
+#include <thrust/iterator/transform_iterator.h>
 #include <cub/device/device_radix_sort.cuh> // stable (bucket, row) sort for the deterministic-chain pass of the build (cold path)
 
 #include "sr_scan.cuh"
@@ -1075,7 +1075,8 @@ static int32_t join_apply_conjunct(sr_join* j, ProberState& ps, int64_t n, int64
     srd::k_conj_flags<<<grid, 256, 0, ctx->stream>>>(j->desc.join_type, ncand, n, ps.conj_keep.as<uint8_t>(), ps.conj_any.as<uint8_t>());
     SR_LAUNCH_CHECK(ctx);
     // exclusive prefix sums over ncand + 1 / n + 1 flags (the last flag is 0: its sum is the total)
-    cub::TransformInputIterator<uint32_t, srd::U8ToU32, const uint8_t*> kin(ps.conj_keep.as<uint8_t>(), srd::U8ToU32()), uin(ps.conj_any.as<uint8_t>(), srd::U8ToU32());
+    auto kin = thrust::make_transform_iterator((const uint8_t*)ps.conj_keep.as<uint8_t>(), srd::U8ToU32());
+    auto uin = thrust::make_transform_iterator((const uint8_t*)ps.conj_any.as<uint8_t>(), srd::U8ToU32());
     size_t tb1 = 0, tb2 = 0;
     SR_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb1, kin, ps.conj_k.as<uint32_t>(), (int)(ncand + 1), ctx->stream));
     SR_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb2, uin, ps.conj_u.as<uint32_t>(), (int)(n + 1), ctx->stream));

@@ -19,13 +19,53 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-cudart", "static"]
 
 
+def _source_files():
+    csrc = os.path.join(_HERE, "csrc")
+    return sorted(os.path.join(csrc, f) for f in os.listdir(csrc)) + [os.path.join(_HERE, "..", "include", "sr_gpu_ops.h")]
+
+
+def _source_hash():
+    """content hash of everything the library is compiled from: survives copies of the tree (file times do not -- a fresh
+    checkout / the snapshot sent to a GPU box would otherwise look stale and every process would recompile on import)"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in _source_files():
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS + os.environ.get("SR_NVCC_EXTRA", "").split()).encode())
+    return h.hexdigest()
+
+
 def build(verbose=False):
-    """compile libsr_gpu.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    """compile libsr_gpu.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).  Safe against concurrent callers
+    (the ranks of a torchrun job): one process compiles under a file lock into a temporary name and renames it into place."""
+    import fcntl
     src = os.path.join(_HERE, "csrc", "sr_gpu.cu")
     extra = os.environ.get("SR_NVCC_EXTRA", "").split()   # e.g. -DSR_EXPERIMENT_... for timing experiments
-    cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, src]
-    subprocess.check_call(cmd)
+    want = _source_hash()
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not verbose and os.path.exists(LIB_PATH) and _recorded_hash() == want:
+                return LIB_PATH                     # another process built it while this one waited for the lock
+            tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+            cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, src]
+            subprocess.check_call(cmd)
+            os.replace(tmp, LIB_PATH)
+            with open(LIB_PATH + ".srchash", "w") as fh:
+                fh.write(want)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
+
+
+def _recorded_hash():
+    try:
+        with open(LIB_PATH + ".srchash") as fh:
+            return fh.read().strip()
+    except OSError:
+        return None
 
 
 def _needs_build():
@@ -33,10 +73,7 @@ def _needs_build():
         return True
     if os.environ.get("SR_GPU_LIB"):
         return False
-    t = os.path.getmtime(LIB_PATH)
-    csrc = os.path.join(_HERE, "csrc")
-    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(_HERE, "..", "include", "sr_gpu_ops.h")]
-    return any(os.path.getmtime(s) > t for s in srcs)
+    return _recorded_hash() != _source_hash()
 
 
 def lib():
