@@ -182,9 +182,10 @@ def test_runtime_in_filter(gpu, ctx, oracle, dtype, typ, lo, hi, n):
     keys = rng.integers(lo, hi, n).astype(dtype)
     half = n // 2
     g, o = gpu.RuntimeFilter(ctx, typ, n), oracle.RuntimeFilter(typ, n)
+    first_nulls = rand_nulls(rng, half, 0.1) if half > 3 else None
     try:
         for f in (g, o):
-            f.insert(Chunk([(0, keys[:half], rand_nulls(rng, half, 0.1) if half > 3 else None, typ)]), 0)
+            f.insert(Chunk([(0, keys[:half], first_nulls, typ)]), 0)
             f.insert(Chunk([(0, keys[half:], None, typ)]), 0)
         _same_info(g.info(), o.info())
         vals = g.in_values()
