@@ -480,6 +480,18 @@ def chunk_serialize(chunk, row_begin=0, row_end=None):
     return buf
 
 
+def ref_hash():
+    """oracle/_ref/libhash_ref.so (HashUtil::fnv_hash / zlib_crc_hash and crc_hash_32 of the reference), or None when it was never built"""
+    path = os.path.join(_HERE, "_ref", "libhash_ref.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    for nm in ("ref_fnv_hash", "ref_zlib_crc_hash", "ref_crc_hash_32"):
+        getattr(L, nm).restype = C.c_uint32
+        getattr(L, nm).argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+    return L
+
+
 def ref_for():
     """oracle/_ref/libfor_ref.so (the reference's own ForEncoder / ForDecoder), or None when it was never built"""
     path = os.path.join(_HERE, "_ref", "libfor_ref.so")

@@ -748,3 +748,21 @@ def test_other_join_conjunct_known_answers(oracle):
         assert list(zip(pi.tolist(), bi.tolist())) == pairs, jt
         if jt in remain:
             assert j.probe_remain([abi.TYPE_INT])[-1][1].tolist() == remain[jt], jt
+
+
+def test_exchange_and_join_hashes_against_the_reference_functions(oracle):
+    # HashUtil::fnv_hash / zlib_crc_hash (hash_util.hpp:34-45,127-134) and crc_hash_32 (hash.h:96-130) compiled from the
+    # reference tree (oracle/_ref/libhash_ref.so) against the restatements, on random byte strings of every length 0..40 and
+    # a few long ones, three seeds each
+    ref = oracle.ref_hash()
+    if ref is None:
+        pytest.skip("oracle/_ref/libhash_ref.so not built (no reference tree on this machine)")
+    o = oracle.lib()
+    rng = np.random.default_rng(2)
+    for n in list(range(0, 41)) + [100, 1000, 4097]:
+        b = rng.integers(0, 256, max(n, 1), dtype=np.uint8)
+        for seed in (0, 0x811C9DC5, 12345):
+            p = b.ctypes.data
+            assert ref.ref_fnv_hash(p, n, seed) == o.orc_fnv_hash(p, n, seed), ("fnv", n, seed)
+            assert ref.ref_zlib_crc_hash(p, n, seed) == o.orc_zlib_crc32(p, n, seed), ("zlib crc", n, seed)
+            assert ref.ref_crc_hash_32(p, n, seed) == o.orc_crc_hash_32(p, n, seed), ("crc_hash_32", n, seed)
