@@ -195,7 +195,44 @@ def _shuffle_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("worker", [_two_phase_worker, _intermediate_format_worker, _global_runtime_filter_worker, _shuffle_worker])
+def _q95_worker(rank, world, port, q):
+    """the distributed TPC-DS Q95 plan (tools/q95_distributed.py) on the CPU: each rank generates its block of orders, both tables
+    are HASH_PARTITIONED on the order number (oracle.hash_partition = FNV + ReduceOp) and exchanged, the local plan runs on
+    the oracle engine, the three results are summed -- and must equal the join-free evaluation of the whole query"""
+    from oracle import oracle
+    from starrocks_b200 import tpcds
+    from starrocks_b200.distributed import exchange_partitions
+    _init(rank, world, port)
+    g = tpcds.Q95Gen(0.4)
+    blk = (g.n_orders + world - 1) // world
+    lo, hi = min(g.n_orders, rank * blk), min(g.n_orders, (rank + 1) * blk)
+    ws, wr = g.web_sales_of_orders(lo, hi), g.web_returns_of_orders(lo, hi)
+
+    def shuffle(table, cols, key_slot):
+        chunk = tpcds.table_chunk(table, cols)
+        _, _, ri, st = oracle.hash_partition(abi.make_part_desc([key_slot], world), chunk)
+        recv = exchange_partitions([torch.from_numpy(np.ascontiguousarray(table[name][ri])) for name, _, _ in cols], st.tolist())
+        return Chunk([(slot, r.numpy(), None, typ) for (_, slot, typ), r in zip(cols, recv)])
+
+    ws_local = shuffle(ws, tpcds.WS_COLS, tpcds.WS_ORDER)
+    wr_local = shuffle(wr, [("wr_order_number", tpcds.WS_ORDER, abi.TYPE_BIGINT)], tpcds.WS_ORDER)
+    dims = {"date": Chunk([(tpcds.D_DATE_SK, g.date_keys(), None)]), "addr": Chunk([(tpcds.CA_ADDRESS_SK, g.address_keys(), None)]),
+            "site": Chunk([(tpcds.WEB_SITE_SK, g.site_keys(), None)])}
+    res, st = tpcds.q95_local_plan(tpcds.OracleEngine(oracle), ws_local, wr_local, dims, morsel_rows=40_000)
+    tot = torch.tensor(list(res) + [ws_local.num_rows], dtype=torch.int64)
+    dist.all_reduce(tot)
+    exp = g.expected(0, g.n_orders)
+    ok = tuple(int(x) for x in tot[:3]) == exp and exp[0] > 10
+    ok = ok and int(tot[3]) == len(g.web_sales_of_orders(0, g.n_orders)["ws_order_number"])      # no row lost or duplicated by the exchange
+    # every order is complete on exactly one rank: its order numbers hash to this rank
+    _, ch, _, _ = oracle.hash_partition(abi.make_part_desc([tpcds.WS_ORDER], world), ws_local)
+    ok = ok and bool((ch == rank).all())
+    q.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("worker", [_two_phase_worker, _intermediate_format_worker, _global_runtime_filter_worker, _shuffle_worker, _q95_worker])
 def test_world_size_2_gloo(oracle, worker):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
