@@ -766,3 +766,64 @@ def test_exchange_and_join_hashes_against_the_reference_functions(oracle):
             assert ref.ref_fnv_hash(p, n, seed) == o.orc_fnv_hash(p, n, seed), ("fnv", n, seed)
             assert ref.ref_zlib_crc_hash(p, n, seed) == o.orc_zlib_crc32(p, n, seed), ("zlib crc", n, seed)
             assert ref.ref_crc_hash_32(p, n, seed) == o.orc_crc_hash_32(p, n, seed), ("crc_hash_32", n, seed)
+
+
+@pytest.mark.parametrize("with_conjunct", [False, True])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_join_types_against_a_row_at_a_time_definition(oracle, seed, with_conjunct):
+    # every join type (probe phase + POST_PROBE rows) against the textbook definition evaluated row by row in Python: the equi
+    # key with SQL NULL semantics (NULL never equals), the other-join conjunct a < b with NULL = false, duplicates on both sides
+    rng = np.random.default_rng(seed)
+    nb, npr = 60, 90
+    bk, pk = rng.integers(0, 12, nb).astype(np.int32), rng.integers(-1, 14, npr).astype(np.int32)
+    bkn, pkn = (rng.random(nb) < 0.1).astype(np.uint8), (rng.random(npr) < 0.1).astype(np.uint8)
+    bv, pv = rng.integers(0, 10, nb).astype(np.int32), rng.integers(0, 10, npr).astype(np.int32)
+    bvn, pvn = (rng.random(nb) < 0.15).astype(np.uint8), (rng.random(npr) < 0.15).astype(np.uint8)
+    build = Chunk([(10, bk, bkn), (11, bv, bvn)])
+    probe = Chunk([(0, pk, pkn), (1, pv, pvn)])
+
+    def match(i, b):      # probe row i joins build row b
+        if pkn[i] or bkn[b] or pk[i] != bk[b]:
+            return False
+        if with_conjunct and (pvn[i] or bvn[b] or not pv[i] < bv[b]):
+            return False
+        return True
+
+    P = lambda i: (None if pkn[i] else int(pk[i]), None if pvn[i] else int(pv[i]))
+    B = lambda b: (None if bkn[b] else int(bk[b]), None if bvn[b] else int(bv[b]))
+    NP, NB = (None, None), (None, None)
+    pairs = [(i, b) for i in range(npr) for b in range(nb) if match(i, b)]
+    p_any = {i for i, _ in pairs}
+    b_any = {b for _, b in pairs}
+    want = {
+        abi.JOIN_INNER: [P(i) + B(b) for i, b in pairs],
+        abi.JOIN_LEFT_OUTER: [P(i) + B(b) for i, b in pairs] + [P(i) + NB for i in range(npr) if i not in p_any],
+        abi.JOIN_LEFT_SEMI: [P(i) for i in range(npr) if i in p_any],
+        abi.JOIN_LEFT_ANTI: [P(i) for i in range(npr) if i not in p_any],
+        abi.JOIN_RIGHT_OUTER: [P(i) + B(b) for i, b in pairs] + [NP + B(b) for b in range(nb) if b not in b_any],
+        abi.JOIN_FULL_OUTER: [P(i) + B(b) for i, b in pairs] + [P(i) + NB for i in range(npr) if i not in p_any] + [NP + B(b) for b in range(nb) if b not in b_any],
+        abi.JOIN_RIGHT_SEMI: [B(b) for b in range(nb) if b in b_any],
+        abi.JOIN_RIGHT_ANTI: [B(b) for b in range(nb) if b not in b_any],
+    }
+    key = lambda r: tuple((0, 0) if v is None else (1, v) for v in r)
+    for jt, exp in want.items():
+        d = abi.make_join_desc(jt, [10], [0], [abi.TYPE_INT], build_out=[10, 11], probe_out=[0, 1],
+                               other_conjunct=[("col", 1), ("col", 11), "<"] if with_conjunct else None)
+        j = oracle.Join(d)
+        j.append_build(build)
+        j.build()
+        got = []
+        for lo, hi in ((0, 40), (40, npr)):         # two probe calls: marks accumulate across them
+            ch = Chunk([(s, a[lo:hi].copy(), nl[lo:hi].copy()) for s, a, nl in probe.columns()])
+            pi, bi = j.probe_all(ch)
+            cols = j.output(ch, pi, bi)
+            vals = [[None if nl[q] else int(a[q]) for q in range(len(pi))] for _, a, nl in cols]
+            got += list(zip(*vals)) if vals and len(pi) else []
+        if jt in (abi.JOIN_RIGHT_OUTER, abi.JOIN_FULL_OUTER, abi.JOIN_RIGHT_SEMI, abi.JOIN_RIGHT_ANTI):
+            rem = j.probe_remain([abi.TYPE_INT, abi.TYPE_INT])
+            n = len(rem[0][1])
+            vals = [[None if nl[q] else int(a[q]) for q in range(n)] for _, a, nl in rem]
+            got += list(zip(*vals)) if n else []
+        if jt in (abi.JOIN_RIGHT_SEMI, abi.JOIN_RIGHT_ANTI):
+            got = [r[-2:] for r in got]
+        assert sorted(got, key=key) == sorted(exp, key=key), (jt, with_conjunct)
