@@ -1150,7 +1150,7 @@ int32_t sr_agg_push_selective(sr_agg* a, const sr_chunk_view* chunk, sr_chunk_ou
         return SR_OK;
     }
     if (n == 0) return SR_OK;
-    if (n >= 0xFFFFFFF0ll) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "selective push of more than 2^32 rows");
+    if (n >= 0x7FFFFFF0ll) return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "selective push of more than 2^31 rows: push smaller batches");
     SR_TRY(a->sel_flags.reserve(ctx, (size_t)n + 16));
     SR_TRY(a->sel_pos.reserve(ctx, sizeof(uint32_t) * ((size_t)n + 2)));
     SR_CUDA(ctx, cudaMemsetAsync((uint8_t*)a->sel_flags.p + n, 0, 1, ctx->stream)); // flag n = 0: its prefix sum is the total

@@ -1038,6 +1038,9 @@ static int32_t conj_slot_type(void* user, int32_t slot) {
 static int32_t join_apply_conjunct(sr_join* j, ProberState& ps, int64_t n, int64_t* total, uint8_t* match) {
     sr_ctx* ctx = j->ctx;
     const int64_t ncand = *total;
+    if (ncand >= 0x7FFFFFF0ll || n >= 0x7FFFFFF0ll)
+        return sr_fail(ctx, SR_ERR_NOT_SUPPORTED, "other-join conjunct over %lld candidate pairs / %lld probe rows: probe in smaller batches (the prefix sums index with 32 bits)",
+                       (long long)ncand, (long long)n);
     ConjTypeCtx tc{j, &ps.staged};
     if (!j->conj_compiled) {
         j->conj_reg = VReg();
