@@ -315,8 +315,10 @@ static int32_t pages_decode(sr_ctx* ctx, PageScratch* sc, int32_t encoding, int3
     if (!out) return sr_fail(ctx, SR_ERR_INVALID_ARGUMENT, "null output");
     SR_CUDA(ctx, cudaMemcpyAsync(sc->pages.p, hp, sizeof(srd::PageDesc) * (size_t)num_pages, cudaMemcpyHostToDevice, ctx->stream));
     if (encoding == SR_PAGE_PLAIN) {
-        srd::k_plain_copy<<<dim3(32, num_pages), 256, 0, ctx->stream>>>((const srd::PageDesc*)sc->pages.p, w, (uint8_t*)out);
-        SR_LAUNCH_CHECK(ctx);
+        for (int p0 = 0; p0 < num_pages; p0 += 65535) { // gridDim.y is limited to 65535
+            srd::k_plain_copy<<<dim3(32, std::min(num_pages - p0, 65535)), 256, 0, ctx->stream>>>((const srd::PageDesc*)sc->pages.p + p0, w, (uint8_t*)out);
+            SR_LAUNCH_CHECK(ctx);
+        }
         return SR_OK;
     }
     SR_TRY(sc->frames.reserve(ctx, sizeof(srd::FrameDesc) * (size_t)frames));
