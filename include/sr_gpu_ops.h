@@ -246,9 +246,12 @@ typedef struct sr_scan_desc {
 
 typedef struct sr_scan sr_scan;
 
+/* ScanOperator / ChunkSource::prepare with the conjuncts of the scan node (scan_operator.cpp:69-112). */
 sr_scan* sr_scan_create(sr_ctx* ctx, const sr_scan_desc* desc);
 void sr_scan_destroy(sr_scan* scan);
-/* filter one batch.  `out` receives DEVICE buffers (owned by the scan handle, valid until the
+/* OlapChunkSource::_read_chunk_from_storage, the part behind the segment iterator (olap_chunk_source.cpp:676-722);
+ * the adapter's ScanOperator::pull_chunk (scan_operator.cpp:286-309) hands its result on.
+ * filter one batch.  `out` receives DEVICE buffers (owned by the scan handle, valid until the
  * next push) holding the surviving rows in input order; out->num_rows is filled after an
  * internal sync on the tiny row counter. */
 int32_t sr_scan_filter(sr_scan* scan, const sr_chunk_view* in, sr_chunk_out* out);
@@ -339,10 +342,16 @@ typedef struct sr_join_info {
     int64_t min_value, max_value;
 } sr_join_info;
 
+/* HashJoiner::prepare_builder / prepare_prober + _init_hash_table_param (be/src/exec/hash_joiner.cpp:115-211). */
 sr_join* sr_join_create(sr_ctx* ctx, const sr_join_desc* desc);
 void sr_join_destroy(sr_join* join);
+/* HashJoinBuildOperator::push_chunk -> HashJoiner::append_chunk_to_ht (hash_join_build_operator.cpp:41-43,
+ * hash_joiner.cpp:213-223). */
 int32_t sr_join_append_build(sr_join* join, const sr_chunk_view* chunk);
+/* HashJoinBuildOperator::set_finishing -> HashJoiner::build_ht (hash_join_build_operator.cpp:86-220, hash_joiner.cpp:248-262):
+ * chooses the hash-map method and builds first[] / next[]. */
 int32_t sr_join_build_finish(sr_join* join);
+/* HashJoinProbeOperator::is_ready (hash_join_probe_operator.cpp:75-77): probers wait for HashJoinPhase::PROBE. */
 int32_t sr_join_is_build_done(const sr_join* join);
 int32_t sr_join_get_info(const sr_join* join, sr_join_info* info);
 /* copy first[] / next[] back to the host (test / debug aid; sizes from sr_join_get_info:
@@ -350,7 +359,9 @@ int32_t sr_join_get_info(const sr_join* join, sr_join_info* info);
  * the reference layout. */
 int32_t sr_join_copy_table(sr_join* join, uint32_t* first_host, uint32_t* next_host);
 
-/* Probe one batch (any number of rows).  Output rows keep probe order; matches of one probe
+/* HashJoinProbeOperator::push_chunk + pull_chunk -> HashJoiner::push_chunk / _pull_probe_output_chunk
+ * (hash_join_probe_operator.cpp:79-88, hash_joiner.cpp:288-330) -> JoinHashTable::probe (join_hash_table.cpp:695-702).
+ * Probe one batch (any number of rows).  Output rows keep probe order; matches of one probe
  * row are adjacent.  `out` holds DEVICE buffers owned by the join handle (per prober_id),
  * valid until the next probe with the same prober_id.  Also exposes the
  * (probe_index, build_index) pairs of HashTableProbeState
@@ -495,13 +506,21 @@ typedef struct sr_agg_desc {
 
 typedef struct sr_agg sr_agg;
 
+/* Aggregator::prepare: hash-map variant and function states from the plan node (be/src/exec/aggregator.cpp:411-570). */
 sr_agg* sr_agg_create(sr_ctx* ctx, const sr_agg_desc* desc);
 void sr_agg_destroy(sr_agg* agg);
+/* AggregateBlockingSinkOperator::push_chunk (aggregate_blocking_sink_operator.cpp:101-138): evaluate_groupby_exprs +
+ * evaluate_agg_fn_exprs + build_hash_map + compute_batch_agg_states (aggregator.cpp:1044,1376,1616,907), or
+ * compute_single_agg_state (:882) without group keys. */
 int32_t sr_agg_push(sr_agg* agg, const sr_chunk_view* chunk);
+/* AggregateBlockingSinkOperator::set_finishing (aggregate_blocking_sink_operator.cpp:56-89): input done, the hash-map
+ * iterator is positioned for the source. */
 int32_t sr_agg_sink_finish(sr_agg* agg);
 /* number of result rows (groups); valid after sink_finish (synchronises on a counter). */
 int64_t sr_agg_num_groups(sr_agg* agg);
-/* Emit up to max_rows groups starting at the handle's cursor: key columns (group_slots order)
+/* AggregateBlockingSourceOperator::pull_chunk (aggregate_blocking_source_operator.cpp:47-72) ->
+ * Aggregator::convert_hash_map_to_chunk / convert_to_chunk_no_groupby (aggregator.cpp:1696-1791, 997-1042).
+ * Emit up to max_rows groups starting at the handle's cursor: key columns (group_slots order)
  * then one result column per function.  out_mem selects host (copied back, synchronised) or
  * device buffers.  Returns SR_OK with out->num_rows == 0 at end of stream. */
 int32_t sr_agg_pull(sr_agg* agg, int64_t max_rows, int32_t out_mem, sr_chunk_out* out);
@@ -602,7 +621,9 @@ typedef struct sr_fragment sr_fragment;
 
 sr_fragment* sr_fragment_create(sr_ctx* ctx, const sr_fragment_desc* desc);
 void sr_fragment_destroy(sr_fragment* frag);
-/* consume one batch of fact rows (one morsel: any number of rows). */
+/* what PipelineDriver::process (pipeline_driver.cpp:270-500) does for one morsel of the probe-side pipeline: scan filter,
+ * every HashJoinProbeOperator in turn, AggregateBlockingSinkOperator::push_chunk -- with no chunk materialised in between.
+ * consume one batch of fact rows (one morsel: any number of rows). */
 int32_t sr_fragment_push(sr_fragment* frag, const sr_chunk_view* fact);
 /* the aggregate the fragment feeds (owned by the fragment): finish / pull / merge through
  * the sr_agg_* calls. */
@@ -661,9 +682,12 @@ typedef struct sr_part_desc {
 
 typedef struct sr_xchg sr_xchg;
 
+/* ExchangeSinkOperator::prepare with the partition exprs of the TDataStreamSink (exchange_sink_operator.cpp:395-483). */
 sr_xchg* sr_xchg_create(sr_ctx* ctx, const sr_part_desc* desc);
 void sr_xchg_destroy(sr_xchg* x);
-/* Partition one batch.  out: DEVICE buffers, all columns of `in` reordered so that the rows
+/* ExchangeSinkOperator::push_chunk, the HASH_PARTITIONED / BUCKET_SHUFFLE branch (exchange_sink_operator.cpp:586-637):
+ * hash of the partition columns, Shuffler::exchange_shuffle (shuffler.h:72-89), per-channel row index lists.
+ * Partition one batch.  out: DEVICE buffers, all columns of `in` reordered so that the rows
  * of channel c occupy [offsets[c], offsets[c+1]) in input order (stable, like the reference's
  * counting sort).  channel_offsets_host: num_channels + 1 int64 written on return (syncs). */
 int32_t sr_xchg_partition(sr_xchg* x, const sr_chunk_view* in, sr_chunk_out* out, int64_t* channel_offsets_host);
