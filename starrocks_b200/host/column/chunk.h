@@ -4,7 +4,8 @@
 //                             get_column_by_slot_id, filter, ...)
 //   FixedLengthColumnBase<T>  be/src/column/fixed_length_column_base.h:49-286 (contiguous Buffer<T>, raw_data, size)
 //   NullableColumn            be/src/column/nullable_column.h:32-110 (data column + uint8 null column, 1 = NULL)
-// Only what the hot path touches is here (fixed-length columns, nullable wrapper).  In the real BE these are the
+// Only what the hot path touches is here (fixed-length columns, nullable wrapper; the string column of the plan around
+// it is column/binary_column.h).  In the real BE these are the
 // BE's own classes; the adapters only need raw_data()/null data()/size()/slot ids.
 #pragma once
 
@@ -33,6 +34,10 @@ public:
     virtual const uint8_t* null_data() const { return nullptr; }
     virtual void resize(size_t n) = 0;
     virtual size_t type_size() const = 0;
+    // variable-length payload (column/binary_column.h): rows are not type_size() apart
+    virtual bool is_binary() const { return false; }
+    // rows [offset, offset + n) as a new column; nullptr = fixed-length payload, the caller copies n * type_size() bytes
+    virtual std::shared_ptr<Column> cut(size_t offset, size_t n) const { return nullptr; }
 };
 using ColumnPtr = std::shared_ptr<Column>;
 using Columns = std::vector<ColumnPtr>;
@@ -72,6 +77,7 @@ public:
     NullableColumn(ColumnPtr data, std::shared_ptr<NullColumn> nulls) : _data(std::move(data)), _nulls(std::move(nulls)) {}
     size_t size() const override { return _data->size(); }
     bool is_nullable() const override { return true; }
+    bool is_binary() const override { return _data->is_binary(); }
     int32_t logical_type() const override { return _data->logical_type(); }
     const uint8_t* raw_data() const override { return _data->raw_data(); }
     uint8_t* mutable_raw_data() override { return _data->mutable_raw_data(); }
@@ -136,8 +142,12 @@ public:
         auto out = std::make_shared<Chunk>();
         for (size_t i = 0; i < _columns.size(); i++) {
             const Column& src = *_columns[i];
-            ColumnPtr data = make_column(src.logical_type(), n);
-            memcpy(data->mutable_raw_data(), src.raw_data() + offset * src.type_size(), n * src.type_size());
+            const Column& payload = src.is_nullable() ? *static_cast<const NullableColumn&>(src).data_column() : src;
+            ColumnPtr data = payload.cut(offset, n);
+            if (!data) {
+                data = make_column(src.logical_type(), n);
+                memcpy(data->mutable_raw_data(), src.raw_data() + offset * src.type_size(), n * src.type_size());
+            }
             if (src.is_nullable()) {
                 auto nulls = std::make_shared<NullColumn>(SR_TYPE_BOOLEAN);
                 nulls->resize(n);

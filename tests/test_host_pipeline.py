@@ -34,6 +34,16 @@ def test_host_layer_builds_and_fails_loudly_without_a_device(gpu, oracle):
         assert r.returncode == 3 and "no CPU fallback" in r.stderr
 
 
+def test_binary_column_and_dictionary_path_on_the_host():
+    """the host string column (BinaryColumn) and the low-cardinality dictionary path that keeps strings out
+    of the GPU operators -- local segment codes -> global ids (TYPE_INT, what the C-ABI sees) -> DictDecodeOperator.  The
+    binary reproduces the reference's binary_column_test.cpp cases (incl. the xor_checksum golden) and needs no GPU."""
+    subprocess.check_call(["make", "-C", CPP, "-s", "binary_column_test"])
+    r = subprocess.run([os.path.join(CPP, "binary_column_test")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "BINARY_COLUMN_TEST_OK" in r.stdout
+
+
 @pytest.mark.gpu
 def test_pipeline_q41_through_the_operator_interface(gpu, oracle):
     _build(gpu, oracle)
